@@ -1,0 +1,126 @@
+"""The oracle (oracle/uegan_oracle.py) against golden vectors produced by the reference itself
+(tests/golden/make_golden.py, run in the build container where /root/reference exists)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import uegan_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gold(regime):
+    return np.load(os.path.join(GOLD, f"golden_{regime}.npz"))
+
+
+def close(a, b, tol):
+    a = torch.as_tensor(np.asarray(a)).double()
+    b = torch.as_tensor(np.asarray(b)).double()
+    err = float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
+    assert err <= tol, f"rel err {err:.3e} > {tol:.1e}"
+
+
+@pytest.mark.parametrize("regime", ["o1", "tiny"])
+@pytest.mark.parametrize("simplified", [False, True])
+def test_generator_matches_reference(regime, simplified):
+    g = gold(regime)
+    gp = O.make_generator_params(32, 0, regime)
+    x = O.make_images((2, 3, 128, 128), 10)
+    with torch.no_grad():
+        out, inter = O.generator_forward(gp, x, simplified=simplified, return_all=True)
+    # fp32 CPU vs fp32 CPU: only summation-order noise is allowed (1e-5 of the tensor scale); the
+    # simplified (GAM-cancelled, hoisted-upsample) form is an algebraic identity -> 1e-4.
+    tol = 1e-4 if simplified else 1e-5
+    close(out, g["g128_out"], tol)
+    close(inter["res"], g["g128_res"], 2e-3 if (simplified and regime == "tiny") else tol * 10)
+    if regime == "o1":
+        assert float(torch.as_tensor(g["g128_res"]).abs().mean()) > 0.05  # parity is not vacuous
+
+
+@pytest.mark.parametrize("regime", ["o1", "tiny"])
+def test_generator_nonsquare(regime):
+    g = gold(regime)
+    gp = O.make_generator_params(32, 0, regime)
+    with torch.no_grad():
+        out = O.generator_forward(gp, O.make_images((1, 3, 96, 160), 11))
+    close(out, g["g96x160_out"], 1e-5)
+
+
+@pytest.mark.parametrize("regime", ["o1", "tiny"])
+def test_discriminator_matches_reference(regime):
+    g = gold(regime)
+    dp = O.make_discriminator_params(32, 1, regime)
+    x = O.make_images((2, 3, 128, 128), 10)
+    with torch.no_grad():
+        preds = O.discriminator_forward(dp, x, training=True)
+    for i, p in enumerate(preds):
+        close(p, g[f"d128_pred{i+1}"], 2e-5)
+    for k in range(1, 6):
+        close(dp[f"d{k}.0.1.weight_u"], g[f"d128_u{k}"], 1e-5)
+        close(dp[f"d{k}.0.1.weight_v"], g[f"d128_v{k}"], 1e-5)
+    with torch.no_grad():
+        preds = O.discriminator_forward(dp, x, training=False)
+    for i, p in enumerate(preds):
+        close(p, g[f"d128_eval_pred{i+1}"], 2e-5)
+
+
+def test_discriminator_bad_loss_type():
+    dp = O.make_discriminator_params(8, 1)
+    with pytest.raises(NotImplementedError):
+        O.discriminator_forward(dp, torch.zeros(1, 3, 96, 96), adv_loss_type="wgan")
+
+
+def test_losses_match_reference():
+    g = gold("o1")
+    vp = O.make_vgg_params()
+    a = O.make_images((2, 3, 64, 64), 12)
+    b = O.make_images((2, 3, 64, 64), 13)
+    with torch.no_grad():
+        close(O.perceptual_loss(vp, (a + 1) / 2, (b + 1) / 2), g["percep64"], 1e-5)
+        mean = torch.tensor(O.IMAGENET_MEAN).view(1, -1, 1, 1)
+        std = torch.tensor(O.IMAGENET_STD).view(1, -1, 1, 1)
+        taps = O.vgg19_taps(vp, ((a + 1) / 2 - mean) / std)
+        close(taps["relu5_1"], g["vgg64_relu5_1"], 1e-5)
+        close(taps["relu3_1"][0, :4], g["vgg64_relu3_1_n0c0"], 1e-5)
+    rp = [torch.tanh(O.make_images((2, 1, s, s), 20 + i)) for i, s in enumerate((64, 32, 16, 8, 4))]
+    fp = [torch.tanh(O.make_images((2, 1, s, s), 30 + i)) for i, s in enumerate((64, 32, 16, 8, 4))]
+    close(O.gan_loss("rahinge", rp, fp, True), g["rahinge_d"], 1e-6)
+    close(O.gan_loss("rahinge", rp, fp, False), g["rahinge_g"], 1e-6)
+    close(O.gan_loss("rals", rp, fp, True), g["rals_d"], 1e-6)
+    close(O.gan_loss("rals", rp, fp, False), g["rals_g"], 1e-6)
+    close(O.multiscale_rec_loss(a, b), g["msl1"], 1e-6)
+    with pytest.raises(NotImplementedError):
+        O.multiscale_rec_loss(a, b, rec_loss_type="huber")
+
+
+def test_train_step_matches_reference():
+    """Two iterations of the trainer.py:75-119 loop body: loss scalars and post-step weights."""
+    g = gold("o1")
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    gp = O.make_generator_params(32, 0, "o1")
+    dp = O.make_discriminator_params(32, 1, "o1")
+    vp = O.make_vgg_params()
+    g_opt, d_opt = O.AdamState(O._trainable(gp)), O.AdamState(O._trainable(dp))
+    raw = O.make_images((2, 3, 128, 128), 40)
+    exp = O.make_images((2, 3, 128, 128), 41)
+    for step in range(2):
+        losses = O.train_step(gp, dp, vp, g_opt, d_opt, raw, exp)
+        got = [losses[k] for k in ("d_loss", "g_adv_loss", "g_percep_loss", "g_idt_loss", "g_loss")]
+        np.testing.assert_allclose(got, g[f"step{step}_losses"], rtol=2e-4)
+    # Adam's first steps move every weight by ~lr regardless of gradient scale, so the post-step weight
+    # DELTAS (in units of lr*steps) are a sharp check of gradient signs and optimizer arithmetic; elements
+    # whose gradient is rounding noise may flip sign, hence a max bound < 1 and a tight mean bound.
+    gp0, dp0 = O.make_generator_params(32, 0, "o1"), O.make_discriminator_params(32, 1, "o1")
+
+    def delta_close(pre, mine, ref, unit, max_tol=0.5, mean_tol=0.01):
+        d = ((mine - pre) - (torch.as_tensor(ref) - pre)).abs() / unit
+        assert float(d.max()) <= max_tol and float(d.mean()) <= mean_tol, (float(d.max()), float(d.mean()))
+
+    delta_close(gp0["enc1.main.1.weight"], gp["enc1.main.1.weight"], g["step_post_enc1_w"], 2e-4)
+    delta_close(gp0["dec5.1.main.1.weight"], gp["dec5.1.main.1.weight"], g["step_post_dec5_1_w"], 2e-4)
+    delta_close(gp0["dec5.1.main.1.bias"], gp["dec5.1.main.1.bias"], g["step_post_dec5_1_b"], 2e-4)
+    delta_close(dp0["d1.0.1.weight_orig"], dp["d1.0.1.weight_orig"], g["step_post_d1_w"], 8e-4)
+    delta_close(dp0["d5_pred.0.1.weight"], dp["d5_pred.0.1.weight"], g["step_post_d5_pred_w"], 8e-4)
+    close(dp["d1.0.1.weight_u"], g["step_post_d1_u"], 1e-4)
