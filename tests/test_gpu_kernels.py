@@ -1,0 +1,192 @@
+"""GPU parity tests of the individual sm_100a kernels (through the C ABI) against fp32 PyTorch ops.
+
+Tolerances: kind::tf32 operands carry 10 mantissa bits (rounded to nearest at the producer) with fp32
+accumulation -> ~1e-3 of the output scale per element for K up to a few thousand; bf16 (8 bits) -> ~1e-2.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from uegan_b200 import kernels
+    from uegan_b200 import _lib
+    _lib.load()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return kernels
+
+
+def fill_nhwc(K, x_nchw, c_stored, halo, pad_mode, dtype):
+    """test helper: NCHW torch tensor -> NHWC-with-halo buffer (halo written with torch ops)."""
+    from uegan_b200 import _lib as L
+    n, c, h, w = x_nchw.shape
+    t = K.NHWC(n, h, w, c_stored, halo, dtype, x_nchw.device, zero=True)
+    xp = x_nchw
+    if halo:
+        xp = F.pad(x_nchw, (halo,) * 4, mode="reflect" if pad_mode == L.PAD_REFLECT else "constant")
+    t.padded_view()[..., :c] = xp.permute(0, 2, 3, 1).to(t.buf.dtype)
+    return t
+
+
+def relerr(a, b):
+    return float((a.double() - b.double()).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+CONV_CASES = [
+    # (name, n, cin, h, w, cout, k, stride, pad_mode)
+    ("enc1_like", 2, 3, 32, 48, 32, 7, 1, "reflect"),
+    ("enc2_like", 2, 32, 32, 32, 64, 3, 2, "reflect"),
+    ("enc5_like", 2, 256, 16, 16, 512, 3, 2, "reflect"),
+    ("dec1_like", 1, 512, 16, 16, 256, 3, 1, "reflect"),
+    ("dec4_like", 1, 64, 64, 64, 32, 3, 1, "reflect"),
+    ("fuse_1x1", 2, 128, 16, 24, 64, 1, 1, "reflect"),
+    ("d1_like", 2, 3, 96, 96, 32, 7, 2, "reflect"),
+    ("d2_like", 2, 32, 48, 48, 64, 7, 2, "reflect"),
+    ("d4_like", 2, 128, 12, 12, 256, 5, 2, "reflect"),
+    ("d5_like_tiny", 2, 256, 6, 6, 512, 5, 2, "reflect"),
+    ("vgg_like", 2, 64, 32, 32, 64, 3, 1, "zero"),
+    ("vgg_first", 2, 3, 32, 32, 64, 3, 1, "zero"),
+    ("ragged", 3, 32, 40, 24, 48, 3, 1, "reflect"),
+    ("tiny_2x2", 3, 64, 4, 4, 32, 3, 2, "reflect"),
+]
+
+
+@pytest.mark.parametrize("dtype_name", ["f32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_fprop(K, case, dtype_name):
+    from uegan_b200 import _lib as L
+    name, n, cin, h, w, cout, k, stride, pad_mode = case
+    dtype = L.F32 if dtype_name == "f32" else L.BF16
+    pm = L.PAD_REFLECT if pad_mode == "reflect" else L.PAD_ZERO
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    wgt = torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k)
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.1
+    pad = (k - 1) // 2
+    vec = 4 if dtype == L.F32 else 8
+    c_stored = (cin + vec - 1) // vec * vec
+    xt = fill_nhwc(K, x, c_stored, pad, pm, dtype)
+    ho = (h + 2 * pad - k) // stride + 1
+    wo = (w + 2 * pad - k) // stride + 1
+    y = K.NHWC(n, ho, wo, cout + 16, 1, dtype, "cuda", zero=True)  # written into a channel slice at offset 16
+    wp = K.packed_weight(wgt, c_stored, dtype)
+    K.conv_fprop(xt, wp, cout, k, stride, pad, y, 16, bias, None, L.ACT_LRELU)
+    assert K.device_error() == 0
+    xq, wq = (x, wgt) if dtype == L.F32 else (x.bfloat16().float(), wgt.bfloat16().float())
+    xpad = F.pad(xq, (pad,) * 4, mode="reflect" if pad_mode == "reflect" else "constant") if pad else xq
+    ref = F.leaky_relu(F.conv2d(xpad, wq, bias, stride=stride), 0.2)
+    got = y.interior_nchw()[:, 16:]
+    tol = 2e-3 if dtype == L.F32 else 1e-2
+    assert relerr(got, ref) < tol, f"{name}: rel err {relerr(got, ref):.3e}"
+    assert float(y.interior_nchw()[:, :16].abs().max()) == 0.0  # neighbouring slice untouched
+    assert float(y.padded_view()[:, 0].abs().max()) == 0.0  # halo untouched by the conv
+
+
+def test_conv_planar_head(K):
+    """cout=1 prediction head with tanh and cout=3 residual+clamp head (planar fp32 NCHW epilogue)."""
+    from uegan_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(7)
+    n, cin, h, w = 2, 32, 24, 40
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    for cout, k, resid in ((1, 7, False), (3, 7, True), (1, 5, False)):
+        wgt = torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k)
+        bias = torch.randn(cout, device="cuda", generator=g) * 0.1
+        pad = (k - 1) // 2
+        xt = fill_nhwc(K, x, cin, pad, L.PAD_REFLECT, L.F32)
+        out = torch.zeros(n, cout, h, w, device="cuda")
+        res = torch.rand(n, cout, h, w, device="cuda", generator=g) * 2 - 1 if resid else None
+        K.conv_fprop(xt, K.packed_weight(wgt, cin, L.F32), cout, k, 1, pad, None, 0, bias, None, L.ACT_TANH, None,
+                     out, res)
+        assert K.device_error() == 0
+        ref = torch.tanh(F.conv2d(F.pad(x, (pad,) * 4, mode="reflect"), wgt, bias))
+        if resid:
+            ref = torch.clamp(ref + res, -1, 1)
+        assert relerr(out, ref) < 2e-3
+
+
+def test_conv_alpha_and_mul(K):
+    from uegan_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(8)
+    n, cin, h, w, cout = 2, 64, 16, 16, 32
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    m = torch.randn(n, cout, h, w, device="cuda", generator=g)
+    wgt = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / math.sqrt(cin * 9)
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.1
+    alpha = torch.tensor([0.37], device="cuda")
+    xt = fill_nhwc(K, x, cin, 1, L.PAD_REFLECT, L.F32)
+    mt = fill_nhwc(K, m, cout, 1, L.PAD_REFLECT, L.F32)
+    y = K.NHWC(n, h, w, cout, 0, L.F32, "cuda", zero=True)
+    K.conv_fprop(xt, K.packed_weight(wgt, cin, L.F32), cout, 3, 1, 1, y, 0, bias, alpha, L.ACT_LRELU, mt)
+    assert K.device_error() == 0
+    ref = F.leaky_relu(0.37 * F.conv2d(F.pad(x, (1,) * 4, mode="reflect"), wgt) + bias.view(1, -1, 1, 1), 0.2) * m
+    assert relerr(y.interior_nchw(), ref) < 2e-3
+
+
+@pytest.mark.parametrize("dtype_name", ["f32", "bf16"])
+def test_elementwise(K, dtype_name):
+    from uegan_b200 import _lib as L
+    dtype = L.F32 if dtype_name == "f32" else L.BF16
+    tol = 1e-3 if dtype == L.F32 else 1e-2
+    g = torch.Generator(device="cuda").manual_seed(3)
+    # pack_input (reflect halo, affine) ------------------------------------------------
+    x = torch.rand(2, 3, 20, 28, device="cuda", generator=g) * 2 - 1
+    t = K.NHWC(2, 20, 28, 8 if dtype == L.BF16 else 4, 3, dtype, "cuda", zero=True)
+    K.pack_input(x, t, L.PAD_REFLECT, scale=[0.5, 0.25, 2.0], shift=[0.1, -0.2, 0.3])
+    ref = x * torch.tensor([0.5, 0.25, 2.0], device="cuda").view(1, 3, 1, 1) + \
+        torch.tensor([0.1, -0.2, 0.3], device="cuda").view(1, 3, 1, 1)
+    refp = F.pad(ref, (3,) * 4, mode="reflect").permute(0, 2, 3, 1)
+    assert relerr(t.padded_view()[..., :3].float(), refp) < tol
+    assert float(t.padded_view()[..., 3:].abs().max()) == 0.0
+    t2 = K.NHWC(2, 20, 28, 8 if dtype == L.BF16 else 4, 1, dtype, "cuda", zero=True)
+    K.pack_input(x, t2, L.PAD_ZERO)
+    assert relerr(t2.padded_view()[..., :3].float(), F.pad(x, (1,) * 4).permute(0, 2, 3, 1)) < tol
+    # halo fill ------------------------------------------------------------------------
+    a = torch.randn(2, 32, 12, 20, device="cuda", generator=g)
+    for halo in (1, 2, 3):
+        ta = fill_nhwc(K, a, 32, 0, L.PAD_REFLECT, dtype)
+        tb = K.NHWC(2, 12, 20, 32, halo, dtype, "cuda", zero=True)
+        tb.padded_view()[:, halo:halo + 12, halo:halo + 20] = ta.padded_view()
+        K.halo_fill(tb, L.PAD_REFLECT)
+        refh = F.pad(ta.interior_nchw(), (halo,) * 4, mode="reflect").permute(0, 2, 3, 1)
+        assert relerr(tb.padded_view().float(), refh) < 1e-6
+        K.halo_fill(tb, L.PAD_ZERO)
+        refz = F.pad(ta.interior_nchw(), (halo,) * 4).permute(0, 2, 3, 1)
+        assert relerr(tb.padded_view().float(), refz) < 1e-6
+    # instance norm into a channel slice ------------------------------------------------
+    for c in (32, 128, 512):
+        a = torch.randn(2, c, 10, 14, device="cuda", generator=g) * 3 + 1.5
+        ta = fill_nhwc(K, a, c, 1, L.PAD_REFLECT, dtype)
+        td = K.NHWC(2, 10, 14, 2 * c, 1, dtype, "cuda", zero=True)
+        ws = torch.empty(3 * 2 * c, dtype=torch.float64, device="cuda")
+        K.instance_norm(ta, td, c, ws)
+        refn = F.instance_norm(ta.interior_nchw(), eps=1e-5)
+        assert relerr(td.interior_nchw()[:, c:], refn) < tol
+        assert float(td.interior_nchw()[:, :c].abs().max()) == 0.0
+    # eps-dominated regime (variance << eps, models.py:227 with orthogonal(0.02) init)
+    a = torch.randn(1, 32, 8, 8, device="cuda", generator=g) * 1e-8
+    ta = fill_nhwc(K, a, 32, 0, L.PAD_REFLECT, L.F32)
+    td = K.NHWC(1, 8, 8, 32, 0, L.F32, "cuda", zero=True)
+    K.instance_norm(ta, td, 0, torch.empty(3 * 32, dtype=torch.float64, device="cuda"))
+    assert relerr(td.interior_nchw(), F.instance_norm(ta.interior_nchw(), eps=1e-5)) < 2e-3
+    # bilinear x2 align_corners=True ---------------------------------------------------------
+    a = torch.randn(2, 64, 6, 10, device="cuda", generator=g)
+    ta = fill_nhwc(K, a, 64, 0, L.PAD_REFLECT, dtype)
+    td = K.NHWC(2, 12, 20, 128, 1, dtype, "cuda", zero=True)
+    K.upsample2x(ta, td, 64)
+    refu = F.interpolate(ta.interior_nchw(), scale_factor=2, mode="bilinear", align_corners=True)
+    assert relerr(td.interior_nchw()[:, 64:], refu) < tol
+    # max pool --------------------------------------------------------------------------
+    ta = fill_nhwc(K, a, 64, 1, L.PAD_ZERO, dtype)
+    td = K.NHWC(2, 3, 5, 64, 1, dtype, "cuda", zero=True)
+    K.maxpool2x2(ta, td)
+    assert relerr(td.interior_nchw(), F.max_pool2d(ta.interior_nchw(), 2, 2)) < 1e-6
+    assert relerr(K.unpack_nchw(ta, 8, 16), ta.interior_nchw()[:, 8:24]) < 1e-6
+    assert K.device_error() == 0

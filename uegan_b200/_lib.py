@@ -1,0 +1,86 @@
+"""ctypes binding of libuegan_sm100.so (the C ABI declared in include/uegan_sm100.h).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing or a call fails, this
+module raises.  Build the library with `python -m uegan_b200.build` (or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libuegan_sm100.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
+PAD_ZERO, PAD_REFLECT = 0, 1
+ABI_VERSION = 1
+
+
+class UeganError(RuntimeError):
+    pass
+
+
+class Tensor(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("halo", C.c_int32), ("dtype", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("x", Tensor), ("y", Tensor), ("y_c_off", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32),
+                ("stride", C.c_int32), ("pad", C.c_int32), ("act", C.c_int32), ("w_packed", C.c_void_p),
+                ("bias", C.c_void_p), ("alpha", C.c_void_p), ("mul", C.POINTER(Tensor)), ("out_nchw", C.c_void_p),
+                ("residual_nchw", C.c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol include/uegan_sm100.h declares
+SYMBOLS = {
+    "uegan_abi_version": (C.c_int, []),
+    "uegan_last_error": (C.c_char_p, []),
+    "uegan_device_error": (C.c_int, []),
+    "uegan_packed_weight_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "uegan_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "uegan_conv2d_fprop": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "uegan_pack_input": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.c_int32, C.POINTER(C.c_float),
+                                   C.POINTER(C.c_float), C.c_void_p]),
+    "uegan_halo_fill": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_void_p]),
+    "uegan_instance_norm": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_int32, C.c_float, C.c_void_p,
+                                      C.c_void_p]),
+    "uegan_upsample2x": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_int32, C.c_void_p]),
+    "uegan_maxpool2x2": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
+    "uegan_unpack_nchw": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "uegan_probe_umma_window": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once) and declares every prototype.  Raises UeganError if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UeganError(f"{LIB_PATH} not found: the CUDA extension is not built "
+                         "(run `python -m uegan_b200.build`); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.uegan_abi_version() != ABI_VERSION:
+        raise UeganError(f"ABI mismatch: library {lib.uegan_abi_version()} != binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().uegan_last_error()
+        raise UeganError(f"{what}: {msg.decode() if msg else rc}")
+
+
+def float3(v):
+    return (C.c_float * 3)(*[float(a) for a in v]) if v is not None else None

@@ -1,0 +1,469 @@
+// Implicit-GEMM convolution, forward, for sm_100a: TMA-staged NHWC tiles -> tcgen05.mma (TMEM accumulators)
+// -> fused epilogue.  One persistent CTA per SM, warp-specialised:
+//   warp 0   TMA producer   (one elected lane)
+//   warp 1   MMA issuer     (one elected lane)
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue      (TMEM -> registers -> alpha/bias/activation/mul -> global)
+//
+// GEMM view (reference call sites: models.py:83,94,162,174; torchvision vgg19 convs, losses.py:43):
+//   M = 128 output pixels (a tn x th x tw box of the output), N = block_n output channels,
+//   K = for each filter row r: the kw*C contiguous input values (s, c) of the padded NHWC row, cut into
+//       128-byte chunks (32 tf32 / 64 bf16 values).  The A tile of one chunk is ONE 5-D TMA box
+//       {chunk, tw, 1, th, tn} over the tensor map {window, wo, r, ho, n} with byte strides
+//       {es, stride*C*es, row, stride*row, img}: sliding windows are expressed by overlapping strides, so any
+//       kernel size / stride 1-2 / channel count (C*es % 16 == 0) is the same code path, and the landing
+//       layout (128 rows x 128 B, SWIZZLE_128B) is exactly the canonical K-major UMMA operand.
+//   Padding is never materialised by this kernel: the producer of x wrote the halo (reflect or zero).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace uegan {
+
+constexpr int kMaxStages = 8;
+constexpr int kABytes = 128 * 128;  // 128 pixel rows x 128 B
+constexpr int kTmemCols = 512;      // 2 accumulator stages x 256 fp32 columns
+
+struct ConvParams {
+  // tiling
+  int tw, th, tn;
+  int tiles_w, tiles_h, tiles_img;  // number of M tiles along wo / ho / n
+  int n_tiles, block_n;
+  int total_tiles;
+  // K loop
+  int kh, chunks_per_row, chunk_elems, num_k_chunks;
+  int num_stages, stage_bytes;
+  // epilogue
+  int Wo, Ho, Nimg, cout;
+  int act;
+  int out_bf16;
+  void* out;  // points at element (n=0, y=0, x=0, c=y_c_off) of the interior
+  long long out_pix, out_row, out_img;  // strides in elements
+  const float* bias;
+  const float* alpha;
+  const void* mul;  // same dtype as out
+  long long mul_pix, mul_row, mul_img;
+  float* out_nchw;
+  const float* residual_nchw;
+  unsigned int* err_sink;  // host-mapped watchdog word
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case UEGAN_ACT_LRELU: return v > 0.f ? v : 0.2f * v;
+    case UEGAN_ACT_RELU: return fmaxf(v, 0.f);
+    case UEGAN_ACT_TANH: return tanhf(v);
+    case UEGAN_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+struct TileCoord {
+  int wo0, ho0, n0, nt;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
+  TileCoord c;
+  c.nt = t % p.n_tiles;
+  int m = t / p.n_tiles;
+  c.wo0 = (m % p.tiles_w) * p.tw;
+  m /= p.tiles_w;
+  c.ho0 = (m % p.tiles_h) * p.th;
+  c.n0 = (m / p.tiles_h) * p.tn;
+  return c;
+}
+
+template <int kTf32>
+__global__ void __launch_bounds__(256, 1)
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full[2];
+  __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = kABytes + p.block_n * 128;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        int r = 0, j = 0;
+        for (int kc = 0; kc < p.num_k_chunks; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 0x100 + stage, p.err_sink);
+          uint8_t* sa = smem + stage * p.stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_5d(&tmA, &full_bar[stage], sa, j * p.chunk_elems, tc.wo0, r, tc.ho0, tc.n0);
+          tma_load_2d(&tmB, &full_bar[stage], sb, kc * p.chunk_elems, tc.nt * p.block_n);
+          if (++j == p.chunks_per_row) { j = 0; ++r; }
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = make_instr_desc(kTf32 ? UMMA_TF32 : UMMA_BF16, 128, p.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 0x200 + acc, p.err_sink);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kc = 0; kc < p.num_k_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase, 0x300 + stage, p.err_sink);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte swizzle row
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+            umma_ss<kTf32>(d_tmem, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int e = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = e * 32 + lane;
+    const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      const int wo = tc.wo0 + m % p.tw;
+      const int ho = tc.ho0 + (m / p.tw) % p.th;
+      const int n = tc.n0 + m / (p.tw * p.th);
+      const bool valid = (wo < p.Wo) && (ho < p.Ho) && (n < p.Nimg);
+      mbar_wait(&tmem_full[acc], acc_phase, 0x400 + acc, p.err_sink);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(e * 32) << 16) + acc * 256;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t rr[16];
+        tmem_ld16(taddr + c0, rr);
+        tmem_ld_wait();
+        const int col0 = tc.nt * p.block_n + c0;
+        if (!valid || col0 >= p.cout) continue;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x = __uint_as_float(rr[i]) * alpha;
+          if (p.bias && col0 + i < p.cout) x += __ldg(p.bias + col0 + i);
+          v[i] = apply_act(x, p.act);
+        }
+        if (p.out_nchw) {
+          // planar fp32 output: cout <= 16 real channels (D prediction heads, G's last conv)
+          const long long plane = (long long)p.Ho * p.Wo;
+          for (int i = 0; i < 16; ++i) {
+            if (col0 + i < p.cout) {
+              const long long o = ((long long)n * p.cout + col0 + i) * plane + (long long)ho * p.Wo + wo;
+              float x = v[i];
+              if (p.residual_nchw) x = fminf(fmaxf(x + __ldg(p.residual_nchw + o), -1.f), 1.f);
+              p.out_nchw[o] = x;
+            }
+          }
+        } else {
+          const long long o = (long long)n * p.out_img + (long long)ho * p.out_row + (long long)wo * p.out_pix + col0;
+          if (p.mul) {
+            const long long mo = (long long)n * p.mul_img + (long long)ho * p.mul_row + (long long)wo * p.mul_pix + col0;
+            if (p.out_bf16) {
+              const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.mul) + mo;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= __bfloat162float(mp[i]);
+            } else {
+              const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.mul) + mo);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 q = __ldg(mp + i);
+                v[4 * i + 0] *= q.x; v[4 * i + 1] *= q.y; v[4 * i + 2] *= q.z; v[4 * i + 3] *= q.w;
+              }
+            }
+          }
+          if (p.out_bf16) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
+            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              op[i] = make_float4(round_tf32(v[4 * i]), round_tf32(v[4 * i + 1]), round_tf32(v[4 * i + 2]),
+                                  round_tf32(v[4 * i + 3]));
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+struct PackGeom {
+  int chunk_elems, chunks_per_row, row_pad, cout_pad;
+};
+static PackGeom pack_geom(int cout, int cin_stored, int k, int dtype) {
+  PackGeom g;
+  g.chunk_elems = 128 / dtype_size(dtype);
+  g.chunks_per_row = (k * cin_stored + g.chunk_elems - 1) / g.chunk_elems;
+  g.row_pad = g.chunks_per_row * g.chunk_elems;
+  g.cout_pad = (cout + 15) / 16 * 16;
+  return g;
+}
+
+int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
+  const uegan_tensor& x = d.x;
+  const int es = dtype_size(x.dtype);
+  UEGAN_CHECK(x.dtype == UEGAN_F32 || x.dtype == UEGAN_BF16, "conv: bad x dtype %d", x.dtype);
+  UEGAN_CHECK((x.c * es) % 16 == 0, "conv: x.c*elem (%d) must be a multiple of 16 bytes", x.c * es);
+  UEGAN_CHECK(d.stride == 1 || d.stride == 2, "conv: stride %d unsupported", d.stride);
+  UEGAN_CHECK(d.pad <= x.halo, "conv: pad %d exceeds input halo %d", d.pad, x.halo);
+  UEGAN_CHECK(d.k >= 1 && d.k <= 7, "conv: k %d unsupported", d.k);
+  UEGAN_CHECK(d.w_packed != nullptr && x.data != nullptr, "conv: null pointer");
+  const int Ho = (x.h + 2 * d.pad - d.k) / d.stride + 1;
+  const int Wo = (x.w + 2 * d.pad - d.k) / d.stride + 1;
+  UEGAN_CHECK(Ho >= 1 && Wo >= 1, "conv: empty output");
+  const PackGeom g = pack_geom(d.cout, x.c, d.k, x.dtype);
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.tw = pow2_ceil(Wo < 16 ? Wo : 16);
+  p.th = pow2_ceil(Ho);
+  if (p.th > 128 / p.tw) p.th = 128 / p.tw;
+  p.tn = 128 / (p.tw * p.th);
+  p.tiles_w = (Wo + p.tw - 1) / p.tw;
+  p.tiles_h = (Ho + p.th - 1) / p.th;
+  p.tiles_img = (x.n + p.tn - 1) / p.tn;
+  p.block_n = g.cout_pad <= 256 ? g.cout_pad : 256;
+  p.n_tiles = (g.cout_pad + p.block_n - 1) / p.block_n;
+  p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_img * p.n_tiles;
+  p.kh = d.k;
+  p.chunks_per_row = g.chunks_per_row;
+  p.chunk_elems = g.chunk_elems;
+  p.num_k_chunks = d.k * g.chunks_per_row;
+  p.stage_bytes = kABytes + ((p.block_n * 128 + 1023) / 1024) * 1024;
+  p.num_stages = (200 * 1024) / p.stage_bytes;
+  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  p.Wo = Wo; p.Ho = Ho; p.Nimg = x.n; p.cout = d.cout;
+  p.act = d.act;
+  p.bias = d.bias;
+  p.alpha = d.alpha;
+  p.out_nchw = d.out_nchw;
+  p.residual_nchw = d.residual_nchw;
+  p.err_sink = error_sink_device();
+  if (d.out_nchw) {
+    UEGAN_CHECK(d.cout <= 16, "conv: planar output needs cout <= 16 (got %d)", d.cout);
+  } else {
+    const uegan_tensor& y = d.y;
+    UEGAN_CHECK(y.data != nullptr, "conv: null output");
+    UEGAN_CHECK(y.n == x.n && y.h == Ho && y.w == Wo, "conv: y is %dx%dx%d, expected %dx%dx%d", y.n, y.h, y.w, x.n,
+                Ho, Wo);
+    UEGAN_CHECK(d.cout % 16 == 0, "conv: NHWC output needs cout %% 16 == 0 (got %d)", d.cout);
+    UEGAN_CHECK(d.y_c_off >= 0 && d.y_c_off + d.cout <= y.c && d.y_c_off % 8 == 0, "conv: bad channel slice");
+    UEGAN_CHECK((y.c * dtype_size(y.dtype)) % 16 == 0, "conv: y.c misaligned");
+    p.out_bf16 = (y.dtype == UEGAN_BF16);
+    p.out_pix = y.c;
+    p.out_row = t_wp(y) * y.c;
+    p.out_img = t_hp(y) * p.out_row;
+    const long long off = (long long)y.halo * p.out_row + (long long)y.halo * p.out_pix + d.y_c_off;
+    p.out = static_cast<uint8_t*>(y.data) + off * dtype_size(y.dtype);
+    if (d.mul) {
+      const uegan_tensor& mt = *d.mul;
+      UEGAN_CHECK(mt.dtype == y.dtype && mt.n == y.n && mt.h == y.h && mt.w == y.w && mt.c >= d.cout,
+                  "conv: mul tensor mismatch");
+      p.mul_pix = mt.c;
+      p.mul_row = t_wp(mt) * mt.c;
+      p.mul_img = t_hp(mt) * p.mul_row;
+      const long long moff = (long long)mt.halo * p.mul_row + (long long)mt.halo * p.mul_pix;
+      p.mul = static_cast<const uint8_t*>(mt.data) + moff * dtype_size(mt.dtype);
+    }
+  }
+
+  // ---- tensor maps
+  const CUtensorMapDataType dt = (x.dtype == UEGAN_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                         : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const uint64_t pix_b = (uint64_t)x.c * es;
+  const uint64_t row_b = (uint64_t)t_wp(x) * pix_b;
+  const uint64_t img_b = (uint64_t)t_hp(x) * row_b;
+  uint8_t* a_base = static_cast<uint8_t*>(x.data) + (uint64_t)(x.halo - d.pad) * row_b + (uint64_t)(x.halo - d.pad) * pix_b;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5] = {(uint64_t)g.row_pad, (uint64_t)Wo, (uint64_t)d.k, (uint64_t)Ho, (uint64_t)x.n};
+    uint64_t strides[4] = {(uint64_t)d.stride * pix_b, row_b, (uint64_t)d.stride * row_b, img_b};
+    uint32_t box[5] = {(uint32_t)g.chunk_elems, (uint32_t)p.tw, 1u, (uint32_t)p.th, (uint32_t)p.tn};
+    if (encode_tiled(&tmA, dt, 5, a_base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+  }
+  {
+    const uint64_t ktot = (uint64_t)d.k * g.row_pad;
+    uint64_t dims[2] = {ktot, (uint64_t)g.cout_pad};
+    uint64_t strides[1] = {ktot * es};
+    uint32_t box[2] = {(uint32_t)g.chunk_elems, (uint32_t)p.block_n};
+    if (encode_tiled(&tmB, dt, 2, const_cast<void*>(d.w_packed), dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return -1;
+  }
+  const int smem_bytes = p.num_stages * p.stage_bytes + 1024;
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  if (x.dtype == UEGAN_F32) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    conv_fprop_kernel<1><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    conv_fprop_kernel<0><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+  }
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing: OIHW fp32 -> [cout_pad][k][row_pad] (row = (s, c) with c over the STORED channels of x)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin_total,
+                                   int cin_first, int cin, int cin_stored, int k, int row_pad, int cout_pad,
+                                   int transpose_flip, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % row_pad);
+  const int r = (int)((i / row_pad) % k);
+  const int o = (int)(i / ((long long)row_pad * k));
+  float v = 0.f;
+  const int s = x / cin_stored, c = x % cin_stored;
+  if (o < cout && s < k && c < cin) {
+    if (!transpose_flip) {
+      v = w[(((long long)o * cin_total + cin_first + c) * k + r) * k + s];
+    } else {
+      // dgrad operand: "output" channel o indexes the ORIGINAL input channels, c the original outputs;
+      // original weight layout is [c_orig_out = c][cin_total][k][k], taps rotated 180 degrees.
+      v = w[(((long long)c * cin_total + cin_first + o) * k + (k - 1 - r)) * k + (k - 1 - s)];
+    }
+  }
+  if constexpr (sizeof(T) == 4) {
+    out[i] = round_tf32(v);
+  } else {
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace uegan
+
+using namespace uegan;
+
+extern "C" {
+
+size_t uegan_packed_weight_bytes(int32_t cout, int32_t cin_stored, int32_t k, int32_t dtype) {
+  const PackGeom g = pack_geom(cout, cin_stored, k, dtype);
+  return (size_t)g.cout_pad * k * g.row_pad * dtype_size(dtype);
+}
+
+int uegan_pack_conv_weight(const float* w_oihw, void* w_packed, int32_t cout, int32_t cin_total, int32_t cin_first,
+                           int32_t cin, int32_t cin_stored, int32_t k, int32_t dtype, int32_t transpose_flip,
+                           void* stream) {
+  UEGAN_CHECK(w_oihw && w_packed, "pack_conv_weight: null pointer");
+  UEGAN_CHECK(cin <= cin_stored, "pack_conv_weight: cin %d > stored %d", cin, cin_stored);
+  if (!transpose_flip) UEGAN_CHECK(cin_first + cin <= cin_total, "pack_conv_weight: channel range out of bounds");
+  const PackGeom g = pack_geom(cout, cin_stored, k, dtype);
+  const long long total = (long long)g.cout_pad * k * g.row_pad;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == UEGAN_F32)
+    pack_weight_kernel<float><<<blocks, threads, 0, st>>>(w_oihw, static_cast<float*>(w_packed), cout, cin_total,
+                                                          cin_first, cin, cin_stored, k, g.row_pad, g.cout_pad,
+                                                          transpose_flip, total);
+  else
+    pack_weight_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), cout,
+                                                                   cin_total, cin_first, cin, cin_stored, k, g.row_pad,
+                                                                   g.cout_pad, transpose_flip, total);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_conv2d_fprop(const uegan_conv_desc* desc, void* stream) {
+  UEGAN_CHECK(desc != nullptr, "conv2d_fprop: null desc");
+  return launch_conv_fprop(*desc, static_cast<cudaStream_t>(stream));
+}
+
+int uegan_device_error(void) {
+  cudaError_t e = cudaDeviceSynchronize();
+  unsigned int* sink = error_sink_host();
+  const unsigned int v = sink ? *sink : 0;
+  if (sink) *sink = 0;
+  if (e != cudaSuccess) {
+    set_error("device error: %s (watchdog code 0x%x)", cudaGetErrorString(e), v);
+    return v ? (int)v : -1;
+  }
+  return (int)v;
+}
+
+}  // extern "C"

@@ -1,0 +1,417 @@
+// HBM-bound helper kernels around the implicit-GEMM convolutions: layout packing, halo (padding) fill,
+// InstanceNorm, bilinear x2 upsample, 2x2 max-pool.  All work on NHWC-with-halo tensors (uegan_sm100.h) in
+// 16-byte channel vectors so that every global access is a full 16 B per thread, coalesced along C then W.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace uegan {
+
+__device__ __forceinline__ float round_tf32_ew(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float (&v)[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+  // F32 activations feed kind::tf32 MMAs: round to nearest tf32 once, at the producer.
+  __device__ static void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(round_tf32_ew(v[0]), round_tf32_ew(v[1]), round_tf32_ew(v[2]),
+                                                round_tf32_ew(v[3]));
+  }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      v[2 * i] = __low2float(h);
+      v[2 * i + 1] = __high2float(h);
+    }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+struct TGeom {  // device-side view of a uegan_tensor
+  void* data;
+  int n, h, w, c, halo;
+  long long wp, hp;
+};
+static TGeom geom(const uegan_tensor& t) {
+  TGeom g;
+  g.data = t.data; g.n = t.n; g.h = t.h; g.w = t.w; g.c = t.c; g.halo = t.halo;
+  g.wp = t_wp(t); g.hp = t_hp(t);
+  return g;
+}
+// element offset of (n, y, x, c) with y, x in interior coordinates (may be negative into the halo)
+__device__ __forceinline__ long long toff(const TGeom& g, int n, int y, int x, int c) {
+  return (((long long)n * g.hp + (y + g.halo)) * g.wp + (x + g.halo)) * g.c + c;
+}
+
+// ------------------------------------------------------------------------------------------
+// NCHW fp32 (3 channels) -> NHWC with halo
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_input_kernel(const float* __restrict__ src, TGeom d, int reflect, float s0, float s1, float s2,
+                                  float b0, float b1, float b2, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int xp = (int)(i % d.wp);
+  const int yp = (int)((i / d.wp) % d.hp);
+  const int n = (int)(i / (d.wp * d.hp));
+  int y = yp - d.halo, x = xp - d.halo;
+  const bool in_halo = (y < 0) || (y >= d.h) || (x < 0) || (x >= d.w);
+  float v[Vec<T>::N];
+#pragma unroll
+  for (int k = 0; k < Vec<T>::N; ++k) v[k] = 0.f;
+  if (!in_halo || reflect) {
+    y = reflect_idx(y, d.h);
+    x = reflect_idx(x, d.w);
+    const long long plane = (long long)d.h * d.w;
+    const float* s = src + (long long)n * 3 * plane + (long long)y * d.w + x;
+    v[0] = __ldg(s) * s0 + b0;
+    v[1] = __ldg(s + plane) * s1 + b1;
+    v[2] = __ldg(s + 2 * plane) * s2 + b2;
+  }
+  T* dp = static_cast<T*>(d.data) + i * d.c;
+  Vec<T>::store(dp, v);
+  // channels beyond the first vector (if c > Vec::N) are zero
+  float z[Vec<T>::N];
+#pragma unroll
+  for (int k = 0; k < Vec<T>::N; ++k) z[k] = 0.f;
+  for (int c = Vec<T>::N; c < d.c; c += Vec<T>::N) Vec<T>::store(dp + c, z);
+}
+
+// ------------------------------------------------------------------------------------------
+// halo fill: top/bottom bands (halo rows x full padded width) then left/right bands (h rows x halo cols)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void halo_fill_kernel(TGeom t, int reflect, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = t.c / Vec<T>::N;
+  const int c = (int)(i % cv) * Vec<T>::N;
+  long long pix = i / cv;
+  const long long per_img = 2LL * t.halo * t.wp + 2LL * t.halo * t.h;
+  const int n = (int)(pix / per_img);
+  pix %= per_img;
+  int yp, xp;
+  if (pix < 2LL * t.halo * t.wp) {
+    const int band_row = (int)(pix / t.wp);
+    xp = (int)(pix % t.wp);
+    yp = band_row < t.halo ? band_row : (int)(t.hp - 2 * t.halo + band_row);
+  } else {
+    pix -= 2LL * t.halo * t.wp;
+    const int row = (int)(pix / (2 * t.halo));
+    const int col = (int)(pix % (2 * t.halo));
+    yp = t.halo + row;
+    xp = col < t.halo ? col : (int)(t.wp - 2 * t.halo + col);
+  }
+  T* base = static_cast<T*>(t.data);
+  float v[Vec<T>::N];
+  if (reflect) {
+    const int y = reflect_idx(yp - t.halo, t.h), x = reflect_idx(xp - t.halo, t.w);
+    Vec<T>::load(base + toff(t, n, y, x, c), v);
+  } else {
+#pragma unroll
+    for (int k = 0; k < Vec<T>::N; ++k) v[k] = 0.f;
+  }
+  Vec<T>::store(base + (((long long)n * t.hp + yp) * t.wp + xp) * t.c + c, v);
+}
+
+// ------------------------------------------------------------------------------------------
+// InstanceNorm: per-(n,c) sum / sum of squares in fp64 (block partials -> atomics), finalize, apply
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void in_stats_kernel(TGeom s, double* __restrict__ stats, int pix_per_block) {
+  // blockDim.x = s.c * groups ; thread -> (channel, pixel group)
+  const int c = threadIdx.x % s.c;
+  const int grp = threadIdx.x / s.c;
+  const int groups = blockDim.x / s.c;
+  const int n = blockIdx.y;
+  const long long npix = (long long)s.h * s.w;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > npix) p1 = npix;
+  const T* base = static_cast<const T*>(s.data);
+  double sum = 0.0, sq = 0.0;
+  for (long long p = p0 + grp; p < p1; p += groups) {
+    const int y = (int)(p / s.w), x = (int)(p % s.w);
+    float v;
+    if constexpr (sizeof(T) == 4) v = base[toff(s, n, y, x, c)];
+    else v = __bfloat162float(base[toff(s, n, y, x, c)]);
+    sum += v;
+    sq += (double)v * v;
+  }
+  extern __shared__ double sh[];
+  sh[threadIdx.x] = sum;
+  sh[blockDim.x + threadIdx.x] = sq;
+  __syncthreads();
+  if (grp == 0) {
+    for (int g = 1; g < groups; ++g) {
+      sum += sh[g * s.c + c];
+      sq += sh[blockDim.x + g * s.c + c];
+    }
+    atomicAdd(&stats[((long long)n * s.c + c) * 2], sum);
+    atomicAdd(&stats[((long long)n * s.c + c) * 2 + 1], sq);
+  }
+}
+
+__global__ void in_finalize_kernel(const double* __restrict__ stats, float* __restrict__ mr, int total, double inv_npix,
+                                   float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double mean = stats[2 * i] * inv_npix;
+  double var = stats[2 * i + 1] * inv_npix - mean * mean;  // biased variance (InstanceNorm2d)
+  if (var < 0.0) var = 0.0;
+  mr[2 * i] = (float)mean;
+  mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+template <typename T>
+__global__ void in_apply_kernel(TGeom s, TGeom d, int dst_c_off, const float* __restrict__ mr, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = s.c / Vec<T>::N;
+  const int c = (int)(i % cv) * Vec<T>::N;
+  long long pix = i / cv;
+  const int x = (int)(pix % s.w);
+  pix /= s.w;
+  const int y = (int)(pix % s.h);
+  const int n = (int)(pix / s.h);
+  float v[Vec<T>::N];
+  Vec<T>::load(static_cast<const T*>(s.data) + toff(s, n, y, x, c), v);
+  const float* m = mr + ((long long)n * s.c + c) * 2;
+#pragma unroll
+  for (int k = 0; k < Vec<T>::N; ++k) v[k] = (v[k] - m[2 * k]) * m[2 * k + 1];
+  Vec<T>::store(static_cast<T*>(d.data) + toff(d, n, y, x, dst_c_off + c), v);
+}
+
+// ------------------------------------------------------------------------------------------
+// bilinear x2, align_corners=True
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void upsample2x_kernel(TGeom s, TGeom d, int dst_c_off, float sy, float sx, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = s.c / Vec<T>::N;
+  const int c = (int)(i % cv) * Vec<T>::N;
+  long long pix = i / cv;
+  const int xo = (int)(pix % d.w);
+  pix /= d.w;
+  const int yo = (int)(pix % d.h);
+  const int n = (int)(pix / d.h);
+  const float fy = sy * yo, fx = sx * xo;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < s.h - 1 ? 1 : 0), x1 = x0 + (x0 < s.w - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fx - x0;
+  const T* base = static_cast<const T*>(s.data);
+  float a[Vec<T>::N], b[Vec<T>::N], e[Vec<T>::N], f[Vec<T>::N], o[Vec<T>::N];
+  Vec<T>::load(base + toff(s, n, y0, x0, c), a);
+  Vec<T>::load(base + toff(s, n, y0, x1, c), b);
+  Vec<T>::load(base + toff(s, n, y1, x0, c), e);
+  Vec<T>::load(base + toff(s, n, y1, x1, c), f);
+#pragma unroll
+  for (int k = 0; k < Vec<T>::N; ++k)
+    o[k] = (1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * e[k] + lx * f[k]);
+  Vec<T>::store(static_cast<T*>(d.data) + toff(d, n, yo, xo, dst_c_off + c), o);
+}
+
+template <typename T>
+__global__ void maxpool2x2_kernel(TGeom s, TGeom d, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = s.c / Vec<T>::N;
+  const int c = (int)(i % cv) * Vec<T>::N;
+  long long pix = i / cv;
+  const int xo = (int)(pix % d.w);
+  pix /= d.w;
+  const int yo = (int)(pix % d.h);
+  const int n = (int)(pix / d.h);
+  const T* base = static_cast<const T*>(s.data);
+  float a[Vec<T>::N], b[Vec<T>::N], e[Vec<T>::N], f[Vec<T>::N], o[Vec<T>::N];
+  Vec<T>::load(base + toff(s, n, 2 * yo, 2 * xo, c), a);
+  Vec<T>::load(base + toff(s, n, 2 * yo, 2 * xo + 1, c), b);
+  Vec<T>::load(base + toff(s, n, 2 * yo + 1, 2 * xo, c), e);
+  Vec<T>::load(base + toff(s, n, 2 * yo + 1, 2 * xo + 1, c), f);
+#pragma unroll
+  for (int k = 0; k < Vec<T>::N; ++k) o[k] = fmaxf(fmaxf(a[k], b[k]), fmaxf(e[k], f[k]));
+  Vec<T>::store(static_cast<T*>(d.data) + toff(d, n, yo, xo, c), o);
+}
+
+template <typename T>
+__global__ void unpack_nchw_kernel(TGeom s, int c_off, int c_count, float* __restrict__ dst, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % s.w);
+  long long r = i / s.w;
+  const int y = (int)(r % s.h);
+  r /= s.h;
+  const int c = (int)(r % c_count);
+  const int n = (int)(r / c_count);
+  const T* base = static_cast<const T*>(s.data);
+  float v;
+  if constexpr (sizeof(T) == 4) v = base[toff(s, n, y, x, c_off + c)];
+  else v = __bfloat162float(base[toff(s, n, y, x, c_off + c)]);
+  dst[i] = v;
+}
+
+static inline unsigned nblocks(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+
+static int check_vec(const uegan_tensor& t, const char* who) {
+  UEGAN_CHECK(t.data != nullptr, "%s: null tensor", who);
+  UEGAN_CHECK(t.dtype == UEGAN_F32 || t.dtype == UEGAN_BF16, "%s: bad dtype", who);
+  UEGAN_CHECK((t.c * dtype_size(t.dtype)) % 16 == 0, "%s: c*elem must be a multiple of 16 B", who);
+  return 0;
+}
+
+}  // namespace uegan
+
+using namespace uegan;
+
+extern "C" {
+
+int uegan_pack_input(const float* x_nchw, const uegan_tensor* dst, int32_t pad_mode, const float* scale_host,
+                     const float* shift_host, void* stream) {
+  UEGAN_CHECK(x_nchw && dst, "pack_input: null pointer");
+  if (check_vec(*dst, "pack_input")) return -1;
+  const TGeom d = geom(*dst);
+  const long long total = (long long)d.n * d.hp * d.wp;
+  const float s0 = scale_host ? scale_host[0] : 1.f, s1 = scale_host ? scale_host[1] : 1.f,
+              s2 = scale_host ? scale_host[2] : 1.f;
+  const float b0 = shift_host ? shift_host[0] : 0.f, b1 = shift_host ? shift_host[1] : 0.f,
+              b2 = shift_host ? shift_host[2] : 0.f;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dst->dtype == UEGAN_F32)
+    pack_input_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(x_nchw, d, pad_mode == UEGAN_PAD_REFLECT, s0, s1, s2,
+                                                                  b0, b1, b2, total);
+  else
+    pack_input_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(x_nchw, d, pad_mode == UEGAN_PAD_REFLECT, s0,
+                                                                          s1, s2, b0, b1, b2, total);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_halo_fill(const uegan_tensor* t, int32_t pad_mode, void* stream) {
+  UEGAN_CHECK(t, "halo_fill: null pointer");
+  if (check_vec(*t, "halo_fill")) return -1;
+  if (t->halo == 0) return 0;
+  if (pad_mode == UEGAN_PAD_REFLECT)
+    UEGAN_CHECK(t->halo < t->h && t->halo < t->w, "halo_fill: reflect halo %d needs h,w > halo (got %dx%d)", t->halo,
+                t->h, t->w);
+  const TGeom g = geom(*t);
+  const int vn = 16 / dtype_size(t->dtype);
+  const long long total = (long long)g.n * (2LL * g.halo * g.wp + 2LL * g.halo * g.h) * (g.c / vn);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (t->dtype == UEGAN_F32)
+    halo_fill_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(g, pad_mode == UEGAN_PAD_REFLECT, total);
+  else
+    halo_fill_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(g, pad_mode == UEGAN_PAD_REFLECT, total);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_instance_norm(const uegan_tensor* src, const uegan_tensor* dst, int32_t dst_c_off, float eps,
+                        double* stats_ws, void* stream) {
+  UEGAN_CHECK(src && dst && stats_ws, "instance_norm: null pointer");
+  if (check_vec(*src, "instance_norm src") || check_vec(*dst, "instance_norm dst")) return -1;
+  UEGAN_CHECK(src->dtype == dst->dtype && src->n == dst->n && src->h == dst->h && src->w == dst->w,
+              "instance_norm: src/dst mismatch");
+  UEGAN_CHECK(dst_c_off >= 0 && dst_c_off + src->c <= dst->c && dst_c_off % 8 == 0, "instance_norm: bad slice");
+  UEGAN_CHECK(src->c <= 1024, "instance_norm: c too large");
+  const TGeom s = geom(*src), d = geom(*dst);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nc = s.n * s.c;
+  UEGAN_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * nc, st));
+  // stats
+  int threads = s.c;
+  while (threads < 256) threads += s.c;
+  const long long npix = (long long)s.h * s.w;
+  int pix_per_block = 1024;
+  const dim3 grid((unsigned)((npix + pix_per_block - 1) / pix_per_block), (unsigned)s.n);
+  const size_t sh = sizeof(double) * 2 * threads;
+  float* mr = reinterpret_cast<float*>(stats_ws + 2 * nc);  // finalised (mean, rstd) live after the raw sums
+  if (src->dtype == UEGAN_F32)
+    in_stats_kernel<float><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
+  else
+    in_stats_kernel<__nv_bfloat16><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
+  in_finalize_kernel<<<nblocks(nc, 128), 128, 0, st>>>(stats_ws, mr, nc, 1.0 / (double)npix, eps);
+  const int vn = 16 / dtype_size(src->dtype);
+  const long long total = (long long)s.n * npix * (s.c / vn);
+  if (src->dtype == UEGAN_F32)
+    in_apply_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, mr, total);
+  else
+    in_apply_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, mr, total);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_upsample2x(const uegan_tensor* src, const uegan_tensor* dst, int32_t dst_c_off, void* stream) {
+  UEGAN_CHECK(src && dst, "upsample2x: null pointer");
+  if (check_vec(*src, "upsample2x src") || check_vec(*dst, "upsample2x dst")) return -1;
+  UEGAN_CHECK(src->dtype == dst->dtype && src->n == dst->n && dst->h == 2 * src->h && dst->w == 2 * src->w,
+              "upsample2x: src/dst mismatch");
+  UEGAN_CHECK(dst_c_off >= 0 && dst_c_off + src->c <= dst->c && dst_c_off % 8 == 0, "upsample2x: bad slice");
+  const TGeom s = geom(*src), d = geom(*dst);
+  const float sy = d.h > 1 ? (float)(s.h - 1) / (float)(d.h - 1) : 0.f;
+  const float sx = d.w > 1 ? (float)(s.w - 1) / (float)(d.w - 1) : 0.f;
+  const int vn = 16 / dtype_size(src->dtype);
+  const long long total = (long long)d.n * d.h * d.w * (s.c / vn);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (src->dtype == UEGAN_F32)
+    upsample2x_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, sy, sx, total);
+  else
+    upsample2x_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, sy, sx, total);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_maxpool2x2(const uegan_tensor* src, const uegan_tensor* dst, void* stream) {
+  UEGAN_CHECK(src && dst, "maxpool2x2: null pointer");
+  if (check_vec(*src, "maxpool2x2 src") || check_vec(*dst, "maxpool2x2 dst")) return -1;
+  UEGAN_CHECK(src->dtype == dst->dtype && src->n == dst->n && dst->h == src->h / 2 && dst->w == src->w / 2 &&
+                  dst->c == src->c,
+              "maxpool2x2: src/dst mismatch");
+  const TGeom s = geom(*src), d = geom(*dst);
+  const int vn = 16 / dtype_size(src->dtype);
+  const long long total = (long long)d.n * d.h * d.w * (s.c / vn);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (src->dtype == UEGAN_F32)
+    maxpool2x2_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(s, d, total);
+  else
+    maxpool2x2_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(s, d, total);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_unpack_nchw(const uegan_tensor* src, int32_t c_off, int32_t c_count, float* dst_nchw, void* stream) {
+  UEGAN_CHECK(src && dst_nchw, "unpack_nchw: null pointer");
+  UEGAN_CHECK(c_off >= 0 && c_off + c_count <= src->c, "unpack_nchw: bad channel range");
+  const TGeom s = geom(*src);
+  const long long total = (long long)s.n * c_count * s.h * s.w;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (src->dtype == UEGAN_F32)
+    unpack_nchw_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(s, c_off, c_count, dst_nchw, total);
+  else
+    unpack_nchw_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(s, c_off, c_count, dst_nchw, total);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

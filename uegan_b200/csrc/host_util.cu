@@ -1,0 +1,91 @@
+#include "host_util.h"
+
+#include <cudaTypedefs.h>
+#include <string.h>
+
+namespace uegan {
+
+static thread_local char g_err[512] = "";
+
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return -1;
+}
+const char* get_error() { return g_err; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, uint32_t rank, void* base, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  UEGAN_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (uint32_t i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUresult r = fn(map, dt, rank, base, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return set_error(
+        "cuTensorMapEncodeTiled failed (CUresult %d): rank %u dims [%llu %llu %llu %llu %llu] strides [%llu %llu %llu "
+        "%llu] box [%u %u %u %u %u]",
+        (int)r, rank, (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0),
+        (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0),
+        (unsigned long long)(rank > 4 ? gdim[4] : 0), (unsigned long long)(rank > 1 ? gstr[0] : 0),
+        (unsigned long long)(rank > 2 ? gstr[1] : 0), (unsigned long long)(rank > 3 ? gstr[2] : 0),
+        (unsigned long long)(rank > 4 ? gstr[3] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0,
+        rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0);
+  }
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  return n;
+}
+
+static unsigned int* g_sink_host = nullptr;
+static unsigned int* g_sink_dev = nullptr;
+static void init_sink() {
+  if (g_sink_host) return;
+  void* h = nullptr;
+  if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) != cudaSuccess) return;
+  memset(h, 0, 64);
+  void* d = nullptr;
+  if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) return;
+  g_sink_host = static_cast<unsigned int*>(h);
+  g_sink_dev = static_cast<unsigned int*>(d);
+}
+unsigned int* error_sink_host() { init_sink(); return g_sink_host; }
+unsigned int* error_sink_device() { init_sink(); return g_sink_dev; }
+
+}  // namespace uegan
+
+extern "C" {
+int uegan_abi_version(void) { return UEGAN_ABI_VERSION; }
+const char* uegan_last_error(void) { return uegan::get_error(); }
+}

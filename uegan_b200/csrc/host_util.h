@@ -1,0 +1,42 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, tensor geometry, TMA encode.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/uegan_sm100.h"
+
+namespace uegan {
+
+int set_error(const char* fmt, ...);  // returns -1
+const char* get_error();
+
+#define UEGAN_CHECK(cond, ...)               \
+  do {                                       \
+    if (!(cond)) return set_error(__VA_ARGS__); \
+  } while (0)
+
+#define UEGAN_CUDA(expr)                                                                      \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) return set_error("%s failed: %s", #expr, cudaGetErrorString(_e));  \
+  } while (0)
+
+inline int dtype_size(int dtype) { return dtype == UEGAN_BF16 ? 2 : 4; }
+inline int64_t t_wp(const uegan_tensor& t) { return (int64_t)t.w + 2 * t.halo; }
+inline int64_t t_hp(const uegan_tensor& t) { return (int64_t)t.h + 2 * t.halo; }
+inline int64_t t_elems(const uegan_tensor& t) { return (int64_t)t.n * t_hp(t) * t_wp(t) * t.c; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
+int encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, uint32_t rank, void* base, const uint64_t* dims,
+                 const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, CUtensorMapSwizzle swz);
+
+int num_sms();
+
+// One host-mapped word the kernels' bounded waits write their code to before trapping.
+unsigned int* error_sink_host();
+unsigned int* error_sink_device();
+
+}  // namespace uegan

@@ -1,0 +1,5 @@
+// Unity translation unit of libuegan_sm100.so (one nvcc invocation, no relocatable device code).
+#include "host_util.cu"
+#include "conv_fprop.cu"
+#include "elementwise.cu"
+#include "probe.cu"

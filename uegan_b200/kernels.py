@@ -1,0 +1,123 @@
+"""Host-side wrappers over the C ABI: NHWC-with-halo activation buffers (torch owns the memory, the kernels are
+ours) and one Python function per exported entry point.  torch is plumbing here: allocator + stream."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+_TORCH_DTYPE = {L.F32: torch.float32, L.BF16: torch.bfloat16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class NHWC:
+    """Activation buffer: n x (h+2*halo) x (w+2*halo) x c, dtype F32 (tf32 math) or BF16, plus zeroed slack so
+    a 128-byte TMA window that starts at the last pixel never leaves the allocation."""
+
+    SLACK = 512
+
+    def __init__(self, n, h, w, c, halo=0, dtype=L.F32, device="cuda", zero=False):
+        es = 2 if dtype == L.BF16 else 4
+        assert (c * es) % 16 == 0, "channel vector must be a multiple of 16 bytes"
+        self.n, self.h, self.w, self.c, self.halo, self.dtype = n, h, w, c, halo, dtype
+        elems = n * (h + 2 * halo) * (w + 2 * halo) * c
+        alloc = torch.zeros if zero else torch.empty
+        self.buf = alloc(elems + self.SLACK // es, dtype=_TORCH_DTYPE[dtype], device=device)
+        if not zero:
+            self.buf[elems:].zero_()
+        self.elems = elems
+        self.ct = L.Tensor(self.buf.data_ptr(), n, h, w, c, halo, dtype)
+
+    def ref(self):
+        return C.byref(self.ct)
+
+    def padded_view(self) -> torch.Tensor:
+        return self.buf[: self.elems].view(self.n, self.h + 2 * self.halo, self.w + 2 * self.halo, self.c)
+
+    def interior_nchw(self) -> torch.Tensor:
+        """Interior as a float32 NCHW torch tensor (test/debug readback; not on the hot path)."""
+        v = self.padded_view()
+        p = self.halo
+        v = v[:, p:p + self.h, p:p + self.w, :]
+        return v.permute(0, 3, 1, 2).float().contiguous()
+
+
+def packed_weight(weight: torch.Tensor, cin_stored: int, dtype: int, cin_first: int = 0, cin: Optional[int] = None,
+                  transpose_flip: bool = False) -> torch.Tensor:
+    """nn.Conv2d.weight (OIHW fp32, CUDA) -> K-major packed operand of the implicit GEMM."""
+    lib = L.load()
+    w = weight.detach()
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+    o, i_total, k, k2 = w.shape
+    assert k == k2
+    if cin is None:
+        cin = i_total - cin_first
+    cout = i_total if transpose_flip else o
+    if transpose_flip:
+        cin = o
+    nbytes = lib.uegan_packed_weight_bytes(cout, cin_stored, k, dtype)
+    buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
+    L.check(lib.uegan_pack_conv_weight(w.data_ptr(), buf.data_ptr(), cout, i_total, cin_first, cin, cin_stored, k,
+                                       dtype, int(transpose_flip), _stream()), "pack_conv_weight")
+    return buf
+
+
+def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, pad: int, y: Optional[NHWC] = None,
+               y_c_off: int = 0, bias: Optional[torch.Tensor] = None, alpha: Optional[torch.Tensor] = None,
+               act: int = L.ACT_NONE, mul: Optional[NHWC] = None, out_nchw: Optional[torch.Tensor] = None,
+               residual_nchw: Optional[torch.Tensor] = None):
+    lib = L.load()
+    d = L.ConvDesc()
+    d.x = x.ct
+    if y is not None:
+        d.y = y.ct
+    d.y_c_off, d.cout, d.k, d.stride, d.pad, d.act = y_c_off, cout, k, stride, pad, act
+    d.w_packed = w_packed.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.alpha = alpha.data_ptr() if alpha is not None else None
+    d.mul = C.pointer(mul.ct) if mul is not None else None
+    d.out_nchw = out_nchw.data_ptr() if out_nchw is not None else None
+    d.residual_nchw = residual_nchw.data_ptr() if residual_nchw is not None else None
+    L.check(lib.uegan_conv2d_fprop(C.byref(d), _stream()), "conv2d_fprop")
+
+
+def pack_input(x_nchw: torch.Tensor, dst: NHWC, pad_mode: int = L.PAD_REFLECT, scale=None, shift=None):
+    assert x_nchw.is_cuda and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and x_nchw.shape[1] == 3
+    assert tuple(x_nchw.shape) == (dst.n, 3, dst.h, dst.w)
+    L.check(L.load().uegan_pack_input(x_nchw.data_ptr(), dst.ref(), pad_mode, L.float3(scale), L.float3(shift),
+                                      _stream()), "pack_input")
+
+
+def halo_fill(t: NHWC, pad_mode: int = L.PAD_REFLECT):
+    L.check(L.load().uegan_halo_fill(t.ref(), pad_mode, _stream()), "halo_fill")
+
+
+def instance_norm(src: NHWC, dst: NHWC, dst_c_off: int, stats_ws: torch.Tensor, eps: float = 1e-5):
+    assert stats_ws.dtype == torch.float64 and stats_ws.numel() >= 3 * src.n * src.c
+    L.check(L.load().uegan_instance_norm(src.ref(), dst.ref(), dst_c_off, eps, stats_ws.data_ptr(), _stream()),
+            "instance_norm")
+
+
+def upsample2x(src: NHWC, dst: NHWC, dst_c_off: int = 0):
+    L.check(L.load().uegan_upsample2x(src.ref(), dst.ref(), dst_c_off, _stream()), "upsample2x")
+
+
+def maxpool2x2(src: NHWC, dst: NHWC):
+    L.check(L.load().uegan_maxpool2x2(src.ref(), dst.ref(), _stream()), "maxpool2x2")
+
+
+def unpack_nchw(src: NHWC, c_off: int, c_count: int) -> torch.Tensor:
+    out = torch.empty(src.n, c_count, src.h, src.w, dtype=torch.float32, device=src.buf.device)
+    L.check(L.load().uegan_unpack_nchw(src.ref(), c_off, c_count, out.data_ptr(), _stream()), "unpack_nchw")
+    return out
+
+
+def device_error() -> int:
+    """Synchronises and returns the watchdog word (0 = no bounded wait expired)."""
+    return L.load().uegan_device_error()

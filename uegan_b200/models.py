@@ -1,0 +1,222 @@
+"""Drop-in `models` module: `Generator` / `Discriminator` with the reference constructors, parameter names
+(state_dict keys) and forward contracts (/root/reference/models.py:10-74, 104-182), executing on the
+hand-written sm_100a kernels behind include/uegan_sm100.h.
+
+The torch.nn modules built here are PARAMETER CONTAINERS ONLY (so that `.parameters()`, `.apply(init_fn)`,
+`.state_dict()` / `.load_state_dict()` and checkpoints behave exactly like the reference's);
+they are never called.  `forward` runs the native plan; there is no PyTorch/CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import kernels as K
+
+_ACTS = {"LeakyReLU": L.ACT_LRELU, "ReLU": L.ACT_RELU, "none": L.ACT_NONE}
+
+
+def _act_module(name):
+    # get_act_fun, models.py:249-264 (containers only; Swish/SELU have no native epilogue yet)
+    if name == "LeakyReLU":
+        return nn.LeakyReLU(0.2, inplace=True)
+    if name == "ReLU":
+        return nn.ReLU(inplace=True)
+    if name == "none":
+        return nn.Sequential()
+    if name in ("Swish", "SELU"):
+        raise NotImplementedError("activation function [%s] has no sm_100a epilogue in uegan_b200" % name)
+    raise NotImplementedError("activation function [%s] is not found" % name)
+
+
+def _check_norm(name):
+    # get_norm_fun, models.py:272-281
+    if name == "none":
+        return
+    if name in ("BatchNorm", "InstanceNorm"):
+        raise NotImplementedError("normalization function [%s] has no sm_100a path in uegan_b200" % name)
+    raise NotImplementedError("normalization function [%s] is not found" % name)
+
+
+class Identity(nn.Module):
+    pass
+
+
+def _holder(cin, cout, k, stride=1, bias=True, extra=()):
+    """ReflectionPad2d + Conv2d (+ norm placeholder + activation) holder with the reference's child indices."""
+    mods = [nn.ReflectionPad2d((k - 1) // 2), nn.Conv2d(cin, cout, k, stride=stride, padding=0, bias=bias)]
+    mods.extend(extra)
+    return nn.Sequential(*mods)
+
+
+class _MainHolder(nn.Module):
+    """ConvBlock / SNConv shell: parameters live under `.main.1` (models.py:77-101)."""
+
+    def __init__(self, cin, cout, k, stride=1, extra=()):
+        super().__init__()
+        self.main = _holder(cin, cout, k, stride, True, extra)
+
+    @property
+    def conv(self):
+        return self.main[1]
+
+
+class _GAMHolder(nn.Module):
+    """GAM parameters (models.py:215-228): conv.0, conv.2 (no bias), fuse.0 (bias)."""
+
+    def __init__(self, c, reduction=8):
+        super().__init__()
+        self.conv = nn.Sequential(nn.Conv2d(2 * c, c // reduction, 1, bias=False), nn.ReLU(inplace=True),
+                                  nn.Conv2d(c // reduction, c, 1, bias=False))
+        self.fuse = nn.Sequential(nn.Conv2d(2 * c, c, 1, bias=True))
+
+
+class _Interp(nn.Module):
+    pass
+
+
+class _ParamCache:
+    """Re-packs a parameter into its kernel operand only when the parameter changed (optimizer step / load)."""
+
+    def __init__(self):
+        self.store = {}
+
+    def get(self, key, param, fn):
+        tag = (param.data_ptr(), param._version)
+        hit = self.store.get(key)
+        if hit is None or hit[0] != tag:
+            hit = (tag, fn())
+            self.store[key] = hit
+        return hit[1]
+
+
+class Generator(nn.Module):
+    """Generator network (reference: models.py:10-74).  forward: (B,3,H,W) fp32 in [-1,1], H,W % 16 == 0."""
+
+    def __init__(self, conv_dim, norm_fun, act_fun, use_sn):
+        super().__init__()
+        _check_norm(norm_fun)
+        if use_sn:
+            raise NotImplementedError("spectral norm inside the Generator has no sm_100a path in uegan_b200 "
+                                      "(reference default g_use_sn=False, config.py:23)")
+        self.conv_dim, self.act_fun = conv_dim, act_fun
+        self._act = _ACTS.get(act_fun)
+        d = conv_dim
+
+        def block(cin, cout, k, stride=1):
+            return _MainHolder(cin, cout, k, stride, (Identity(), _act_module(act_fun)))
+
+        self.enc1 = block(3, d, 7)
+        self.enc2 = block(d, 2 * d, 3, 2)
+        self.enc3 = block(2 * d, 4 * d, 3, 2)
+        self.enc4 = block(4 * d, 8 * d, 3, 2)
+        self.enc5 = block(8 * d, 16 * d, 3, 2)
+        self.upsample1 = nn.Sequential(_Interp(), _MainHolder(16 * d, 8 * d, 1))
+        self.upsample2 = nn.Sequential(_Interp(), _MainHolder(8 * d, 4 * d, 1))
+        self.upsample3 = nn.Sequential(_Interp(), _MainHolder(4 * d, 2 * d, 1))
+        self.upsample4 = nn.Sequential(_Interp(), _MainHolder(2 * d, d, 1))
+        self.dec1 = block(16 * d, 8 * d, 3)
+        self.dec2 = block(8 * d, 4 * d, 3)
+        self.dec3 = block(4 * d, 2 * d, 3)
+        self.dec4 = block(2 * d, d, 3)
+        self.dec5 = nn.Sequential(_MainHolder(d, d, 3), _MainHolder(d, 3, 7), nn.Tanh())
+        self.ga5 = _GAMHolder(16 * d)
+        self.ga4 = _GAMHolder(8 * d)
+        self.ga3 = _GAMHolder(4 * d)
+        self.ga2 = _GAMHolder(2 * d)
+        self.ga1 = _GAMHolder(d)
+        self._plans = {}
+        self._wcache = _ParamCache()
+
+    # ---------------------------------------------------------------- native forward
+    def _w(self, name, conv, cin_stored, cin_first=0, cin=None):
+        return self._wcache.get(name, conv.weight,
+                                lambda: K.packed_weight(conv.weight, cin_stored, L.F32, cin_first, cin))
+
+    def _plan(self, b, h, w, device):
+        key = (b, h, w, str(device))
+        pl = self._plans.get(key)
+        if pl is None:
+            d = self.conv_dim
+            T = lambda hh, ww, c, halo=0, zero=False: K.NHWC(b, hh, ww, c, halo, L.F32, device, zero)
+            pl = dict(
+                x0=T(h, w, 4, 3, zero=True),
+                x1=T(h, w, d, 1), x2=T(h // 2, w // 2, 2 * d, 1), x3=T(h // 4, w // 4, 4 * d, 1),
+                x4=T(h // 8, w // 8, 8 * d, 1), x5=T(h // 16, w // 16, 16 * d),
+                z5=T(h // 16, w // 16, 16 * d), x5n=T(h // 16, w // 16, 16 * d),
+                u1=T(h // 16, w // 16, 8 * d), cat1=T(h // 8, w // 8, 16 * d, 1), z4=T(h // 8, w // 8, 8 * d),
+                y1=T(h // 8, w // 8, 8 * d),
+                u2=T(h // 8, w // 8, 4 * d), cat2=T(h // 4, w // 4, 8 * d, 1), z3=T(h // 4, w // 4, 4 * d),
+                y2=T(h // 4, w // 4, 4 * d),
+                u3=T(h // 4, w // 4, 2 * d), cat3=T(h // 2, w // 2, 4 * d, 1), z2=T(h // 2, w // 2, 2 * d),
+                y3=T(h // 2, w // 2, 2 * d),
+                u4=T(h // 2, w // 2, d), cat4=T(h, w, 2 * d, 1), z1=T(h, w, d),
+                y4m=T(h, w, d, 1), t=T(h, w, d, 3),
+                stats=torch.empty(3 * b * 16 * d, dtype=torch.float64, device=device),
+            )
+            self._plans[key] = pl
+        return pl
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise L.UeganError("uegan_b200.models.Generator runs on CUDA (sm_100a) only; no CPU fallback")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import generator_apply  # training path (fprop + dgrad + wgrad kernels)
+            return generator_apply(self, x)
+        return self.forward_native(x)
+
+    @torch.no_grad()
+    def forward_native(self, x, keep=None):
+        assert x.dim() == 4 and x.shape[1] == 3, "expected (B,3,H,W)"
+        b, _, h, w = x.shape
+        if h % 16 or w % 16 or h < 32 or w < 32:
+            raise ValueError("Generator needs H, W multiples of 16 and >= 32 (models.py:55-67 skip concat)")
+        if self._act is None:
+            raise NotImplementedError("activation function [%s] has no sm_100a epilogue" % self.act_fun)
+        x = x.contiguous().float()
+        d, act, P = self.conv_dim, self._act, self._plan(b, h, w, x.device)
+        c = lambda holder: holder.conv
+
+        def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE, off=0, mul=None, bias=True):
+            cv = c(holder)
+            K.conv_fprop(src, self._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, off,
+                         cv.bias if bias else None, None, act_, mul)
+
+        K.pack_input(x, P["x0"], L.PAD_REFLECT)
+        conv(P["x0"], "enc1", self.enc1, d, 7, 1, P["x1"], act); K.halo_fill(P["x1"])
+        conv(P["x1"], "enc2", self.enc2, 2 * d, 3, 2, P["x2"], act); K.halo_fill(P["x2"])
+        conv(P["x2"], "enc3", self.enc3, 4 * d, 3, 2, P["x3"], act); K.halo_fill(P["x3"])
+        conv(P["x3"], "enc4", self.enc4, 8 * d, 3, 2, P["x4"], act); K.halo_fill(P["x4"])
+        conv(P["x4"], "enc5", self.enc5, 16 * d, 3, 2, P["x5"], act)
+
+        def gam(name, ga, src, ch, z, dst, off):
+            # GAM(x) == IN(conv1x1(x, fuse.weight[:, :C])): the attention branch and fuse bias are constant per
+            # (n, c) and cancel in the InstanceNorm that follows (models.py:230-237; SURVEY.md 8a rewrite 1).
+            fuse = ga.fuse[0]
+            wp = self._wcache.get(name, fuse.weight, lambda: K.packed_weight(fuse.weight, src.c, L.F32, 0, ch))
+            K.conv_fprop(src, wp, ch, 1, 1, 0, z)
+            K.instance_norm(z, dst, off, P["stats"])
+
+        gam("ga5", self.ga5, P["x5"], 16 * d, P["z5"], P["x5n"], 0)
+        stages = [("upsample1", self.upsample1, "ga4", self.ga4, "dec1", self.dec1, "x5n", "x4", "u1", "cat1", "z4", "y1", 8 * d),
+                  ("upsample2", self.upsample2, "ga3", self.ga3, "dec2", self.dec2, "y1", "x3", "u2", "cat2", "z3", "y2", 4 * d),
+                  ("upsample3", self.upsample3, "ga2", self.ga2, "dec3", self.dec3, "y2", "x2", "u3", "cat3", "z2", "y3", 2 * d),
+                  ("upsample4", self.upsample4, "ga1", self.ga1, "dec4", self.dec4, "y3", "x1", "u4", "cat4", "z1", "y4m", d)]
+        for un, up, gn, ga, dn, dec, src, skip, u, cat, z, y, ch in stages:
+            # conv1x1 then bilinear x2 == bilinear x2 then conv1x1 (both linear, lerp weights sum to 1): run the
+            # 1x1 at low resolution (models.py:23-26; SURVEY.md 8a rewrite 2)
+            conv(P[src], un, up[1], ch, 1, 1, P[u])
+            K.upsample2x(P[u], P[cat], 0)
+            gam(gn, ga, P[skip], ch, P[z], P[cat], ch)
+            K.halo_fill(P[cat])
+            last = dn == "dec4"
+            conv(P[cat], dn, dec, ch, 3, 1, P[y], act, 0, P["x1"] if last else None)  # dec4 fuses y4.mul(x1)
+        K.halo_fill(P["y4m"])
+        conv(P["y4m"], "dec5.0", self.dec5[0], d, 3, 1, P["t"]); K.halo_fill(P["t"])
+        out = torch.empty_like(x)
+        cv = c(self.dec5[1])
+        K.conv_fprop(P["t"], self._w("dec5.1", cv, d), 3, 7, 1, 3, None, 0, cv.bias, None, L.ACT_TANH, None, out, x)
+        if keep is not None:
+            keep.update(P)
+        return out
