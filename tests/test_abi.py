@@ -1,0 +1,77 @@
+"""CPU-side checks of the boundary: the shared library loads, exports every symbol include/uegan_sm100.h declares,
+and the native modules keep the reference's parameter names / counts.  No compute calls."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "uegan_sm100.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(uegan_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from uegan_b200 import _lib
+    lib = _lib.load()
+    declared = header_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype in uegan_b200/_lib.py"
+    assert set(_lib.SYMBOLS) == set(declared)
+    assert lib.uegan_abi_version() == _lib.ABI_VERSION
+
+
+def test_sass_is_blackwell_native():
+    """tcgen05.mma -> UTC*MMA, TMA -> UTMALDG, tcgen05.ld -> LDTM must be present in the shipped SASS."""
+    import shutil
+    import subprocess
+    from uegan_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_generator_state_dict_matches_reference_keys():
+    from oracle import uegan_oracle as O
+    from uegan_b200.models import Generator
+    G = Generator(32, "none", "LeakyReLU", False)
+    ref = O.make_generator_params(32, 0)
+    sd = G.state_dict()
+    assert set(sd) == set(ref) and len(sd) == 50
+    for k in ref:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    assert sum(p.numel() for p in G.parameters()) == 4158435  # trainer.py:393-399 printout of the reference
+    # init_weights (trainer.py:357-390) keys on class names containing 'Conv'
+    convs = [m for m in G.modules() if m.__class__.__name__.find("Conv") != -1 and hasattr(m, "weight")]
+    assert len(convs) == 30
+
+
+def test_product_path_has_no_cpu_fallback():
+    from uegan_b200 import _lib
+    from uegan_b200.models import Generator
+    G = Generator(8, "none", "LeakyReLU", False)
+    with pytest.raises(_lib.UeganError):
+        G(torch.zeros(1, 3, 32, 32))
+    for bad in (dict(norm_fun="BatchNorm"), dict(act_fun="Swish"), dict(use_sn=True), dict(norm_fun="nope")):
+        kw = dict(conv_dim=8, norm_fun="none", act_fun="LeakyReLU", use_sn=False)
+        kw.update(bad)
+        with pytest.raises(NotImplementedError):
+            Generator(**kw)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "uegan_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("no oracle", ""), f

@@ -36,6 +36,17 @@ def fill_nhwc(K, x_nchw, c_stored, halo, pad_mode, dtype):
     return t
 
 
+def tf32(x):
+    """cvt.rna.tf32.f32 emulation: round to nearest (ties away) onto 10 mantissa bits."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def quant(x, dtype):
+    from uegan_b200 import _lib as L
+    return tf32(x) if dtype == L.F32 else x.bfloat16().float()
+
+
 def relerr(a, b):
     return float((a.double() - b.double()).abs().max() / max(float(b.abs().max()), 1e-30))
 
@@ -67,8 +78,8 @@ def test_conv_fprop(K, case, dtype_name):
     dtype = L.F32 if dtype_name == "f32" else L.BF16
     pm = L.PAD_REFLECT if pad_mode == "reflect" else L.PAD_ZERO
     g = torch.Generator(device="cuda").manual_seed(1234)
-    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
-    wgt = torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k)
+    x = quant(torch.randn(n, cin, h, w, device="cuda", generator=g), dtype)
+    wgt = quant(torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k), dtype)
     bias = torch.randn(cout, device="cuda", generator=g) * 0.1
     pad = (k - 1) // 2
     vec = 4 if dtype == L.F32 else 8
@@ -80,11 +91,12 @@ def test_conv_fprop(K, case, dtype_name):
     wp = K.packed_weight(wgt, c_stored, dtype)
     K.conv_fprop(xt, wp, cout, k, stride, pad, y, 16, bias, None, L.ACT_LRELU)
     assert K.device_error() == 0
-    xq, wq = (x, wgt) if dtype == L.F32 else (x.bfloat16().float(), wgt.bfloat16().float())
-    xpad = F.pad(xq, (pad,) * 4, mode="reflect" if pad_mode == "reflect" else "constant") if pad else xq
-    ref = F.leaky_relu(F.conv2d(xpad, wq, bias, stride=stride), 0.2)
+    xpad = F.pad(x, (pad,) * 4, mode="reflect" if pad_mode == "reflect" else "constant") if pad else x
+    ref = F.leaky_relu(F.conv2d(xpad.double(), wgt.double(), bias.double(), stride=stride), 0.2).float()
     got = y.interior_nchw()[:, 16:]
-    tol = 2e-3 if dtype == L.F32 else 1e-2
+    # operands are exactly representable, accumulation is fp32: what is left is the output rounding to the
+    # storage format (tf32: 2^-11, bf16: 2^-8 of the value) and fp32 summation order
+    tol = 6e-4 if dtype == L.F32 else 5e-3
     assert relerr(got, ref) < tol, f"{name}: rel err {relerr(got, ref):.3e}"
     assert float(y.interior_nchw()[:, :16].abs().max()) == 0.0  # neighbouring slice untouched
     assert float(y.padded_view()[:, 0].abs().max()) == 0.0  # halo untouched by the conv
@@ -95,9 +107,9 @@ def test_conv_planar_head(K):
     from uegan_b200 import _lib as L
     g = torch.Generator(device="cuda").manual_seed(7)
     n, cin, h, w = 2, 32, 24, 40
-    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    x = tf32(torch.randn(n, cin, h, w, device="cuda", generator=g))
     for cout, k, resid in ((1, 7, False), (3, 7, True), (1, 5, False)):
-        wgt = torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k)
+        wgt = tf32(torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k))
         bias = torch.randn(cout, device="cuda", generator=g) * 0.1
         pad = (k - 1) // 2
         xt = fill_nhwc(K, x, cin, pad, L.PAD_REFLECT, L.F32)
@@ -106,19 +118,19 @@ def test_conv_planar_head(K):
         K.conv_fprop(xt, K.packed_weight(wgt, cin, L.F32), cout, k, 1, pad, None, 0, bias, None, L.ACT_TANH, None,
                      out, res)
         assert K.device_error() == 0
-        ref = torch.tanh(F.conv2d(F.pad(x, (pad,) * 4, mode="reflect"), wgt, bias))
+        ref = torch.tanh(F.conv2d(F.pad(x, (pad,) * 4, mode="reflect").double(), wgt.double(), bias.double())).float()
         if resid:
             ref = torch.clamp(ref + res, -1, 1)
-        assert relerr(out, ref) < 2e-3
+        assert relerr(out, ref) < 2e-5  # planar fp32 output is not rounded: fp32 accumulation error only
 
 
 def test_conv_alpha_and_mul(K):
     from uegan_b200 import _lib as L
     g = torch.Generator(device="cuda").manual_seed(8)
     n, cin, h, w, cout = 2, 64, 16, 16, 32
-    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
-    m = torch.randn(n, cout, h, w, device="cuda", generator=g)
-    wgt = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / math.sqrt(cin * 9)
+    x = tf32(torch.randn(n, cin, h, w, device="cuda", generator=g))
+    m = tf32(torch.randn(n, cout, h, w, device="cuda", generator=g))
+    wgt = tf32(torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / math.sqrt(cin * 9))
     bias = torch.randn(cout, device="cuda", generator=g) * 0.1
     alpha = torch.tensor([0.37], device="cuda")
     xt = fill_nhwc(K, x, cin, 1, L.PAD_REFLECT, L.F32)
@@ -127,7 +139,7 @@ def test_conv_alpha_and_mul(K):
     K.conv_fprop(xt, K.packed_weight(wgt, cin, L.F32), cout, 3, 1, 1, y, 0, bias, alpha, L.ACT_LRELU, mt)
     assert K.device_error() == 0
     ref = F.leaky_relu(0.37 * F.conv2d(F.pad(x, (1,) * 4, mode="reflect"), wgt) + bias.view(1, -1, 1, 1), 0.2) * m
-    assert relerr(y.interior_nchw(), ref) < 2e-3
+    assert relerr(y.interior_nchw(), ref) < 6e-4
 
 
 @pytest.mark.parametrize("dtype_name", ["f32", "bf16"])
@@ -149,7 +161,7 @@ def test_elementwise(K, dtype_name):
     K.pack_input(x, t2, L.PAD_ZERO)
     assert relerr(t2.padded_view()[..., :3].float(), F.pad(x, (1,) * 4).permute(0, 2, 3, 1)) < tol
     # halo fill ------------------------------------------------------------------------
-    a = torch.randn(2, 32, 12, 20, device="cuda", generator=g)
+    a = quant(torch.randn(2, 32, 12, 20, device="cuda", generator=g), dtype)
     for halo in (1, 2, 3):
         ta = fill_nhwc(K, a, 32, 0, L.PAD_REFLECT, dtype)
         tb = K.NHWC(2, 12, 20, 32, halo, dtype, "cuda", zero=True)
@@ -177,7 +189,7 @@ def test_elementwise(K, dtype_name):
     K.instance_norm(ta, td, 0, torch.empty(3 * 32, dtype=torch.float64, device="cuda"))
     assert relerr(td.interior_nchw(), F.instance_norm(ta.interior_nchw(), eps=1e-5)) < 2e-3
     # bilinear x2 align_corners=True ---------------------------------------------------------
-    a = torch.randn(2, 64, 6, 10, device="cuda", generator=g)
+    a = quant(torch.randn(2, 64, 6, 10, device="cuda", generator=g), dtype)
     ta = fill_nhwc(K, a, 64, 0, L.PAD_REFLECT, dtype)
     td = K.NHWC(2, 12, 20, 128, 1, dtype, "cuda", zero=True)
     K.upsample2x(ta, td, 64)

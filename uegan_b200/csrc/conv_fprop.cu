@@ -369,14 +369,14 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   if (x.dtype == UEGAN_F32) {
     static bool attr_set = false;
     if (!attr_set) {
-      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
       attr_set = true;
     }
     conv_fprop_kernel<1><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
   } else {
     static bool attr_set = false;
     if (!attr_set) {
-      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
       attr_set = true;
     }
     conv_fprop_kernel<0><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);

@@ -85,10 +85,10 @@ extern "C" int uegan_probe_umma_window(const float* a, const float* b, float* ou
   const int need_rows = row_shift + 15 * (sbo_bytes / 128) + 8;
   UEGAN_CHECK(a_rows >= need_rows, "probe: a_rows %d < %d", a_rows, need_rows);
   const int smem = ((a_rows * 128 + 1023) / 1024) * 1024 + n * 128 + 2048;
-  UEGAN_CHECK(smem <= 227 * 1024, "probe: too much smem");
+  UEGAN_CHECK(smem <= 210 * 1024, "probe: too much smem");
   static bool attr_set = false;
   if (!attr_set) {
-    UEGAN_CUDA(cudaFuncSetAttribute(probe_umma_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UEGAN_CUDA(cudaFuncSetAttribute(probe_umma_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_set = true;
   }
   probe_umma_window_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(a, b, out, a_rows, n, row_shift,

@@ -1,0 +1,111 @@
+// Spectral normalisation of the Discriminator's strided convs (reference: models.py:185-188 ->
+// torch.nn.utils.spectral_norm, n_power_iterations=1, dim=0, eps=1e-12).  W is the OIHW fp32 weight viewed as a
+// (rows = cout) x (cols = cin*k*k) row-major matrix.
+//   train:  v <- normalize(W^T u);  u <- normalize(W v);  sigma = u . (W v)
+//   eval :  sigma = u . (W v) with the stored u, v
+// The convolution consumes the UN-normalised packed weight; 1/sigma is applied as the epilogue's `alpha`.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace uegan {
+
+// t[col] = sum_row W[row][col] * u[row];  threads along columns (coalesced), each block covers a row slab.
+__global__ void sn_wt_u_kernel(const float* __restrict__ w, const float* __restrict__ u, float* __restrict__ t,
+                               int rows, int cols, int rows_per_block) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cols) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  int r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc += __ldg(w + (long long)r * cols + col) * __ldg(u + r);
+  atomicAdd(t + col, acc);
+}
+
+// nrm2[0] = sum_i t[i]^2
+__global__ void sn_sumsq_kernel(const float* __restrict__ t, int n, double* __restrict__ out) {
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += (double)t[i] * t[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// optional v <- t / max(||t||, eps) (train), then wv[row] = W[row] . v ; one warp per row
+__global__ void sn_w_v_kernel(const float* __restrict__ w, const float* __restrict__ t, const double* __restrict__ t_sumsq,
+                              float* __restrict__ v, float* __restrict__ wv, int rows, int cols, int train, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  float inv = 1.f;
+  if (train) inv = 1.f / fmaxf((float)sqrt(*t_sumsq), eps);
+  const float* src = train ? t : v;
+  float acc = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const float vv = src[c] * inv;
+    acc += __ldg(w + (long long)warp * cols + c) * vv;
+    if (train && warp == 0) v[c] = vv;  // row 0's warp also publishes the new v
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) wv[warp] = acc;
+}
+
+// single block: u <- normalize(wv) (train); sigma = u . wv; out[0] = sigma, out[1] = 1/sigma
+__global__ void sn_finalize_kernel(const float* __restrict__ wv, float* __restrict__ u, float* __restrict__ out, int rows,
+                                   int train, float eps) {
+  __shared__ double sh[32];
+  __shared__ float s_inv;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) acc += (double)wv[i] * wv[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
+    s_inv = 1.f / fmaxf((float)sqrt(s), eps);
+  }
+  __syncthreads();
+  double dot = 0.0;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    float ui = train ? wv[i] * s_inv : u[i];
+    if (train) u[i] = ui;
+    dot += (double)ui * wv[i];
+  }
+  dot = warp_sum(dot);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
+    out[0] = (float)s;
+    out[1] = (float)(1.0 / s);
+  }
+}
+
+}  // namespace uegan
+
+using namespace uegan;
+
+extern "C" int uegan_spectral_sigma(const float* w, float* u, float* v, int32_t rows, int32_t cols, int32_t train,
+                                    float* sigma_out, float* ws, void* stream) {
+  UEGAN_CHECK(w && u && v && sigma_out && ws, "spectral_sigma: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // ws layout: t[cols] | wv[rows] | sumsq (double, 8-byte aligned)
+  float* t = ws;
+  float* wv = ws + cols;
+  double* sumsq = reinterpret_cast<double*>(ws + ((cols + rows + 1) / 2) * 2);
+  const float eps = 1e-12f;
+  if (train) {
+    UEGAN_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * cols, st));
+    UEGAN_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double), st));
+    const int rpb = 32;
+    dim3 grid((cols + 127) / 128, (rows + rpb - 1) / rpb);
+    sn_wt_u_kernel<<<grid, 128, 0, st>>>(w, u, t, rows, cols, rpb);
+    sn_sumsq_kernel<<<(cols + 1023) / 1024 < 32 ? (cols + 1023) / 1024 : 32, 256, 0, st>>>(t, cols, sumsq);
+  }
+  sn_w_v_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(w, t, sumsq, v, wv, rows, cols, train, eps);
+  sn_finalize_kernel<<<1, 256, 0, st>>>(wv, u, sigma_out, rows, train, eps);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -16,6 +16,19 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _Counters:
+    launches = 0          # kernels of libuegan_sm100.so launched through this module
+    conv_events = None    # when a list: (start, end, flops) CUDA-event triples around every conv launch
+
+
+def _count(n: int):
+    _Counters.launches += n
+
+
+def launches() -> int:
+    return _Counters.launches
+
+
 class NHWC:
     """Activation buffer: n x (h+2*halo) x (w+2*halo) x c, dtype F32 (tf32 math) or BF16, plus zeroed slack so
     a 128-byte TMA window that starts at the last pixel never leaves the allocation."""
@@ -65,6 +78,7 @@ def packed_weight(weight: torch.Tensor, cin_stored: int, dtype: int, cin_first: 
     buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
     L.check(lib.uegan_pack_conv_weight(w.data_ptr(), buf.data_ptr(), cout, i_total, cin_first, cin, cin_stored, k,
                                        dtype, int(transpose_flip), _stream()), "pack_conv_weight")
+    _count(1)
     return buf
 
 
@@ -84,7 +98,18 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
     d.mul = C.pointer(mul.ct) if mul is not None else None
     d.out_nchw = out_nchw.data_ptr() if out_nchw is not None else None
     d.residual_nchw = residual_nchw.data_ptr() if residual_nchw is not None else None
+    ev = _Counters.conv_events
+    if ev is not None:
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
     L.check(lib.uegan_conv2d_fprop(C.byref(d), _stream()), "conv2d_fprop")
+    if ev is not None:
+        s1.record()
+        ho = (x.h + 2 * pad - k) // stride + 1
+        wo = (x.w + 2 * pad - k) // stride + 1
+        cin = 3 if x.c * (2 if x.dtype == L.BF16 else 4) == 16 else x.c
+        ev.append((s0, s1, 2.0 * x.n * ho * wo * cout * k * k * cin, x, cout, k, stride))
+    _count(1)
 
 
 def pack_input(x_nchw: torch.Tensor, dst: NHWC, pad_mode: int = L.PAD_REFLECT, scale=None, shift=None):
@@ -92,24 +117,29 @@ def pack_input(x_nchw: torch.Tensor, dst: NHWC, pad_mode: int = L.PAD_REFLECT, s
     assert tuple(x_nchw.shape) == (dst.n, 3, dst.h, dst.w)
     L.check(L.load().uegan_pack_input(x_nchw.data_ptr(), dst.ref(), pad_mode, L.float3(scale), L.float3(shift),
                                       _stream()), "pack_input")
+    _count(1)
 
 
 def halo_fill(t: NHWC, pad_mode: int = L.PAD_REFLECT):
     L.check(L.load().uegan_halo_fill(t.ref(), pad_mode, _stream()), "halo_fill")
+    _count(1)
 
 
 def instance_norm(src: NHWC, dst: NHWC, dst_c_off: int, stats_ws: torch.Tensor, eps: float = 1e-5):
     assert stats_ws.dtype == torch.float64 and stats_ws.numel() >= 3 * src.n * src.c
     L.check(L.load().uegan_instance_norm(src.ref(), dst.ref(), dst_c_off, eps, stats_ws.data_ptr(), _stream()),
             "instance_norm")
+    _count(3)
 
 
 def upsample2x(src: NHWC, dst: NHWC, dst_c_off: int = 0):
     L.check(L.load().uegan_upsample2x(src.ref(), dst.ref(), dst_c_off, _stream()), "upsample2x")
+    _count(1)
 
 
 def maxpool2x2(src: NHWC, dst: NHWC):
     L.check(L.load().uegan_maxpool2x2(src.ref(), dst.ref(), _stream()), "maxpool2x2")
+    _count(1)
 
 
 def unpack_nchw(src: NHWC, c_off: int, c_count: int) -> torch.Tensor:
