@@ -26,7 +26,8 @@ extern "C" {
 
 #define UEGAN_ABI_VERSION 1
 
-enum { UEGAN_F32 = 0, UEGAN_BF16 = 1 };                 /* storage dtype; F32 tensors feed kind::tf32 MMAs */
+enum { UEGAN_F32 = 0, UEGAN_BF16 = 1, UEGAN_F16 = 2 };  /* storage dtype; F32 tensors feed kind::tf32 MMAs, the
+                                                           16-bit types kind::f16 */
 enum { UEGAN_ACT_NONE = 0, UEGAN_ACT_LRELU = 1, UEGAN_ACT_RELU = 2, UEGAN_ACT_TANH = 3, UEGAN_ACT_SIGMOID = 4 };
 enum { UEGAN_PAD_ZERO = 0, UEGAN_PAD_REFLECT = 1 };
 
@@ -35,7 +36,7 @@ typedef struct uegan_tensor {
   int32_t n, h, w; /* logical (interior) extent */
   int32_t c;       /* stored channels per pixel (c * sizeof(dtype) must be a multiple of 16) */
   int32_t halo;    /* halo pixels on each side */
-  int32_t dtype;   /* UEGAN_F32 | UEGAN_BF16 */
+  int32_t dtype;   /* UEGAN_F32 | UEGAN_BF16 | UEGAN_F16 */
 } uegan_tensor;
 
 /* One implicit-GEMM convolution (tcgen05.mma + TMA), forward.
@@ -61,6 +62,9 @@ typedef struct uegan_conv_desc {
   const uegan_tensor* mul;     /* optional: y *= mul[n,ho,wo,co] after the activation (y4.mul(x1), models.py:70) */
   float* out_nchw;             /* optional planar fp32 output, see above */
   const float* residual_nchw;  /* optional, with out_nchw */
+  double* in_stats;            /* optional [n][cout][2]: the epilogue accumulates sum / sum of squares of the stored
+                                  outputs per (n, c) (zeroed by the call); consumed by uegan_instance_norm_apply.
+                                  Needs Ho*Wo >= 128 (tiles within one image). */
 } uegan_conv_desc;
 
 int uegan_abi_version(void);
@@ -89,15 +93,51 @@ int uegan_pack_input(const float* x_nchw, const uegan_tensor* dst, int32_t pad_m
 /* Writes the halo of t from its interior (reflect) or with zeros. */
 int uegan_halo_fill(const uegan_tensor* t, int32_t pad_mode, void* stream);
 /* nn.InstanceNorm2d(affine=False), biased variance, eps (models.py:227,236; losses.py:18):
- * dst[..., dst_c_off + c] = (src[..., c] - mean[n,c]) * rsqrt(var[n,c] + eps).  stats_ws: 2*n*c doubles. */
+ * dst[..., dst_c_off + c] = (src[..., c] - mean[n,c]) * rsqrt(var[n,c] + eps).  stats_ws: 3*n*c doubles. */
 int uegan_instance_norm(const uegan_tensor* src, const uegan_tensor* dst, int32_t dst_c_off, float eps,
                         double* stats_ws, void* stream);
+/* Second half of uegan_instance_norm for statistics produced by a convolution epilogue (conv_desc.in_stats):
+ * stats_ws holds [n][c][2] sums followed by room for n*c (mean, rstd) float pairs (3*n*c doubles in total). */
+int uegan_instance_norm_apply(const uegan_tensor* src, const uegan_tensor* dst, int32_t dst_c_off, float eps,
+                              double* stats_ws, void* stream);
 /* F.interpolate(scale_factor=2, mode='bilinear', align_corners=True) (models.py:191-201) into a channel slice. */
 int uegan_upsample2x(const uegan_tensor* src, const uegan_tensor* dst, int32_t dst_c_off, void* stream);
 /* nn.MaxPool2d(2,2) of torchvision vgg19.features (losses.py:43). */
 int uegan_maxpool2x2(const uegan_tensor* src, const uegan_tensor* dst, void* stream);
 /* NHWC tensor interior channels [c_off, c_off+c_count) -> NCHW fp32 (test / debug readback). */
 int uegan_unpack_nchw(const uegan_tensor* src, int32_t c_off, int32_t c_count, float* dst_nchw, void* stream);
+
+/* Spectral norm of one conv weight viewed as rows x cols (torch.nn.utils.spectral_norm, models.py:185-188):
+ * train != 0: v <- normalize(W^T u), u <- normalize(W v) in place; sigma_out[0] = u.(W v), sigma_out[1] = 1/sigma.
+ * ws: rows + cols + 8 floats of scratch. */
+int uegan_spectral_sigma(const float* w, float* u, float* v, int32_t rows, int32_t cols, int32_t train,
+                         float* sigma_out, float* ws, void* stream);
+
+/* Relativistic average GAN loss summed over `nscales` prediction maps (GANLoss.__call__, losses.py:393-409 with
+ * gan_mode 'rahinge' (mode 0, losses.py:348-362) or 'rals' (mode 1, :363-377)).  real[i] / fake[i]: fp32 maps of
+ * counts[i] elements (the mean is over the whole map incl. batch).  ws: 48 doubles, kept for the backward call.
+ * HOST arrays of device pointers. */
+int uegan_gan_loss_fwd(int32_t mode, int32_t for_discriminator, int32_t nscales, const float* const* real,
+                       const float* const* fake, const int64_t* counts, double* ws, float* loss_out, void* stream);
+/* d_real[i] / d_fake[i] (either may be NULL) += gscale * dloss/dmap, gscale = gscale_host * (gscale_dev ? *gscale_dev : 1).
+ * Includes the path through the batch-global means. */
+int uegan_gan_loss_bwd(int32_t mode, int32_t for_discriminator, int32_t nscales, const float* const* real,
+                       const float* const* fake, const int64_t* counts, const double* ws, float* const* d_real,
+                       float* const* d_fake, const float* gscale_dev, float gscale_host, void* stream);
+/* One PerceptualLoss term (losses.py:30-34): loss_inout[0] += weight * mean( (IN(x) - IN(y))^2 ), with the per-(n,c)
+ * (mean, rstd) pairs of x and y as produced by uegan_instance_norm_stats / a conv epilogue.  accum: 1 double (zero). */
+int uegan_in_mse_fwd(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
+                     float weight, double* accum, float* loss_inout, void* stream);
+/* MultiscaleRecLoss.forward (losses.py:219-231) on fp32 NCHW images: type 0 l1, 1 smoothl1, 2 l2; scales 1..3 with
+ * weights 1, 1/2, 1/4 and AvgPool2d(2) between scales.  If grad_nchw != NULL also writes grad_scale * dloss/dpred. */
+int uegan_msrec_loss(const float* pred_nchw, const float* gt_nchw, int32_t n, int32_t c, int32_t h, int32_t w,
+                     int32_t type, int32_t scales, double* accum, float* loss_out, float* grad_nchw, float grad_scale,
+                     void* stream);
+/* Per-(n,c) InstanceNorm statistics only: stats_ws gets [n][c][2] sums (doubles) followed by n*c (mean, rstd) float
+ * pairs; with sums_ready != 0 the sums are taken as already accumulated (conv_desc.in_stats) and only finalised.
+ * Returns the device pointer of the (mean, rstd) pairs in *mean_rstd_out. */
+int uegan_instance_norm_stats(const uegan_tensor* src, float eps, double* stats_ws, int32_t sums_ready,
+                              float** mean_rstd_out, void* stream);
 
 /* Hardware probe used by tests/DESIGN.md: runs a 128xNx(32*kchunks) tf32 GEMM whose A operand is read from a
  * shared-memory window shifted by `row_shift` 128-byte rows with the given descriptor base_offset; see

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libuegan_sm100.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 PAD_ZERO, PAD_REFLECT = 0, 1
 ABI_VERSION = 1
@@ -30,7 +30,7 @@ class ConvDesc(C.Structure):
     _fields_ = [("x", Tensor), ("y", Tensor), ("y_c_off", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32),
                 ("stride", C.c_int32), ("pad", C.c_int32), ("act", C.c_int32), ("w_packed", C.c_void_p),
                 ("bias", C.c_void_p), ("alpha", C.c_void_p), ("mul", C.POINTER(Tensor)), ("out_nchw", C.c_void_p),
-                ("residual_nchw", C.c_void_p)]
+                ("residual_nchw", C.c_void_p), ("in_stats", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/uegan_sm100.h declares
@@ -47,6 +47,21 @@ SYMBOLS = {
     "uegan_halo_fill": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_void_p]),
     "uegan_instance_norm": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_int32, C.c_float, C.c_void_p,
                                       C.c_void_p]),
+    "uegan_instance_norm_apply": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_int32, C.c_float, C.c_void_p,
+                                            C.c_void_p]),
+    "uegan_spectral_sigma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uegan_instance_norm_stats": (C.c_int, [C.POINTER(Tensor), C.c_float, C.c_void_p, C.c_int32,
+                                            C.POINTER(C.c_void_p), C.c_void_p]),
+    "uegan_gan_loss_fwd": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uegan_gan_loss_bwd": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.c_void_p, C.c_float, C.c_void_p]),
+    "uegan_in_mse_fwd": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uegan_msrec_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "uegan_upsample2x": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_int32, C.c_void_p]),
     "uegan_maxpool2x2": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
     "uegan_unpack_nchw": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -3,7 +3,7 @@
 //   warp 0   TMA producer   (one elected lane)
 //   warp 1   MMA issuer     (one elected lane)
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue      (TMEM -> registers -> alpha/bias/activation/mul -> global)
+//   warps 4-11 epilogue     (TMEM -> registers -> alpha/bias/activation/mul -> global)
 //
 // GEMM view (reference call sites: models.py:83,94,162,174; torchvision vgg19 convs, losses.py:43):
 //   M = 128 output pixels (a tn x th x tw box of the output), N = block_n output channels,
@@ -14,6 +14,8 @@
 //       kernel size / stride 1-2 / channel count (C*es % 16 == 0) is the same code path, and the landing
 //       layout (128 rows x 128 B, SWIZZLE_128B) is exactly the canonical K-major UMMA operand.
 //   Padding is never materialised by this kernel: the producer of x wrote the halo (reflect or zero).
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -26,16 +28,21 @@ constexpr int kTmemCols = 512;      // 2 accumulator stages x 256 fp32 columns
 struct ConvParams {
   // tiling
   int tw, th, tn;
+  int tw_log2, th_log2;
   int tiles_w, tiles_h, tiles_img;  // number of M tiles along wo / ho / n
   int n_tiles, block_n;
   int total_tiles;
   // K loop
   int kh, chunks_per_row, chunk_elems, num_k_chunks;
   int num_stages, stage_bytes;
+  // patch mode (stride-1, pixel = whole 128-byte chunks, weights resident in smem)
+  int patch_w, patch_nch, patch_k, patch_off;  // patch width in pixels, chunks per pixel, kernel size, halo - pad
+  int w_tile_bytes, w_total_bytes, stage_tx_bytes;
   // epilogue
   int Wo, Ho, Nimg, cout;
   int act;
-  int out_bf16;
+  int out_kind;  // storage of y / mul: UEGAN_F32 (tf32-rounded), UEGAN_BF16, UEGAN_F16
+  int ab_fmt;    // UMMA operand format of x and w
   void* out;  // points at element (n=0, y=0, x=0, c=y_c_off) of the interior
   long long out_pix, out_row, out_img;  // strides in elements
   const float* bias;
@@ -45,6 +52,7 @@ struct ConvParams {
   float* out_nchw;
   const float* residual_nchw;
   unsigned int* err_sink;  // host-mapped watchdog word
+  double* in_stats;        // optional [Nimg][cout][2] sum / sum-of-squares of the stored outputs (InstanceNorm)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -62,6 +70,13 @@ __device__ __forceinline__ float round_tf32(float v) {
   return __uint_as_float(r);
 }
 
+// value as it will be stored (so statistics and stores agree)
+__device__ __forceinline__ float round_store(float v, int kind) {
+  if (kind == UEGAN_F32) return round_tf32(v);
+  if (kind == UEGAN_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+  return __half2float(__float2half_rn(v));
+}
+
 struct TileCoord {
   int wo0, ho0, n0, nt;
 };
@@ -76,8 +91,144 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   return c;
 }
 
-template <int kTf32>
-__global__ void __launch_bounds__(256, 1)
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, int act_rt) {
+  if constexpr (ACT == UEGAN_ACT_LRELU) return fmaxf(v, 0.2f * v);
+  else if constexpr (ACT == UEGAN_ACT_RELU) return fmaxf(v, 0.f);
+  else if constexpr (ACT == UEGAN_ACT_NONE) return v;
+  else return apply_act(v, act_rt);
+}
+
+// NHWC epilogue of one warp: its 32 rows x the 16-column chunks {half, half+2, ...} of the tile.
+template <int ACT>
+__device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t taddr, int colbase, int half, long long o,
+                                              long long mo, bool valid, float alpha, float* stat_slice) {
+  for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
+    uint32_t rr[16];
+    tmem_ld16(taddr + c0, rr);
+    tmem_ld_wait();
+    const int col0 = colbase + c0;
+    if (col0 >= p.cout) continue;  // warp-uniform
+    if (p.in_stats) {
+      // per-(n, c) sum and sum of squares over this warp's 32 rows (all rows of a tile share n when tn == 1):
+      // recursive-halving butterfly, 31 shuffles for 32 values; lane L ends with the total of element L.
+      float a[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = __uint_as_float(rr[i]) * alpha;
+        if (p.bias) x += __ldg(p.bias + col0 + i);
+        x = act_t<ACT>(x, p.act);
+        x = round_store(x, p.out_kind);
+        x = valid ? x : 0.f;
+        a[i] = x;
+        a[16 + i] = x * x;
+      }
+#pragma unroll
+      for (int ofs = 16, len = 16; ofs >= 1; ofs >>= 1, len >>= 1) {
+        const bool up = (threadIdx.x & ofs) != 0;
+#pragma unroll
+        for (int i = 0; i < len; ++i) {
+          const float send = up ? a[i] : a[i + len];
+          const float keep = up ? a[i + len] : a[i];
+          a[i] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+        }
+      }
+      stat_slice[(c0 >> 5) * 32 + (threadIdx.x & 31)] += a[0];  // private to this lane; flushed when n changes
+    }
+    if (!valid) continue;
+    float v[16];
+    if (p.bias) {
+      const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b = __ldg(bp + i);
+        v[4 * i + 0] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 0]), alpha, b.x), p.act);
+        v[4 * i + 1] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 1]), alpha, b.y), p.act);
+        v[4 * i + 2] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 2]), alpha, b.z), p.act);
+        v[4 * i + 3] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 3]), alpha, b.w), p.act);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = act_t<ACT>(__uint_as_float(rr[i]) * alpha, p.act);
+    }
+    if (p.mul) {
+      if (p.out_kind != UEGAN_F32) {
+        const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.mul) + mo + c0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint4 qv = __ldg(mp + i);
+          const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (p.out_kind == UEGAN_BF16) {
+              const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+              v[8 * i + 2 * j] *= __low2float(h);
+              v[8 * i + 2 * j + 1] *= __high2float(h);
+            } else {
+              const __half2 h = *reinterpret_cast<const __half2*>(&w[j]);
+              v[8 * i + 2 * j] *= __low2float(h);
+              v[8 * i + 2 * j + 1] *= __high2float(h);
+            }
+          }
+        }
+      } else {
+        const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.mul) + mo + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 qv = __ldg(mp + i);
+          v[4 * i + 0] *= qv.x; v[4 * i + 1] *= qv.y; v[4 * i + 2] *= qv.z; v[4 * i + 3] *= qv.w;
+        }
+      }
+    }
+    if (p.out_kind != UEGAN_F32) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (p.out_kind == UEGAN_BF16) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+          pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        } else {
+          __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+          pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+      }
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + o + c0);
+      op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    } else {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o + c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        op[i] = make_float4(round_tf32(v[4 * i]), round_tf32(v[4 * i + 1]), round_tf32(v[4 * i + 2]),
+                            round_tf32(v[4 * i + 3]));
+    }
+  }
+}
+
+// planar fp32 NCHW epilogue (cout <= 16): D prediction heads, G's last conv (tanh, + residual, clamp)
+__device__ __forceinline__ void epilogue_planar(const ConvParams& p, uint32_t taddr, int colbase, int n, int ho, int wo,
+                                                bool valid, float alpha) {
+  uint32_t rr[16];
+  tmem_ld16(taddr, rr);
+  tmem_ld_wait();
+  if (!valid) return;
+  const long long plane = (long long)p.Ho * p.Wo;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (colbase + i < p.cout) {
+      const long long o = ((long long)n * p.cout + colbase + i) * plane + (long long)ho * p.Wo + wo;
+      float x = __uint_as_float(rr[i]) * alpha;
+      if (p.bias) x += __ldg(p.bias + colbase + i);
+      x = apply_act(x, p.act);
+      if (p.residual_nchw) x = fminf(fmaxf(x + __ldg(p.residual_nchw + o), -1.f), 1.f);
+      p.out_nchw[o] = x;
+    }
+  }
+}
+
+template <int kTf32, int kPatch>
+__global__ void __launch_bounds__(384, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -86,7 +237,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ __align__(8) uint64_t w_full;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_stats[8 * 256];  // InstanceNorm partial sums: [epilogue warp][chunk slot][lane]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,8 +255,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
+    mbar_init(&w_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, kTmemCols);
@@ -117,47 +271,101 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kABytes + p.block_n * 128;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
-        int r = 0, j = 0;
-        for (int kc = 0; kc < p.num_k_chunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1, 0x100 + stage, p.err_sink);
-          uint8_t* sa = smem + stage * p.stage_bytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          tma_load_5d(&tmA, &full_bar[stage], sa, j * p.chunk_elems, tc.wo0, r, tc.ho0, tc.n0);
-          tma_load_2d(&tmB, &full_bar[stage], sb, kc * p.chunk_elems, tc.nt * p.block_n);
-          if (++j == p.chunks_per_row) { j = 0; ++r; }
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+      if constexpr (kPatch) {
+        // weights: all k*k*nch [block_n x 128 B] tiles once per CTA, resident behind the A ring
+        uint8_t* sw = smem;
+        mbar_arrive_expect_tx(&w_full, (uint32_t)p.w_total_bytes);
+        const int ntiles_w = p.patch_k * p.patch_k * p.patch_nch;
+        for (int wi = 0; wi < ntiles_w; ++wi) {
+          const int c = wi % p.patch_nch, tap = wi / p.patch_nch;
+          const int r = tap / p.patch_k, s_ = tap % p.patch_k;
+          const int kofs = (r * p.chunks_per_row + s_ * p.patch_nch + c) * p.chunk_elems;
+          tma_load_2d(&tmB, &w_full, sw + wi * p.w_tile_bytes, kofs, 0);
+        }
+        uint8_t* sa0 = smem + p.w_total_bytes;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+          const TileCoord tc = decode_tile(p, t);
+          for (int c = 0; c < p.patch_nch; ++c) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 0x100 + stage, p.err_sink);
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_tx_bytes);
+            tma_load_4d(&tmA, &full_bar[stage], sa0 + stage * p.stage_bytes, c * p.chunk_elems, tc.wo0 + p.patch_off,
+                        tc.ho0 + p.patch_off, tc.n0);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else {
+        const uint32_t tx_bytes = kABytes + p.block_n * 128;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+          const TileCoord tc = decode_tile(p, t);
+          int r = 0, j = 0;
+          for (int kc = 0; kc < p.num_k_chunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 0x100 + stage, p.err_sink);
+            uint8_t* sa = smem + stage * p.stage_bytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_5d(&tmA, &full_bar[stage], sa, j * p.chunk_elems, tc.wo0, r, tc.ho0, tc.n0);
+            tma_load_2d(&tmB, &full_bar[stage], sb, kc * p.chunk_elems, tc.nt * p.block_n);
+            if (++j == p.chunks_per_row) { j = 0; ++r; }
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       // ===================== MMA issuer =====================
-      const uint32_t idesc = make_instr_desc(kTf32 ? UMMA_TF32 : UMMA_BF16, 128, p.block_n);
+      const uint32_t idesc = make_instr_desc(p.ab_fmt, 128, p.block_n);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if constexpr (kPatch) mbar_wait(&w_full, 0, 0x500, p.err_sink);
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 0x200 + acc, p.err_sink);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int kc = 0; kc < p.num_k_chunks; ++kc) {
-          mbar_wait(&full_bar[stage], phase, 0x300 + stage, p.err_sink);
-          tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-          const uint32_t b_addr = a_addr + kABytes;
+        if constexpr (kPatch) {
+          // one staged patch per 128-byte channel chunk; every filter tap (r, s) is the SAME smem patch read
+          // through a descriptor window shifted by (r*patch_w + s) rows (tcgen05 swizzles on absolute address bits,
+          // profiles/r1_probe_umma_window.json), 8-row groups = one output row of 8 pixels, SBO = patch row pitch.
+          const uint32_t w_addr = smem_u32(smem);
+          const uint32_t sbo = p.patch_w * 128;
+          uint32_t first = 0;
+          for (int c = 0; c < p.patch_nch; ++c) {
+            mbar_wait(&full_bar[stage], phase, 0x300 + stage, p.err_sink);
+            tcgen05_fence_after();
+            const uint32_t a_base = w_addr + p.w_total_bytes + stage * p.stage_bytes;
+            for (int r = 0; r < p.patch_k; ++r) {
+              for (int s_ = 0; s_ < p.patch_k; ++s_) {
+                const uint32_t a_addr = a_base + (r * p.patch_w + s_) * 128;
+                const uint32_t b_addr = w_addr + ((r * p.patch_k + s_) * p.patch_nch + c) * p.w_tile_bytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte swizzle row
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-            umma_ss<kTf32>(d_tmem, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, UMMA_LAYOUT_SW128);
+                  const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+                  umma_ss<kTf32>(d_tmem, da, db, idesc, first);
+                  first = 1;
+                }
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        } else {
+          for (int kc = 0; kc < p.num_k_chunks; ++kc) {
+            mbar_wait(&full_bar[stage], phase, 0x300 + stage, p.err_sink);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
+            const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte swizzle row
+              const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+              const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+              umma_ss<kTf32>(d_tmem, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         acc ^= 1;
@@ -165,79 +373,52 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int e = warp & 3;  // TMEM lane quarter this warp may read
-    const int m = e * 32 + lane;
+    // ===================== epilogue (8 warps: lane quarter = warp & 3, column half = (warp - 4) >> 2) ==========
+    const int q = warp & 3;          // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;  // interleaved 16-column chunks: half, half + 2, ...
+    const int m = q * 32 + lane;
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+    const int mw = m & (p.tw - 1), mh = (m >> p.tw_log2) & (p.th - 1), mn = m >> (p.tw_log2 + p.th_log2);
     int acc = 0;
     uint32_t acc_phase = 0;
+    float* stat_slice = s_stats + (warp - 4) * 256;
+    int stat_n = -1;
+    if (p.in_stats) {
+      for (int i = lane; i < 256; i += 32) stat_slice[i] = 0.f;
+    }
+    // element (slot, lane) of the slice = column (slot*32 + half*16 + (lane & 15)), sum if lane < 16 else sum of squares
+    auto flush_stats = [&](int key) {
+      const int n_img = key / p.n_tiles, nt = key % p.n_tiles;
+      for (int slot = 0; slot * 32 + half * 16 < p.block_n; ++slot) {
+        const int col = nt * p.block_n + slot * 32 + half * 16 + (lane & 15);
+        const float v = stat_slice[slot * 32 + lane];
+        stat_slice[slot * 32 + lane] = 0.f;
+        if (col < p.cout && v != 0.f)
+          atomicAdd(p.in_stats + ((long long)n_img * p.cout + col) * 2 + (lane >> 4), (double)v);
+      }
+    };
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
-      const int wo = tc.wo0 + m % p.tw;
-      const int ho = tc.ho0 + (m / p.tw) % p.th;
-      const int n = tc.n0 + m / (p.tw * p.th);
+      if (p.in_stats && tc.n0 * p.n_tiles + tc.nt != stat_n) {
+        if (stat_n >= 0) flush_stats(stat_n);
+        stat_n = tc.n0 * p.n_tiles + tc.nt;
+      }
+      const int wo = tc.wo0 + mw, ho = tc.ho0 + mh, n = tc.n0 + mn;
       const bool valid = (wo < p.Wo) && (ho < p.Ho) && (n < p.Nimg);
       mbar_wait(&tmem_full[acc], acc_phase, 0x400 + acc, p.err_sink);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(e * 32) << 16) + acc * 256;
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t rr[16];
-        tmem_ld16(taddr + c0, rr);
-        tmem_ld_wait();
-        const int col0 = tc.nt * p.block_n + c0;
-        if (!valid || col0 >= p.cout) continue;
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x = __uint_as_float(rr[i]) * alpha;
-          if (p.bias && col0 + i < p.cout) x += __ldg(p.bias + col0 + i);
-          v[i] = apply_act(x, p.act);
-        }
-        if (p.out_nchw) {
-          // planar fp32 output: cout <= 16 real channels (D prediction heads, G's last conv)
-          const long long plane = (long long)p.Ho * p.Wo;
-          for (int i = 0; i < 16; ++i) {
-            if (col0 + i < p.cout) {
-              const long long o = ((long long)n * p.cout + col0 + i) * plane + (long long)ho * p.Wo + wo;
-              float x = v[i];
-              if (p.residual_nchw) x = fminf(fmaxf(x + __ldg(p.residual_nchw + o), -1.f), 1.f);
-              p.out_nchw[o] = x;
-            }
-          }
-        } else {
-          const long long o = (long long)n * p.out_img + (long long)ho * p.out_row + (long long)wo * p.out_pix + col0;
-          if (p.mul) {
-            const long long mo = (long long)n * p.mul_img + (long long)ho * p.mul_row + (long long)wo * p.mul_pix + col0;
-            if (p.out_bf16) {
-              const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.mul) + mo;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] *= __bfloat162float(mp[i]);
-            } else {
-              const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.mul) + mo);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 q = __ldg(mp + i);
-                v[4 * i + 0] *= q.x; v[4 * i + 1] *= q.y; v[4 * i + 2] *= q.z; v[4 * i + 3] *= q.w;
-              }
-            }
-          }
-          if (p.out_bf16) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
-            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          } else {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              op[i] = make_float4(round_tf32(v[4 * i]), round_tf32(v[4 * i + 1]), round_tf32(v[4 * i + 2]),
-                                  round_tf32(v[4 * i + 3]));
-          }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+      const int colbase = tc.nt * p.block_n;
+      if (p.out_nchw) {
+        if (half == 0) epilogue_planar(p, taddr, colbase, n, ho, wo, valid, alpha);
+      } else {
+        const long long o = (long long)n * p.out_img + (long long)ho * p.out_row + (long long)wo * p.out_pix + colbase;
+        const long long mo = (long long)n * p.mul_img + (long long)ho * p.mul_row + (long long)wo * p.mul_pix + colbase;
+        switch (p.act) {
+          case UEGAN_ACT_LRELU: epilogue_nhwc<UEGAN_ACT_LRELU>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice); break;
+          case UEGAN_ACT_RELU: epilogue_nhwc<UEGAN_ACT_RELU>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice); break;
+          case UEGAN_ACT_NONE: epilogue_nhwc<UEGAN_ACT_NONE>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice); break;
+          default: epilogue_nhwc<-1>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice); break;
         }
       }
       tcgen05_fence_before();
@@ -246,6 +427,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.in_stats && stat_n >= 0) flush_stats(stat_n);
   }
 
   tcgen05_fence_before();
@@ -277,7 +459,7 @@ static PackGeom pack_geom(int cout, int cin_stored, int k, int dtype) {
 int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   const uegan_tensor& x = d.x;
   const int es = dtype_size(x.dtype);
-  UEGAN_CHECK(x.dtype == UEGAN_F32 || x.dtype == UEGAN_BF16, "conv: bad x dtype %d", x.dtype);
+  UEGAN_CHECK(dtype_ok(x.dtype), "conv: bad x dtype %d", x.dtype);
   UEGAN_CHECK((x.c * es) % 16 == 0, "conv: x.c*elem (%d) must be a multiple of 16 bytes", x.c * es);
   UEGAN_CHECK(d.stride == 1 || d.stride == 2, "conv: stride %d unsupported", d.stride);
   UEGAN_CHECK(d.pad <= x.halo, "conv: pad %d exceeds input halo %d", d.pad, x.halo);
@@ -294,6 +476,8 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   p.th = pow2_ceil(Ho);
   if (p.th > 128 / p.tw) p.th = 128 / p.tw;
   p.tn = 128 / (p.tw * p.th);
+  for (p.tw_log2 = 0; (1 << p.tw_log2) < p.tw; ++p.tw_log2) {}
+  for (p.th_log2 = 0; (1 << p.th_log2) < p.th; ++p.th_log2) {}
   p.tiles_w = (Wo + p.tw - 1) / p.tw;
   p.tiles_h = (Ho + p.th - 1) / p.th;
   p.tiles_img = (x.n + p.tn - 1) / p.tn;
@@ -309,11 +493,13 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   p.Wo = Wo; p.Ho = Ho; p.Nimg = x.n; p.cout = d.cout;
   p.act = d.act;
+  p.ab_fmt = x.dtype == UEGAN_F32 ? UMMA_TF32 : (x.dtype == UEGAN_BF16 ? UMMA_BF16 : UMMA_F16);
   p.bias = d.bias;
   p.alpha = d.alpha;
   p.out_nchw = d.out_nchw;
   p.residual_nchw = d.residual_nchw;
   p.err_sink = error_sink_device();
+  p.in_stats = d.in_stats;
   if (d.out_nchw) {
     UEGAN_CHECK(d.cout <= 16, "conv: planar output needs cout <= 16 (got %d)", d.cout);
   } else {
@@ -324,7 +510,8 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
     UEGAN_CHECK(d.cout % 16 == 0, "conv: NHWC output needs cout %% 16 == 0 (got %d)", d.cout);
     UEGAN_CHECK(d.y_c_off >= 0 && d.y_c_off + d.cout <= y.c && d.y_c_off % 8 == 0, "conv: bad channel slice");
     UEGAN_CHECK((y.c * dtype_size(y.dtype)) % 16 == 0, "conv: y.c misaligned");
-    p.out_bf16 = (y.dtype == UEGAN_BF16);
+    UEGAN_CHECK(dtype_ok(y.dtype), "conv: bad y dtype %d", y.dtype);
+    p.out_kind = y.dtype;
     p.out_pix = y.c;
     p.out_row = t_wp(y) * y.c;
     p.out_img = t_hp(y) * p.out_row;
@@ -342,15 +529,49 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
     }
   }
 
-  // ---- tensor maps
-  const CUtensorMapDataType dt = (x.dtype == UEGAN_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                                         : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  // ---- patch mode?  stride 1, k > 1, pixel = whole 128-byte chunks, single N tile, weights fit next to >= 2 A stages
+  const CUtensorMapDataType dt = x.dtype == UEGAN_BF16  ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : x.dtype == UEGAN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                        : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const uint64_t pix_b = (uint64_t)x.c * es;
   const uint64_t row_b = (uint64_t)t_wp(x) * pix_b;
   const uint64_t img_b = (uint64_t)t_hp(x) * row_b;
-  uint8_t* a_base = static_cast<uint8_t*>(x.data) + (uint64_t)(x.halo - d.pad) * row_b + (uint64_t)(x.halo - d.pad) * pix_b;
-  CUtensorMap tmA, tmB;
+  bool patch = false;
   {
+    const char* env = getenv("UEGAN_NO_PATCH");
+    const int PH = 16 + d.k - 1, PW = 8 + d.k - 1;
+    const long long a_stage = ((long long)PH * PW * 128 + 1023) / 1024 * 1024;
+    const long long w_tile = (long long)p.block_n * 128;
+    const long long w_total = w_tile * d.k * d.k * (pix_b / 128);
+    if (!(env && env[0] == '1') && d.stride == 1 && d.k > 1 && pix_b % 128 == 0 && p.n_tiles == 1 && Ho >= 16 &&
+        Wo >= 8 && w_total + 2 * a_stage <= 200 * 1024) {
+      patch = true;
+      p.tw = 8; p.th = 16; p.tn = 1; p.tw_log2 = 3; p.th_log2 = 4;
+      p.tiles_w = (Wo + 7) / 8;
+      p.tiles_h = (Ho + 15) / 16;
+      p.tiles_img = x.n;
+      p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_img;
+      p.patch_w = PW;
+      p.patch_nch = (int)(pix_b / 128);
+      p.patch_k = d.k;
+      p.patch_off = x.halo - d.pad;
+      p.w_tile_bytes = (int)w_tile;
+      p.w_total_bytes = (int)w_total;
+      p.stage_bytes = (int)a_stage;
+      p.stage_tx_bytes = PH * PW * 128;
+      p.num_stages = (int)((200 * 1024 - w_total) / a_stage);
+      if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+    }
+  }
+  // ---- tensor maps
+  CUtensorMap tmA, tmB;
+  if (patch) {
+    uint64_t dims[4] = {(uint64_t)x.c, (uint64_t)t_wp(x), (uint64_t)t_hp(x), (uint64_t)x.n};
+    uint64_t strides[3] = {pix_b, row_b, img_b};
+    uint32_t box[4] = {(uint32_t)g.chunk_elems, (uint32_t)p.patch_w, (uint32_t)(16 + d.k - 1), 1u};
+    if (encode_tiled(&tmA, dt, 4, x.data, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+  } else {
+    uint8_t* a_base = static_cast<uint8_t*>(x.data) + (uint64_t)(x.halo - d.pad) * row_b + (uint64_t)(x.halo - d.pad) * pix_b;
     uint64_t dims[5] = {(uint64_t)g.row_pad, (uint64_t)Wo, (uint64_t)d.k, (uint64_t)Ho, (uint64_t)x.n};
     uint64_t strides[4] = {(uint64_t)d.stride * pix_b, row_b, (uint64_t)d.stride * row_b, img_b};
     uint32_t box[5] = {(uint32_t)g.chunk_elems, (uint32_t)p.tw, 1u, (uint32_t)p.th, (uint32_t)p.tn};
@@ -364,22 +585,29 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
     if (encode_tiled(&tmB, dt, 2, const_cast<void*>(d.w_packed), dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return -1;
   }
-  const int smem_bytes = p.num_stages * p.stage_bytes + 1024;
+  if (d.in_stats) {
+    UEGAN_CHECK(!d.out_nchw && !d.mul, "conv: in_stats needs a plain NHWC epilogue");
+    UEGAN_CHECK(p.tn == 1, "conv: in_stats needs tiles within one image (Ho*Wo >= 128); use uegan_instance_norm");
+    UEGAN_CUDA(cudaMemsetAsync(d.in_stats, 0, sizeof(double) * 2 * (size_t)x.n * d.cout, stream));
+  }
+  const int smem_bytes = (patch ? p.w_total_bytes : 0) + p.num_stages * p.stage_bytes + 1024;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  {
+    static bool attr_set = false;
+    if (!attr_set) {
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      attr_set = true;
+    }
+  }
   if (x.dtype == UEGAN_F32) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      attr_set = true;
-    }
-    conv_fprop_kernel<1><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+    if (patch) conv_fprop_kernel<1, 1><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    else conv_fprop_kernel<1, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
   } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      attr_set = true;
-    }
-    conv_fprop_kernel<0><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+    if (patch) conv_fprop_kernel<0, 1><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    else conv_fprop_kernel<0, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
   }
   UEGAN_CUDA(cudaGetLastError());
   return 0;
@@ -410,6 +638,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
   }
   if constexpr (sizeof(T) == 4) {
     out[i] = round_tf32(v);
+  } else if constexpr (std::is_same<T, __half>::value) {
+    out[i] = __float2half_rn(v);
   } else {
     out[i] = __float2bfloat16_rn(v);
   }
@@ -441,10 +671,14 @@ int uegan_pack_conv_weight(const float* w_oihw, void* w_packed, int32_t cout, in
     pack_weight_kernel<float><<<blocks, threads, 0, st>>>(w_oihw, static_cast<float*>(w_packed), cout, cin_total,
                                                           cin_first, cin, cin_stored, k, g.row_pad, g.cout_pad,
                                                           transpose_flip, total);
-  else
+  else if (dtype == UEGAN_BF16)
     pack_weight_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), cout,
                                                                    cin_total, cin_first, cin, cin_stored, k, g.row_pad,
                                                                    g.cout_pad, transpose_flip, total);
+  else
+    pack_weight_kernel<__half><<<blocks, threads, 0, st>>>(w_oihw, static_cast<__half*>(w_packed), cout, cin_total,
+                                                           cin_first, cin, cin_stored, k, g.row_pad, g.cout_pad,
+                                                           transpose_flip, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

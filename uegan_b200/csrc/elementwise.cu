@@ -48,6 +48,33 @@ template <> struct Vec<__nv_bfloat16> {
   }
 };
 
+template <> struct Vec<__half> {
+  static constexpr int N = 8;
+  __device__ static void load(const __half* p, float (&v)[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      v[2 * i] = __low2float(h);
+      v[2 * i + 1] = __high2float(h);
+    }
+  }
+  __device__ static void store(__half* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
 struct TGeom {  // device-side view of a uegan_tensor
   void* data;
   int n, h, w, c, halo;
@@ -153,9 +180,7 @@ __global__ void in_stats_kernel(TGeom s, double* __restrict__ stats, int pix_per
   double sum = 0.0, sq = 0.0;
   for (long long p = p0 + grp; p < p1; p += groups) {
     const int y = (int)(p / s.w), x = (int)(p % s.w);
-    float v;
-    if constexpr (sizeof(T) == 4) v = base[toff(s, n, y, x, c)];
-    else v = __bfloat162float(base[toff(s, n, y, x, c)]);
+    const float v = to_f32<T>(base[toff(s, n, y, x, c)]);
     sum += v;
     sq += (double)v * v;
   }
@@ -266,17 +291,14 @@ __global__ void unpack_nchw_kernel(TGeom s, int c_off, int c_count, float* __res
   const int c = (int)(r % c_count);
   const int n = (int)(r / c_count);
   const T* base = static_cast<const T*>(s.data);
-  float v;
-  if constexpr (sizeof(T) == 4) v = base[toff(s, n, y, x, c_off + c)];
-  else v = __bfloat162float(base[toff(s, n, y, x, c_off + c)]);
-  dst[i] = v;
+  dst[i] = to_f32<T>(base[toff(s, n, y, x, c_off + c)]);
 }
 
 static inline unsigned nblocks(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
 
 static int check_vec(const uegan_tensor& t, const char* who) {
   UEGAN_CHECK(t.data != nullptr, "%s: null tensor", who);
-  UEGAN_CHECK(t.dtype == UEGAN_F32 || t.dtype == UEGAN_BF16, "%s: bad dtype", who);
+  UEGAN_CHECK(dtype_ok(t.dtype), "%s: bad dtype", who);
   UEGAN_CHECK((t.c * dtype_size(t.dtype)) % 16 == 0, "%s: c*elem must be a multiple of 16 B", who);
   return 0;
 }
@@ -301,8 +323,11 @@ int uegan_pack_input(const float* x_nchw, const uegan_tensor* dst, int32_t pad_m
   if (dst->dtype == UEGAN_F32)
     pack_input_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(x_nchw, d, pad_mode == UEGAN_PAD_REFLECT, s0, s1, s2,
                                                                   b0, b1, b2, total);
-  else
+  else if (dst->dtype == UEGAN_BF16)
     pack_input_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(x_nchw, d, pad_mode == UEGAN_PAD_REFLECT, s0,
+                                                                          s1, s2, b0, b1, b2, total);
+  else
+    pack_input_kernel<__half><<<nblocks(total, 256), 256, 0, st>>>(x_nchw, d, pad_mode == UEGAN_PAD_REFLECT, s0,
                                                                           s1, s2, b0, b1, b2, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
@@ -321,14 +346,16 @@ int uegan_halo_fill(const uegan_tensor* t, int32_t pad_mode, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (t->dtype == UEGAN_F32)
     halo_fill_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(g, pad_mode == UEGAN_PAD_REFLECT, total);
-  else
+  else if (t->dtype == UEGAN_BF16)
     halo_fill_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(g, pad_mode == UEGAN_PAD_REFLECT, total);
+  else
+    halo_fill_kernel<__half><<<nblocks(total, 256), 256, 0, st>>>(g, pad_mode == UEGAN_PAD_REFLECT, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
 
-int uegan_instance_norm(const uegan_tensor* src, const uegan_tensor* dst, int32_t dst_c_off, float eps,
-                        double* stats_ws, void* stream) {
+static int instance_norm_impl(const uegan_tensor* src, const uegan_tensor* dst, int32_t dst_c_off, float eps,
+                              double* stats_ws, void* stream, bool compute_stats) {
   UEGAN_CHECK(src && dst && stats_ws, "instance_norm: null pointer");
   if (check_vec(*src, "instance_norm src") || check_vec(*dst, "instance_norm dst")) return -1;
   UEGAN_CHECK(src->dtype == dst->dtype && src->n == dst->n && src->h == dst->h && src->w == dst->w,
@@ -338,28 +365,73 @@ int uegan_instance_norm(const uegan_tensor* src, const uegan_tensor* dst, int32_
   const TGeom s = geom(*src), d = geom(*dst);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nc = s.n * s.c;
-  UEGAN_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * nc, st));
-  // stats
-  int threads = s.c;
-  while (threads < 256) threads += s.c;
   const long long npix = (long long)s.h * s.w;
-  int pix_per_block = 1024;
-  const dim3 grid((unsigned)((npix + pix_per_block - 1) / pix_per_block), (unsigned)s.n);
-  const size_t sh = sizeof(double) * 2 * threads;
+  if (compute_stats) {
+    UEGAN_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * nc, st));
+    int threads = s.c;
+    while (threads < 256) threads += s.c;
+    int pix_per_block = 1024;
+    const dim3 grid((unsigned)((npix + pix_per_block - 1) / pix_per_block), (unsigned)s.n);
+    const size_t sh = sizeof(double) * 2 * threads;
+    if (src->dtype == UEGAN_F32)
+      in_stats_kernel<float><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
+    else if (src->dtype == UEGAN_BF16)
+      in_stats_kernel<__nv_bfloat16><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
+    else
+      in_stats_kernel<__half><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
+  }
   float* mr = reinterpret_cast<float*>(stats_ws + 2 * nc);  // finalised (mean, rstd) live after the raw sums
-  if (src->dtype == UEGAN_F32)
-    in_stats_kernel<float><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
-  else
-    in_stats_kernel<__nv_bfloat16><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
   in_finalize_kernel<<<nblocks(nc, 128), 128, 0, st>>>(stats_ws, mr, nc, 1.0 / (double)npix, eps);
   const int vn = 16 / dtype_size(src->dtype);
   const long long total = (long long)s.n * npix * (s.c / vn);
   if (src->dtype == UEGAN_F32)
     in_apply_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, mr, total);
-  else
+  else if (src->dtype == UEGAN_BF16)
     in_apply_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, mr, total);
+  else
+    in_apply_kernel<__half><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, mr, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
+}
+
+int uegan_instance_norm_stats(const uegan_tensor* src, float eps, double* stats_ws, int32_t sums_ready,
+                              float** mean_rstd_out, void* stream) {
+  UEGAN_CHECK(src && stats_ws && mean_rstd_out, "instance_norm_stats: null pointer");
+  if (check_vec(*src, "instance_norm_stats")) return -1;
+  UEGAN_CHECK(src->c <= 1024, "instance_norm_stats: c too large");
+  const TGeom s = geom(*src);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nc = s.n * s.c;
+  const long long npix = (long long)s.h * s.w;
+  if (!sums_ready) {
+    UEGAN_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * nc, st));
+    int threads = s.c;
+    while (threads < 256) threads += s.c;
+    const int pix_per_block = 1024;
+    const dim3 grid((unsigned)((npix + pix_per_block - 1) / pix_per_block), (unsigned)s.n);
+    const size_t sh = sizeof(double) * 2 * threads;
+    if (src->dtype == UEGAN_F32)
+      in_stats_kernel<float><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
+    else if (src->dtype == UEGAN_BF16)
+      in_stats_kernel<__nv_bfloat16><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
+    else
+      in_stats_kernel<__half><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
+  }
+  float* mr = reinterpret_cast<float*>(stats_ws + 2 * nc);
+  in_finalize_kernel<<<nblocks(nc, 128), 128, 0, st>>>(stats_ws, mr, nc, 1.0 / (double)npix, eps);
+  *mean_rstd_out = mr;
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_instance_norm(const uegan_tensor* src, const uegan_tensor* dst, int32_t dst_c_off, float eps,
+                        double* stats_ws, void* stream) {
+  return instance_norm_impl(src, dst, dst_c_off, eps, stats_ws, stream, true);
+}
+
+int uegan_instance_norm_apply(const uegan_tensor* src, const uegan_tensor* dst, int32_t dst_c_off, float eps,
+                              double* stats_ws, void* stream) {
+  return instance_norm_impl(src, dst, dst_c_off, eps, stats_ws, stream, false);
 }
 
 int uegan_upsample2x(const uegan_tensor* src, const uegan_tensor* dst, int32_t dst_c_off, void* stream) {
@@ -376,8 +448,10 @@ int uegan_upsample2x(const uegan_tensor* src, const uegan_tensor* dst, int32_t d
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (src->dtype == UEGAN_F32)
     upsample2x_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, sy, sx, total);
-  else
+  else if (src->dtype == UEGAN_BF16)
     upsample2x_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, sy, sx, total);
+  else
+    upsample2x_kernel<__half><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, sy, sx, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -394,8 +468,10 @@ int uegan_maxpool2x2(const uegan_tensor* src, const uegan_tensor* dst, void* str
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (src->dtype == UEGAN_F32)
     maxpool2x2_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(s, d, total);
-  else
+  else if (src->dtype == UEGAN_BF16)
     maxpool2x2_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(s, d, total);
+  else
+    maxpool2x2_kernel<__half><<<nblocks(total, 256), 256, 0, st>>>(s, d, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -408,8 +484,10 @@ int uegan_unpack_nchw(const uegan_tensor* src, int32_t c_off, int32_t c_count, f
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (src->dtype == UEGAN_F32)
     unpack_nchw_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(s, c_off, c_count, dst_nchw, total);
-  else
+  else if (src->dtype == UEGAN_BF16)
     unpack_nchw_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(s, c_off, c_count, dst_nchw, total);
+  else
+    unpack_nchw_kernel<__half><<<nblocks(total, 256), 256, 0, st>>>(s, c_off, c_count, dst_nchw, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

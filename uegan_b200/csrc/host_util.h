@@ -24,7 +24,8 @@ const char* get_error();
     if (_e != cudaSuccess) return set_error("%s failed: %s", #expr, cudaGetErrorString(_e));  \
   } while (0)
 
-inline int dtype_size(int dtype) { return dtype == UEGAN_BF16 ? 2 : 4; }
+inline int dtype_size(int dtype) { return dtype == UEGAN_F32 ? 4 : 2; }
+inline bool dtype_ok(int dtype) { return dtype == UEGAN_F32 || dtype == UEGAN_BF16 || dtype == UEGAN_F16; }
 inline int64_t t_wp(const uegan_tensor& t) { return (int64_t)t.w + 2 * t.halo; }
 inline int64_t t_hp(const uegan_tensor& t) { return (int64_t)t.h + 2 * t.halo; }
 inline int64_t t_elems(const uegan_tensor& t) { return (int64_t)t.n * t_hp(t) * t_wp(t) * t.c; }

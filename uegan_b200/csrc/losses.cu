@@ -1,0 +1,318 @@
+// Loss reductions (warp-shuffle, fp64 accumulation) and their gradients.
+//   relativistic average GAN loss, 5 scales     losses.py:348-377 (rahinge / rals), summed as in :393-409
+//   InstanceNorm + MSE per VGG tap              losses.py:18, 30-34
+//   multi-scale L1 / L2 / smooth-L1             losses.py:202-231 (AvgPool2d(2) pyramid, weights 1, 1/2, 1/4)
+#include "common.cuh"
+#include "host_util.h"
+
+namespace uegan {
+
+constexpr int kMaxScales = 8;
+struct GanArgs {
+  const float* real[kMaxScales];
+  const float* fake[kMaxScales];
+  float* d_real[kMaxScales];
+  float* d_fake[kMaxScales];
+  long long count[kMaxScales];
+  int nscales;
+  int mode;    // 0 rahinge, 1 rals
+  int for_d;   // 1: discriminator side, 0: generator side
+};
+
+__device__ __forceinline__ void block_atomic_add(double v, double* dst) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(dst, v);
+}
+
+// ws[2*i] = sum real_i, ws[2*i+1] = sum fake_i
+__global__ void gan_sums_kernel(GanArgs a, double* __restrict__ ws) {
+  const int i = blockIdx.y;
+  double sr = 0.0, sf = 0.0;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.count[i]; j += (long long)gridDim.x * blockDim.x) {
+    sr += a.real[i][j];
+    sf += a.fake[i][j];
+  }
+  block_atomic_add(sr, ws + 2 * i);
+  block_atomic_add(sf, ws + 2 * i + 1);
+}
+
+// per scale: ws2[4*i+0] = sum term(real), [1] = sum term(fake), [2] = sum dterm/dx(real), [3] = sum dterm/dx(fake)
+//  rahinge D: relu(1 - (r - mf)) , relu(1 + (f - mr));  G: relu(1 + (r - mf)), relu(1 - (f - mr))
+//  rals    D: ((r - mf) - 1)^2   , ((f - mr) + 1)^2  ;  G: ((r - mf) + 1)^2 , ((f - mr) - 1)^2
+__device__ __forceinline__ void gan_terms(int mode, float sgn, float x, float& term, float& dterm) {
+  // term(x) with x = r - mean(f) (or f - mean(r)); sgn = +1 -> "push x below -1" form relu(1 + x) / (x + 1)^2,
+  // sgn = -1 -> relu(1 - x) / (x - 1)^2
+  const float z = 1.f + sgn * x;
+  if (mode == 0) {
+    term = fmaxf(z, 0.f);
+    dterm = z > 0.f ? sgn : 0.f;
+  } else {
+    term = z * z;           // (x + sgn)^2 == (1 + sgn*x)^2
+    dterm = 2.f * z * sgn;
+  }
+}
+__global__ void gan_terms_kernel(GanArgs a, const double* __restrict__ ws, double* __restrict__ ws2) {
+  const int i = blockIdx.y;
+  const double inv = 1.0 / (double)a.count[i];
+  const float mr = (float)(ws[2 * i] * inv), mf = (float)(ws[2 * i + 1] * inv);
+  const float sr = a.for_d ? -1.f : 1.f;  // sign for the real-side term
+  const float sf = -sr;
+  double t0 = 0.0, t1 = 0.0, g0 = 0.0, g1 = 0.0;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.count[i]; j += (long long)gridDim.x * blockDim.x) {
+    float t, g;
+    gan_terms(a.mode, sr, a.real[i][j] - mf, t, g);
+    t0 += t; g0 += g;
+    gan_terms(a.mode, sf, a.fake[i][j] - mr, t, g);
+    t1 += t; g1 += g;
+  }
+  block_atomic_add(t0, ws2 + 4 * i);
+  block_atomic_add(t1, ws2 + 4 * i + 1);
+  block_atomic_add(g0, ws2 + 4 * i + 2);
+  block_atomic_add(g1, ws2 + 4 * i + 3);
+}
+__global__ void gan_finalize_kernel(GanArgs a, const double* __restrict__ ws2, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double l = 0.0;
+    for (int i = 0; i < a.nscales; ++i) l += 0.5 * (ws2[4 * i] + ws2[4 * i + 1]) / (double)a.count[i];
+    loss[0] = (float)l;
+  }
+}
+// d loss / d real_j = gscale * 0.5/n * ( dterm_r(j) - mean_k dterm_f(k) ),  same for fake with roles swapped
+// (the second part is the path through the batch-global mean, losses.py:351-353)
+__global__ void gan_backward_kernel(GanArgs a, const double* __restrict__ ws, const double* __restrict__ ws2,
+                                    const float* __restrict__ gscale_ptr, float gscale_host) {
+  const int i = blockIdx.y;
+  const double inv = 1.0 / (double)a.count[i];
+  const float mr = (float)(ws[2 * i] * inv), mf = (float)(ws[2 * i + 1] * inv);
+  const float sr = a.for_d ? -1.f : 1.f, sf = -sr;
+  const float gs = (gscale_ptr ? gscale_ptr[0] : 1.f) * gscale_host * 0.5f * (float)inv;
+  const float mean_gr = (float)(ws2[4 * i + 2] * inv), mean_gf = (float)(ws2[4 * i + 3] * inv);
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.count[i]; j += (long long)gridDim.x * blockDim.x) {
+    float t, g;
+    if (a.d_real[i]) {
+      gan_terms(a.mode, sr, a.real[i][j] - mf, t, g);
+      a.d_real[i][j] += gs * (g - mean_gf);
+    }
+    if (a.d_fake[i]) {
+      gan_terms(a.mode, sf, a.fake[i][j] - mr, t, g);
+      a.d_fake[i][j] += gs * (g - mean_gr);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// InstanceNorm + MSE of one VGG tap.  mrx / mry: per-(n,c) (mean, rstd) float pairs.
+// ------------------------------------------------------------------------------------------
+struct TapGeom {
+  const void* x;
+  const void* y;
+  int n, h, w, c, halo;
+  long long wp, hp;
+  int dtype;
+};
+__device__ __forceinline__ long long tap_off(const TapGeom& g, int n, int yy, int xx, int c) {
+  return (((long long)n * g.hp + (yy + g.halo)) * g.wp + (xx + g.halo)) * g.c + c;
+}
+__device__ __forceinline__ float tap_load(const void* p, long long o, int dtype) {
+  if (dtype == UEGAN_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[o]);
+  if (dtype == UEGAN_F16) return __half2float(static_cast<const __half*>(p)[o]);
+  return static_cast<const float*>(p)[o];
+}
+// accum[0] += sum ((x-mx)*rx - (y-my)*ry)^2
+__global__ void in_mse_kernel(TapGeom g, const float* __restrict__ mrx, const float* __restrict__ mry,
+                              double* __restrict__ accum) {
+  const long long total = (long long)g.n * g.h * g.w * g.c;
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % g.c);
+    long long pix = i / g.c;
+    const int xx = (int)(pix % g.w);
+    pix /= g.w;
+    const int yy = (int)(pix % g.h);
+    const int n = (int)(pix / g.h);
+    const long long o = tap_off(g, n, yy, xx, c);
+    const long long si = ((long long)n * g.c + c) * 2;
+    const float a = (tap_load(g.x, o, g.dtype) - mrx[si]) * mrx[si + 1];
+    const float b = (tap_load(g.y, o, g.dtype) - mry[si]) * mry[si + 1];
+    const float d = a - b;
+    s += (double)d * d;
+  }
+  block_atomic_add(s, accum);
+}
+// loss += weight * accum / numel ; accum reset
+__global__ void scalar_axpy_kernel(double* accum, double scale, float* loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    loss[0] += (float)(accum[0] * scale);
+    accum[0] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-scale reconstruction loss on fp32 NCHW images; one thread per 4x4 pixel block of one (n, c) plane
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rec_term(float d, int type) {
+  if (type == 0) return fabsf(d);
+  if (type == 2) return d * d;
+  const float a = fabsf(d);  // smooth-L1, beta = 1
+  return a < 1.f ? 0.5f * d * d : a - 0.5f;
+}
+__device__ __forceinline__ float rec_dterm(float d, int type) {
+  if (type == 0) return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+  if (type == 2) return 2.f * d;
+  return fabsf(d) < 1.f ? d : (d > 0.f ? 1.f : -1.f);
+}
+// accum[0..2] = sum of term at scale 0, 1, 2.  If grad != NULL also writes d loss / d pred (needs w0..w2 = weight_i / N_i
+// already multiplied by the upstream scale).
+__global__ void msrec_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int planes, int h, int w,
+                             int type, int scales, double* __restrict__ accum, float* __restrict__ grad, float w0,
+                             float w1, float w2) {
+  const int bw = w >> 2, bh = h >> 2;
+  const long long total = (long long)planes * bh * bw;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int bx = (int)(i % bw);
+    const int by = (int)((i / bw) % bh);
+    const long long pl = i / ((long long)bw * bh);
+    const long long base = pl * h * w + (long long)(by * 4) * w + bx * 4;
+    float d[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float4 p4 = *reinterpret_cast<const float4*>(pred + base + (long long)r * w);
+      const float4 g4 = *reinterpret_cast<const float4*>(gt + base + (long long)r * w);
+      d[r][0] = p4.x - g4.x; d[r][1] = p4.y - g4.y; d[r][2] = p4.z - g4.z; d[r][3] = p4.w - g4.w;
+    }
+    float d1[2][2], d2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        d1[r][c] = 0.25f * (d[2 * r][2 * c] + d[2 * r][2 * c + 1] + d[2 * r + 1][2 * c] + d[2 * r + 1][2 * c + 1]);
+        d2 += 0.25f * d1[r][c];
+      }
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) t0 += rec_term(d[r][c], type);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) t1 += rec_term(d1[r][c], type);
+    s0 += t0;
+    if (scales > 1) s1 += t1;
+    if (scales > 2) s2 += rec_term(d2, type);
+    if (grad) {
+      const float g2 = scales > 2 ? w2 * rec_dterm(d2, type) * (1.f / 16.f) : 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float g = w0 * rec_dterm(d[r][c], type) + g2;
+          if (scales > 1) g += w1 * rec_dterm(d1[r >> 1][c >> 1], type) * 0.25f;
+          o[c] = g;
+        }
+        *reinterpret_cast<float4*>(grad + base + (long long)r * w) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  block_atomic_add(s0, accum);
+  block_atomic_add(s1, accum + 1);
+  block_atomic_add(s2, accum + 2);
+}
+__global__ void msrec_finalize_kernel(double* accum, double c0, double c1, double c2, float* loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    loss[0] = (float)(accum[0] * c0 + accum[1] * c1 + accum[2] * c2);
+  }
+}
+
+}  // namespace uegan
+
+using namespace uegan;
+
+extern "C" {
+
+static int fill_gan_args(GanArgs& a, int nscales, const float* const* real, const float* const* fake,
+                         const int64_t* counts, int mode, int for_d) {
+  UEGAN_CHECK(nscales >= 1 && nscales <= kMaxScales, "gan loss: bad number of scales %d", nscales);
+  UEGAN_CHECK(mode == 0 || mode == 1, "gan loss: mode must be 0 (rahinge) or 1 (rals)");
+  memset(&a, 0, sizeof(a));
+  a.nscales = nscales; a.mode = mode; a.for_d = for_d;
+  for (int i = 0; i < nscales; ++i) {
+    UEGAN_CHECK(real[i] && fake[i] && counts[i] > 0, "gan loss: null / empty prediction map %d", i);
+    a.real[i] = real[i]; a.fake[i] = fake[i]; a.count[i] = counts[i];
+  }
+  return 0;
+}
+
+int uegan_gan_loss_fwd(int32_t mode, int32_t for_discriminator, int32_t nscales, const float* const* real,
+                       const float* const* fake, const int64_t* counts, double* ws, float* loss_out, void* stream) {
+  GanArgs a;
+  if (fill_gan_args(a, nscales, real, fake, counts, mode, for_discriminator)) return -1;
+  UEGAN_CHECK(ws && loss_out, "gan loss: null workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UEGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 6 * kMaxScales, st));
+  dim3 grid(64, nscales);
+  gan_sums_kernel<<<grid, 256, 0, st>>>(a, ws);
+  gan_terms_kernel<<<grid, 256, 0, st>>>(a, ws, ws + 2 * kMaxScales);
+  gan_finalize_kernel<<<1, 32, 0, st>>>(a, ws + 2 * kMaxScales, loss_out);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_gan_loss_bwd(int32_t mode, int32_t for_discriminator, int32_t nscales, const float* const* real,
+                       const float* const* fake, const int64_t* counts, const double* ws, float* const* d_real,
+                       float* const* d_fake, const float* gscale_dev, float gscale_host, void* stream) {
+  GanArgs a;
+  if (fill_gan_args(a, nscales, real, fake, counts, mode, for_discriminator)) return -1;
+  for (int i = 0; i < nscales; ++i) {
+    a.d_real[i] = d_real ? d_real[i] : nullptr;
+    a.d_fake[i] = d_fake ? d_fake[i] : nullptr;
+  }
+  dim3 grid(64, nscales);
+  gan_backward_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, ws, ws + 2 * kMaxScales, gscale_dev,
+                                                                          gscale_host);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_in_mse_fwd(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
+                     float weight, double* accum, float* loss_inout, void* stream) {
+  UEGAN_CHECK(x && y && mean_rstd_x && mean_rstd_y && accum && loss_inout, "in_mse: null pointer");
+  UEGAN_CHECK(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c && x->halo == y->halo &&
+                  x->dtype == y->dtype,
+              "in_mse: x / y mismatch");
+  TapGeom g;
+  g.x = x->data; g.y = y->data; g.n = x->n; g.h = x->h; g.w = x->w; g.c = x->c; g.halo = x->halo;
+  g.wp = t_wp(*x); g.hp = t_hp(*x); g.dtype = x->dtype;
+  const long long total = (long long)g.n * g.h * g.w * g.c;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  in_mse_kernel<<<blocks, 256, 0, st>>>(g, mean_rstd_x, mean_rstd_y, accum);
+  scalar_axpy_kernel<<<1, 32, 0, st>>>(accum, (double)weight / (double)total, loss_inout);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_msrec_loss(const float* pred_nchw, const float* gt_nchw, int32_t n, int32_t c, int32_t h, int32_t w,
+                     int32_t type, int32_t scales, double* accum, float* loss_out, float* grad_nchw,
+                     float grad_scale, void* stream) {
+  UEGAN_CHECK(pred_nchw && gt_nchw && accum && loss_out, "msrec: null pointer");
+  UEGAN_CHECK(h % 4 == 0 && w % 4 == 0, "msrec: H, W must be multiples of 4 (got %dx%d)", h, w);
+  UEGAN_CHECK(scales >= 1 && scales <= 3 && type >= 0 && type <= 2, "msrec: bad scales/type");
+  const double n0 = (double)n * c * h * w, n1 = n0 / 4, n2 = n0 / 16;
+  const double c0 = 1.0 / n0, c1 = scales > 1 ? 0.5 / n1 : 0.0, c2 = scales > 2 ? 0.25 / n2 : 0.0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UEGAN_CUDA(cudaMemsetAsync(accum, 0, sizeof(double) * 3, st));
+  const long long total = (long long)n * c * (h / 4) * (w / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  msrec_kernel<<<blocks, 256, 0, st>>>(pred_nchw, gt_nchw, n * c, h, w, type, scales, accum, grad_nchw,
+                                      (float)(c0 * grad_scale), (float)(c1 * grad_scale), (float)(c2 * grad_scale));
+  msrec_finalize_kernel<<<1, 32, 0, st>>>(accum, c0, c1, c2, loss_out);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -2,4 +2,6 @@
 #include "host_util.cu"
 #include "conv_fprop.cu"
 #include "elementwise.cu"
+#include "spectral.cu"
+#include "losses.cu"
 #include "probe.cu"

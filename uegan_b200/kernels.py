@@ -9,7 +9,7 @@ import torch
 
 from . import _lib as L
 
-_TORCH_DTYPE = {L.F32: torch.float32, L.BF16: torch.bfloat16}
+_TORCH_DTYPE = {L.F32: torch.float32, L.BF16: torch.bfloat16, L.F16: torch.float16}
 
 
 def _stream() -> int:
@@ -36,7 +36,7 @@ class NHWC:
     SLACK = 512
 
     def __init__(self, n, h, w, c, halo=0, dtype=L.F32, device="cuda", zero=False):
-        es = 2 if dtype == L.BF16 else 4
+        es = 4 if dtype == L.F32 else 2
         assert (c * es) % 16 == 0, "channel vector must be a multiple of 16 bytes"
         self.n, self.h, self.w, self.c, self.halo, self.dtype = n, h, w, c, halo, dtype
         elems = n * (h + 2 * halo) * (w + 2 * halo) * c
@@ -85,7 +85,7 @@ def packed_weight(weight: torch.Tensor, cin_stored: int, dtype: int, cin_first: 
 def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, pad: int, y: Optional[NHWC] = None,
                y_c_off: int = 0, bias: Optional[torch.Tensor] = None, alpha: Optional[torch.Tensor] = None,
                act: int = L.ACT_NONE, mul: Optional[NHWC] = None, out_nchw: Optional[torch.Tensor] = None,
-               residual_nchw: Optional[torch.Tensor] = None):
+               residual_nchw: Optional[torch.Tensor] = None, in_stats: Optional[torch.Tensor] = None):
     lib = L.load()
     d = L.ConvDesc()
     d.x = x.ct
@@ -98,6 +98,7 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
     d.mul = C.pointer(mul.ct) if mul is not None else None
     d.out_nchw = out_nchw.data_ptr() if out_nchw is not None else None
     d.residual_nchw = residual_nchw.data_ptr() if residual_nchw is not None else None
+    d.in_stats = in_stats.data_ptr() if in_stats is not None else None
     ev = _Counters.conv_events
     if ev is not None:
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -107,7 +108,7 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
         s1.record()
         ho = (x.h + 2 * pad - k) // stride + 1
         wo = (x.w + 2 * pad - k) // stride + 1
-        cin = 3 if x.c * (2 if x.dtype == L.BF16 else 4) == 16 else x.c
+        cin = 3 if x.c * (4 if x.dtype == L.F32 else 2) == 16 else x.c
         ev.append((s0, s1, 2.0 * x.n * ho * wo * cout * k * k * cin, x, cout, k, stride))
     _count(1)
 
@@ -132,6 +133,29 @@ def instance_norm(src: NHWC, dst: NHWC, dst_c_off: int, stats_ws: torch.Tensor, 
     _count(3)
 
 
+def instance_norm_apply(src: NHWC, dst: NHWC, dst_c_off: int, stats_ws: torch.Tensor, eps: float = 1e-5):
+    """InstanceNorm whose sums were accumulated by the producing conv's epilogue (conv_fprop(in_stats=...))."""
+    assert stats_ws.dtype == torch.float64 and stats_ws.numel() >= 3 * src.n * src.c
+    L.check(L.load().uegan_instance_norm_apply(src.ref(), dst.ref(), dst_c_off, eps, stats_ws.data_ptr(), _stream()),
+            "instance_norm_apply")
+    _count(2)
+
+
+def fused_stats_ok(ho: int, wo: int) -> bool:
+    """conv epilogue statistics need every 128-pixel tile inside one image."""
+    return ho * wo >= 128 and wo >= 8
+
+
+def spectral_sigma(w: torch.Tensor, u: torch.Tensor, v: torch.Tensor, train: bool, sigma_out: torch.Tensor,
+                   ws: torch.Tensor):
+    rows = w.shape[0]
+    cols = w.numel() // rows
+    assert ws.numel() >= rows + cols + 8 and sigma_out.numel() >= 2
+    L.check(L.load().uegan_spectral_sigma(w.data_ptr(), u.data_ptr(), v.data_ptr(), rows, cols, int(train),
+                                          sigma_out.data_ptr(), ws.data_ptr(), _stream()), "spectral_sigma")
+    _count(6 if train else 2)
+
+
 def upsample2x(src: NHWC, dst: NHWC, dst_c_off: int = 0):
     L.check(L.load().uegan_upsample2x(src.ref(), dst.ref(), dst_c_off, _stream()), "upsample2x")
     _count(1)
@@ -151,3 +175,68 @@ def unpack_nchw(src: NHWC, c_off: int, c_count: int) -> torch.Tensor:
 def device_error() -> int:
     """Synchronises and returns the watchdog word (0 = no bounded wait expired)."""
     return L.load().uegan_device_error()
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+GAN_MODES = {"rahinge": 0, "rals": 1}
+REC_TYPES = {"l1": 0, "smoothl1": 1, "l2": 2}
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def gan_loss_fwd(mode: int, for_d: bool, real, fake, ws: torch.Tensor, loss_out: torch.Tensor):
+    """real / fake: lists of contiguous fp32 CUDA prediction maps.  ws: >= 48 float64 (kept for gan_loss_bwd)."""
+    assert len(real) == len(fake) and ws.dtype == torch.float64 and ws.numel() >= 48
+    for t in list(real) + list(fake):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    counts = (C.c_int64 * len(real))(*[t.numel() for t in real])
+    for r, f in zip(real, fake):
+        assert r.numel() == f.numel()
+    L.check(L.load().uegan_gan_loss_fwd(mode, int(for_d), len(real), _ptr_array(real), _ptr_array(fake), counts,
+                                        ws.data_ptr(), loss_out.data_ptr(), _stream()), "gan_loss_fwd")
+    _count(3)
+
+
+def gan_loss_bwd(mode: int, for_d: bool, real, fake, ws: torch.Tensor, d_real, d_fake, gscale_dev=None,
+                 gscale_host: float = 1.0):
+    counts = (C.c_int64 * len(real))(*[t.numel() for t in real])
+    L.check(L.load().uegan_gan_loss_bwd(mode, int(for_d), len(real), _ptr_array(real), _ptr_array(fake), counts,
+                                        ws.data_ptr(), _ptr_array(d_real) if d_real is not None else None,
+                                        _ptr_array(d_fake) if d_fake is not None else None,
+                                        gscale_dev.data_ptr() if gscale_dev is not None else None, float(gscale_host),
+                                        _stream()), "gan_loss_bwd")
+    _count(1)
+
+
+def instance_norm_stats(src: NHWC, stats_ws: torch.Tensor, sums_ready: bool = False, eps: float = 1e-5) -> int:
+    """Returns the device address of the per-(n,c) (mean, rstd) float pairs inside stats_ws."""
+    assert stats_ws.dtype == torch.float64 and stats_ws.numel() >= 3 * src.n * src.c
+    out = C.c_void_p()
+    L.check(L.load().uegan_instance_norm_stats(src.ref(), eps, stats_ws.data_ptr(), int(sums_ready), C.byref(out),
+                                               _stream()), "instance_norm_stats")
+    _count(1 if sums_ready else 2)
+    return out.value
+
+
+def in_mse_fwd(x: NHWC, y: NHWC, mr_x: int, mr_y: int, weight: float, accum: torch.Tensor, loss: torch.Tensor):
+    L.check(L.load().uegan_in_mse_fwd(x.ref(), y.ref(), mr_x, mr_y, float(weight), accum.data_ptr(), loss.data_ptr(),
+                                      _stream()), "in_mse_fwd")
+    _count(2)
+
+
+def msrec_loss(pred: torch.Tensor, gt: torch.Tensor, rec_type: int, scales: int, accum: torch.Tensor,
+               loss: torch.Tensor, grad: Optional[torch.Tensor] = None, grad_scale: float = 1.0):
+    assert pred.shape == gt.shape and pred.is_cuda and pred.dtype == torch.float32
+    assert pred.is_contiguous() and gt.is_contiguous()
+    n, c, h, w = pred.shape
+    L.check(L.load().uegan_msrec_loss(pred.data_ptr(), gt.data_ptr(), n, c, h, w, rec_type, scales, accum.data_ptr(),
+                                      loss.data_ptr(), grad.data_ptr() if grad is not None else None,
+                                      float(grad_scale), _stream()), "msrec_loss")
+    _count(2)

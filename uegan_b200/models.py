@@ -195,8 +195,12 @@ class Generator(nn.Module):
             # (n, c) and cancel in the InstanceNorm that follows (models.py:230-237; SURVEY.md 8a rewrite 1).
             fuse = ga.fuse[0]
             wp = self._wcache.get(name, fuse.weight, lambda: K.packed_weight(fuse.weight, src.c, L.F32, 0, ch))
-            K.conv_fprop(src, wp, ch, 1, 1, 0, z)
-            K.instance_norm(z, dst, off, P["stats"])
+            if K.fused_stats_ok(src.h, src.w):  # statistics ride in the conv epilogue
+                K.conv_fprop(src, wp, ch, 1, 1, 0, z, in_stats=P["stats"])
+                K.instance_norm_apply(z, dst, off, P["stats"])
+            else:
+                K.conv_fprop(src, wp, ch, 1, 1, 0, z)
+                K.instance_norm(z, dst, off, P["stats"])
 
         gam("ga5", self.ga5, P["x5"], 16 * d, P["z5"], P["x5n"], 0)
         stages = [("upsample1", self.upsample1, "ga4", self.ga4, "dec1", self.dec1, "x5n", "x4", "u1", "cat1", "z4", "y1", 8 * d),
@@ -220,3 +224,104 @@ class Generator(nn.Module):
         if keep is not None:
             keep.update(P)
         return out
+
+
+class Discriminator(nn.Module):
+    """Multi-scale PatchGAN discriminator (reference: models.py:104-182): five spectrally-normalised strided convs,
+    each followed by a Cout=1 prediction head; forward returns the list of five (B,1,H/2^k,W/2^k) maps."""
+
+    _SPEC = [(7, 3), (7, 3), (7, 3), (5, 2), (5, 2)]  # (kernel, pad) of d{k} and d{k}_pred, models.py:109-126
+
+    def __init__(self, conv_dim, norm_fun, act_fun, use_sn, adv_loss_type):
+        super().__init__()
+        _check_norm(norm_fun)
+        if adv_loss_type in ("ls", "rals"):
+            self._head_act = L.ACT_SIGMOID
+        elif adv_loss_type in ("hinge", "rahinge"):
+            self._head_act = L.ACT_TANH
+        else:
+            raise NotImplementedError("Adversarial loss [{}] is not found".format(adv_loss_type))
+        self.conv_dim, self.act_fun, self.use_sn = conv_dim, act_fun, bool(use_sn)
+        self._act = _ACTS.get(act_fun)
+        d = conv_dim
+        chans = [3, d, 2 * d, 4 * d, 8 * d, 16 * d]
+        for i, (k, _) in enumerate(self._SPEC, start=1):
+            conv = nn.Conv2d(chans[i - 1], chans[i], k, stride=2, padding=0, bias=True)
+            if use_sn:
+                conv = nn.utils.spectral_norm(conv)  # container semantics only: weight_orig / weight_u / weight_v
+            body = nn.Sequential(nn.ReflectionPad2d((k - 1) // 2), conv, Identity(), _act_module(act_fun))
+            setattr(self, f"d{i}", nn.Sequential(body))
+            head_act = nn.Sigmoid() if self._head_act == L.ACT_SIGMOID else nn.Tanh()
+            head = nn.Sequential(nn.ReflectionPad2d((k - 1) // 2), nn.Conv2d(chans[i], 1, k, bias=False), head_act)
+            setattr(self, f"d{i}_pred", nn.Sequential(head))
+        self._plans = {}
+        self._wcache = _ParamCache()
+
+    def _conv(self, i):
+        return getattr(self, f"d{i}")[0][1]
+
+    def _head(self, i):
+        return getattr(self, f"d{i}_pred")[0][1]
+
+    def _weight(self, i):
+        c = self._conv(i)
+        return c.weight_orig if self.use_sn else c.weight
+
+    def _plan(self, b, h, w, device):
+        key = (b, h, w, str(device))
+        pl = self._plans.get(key)
+        if pl is None:
+            d = self.conv_dim
+            chans = [d, 2 * d, 4 * d, 8 * d, 16 * d]
+            pl = dict(x0=K.NHWC(b, h, w, 4, 3, L.F32, device, zero=True), ds=[], sig=[], ws=[])
+            hh, ww = h, w
+            for i in range(5):
+                hh, ww = (hh + 1) // 2, (ww + 1) // 2
+                halo = 3 if i < 3 else 2
+                pl["ds"].append(K.NHWC(b, hh, ww, chans[i], halo, L.F32, device))
+                wgt = self._weight(i + 1)
+                pl["sig"].append(torch.ones(2, dtype=torch.float32, device=device))
+                pl["ws"].append(torch.empty(wgt.shape[0] + wgt.numel() // wgt.shape[0] + 8, dtype=torch.float32,
+                                            device=device))
+            self._plans[key] = pl
+        return pl
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise L.UeganError("uegan_b200.models.Discriminator runs on CUDA (sm_100a) only; no CPU fallback")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import discriminator_apply
+            return discriminator_apply(self, x)
+        return self.forward_native(x)
+
+    @torch.no_grad()
+    def forward_native(self, x, keep=None):
+        assert x.dim() == 4 and x.shape[1] == 3, "expected (B,3,H,W)"
+        b, _, h, w = x.shape
+        if min(h, w) < 96:
+            raise ValueError("Discriminator needs H, W >= 96 (ReflectionPad2d(2) on the 1/32-scale map, models.py:125)")
+        if self._act is None:
+            raise NotImplementedError("activation function [%s] has no sm_100a epilogue" % self.act_fun)
+        x = x.contiguous().float()
+        P = self._plan(b, h, w, x.device)
+        K.pack_input(x, P["x0"], L.PAD_REFLECT)
+        src, preds = P["x0"], []
+        for i, (k, pad) in enumerate(self._SPEC, start=1):
+            conv, head, wgt = self._conv(i), self._head(i), self._weight(i)
+            alpha = None
+            if self.use_sn:
+                # one power iteration per train-mode forward, in place on the weight_u / weight_v buffers
+                K.spectral_sigma(wgt, conv.weight_u, conv.weight_v, self.training, P["sig"][i - 1], P["ws"][i - 1])
+                alpha = P["sig"][i - 1][1:2]
+            dst = P["ds"][i - 1]
+            wp = self._wcache.get(f"d{i}", wgt, lambda: K.packed_weight(wgt, src.c, L.F32))
+            K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, self._act)
+            K.halo_fill(dst)
+            pred = torch.empty(b, 1, dst.h, dst.w, dtype=torch.float32, device=x.device)
+            hp = self._wcache.get(f"p{i}", head.weight, lambda: K.packed_weight(head.weight, dst.c, L.F32))
+            K.conv_fprop(dst, hp, 1, k, 1, pad, None, 0, None, None, self._head_act, None, pred)
+            preds.append(pred)
+            src = dst
+        if keep is not None:
+            keep.update(P)
+        return preds
