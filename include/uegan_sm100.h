@@ -62,6 +62,12 @@ typedef struct uegan_conv_desc {
   const uegan_tensor* mul;     /* optional: y *= mul[n,ho,wo,co] after the activation (y4.mul(x1), models.py:70) */
   float* out_nchw;             /* optional planar fp32 output, see above */
   const float* residual_nchw;  /* optional, with out_nchw */
+  int32_t y_mul;               /* 0/1: dense output.  2: output (a, b) is written at (y_off_h + 2a, y_off_w + 2b) of y
+                                  (one parity class of the dgrad of a stride-2 conv per launch) */
+  int32_t y_off_h, y_off_w;
+  const uegan_tensor* mask;    /* optional: y *= act'(mask[n,ho,wo,co]) (LRELU: 1 / 0.2, RELU: 1 / 0 by the sign of the
+                                  forward activation) -- fuses the activation backward into a dgrad launch */
+  int32_t mask_act;
   double* in_stats;            /* optional [n][cout][2]: the epilogue accumulates sum / sum of squares of the stored
                                   outputs per (n, c) (zeroed by the call); consumed by uegan_instance_norm_apply.
                                   Needs Ho*Wo >= 128 (tiles within one image). */
@@ -82,6 +88,14 @@ size_t uegan_packed_weight_bytes(int32_t cout, int32_t cin_stored, int32_t k, in
 int uegan_pack_conv_weight(const float* w_oihw, void* w_packed, int32_t cout, int32_t cin_total, int32_t cin_first,
                            int32_t cin, int32_t cin_stored, int32_t k, int32_t dtype, int32_t transpose_flip,
                            void* stream);
+
+/* dgrad operand of a conv with weight w (cout_orig x cin_total x k_orig x k_orig, stride 1 or 2): the data gradient
+ * is itself a stride-1 valid convolution of the zero-haloed output gradient dz (cout_stored channels per pixel) with
+ * this operand; for stride 2 one operand per parity class (pi, pj) of the input position, kernel size ceil(k/2).
+ * Packed size: uegan_packed_weight_bytes(cin, cout_stored, ceil(k_orig/stride), dtype). */
+int uegan_pack_conv_weight_dgrad(const float* w_oihw, void* w_packed, int32_t cout_orig, int32_t cin_total,
+                                 int32_t cin_first, int32_t cin, int32_t cout_stored, int32_t k_orig, int32_t stride,
+                                 int32_t pi, int32_t pj, int32_t dtype, void* stream);
 
 int uegan_conv2d_fprop(const uegan_conv_desc* desc, void* stream);
 
@@ -138,6 +152,41 @@ int uegan_msrec_loss(const float* pred_nchw, const float* gt_nchw, int32_t n, in
  * Returns the device pointer of the (mean, rstd) pairs in *mean_rstd_out. */
 int uegan_instance_norm_stats(const uegan_tensor* src, float eps, double* stats_ws, int32_t sums_ready,
                               float** mean_rstd_out, void* stream);
+
+/* ---- backward pass ---------------------------------------------------------------------------------------------
+ * Weight gradient (autograd of nn.Conv2d, `aten::convolution_backward`): dw_oihw[o][cin_first + c][r][s] += scale *
+ * (alpha ? *alpha : 1) * sum_pix dz[pix][o] * xpad[pix*stride + (r,s)][c].  fp32 NHWC tensors (kind::tf32, MN-major
+ * operands), dz must store a multiple of 32 channels, x 4 or a multiple of 32.  The caller zeroes dw_oihw. */
+int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz, int32_t cout, int32_t cin, int32_t cin_total,
+                       int32_t cin_first, int32_t k, int32_t stride, int32_t pad, float* dw_oihw,
+                       const float* alpha_dev, float scale, void* stream);
+/* Gradient of the planar heads into a zero-haloed NHWC tensor: mode 0 tanh (models.py:178), 1 sigmoid, 2
+ * clamp(tanh(z) + x, -1, 1) with out_nchw = tanh(z) (models.py:35,72). */
+int uegan_head_bwd(const float* dout_nchw, const float* out_nchw, const float* x_nchw, int32_t channels, int32_t mode,
+                   const uegan_tensor* dz, void* stream);
+/* dst[.., dst_c_off + c] = act'(mask) * mul * ( fold(src_a) + add_b + add_c ) for c < channels; halo of dst := 0.
+ * src_a has extent (h + 2*pad_a, w + 2*pad_a): the gradient w.r.t. a PADDED conv input; reflection padding folds
+ * its border back (adjoint of nn.ReflectionPad2d), zero padding crops.  Any of src_a / add_b / add_c may be NULL. */
+int uegan_grad_combine(const uegan_tensor* dst, int32_t dst_c_off, int32_t channels, const uegan_tensor* src_a,
+                       int32_t a_c_off, int32_t pad_a, int32_t pad_mode_a, const uegan_tensor* add_b, int32_t b_c_off,
+                       const uegan_tensor* add_c, int32_t c_c_off, const uegan_tensor* mask, int32_t mask_c_off,
+                       int32_t act, const uegan_tensor* mul, int32_t mul_c_off, void* stream);
+/* out[c] = sum over n, h, w of src[.., c_off + c]  (bias gradient). */
+int uegan_channel_sum(const uegan_tensor* src, int32_t c_off, int32_t channels, float* out, void* stream);
+/* InstanceNorm backward: dz = rstd * (dout - mean(dout) - xhat * mean(dout * xhat)); ws: 2*n*c doubles. */
+int uegan_instance_norm_bwd(const uegan_tensor* dout, int32_t d_c_off, const uegan_tensor* z, const float* mean_rstd,
+                            const uegan_tensor* dz, double* ws, void* stream);
+/* Adjoint of uegan_upsample2x: dsrc = up^T(dout[.., d_c_off : d_c_off + dsrc.c]). */
+int uegan_upsample2x_bwd(const uegan_tensor* dout, int32_t d_c_off, const uegan_tensor* dsrc, void* stream);
+/* MaxPool2d(2,2) backward fused with the ReLU mask of the pooled activation (fp16 activations, bf16 gradients). */
+int uegan_maxpool2x2_bwd(const uegan_tensor* src, const uegan_tensor* dpool, const uegan_tensor* dsrc, void* stream);
+/* Backward of one PerceptualLoss term w.r.t. the fp16 feature map x (+ optional gradient from deeper layers, then
+ * the tap's own ReLU mask): dx (bf16, zero halo).  Upstream scale = weight * (gscale_dev ? *gscale_dev : 1). */
+int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
+                     float weight, const float* gscale_dev, const uegan_tensor* deep, const uegan_tensor* dx, double* ws,
+                     void* stream);
+/* Gradient of uegan_pack_input: NHWC (first 3 channels) -> NCHW fp32 times scale_host[c]. */
+int uegan_unpack_input_grad(const uegan_tensor* dx, const float* scale_host, float* dst_nchw, void* stream);
 
 /* Hardware probe used by tests/DESIGN.md: runs a 128xNx(32*kchunks) tf32 GEMM whose A operand is read from a
  * shared-memory window shifted by `row_shift` 128-byte rows with the given descriptor base_offset; see

@@ -30,7 +30,8 @@ class ConvDesc(C.Structure):
     _fields_ = [("x", Tensor), ("y", Tensor), ("y_c_off", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32),
                 ("stride", C.c_int32), ("pad", C.c_int32), ("act", C.c_int32), ("w_packed", C.c_void_p),
                 ("bias", C.c_void_p), ("alpha", C.c_void_p), ("mul", C.POINTER(Tensor)), ("out_nchw", C.c_void_p),
-                ("residual_nchw", C.c_void_p), ("in_stats", C.c_void_p)]
+                ("residual_nchw", C.c_void_p), ("y_mul", C.c_int32), ("y_off_h", C.c_int32), ("y_off_w", C.c_int32),
+                ("mask", C.POINTER(Tensor)), ("mask_act", C.c_int32), ("in_stats", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/uegan_sm100.h declares
@@ -62,6 +63,23 @@ SYMBOLS = {
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "uegan_msrec_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "uegan_pack_conv_weight_dgrad": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 10 + [C.c_void_p]),
+    "uegan_conv2d_wgrad": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor)] + [C.c_int32] * 7 +
+                           [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "uegan_head_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Tensor),
+                                 C.c_void_p]),
+    "uegan_grad_combine": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.POINTER(Tensor), C.c_int32, C.c_int32,
+                                     C.c_int32, C.POINTER(Tensor), C.c_int32, C.POINTER(Tensor), C.c_int32,
+                                     C.POINTER(Tensor), C.c_int32, C.c_int32, C.POINTER(Tensor), C.c_int32,
+                                     C.c_void_p]),
+    "uegan_channel_sum": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "uegan_instance_norm_bwd": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.POINTER(Tensor), C.c_void_p,
+                                          C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
+    "uegan_upsample2x_bwd": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.POINTER(Tensor), C.c_void_p]),
+    "uegan_maxpool2x2_bwd": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
+    "uegan_in_mse_bwd": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p, C.c_float,
+                                   C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
+    "uegan_unpack_input_grad": (C.c_int, [C.POINTER(Tensor), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
     "uegan_upsample2x": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_int32, C.c_void_p]),
     "uegan_maxpool2x2": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
     "uegan_unpack_nchw": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

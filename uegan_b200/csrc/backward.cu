@@ -1,0 +1,598 @@
+// HBM-bound kernels of the backward pass (everything that is not a GEMM): gradient of the planar heads, reflect-pad
+// fold + activation masks, InstanceNorm backward, bilinear-x2 backward, max-pool backward, per-channel sums (bias
+// gradients), InstanceNorm+MSE backward.  Same NHWC-with-halo tensors and 16-byte channel vectors as elementwise.cu.
+// Gradient tensors that feed a dgrad GEMM are written WITH A ZERO HALO (the transposed convolution's padding).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace uegan {
+
+// reuse Vec<T>, TGeom, geom(), toff(), to_f32<T>() from elementwise.cu (same translation unit)
+
+// ------------------------------------------------------------------------------------------
+// planar heads: dz[n,y,x,c] = dout_nchw * act'(.) (* clamp mask), written as NHWC with a zero halo
+//   mode 0: out = tanh(z)                      -> dz = dout * (1 - out^2)                  (D heads, models.py:178)
+//   mode 1: out = sigmoid(z)                   -> dz = dout * out * (1 - out)              (ls / rals heads)
+//   mode 2: out = clamp(tanh(z) + x, -1, 1)    -> dz = dout * [|res + x| <= 1] * (1 - res^2), res given (models.py:72)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ outv, const float* __restrict__ xin,
+                                TGeom d, int cch, int mode, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int xp = (int)(i % d.wp);
+  const int yp = (int)((i / d.wp) % d.hp);
+  const int n = (int)(i / (d.wp * d.hp));
+  const int y = yp - d.halo, x = xp - d.halo;
+  float v[Vec<T>::N];
+#pragma unroll
+  for (int k = 0; k < Vec<T>::N; ++k) v[k] = 0.f;
+  if (y >= 0 && y < d.h && x >= 0 && x < d.w) {
+    const long long plane = (long long)d.h * d.w;
+    for (int c = 0; c < cch; ++c) {
+      const long long o = ((long long)n * cch + c) * plane + (long long)y * d.w + x;
+      const float g = __ldg(dout + o), r = __ldg(outv + o);
+      float dz;
+      if (mode == 0) dz = g * (1.f - r * r);
+      else if (mode == 1) dz = g * r * (1.f - r);
+      else {
+        const float s = r + __ldg(xin + o);
+        dz = (s >= -1.f && s <= 1.f) ? g * (1.f - r * r) : 0.f;
+      }
+      v[c] = dz;
+    }
+  }
+  T* dp = static_cast<T*>(d.data) + i * d.c;
+  Vec<T>::store(dp, v);
+  float z[Vec<T>::N];
+#pragma unroll
+  for (int k = 0; k < Vec<T>::N; ++k) z[k] = 0.f;
+  for (int c = Vec<T>::N; c < d.c; c += Vec<T>::N) Vec<T>::store(dp + c, z);
+}
+
+// ------------------------------------------------------------------------------------------
+// grad_combine: dst = mask(act; fwd) * mul * ( fold(src_a) + add_b + add_c ), interior; halo of dst := 0
+//   src_a has spatial extent (h + 2*pa, w + 2*pa) (halo 0): gradient w.r.t. the PADDED input of a conv; reflect padding
+//   folds the border back (adjoint of nn.ReflectionPad2d), zero padding crops.
+// ------------------------------------------------------------------------------------------
+struct CombineArgs {
+  TGeom dst; int dst_c_off;
+  TGeom a; int a_c_off; int pa; int reflect_a; int has_a;
+  TGeom b; int b_c_off; int has_b;
+  TGeom c; int c_c_off; int has_c;
+  TGeom mask; int mask_c_off; int act; int has_mask;
+  TGeom mul; int mul_c_off; int has_mul;
+  int cch;  // channels produced
+};
+template <typename T>
+__global__ void grad_combine_kernel(CombineArgs q, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  constexpr int VN = Vec<T>::N;
+  const int cv = q.cch / VN;
+  const int c = (int)(i % cv) * VN;
+  long long pix = i / cv;
+  const int xp = (int)(pix % q.dst.wp);
+  pix /= q.dst.wp;
+  const int yp = (int)(pix % q.dst.hp);
+  const int n = (int)(pix / q.dst.hp);
+  const int y = yp - q.dst.halo, x = xp - q.dst.halo;
+  float v[VN];
+#pragma unroll
+  for (int k = 0; k < VN; ++k) v[k] = 0.f;
+  const bool interior = (y >= 0 && y < q.dst.h && x >= 0 && x < q.dst.w);
+  if (interior) {
+    if (q.has_a) {
+      const T* ab = static_cast<const T*>(q.a.data);
+      // positions of the padded tensor that map to (y, x)
+      int ys[3], xs[3], ny = 0, nx = 0;
+      ys[ny++] = y + q.pa;
+      xs[nx++] = x + q.pa;
+      if (q.reflect_a && q.pa > 0) {
+        if (y >= 1 && y <= q.pa) ys[ny++] = q.pa - y;
+        if (y <= q.dst.h - 2 && y >= q.dst.h - 1 - q.pa) ys[ny++] = q.pa + 2 * (q.dst.h - 1) - y;
+        if (x >= 1 && x <= q.pa) xs[nx++] = q.pa - x;
+        if (x <= q.dst.w - 2 && x >= q.dst.w - 1 - q.pa) xs[nx++] = q.pa + 2 * (q.dst.w - 1) - x;
+      }
+      for (int iy = 0; iy < ny; ++iy)
+        for (int ix = 0; ix < nx; ++ix) {
+          float t[VN];
+          Vec<T>::load(ab + toff(q.a, n, ys[iy], xs[ix], q.a_c_off + c), t);
+#pragma unroll
+          for (int k = 0; k < VN; ++k) v[k] += t[k];
+        }
+    }
+    if (q.has_b) {
+      float t[VN];
+      Vec<T>::load(static_cast<const T*>(q.b.data) + toff(q.b, n, y, x, q.b_c_off + c), t);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) v[k] += t[k];
+    }
+    if (q.has_c) {
+      float t[VN];
+      Vec<T>::load(static_cast<const T*>(q.c.data) + toff(q.c, n, y, x, q.c_c_off + c), t);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) v[k] += t[k];
+    }
+    if (q.has_mul) {
+      float t[VN];
+      Vec<T>::load(static_cast<const T*>(q.mul.data) + toff(q.mul, n, y, x, q.mul_c_off + c), t);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) v[k] *= t[k];
+    }
+    if (q.has_mask) {
+      float t[VN];
+      Vec<T>::load(static_cast<const T*>(q.mask.data) + toff(q.mask, n, y, x, q.mask_c_off + c), t);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) {
+        if (q.act == UEGAN_ACT_LRELU) v[k] *= (t[k] > 0.f ? 1.f : 0.2f);
+        else if (q.act == UEGAN_ACT_RELU) v[k] = t[k] > 0.f ? v[k] : 0.f;
+      }
+    }
+  }
+  Vec<T>::store(static_cast<T*>(q.dst.data) + toff(q.dst, n, y, x, q.dst_c_off + c), v);
+}
+
+// ------------------------------------------------------------------------------------------
+// per-channel sum over n, h, w (bias gradient): out[c] += sum
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void channel_sum_kernel(TGeom s, int c_off, int cch, float* __restrict__ out, int pix_per_block) {
+  const int c = threadIdx.x % cch;
+  const int grp = threadIdx.x / cch;
+  const int groups = blockDim.x / cch;
+  const long long npix = (long long)s.n * s.h * s.w;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > npix) p1 = npix;
+  const T* base = static_cast<const T*>(s.data);
+  float sum = 0.f;
+  for (long long p = p0 + grp; p < p1; p += groups) {
+    const int x = (int)(p % s.w);
+    const int y = (int)((p / s.w) % s.h);
+    const int n = (int)(p / ((long long)s.w * s.h));
+    sum += to_f32<T>(base[toff(s, n, y, x, c_off + c)]);
+  }
+  extern __shared__ float shf[];
+  shf[threadIdx.x] = sum;
+  __syncthreads();
+  if (grp == 0) {
+    for (int g = 1; g < groups; ++g) sum += shf[g * cch + c];
+    atomicAdd(out + c, sum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// InstanceNorm backward.  xhat = (z - mean) * rstd ; out = xhat
+//   dz = rstd * (dout - mean_p(dout) - xhat * mean_p(dout * xhat))
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void in_bwd_stats_kernel(TGeom dz_src, int d_c_off, TGeom z, const float* __restrict__ mr,
+                                    double* __restrict__ sums, int cch, int pix_per_block) {
+  const int c = threadIdx.x % cch;
+  const int grp = threadIdx.x / cch;
+  const int groups = blockDim.x / cch;
+  const int n = blockIdx.y;
+  const long long npix = (long long)z.h * z.w;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > npix) p1 = npix;
+  const float mean = mr[((long long)n * cch + c) * 2], rstd = mr[((long long)n * cch + c) * 2 + 1];
+  double s1 = 0.0, s2 = 0.0;
+  for (long long p = p0 + grp; p < p1; p += groups) {
+    const int y = (int)(p / z.w), x = (int)(p % z.w);
+    const float g = to_f32<T>(static_cast<const T*>(dz_src.data)[toff(dz_src, n, y, x, d_c_off + c)]);
+    const float xh = (to_f32<T>(static_cast<const T*>(z.data)[toff(z, n, y, x, c)]) - mean) * rstd;
+    s1 += g;
+    s2 += (double)g * xh;
+  }
+  extern __shared__ double shd[];
+  shd[threadIdx.x] = s1;
+  shd[blockDim.x + threadIdx.x] = s2;
+  __syncthreads();
+  if (grp == 0) {
+    for (int g = 1; g < groups; ++g) {
+      s1 += shd[g * cch + c];
+      s2 += shd[blockDim.x + g * cch + c];
+    }
+    atomicAdd(&sums[((long long)n * cch + c) * 2], s1);
+    atomicAdd(&sums[((long long)n * cch + c) * 2 + 1], s2);
+  }
+}
+template <typename T>
+__global__ void in_bwd_apply_kernel(TGeom dsrc, int d_c_off, TGeom z, TGeom dst, const float* __restrict__ mr,
+                                    const double* __restrict__ sums, double inv_npix, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  constexpr int VN = Vec<T>::N;
+  const int cv = z.c / VN;
+  const int c = (int)(i % cv) * VN;
+  long long pix = i / cv;
+  const int xp = (int)(pix % dst.wp);
+  pix /= dst.wp;
+  const int yp = (int)(pix % dst.hp);
+  const int n = (int)(pix / dst.hp);
+  const int y = yp - dst.halo, x = xp - dst.halo;
+  float v[VN];
+#pragma unroll
+  for (int k = 0; k < VN; ++k) v[k] = 0.f;
+  if (y >= 0 && y < dst.h && x >= 0 && x < dst.w) {
+    float g[VN], zz[VN];
+    Vec<T>::load(static_cast<const T*>(dsrc.data) + toff(dsrc, n, y, x, d_c_off + c), g);
+    Vec<T>::load(static_cast<const T*>(z.data) + toff(z, n, y, x, c), zz);
+#pragma unroll
+    for (int k = 0; k < VN; ++k) {
+      const long long si = ((long long)n * z.c + c + k) * 2;
+      const float mean = mr[si], rstd = mr[si + 1];
+      const float xh = (zz[k] - mean) * rstd;
+      const float m1 = (float)(sums[si] * inv_npix), m2 = (float)(sums[si + 1] * inv_npix);
+      v[k] = rstd * (g[k] - m1 - xh * m2);
+    }
+  }
+  Vec<T>::store(static_cast<T*>(dst.data) + toff(dst, n, y, x, c), v);
+}
+
+// ------------------------------------------------------------------------------------------
+// bilinear x2 (align_corners) backward, gather form: exact adjoint of upsample2x_kernel
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void upsample2x_bwd_kernel(TGeom g, int g_c_off, TGeom d, float sy, float sx, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  constexpr int VN = Vec<T>::N;
+  const int cv = d.c / VN;
+  const int c = (int)(i % cv) * VN;
+  long long pix = i / cv;
+  const int xi = (int)(pix % d.w);
+  pix /= d.w;
+  const int yi = (int)(pix % d.h);
+  const int n = (int)(pix / d.h);
+  float acc[VN];
+#pragma unroll
+  for (int k = 0; k < VN; ++k) acc[k] = 0.f;
+  // candidate output rows / cols whose 2-tap footprint can touch (yi, xi)
+  int yo0 = sy > 0.f ? (int)floorf((yi - 1) / sy) : 0, yo1 = sy > 0.f ? (int)ceilf((yi + 1) / sy) : g.h - 1;
+  int xo0 = sx > 0.f ? (int)floorf((xi - 1) / sx) : 0, xo1 = sx > 0.f ? (int)ceilf((xi + 1) / sx) : g.w - 1;
+  yo0 = max(yo0, 0); xo0 = max(xo0, 0); yo1 = min(yo1, g.h - 1); xo1 = min(xo1, g.w - 1);
+  const T* gb = static_cast<const T*>(g.data);
+  for (int yo = yo0; yo <= yo1; ++yo) {
+    const float fy = sy * yo;
+    const int y0 = (int)fy;
+    const int y1 = y0 + (y0 < d.h - 1 ? 1 : 0);
+    const float ly = fy - y0;
+    float wy = 0.f;
+    if (y0 == yi) wy += 1.f - ly;
+    if (y1 == yi) wy += ly;
+    if (wy == 0.f) continue;
+    for (int xo = xo0; xo <= xo1; ++xo) {
+      const float fx = sx * xo;
+      const int x0 = (int)fx;
+      const int x1 = x0 + (x0 < d.w - 1 ? 1 : 0);
+      const float lx = fx - x0;
+      float wx = 0.f;
+      if (x0 == xi) wx += 1.f - lx;
+      if (x1 == xi) wx += lx;
+      if (wx == 0.f) continue;
+      float t[VN];
+      Vec<T>::load(gb + toff(g, n, yo, xo, g_c_off + c), t);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) acc[k] += wy * wx * t[k];
+    }
+  }
+  Vec<T>::store(static_cast<T*>(d.data) + toff(d, n, yi, xi, c), acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// max-pool 2x2 backward fused with the ReLU mask of the pooled conv's output and an optional extra gradient:
+//   dsrc[2yo+a, 2xo+b] = (src is the argmax of its window ? dpool[yo, xo] : 0)   (first max wins, like PyTorch)
+// written with a zero halo.
+// ------------------------------------------------------------------------------------------
+template <typename T, typename TG>
+__global__ void maxpool2x2_bwd_kernel(TGeom src, TGeom dpool, TGeom dst, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  constexpr int VN = 8;
+  const int cv = src.c / VN;
+  const int c = (int)(i % cv) * VN;
+  long long pix = i / cv;
+  const int xo = (int)(pix % dpool.w);
+  pix /= dpool.w;
+  const int yo = (int)(pix % dpool.h);
+  const int n = (int)(pix / dpool.h);
+  float v[4][VN], g[VN];
+  const T* sb = static_cast<const T*>(src.data);
+  Vec<T>::load(sb + toff(src, n, 2 * yo, 2 * xo, c), v[0]);
+  Vec<T>::load(sb + toff(src, n, 2 * yo, 2 * xo + 1, c), v[1]);
+  Vec<T>::load(sb + toff(src, n, 2 * yo + 1, 2 * xo, c), v[2]);
+  Vec<T>::load(sb + toff(src, n, 2 * yo + 1, 2 * xo + 1, c), v[3]);
+  Vec<TG>::load(static_cast<const TG*>(dpool.data) + toff(dpool, n, yo, xo, c), g);
+  float o[4][VN];
+#pragma unroll
+  for (int k = 0; k < VN; ++k) {
+    int best = 0;
+    float bv = v[0][k];
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+      if (v[j][k] > bv) { bv = v[j][k]; best = j; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j][k] = (j == best) ? g[k] : 0.f;
+  }
+  TG* db = static_cast<TG*>(dst.data);
+  Vec<TG>::store(db + toff(dst, n, 2 * yo, 2 * xo, c), o[0]);
+  Vec<TG>::store(db + toff(dst, n, 2 * yo, 2 * xo + 1, c), o[1]);
+  Vec<TG>::store(db + toff(dst, n, 2 * yo + 1, 2 * xo, c), o[2]);
+  Vec<TG>::store(db + toff(dst, n, 2 * yo + 1, 2 * xo + 1, c), o[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// VGG tap: d/dx of  weight * mean((IN(x) - IN(y))^2)  w.r.t. the feature map x (y is a constant):
+//   e = xh - yh ; dxh = (2 * weight / numel) * e ; dx = rstd * (dxh - mean_p(dxh) - xh * mean_p(dxh * xh))
+// followed by the ReLU mask of the tap itself (x is a ReLU output) and accumulation with the gradient that arrives from
+// deeper layers (`deep`, optional).  Output gradient tensor TG (bf16), zero halo.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void tap_bwd_stats_kernel(TGeom x, TGeom y, const float* __restrict__ mrx, const float* __restrict__ mry,
+                                     double* __restrict__ sums, int pix_per_block) {
+  const int c = threadIdx.x % x.c;
+  const int grp = threadIdx.x / x.c;
+  const int groups = blockDim.x / x.c;
+  const int n = blockIdx.y;
+  const long long npix = (long long)x.h * x.w;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > npix) p1 = npix;
+  const long long si = ((long long)n * x.c + c) * 2;
+  const float mx = mrx[si], rx = mrx[si + 1], my = mry[si], ry = mry[si + 1];
+  double s1 = 0.0, s2 = 0.0;
+  for (long long p = p0 + grp; p < p1; p += groups) {
+    const int yy = (int)(p / x.w), xx = (int)(p % x.w);
+    const float xh = (to_f32<T>(static_cast<const T*>(x.data)[toff(x, n, yy, xx, c)]) - mx) * rx;
+    const float yh = (to_f32<T>(static_cast<const T*>(y.data)[toff(y, n, yy, xx, c)]) - my) * ry;
+    const float e = xh - yh;
+    s1 += e;
+    s2 += (double)e * xh;
+  }
+  extern __shared__ double shd[];
+  shd[threadIdx.x] = s1;
+  shd[blockDim.x + threadIdx.x] = s2;
+  __syncthreads();
+  if (grp == 0) {
+    for (int g = 1; g < groups; ++g) {
+      s1 += shd[g * x.c + c];
+      s2 += shd[blockDim.x + g * x.c + c];
+    }
+    atomicAdd(&sums[si], s1);
+    atomicAdd(&sums[si + 1], s2);
+  }
+}
+template <typename T, typename TG>
+__global__ void tap_bwd_apply_kernel(TGeom x, TGeom y, TGeom deep, int has_deep, TGeom dst, const float* __restrict__ mrx,
+                                     const float* __restrict__ mry, const double* __restrict__ sums, double inv_npix,
+                                     float coef, const float* __restrict__ gscale, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  constexpr int VN = 8;
+  const int cv = x.c / VN;
+  const int c = (int)(i % cv) * VN;
+  long long pix = i / cv;
+  const int xp = (int)(pix % dst.wp);
+  pix /= dst.wp;
+  const int yp = (int)(pix % dst.hp);
+  const int n = (int)(pix / dst.hp);
+  const int yy = yp - dst.halo, xx = xp - dst.halo;
+  float v[VN];
+#pragma unroll
+  for (int k = 0; k < VN; ++k) v[k] = 0.f;
+  if (yy >= 0 && yy < dst.h && xx >= 0 && xx < dst.w) {
+    float xv[VN], yv[VN], dv[VN];
+    Vec<T>::load(static_cast<const T*>(x.data) + toff(x, n, yy, xx, c), xv);
+    Vec<T>::load(static_cast<const T*>(y.data) + toff(y, n, yy, xx, c), yv);
+    if (has_deep) Vec<TG>::load(static_cast<const TG*>(deep.data) + toff(deep, n, yy, xx, c), dv);
+    const float cf = coef * (gscale ? gscale[0] : 1.f);
+#pragma unroll
+    for (int k = 0; k < VN; ++k) {
+      const long long si = ((long long)n * x.c + c + k) * 2;
+      const float xh = (xv[k] - mrx[si]) * mrx[si + 1];
+      const float yh = (yv[k] - mry[si]) * mry[si + 1];
+      const float e = xh - yh;
+      const float m1 = (float)(sums[si] * inv_npix), m2 = (float)(sums[si + 1] * inv_npix);
+      float g = cf * mrx[si + 1] * (e - m1 - xh * m2);
+      if (has_deep) g += dv[k];
+      v[k] = xv[k] > 0.f ? g : 0.f;  // ReLU mask of the tap
+    }
+  }
+  Vec<TG>::store(static_cast<TG*>(dst.data) + toff(dst, n, yy, xx, c), v);
+}
+
+// gradient of the packed input: NHWC (c >= 3) -> NCHW fp32 (3 channels) times per-channel scale
+template <typename TG>
+__global__ void unpack_grad_kernel(TGeom s, float* __restrict__ dst, float s0, float s1, float s2, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % s.w);
+  long long r = i / s.w;
+  const int y = (int)(r % s.h);
+  r /= s.h;
+  const int c = (int)(r % 3);
+  const int n = (int)(r / 3);
+  const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
+  dst[i] = to_f32<TG>(static_cast<const TG*>(s.data)[toff(s, n, y, x, c)]) * sc;
+}
+
+static inline unsigned nblk(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+
+}  // namespace uegan
+
+using namespace uegan;
+
+#define UEGAN_DISPATCH(dtype, KERNEL, ...)                      \
+  do {                                                          \
+    if ((dtype) == UEGAN_F32) KERNEL<float> __VA_ARGS__;        \
+    else if ((dtype) == UEGAN_BF16) KERNEL<__nv_bfloat16> __VA_ARGS__; \
+    else KERNEL<__half> __VA_ARGS__;                            \
+  } while (0)
+
+extern "C" {
+
+int uegan_head_bwd(const float* dout_nchw, const float* out_nchw, const float* x_nchw, int32_t channels, int32_t mode,
+                   const uegan_tensor* dz, void* stream) {
+  UEGAN_CHECK(dout_nchw && out_nchw && dz && dz->data, "head_bwd: null pointer");
+  UEGAN_CHECK(mode >= 0 && mode <= 2 && (mode != 2 || x_nchw), "head_bwd: bad mode");
+  UEGAN_CHECK(dtype_ok(dz->dtype) && (dz->c * dtype_size(dz->dtype)) % 16 == 0, "head_bwd: bad dz tensor");
+  UEGAN_CHECK(channels <= 16 / dtype_size(dz->dtype), "head_bwd: too many channels");
+  const TGeom d = geom(*dz);
+  const long long total = (long long)d.n * d.hp * d.wp;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UEGAN_DISPATCH(dz->dtype, head_bwd_kernel, <<<nblk(total, 256), 256, 0, st>>>(dout_nchw, out_nchw, x_nchw, d, channels,
+                                                                                mode, total));
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_grad_combine(const uegan_tensor* dst, int32_t dst_c_off, int32_t channels, const uegan_tensor* src_a,
+                       int32_t a_c_off, int32_t pad_a, int32_t pad_mode_a, const uegan_tensor* add_b, int32_t b_c_off,
+                       const uegan_tensor* add_c, int32_t c_c_off, const uegan_tensor* mask, int32_t mask_c_off,
+                       int32_t act, const uegan_tensor* mul, int32_t mul_c_off, void* stream) {
+  UEGAN_CHECK(dst && dst->data && (src_a || add_b || add_c), "grad_combine: null pointer");
+  CombineArgs q;
+  memset(&q, 0, sizeof(q));
+  q.dst = geom(*dst); q.dst_c_off = dst_c_off; q.cch = channels; q.act = act;
+  const int vn = 16 / dtype_size(dst->dtype);
+  UEGAN_CHECK(channels % vn == 0 && dst_c_off % vn == 0 && dst_c_off + channels <= dst->c, "grad_combine: bad channels");
+  auto chk = [&](const uegan_tensor* t, int off, int extra, const char* who) -> int {
+    UEGAN_CHECK(t->data && t->dtype == dst->dtype && t->n == dst->n && t->h == dst->h + 2 * extra &&
+                    t->w == dst->w + 2 * extra && off % vn == 0 && off + channels <= t->c,
+                "grad_combine: %s mismatch (%dx%dx%dx%d vs dst %dx%dx%dx%d, extra %d)", who, t->n, t->h, t->w, t->c,
+                dst->n, dst->h, dst->w, dst->c, extra);
+    return 0;
+  };
+  if (src_a) {
+    if (chk(src_a, a_c_off, pad_a, "src_a")) return -1;
+    q.a = geom(*src_a); q.a_c_off = a_c_off; q.pa = pad_a; q.reflect_a = pad_mode_a == UEGAN_PAD_REFLECT; q.has_a = 1;
+    UEGAN_CHECK(!q.reflect_a || (pad_a < dst->h && pad_a < dst->w), "grad_combine: pad too large");
+  }
+  if (add_b) { if (chk(add_b, b_c_off, 0, "add_b")) return -1; q.b = geom(*add_b); q.b_c_off = b_c_off; q.has_b = 1; }
+  if (add_c) { if (chk(add_c, c_c_off, 0, "add_c")) return -1; q.c = geom(*add_c); q.c_c_off = c_c_off; q.has_c = 1; }
+  if (mask) { if (chk(mask, mask_c_off, 0, "mask")) return -1; q.mask = geom(*mask); q.mask_c_off = mask_c_off; q.has_mask = 1; }
+  if (mul) { if (chk(mul, mul_c_off, 0, "mul")) return -1; q.mul = geom(*mul); q.mul_c_off = mul_c_off; q.has_mul = 1; }
+  const long long total = (long long)q.dst.n * q.dst.hp * q.dst.wp * (channels / vn);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UEGAN_DISPATCH(dst->dtype, grad_combine_kernel, <<<nblk(total, 256), 256, 0, st>>>(q, total));
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_channel_sum(const uegan_tensor* src, int32_t c_off, int32_t channels, float* out, void* stream) {
+  UEGAN_CHECK(src && src->data && out, "channel_sum: null pointer");
+  UEGAN_CHECK(c_off >= 0 && c_off + channels <= src->c && channels <= 1024, "channel_sum: bad channel range");
+  const TGeom s = geom(*src);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UEGAN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * channels, st));
+  int threads = channels;
+  while (threads < 256) threads += channels;
+  const long long npix = (long long)s.n * s.h * s.w;
+  const int ppb = 2048;
+  UEGAN_DISPATCH(src->dtype, channel_sum_kernel,
+                 <<<nblk(npix, ppb), threads, sizeof(float) * threads, st>>>(s, c_off, channels, out, ppb));
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_instance_norm_bwd(const uegan_tensor* dout, int32_t d_c_off, const uegan_tensor* z, const float* mean_rstd,
+                            const uegan_tensor* dz, double* ws, void* stream) {
+  UEGAN_CHECK(dout && z && dz && mean_rstd && ws, "instance_norm_bwd: null pointer");
+  UEGAN_CHECK(dout->dtype == z->dtype && z->dtype == dz->dtype && dout->n == z->n && dout->h == z->h && dout->w == z->w &&
+                  dz->n == z->n && dz->h == z->h && dz->w == z->w && dz->c == z->c && d_c_off + z->c <= dout->c,
+              "instance_norm_bwd: tensor mismatch");
+  const TGeom g = geom(*dout), zz = geom(*z), d = geom(*dz);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nc = zz.n * zz.c;
+  UEGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * nc, st));
+  int threads = zz.c;
+  while (threads < 256) threads += zz.c;
+  const long long npix = (long long)zz.h * zz.w;
+  const int ppb = 1024;
+  const dim3 grid(nblk(npix, ppb), (unsigned)zz.n);
+  UEGAN_DISPATCH(z->dtype, in_bwd_stats_kernel,
+                 <<<grid, threads, sizeof(double) * 2 * threads, st>>>(g, d_c_off, zz, mean_rstd, ws, zz.c, ppb));
+  const int vn = 16 / dtype_size(z->dtype);
+  const long long total = (long long)d.n * d.hp * d.wp * (zz.c / vn);
+  UEGAN_DISPATCH(z->dtype, in_bwd_apply_kernel,
+                 <<<nblk(total, 256), 256, 0, st>>>(g, d_c_off, zz, d, mean_rstd, ws, 1.0 / (double)npix, total));
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_upsample2x_bwd(const uegan_tensor* dout, int32_t d_c_off, const uegan_tensor* dsrc, void* stream) {
+  UEGAN_CHECK(dout && dsrc, "upsample2x_bwd: null pointer");
+  UEGAN_CHECK(dout->dtype == dsrc->dtype && dout->n == dsrc->n && dout->h == 2 * dsrc->h && dout->w == 2 * dsrc->w &&
+                  d_c_off + dsrc->c <= dout->c,
+              "upsample2x_bwd: tensor mismatch");
+  const TGeom g = geom(*dout), d = geom(*dsrc);
+  const float sy = g.h > 1 ? (float)(d.h - 1) / (float)(g.h - 1) : 0.f;
+  const float sx = g.w > 1 ? (float)(d.w - 1) / (float)(g.w - 1) : 0.f;
+  const int vn = 16 / dtype_size(dsrc->dtype);
+  const long long total = (long long)d.n * d.h * d.w * (d.c / vn);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UEGAN_DISPATCH(dsrc->dtype, upsample2x_bwd_kernel, <<<nblk(total, 256), 256, 0, st>>>(g, d_c_off, d, sy, sx, total));
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_maxpool2x2_bwd(const uegan_tensor* src, const uegan_tensor* dpool, const uegan_tensor* dsrc, void* stream) {
+  UEGAN_CHECK(src && dpool && dsrc, "maxpool2x2_bwd: null pointer");
+  UEGAN_CHECK(src->dtype == UEGAN_F16 && dpool->dtype == UEGAN_BF16 && dsrc->dtype == UEGAN_BF16,
+              "maxpool2x2_bwd: expects fp16 activations and bf16 gradients");
+  UEGAN_CHECK(src->n == dsrc->n && src->h == dsrc->h && src->w == dsrc->w && src->c == dsrc->c && dpool->h == src->h / 2 &&
+                  dpool->w == src->w / 2 && dpool->c == src->c && src->c % 8 == 0,
+              "maxpool2x2_bwd: tensor mismatch");
+  const TGeom s = geom(*src), g = geom(*dpool), d = geom(*dsrc);
+  const long long total = (long long)g.n * g.h * g.w * (s.c / 8);
+  maxpool2x2_bwd_kernel<__half, __nv_bfloat16><<<nblk(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(s, g, d, total);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
+                     float weight, const float* gscale_dev, const uegan_tensor* deep, const uegan_tensor* dx, double* ws,
+                     void* stream) {
+  UEGAN_CHECK(x && y && dx && mean_rstd_x && mean_rstd_y && ws, "in_mse_bwd: null pointer");
+  UEGAN_CHECK(x->dtype == UEGAN_F16 && y->dtype == UEGAN_F16 && dx->dtype == UEGAN_BF16 && x->c % 8 == 0 && x->c <= 1024,
+              "in_mse_bwd: expects fp16 features and a bf16 gradient");
+  UEGAN_CHECK(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c && dx->n == x->n && dx->h == x->h &&
+                  dx->w == x->w && dx->c == x->c,
+              "in_mse_bwd: tensor mismatch");
+  if (deep) UEGAN_CHECK(deep->dtype == UEGAN_BF16 && deep->h == x->h && deep->w == x->w && deep->c == x->c, "in_mse_bwd: deep mismatch");
+  const TGeom gx = geom(*x), gy = geom(*y), gd = geom(*dx);
+  TGeom gdeep = gd;
+  if (deep) gdeep = geom(*deep);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nc = gx.n * gx.c;
+  UEGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * nc, st));
+  int threads = gx.c;
+  while (threads < 256) threads += gx.c;
+  const long long npix = (long long)gx.h * gx.w;
+  const int ppb = 1024;
+  const dim3 grid(nblk(npix, ppb), (unsigned)gx.n);
+  tap_bwd_stats_kernel<__half><<<grid, threads, sizeof(double) * 2 * threads, st>>>(gx, gy, mean_rstd_x, mean_rstd_y, ws, ppb);
+  const double numel = (double)gx.n * gx.c * (double)npix;
+  const long long total = (long long)gd.n * gd.hp * gd.wp * (gx.c / 8);
+  tap_bwd_apply_kernel<__half, __nv_bfloat16><<<nblk(total, 256), 256, 0, st>>>(
+      gx, gy, gdeep, deep ? 1 : 0, gd, mean_rstd_x, mean_rstd_y, ws, 1.0 / (double)npix, (float)(2.0 * weight / numel),
+      gscale_dev, total);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_unpack_input_grad(const uegan_tensor* dx, const float* scale_host, float* dst_nchw, void* stream) {
+  UEGAN_CHECK(dx && dx->data && dst_nchw && dx->c >= 3, "unpack_input_grad: null pointer");
+  const TGeom s = geom(*dx);
+  const long long total = (long long)s.n * 3 * s.h * s.w;
+  const float s0 = scale_host ? scale_host[0] : 1.f, s1 = scale_host ? scale_host[1] : 1.f, s2 = scale_host ? scale_host[2] : 1.f;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UEGAN_DISPATCH(dx->dtype, unpack_grad_kernel, <<<nblk(total, 256), 256, 0, st>>>(s, dst_nchw, s0, s1, s2, total));
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

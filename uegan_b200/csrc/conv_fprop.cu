@@ -49,6 +49,9 @@ struct ConvParams {
   const float* alpha;
   const void* mul;  // same dtype as out
   long long mul_pix, mul_row, mul_img;
+  const void* mask;  // activation-derivative mask from a forward tensor (dgrad epilogue); dtype mask_kind
+  long long mask_pix, mask_row, mask_img;
+  int mask_kind, mask_act;
   float* out_nchw;
   const float* residual_nchw;
   unsigned int* err_sink;  // host-mapped watchdog word
@@ -103,7 +106,8 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
 // NHWC epilogue of one warp: its 32 rows x the 16-column chunks {half, half+2, ...} of the tile.
 template <int ACT>
 __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t taddr, int colbase, int half, long long o,
-                                              long long mo, bool valid, float alpha, float* stat_slice) {
+                                              long long mo, bool valid, float alpha, float* stat_slice, int mk_n, int mk_h,
+                                              int mk_w) {
   for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
     uint32_t rr[16];
     tmem_ld16(taddr + c0, rr);
@@ -179,6 +183,18 @@ __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t tadd
           const float4 qv = __ldg(mp + i);
           v[4 * i + 0] *= qv.x; v[4 * i + 1] *= qv.y; v[4 * i + 2] *= qv.z; v[4 * i + 3] *= qv.w;
         }
+      }
+    }
+    if (p.mask) {
+      const long long ko = (long long)mk_n * p.mask_img + (long long)mk_h * p.mask_row + (long long)mk_w * p.mask_pix + colbase + c0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float t;
+        if (p.mask_kind == UEGAN_F32) t = __ldg(reinterpret_cast<const float*>(p.mask) + ko + i);
+        else if (p.mask_kind == UEGAN_F16) t = __half2float(reinterpret_cast<const __half*>(p.mask)[ko + i]);
+        else t = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.mask)[ko + i]);
+        if (p.mask_act == UEGAN_ACT_LRELU) v[i] *= (t > 0.f ? 1.f : 0.2f);
+        else v[i] = t > 0.f ? v[i] : 0.f;
       }
     }
     if (p.out_kind != UEGAN_F32) {
@@ -415,10 +431,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const long long o = (long long)n * p.out_img + (long long)ho * p.out_row + (long long)wo * p.out_pix + colbase;
         const long long mo = (long long)n * p.mul_img + (long long)ho * p.mul_row + (long long)wo * p.mul_pix + colbase;
         switch (p.act) {
-          case UEGAN_ACT_LRELU: epilogue_nhwc<UEGAN_ACT_LRELU>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice); break;
-          case UEGAN_ACT_RELU: epilogue_nhwc<UEGAN_ACT_RELU>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice); break;
-          case UEGAN_ACT_NONE: epilogue_nhwc<UEGAN_ACT_NONE>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice); break;
-          default: epilogue_nhwc<-1>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice); break;
+          case UEGAN_ACT_LRELU: epilogue_nhwc<UEGAN_ACT_LRELU>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice, n, ho, wo); break;
+          case UEGAN_ACT_RELU: epilogue_nhwc<UEGAN_ACT_RELU>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice, n, ho, wo); break;
+          case UEGAN_ACT_NONE: epilogue_nhwc<UEGAN_ACT_NONE>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice, n, ho, wo); break;
+          default: epilogue_nhwc<-1>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice, n, ho, wo); break;
         }
       }
       tcgen05_fence_before();
@@ -500,13 +516,23 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   p.residual_nchw = d.residual_nchw;
   p.err_sink = error_sink_device();
   p.in_stats = d.in_stats;
+  const int ymul = d.y_mul > 1 ? d.y_mul : 1;
   if (d.out_nchw) {
     UEGAN_CHECK(d.cout <= 16, "conv: planar output needs cout <= 16 (got %d)", d.cout);
   } else {
     const uegan_tensor& y = d.y;
     UEGAN_CHECK(y.data != nullptr, "conv: null output");
-    UEGAN_CHECK(y.n == x.n && y.h == Ho && y.w == Wo, "conv: y is %dx%dx%d, expected %dx%dx%d", y.n, y.h, y.w, x.n,
-                Ho, Wo);
+    if (ymul == 1 && d.y_off_h == 0 && d.y_off_w == 0) {
+      UEGAN_CHECK(y.n == x.n && y.h == Ho && y.w == Wo, "conv: y is %dx%dx%d, expected %dx%dx%d", y.n, y.h, y.w, x.n,
+                  Ho, Wo);
+    } else {
+      // strided view: output (a, b) lands at (y_off_h + a*y_mul, y_off_w + b*y_mul); rows/cols beyond y are dropped
+      UEGAN_CHECK(y.n == x.n && d.y_off_h >= 0 && d.y_off_w >= 0 && d.y_off_h < y.h && d.y_off_w < y.w && !d.mul,
+                  "conv: bad strided output view");
+      const int hv = (y.h - d.y_off_h + ymul - 1) / ymul, wv = (y.w - d.y_off_w + ymul - 1) / ymul;
+      if (p.Ho > hv) p.Ho = hv;
+      if (p.Wo > wv) p.Wo = wv;
+    }
     UEGAN_CHECK(d.cout % 16 == 0, "conv: NHWC output needs cout %% 16 == 0 (got %d)", d.cout);
     UEGAN_CHECK(d.y_c_off >= 0 && d.y_c_off + d.cout <= y.c && d.y_c_off % 8 == 0, "conv: bad channel slice");
     UEGAN_CHECK((y.c * dtype_size(y.dtype)) % 16 == 0, "conv: y.c misaligned");
@@ -515,8 +541,23 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
     p.out_pix = y.c;
     p.out_row = t_wp(y) * y.c;
     p.out_img = t_hp(y) * p.out_row;
-    const long long off = (long long)y.halo * p.out_row + (long long)y.halo * p.out_pix + d.y_c_off;
+    const long long off = (long long)(y.halo + d.y_off_h) * p.out_row + (long long)(y.halo + d.y_off_w) * p.out_pix +
+                          d.y_c_off;
+    p.out_pix *= ymul;
+    p.out_row *= ymul;
     p.out = static_cast<uint8_t*>(y.data) + off * dtype_size(y.dtype);
+    if (d.mask) {
+      const uegan_tensor& kt = *d.mask;
+      UEGAN_CHECK(dtype_ok(kt.dtype) && kt.n == y.n && kt.h == y.h && kt.w == y.w && kt.c >= d.cout && ymul == 1,
+                  "conv: mask tensor mismatch");
+      p.mask_pix = kt.c;
+      p.mask_row = t_wp(kt) * kt.c;
+      p.mask_img = t_hp(kt) * p.mask_row;
+      const long long koff = (long long)kt.halo * p.mask_row + (long long)kt.halo * p.mask_pix;
+      p.mask = static_cast<const uint8_t*>(kt.data) + koff * dtype_size(kt.dtype);
+      p.mask_kind = kt.dtype;
+      p.mask_act = d.mask_act;
+    }
     if (d.mul) {
       const uegan_tensor& mt = *d.mul;
       UEGAN_CHECK(mt.dtype == y.dtype && mt.n == y.n && mt.h == y.h && mt.w == y.w && mt.c >= d.cout,
@@ -616,10 +657,14 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 // weight packing: OIHW fp32 -> [cout_pad][k][row_pad] (row = (s, c) with c over the STORED channels of x)
 // ------------------------------------------------------------------------------------------
+// mode 0: fprop operand.  out[o][r][(s, c)] = w[o][cin_first + c][r][s]
+// mode 1: dgrad operand of a stride-`q` conv, parity class (pi, pj), packed kernel size k (= ceil(k_orig / q)):
+//         out[o][t_r][(t_s, c)] = w[c][cin_first + o][q*(k-1-t_r) + pi][q*(k-1-t_s) + pj]   (0 beyond k_orig)
+//         i.e. the roles of O and I are swapped and the taps run backwards (transposed convolution).
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin_total,
                                    int cin_first, int cin, int cin_stored, int k, int row_pad, int cout_pad,
-                                   int transpose_flip, long long total) {
+                                   int mode, int k_orig, int q, int pi, int pj, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int x = (int)(i % row_pad);
@@ -628,12 +673,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
   float v = 0.f;
   const int s = x / cin_stored, c = x % cin_stored;
   if (o < cout && s < k && c < cin) {
-    if (!transpose_flip) {
+    if (mode == 0) {
       v = w[(((long long)o * cin_total + cin_first + c) * k + r) * k + s];
     } else {
-      // dgrad operand: "output" channel o indexes the ORIGINAL input channels, c the original outputs;
-      // original weight layout is [c_orig_out = c][cin_total][k][k], taps rotated 180 degrees.
-      v = w[(((long long)c * cin_total + cin_first + o) * k + (k - 1 - r)) * k + (k - 1 - s)];
+      const int rr = q * (k - 1 - r) + pi, ss = q * (k - 1 - s) + pj;
+      if (rr < k_orig && ss < k_orig)
+        v = w[(((long long)c * cin_total + cin_first + o) * k_orig + rr) * k_orig + ss];
     }
   }
   if constexpr (sizeof(T) == 4) {
@@ -656,12 +701,11 @@ size_t uegan_packed_weight_bytes(int32_t cout, int32_t cin_stored, int32_t k, in
   return (size_t)g.cout_pad * k * g.row_pad * dtype_size(dtype);
 }
 
-int uegan_pack_conv_weight(const float* w_oihw, void* w_packed, int32_t cout, int32_t cin_total, int32_t cin_first,
-                           int32_t cin, int32_t cin_stored, int32_t k, int32_t dtype, int32_t transpose_flip,
-                           void* stream) {
+static int pack_impl(const float* w_oihw, void* w_packed, int cout, int cin_total, int cin_first, int cin,
+                     int cin_stored, int k, int dtype, int mode, int k_orig, int q, int pi, int pj, void* stream) {
   UEGAN_CHECK(w_oihw && w_packed, "pack_conv_weight: null pointer");
   UEGAN_CHECK(cin <= cin_stored, "pack_conv_weight: cin %d > stored %d", cin, cin_stored);
-  if (!transpose_flip) UEGAN_CHECK(cin_first + cin <= cin_total, "pack_conv_weight: channel range out of bounds");
+  UEGAN_CHECK(dtype_ok(dtype), "pack_conv_weight: bad dtype");
   const PackGeom g = pack_geom(cout, cin_stored, k, dtype);
   const long long total = (long long)g.cout_pad * k * g.row_pad;
   const int threads = 256;
@@ -669,18 +713,38 @@ int uegan_pack_conv_weight(const float* w_oihw, void* w_packed, int32_t cout, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == UEGAN_F32)
     pack_weight_kernel<float><<<blocks, threads, 0, st>>>(w_oihw, static_cast<float*>(w_packed), cout, cin_total,
-                                                          cin_first, cin, cin_stored, k, g.row_pad, g.cout_pad,
-                                                          transpose_flip, total);
+                                                          cin_first, cin, cin_stored, k, g.row_pad, g.cout_pad, mode,
+                                                          k_orig, q, pi, pj, total);
   else if (dtype == UEGAN_BF16)
     pack_weight_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), cout,
                                                                    cin_total, cin_first, cin, cin_stored, k, g.row_pad,
-                                                                   g.cout_pad, transpose_flip, total);
+                                                                   g.cout_pad, mode, k_orig, q, pi, pj, total);
   else
     pack_weight_kernel<__half><<<blocks, threads, 0, st>>>(w_oihw, static_cast<__half*>(w_packed), cout, cin_total,
-                                                           cin_first, cin, cin_stored, k, g.row_pad, g.cout_pad,
-                                                           transpose_flip, total);
+                                                           cin_first, cin, cin_stored, k, g.row_pad, g.cout_pad, mode,
+                                                           k_orig, q, pi, pj, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
+}
+
+int uegan_pack_conv_weight(const float* w_oihw, void* w_packed, int32_t cout, int32_t cin_total, int32_t cin_first,
+                           int32_t cin, int32_t cin_stored, int32_t k, int32_t dtype, int32_t transpose_flip,
+                           void* stream) {
+  if (!transpose_flip) UEGAN_CHECK(cin_first + cin <= cin_total, "pack_conv_weight: channel range out of bounds");
+  return pack_impl(w_oihw, w_packed, cout, cin_total, cin_first, cin, cin_stored, k, dtype, transpose_flip ? 1 : 0, k,
+                   1, 0, 0, stream);
+}
+
+int uegan_pack_conv_weight_dgrad(const float* w_oihw, void* w_packed, int32_t cout_orig, int32_t cin_total,
+                                 int32_t cin_first, int32_t cin, int32_t cout_stored, int32_t k_orig, int32_t stride,
+                                 int32_t pi, int32_t pj, int32_t dtype, void* stream) {
+  UEGAN_CHECK(stride == 1 || stride == 2, "pack_conv_weight_dgrad: stride %d", stride);
+  UEGAN_CHECK(cin_first + cin <= cin_total, "pack_conv_weight_dgrad: channel range out of bounds");
+  const int k = (k_orig + stride - 1) / stride;
+  // dgrad GEMM: "output" channels = the original input channels [cin_first, cin_first+cin), reduction over the
+  // original output channels (stored count cout_stored in the dz tensor)
+  return pack_impl(w_oihw, w_packed, cin, cin_total, cin_first, cout_orig, cout_stored, k, dtype, 1, k_orig, stride, pi,
+                   pj, stream);
 }
 
 int uegan_conv2d_fprop(const uegan_conv_desc* desc, void* stream) {

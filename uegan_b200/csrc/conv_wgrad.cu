@@ -1,0 +1,243 @@
+// Weight gradient of a convolution as a tcgen05 GEMM with BOTH operands MN-major (fp32 storage, kind::tf32):
+//   dW[o][c][r][s] = alpha * sum_{n,ho,wo} dz[n,ho,wo,o] * xpad[n, ho*stride + r, wo*stride + s, c]
+// (autograd of nn.Conv2d at models.py:83,94,162,174 -- `aten::convolution_backward`'s wgrad half).
+// GEMM view per filter tap (r, s):  D[M = Cout tile (128)][N = Cin chunk (<= 256)] += A^T B, K = output pixels.
+//   A = dz : NHWC, pixel-major  -> rows = pixels (K), 128-byte row = 32 channels (M)  == MN-major SWIZZLE_128B_ATOM_32B atoms
+//   B = x  : NHWC window shifted by the tap, same layout with N = 32-channel groups
+// One K stage = an 8x8 box of output pixels (64 rows): A = 4 TMA boxes {32 ch, 8, 8, 1} (M = 128), B = N/32 boxes;
+// 8 MMAs (K = 8 pixels = one swizzle atom of rows) per stage.  Channels beyond the tensor are TMA zero-fill, so
+// Cout < 128 costs no bandwidth.  Split-K over CTAs, fp32 atomics into the OIHW gradient (caller zeroes it).
+// Small-Cin layers (RGB stored as 4 channels, enc1 / d1) use the sliding-window map of the fprop kernel: N = the 32
+// (s, c) values of one filter row.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace uegan {
+
+constexpr int kWgStageRows = 64;                      // pixels per K stage
+constexpr int kWgBoxBytes = kWgStageRows * 128;       // one {32 ch x 64 px} box
+constexpr int kWgABytes = 4 * kWgBoxBytes;            // M = 128 channels
+
+struct WgradParams {
+  int tiles_w, tiles_h, nimg;      // 8x8 pixel tiles over (wo, ho, n)
+  int total_ktiles, ksplit;
+  int taps, k;                     // taps iterated by blockIdx.y: k*k, or k (filter rows) in window mode
+  int n_boxes;                     // N / 32
+  int num_stages, stage_bytes;
+  int window_mode;                 // 1: small-Cin sliding-window B map
+  int cout, cin, cin_total, cin_first, x_c;
+  int m_tiles, n_chunks;
+  float* dw;                       // OIHW fp32
+  const float* alpha;
+  float scale;
+  unsigned int* err_sink;
+};
+
+__global__ void __launch_bounds__(256, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[4];
+  __shared__ __align__(8) uint64_t empty_bar[4];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // work decomposition: blockIdx.x = k-split slice, blockIdx.y = tap, blockIdx.z = m_tile * n_chunks + n_chunk
+  const int tap = blockIdx.y;
+  const int mt = blockIdx.z / p.n_chunks, nc = blockIdx.z % p.n_chunks;
+  const int per = (p.total_ktiles + p.ksplit - 1) / p.ksplit;
+  const int kt0 = blockIdx.x * per;
+  const int kt1 = min(kt0 + per, p.total_ktiles);
+  const int r = p.window_mode ? tap : tap / p.k, s_ = p.window_mode ? 0 : tap % p.k;
+  const int N = p.n_boxes * 32;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 256);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (kt0 < kt1) {
+    if (warp == 0) {
+      if (elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx = kWgABytes + p.n_boxes * kWgBoxBytes;
+        for (int kt = kt0; kt < kt1; ++kt) {
+          const int wo0 = (kt % p.tiles_w) * 8;
+          const int ho0 = ((kt / p.tiles_w) % p.tiles_h) * 8;
+          const int n = kt / (p.tiles_w * p.tiles_h);
+          mbar_wait(&empty_bar[stage], phase ^ 1, 0x600 + stage, p.err_sink);
+          uint8_t* sa = smem + stage * p.stage_bytes;
+          uint8_t* sb = sa + kWgABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx);
+          for (int g = 0; g < 4; ++g)
+            tma_load_4d(&tmA, &full_bar[stage], sa + g * kWgBoxBytes, mt * 128 + g * 32, wo0, ho0, n);
+          // B map = the fprop sliding-window map {window, wo, r, ho, n}: tap column s and channel offset are both
+          // positions inside the window of k*C contiguous (s, c) values that starts at the pixel
+          for (int g = 0; g < p.n_boxes; ++g)
+            tma_load_5d(&tmB, &full_bar[stage], sb + g * kWgBoxBytes, s_ * p.x_c + nc * N + g * 32, wo0, r, ho0, n);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        const uint32_t idesc = make_instr_desc(UMMA_TF32, 128, N, /*a_mn_major=*/1, /*b_mn_major=*/1);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t first = 0;
+        for (int kt = kt0; kt < kt1; ++kt) {
+          mbar_wait(&full_bar[stage], phase, 0x700 + stage, p.err_sink);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
+          const uint32_t b_addr = a_addr + kWgABytes;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {  // 8 pixels (one 1024-byte atom of rows) per MMA
+            // MN-major tf32 operands exist only in the SWIZZLE_128B_BASE32B layout (32-byte chunks XORed with row & 3,
+            // 4-row atoms; cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem
+            // layout"): LBO = stride between 32-channel groups (one TMA box), SBO = stride between 4-row groups.
+            const uint64_t da = make_smem_desc(a_addr + ks * 1024, kWgBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
+            const uint64_t db = make_smem_desc(b_addr + ks * 1024, kWgBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
+            umma_ss<1>(tmem_base, da, db, idesc, first);
+            first = 1;
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&done_bar);
+      }
+    } else if (warp >= 4) {
+      // epilogue: D[o][j] -> atomicAdd into dW (OIHW)
+      const int q = warp & 3;
+      mbar_wait(&done_bar, 0, 0x800, p.err_sink);
+      tcgen05_fence_after();
+      const int o = mt * 128 + q * 32 + lane;
+      const float sc = p.scale * (p.alpha ? __ldg(p.alpha) : 1.f);
+      const int kk = p.k * p.k;
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t rr[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, rr);
+        tmem_ld_wait();
+        if (o >= p.cout) continue;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int j = c0 + i;
+          int c, ss;
+          if (p.window_mode) { ss = j >> 2; c = j & 3; }  // window column = (s, c) with 4 stored channels
+          else { ss = s_; c = nc * N + j; }
+          if (c < p.cin && ss < p.k) {
+            const float v = __uint_as_float(rr[i]) * sc;
+            atomicAdd(p.dw + ((long long)o * p.cin_total + p.cin_first + c) * kk + r * p.k + ss, v);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------
+// CUDA-core fallback for tiny spatial extents is not needed: TMA zero-fill covers partial tiles.
+// ------------------------------------------------------------------------------------------
+
+}  // namespace uegan
+
+using namespace uegan;
+
+extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz, int32_t cout, int32_t cin,
+                                  int32_t cin_total, int32_t cin_first, int32_t k, int32_t stride, int32_t pad,
+                                  float* dw_oihw, const float* alpha_dev, float scale, void* stream) {
+  UEGAN_CHECK(x && dz && x->data && dz->data && dw_oihw, "conv2d_wgrad: null pointer");
+  UEGAN_CHECK(x->dtype == UEGAN_F32 && dz->dtype == UEGAN_F32, "conv2d_wgrad: fp32 (tf32) tensors only");
+  UEGAN_CHECK(stride == 1 || stride == 2, "conv2d_wgrad: stride %d", stride);
+  UEGAN_CHECK(pad <= x->halo && k >= 1 && k <= 7, "conv2d_wgrad: bad pad/k");
+  const int Ho = (x->h + 2 * pad - k) / stride + 1, Wo = (x->w + 2 * pad - k) / stride + 1;
+  UEGAN_CHECK(dz->n == x->n && dz->h == Ho && dz->w == Wo, "conv2d_wgrad: dz is %dx%dx%d, expected %dx%dx%d", dz->n,
+              dz->h, dz->w, x->n, Ho, Wo);
+  UEGAN_CHECK(cout <= dz->c && cin <= x->c && cin_first + cin <= cin_total, "conv2d_wgrad: channel mismatch");
+  UEGAN_CHECK((dz->c * 4) % 128 == 0, "conv2d_wgrad: dz must store a multiple of 32 channels (got %d)", dz->c);
+  const bool window = (x->c == 4);
+  UEGAN_CHECK(window || (x->c * 4) % 128 == 0, "conv2d_wgrad: x must store 4 or a multiple of 32 channels (got %d)", x->c);
+
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.tiles_w = (Wo + 7) / 8;
+  p.tiles_h = (Ho + 7) / 8;
+  p.nimg = x->n;
+  p.total_ktiles = p.tiles_w * p.tiles_h * p.nimg;
+  p.k = k;
+  p.window_mode = window;
+  p.taps = window ? k : k * k;
+  p.cout = cout; p.cin = cin; p.cin_total = cin_total; p.cin_first = cin_first;
+  p.m_tiles = (cout + 127) / 128;
+  int N;
+  if (window) {
+    UEGAN_CHECK(k * 4 <= 32, "conv2d_wgrad: window mode needs k*4 <= 32");
+    N = 32; p.n_chunks = 1;
+  } else {
+    const int cpad = (cin + 31) / 32 * 32;
+    N = cpad < 256 ? cpad : 256;
+    p.n_chunks = (cpad + N - 1) / N;
+  }
+  p.n_boxes = N / 32;
+  p.stage_bytes = kWgABytes + p.n_boxes * kWgBoxBytes;
+  p.num_stages = (200 * 1024) / p.stage_bytes;
+  if (p.num_stages > 4) p.num_stages = 4;
+  UEGAN_CHECK(p.num_stages >= 2, "conv2d_wgrad: stage too large");
+  const int groups = p.taps * p.m_tiles * p.n_chunks;
+  int ksplit = (2 * num_sms() + groups - 1) / groups;
+  if (ksplit > p.total_ktiles) ksplit = p.total_ktiles;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = ksplit;
+  p.dw = dw_oihw;
+  p.alpha = alpha_dev;
+  p.scale = scale;
+  p.err_sink = error_sink_device();
+
+  p.x_c = x->c;
+  CUtensorMap tmA, tmB;
+  {  // dz interior: {c, wo, ho, n}; coordinates beyond the interior / beyond Cout are zero-filled
+    const uint64_t pix = (uint64_t)dz->c * 4, row = (uint64_t)t_wp(*dz) * pix, img = (uint64_t)t_hp(*dz) * row;
+    uint8_t* base = static_cast<uint8_t*>(dz->data) + (uint64_t)dz->halo * row + (uint64_t)dz->halo * pix;
+    uint64_t dims[4] = {(uint64_t)dz->c, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)dz->n};
+    uint64_t strides[3] = {pix, row, img};
+    uint32_t box[4] = {32u, 8u, 8u, 1u};
+    if (encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return -1;
+  }
+  {  // x: sliding-window map {window, wo, r, ho, n} (conv_fprop.cu)
+    const uint64_t pix = (uint64_t)x->c * 4, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
+    uint8_t* base = static_cast<uint8_t*>(x->data) + (uint64_t)(x->halo - pad) * row + (uint64_t)(x->halo - pad) * pix;
+    const uint64_t win = window ? 32u : (uint64_t)k * x->c;
+    uint64_t dims[5] = {win, (uint64_t)Wo, (uint64_t)k, (uint64_t)Ho, (uint64_t)x->n};
+    uint64_t strides[4] = {(uint64_t)stride * pix, row, (uint64_t)stride * row, img};
+    uint32_t box[5] = {32u, 8u, 1u, 8u, 1u};
+    if (encode_tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return -1;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    UEGAN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    attr_set = true;
+  }
+  const int smem_bytes = p.num_stages * p.stage_bytes + 1024;
+  dim3 grid((unsigned)p.ksplit, (unsigned)p.taps, (unsigned)(p.m_tiles * p.n_chunks));
+  conv_wgrad_kernel<<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}

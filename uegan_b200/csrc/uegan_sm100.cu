@@ -4,4 +4,6 @@
 #include "elementwise.cu"
 #include "spectral.cu"
 #include "losses.cu"
+#include "backward.cu"
+#include "conv_wgrad.cu"
 #include "probe.cu"

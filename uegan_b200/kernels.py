@@ -240,3 +240,125 @@ def msrec_loss(pred: torch.Tensor, gt: torch.Tensor, rec_type: int, scales: int,
                                       loss.data_ptr(), grad.data_ptr() if grad is not None else None,
                                       float(grad_scale), _stream()), "msrec_loss")
     _count(2)
+
+
+# ------------------------------------------------------------------------------------------------
+# backward
+# ------------------------------------------------------------------------------------------------
+def packed_weight_dgrad(weight: torch.Tensor, cout_stored: int, dtype: int, stride: int = 1, pi: int = 0, pj: int = 0,
+                        cin_first: int = 0, cin: Optional[int] = None) -> torch.Tensor:
+    """Operand of the data-gradient GEMM of a conv with `weight` (OIHW): see uegan_pack_conv_weight_dgrad."""
+    lib = L.load()
+    w = weight.detach()
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+    o, i_total, k, _ = w.shape
+    if cin is None:
+        cin = i_total - cin_first
+    kq = (k + stride - 1) // stride
+    nbytes = lib.uegan_packed_weight_bytes(cin, cout_stored, kq, dtype)
+    buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
+    L.check(lib.uegan_pack_conv_weight_dgrad(w.data_ptr(), buf.data_ptr(), o, i_total, cin_first, cin, cout_stored, k,
+                                             stride, pi, pj, dtype, _stream()), "pack_conv_weight_dgrad")
+    _count(1)
+    return buf
+
+
+def conv_generic(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, pad: int, y: NHWC, y_c_off: int = 0,
+                 bias=None, alpha=None, act: int = L.ACT_NONE, mask: Optional[NHWC] = None, mask_act: int = L.ACT_NONE,
+                 y_mul: int = 1, y_off_h: int = 0, y_off_w: int = 0):
+    """conv_fprop with the dgrad-only options (activation-derivative mask, strided output view)."""
+    lib = L.load()
+    d = L.ConvDesc()
+    d.x, d.y = x.ct, y.ct
+    d.y_c_off, d.cout, d.k, d.stride, d.pad, d.act = y_c_off, cout, k, stride, pad, act
+    d.w_packed = w_packed.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.alpha = alpha.data_ptr() if alpha is not None else None
+    d.mask = C.pointer(mask.ct) if mask is not None else None
+    d.mask_act = mask_act
+    d.y_mul, d.y_off_h, d.y_off_w = y_mul, y_off_h, y_off_w
+    L.check(lib.uegan_conv2d_fprop(C.byref(d), _stream()), "conv2d (dgrad)")
+    _count(1)
+
+
+def conv_dgrad(dz: NHWC, weight: torch.Tensor, k: int, stride: int, dxp: NHWC, cache=None, key=None, alpha=None,
+               cin_first: int = 0, cin: Optional[int] = None, mask: Optional[NHWC] = None, mask_act: int = L.ACT_NONE):
+    """Data gradient of y = conv(xpad, weight, stride) w.r.t. the PADDED input: dxp (extent of xpad, halo 0).
+    dz: output gradient with a zero halo of ceil(k/stride) - 1.  stride 2 = four parity-class launches."""
+    kq = (k + stride - 1) // stride
+    assert dz.halo >= kq - 1, "dz needs a zero halo of ceil(k/stride)-1"
+    cin_n = (weight.shape[1] - cin_first) if cin is None else cin
+    for pi in range(stride):
+        for pj in range(stride):
+            fn = lambda: packed_weight_dgrad(weight, dz.c, dz.dtype, stride, pi, pj, cin_first, cin)
+            wp = cache.get((key, "dg", pi, pj, dz.dtype), weight, fn) if cache is not None else fn()
+            conv_generic(dz, wp, cin_n, kq, 1, kq - 1, dxp, 0, None, alpha, L.ACT_NONE, mask, mask_act,
+                         y_mul=stride, y_off_h=pi, y_off_w=pj)
+
+
+def conv_wgrad(x: NHWC, dz: NHWC, dw: torch.Tensor, k: int, stride: int, pad: int, cin_first: int = 0,
+               cin: Optional[int] = None, alpha=None, scale: float = 1.0):
+    """dw (OIHW fp32, pre-zeroed or accumulating) += scale * alpha * wgrad(x, dz)."""
+    cout, cin_total = dw.shape[0], dw.shape[1]
+    cin_n = (cin_total - cin_first) if cin is None else cin
+    assert dw.is_cuda and dw.dtype == torch.float32 and dw.is_contiguous()
+    L.check(L.load().uegan_conv2d_wgrad(x.ref(), dz.ref(), cout, cin_n, cin_total, cin_first, k, stride, pad,
+                                        dw.data_ptr(), alpha.data_ptr() if alpha is not None else None, float(scale),
+                                        _stream()), "conv2d_wgrad")
+    _count(1)
+
+
+def head_bwd(dout: torch.Tensor, out: torch.Tensor, x, mode: int, dz: NHWC):
+    assert dout.is_contiguous() and out.is_contiguous() and dout.dtype == torch.float32
+    L.check(L.load().uegan_head_bwd(dout.data_ptr(), out.data_ptr(), x.data_ptr() if x is not None else None,
+                                    dout.shape[1], mode, dz.ref(), _stream()), "head_bwd")
+    _count(1)
+
+
+def grad_combine(dst: NHWC, channels: int, src_a: Optional[NHWC] = None, pad_a: int = 0, pad_mode_a: int = L.PAD_REFLECT,
+                 add_b: Optional[NHWC] = None, add_c: Optional[NHWC] = None, mask: Optional[NHWC] = None,
+                 act: int = L.ACT_NONE, mul: Optional[NHWC] = None, dst_c_off: int = 0, a_c_off: int = 0, b_c_off: int = 0,
+                 c_c_off: int = 0, mask_c_off: int = 0, mul_c_off: int = 0):
+    r = lambda t: t.ref() if t is not None else None
+    L.check(L.load().uegan_grad_combine(dst.ref(), dst_c_off, channels, r(src_a), a_c_off, pad_a, pad_mode_a, r(add_b),
+                                        b_c_off, r(add_c), c_c_off, r(mask), mask_c_off, act, r(mul), mul_c_off,
+                                        _stream()), "grad_combine")
+    _count(1)
+
+
+def channel_sum(src: NHWC, out: torch.Tensor, c_off: int = 0, channels: Optional[int] = None):
+    channels = out.numel() if channels is None else channels
+    assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
+    L.check(L.load().uegan_channel_sum(src.ref(), c_off, channels, out.data_ptr(), _stream()), "channel_sum")
+    _count(1)
+
+
+def instance_norm_bwd(dout: NHWC, d_c_off: int, z: NHWC, mean_rstd: int, dz: NHWC, ws: torch.Tensor):
+    assert ws.dtype == torch.float64 and ws.numel() >= 2 * z.n * z.c
+    L.check(L.load().uegan_instance_norm_bwd(dout.ref(), d_c_off, z.ref(), mean_rstd, dz.ref(), ws.data_ptr(),
+                                             _stream()), "instance_norm_bwd")
+    _count(2)
+
+
+def upsample2x_bwd(dout: NHWC, d_c_off: int, dsrc: NHWC):
+    L.check(L.load().uegan_upsample2x_bwd(dout.ref(), d_c_off, dsrc.ref(), _stream()), "upsample2x_bwd")
+    _count(1)
+
+
+def maxpool2x2_bwd(src: NHWC, dpool: NHWC, dsrc: NHWC):
+    L.check(L.load().uegan_maxpool2x2_bwd(src.ref(), dpool.ref(), dsrc.ref(), _stream()), "maxpool2x2_bwd")
+    _count(1)
+
+
+def in_mse_bwd(x: NHWC, y: NHWC, mr_x: int, mr_y: int, weight: float, gscale, deep: Optional[NHWC], dx: NHWC,
+               ws: torch.Tensor):
+    L.check(L.load().uegan_in_mse_bwd(x.ref(), y.ref(), mr_x, mr_y, float(weight),
+                                      gscale.data_ptr() if gscale is not None else None,
+                                      deep.ref() if deep is not None else None, dx.ref(), ws.data_ptr(), _stream()),
+            "in_mse_bwd")
+    _count(2)
+
+
+def unpack_input_grad(dx: NHWC, scale, out: torch.Tensor):
+    L.check(L.load().uegan_unpack_input_grad(dx.ref(), L.float3(scale), out.data_ptr(), _stream()), "unpack_input_grad")
+    _count(1)
