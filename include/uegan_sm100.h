@@ -62,6 +62,7 @@ typedef struct uegan_conv_desc {
   const uegan_tensor* mul;     /* optional: y *= mul[n,ho,wo,co] after the activation (y4.mul(x1), models.py:70) */
   float* out_nchw;             /* optional planar fp32 output, see above */
   const float* residual_nchw;  /* optional, with out_nchw */
+  float* aux_nchw;             /* optional, with out_nchw: act(.) before the residual / clamp (saved for backward) */
   int32_t y_mul;               /* 0/1: dense output.  2: output (a, b) is written at (y_off_h + 2a, y_off_w + 2b) of y
                                   (one parity class of the dgrad of a stride-2 conv per launch) */
   int32_t y_off_h, y_off_w;
@@ -143,10 +144,11 @@ int uegan_gan_loss_bwd(int32_t mode, int32_t for_discriminator, int32_t nscales,
 int uegan_in_mse_fwd(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
                      float weight, double* accum, float* loss_inout, void* stream);
 /* MultiscaleRecLoss.forward (losses.py:219-231) on fp32 NCHW images: type 0 l1, 1 smoothl1, 2 l2; scales 1..3 with
- * weights 1, 1/2, 1/4 and AvgPool2d(2) between scales.  If grad_nchw != NULL also writes grad_scale * dloss/dpred. */
+ * weights 1, 1/2, 1/4 and AvgPool2d(2) between scales.  If grad_nchw != NULL also writes
+ * grad_scale * (gscale_dev ? *gscale_dev : 1) * dloss/dpred. */
 int uegan_msrec_loss(const float* pred_nchw, const float* gt_nchw, int32_t n, int32_t c, int32_t h, int32_t w,
                      int32_t type, int32_t scales, double* accum, float* loss_out, float* grad_nchw, float grad_scale,
-                     void* stream);
+                     const float* gscale_dev, void* stream);
 /* Per-(n,c) InstanceNorm statistics only: stats_ws gets [n][c][2] sums (doubles) followed by n*c (mean, rstd) float
  * pairs; with sums_ready != 0 the sums are taken as already accumulated (conv_desc.in_stats) and only finalised.
  * Returns the device pointer of the (mean, rstd) pairs in *mean_rstd_out. */
@@ -178,15 +180,21 @@ int uegan_instance_norm_bwd(const uegan_tensor* dout, int32_t d_c_off, const ueg
                             const uegan_tensor* dz, double* ws, void* stream);
 /* Adjoint of uegan_upsample2x: dsrc = up^T(dout[.., d_c_off : d_c_off + dsrc.c]). */
 int uegan_upsample2x_bwd(const uegan_tensor* dout, int32_t d_c_off, const uegan_tensor* dsrc, void* stream);
-/* MaxPool2d(2,2) backward fused with the ReLU mask of the pooled activation (fp16 activations, bf16 gradients). */
+/* MaxPool2d(2,2) backward fused with the ReLU mask of the pooled activation (fp16 activations and gradients). */
 int uegan_maxpool2x2_bwd(const uegan_tensor* src, const uegan_tensor* dpool, const uegan_tensor* dsrc, void* stream);
 /* Backward of one PerceptualLoss term w.r.t. the fp16 feature map x (+ optional gradient from deeper layers, then
- * the tap's own ReLU mask): dx (bf16, zero halo).  Upstream scale = weight * (gscale_dev ? *gscale_dev : 1). */
+ * the tap's own ReLU mask): dx (fp16, zero halo).  Upstream scale = weight * (gscale_dev ? *gscale_dev : 1); the
+ * caller folds a loss scale into `weight` (and divides it out in uegan_unpack_input_grad) to stay inside fp16's range. */
 int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
                      float weight, const float* gscale_dev, const uegan_tensor* deep, const uegan_tensor* dx, double* ws,
                      void* stream);
 /* Gradient of uegan_pack_input: NHWC (first 3 channels) -> NCHW fp32 times scale_host[c]. */
 int uegan_unpack_input_grad(const uegan_tensor* dx, const float* scale_host, float* dst_nchw, void* stream);
+
+/* Backward of spectral normalisation through sigma (u, v constant, torch spectral_norm semantics): in place on
+ * grad_inout = (dL/dW_sn)/sigma (rows x cols): grad -= (<grad, W>/sigma) u v^T.  sigma = {sigma, 1/sigma}; ws: 1 double. */
+int uegan_spectral_bwd(float* grad_inout, const float* w, const float* u, const float* v, const float* sigma,
+                       int32_t rows, int32_t cols, double* ws, void* stream);
 
 /* Hardware probe used by tests/DESIGN.md: runs a 128xNx(32*kchunks) tf32 GEMM whose A operand is read from a
  * shared-memory window shifted by `row_shift` 128-byte rows with the given descriptor base_offset; see

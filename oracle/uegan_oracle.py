@@ -306,7 +306,7 @@ def vgg19_taps(vp: Params, x: Tensor, last: str = "relu5_1") -> Dict[str, Tensor
     return taps
 
 
-def perceptual_loss(vp: Params, x: Tensor, y: Tensor) -> Tensor:
+def perceptual_loss(vp: Params, x: Tensor, y: Tensor, eps: float = 1e-5) -> Tensor:
     """PerceptualLoss.__call__ (losses.py:22-36); x, y in [0,1]."""
     if x.shape[1] != 3:
         x, y = x.repeat(1, 3, 1, 1), y.repeat(1, 3, 1, 1)
@@ -316,7 +316,7 @@ def perceptual_loss(vp: Params, x: Tensor, y: Tensor) -> Tensor:
     weights = [1.0 / 64, 1.0 / 64, 1.0 / 32, 1.0 / 32, 1.0]
     loss = 0
     for wgt, k in zip(weights, ("relu1_1", "relu2_1", "relu3_1", "relu4_1", "relu5_1")):
-        loss = loss + wgt * F.mse_loss(instance_norm(xv[k]), instance_norm(yv[k]))
+        loss = loss + wgt * F.mse_loss(instance_norm(xv[k], eps), instance_norm(yv[k], eps))
     return loss
 
 

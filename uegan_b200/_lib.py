@@ -30,7 +30,7 @@ class ConvDesc(C.Structure):
     _fields_ = [("x", Tensor), ("y", Tensor), ("y_c_off", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32),
                 ("stride", C.c_int32), ("pad", C.c_int32), ("act", C.c_int32), ("w_packed", C.c_void_p),
                 ("bias", C.c_void_p), ("alpha", C.c_void_p), ("mul", C.POINTER(Tensor)), ("out_nchw", C.c_void_p),
-                ("residual_nchw", C.c_void_p), ("y_mul", C.c_int32), ("y_off_h", C.c_int32), ("y_off_w", C.c_int32),
+                ("residual_nchw", C.c_void_p), ("aux_nchw", C.c_void_p), ("y_mul", C.c_int32), ("y_off_h", C.c_int32), ("y_off_w", C.c_int32),
                 ("mask", C.POINTER(Tensor)), ("mask_act", C.c_int32), ("in_stats", C.c_void_p)]
 
 
@@ -62,7 +62,9 @@ SYMBOLS = {
     "uegan_in_mse_fwd": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "uegan_msrec_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "uegan_spectral_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p]),
     "uegan_pack_conv_weight_dgrad": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 10 + [C.c_void_p]),
     "uegan_conv2d_wgrad": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor)] + [C.c_int32] * 7 +
                            [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),

@@ -1,14 +1,554 @@
-"""Training path (torch.autograd.Function wrappers over the fprop / dgrad / wgrad kernels).
+"""Training path: torch.autograd.Function wrappers whose forward AND backward run on the sm_100a kernels.
 
-Not built yet in this round: the forward-only (inference) path is native; calling the Generator or the
-Discriminator with gradients enabled raises instead of silently falling back to PyTorch ops."""
+torch.autograd is only the OUTER tape (it sequences `d_loss.backward()` / `g_loss.backward()` of trainer.py:96,117
+and accumulates parameter `.grad`s); every tensor operation below is a call into libuegan_sm100.so:
+  fprop   conv_fprop_kernel            dgrad  the same kernel on the transposed/rotated operand (4 parity launches
+  wgrad   conv_wgrad_kernel (tcgen05, MN-major tf32)                                      for stride-2 convs)
+plus the HBM-bound backward kernels of csrc/backward.cu.  Reference: autograd of models.py:44-74, 139-155 and
+losses.py:22-36, 219-231, 348-377 (`aten::convolution_backward`, reflection_pad2d_backward, native_batch_norm_backward,
+upsample_bilinear2d_backward, ...).
+
+Dead parameters: GAM's attention branch (ga*.conv.0/.2), the second half of ga*.fuse.0.weight and ga*.fuse.0.bias only
+shift the input of an InstanceNorm by a per-(n,c) constant; their true gradient is exactly zero (the
+reference produces rounding noise of ~1e-5 there) and zeros are returned.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from . import kernels as K
+
+F32 = L.F32
+
+
+class _Scratch:
+    """Gradient scratch buffers, reused across calls (backward passes run one at a time)."""
+
+    def __init__(self):
+        self.store = {}
+
+    def get(self, name, n, h, w, c, halo=0, dtype=F32, device="cuda", zero=False):
+        key = (name, n, h, w, c, halo, dtype, str(device))
+        t = self.store.get(key)
+        if t is None:
+            t = K.NHWC(n, h, w, c, halo, dtype, device, zero=zero)
+            self.store[key] = t
+        return t
+
+
+_scratch = _Scratch()
+
+
+def _zeros_like(p):
+    return torch.zeros_like(p, memory_format=torch.contiguous_format)
+
+
+# =================================================================================================
+# Generator
+# =================================================================================================
+def _g_workspace(G, b, h, w, dev):
+    d = G.conv_dim
+    T = lambda hh, ww, c, halo=0, zero=False: K.NHWC(b, hh, ww, c, halo, F32, dev, zero)
+    f64 = lambda n: torch.empty(n, dtype=torch.float64, device=dev)
+    chs = [8 * d, 4 * d, 2 * d, d]
+    res = [(h // 8, w // 8), (h // 4, w // 4), (h // 2, w // 2), (h, w)]
+    return dict(
+        x0=T(h, w, 4, 3, True), x1=T(h, w, d, 1), x2=T(h // 2, w // 2, 2 * d, 1), x3=T(h // 4, w // 4, 4 * d, 1),
+        x4=T(h // 8, w // 8, 8 * d, 1), x5=T(h // 16, w // 16, 16 * d),
+        z5=T(h // 16, w // 16, 16 * d), x5n=T(h // 16, w // 16, 16 * d), st5=f64(3 * b * 16 * d),
+        u=[T(r[0] // 2, r[1] // 2, c) for r, c in zip(res, chs)],
+        cat=[T(r[0], r[1], 2 * c, 1) for r, c in zip(res, chs)],
+        z=[T(r[0], r[1], c) for r, c in zip(res, chs)],
+        st=[f64(3 * b * c) for c in chs],
+        y=[T(r[0], r[1], c) for r, c in zip(res, chs)],
+        y4m=T(h, w, d, 1), t=T(h, w, d, 3),
+        res=torch.empty(b, 3, h, w, dtype=torch.float32, device=dev),
+        mr={},
+    )
+
+
+def _gam_forward(G, name, ga, src, ch, z, dst, off, stats, ws):
+    fuse = ga.fuse[0]
+    wp = G._wcache.get(name, fuse.weight, lambda: K.packed_weight(fuse.weight, src.c, F32, 0, ch))
+    if K.fused_stats_ok(src.h, src.w):
+        K.conv_fprop(src, wp, ch, 1, 1, 0, z, in_stats=stats)
+        K.instance_norm_apply(z, dst, off, stats)
+        ws["mr"][name] = stats.data_ptr() + 2 * src.n * ch * 8
+    else:
+        K.conv_fprop(src, wp, ch, 1, 1, 0, z)
+        K.instance_norm(z, dst, off, stats)
+        ws["mr"][name] = stats.data_ptr() + 2 * src.n * ch * 8
+
+
+def _g_layers(G):
+    d = G.conv_dim
+    ups = [G.upsample1[1], G.upsample2[1], G.upsample3[1], G.upsample4[1]]
+    gas = [G.ga4, G.ga3, G.ga2, G.ga1]
+    decs = [G.dec1, G.dec2, G.dec3, G.dec4]
+    return d, ups, gas, decs
+
+
+def _g_forward_train(G, x, ws):
+    d, ups, gas, decs = _g_layers(G)
+    act = G._act
+    P = ws
+
+    def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE):
+        cv = holder.conv
+        K.conv_fprop(src, G._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, 0, cv.bias, None, act_)
+
+    K.pack_input(x, P["x0"], L.PAD_REFLECT)
+    conv(P["x0"], "enc1", G.enc1, d, 7, 1, P["x1"], act); K.halo_fill(P["x1"])
+    conv(P["x1"], "enc2", G.enc2, 2 * d, 3, 2, P["x2"], act); K.halo_fill(P["x2"])
+    conv(P["x2"], "enc3", G.enc3, 4 * d, 3, 2, P["x3"], act); K.halo_fill(P["x3"])
+    conv(P["x3"], "enc4", G.enc4, 8 * d, 3, 2, P["x4"], act); K.halo_fill(P["x4"])
+    conv(P["x4"], "enc5", G.enc5, 16 * d, 3, 2, P["x5"], act)
+    _gam_forward(G, "ga5", G.ga5, P["x5"], 16 * d, P["z5"], P["x5n"], 0, P["st5"], ws)
+    src = P["x5n"]
+    skips = [P["x4"], P["x3"], P["x2"], P["x1"]]
+    for i in range(4):
+        ch = P["u"][i].c
+        conv(src, f"upsample{i+1}", ups[i], ch, 1, 1, P["u"][i])
+        K.upsample2x(P["u"][i], P["cat"][i], 0)
+        _gam_forward(G, f"ga{4-i}", gas[i], skips[i], ch, P["z"][i], P["cat"][i], ch, P["st"][i], ws)
+        K.halo_fill(P["cat"][i])
+        conv(P["cat"][i], f"dec{i+1}", decs[i], ch, 3, 1, P["y"][i], act)
+        src = P["y"][i]
+    K.grad_combine(P["y4m"], d, add_b=P["y"][3], mul=P["x1"])  # y4.mul(x1), models.py:70 (y4 itself is kept for backward)
+    K.halo_fill(P["y4m"])
+    conv(P["y4m"], "dec5.0", G.dec5[0], d, 3, 1, P["t"]); K.halo_fill(P["t"])
+    out = torch.empty_like(x)
+    cv = G.dec5[1].conv
+    K.conv_fprop(P["t"], G._w("dec5.1", cv, d), 3, 7, 1, 3, None, 0, cv.bias, None, L.ACT_TANH, None, out, x,
+                 aux_nchw=P["res"])
+    return out
+
+
+def _g_backward(G, x, out_grad, ws, need_dx):
+    d, ups, gas, decs = _g_layers(G)
+    P = ws
+    b, _, h, w = x.shape
+    dev = x.device
+    S = lambda name, hh, ww, c, halo=0: _scratch.get(name, b, hh, ww, c, halo, F32, dev)
+    grads = {}
+    cache = G._wcache
+    act = G._act
+
+    def wgrad(name, conv, xin, dz, k, stride, pad, cin_first=0, cin=None, bias_from=None):
+        gw = _zeros_like(conv.weight)
+        K.conv_wgrad(xin, dz, gw, k, stride, pad, cin_first=cin_first, cin=cin)
+        grads[name + ".weight"] = gw
+        if bias_from is not None and conv.bias is not None:
+            gb = torch.empty_like(conv.bias)
+            K.channel_sum(bias_from, gb)
+            grads[name + ".bias"] = gb
+
+    # ---- dec5.1 + tanh + clamp(res + x)   (models.py:34-35, 72)
+    dz5 = S("dz5", h, w, 4, 6)
+    dz5w = S("dz5w", h, w, 32, 0)
+    K.head_bwd(out_grad, P["res"], x, 2, dz5)
+    K.head_bwd(out_grad, P["res"], x, 2, dz5w)
+    c51 = G.dec5[1].conv
+    wgrad("dec5.1.main.1", c51, P["t"], dz5w, 7, 1, 3)
+    gb = torch.empty_like(c51.bias); K.channel_sum(dz5, gb, 0, 3); grads["dec5.1.main.1.bias"] = gb
+    dxp = S("dxp_t", h + 6, w + 6, d)
+    K.conv_dgrad(dz5, c51.weight, 7, 1, dxp, cache, "dec5.1")
+    dt = S("dt", h, w, d, 2)
+    K.grad_combine(dt, d, src_a=dxp, pad_a=3)
+    # ---- dec5.0 (no activation)
+    c50 = G.dec5[0].conv
+    wgrad("dec5.0.main.1", c50, P["y4m"], dt, 3, 1, 1, bias_from=dt)
+    dxp2 = S("dxp_y4m", h + 2, w + 2, d)
+    K.conv_dgrad(dt, c50.weight, 3, 1, dxp2, cache, "dec5.0")
+    # y4m = y4 * x1 ;  y4 = act(z4)
+    dz = S("dz_dec3", h, w, d, 2)
+    K.grad_combine(dz, d, src_a=dxp2, pad_a=1, mul=P["x1"], mask=P["y"][3], act=act)
+    dx1a = S("dx1a", h, w, d)
+    K.grad_combine(dx1a, d, src_a=dxp2, pad_a=1, mul=P["y"][3])
+    # ---- decoder stages 4..1
+    skips = [P["x4"], P["x3"], P["x2"], P["x1"]]
+    dskip = [None] * 4
+    srcs = [P["x5n"], P["y"][0], P["y"][1], P["y"][2]]
+    d_x5n = None
+    for i in (3, 2, 1, 0):
+        ch = P["u"][i].c
+        hh, ww = P["y"][i].h, P["y"][i].w
+        dec, up, ga = decs[i].conv, ups[i].conv, gas[i].fuse[0]
+        wgrad(f"dec{i+1}.main.1", dec, P["cat"][i], dz, 3, 1, 1, bias_from=dz)
+        dxpc = S(f"dxp_cat{i}", hh + 2, ww + 2, 2 * ch)
+        K.conv_dgrad(dz, dec.weight, 3, 1, dxpc, cache, f"dec{i+1}")
+        dcat = S(f"dcat{i}", hh, ww, 2 * ch)
+        K.grad_combine(dcat, 2 * ch, src_a=dxpc, pad_a=1)
+        # first half: bilinear x2 of the (hoisted) 1x1 conv
+        du = S(f"du{i}", hh // 2, ww // 2, ch)
+        K.upsample2x_bwd(dcat, 0, du)
+        wgrad(f"upsample{i+1}.1.main.1", up, srcs[i], du, 1, 1, 0, bias_from=du)
+        dsrc = S(f"dsrc{i}", hh // 2, ww // 2, 2 * ch)
+        K.conv_dgrad(du, up.weight, 1, 1, dsrc, cache, f"upsample{i+1}")
+        # second half: InstanceNorm(conv1x1(skip, fuse.weight[:, :ch]))
+        dzs = S(f"dzs{i}", hh, ww, ch)
+        K.instance_norm_bwd(dcat, ch, P["z"][i], P["mr"][f"ga{4-i}"], dzs,
+                            torch.empty(2 * b * ch, dtype=torch.float64, device=dev))
+        gname = f"ga{4-i}"
+        wgrad(gname + ".fuse.0", ga, skips[i], dzs, 1, 1, 0, cin_first=0, cin=ch)
+        grads[gname + ".fuse.0.bias"] = torch.zeros_like(ga.bias)
+        dsk = S(f"dskip{i}", hh, ww, ch)
+        K.conv_dgrad(dzs, ga.weight, 1, 1, dsk, cache, gname, cin_first=0, cin=ch)
+        dskip[i] = dsk
+        if i > 0:
+            dz = S(f"dz_dec{i-1}", hh // 2, ww // 2, 2 * ch, 2)
+            K.grad_combine(dz, 2 * ch, add_b=dsrc, mask=P["y"][i - 1], act=act)
+        else:
+            d_x5n = dsrc
+    # ---- ga5 on x5
+    c5 = 16 * d
+    h5, w5 = P["x5"].h, P["x5"].w
+    dz5g = S("dz5g", h5, w5, c5)
+    K.instance_norm_bwd(d_x5n, 0, P["z5"], P["mr"]["ga5"], dz5g, torch.empty(2 * b * c5, dtype=torch.float64, device=dev))
+    f5 = G.ga5.fuse[0]
+    wgrad("ga5.fuse.0", f5, P["x5"], dz5g, 1, 1, 0, cin_first=0, cin=c5)
+    grads["ga5.fuse.0.bias"] = torch.zeros_like(f5.bias)
+    dx5 = S("dx5", h5, w5, c5)
+    K.conv_dgrad(dz5g, f5.weight, 1, 1, dx5, cache, "ga5", cin_first=0, cin=c5)
+    # ---- encoder 5..1
+    encs = [G.enc1, G.enc2, G.enc3, G.enc4, G.enc5]
+    xs = [P["x0"], P["x1"], P["x2"], P["x3"], P["x4"], P["x5"]]
+    dze = S("dz_e5", h5, w5, c5, 1)
+    K.grad_combine(dze, c5, add_b=dx5, mask=P["x5"], act=act)
+    for li in (5, 4, 3, 2):  # enc{li}: x_{li-1} -> x_li, k3 s2
+        conv = encs[li - 1].conv
+        xin = xs[li - 1]
+        wgrad(f"enc{li}.main.1", conv, xin, dze, 3, 2, 1, bias_from=dze)
+        dxpe = S(f"dxp_x{li-1}", xin.h + 2, xin.w + 2, xin.c)
+        K.conv_dgrad(dze, conv.weight, 3, 2, dxpe, cache, f"enc{li}")
+        halo = 1 if li > 2 else 3  # next dz feeds the dgrad of a k3s2 conv (halo 1); enc1's dz only feeds wgrad
+        nxt = S(f"dz_e{li-1}", xin.h, xin.w, xin.c, halo if li > 2 else 0)
+        K.grad_combine(nxt, xin.c, src_a=dxpe, pad_a=1, add_b=dskip[5 - li], add_c=dx1a if li == 2 else None,
+                       mask=xin, act=act)
+        dze = nxt
+    wgrad("enc1.main.1", G.enc1.conv, P["x0"], dze, 7, 1, 3, bias_from=dze)
+    dx = None
+    if need_dx:
+        dxp0 = S("dxp_x0", h + 6, w + 6, 16)
+        dze3 = S("dz_e1h", h, w, d, 6)
+        K.grad_combine(dze3, d, add_b=dze)
+        K.conv_dgrad(dze3, G.enc1.conv.weight, 7, 1, dxp0, cache, "enc1")
+        dx0 = S("dx0", h, w, 16)
+        K.grad_combine(dx0, 16, src_a=dxp0, pad_a=3)
+        dx = torch.empty_like(x)
+        K.unpack_input_grad(dx0, None, dx)
+    # dead parameters (see module docstring)
+    for i in range(1, 6):
+        ga = getattr(G, f"ga{i}")
+        grads[f"ga{i}.conv.0.weight"] = torch.zeros_like(ga.conv[0].weight)
+        grads[f"ga{i}.conv.2.weight"] = torch.zeros_like(ga.conv[2].weight)
+    return grads, dx
+
+
+class _GeneratorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        b, _, h, w = x.shape
+        if module.conv_dim % 32:
+            raise NotImplementedError("training kernels need conv_dim to be a multiple of 32 (wgrad operand rows)")
+        x = x.detach().contiguous().float()
+        key = (b, h, w, str(x.device))
+        pool = module._train_pool.setdefault(key, [])
+        ws = pool.pop() if pool else _g_workspace(module, b, h, w, x.device)
+        out = _g_forward_train(module, x, ws)
+        ctx.module, ctx.ws, ctx.key, ctx.x = module, ws, key, x
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        G = ctx.module
+        grads, dx = _g_backward(G, ctx.x, gout.contiguous().float(), ctx.ws, ctx.needs_input_grad[1])
+        G._train_pool[ctx.key].append(ctx.ws)
+        names = [n for n, _ in G.named_parameters()]
+        return (None, dx) + tuple(grads[n] for n in names)
 
 
 def generator_apply(module, x):
-    raise NotImplementedError("uegan_b200: the Generator backward (dgrad/wgrad kernels) is not built yet; "
-                              "call under torch.no_grad() for inference")
+    if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] % 16 or x.shape[3] % 16 or min(x.shape[2:]) < 32:
+        raise ValueError("Generator needs (B,3,H,W) with H, W multiples of 16 and >= 32")
+    if module._act is None:
+        raise NotImplementedError("activation function [%s] has no sm_100a epilogue" % module.act_fun)
+    if not hasattr(module, "_train_pool"):
+        module._train_pool = {}
+    return _GeneratorFn.apply(module, x, *[p for _, p in module.named_parameters()])
+
+
+# =================================================================================================
+# Discriminator
+# =================================================================================================
+def _d_workspace(D, b, h, w, dev):
+    d = D.conv_dim
+    chans = [d, 2 * d, 4 * d, 8 * d, 16 * d]
+    ws = dict(x0=K.NHWC(b, h, w, 4, 3, F32, dev, zero=True), ds=[], sig=[], u=[], v=[], preds=[])
+    hh, ww = h, w
+    for i in range(5):
+        hh, ww = (hh + 1) // 2, (ww + 1) // 2
+        ws["ds"].append(K.NHWC(b, hh, ww, chans[i], 3 if i < 3 else 2, F32, dev))
+        ws["sig"].append(torch.ones(2, dtype=torch.float32, device=dev))
+    return ws
+
+
+def _d_forward_train(D, x, ws):
+    K.pack_input(x, ws["x0"], L.PAD_REFLECT)
+    src, preds = ws["x0"], []
+    ws["u"], ws["v"] = [], []
+    for i, (k, pad) in enumerate(D._SPEC, start=1):
+        conv, head, wgt = D._conv(i), D._head(i), D._weight(i)
+        alpha = None
+        if D.use_sn:
+            scratch = torch.empty(wgt.shape[0] + wgt.numel() // wgt.shape[0] + 8, dtype=torch.float32, device=x.device)
+            K.spectral_sigma(wgt, conv.weight_u, conv.weight_v, D.training, ws["sig"][i - 1], scratch)
+            alpha = ws["sig"][i - 1][1:2]
+            ws["u"].append(conv.weight_u.detach().clone())  # the values this forward used (later forwards move on)
+            ws["v"].append(conv.weight_v.detach().clone())
+        dst = ws["ds"][i - 1]
+        wp = D._wcache.get(f"d{i}", wgt, lambda: K.packed_weight(wgt, src.c, F32))
+        K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, D._act)
+        K.halo_fill(dst)
+        pred = torch.empty(x.shape[0], 1, dst.h, dst.w, dtype=torch.float32, device=x.device)
+        hp = D._wcache.get(f"p{i}", head.weight, lambda: K.packed_weight(head.weight, dst.c, F32))
+        K.conv_fprop(dst, hp, 1, k, 1, pad, None, 0, None, None, D._head_act, None, pred)
+        preds.append(pred)
+        src = dst
+    ws["preds"] = preds
+    return preds
+
+
+def _d_backward(D, x, dpreds, ws, need_dx):
+    b, _, h, w = x.shape
+    dev = x.device
+    S = lambda name, hh, ww, c, halo=0: _scratch.get("D" + name, b, hh, ww, c, halo, F32, dev)
+    cache = D._wcache
+    grads = {}
+    srcs = [ws["x0"]] + ws["ds"]
+    carry = None  # gradient w.r.t. the padded ds_k coming from d_{k+1}
+    head_mode = 0 if D._head_act == L.ACT_TANH else 1
+    for i in (5, 4, 3, 2, 1):
+        k, pad = D._SPEC[i - 1]
+        kq = (k + 1) // 2
+        ds = ws["ds"][i - 1]
+        conv, head, wgt = D._conv(i), D._head(i), D._weight(i)
+        dzp = S(f"dzp{i}", ds.h, ds.w, 4, k - 1)
+        dzpw = S(f"dzpw{i}", ds.h, ds.w, 32, 0)
+        dp = dpreds[i - 1]
+        if dp is None:
+            dp = torch.zeros_like(ws["preds"][i - 1])
+        dp = dp.contiguous().float()
+        K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzp)
+        K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzpw)
+        gw = _zeros_like(head.weight)
+        K.conv_wgrad(ds, dzpw, gw, k, 1, pad)
+        grads[f"d{i}_pred.0.1.weight"] = gw
+        dxa = S(f"dxa{i}", ds.h + 2 * pad, ds.w + 2 * pad, ds.c)
+        K.conv_dgrad(dzp, head.weight, k, 1, dxa, cache, f"p{i}")
+        dz = S(f"dz{i}", ds.h, ds.w, ds.c, kq - 1)
+        if carry is not None:
+            tmp = S(f"tmp{i}", ds.h, ds.w, ds.c)
+            K.grad_combine(tmp, ds.c, src_a=carry[0], pad_a=carry[1])
+            K.grad_combine(dz, ds.c, src_a=dxa, pad_a=pad, add_b=tmp, mask=ds, act=D._act)
+        else:
+            K.grad_combine(dz, ds.c, src_a=dxa, pad_a=pad, mask=ds, act=D._act)
+        # strided SN conv d_i: input srcs[i-1]
+        xin = srcs[i - 1]
+        alpha = ws["sig"][i - 1][1:2] if D.use_sn else None
+        gw = _zeros_like(wgt)
+        K.conv_wgrad(xin, dz, gw, k, 2, pad, alpha=alpha)
+        if D.use_sn:
+            K.spectral_bwd(gw, wgt, ws["u"][i - 1], ws["v"][i - 1], ws["sig"][i - 1],
+                           torch.empty(1, dtype=torch.float64, device=dev))
+            grads[f"d{i}.0.1.weight_orig"] = gw
+        else:
+            grads[f"d{i}.0.1.weight"] = gw
+        gb = torch.empty_like(conv.bias)
+        K.channel_sum(dz, gb)
+        grads[f"d{i}.0.1.bias"] = gb
+        if i > 1:
+            dxb = S(f"dxb{i}", xin.h + 2 * pad, xin.w + 2 * pad, xin.c)
+            K.conv_dgrad(dz, wgt, k, 2, dxb, cache, f"d{i}", alpha=alpha)
+            carry = (dxb, pad)
+        elif need_dx:
+            dxb = S("dxb1", h + 2 * pad, w + 2 * pad, 16)
+            K.conv_dgrad(dz, wgt, k, 2, dxb, cache, "d1", alpha=alpha)
+            dx0 = S("dx0", h, w, 16)
+            K.grad_combine(dx0, 16, src_a=dxb, pad_a=pad)
+            dx = torch.empty_like(x)
+            K.unpack_input_grad(dx0, None, dx)
+            return grads, dx
+    return grads, None
+
+
+class _DiscriminatorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        b, _, h, w = x.shape
+        if module.conv_dim % 32:
+            raise NotImplementedError("training kernels need conv_dim to be a multiple of 32 (wgrad operand rows)")
+        x = x.detach().contiguous().float()
+        key = (b, h, w, str(x.device))
+        pool = module._train_pool.setdefault(key, [])
+        ws = pool.pop() if pool else _d_workspace(module, b, h, w, x.device)
+        preds = _d_forward_train(module, x, ws)
+        ctx.module, ctx.ws, ctx.key, ctx.x = module, ws, key, x
+        return tuple(preds)
+
+    @staticmethod
+    def backward(ctx, *dpreds):
+        D = ctx.module
+        grads, dx = _d_backward(D, ctx.x, dpreds, ctx.ws, ctx.needs_input_grad[1])
+        D._train_pool[ctx.key].append(ctx.ws)
+        names = [n for n, _ in D.named_parameters()]
+        return (None, dx) + tuple(grads[n] for n in names)
 
 
 def discriminator_apply(module, x):
-    raise NotImplementedError("uegan_b200: the Discriminator backward (dgrad/wgrad kernels) is not built yet; "
-                              "call under torch.no_grad()")
+    if x.dim() != 4 or x.shape[1] != 3 or min(x.shape[2:]) < 96:
+        raise ValueError("Discriminator needs (B,3,H,W) with H, W >= 96")
+    if module._act is None:
+        raise NotImplementedError("activation function [%s] has no sm_100a epilogue" % module.act_fun)
+    if not hasattr(module, "_train_pool"):
+        module._train_pool = {}
+    return list(_DiscriminatorFn.apply(module, x, *[p for _, p in module.named_parameters()]))
+
+
+# =================================================================================================
+# losses
+# =================================================================================================
+class _GanLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mode, for_d, n, *maps):
+        real = [t.detach().contiguous().float() for t in maps[:n]]
+        fake = [t.detach().contiguous().float() for t in maps[n:]]
+        ws = torch.empty(48, dtype=torch.float64, device=real[0].device)
+        loss = torch.empty((), dtype=torch.float32, device=real[0].device)
+        K.gan_loss_fwd(mode, for_d, real, fake, ws, loss)
+        ctx.mode, ctx.for_d, ctx.n, ctx.real, ctx.fake, ctx.ws = mode, for_d, n, real, fake, ws
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        n = ctx.n
+        need = ctx.needs_input_grad[3:]
+        d_real = [torch.zeros_like(t) if need[i] else None for i, t in enumerate(ctx.real)]
+        d_fake = [torch.zeros_like(t) if need[n + i] else None for i, t in enumerate(ctx.fake)]
+        g = gout.detach().reshape(1).float().contiguous()
+        K.gan_loss_bwd(ctx.mode, ctx.for_d, ctx.real, ctx.fake, ctx.ws, d_real, d_fake, gscale_dev=g)
+        return (None, None, None) + tuple(d_real) + tuple(d_fake)
+
+
+def gan_loss_apply(mode, for_d, real, fake):
+    return _GanLossFn.apply(mode, for_d, len(real), *real, *fake)
+
+
+class _MsRecFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rec_type, scales, pred, gt):
+        p, g = pred.detach().contiguous().float(), gt.detach().contiguous().float()
+        accum = torch.empty(3, dtype=torch.float64, device=p.device)
+        loss = torch.empty((), dtype=torch.float32, device=p.device)
+        K.msrec_loss(p, g, rec_type, scales, accum, loss)
+        ctx.rec_type, ctx.scales, ctx.p, ctx.g = rec_type, scales, p, g
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        grad = torch.empty_like(ctx.p)
+        accum = torch.empty(3, dtype=torch.float64, device=grad.device)
+        loss = torch.empty(1, dtype=torch.float32, device=grad.device)
+        K.msrec_loss(ctx.p, ctx.g, ctx.rec_type, ctx.scales, accum, loss, grad, 1.0,
+                     gout.detach().reshape(1).float().contiguous())
+        return None, None, grad, None
+
+
+def msrec_apply(module, pred, gt):
+    return _MsRecFn.apply(module.rec_type, module.scales, pred, gt)
+
+
+class _PerceptualFn(torch.autograd.Function):
+    """PerceptualLoss forward + backward w.r.t. x (the frozen tower has no weight gradients, losses.py:117-118)."""
+
+    @staticmethod
+    def forward(ctx, module, x, y):
+        x = x.detach().contiguous().float()
+        y = y.detach().contiguous().float()
+        vgg = module.vgg
+        taps_x, Px = vgg.run(x, "x", module.eps)
+        taps_y, _ = vgg.run(y, "y", module.eps)
+        loss = torch.zeros((), dtype=torch.float32, device=x.device)
+        if module._accum is None or module._accum.device != x.device:
+            module._accum = torch.zeros(1, dtype=torch.float64, device=x.device)
+        for wgt, (tx, mx), (ty, my) in zip(module.weights, taps_x, taps_y):
+            K.in_mse_fwd(tx, ty, mx, my, wgt, module._accum, loss)
+        ctx.module, ctx.taps_x, ctx.taps_y, ctx.Px, ctx.shape = module, taps_x, taps_y, Px, x.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        from .losses import _VGG_LAYERS, _TAP_IDX, IMAGENET_STD
+        module, vgg, P = ctx.module, ctx.module.vgg, ctx.Px
+        acts = P["acts"]
+        b, _, h, w = ctx.shape
+        dev = acts[0].buf.device
+        g = gout.detach().reshape(1).float().contiguous()
+        # fp16 gradient chain with a fixed loss scale: per-element gradients of a mean over ~1e8 features are ~1e-9,
+        # far below fp16's range; S makes the deepest tap's gradient O(1) (the others are <= 2^-11 of that), and is
+        # divided out when the image gradient is unpacked.  fp16 keeps 10 mantissa bits (bf16's 8 cost 12 % rel-L2).
+        t5 = ctx.taps_x[4][0]
+        scale = float(t5.n * t5.c * t5.h * t5.w) / (2.0 * module.weights[4])
+        # gradient buffers are zero-initialised once: nobody writes their halo, which is the dgrad's zero padding
+        if "grads" not in P:
+            P["grads"] = [K.NHWC(a.n, a.h, a.w, max(a.c, 16), 1, L.F16, dev, zero=True) for a in acts]
+            P["gws"] = torch.empty(2 * b * 512, dtype=torch.float64, device=dev)
+        G = P["grads"]
+        tap_of = {}
+        ti = 0
+        for li, spec in enumerate(_VGG_LAYERS):
+            if spec != "M" and spec[0] in _TAP_IDX:
+                tap_of[li + 1] = ti
+                ti += 1
+        have = [False] * len(acts)  # have[j]: G[j] holds dL/d(acts[j]) (for conv outputs: already ReLU-masked)
+        for li in range(len(_VGG_LAYERS) - 1, -1, -1):
+            spec = _VGG_LAYERS[li]
+            out_idx = li + 1
+            if spec == "M":
+                # acts[out_idx] = pool(acts[li]); route to the arg-max and apply the ReLU mask of acts[li]
+                K.maxpool2x2_bwd(acts[li], G[out_idx], G[li])
+                have[li] = True
+                continue
+            idx, cin, cout = spec
+            if out_idx in tap_of:
+                t = tap_of[out_idx]
+                (tx, mx), (ty, my) = ctx.taps_x[t], ctx.taps_y[t]
+                deep = G[out_idx] if have[out_idx] else None
+                dzt = _scratch.get(f"vgg_dz{out_idx}", tx.n, tx.h, tx.w, tx.c, 1, L.F16, dev, zero=True)
+                K.in_mse_bwd(tx, ty, mx, my, module.weights[t] * scale, g, deep, dzt, P["gws"])
+                dz = dzt
+            else:
+                dz = G[out_idx]  # masked by the producer (dgrad epilogue mask or max-pool backward)
+            conv = vgg.features[idx]
+            src = acts[li]
+            key = ("vgg_dg", idx)
+            tag = (conv.weight.data_ptr(), conv.weight._version)
+            hit = vgg._wcache.get(key)
+            if hit is None or hit[0] != tag:
+                hit = (tag, K.packed_weight_dgrad(conv.weight, dz.c, L.F16, 1, 0, 0))
+                vgg._wcache[key] = hit
+            # the producer of `src`: a conv (ReLU mask needed, unless it is a tap, masked later) or a pool / the input
+            prev_is_conv = li > 0 and _VGG_LAYERS[li - 1] != "M"
+            prev_is_tap = li in tap_of
+            mask = src if (prev_is_conv and not prev_is_tap) else None
+            cout_dg = cin if cin != 3 else 16
+            K.conv_generic(dz, hit[1], cout_dg, 3, 1, 1, G[li], 0, None, None, L.ACT_NONE, mask, L.ACT_RELU)
+            have[li] = True
+        dx = torch.empty(b, 3, h, w, dtype=torch.float32, device=dev)
+        K.unpack_input_grad(G[0], [1.0 / (s * scale) for s in IMAGENET_STD], dx)
+        return None, dx, None
+
+
+def perceptual_apply(module, x, y):
+    return _PerceptualFn.apply(module, x, y)

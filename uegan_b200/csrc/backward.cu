@@ -315,7 +315,7 @@ __global__ void maxpool2x2_bwd_kernel(TGeom src, TGeom dpool, TGeom dst, long lo
     for (int j = 1; j < 4; ++j)
       if (v[j][k] > bv) { bv = v[j][k]; best = j; }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j][k] = (j == best) ? g[k] : 0.f;
+    for (int j = 0; j < 4; ++j) o[j][k] = (j == best && bv > 0.f) ? g[k] : 0.f;  // + ReLU mask of the activation
   }
   TG* db = static_cast<TG*>(dst.data);
   Vec<TG>::store(db + toff(dst, n, 2 * yo, 2 * xo, c), o[0]);
@@ -328,7 +328,8 @@ __global__ void maxpool2x2_bwd_kernel(TGeom src, TGeom dpool, TGeom dst, long lo
 // VGG tap: d/dx of  weight * mean((IN(x) - IN(y))^2)  w.r.t. the feature map x (y is a constant):
 //   e = xh - yh ; dxh = (2 * weight / numel) * e ; dx = rstd * (dxh - mean_p(dxh) - xh * mean_p(dxh * xh))
 // followed by the ReLU mask of the tap itself (x is a ReLU output) and accumulation with the gradient that arrives from
-// deeper layers (`deep`, optional).  Output gradient tensor TG (bf16), zero halo.
+// deeper layers (`deep`, optional).  Output gradient tensor TG (fp16, loss-scaled by the caller through `weight`:
+// per-element gradients of a mean over 1e8 elements are far below fp16's range unscaled), zero halo.
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void tap_bwd_stats_kernel(TGeom x, TGeom y, const float* __restrict__ mrx, const float* __restrict__ mry,
@@ -541,14 +542,14 @@ int uegan_upsample2x_bwd(const uegan_tensor* dout, int32_t d_c_off, const uegan_
 
 int uegan_maxpool2x2_bwd(const uegan_tensor* src, const uegan_tensor* dpool, const uegan_tensor* dsrc, void* stream) {
   UEGAN_CHECK(src && dpool && dsrc, "maxpool2x2_bwd: null pointer");
-  UEGAN_CHECK(src->dtype == UEGAN_F16 && dpool->dtype == UEGAN_BF16 && dsrc->dtype == UEGAN_BF16,
-              "maxpool2x2_bwd: expects fp16 activations and bf16 gradients");
+  UEGAN_CHECK(src->dtype == UEGAN_F16 && dpool->dtype == UEGAN_F16 && dsrc->dtype == UEGAN_F16,
+              "maxpool2x2_bwd: expects fp16 activations and (loss-scaled) fp16 gradients");
   UEGAN_CHECK(src->n == dsrc->n && src->h == dsrc->h && src->w == dsrc->w && src->c == dsrc->c && dpool->h == src->h / 2 &&
                   dpool->w == src->w / 2 && dpool->c == src->c && src->c % 8 == 0,
               "maxpool2x2_bwd: tensor mismatch");
   const TGeom s = geom(*src), g = geom(*dpool), d = geom(*dsrc);
   const long long total = (long long)g.n * g.h * g.w * (s.c / 8);
-  maxpool2x2_bwd_kernel<__half, __nv_bfloat16><<<nblk(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(s, g, d, total);
+  maxpool2x2_bwd_kernel<__half, __half><<<nblk(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(s, g, d, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -557,12 +558,12 @@ int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* 
                      float weight, const float* gscale_dev, const uegan_tensor* deep, const uegan_tensor* dx, double* ws,
                      void* stream) {
   UEGAN_CHECK(x && y && dx && mean_rstd_x && mean_rstd_y && ws, "in_mse_bwd: null pointer");
-  UEGAN_CHECK(x->dtype == UEGAN_F16 && y->dtype == UEGAN_F16 && dx->dtype == UEGAN_BF16 && x->c % 8 == 0 && x->c <= 1024,
-              "in_mse_bwd: expects fp16 features and a bf16 gradient");
+  UEGAN_CHECK(x->dtype == UEGAN_F16 && y->dtype == UEGAN_F16 && dx->dtype == UEGAN_F16 && x->c % 8 == 0 && x->c <= 1024,
+              "in_mse_bwd: expects fp16 features and a (loss-scaled) fp16 gradient");
   UEGAN_CHECK(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c && dx->n == x->n && dx->h == x->h &&
                   dx->w == x->w && dx->c == x->c,
               "in_mse_bwd: tensor mismatch");
-  if (deep) UEGAN_CHECK(deep->dtype == UEGAN_BF16 && deep->h == x->h && deep->w == x->w && deep->c == x->c, "in_mse_bwd: deep mismatch");
+  if (deep) UEGAN_CHECK(deep->dtype == UEGAN_F16 && deep->h == x->h && deep->w == x->w && deep->c == x->c, "in_mse_bwd: deep mismatch");
   const TGeom gx = geom(*x), gy = geom(*y), gd = geom(*dx);
   TGeom gdeep = gd;
   if (deep) gdeep = geom(*deep);
@@ -577,7 +578,7 @@ int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* 
   tap_bwd_stats_kernel<__half><<<grid, threads, sizeof(double) * 2 * threads, st>>>(gx, gy, mean_rstd_x, mean_rstd_y, ws, ppb);
   const double numel = (double)gx.n * gx.c * (double)npix;
   const long long total = (long long)gd.n * gd.hp * gd.wp * (gx.c / 8);
-  tap_bwd_apply_kernel<__half, __nv_bfloat16><<<nblk(total, 256), 256, 0, st>>>(
+  tap_bwd_apply_kernel<__half, __half><<<nblk(total, 256), 256, 0, st>>>(
       gx, gy, gdeep, deep ? 1 : 0, gd, mean_rstd_x, mean_rstd_y, ws, 1.0 / (double)npix, (float)(2.0 * weight / numel),
       gscale_dev, total);
   UEGAN_CUDA(cudaGetLastError());

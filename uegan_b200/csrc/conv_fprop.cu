@@ -54,6 +54,7 @@ struct ConvParams {
   int mask_kind, mask_act;
   float* out_nchw;
   const float* residual_nchw;
+  float* aux_nchw;  // optional: activation before the residual/clamp
   unsigned int* err_sink;  // host-mapped watchdog word
   double* in_stats;        // optional [Nimg][cout][2] sum / sum-of-squares of the stored outputs (InstanceNorm)
 };
@@ -237,6 +238,7 @@ __device__ __forceinline__ void epilogue_planar(const ConvParams& p, uint32_t ta
       float x = __uint_as_float(rr[i]) * alpha;
       if (p.bias) x += __ldg(p.bias + colbase + i);
       x = apply_act(x, p.act);
+      if (p.aux_nchw) p.aux_nchw[o] = x;
       if (p.residual_nchw) x = fminf(fmaxf(x + __ldg(p.residual_nchw + o), -1.f), 1.f);
       p.out_nchw[o] = x;
     }
@@ -514,6 +516,7 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   p.alpha = d.alpha;
   p.out_nchw = d.out_nchw;
   p.residual_nchw = d.residual_nchw;
+  p.aux_nchw = d.aux_nchw;
   p.err_sink = error_sink_device();
   p.in_stats = d.in_stats;
   const int ymul = d.y_mul > 1 ? d.y_mul : 1;

@@ -164,8 +164,10 @@ __device__ __forceinline__ float rec_dterm(float d, int type) {
 // accum[0..2] = sum of term at scale 0, 1, 2.  If grad != NULL also writes d loss / d pred (needs w0..w2 = weight_i / N_i
 // already multiplied by the upstream scale).
 __global__ void msrec_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int planes, int h, int w,
-                             int type, int scales, double* __restrict__ accum, float* __restrict__ grad, float w0,
-                             float w1, float w2) {
+                             int type, int scales, double* __restrict__ accum, float* __restrict__ grad, float w0_,
+                             float w1_, float w2_, const float* __restrict__ gscale) {
+  const float gs = gscale ? gscale[0] : 1.f;
+  const float w0 = w0_ * gs, w1 = w1_ * gs, w2 = w2_ * gs;
   const int bw = w >> 2, bh = h >> 2;
   const long long total = (long long)planes * bh * bw;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -297,7 +299,7 @@ int uegan_in_mse_fwd(const uegan_tensor* x, const uegan_tensor* y, const float* 
 
 int uegan_msrec_loss(const float* pred_nchw, const float* gt_nchw, int32_t n, int32_t c, int32_t h, int32_t w,
                      int32_t type, int32_t scales, double* accum, float* loss_out, float* grad_nchw,
-                     float grad_scale, void* stream) {
+                     float grad_scale, const float* gscale_dev, void* stream) {
   UEGAN_CHECK(pred_nchw && gt_nchw && accum && loss_out, "msrec: null pointer");
   UEGAN_CHECK(h % 4 == 0 && w % 4 == 0, "msrec: H, W must be multiples of 4 (got %dx%d)", h, w);
   UEGAN_CHECK(scales >= 1 && scales <= 3 && type >= 0 && type <= 2, "msrec: bad scales/type");
@@ -309,7 +311,7 @@ int uegan_msrec_loss(const float* pred_nchw, const float* gt_nchw, int32_t n, in
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   msrec_kernel<<<blocks, 256, 0, st>>>(pred_nchw, gt_nchw, n * c, h, w, type, scales, accum, grad_nchw,
-                                      (float)(c0 * grad_scale), (float)(c1 * grad_scale), (float)(c2 * grad_scale));
+                                      (float)(c0 * grad_scale), (float)(c1 * grad_scale), (float)(c2 * grad_scale), gscale_dev);
   msrec_finalize_kernel<<<1, 32, 0, st>>>(accum, c0, c1, c2, loss_out);
   UEGAN_CUDA(cudaGetLastError());
   return 0;

@@ -83,6 +83,23 @@ __global__ void sn_finalize_kernel(const float* __restrict__ wv, float* __restri
   }
 }
 
+// backward through sigma (u, v constants): dW = A - (<A, W> / sigma) * u v^T with A = (dL/dW_sn) / sigma already
+// produced by the wgrad kernel (alpha = 1/sigma).
+__global__ void sn_dot_kernel(const float* __restrict__ a, const float* __restrict__ w, long long n, double* __restrict__ out) {
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += (double)a[i] * w[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+__global__ void sn_rank1_kernel(float* __restrict__ a, const float* __restrict__ u, const float* __restrict__ v,
+                                const double* __restrict__ dot, const float* __restrict__ sigma, int rows, int cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const float coef = (float)(dot[0]) * sigma[1];  // <A, W> / sigma
+  a[i] -= coef * u[i / cols] * v[i % cols];
+}
+
 }  // namespace uegan
 
 using namespace uegan;
@@ -106,6 +123,20 @@ extern "C" int uegan_spectral_sigma(const float* w, float* u, float* v, int32_t 
   }
   sn_w_v_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(w, t, sumsq, v, wv, rows, cols, train, eps);
   sn_finalize_kernel<<<1, 256, 0, st>>>(wv, u, sigma_out, rows, train, eps);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int uegan_spectral_bwd(float* grad_inout, const float* w, const float* u, const float* v, const float* sigma,
+                                  int32_t rows, int32_t cols, double* ws, void* stream) {
+  UEGAN_CHECK(grad_inout && w && u && v && sigma && ws, "spectral_bwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n = (long long)rows * cols;
+  UEGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(double), st));
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 256) blocks = 256;
+  sn_dot_kernel<<<blocks, 256, 0, st>>>(grad_inout, w, n, ws);
+  sn_rank1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grad_inout, u, v, ws, sigma, rows, cols);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

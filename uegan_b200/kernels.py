@@ -85,7 +85,8 @@ def packed_weight(weight: torch.Tensor, cin_stored: int, dtype: int, cin_first: 
 def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, pad: int, y: Optional[NHWC] = None,
                y_c_off: int = 0, bias: Optional[torch.Tensor] = None, alpha: Optional[torch.Tensor] = None,
                act: int = L.ACT_NONE, mul: Optional[NHWC] = None, out_nchw: Optional[torch.Tensor] = None,
-               residual_nchw: Optional[torch.Tensor] = None, in_stats: Optional[torch.Tensor] = None):
+               residual_nchw: Optional[torch.Tensor] = None, in_stats: Optional[torch.Tensor] = None,
+               aux_nchw: Optional[torch.Tensor] = None):
     lib = L.load()
     d = L.ConvDesc()
     d.x = x.ct
@@ -99,6 +100,7 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
     d.out_nchw = out_nchw.data_ptr() if out_nchw is not None else None
     d.residual_nchw = residual_nchw.data_ptr() if residual_nchw is not None else None
     d.in_stats = in_stats.data_ptr() if in_stats is not None else None
+    d.aux_nchw = aux_nchw.data_ptr() if aux_nchw is not None else None
     ev = _Counters.conv_events
     if ev is not None:
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -232,13 +234,14 @@ def in_mse_fwd(x: NHWC, y: NHWC, mr_x: int, mr_y: int, weight: float, accum: tor
 
 
 def msrec_loss(pred: torch.Tensor, gt: torch.Tensor, rec_type: int, scales: int, accum: torch.Tensor,
-               loss: torch.Tensor, grad: Optional[torch.Tensor] = None, grad_scale: float = 1.0):
+               loss: torch.Tensor, grad: Optional[torch.Tensor] = None, grad_scale: float = 1.0, gscale_dev=None):
     assert pred.shape == gt.shape and pred.is_cuda and pred.dtype == torch.float32
     assert pred.is_contiguous() and gt.is_contiguous()
     n, c, h, w = pred.shape
     L.check(L.load().uegan_msrec_loss(pred.data_ptr(), gt.data_ptr(), n, c, h, w, rec_type, scales, accum.data_ptr(),
                                       loss.data_ptr(), grad.data_ptr() if grad is not None else None,
-                                      float(grad_scale), _stream()), "msrec_loss")
+                                      float(grad_scale), gscale_dev.data_ptr() if gscale_dev is not None else None,
+                                      _stream()), "msrec_loss")
     _count(2)
 
 
@@ -288,11 +291,13 @@ def conv_dgrad(dz: NHWC, weight: torch.Tensor, k: int, stride: int, dxp: NHWC, c
     kq = (k + stride - 1) // stride
     assert dz.halo >= kq - 1, "dz needs a zero halo of ceil(k/stride)-1"
     cin_n = (weight.shape[1] - cin_first) if cin is None else cin
+    cout_arg = (cin_n + 15) // 16 * 16  # RGB input (3 channels): the packed operand's rows 3..15 are zero
+    assert dxp.c >= cout_arg
     for pi in range(stride):
         for pj in range(stride):
             fn = lambda: packed_weight_dgrad(weight, dz.c, dz.dtype, stride, pi, pj, cin_first, cin)
             wp = cache.get((key, "dg", pi, pj, dz.dtype), weight, fn) if cache is not None else fn()
-            conv_generic(dz, wp, cin_n, kq, 1, kq - 1, dxp, 0, None, alpha, L.ACT_NONE, mask, mask_act,
+            conv_generic(dz, wp, cout_arg, kq, 1, kq - 1, dxp, 0, None, alpha, L.ACT_NONE, mask, mask_act,
                          y_mul=stride, y_off_h=pi, y_off_w=pj)
 
 
@@ -362,3 +367,11 @@ def in_mse_bwd(x: NHWC, y: NHWC, mr_x: int, mr_y: int, weight: float, gscale, de
 def unpack_input_grad(dx: NHWC, scale, out: torch.Tensor):
     L.check(L.load().uegan_unpack_input_grad(dx.ref(), L.float3(scale), out.data_ptr(), _stream()), "unpack_input_grad")
     _count(1)
+
+
+def spectral_bwd(grad: torch.Tensor, w: torch.Tensor, u: torch.Tensor, v: torch.Tensor, sigma: torch.Tensor,
+                 ws: torch.Tensor):
+    rows = w.shape[0]
+    L.check(L.load().uegan_spectral_bwd(grad.data_ptr(), w.data_ptr(), u.data_ptr(), v.data_ptr(), sigma.data_ptr(),
+                                        rows, w.numel() // rows, ws.data_ptr(), _stream()), "spectral_bwd")
+    _count(2)

@@ -69,7 +69,7 @@ class VGG19_relu(nn.Module):
         return pl
 
     @torch.no_grad()
-    def run(self, x01, slot="x"):
+    def run(self, x01, slot="x", eps=1e-5):
         """x01: (B,3,H,W) fp32 in [0,1].  Returns (taps, plan): taps = list of (NHWC activation, mean/rstd address)."""
         b, _, h, w = x01.shape
         if h % 16 or w % 16:
@@ -92,7 +92,7 @@ class VGG19_relu(nn.Module):
             K.conv_fprop(src, self._packed(idx, src.c), cout, 3, 1, 1, dst, 0, conv.bias, None, L.ACT_RELU,
                          in_stats=P["stats"][ti] if fused else None)
             if is_tap:
-                mr = K.instance_norm_stats(dst, P["stats"][ti], sums_ready=fused)
+                mr = K.instance_norm_stats(dst, P["stats"][ti], sums_ready=fused, eps=eps)
                 taps.append((dst, mr))
                 ti += 1
         return taps, P
@@ -105,6 +105,7 @@ class PerceptualLoss(nn.Module):
         super().__init__()
         self.add_module("vgg", VGG19_relu(vgg_state_dict))
         self.weights = [1.0 / 64, 1.0 / 64, 1.0 / 32, 1.0 / 32, 1.0 / 1]
+        self.eps = 1e-5  # nn.InstanceNorm2d default (losses.py:18); exposed for conditioning tests
         self._accum = None
 
     def __call__(self, x, y):
@@ -121,8 +122,8 @@ class PerceptualLoss(nn.Module):
 
     @torch.no_grad()
     def forward_native(self, x, y):
-        taps_x, _ = self.vgg.run(x, "x")
-        taps_y, _ = self.vgg.run(y, "y")
+        taps_x, _ = self.vgg.run(x, "x", self.eps)
+        taps_y, _ = self.vgg.run(y, "y", self.eps)
         loss = torch.zeros(1, dtype=torch.float32, device=x.device)
         if self._accum is None or self._accum.device != x.device:
             self._accum = torch.zeros(1, dtype=torch.float64, device=x.device)
