@@ -1,22 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- UEGAN hot path on B200.  One JSON line on stdout (rank 0).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload inference|train]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload train|inference]
 
-Workload (config.workload): BASELINE.json configs[1] "Generator inference, synthetic 3x512x512 batch=32, 1xB200"
-while the native training step (configs[2]) is being built; one "step" = one pass of the Generator over one batch of
-32 synthetic 512x512 images per GPU (weak scaling: every rank runs its own batch, no data-path collective --
-inference is embarrassingly parallel).
+Default workload = the configuration BASELINE.json's metric is quoted on: configs[2] "full G+D+VGG-perceptual training
+step, 3x512x512 batch=16" per GPU (configs[3] at N=8: global batch 128).  One "step" = one iteration of the loop body
+of trainer.py:75-119 (2 G forwards, 5 D forwards, 2 VGG forwards, all backwards, two Adam steps) on one batch of 16
+synthetic 512x512 image pairs per GPU; weak scaling.  N > 1: torchrun, one process per GPU, two flat NCCL gradient
+all-reduces per step (+ the tiny all-reduces of the relativistic means).
+`--workload inference` = configs[1]: Generator forward on 32 x 3x512x512 per GPU (replicas, no collective).
 
 * `value`      : images/s, all ranks, inputs resident in HBM, CUDA events, max over ranks.
-* `e2e`        : same metric through the public API (`uegan_b200.models.Generator.__call__`) with the batch in pinned
-                 HOST memory: H2D of the batch and D2H of the enhanced images are inside the timed region every step.
-* `roofline`   : dominant kernel = conv_fprop_kernel (tcgen05 implicit GEMM); achieved = algorithmic conv FLOPs of all
-                 its launches in a step / their summed CUDA-event durations (measured in a separate instrumented pass).
-* `cpu_baseline`: the oracle port (oracle/uegan_oracle.py, fp32 torch-CPU restatement of models.py:44-74) on the box's
-                 host cores, bounded sample.
-* `--impl reference`: the same oracle port as the reference arm (the reference is Python; /root/reference does not
-                 exist on the GPU box), all host threads, same metric/unit/config.
+* `e2e`        : same metric through the public API (`uegan_b200.trainer.Trainer.train_step` /
+                 `models.Generator.__call__`) with the batch in pinned HOST memory: H2D of the batch and D2H of the
+                 result (5 loss scalars / enhanced images) inside the timed region every step.
+* `roofline`   : dominant kernel family = the tcgen05 implicit-GEMM convolutions (conv_fprop_kernel for fprop and
+                 dgrad, conv_wgrad_kernel); achieved = algorithmic conv FLOPs of their launches in a step / their summed
+                 CUDA-event durations (separate instrumented pass); peak = FLOP-weighted tensor peak (tf32 launches at
+                 half the measured bf16 figure, fp16 launches at the full figure).
+* `cpu_baseline` / `--impl reference`: the oracle port (oracle/uegan_oracle.py, fp32 torch-CPU restatement of the same
+                 step) on the box's host cores -- the reference is Python and /root/reference is not on the GPU box.
 """
 import argparse
 import json
@@ -25,12 +28,13 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-G_GFLOP_PER_IMAGE = 67.747  # conv FLOPs (2*MAC) of one Generator forward at 512x512, SURVEY.md 8(d)
-BATCH = 32
+G_GFLOP_PER_IMAGE = 67.747     # conv FLOPs of one Generator forward at 512x512
+TRAIN_GFLOP_PER_IMAGE = 1098.9  # algorithmic conv FLOPs of one training step per image at 512x512
 RES = 512
 
 
@@ -75,70 +79,99 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, power = [], None, set(), []
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx = float(r[1])
+                sm.append(float(r[0])); mx = float(r[1]); power.append(float(r[2]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        # median over the samples taken under load (upper half: idle samples at the edges pull the median down)
-        load = sm[len(sm) // 2:] if sm else []
+        load = sm[len(sm) // 2:] if sm else []  # samples under load (the idle edges pull a plain median down)
         return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def oracle_generator_rate(batch, iters, threads):
-    """images/s of the CPU oracle port of Generator.forward at 512x512 (bounded sample)."""
+def train_args(batch):
+    return types.SimpleNamespace(
+        g_conv_dim=32, d_conv_dim=32, g_norm_fun="none", d_norm_fun="none", g_act_fun="LeakyReLU",
+        d_act_fun="LeakyReLU", g_use_sn=False, d_use_sn=True, adv_loss_type="rahinge", init_type="", optimizer_type="adam",
+        g_lr=1e-4, d_lr=4e-4, beta1=0.5, beta2=0.999, alpha=0.9, lr_decay=False, pool_size=0, adv_input=True,
+        lambda_adv=0.10, lambda_percep=1.0, lambda_idt=0.10, idt_loss_type="l1", save_root_dir="/tmp/uegan_b200",
+        version="bench", model_save_path="models", train_batch_size=batch, total_epochs=1, pretrained_model=0.0,
+        model_save_epoch=1, info_step=100)
+
+
+# ------------------------------------------------------------------------------------------------ CPU (oracle port)
+def oracle_step_fn(workload, batch):
     import torch
     from oracle import uegan_oracle as O
-    torch.set_num_threads(threads)
     gp = O.make_generator_params(32, 0, "o1")
     x = O.make_images((batch, 3, RES, RES), 0)
-    with torch.no_grad():
-        O.generator_forward(gp, x[:1])  # warm-up
-        t0 = time.perf_counter()
-        for _ in range(iters):
-            O.generator_forward(gp, x)
-        dt = time.perf_counter() - t0
+    if workload == "inference":
+        def step():
+            with torch.no_grad():
+                O.generator_forward(gp, x)
+        return step
+    dp, vp = O.make_discriminator_params(32, 1, "o1"), O.make_vgg_params()
+    g_opt, d_opt = O.AdamState(O._trainable(gp)), O.AdamState(O._trainable(dp))
+    y = O.make_images((batch, 3, RES, RES), 1)
+
+    def step():
+        O.train_step(gp, dp, vp, g_opt, d_opt, x, y)
+    return step
+
+
+def cpu_rate(workload, batch, iters, threads, warm=0):
+    import torch
+    torch.set_num_threads(threads)
+    step = oracle_step_fn(workload, batch)
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        step()
+    dt = time.perf_counter() - t0
     return batch * iters / dt, dt
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
-    batch = 2
-    times = []
+    batch = 1 if args.workload == "train" else 2
     import torch
-    from oracle import uegan_oracle as O
     torch.set_num_threads(threads)
-    gp = O.make_generator_params(32, 0, "o1")
-    x = O.make_images((batch, 3, RES, RES), 0)
-    with torch.no_grad():
-        for i in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            O.generator_forward(gp, x)
-            if i >= args.warmup:
-                times.append(time.perf_counter() - t0)
+    step = oracle_step_fn(args.workload, batch)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        step()
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     val = batch / (ms / 1e3)
-    sample = f"oracle port of Generator.forward, {batch}x3x{RES}x{RES} per step, {threads} threads, fp32"
+    what = "training step (trainer.py:75-119)" if args.workload == "train" else "Generator.forward"
+    sample = f"oracle port of the {what}, {batch}x3x{RES}x{RES} per step, {threads} threads, fp32"
     print(json.dumps({
-        "impl": "reference", "metric": "512x512 images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "generator_inference_3x512x512 (BASELINE.json configs[1])", "batch_per_step": batch,
-                   "note": "CPU steps are a bounded sample (batch 2) of the batch-32 GPU step"},
+        "impl": "reference", "metric": "512x512 training images/sec" if args.workload == "train" else "512x512 images/sec",
+        "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_name(args.workload), "batch_per_step": batch,
+                                        "note": "CPU steps are a bounded sample of the GPU arm's per-step batch"},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+def workload_name(w):
+    return ("train_step_G+D+VGG_3x512x512_b16 (BASELINE.json configs[2]; configs[3] at 8 GPUs)" if w == "train"
+            else "generator_inference_3x512x512_b32 (BASELINE.json configs[1])")
+
+
+# ------------------------------------------------------------------------------------------------ GPU (native)
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -146,19 +179,52 @@ def run_native(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from oracle import uegan_oracle as O  # synthetic weights/images only (checker code is not timed as product)
+        group = dist.group.WORLD
+    from oracle import uegan_oracle as O  # deterministic synthetic WEIGHTS only; nothing of the oracle is timed here
     from uegan_b200 import kernels as K
-    from uegan_b200.models import Generator
-
-    G = Generator(32, "none", "LeakyReLU", False)
-    G.load_state_dict(O.make_generator_params(32, 0, "o1"))
-    G = G.cuda().eval()
-    g = torch.Generator(device="cuda").manual_seed(rank)
-    x = torch.rand(BATCH, 3, RES, RES, device="cuda", generator=g) * 2 - 1
+    train = args.workload == "train"
+    batch = args.batch or (16 if train else 32)
+    gen = torch.Generator(device="cuda").manual_seed(rank)
+    x = torch.rand(batch, 3, RES, RES, device="cuda", generator=gen) * 2 - 1
     x_host = x.cpu().pin_memory()
-    out_host = torch.empty_like(x_host).pin_memory()
+    if train:
+        from uegan_b200.trainer import Trainer
+        T = Trainer(None, train_args(batch), process_group=group if world > 1 else None,
+                    vgg_state_dict=O.make_vgg_params())
+        T.G.load_state_dict(O.make_generator_params(32, 0, "o1"))
+        T.D.load_state_dict(O.make_discriminator_params(32, 1, "o1"))
+        y = torch.rand(batch, 3, RES, RES, device="cuda", generator=gen) * 2 - 1
+        y_host = y.cpu().pin_memory()
+
+        def step_resident():
+            T.train_step(x, y, sync_scalars=False)
+
+        def step_e2e():
+            xd, yd = x_host.cuda(non_blocking=True), y_host.cuda(non_blocking=True)
+            return T.train_step(xd, yd, sync_scalars=True)  # 5 x .item(): the reference's D2H reads (trainer.py:98-119)
+        h2d, d2h = 2 * x_host.numel() * 4, 5 * 4
+        gflop = TRAIN_GFLOP_PER_IMAGE
+        ctx = torch.enable_grad
+    else:
+        from uegan_b200.models import Generator
+        G = Generator(32, "none", "LeakyReLU", False)
+        G.load_state_dict(O.make_generator_params(32, 0, "o1"))
+        G = G.cuda().eval()
+        out_host = torch.empty_like(x_host).pin_memory()
+
+        def step_resident():
+            return G(x)
+
+        def step_e2e():
+            out = G(x_host.cuda(non_blocking=True))
+            out_host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h2d, d2h = x_host.numel() * 4, x_host.numel() * 4
+        gflop = G_GFLOP_PER_IMAGE
+        ctx = torch.no_grad
 
     def barrier():
         if world > 1:
@@ -166,7 +232,7 @@ def run_native(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
-        with torch.no_grad():
+        with ctx():
             for _ in range(warmup):
                 fn()
             barrier()
@@ -177,20 +243,10 @@ def run_native(args):
                 fn()
             e1.record()
             barrier()
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], device="cuda")
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), K.launches() - l0
-
-    def step_resident():
-        return G(x)
-
-    def step_e2e():
-        xd = x_host.cuda(non_blocking=True)
-        out = G(xd)
-        out_host.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -199,51 +255,59 @@ def run_native(args):
     clocks = sampler.stop() if sampler else None
     ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 1))
 
-    # ---- instrumented pass: CUDA events around every conv launch (dominant kernel), rank 0
     roof = None
-    if rank == 0:
+    if rank == 0:  # instrumented pass (rank 0 only, after the timed regions): CUDA events around every GEMM launch
+        reps = 2
         K._Counters.conv_events = []
-        with torch.no_grad():
-            for _ in range(3):
-                G(x)
+        with ctx():
+            for _ in range(reps):
+                step_resident()
         torch.cuda.synchronize()
         ev = K._Counters.conv_events
         K._Counters.conv_events = None
-        conv_ms = sum(a.elapsed_time(b) for a, b, *_ in ev) / 3
-        conv_flops = sum(f for _, _, f, *_ in ev) / 3
         hbm, tf_burst, tf_sus, src = peaks()
-        peak = tf_burst / 2  # kind::tf32 runs at half the bf16 rate; MEASURED_PEAKS.json holds the bf16 figure
-        achieved = conv_flops / (conv_ms * 1e-3) / 1e12
-        per_layer = {}
-        for a, b, f, xt, cout, k, s in ev:
-            key = f"{xt.c}->{cout} k{k}s{s} @{xt.h}"
-            per_layer[key] = per_layer.get(key, 0.0) + a.elapsed_time(b) / 3
-        roof = {"bound": "tensor", "kernel": "conv_fprop_kernel<tf32> (all 25 launches of a step)",
+        tot_ms = tot_fl = t_at_peak = 0.0
+        per = {}
+        for a, b, f, xt, cout, k, s, kind, dt in ev:
+            ms = a.elapsed_time(b) / reps
+            pk = tf_burst / 2 if dt == 0 else tf_burst
+            tot_ms += ms; tot_fl += f / reps; t_at_peak += (f / reps) / (pk * 1e12)
+            key = f"{kind} {'tf32' if dt == 0 else 'f16'} {xt.c}->{cout} k{k}s{s} @{xt.h}"
+            e = per.setdefault(key, [0.0, 0.0]); e[0] += ms; e[1] += f / reps
+        achieved = tot_fl / (tot_ms * 1e-3) / 1e12
+        peak = tot_fl / t_at_peak / 1e12
+        top = sorted(per.items(), key=lambda kv: -kv[1][0])[:24]
+        roof = {"bound": "tensor", "kernel": "conv_fprop_kernel (fprop+dgrad) + conv_wgrad_kernel, all launches of a step",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": f"{src}: bf16_tflops {tf_burst} / 2 for kind::tf32",
-                "conv_ms_per_step": conv_ms, "step_ms": ms_total / args.steps,
-                "conv_share_of_step": conv_ms / (ms_total / args.steps),
-                "per_layer_ms": {k: round(v, 4) for k, v in sorted(per_layer.items(), key=lambda kv: -kv[1])}}
+                "peak_source": f"{src}: FLOP-weighted mix of bf16_tflops {tf_burst} (fp16 launches) and half of it (tf32 launches)",
+                "gemm_ms_per_step": tot_ms, "step_ms": ms_total / args.steps, "gemm_launches_per_step": len(ev) // reps,
+                "gemm_share_of_step": tot_ms / (ms_total / args.steps),
+                "algorithmic_gflop_per_step_measured": tot_fl / 1e9,
+                "top_layers_ms_tflops": {k: [round(v[0], 3), round(v[1] / (v[0] * 1e-3) / 1e12, 1)] for k, v in top}}
 
     if rank == 0:
         cpu_threads = os.cpu_count() or 1
-        cpu_val, cpu_dt = oracle_generator_rate(2, 2, cpu_threads)
+        cpu_batch = 1 if train else 2
+        cpu_val, cpu_dt = cpu_rate(args.workload, cpu_batch, 1 if train else 2, cpu_threads, warm=0 if train else 1)
         ms_step = ms_total / args.steps
-        value = world * BATCH / (ms_step * 1e-3)
-        e2e = world * BATCH / (ms_e2e / args.steps * 1e-3)
+        value = world * batch / (ms_step * 1e-3)
+        e2e = world * batch / (ms_e2e / args.steps * 1e-3)
+        hbm, tf_burst, tf_sus, src = peaks()
         print(json.dumps({
-            "metric": "512x512 images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-            "config": {"workload": "generator_inference_3x512x512 (BASELINE.json configs[1])", "batch_per_gpu": BATCH,
-                       "global_batch": world * BATCH, "parallelism": f"replicas x{world}",
-                       "l2": "activation traffic per step (GBs) >> 126 MB L2; no flush needed",
-                       "achieved_tflops_per_gpu": G_GFLOP_PER_IMAGE * value / world / 1e3},
-            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
-                    "d2h_bytes_per_step": out_host.numel() * 4},
+            "metric": "512x512 training images/sec" if train else "512x512 images/sec", "value": value,
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 (G, D) + f16 (VGG), fp32 accumulate" if train else "tf32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "batch_per_gpu": batch, "global_batch": world * batch,
+                       "parallelism": (f"dp{world}: 2 flat NCCL grad all-reduces/step" if train else f"replicas x{world}"),
+                       "l2": "per-step activation traffic (tens of GB) >> 126 MB L2; no flush needed",
+                       "achieved_tflops_per_gpu": gflop * value / world / 1e3,
+                       "frac_of_bf16_peak": gflop * value / world / 1e3 / tf_burst},
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "cpu_baseline": {"value": cpu_val, "unit": "images/s", "cores": cpu_threads, "kind": "port",
-                             "sample": f"oracle Generator.forward, 2 iterations of 2x3x512x512 ({cpu_dt:.1f} s)"},
+                             "sample": f"oracle {'train_step' if train else 'Generator.forward'}, "
+                                       f"{1 if train else 2} iteration(s) of {cpu_batch}x3x512x512 ({cpu_dt:.1f} s)"},
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -252,9 +316,11 @@ def run_native(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "inference"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 16 train / 32 inference)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -134,8 +134,14 @@ int uegan_spectral_sigma(const float* w, float* u, float* v, int32_t rows, int32
  * HOST arrays of device pointers. */
 int uegan_gan_loss_fwd(int32_t mode, int32_t for_discriminator, int32_t nscales, const float* const* real,
                        const float* const* fake, const int64_t* counts, double* ws, float* loss_out, void* stream);
+/* The same loss in three phases for data-parallel training (the relativistic means are over the GLOBAL
+ * batch): phase 0 local sums -> ws[0..2*nscales) ; [all-reduce ws[0..16)] ; phase 1 hinge terms and their derivative
+ * sums -> ws[16..48) ; [all-reduce ws[16..48)] ; phase 2 loss_out = global loss.  world = number of ranks. */
+int uegan_gan_loss_phase(int32_t phase, int32_t mode, int32_t for_discriminator, int32_t nscales,
+                         const float* const* real, const float* const* fake, const int64_t* counts, int32_t world,
+                         double* ws, float* loss_out, void* stream);
 /* d_real[i] / d_fake[i] (either may be NULL) += gscale * dloss/dmap, gscale = gscale_host * (gscale_dev ? *gscale_dev : 1).
- * Includes the path through the batch-global means. */
+ * Includes the path through the batch-global means.  Data parallel: pass gscale_host = -(world size). */
 int uegan_gan_loss_bwd(int32_t mode, int32_t for_discriminator, int32_t nscales, const float* const* real,
                        const float* const* fake, const int64_t* counts, const double* ws, float* const* d_real,
                        float* const* d_fake, const float* gscale_dev, float gscale_host, void* stream);

@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 for t in "$@"; do
   name=$(basename "$t" .py)
   echo "=== $t"
-  timeout 600 python -m pytest "$t" -m gpu -q -s --no-header -p no:cacheprovider > "gpurun_out/$name.log" 2>&1
+  timeout 600 python -m pytest "$t" -m gpu -q -s --durations=4 --no-header -p no:cacheprovider > "gpurun_out/$name.log" 2>&1
   echo "exit $?" >> "gpurun_out/$name.log"
   tail -n 25 "gpurun_out/$name.log"
 done

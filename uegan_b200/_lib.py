@@ -56,6 +56,9 @@ SYMBOLS = {
                                             C.POINTER(C.c_void_p), C.c_void_p]),
     "uegan_gan_loss_fwd": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uegan_gan_loss_phase": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "uegan_gan_loss_bwd": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.c_void_p, C.c_float, C.c_void_p]),

@@ -151,7 +151,8 @@ def _g_backward(G, x, out_grad, ws, need_dx):
     K.head_bwd(out_grad, P["res"], x, 2, dz5w)
     c51 = G.dec5[1].conv
     wgrad("dec5.1.main.1", c51, P["t"], dz5w, 7, 1, 3)
-    gb = torch.empty_like(c51.bias); K.channel_sum(dz5, gb, 0, 3); grads["dec5.1.main.1.bias"] = gb
+    gb = torch.empty(4, dtype=torch.float32, device=dev); K.channel_sum(dz5, gb, 0, 4)
+    grads["dec5.1.main.1.bias"] = gb[:3]
     dxp = S("dxp_t", h + 6, w + 6, d)
     K.conv_dgrad(dz5, c51.weight, 7, 1, dxp, cache, "dec5.1")
     dt = S("dt", h, w, d, 2)
@@ -421,28 +422,28 @@ def discriminator_apply(module, x):
 # =================================================================================================
 class _GanLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mode, for_d, n, *maps):
+    def forward(ctx, mode, for_d, n, group, *maps):
         real = [t.detach().contiguous().float() for t in maps[:n]]
         fake = [t.detach().contiguous().float() for t in maps[n:]]
         ws = torch.empty(48, dtype=torch.float64, device=real[0].device)
         loss = torch.empty((), dtype=torch.float32, device=real[0].device)
-        K.gan_loss_fwd(mode, for_d, real, fake, ws, loss)
+        ctx.world = K.gan_loss_fwd(mode, for_d, real, fake, ws, loss, group)
         ctx.mode, ctx.for_d, ctx.n, ctx.real, ctx.fake, ctx.ws = mode, for_d, n, real, fake, ws
         return loss
 
     @staticmethod
     def backward(ctx, gout):
         n = ctx.n
-        need = ctx.needs_input_grad[3:]
+        need = ctx.needs_input_grad[4:]
         d_real = [torch.zeros_like(t) if need[i] else None for i, t in enumerate(ctx.real)]
         d_fake = [torch.zeros_like(t) if need[n + i] else None for i, t in enumerate(ctx.fake)]
         g = gout.detach().reshape(1).float().contiguous()
-        K.gan_loss_bwd(ctx.mode, ctx.for_d, ctx.real, ctx.fake, ctx.ws, d_real, d_fake, gscale_dev=g)
-        return (None, None, None) + tuple(d_real) + tuple(d_fake)
+        K.gan_loss_bwd(ctx.mode, ctx.for_d, ctx.real, ctx.fake, ctx.ws, d_real, d_fake, gscale_dev=g, world=ctx.world)
+        return (None, None, None, None) + tuple(d_real) + tuple(d_fake)
 
 
-def gan_loss_apply(mode, for_d, real, fake):
-    return _GanLossFn.apply(mode, for_d, len(real), *real, *fake)
+def gan_loss_apply(mode, for_d, real, fake, group=None):
+    return _GanLossFn.apply(mode, for_d, len(real), group, *real, *fake)
 
 
 class _MsRecFn(torch.autograd.Function):

@@ -137,68 +137,46 @@ __global__ void grad_combine_kernel(CombineArgs q, long long total) {
 // per-channel sum over n, h, w (bias gradient): out[c] += sum
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void channel_sum_kernel(TGeom s, int c_off, int cch, float* __restrict__ out, int pix_per_block) {
-  const int c = threadIdx.x % cch;
-  const int grp = threadIdx.x / cch;
-  const int groups = blockDim.x / cch;
-  const long long npix = (long long)s.n * s.h * s.w;
-  const long long p0 = (long long)blockIdx.x * pix_per_block;
-  long long p1 = p0 + pix_per_block;
-  if (p1 > npix) p1 = npix;
-  const T* base = static_cast<const T*>(s.data);
-  float sum = 0.f;
-  for (long long p = p0 + grp; p < p1; p += groups) {
-    const int x = (int)(p % s.w);
-    const int y = (int)((p / s.w) % s.h);
-    const int n = (int)(p / ((long long)s.w * s.h));
-    sum += to_f32<T>(base[toff(s, n, y, x, c_off + c)]);
+struct ChannelSumOp {
+  TGeom s;
+  int c_off;
+  float* out;
+  __device__ void acc(int n, int y, int x, int c, float (&a)[Vec<T>::N][1]) const {
+    float v[Vec<T>::N];
+    Vec<T>::load(static_cast<const T*>(s.data) + toff(s, n, y, x, c_off + c), v);
+#pragma unroll
+    for (int k = 0; k < Vec<T>::N; ++k) a[k][0] += v[k];
   }
-  extern __shared__ float shf[];
-  shf[threadIdx.x] = sum;
-  __syncthreads();
-  if (grp == 0) {
-    for (int g = 1; g < groups; ++g) sum += shf[g * cch + c];
-    atomicAdd(out + c, sum);
-  }
-}
+  __device__ void flush(int n, int c, const float (&t)[1]) const { atomicAdd(out + c, t[0]); }
+};
 
 // ------------------------------------------------------------------------------------------
 // InstanceNorm backward.  xhat = (z - mean) * rstd ; out = xhat
 //   dz = rstd * (dout - mean_p(dout) - xhat * mean_p(dout * xhat))
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void in_bwd_stats_kernel(TGeom dz_src, int d_c_off, TGeom z, const float* __restrict__ mr,
-                                    double* __restrict__ sums, int cch, int pix_per_block) {
-  const int c = threadIdx.x % cch;
-  const int grp = threadIdx.x / cch;
-  const int groups = blockDim.x / cch;
-  const int n = blockIdx.y;
-  const long long npix = (long long)z.h * z.w;
-  const long long p0 = (long long)blockIdx.x * pix_per_block;
-  long long p1 = p0 + pix_per_block;
-  if (p1 > npix) p1 = npix;
-  const float mean = mr[((long long)n * cch + c) * 2], rstd = mr[((long long)n * cch + c) * 2 + 1];
-  double s1 = 0.0, s2 = 0.0;
-  for (long long p = p0 + grp; p < p1; p += groups) {
-    const int y = (int)(p / z.w), x = (int)(p % z.w);
-    const float g = to_f32<T>(static_cast<const T*>(dz_src.data)[toff(dz_src, n, y, x, d_c_off + c)]);
-    const float xh = (to_f32<T>(static_cast<const T*>(z.data)[toff(z, n, y, x, c)]) - mean) * rstd;
-    s1 += g;
-    s2 += (double)g * xh;
-  }
-  extern __shared__ double shd[];
-  shd[threadIdx.x] = s1;
-  shd[blockDim.x + threadIdx.x] = s2;
-  __syncthreads();
-  if (grp == 0) {
-    for (int g = 1; g < groups; ++g) {
-      s1 += shd[g * cch + c];
-      s2 += shd[blockDim.x + g * cch + c];
+struct InBwdStatsOp {
+  TGeom g; int d_c_off;
+  TGeom z;
+  const float* mr;
+  double* sums;
+  __device__ void acc(int n, int y, int x, int c, float (&a)[Vec<T>::N][2]) const {
+    float gv[Vec<T>::N], zv[Vec<T>::N];
+    Vec<T>::load(static_cast<const T*>(g.data) + toff(g, n, y, x, d_c_off + c), gv);
+    Vec<T>::load(static_cast<const T*>(z.data) + toff(z, n, y, x, c), zv);
+#pragma unroll
+    for (int k = 0; k < Vec<T>::N; ++k) {
+      const long long si = ((long long)n * z.c + c + k) * 2;
+      const float xh = (zv[k] - mr[si]) * mr[si + 1];
+      a[k][0] += gv[k];
+      a[k][1] += gv[k] * xh;
     }
-    atomicAdd(&sums[((long long)n * cch + c) * 2], s1);
-    atomicAdd(&sums[((long long)n * cch + c) * 2 + 1], s2);
   }
-}
+  __device__ void flush(int n, int c, const float (&t)[2]) const {
+    atomicAdd(&sums[((long long)n * z.c + c) * 2], (double)t[0]);
+    atomicAdd(&sums[((long long)n * z.c + c) * 2 + 1], (double)t[1]);
+  }
+};
 template <typename T>
 __global__ void in_bwd_apply_kernel(TGeom dsrc, int d_c_off, TGeom z, TGeom dst, const float* __restrict__ mr,
                                     const double* __restrict__ sums, double inv_npix, long long total) {
@@ -332,40 +310,29 @@ __global__ void maxpool2x2_bwd_kernel(TGeom src, TGeom dpool, TGeom dst, long lo
 // per-element gradients of a mean over 1e8 elements are far below fp16's range unscaled), zero halo.
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void tap_bwd_stats_kernel(TGeom x, TGeom y, const float* __restrict__ mrx, const float* __restrict__ mry,
-                                     double* __restrict__ sums, int pix_per_block) {
-  const int c = threadIdx.x % x.c;
-  const int grp = threadIdx.x / x.c;
-  const int groups = blockDim.x / x.c;
-  const int n = blockIdx.y;
-  const long long npix = (long long)x.h * x.w;
-  const long long p0 = (long long)blockIdx.x * pix_per_block;
-  long long p1 = p0 + pix_per_block;
-  if (p1 > npix) p1 = npix;
-  const long long si = ((long long)n * x.c + c) * 2;
-  const float mx = mrx[si], rx = mrx[si + 1], my = mry[si], ry = mry[si + 1];
-  double s1 = 0.0, s2 = 0.0;
-  for (long long p = p0 + grp; p < p1; p += groups) {
-    const int yy = (int)(p / x.w), xx = (int)(p % x.w);
-    const float xh = (to_f32<T>(static_cast<const T*>(x.data)[toff(x, n, yy, xx, c)]) - mx) * rx;
-    const float yh = (to_f32<T>(static_cast<const T*>(y.data)[toff(y, n, yy, xx, c)]) - my) * ry;
-    const float e = xh - yh;
-    s1 += e;
-    s2 += (double)e * xh;
-  }
-  extern __shared__ double shd[];
-  shd[threadIdx.x] = s1;
-  shd[blockDim.x + threadIdx.x] = s2;
-  __syncthreads();
-  if (grp == 0) {
-    for (int g = 1; g < groups; ++g) {
-      s1 += shd[g * x.c + c];
-      s2 += shd[blockDim.x + g * x.c + c];
+struct TapBwdStatsOp {
+  TGeom x, y;
+  const float* mrx;
+  const float* mry;
+  double* sums;
+  __device__ void acc(int n, int yy, int xx, int c, float (&a)[Vec<T>::N][2]) const {
+    float xv[Vec<T>::N], yv[Vec<T>::N];
+    Vec<T>::load(static_cast<const T*>(x.data) + toff(x, n, yy, xx, c), xv);
+    Vec<T>::load(static_cast<const T*>(y.data) + toff(y, n, yy, xx, c), yv);
+#pragma unroll
+    for (int k = 0; k < Vec<T>::N; ++k) {
+      const long long si = ((long long)n * x.c + c + k) * 2;
+      const float xh = (xv[k] - mrx[si]) * mrx[si + 1];
+      const float e = xh - (yv[k] - mry[si]) * mry[si + 1];
+      a[k][0] += e;
+      a[k][1] += e * xh;
     }
-    atomicAdd(&sums[si], s1);
-    atomicAdd(&sums[si + 1], s2);
   }
-}
+  __device__ void flush(int n, int c, const float (&t)[2]) const {
+    atomicAdd(&sums[((long long)n * x.c + c) * 2], (double)t[0]);
+    atomicAdd(&sums[((long long)n * x.c + c) * 2 + 1], (double)t[1]);
+  }
+};
 template <typename T, typename TG>
 __global__ void tap_bwd_apply_kernel(TGeom x, TGeom y, TGeom deep, int has_deep, TGeom dst, const float* __restrict__ mrx,
                                      const float* __restrict__ mry, const double* __restrict__ sums, double inv_npix,
@@ -489,12 +456,19 @@ int uegan_channel_sum(const uegan_tensor* src, int32_t c_off, int32_t channels, 
   const TGeom s = geom(*src);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   UEGAN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * channels, st));
-  int threads = channels;
-  while (threads < 256) threads += channels;
-  const long long npix = (long long)s.n * s.h * s.w;
-  const int ppb = 2048;
-  UEGAN_DISPATCH(src->dtype, channel_sum_kernel,
-                 <<<nblk(npix, ppb), threads, sizeof(float) * threads, st>>>(s, c_off, channels, out, ppb));
+  const int vn = 16 / dtype_size(src->dtype);
+  UEGAN_CHECK(channels % vn == 0 && c_off % vn == 0 && 256 % (channels / vn) == 0,
+              "channel_sum: unsupported channel count %d", channels);
+  if (src->dtype == UEGAN_F32) {
+    ChannelSumOp<float> op{s, c_off, out};
+    launch_strip_reduce<float, 1>(op, channels, s.n, s.h, s.w, st);
+  } else if (src->dtype == UEGAN_BF16) {
+    ChannelSumOp<__nv_bfloat16> op{s, c_off, out};
+    launch_strip_reduce<__nv_bfloat16, 1>(op, channels, s.n, s.h, s.w, st);
+  } else {
+    ChannelSumOp<__half> op{s, c_off, out};
+    launch_strip_reduce<__half, 1>(op, channels, s.n, s.h, s.w, st);
+  }
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -509,13 +483,18 @@ int uegan_instance_norm_bwd(const uegan_tensor* dout, int32_t d_c_off, const ueg
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nc = zz.n * zz.c;
   UEGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * nc, st));
-  int threads = zz.c;
-  while (threads < 256) threads += zz.c;
   const long long npix = (long long)zz.h * zz.w;
-  const int ppb = 1024;
-  const dim3 grid(nblk(npix, ppb), (unsigned)zz.n);
-  UEGAN_DISPATCH(z->dtype, in_bwd_stats_kernel,
-                 <<<grid, threads, sizeof(double) * 2 * threads, st>>>(g, d_c_off, zz, mean_rstd, ws, zz.c, ppb));
+  UEGAN_CHECK(256 % (zz.c / (16 / dtype_size(z->dtype))) == 0, "instance_norm_bwd: unsupported channel count %d", zz.c);
+  if (z->dtype == UEGAN_F32) {
+    InBwdStatsOp<float> op{g, d_c_off, zz, mean_rstd, ws};
+    launch_strip_reduce<float, 2>(op, zz.c, zz.n, zz.h, zz.w, st);
+  } else if (z->dtype == UEGAN_BF16) {
+    InBwdStatsOp<__nv_bfloat16> op{g, d_c_off, zz, mean_rstd, ws};
+    launch_strip_reduce<__nv_bfloat16, 2>(op, zz.c, zz.n, zz.h, zz.w, st);
+  } else {
+    InBwdStatsOp<__half> op{g, d_c_off, zz, mean_rstd, ws};
+    launch_strip_reduce<__half, 2>(op, zz.c, zz.n, zz.h, zz.w, st);
+  }
   const int vn = 16 / dtype_size(z->dtype);
   const long long total = (long long)d.n * d.hp * d.wp * (zz.c / vn);
   UEGAN_DISPATCH(z->dtype, in_bwd_apply_kernel,
@@ -570,12 +549,12 @@ int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nc = gx.n * gx.c;
   UEGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * nc, st));
-  int threads = gx.c;
-  while (threads < 256) threads += gx.c;
   const long long npix = (long long)gx.h * gx.w;
-  const int ppb = 1024;
-  const dim3 grid(nblk(npix, ppb), (unsigned)gx.n);
-  tap_bwd_stats_kernel<__half><<<grid, threads, sizeof(double) * 2 * threads, st>>>(gx, gy, mean_rstd_x, mean_rstd_y, ws, ppb);
+  UEGAN_CHECK(256 % (gx.c / 8) == 0, "in_mse_bwd: unsupported channel count %d", gx.c);
+  {
+    TapBwdStatsOp<__half> op{gx, gy, mean_rstd_x, mean_rstd_y, ws};
+    launch_strip_reduce<__half, 2>(op, gx.c, gx.n, gx.h, gx.w, st);
+  }
   const double numel = (double)gx.n * gx.c * (double)npix;
   const long long total = (long long)gd.n * gd.hp * gd.wp * (gx.c / 8);
   tap_bwd_apply_kernel<__half, __half><<<nblk(total, 256), 256, 0, st>>>(

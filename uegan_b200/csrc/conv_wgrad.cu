@@ -8,7 +8,9 @@
 // 8 MMAs (K = 8 pixels = one swizzle atom of rows) per stage.  Channels beyond the tensor are TMA zero-fill, so
 // Cout < 128 costs no bandwidth.  Split-K over CTAs, fp32 atomics into the OIHW gradient (caller zeroes it).
 // Small-Cin layers (RGB stored as 4 channels, enc1 / d1) use the sliding-window map of the fprop kernel: N = the 32
-// (s, c) values of one filter row.
+// (s, c) values of one filter row.  Tiny-Cout layers (G's last conv, D's prediction heads) swap the roles: M = 128
+// consecutive (s, c) window elements of one filter row, N = the 32 stored dz channels -- k launches-worth of taps
+// instead of k*k, and no MMA rows wasted on zero-filled output channels.
 #include "common.cuh"
 #include "host_util.h"
 
@@ -25,6 +27,7 @@ struct WgradParams {
   int n_boxes;                     // N / 32
   int num_stages, stage_bytes;
   int window_mode;                 // 1: small-Cin sliding-window B map
+  int swap_mode;                   // 1: tiny Cout: M = 128 window elements (s, c) of one filter row, N = dz channels
   int cout, cin, cin_total, cin_first, x_c;
   int m_tiles, n_chunks;
   float* dw;                       // OIHW fp32
@@ -49,7 +52,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int per = (p.total_ktiles + p.ksplit - 1) / p.ksplit;
   const int kt0 = blockIdx.x * per;
   const int kt1 = min(kt0 + per, p.total_ktiles);
-  const int r = p.window_mode ? tap : tap / p.k, s_ = p.window_mode ? 0 : tap % p.k;
+  const int r = (p.window_mode || p.swap_mode) ? tap : tap / p.k, s_ = (p.window_mode || p.swap_mode) ? 0 : tap % p.k;
   const int N = p.n_boxes * 32;
 
   if (warp == 0 && elect_one()) {
@@ -84,12 +87,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint8_t* sa = smem + stage * p.stage_bytes;
           uint8_t* sb = sa + kWgABytes;
           mbar_arrive_expect_tx(&full_bar[stage], tx);
-          for (int g = 0; g < 4; ++g)
-            tma_load_4d(&tmA, &full_bar[stage], sa + g * kWgBoxBytes, mt * 128 + g * 32, wo0, ho0, n);
-          // B map = the fprop sliding-window map {window, wo, r, ho, n}: tap column s and channel offset are both
-          // positions inside the window of k*C contiguous (s, c) values that starts at the pixel
-          for (int g = 0; g < p.n_boxes; ++g)
-            tma_load_5d(&tmB, &full_bar[stage], sb + g * kWgBoxBytes, s_ * p.x_c + nc * N + g * 32, wo0, r, ho0, n);
+          if (p.swap_mode) {
+            // M operand = 128 consecutive window elements (s, c) of filter row r, N operand = the 32 stored dz channels
+            for (int g = 0; g < 4; ++g)
+              tma_load_5d(&tmB, &full_bar[stage], sa + g * kWgBoxBytes, mt * 128 + g * 32, wo0, r, ho0, n);
+            tma_load_4d(&tmA, &full_bar[stage], sb, 0, wo0, ho0, n);
+          } else {
+            for (int g = 0; g < 4; ++g)
+              tma_load_4d(&tmA, &full_bar[stage], sa + g * kWgBoxBytes, mt * 128 + g * 32, wo0, ho0, n);
+            // B map = the fprop sliding-window map {window, wo, r, ho, n}: tap column s and channel offset are both
+            // positions inside the window of k*C contiguous (s, c) values that starts at the pixel
+            for (int g = 0; g < p.n_boxes; ++g)
+              tma_load_5d(&tmB, &full_bar[stage], sb + g * kWgBoxBytes, s_ * p.x_c + nc * N + g * 32, wo0, r, ho0, n);
+          }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -131,6 +141,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t rr[16];
         tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, rr);
         tmem_ld_wait();
+        if (p.swap_mode) {
+          const int j = o;  // window element (s, c) of filter row r
+          const int ss = j / p.x_c, c = j % p.x_c;
+          if (ss < p.k && c < p.cin) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int oc = c0 + i;
+              if (oc < p.cout)
+                atomicAdd(p.dw + ((long long)oc * p.cin_total + p.cin_first + c) * kk + r * p.k + ss,
+                          __uint_as_float(rr[i]) * sc);
+            }
+          }
+          continue;
+        }
         if (o >= p.cout) continue;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -185,8 +209,14 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   p.taps = window ? k : k * k;
   p.cout = cout; p.cin = cin; p.cin_total = cin_total; p.cin_first = cin_first;
   p.m_tiles = (cout + 127) / 128;
+  const bool swap = !window && cout <= 16 && dz->c == 32;
+  p.swap_mode = swap;
   int N;
-  if (window) {
+  if (swap) {
+    N = 32; p.n_chunks = 1;
+    p.taps = k;
+    p.m_tiles = (k * x->c + 127) / 128;
+  } else if (window) {
     UEGAN_CHECK(k * 4 <= 32, "conv2d_wgrad: window mode needs k*4 <= 32");
     N = 32; p.n_chunks = 1;
   } else {

@@ -92,6 +92,56 @@ __device__ __forceinline__ long long toff(const TGeom& g, int n, int y, int x, i
 }
 
 // ------------------------------------------------------------------------------------------
+// Strip reduction skeleton for every per-channel / per-(n, c) sum over pixels (InstanceNorm statistics and their
+// backward, bias gradients, the perceptual MSE): block = (`rows` image rows of image n), thread = (pixel lane,
+// 16-byte channel vector).  Loads are 16 B per thread, coalesced along C then W; integer division only per row;
+// fp32 partials per thread, one smem tree per block, then Op::flush (atomics) once per (block, channel).
+//   Op: void acc(int n, int y, int x, int c, float (&a)[VN][NACC])  -- add the contributions of channels c..c+VN-1
+//       void flush(int n, int c, const float (&tot)[NACC])          -- publish one channel's block total
+// ------------------------------------------------------------------------------------------
+template <typename T, int NACC, typename Op>
+__global__ void __launch_bounds__(256) strip_reduce_kernel(Op op, int cch, int h, int w, int rows) {
+  constexpr int VN = Vec<T>::N;
+  __shared__ float sh[256 * VN * NACC];
+  const int cv = cch / VN;
+  const int lanes = 256 / cv;
+  const int lane = threadIdx.x / cv, c = (threadIdx.x % cv) * VN;
+  const int n = blockIdx.y;
+  const int y0 = blockIdx.x * rows, y1 = min(y0 + rows, h);
+  float a[VN][NACC];
+#pragma unroll
+  for (int k = 0; k < VN; ++k)
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) a[k][j] = 0.f;
+  if (lane < lanes) {
+    for (int y = y0; y < y1; ++y)
+      for (int x = lane; x < w; x += lanes) op.acc(n, y, x, c, a);
+  }
+#pragma unroll
+  for (int k = 0; k < VN; ++k)
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) sh[(threadIdx.x * VN + k) * NACC + j] = (lane < lanes) ? a[k][j] : 0.f;
+  __syncthreads();
+  // each thread totals one channel (or several when cch > 256) over the pixel lanes
+  for (int ch = threadIdx.x; ch < cch; ch += 256) {
+    const int v = ch / VN, k = ch % VN;
+    float tot[NACC];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) tot[j] = 0.f;
+    for (int l = 0; l < lanes; ++l)
+#pragma unroll
+      for (int j = 0; j < NACC; ++j) tot[j] += sh[((l * cv + v) * VN + k) * NACC + j];
+    op.flush(n, ch, tot);
+  }
+}
+template <typename T, int NACC, typename Op>
+static void launch_strip_reduce(const Op& op, int cch, int n, int h, int w, cudaStream_t st) {
+  const int rows = h >= 64 ? 8 : (h >= 16 ? 4 : h);
+  dim3 grid((unsigned)((h + rows - 1) / rows), (unsigned)n);
+  strip_reduce_kernel<T, NACC, Op><<<grid, 256, 0, st>>>(op, cch, h, w, rows);
+}
+
+// ------------------------------------------------------------------------------------------
 // NCHW fp32 (3 channels) -> NHWC with halo
 // ------------------------------------------------------------------------------------------
 template <typename T>
@@ -166,36 +216,24 @@ __global__ void halo_fill_kernel(TGeom t, int reflect, long long total) {
 // InstanceNorm: per-(n,c) sum / sum of squares in fp64 (block partials -> atomics), finalize, apply
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void in_stats_kernel(TGeom s, double* __restrict__ stats, int pix_per_block) {
-  // blockDim.x = s.c * groups ; thread -> (channel, pixel group)
-  const int c = threadIdx.x % s.c;
-  const int grp = threadIdx.x / s.c;
-  const int groups = blockDim.x / s.c;
-  const int n = blockIdx.y;
-  const long long npix = (long long)s.h * s.w;
-  const long long p0 = (long long)blockIdx.x * pix_per_block;
-  long long p1 = p0 + pix_per_block;
-  if (p1 > npix) p1 = npix;
-  const T* base = static_cast<const T*>(s.data);
-  double sum = 0.0, sq = 0.0;
-  for (long long p = p0 + grp; p < p1; p += groups) {
-    const int y = (int)(p / s.w), x = (int)(p % s.w);
-    const float v = to_f32<T>(base[toff(s, n, y, x, c)]);
-    sum += v;
-    sq += (double)v * v;
+struct InStatsOp {
+  TGeom s;
+  double* stats;
+  __device__ void acc(int n, int y, int x, int c, float (&a)[Vec<T>::N][2]) const {
+    float v[Vec<T>::N];
+    Vec<T>::load(static_cast<const T*>(s.data) + toff(s, n, y, x, c), v);
+#pragma unroll
+    for (int k = 0; k < Vec<T>::N; ++k) { a[k][0] += v[k]; a[k][1] += v[k] * v[k]; }
   }
-  extern __shared__ double sh[];
-  sh[threadIdx.x] = sum;
-  sh[blockDim.x + threadIdx.x] = sq;
-  __syncthreads();
-  if (grp == 0) {
-    for (int g = 1; g < groups; ++g) {
-      sum += sh[g * s.c + c];
-      sq += sh[blockDim.x + g * s.c + c];
-    }
-    atomicAdd(&stats[((long long)n * s.c + c) * 2], sum);
-    atomicAdd(&stats[((long long)n * s.c + c) * 2 + 1], sq);
+  __device__ void flush(int n, int c, const float (&t)[2]) const {
+    atomicAdd(&stats[((long long)n * s.c + c) * 2], (double)t[0]);
+    atomicAdd(&stats[((long long)n * s.c + c) * 2 + 1], (double)t[1]);
   }
+};
+template <typename T>
+static void run_in_stats(const TGeom& s, double* stats, cudaStream_t st) {
+  InStatsOp<T> op{s, stats};
+  launch_strip_reduce<T, 2>(op, s.c, s.n, s.h, s.w, st);
 }
 
 __global__ void in_finalize_kernel(const double* __restrict__ stats, float* __restrict__ mr, int total, double inv_npix,
@@ -361,24 +399,17 @@ static int instance_norm_impl(const uegan_tensor* src, const uegan_tensor* dst, 
   UEGAN_CHECK(src->dtype == dst->dtype && src->n == dst->n && src->h == dst->h && src->w == dst->w,
               "instance_norm: src/dst mismatch");
   UEGAN_CHECK(dst_c_off >= 0 && dst_c_off + src->c <= dst->c && dst_c_off % 8 == 0, "instance_norm: bad slice");
-  UEGAN_CHECK(src->c <= 1024, "instance_norm: c too large");
+  UEGAN_CHECK(src->c <= 256 * (16 / dtype_size(src->dtype)) && 256 % (src->c / (16 / dtype_size(src->dtype))) == 0,
+              "instance_norm: unsupported channel count %d", src->c);
   const TGeom s = geom(*src), d = geom(*dst);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nc = s.n * s.c;
   const long long npix = (long long)s.h * s.w;
   if (compute_stats) {
     UEGAN_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * nc, st));
-    int threads = s.c;
-    while (threads < 256) threads += s.c;
-    int pix_per_block = 1024;
-    const dim3 grid((unsigned)((npix + pix_per_block - 1) / pix_per_block), (unsigned)s.n);
-    const size_t sh = sizeof(double) * 2 * threads;
-    if (src->dtype == UEGAN_F32)
-      in_stats_kernel<float><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
-    else if (src->dtype == UEGAN_BF16)
-      in_stats_kernel<__nv_bfloat16><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
-    else
-      in_stats_kernel<__half><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
+    if (src->dtype == UEGAN_F32) run_in_stats<float>(s, stats_ws, st);
+    else if (src->dtype == UEGAN_BF16) run_in_stats<__nv_bfloat16>(s, stats_ws, st);
+    else run_in_stats<__half>(s, stats_ws, st);
   }
   float* mr = reinterpret_cast<float*>(stats_ws + 2 * nc);  // finalised (mean, rstd) live after the raw sums
   in_finalize_kernel<<<nblocks(nc, 128), 128, 0, st>>>(stats_ws, mr, nc, 1.0 / (double)npix, eps);
@@ -398,24 +429,17 @@ int uegan_instance_norm_stats(const uegan_tensor* src, float eps, double* stats_
                               float** mean_rstd_out, void* stream) {
   UEGAN_CHECK(src && stats_ws && mean_rstd_out, "instance_norm_stats: null pointer");
   if (check_vec(*src, "instance_norm_stats")) return -1;
-  UEGAN_CHECK(src->c <= 1024, "instance_norm_stats: c too large");
+  UEGAN_CHECK(src->c <= 256 * (16 / dtype_size(src->dtype)) && 256 % (src->c / (16 / dtype_size(src->dtype))) == 0,
+              "instance_norm_stats: unsupported channel count %d", src->c);
   const TGeom s = geom(*src);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nc = s.n * s.c;
   const long long npix = (long long)s.h * s.w;
   if (!sums_ready) {
     UEGAN_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * nc, st));
-    int threads = s.c;
-    while (threads < 256) threads += s.c;
-    const int pix_per_block = 1024;
-    const dim3 grid((unsigned)((npix + pix_per_block - 1) / pix_per_block), (unsigned)s.n);
-    const size_t sh = sizeof(double) * 2 * threads;
-    if (src->dtype == UEGAN_F32)
-      in_stats_kernel<float><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
-    else if (src->dtype == UEGAN_BF16)
-      in_stats_kernel<__nv_bfloat16><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
-    else
-      in_stats_kernel<__half><<<grid, threads, sh, st>>>(s, stats_ws, pix_per_block);
+    if (src->dtype == UEGAN_F32) run_in_stats<float>(s, stats_ws, st);
+    else if (src->dtype == UEGAN_BF16) run_in_stats<__nv_bfloat16>(s, stats_ws, st);
+    else run_in_stats<__half>(s, stats_ws, st);
   }
   float* mr = reinterpret_cast<float*>(stats_ws + 2 * nc);
   in_finalize_kernel<<<nblocks(nc, 128), 128, 0, st>>>(stats_ws, mr, nc, 1.0 / (double)npix, eps);

@@ -17,6 +17,7 @@ struct GanArgs {
   int nscales;
   int mode;    // 0 rahinge, 1 rals
   int for_d;   // 1: discriminator side, 0: generator side
+  double count_mul;  // data-parallel world size: means and normalisation are over the GLOBAL batch
 };
 
 __device__ __forceinline__ void block_atomic_add(double v, double* dst) {
@@ -53,7 +54,7 @@ __device__ __forceinline__ void gan_terms(int mode, float sgn, float x, float& t
 }
 __global__ void gan_terms_kernel(GanArgs a, const double* __restrict__ ws, double* __restrict__ ws2) {
   const int i = blockIdx.y;
-  const double inv = 1.0 / (double)a.count[i];
+  const double inv = 1.0 / ((double)a.count[i] * a.count_mul);
   const float mr = (float)(ws[2 * i] * inv), mf = (float)(ws[2 * i + 1] * inv);
   const float sr = a.for_d ? -1.f : 1.f;  // sign for the real-side term
   const float sf = -sr;
@@ -73,7 +74,7 @@ __global__ void gan_terms_kernel(GanArgs a, const double* __restrict__ ws, doubl
 __global__ void gan_finalize_kernel(GanArgs a, const double* __restrict__ ws2, float* __restrict__ loss) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double l = 0.0;
-    for (int i = 0; i < a.nscales; ++i) l += 0.5 * (ws2[4 * i] + ws2[4 * i + 1]) / (double)a.count[i];
+    for (int i = 0; i < a.nscales; ++i) l += 0.5 * (ws2[4 * i] + ws2[4 * i + 1]) / ((double)a.count[i] * a.count_mul);
     loss[0] = (float)l;
   }
 }
@@ -82,7 +83,7 @@ __global__ void gan_finalize_kernel(GanArgs a, const double* __restrict__ ws2, f
 __global__ void gan_backward_kernel(GanArgs a, const double* __restrict__ ws, const double* __restrict__ ws2,
                                     const float* __restrict__ gscale_ptr, float gscale_host) {
   const int i = blockIdx.y;
-  const double inv = 1.0 / (double)a.count[i];
+  const double inv = 1.0 / ((double)a.count[i] * a.count_mul);
   const float mr = (float)(ws[2 * i] * inv), mf = (float)(ws[2 * i + 1] * inv);
   const float sr = a.for_d ? -1.f : 1.f, sf = -sr;
   const float gs = (gscale_ptr ? gscale_ptr[0] : 1.f) * gscale_host * 0.5f * (float)inv;
@@ -239,7 +240,7 @@ static int fill_gan_args(GanArgs& a, int nscales, const float* const* real, cons
   UEGAN_CHECK(nscales >= 1 && nscales <= kMaxScales, "gan loss: bad number of scales %d", nscales);
   UEGAN_CHECK(mode == 0 || mode == 1, "gan loss: mode must be 0 (rahinge) or 1 (rals)");
   memset(&a, 0, sizeof(a));
-  a.nscales = nscales; a.mode = mode; a.for_d = for_d;
+  a.nscales = nscales; a.mode = mode; a.for_d = for_d; a.count_mul = 1.0;
   for (int i = 0; i < nscales; ++i) {
     UEGAN_CHECK(real[i] && fake[i] && counts[i] > 0, "gan loss: null / empty prediction map %d", i);
     a.real[i] = real[i]; a.fake[i] = fake[i]; a.count[i] = counts[i];
@@ -262,11 +263,35 @@ int uegan_gan_loss_fwd(int32_t mode, int32_t for_discriminator, int32_t nscales,
   return 0;
 }
 
+int uegan_gan_loss_phase(int32_t phase, int32_t mode, int32_t for_discriminator, int32_t nscales,
+                         const float* const* real, const float* const* fake, const int64_t* counts, int32_t world,
+                         double* ws, float* loss_out, void* stream) {
+  GanArgs a;
+  if (fill_gan_args(a, nscales, real, fake, counts, mode, for_discriminator)) return -1;
+  UEGAN_CHECK(ws && world >= 1 && phase >= 0 && phase <= 2, "gan loss phase: bad arguments");
+  a.count_mul = (double)world;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(64, nscales);
+  if (phase == 0) {
+    UEGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 6 * kMaxScales, st));
+    gan_sums_kernel<<<grid, 256, 0, st>>>(a, ws);
+  } else if (phase == 1) {
+    gan_terms_kernel<<<grid, 256, 0, st>>>(a, ws, ws + 2 * kMaxScales);
+  } else {
+    UEGAN_CHECK(loss_out, "gan loss phase 2: null loss");
+    gan_finalize_kernel<<<1, 32, 0, st>>>(a, ws + 2 * kMaxScales, loss_out);
+  }
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int uegan_gan_loss_bwd(int32_t mode, int32_t for_discriminator, int32_t nscales, const float* const* real,
                        const float* const* fake, const int64_t* counts, const double* ws, float* const* d_real,
                        float* const* d_fake, const float* gscale_dev, float gscale_host, void* stream) {
   GanArgs a;
   if (fill_gan_args(a, nscales, real, fake, counts, mode, for_discriminator)) return -1;
+  a.count_mul = gscale_host < 0.f ? (double)(-gscale_host) : 1.0;  // world size is passed as a negative gscale_host
+  if (gscale_host < 0.f) gscale_host = 1.f;
   for (int i = 0; i < nscales; ++i) {
     a.d_real[i] = d_real ? d_real[i] : nullptr;
     a.d_fake[i] = d_fake ? d_fake[i] : nullptr;

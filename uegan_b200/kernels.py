@@ -111,7 +111,7 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
         ho = (x.h + 2 * pad - k) // stride + 1
         wo = (x.w + 2 * pad - k) // stride + 1
         cin = 3 if x.c * (4 if x.dtype == L.F32 else 2) == 16 else x.c
-        ev.append((s0, s1, 2.0 * x.n * ho * wo * cout * k * k * cin, x, cout, k, stride))
+        ev.append((s0, s1, 2.0 * x.n * ho * wo * cout * k * k * cin, x, cout, k, stride, "fprop", x.dtype))
     _count(1)
 
 
@@ -193,27 +193,45 @@ def _ptr_array(tensors):
     return arr
 
 
-def gan_loss_fwd(mode: int, for_d: bool, real, fake, ws: torch.Tensor, loss_out: torch.Tensor):
-    """real / fake: lists of contiguous fp32 CUDA prediction maps.  ws: >= 48 float64 (kept for gan_loss_bwd)."""
+def gan_loss_fwd(mode: int, for_d: bool, real, fake, ws: torch.Tensor, loss_out: torch.Tensor, group=None):
+    """real / fake: lists of contiguous fp32 CUDA prediction maps.  ws: >= 48 float64 (kept for gan_loss_bwd).
+    With a torch.distributed `group` the relativistic means and the normalisation run over the global batch: two
+    all-reduces of 16 / 32 doubles between the three phases."""
     assert len(real) == len(fake) and ws.dtype == torch.float64 and ws.numel() >= 48
     for t in list(real) + list(fake):
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
     counts = (C.c_int64 * len(real))(*[t.numel() for t in real])
     for r, f in zip(real, fake):
         assert r.numel() == f.numel()
-    L.check(L.load().uegan_gan_loss_fwd(mode, int(for_d), len(real), _ptr_array(real), _ptr_array(fake), counts,
-                                        ws.data_ptr(), loss_out.data_ptr(), _stream()), "gan_loss_fwd")
+    lib = L.load()
+    if group is None:
+        L.check(lib.uegan_gan_loss_fwd(mode, int(for_d), len(real), _ptr_array(real), _ptr_array(fake), counts,
+                                       ws.data_ptr(), loss_out.data_ptr(), _stream()), "gan_loss_fwd")
+        _count(3)
+        return 1
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rp, fp = _ptr_array(real), _ptr_array(fake)
+    L.check(lib.uegan_gan_loss_phase(0, mode, int(for_d), len(real), rp, fp, counts, world, ws.data_ptr(), None,
+                                     _stream()), "gan_loss_phase0")
+    dist.all_reduce(ws[:16], group=group)
+    L.check(lib.uegan_gan_loss_phase(1, mode, int(for_d), len(real), rp, fp, counts, world, ws.data_ptr(), None,
+                                     _stream()), "gan_loss_phase1")
+    dist.all_reduce(ws[16:48], group=group)
+    L.check(lib.uegan_gan_loss_phase(2, mode, int(for_d), len(real), rp, fp, counts, world, ws.data_ptr(),
+                                     loss_out.data_ptr(), _stream()), "gan_loss_phase2")
     _count(3)
+    return world
 
 
 def gan_loss_bwd(mode: int, for_d: bool, real, fake, ws: torch.Tensor, d_real, d_fake, gscale_dev=None,
-                 gscale_host: float = 1.0):
+                 world: int = 1):
     counts = (C.c_int64 * len(real))(*[t.numel() for t in real])
     L.check(L.load().uegan_gan_loss_bwd(mode, int(for_d), len(real), _ptr_array(real), _ptr_array(fake), counts,
                                         ws.data_ptr(), _ptr_array(d_real) if d_real is not None else None,
                                         _ptr_array(d_fake) if d_fake is not None else None,
-                                        gscale_dev.data_ptr() if gscale_dev is not None else None, float(gscale_host),
-                                        _stream()), "gan_loss_bwd")
+                                        gscale_dev.data_ptr() if gscale_dev is not None else None,
+                                        -float(world) if world > 1 else 1.0, _stream()), "gan_loss_bwd")
     _count(1)
 
 
@@ -268,7 +286,7 @@ def packed_weight_dgrad(weight: torch.Tensor, cout_stored: int, dtype: int, stri
 
 def conv_generic(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, pad: int, y: NHWC, y_c_off: int = 0,
                  bias=None, alpha=None, act: int = L.ACT_NONE, mask: Optional[NHWC] = None, mask_act: int = L.ACT_NONE,
-                 y_mul: int = 1, y_off_h: int = 0, y_off_w: int = 0):
+                 y_mul: int = 1, y_off_h: int = 0, y_off_w: int = 0, real_taps: Optional[int] = None):
     """conv_fprop with the dgrad-only options (activation-derivative mask, strided output view)."""
     lib = L.load()
     d = L.ConvDesc()
@@ -280,7 +298,17 @@ def conv_generic(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int
     d.mask = C.pointer(mask.ct) if mask is not None else None
     d.mask_act = mask_act
     d.y_mul, d.y_off_h, d.y_off_w = y_mul, y_off_h, y_off_w
+    ev = _Counters.conv_events
+    if ev is not None:
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
     L.check(lib.uegan_conv2d_fprop(C.byref(d), _stream()), "conv2d (dgrad)")
+    if ev is not None:
+        s1.record()
+        # algorithmic MACs of a data-gradient launch = its share of the forward conv's MACs (real taps only)
+        taps = real_taps if real_taps is not None else k * k
+        real_c = 3 if cout == 16 and y.c == 16 else cout
+        ev.append((s0, s1, 2.0 * x.n * x.h * x.w * x.c * real_c * taps, x, cout, k, stride, "dgrad", x.dtype))
     _count(1)
 
 
@@ -297,8 +325,9 @@ def conv_dgrad(dz: NHWC, weight: torch.Tensor, k: int, stride: int, dxp: NHWC, c
         for pj in range(stride):
             fn = lambda: packed_weight_dgrad(weight, dz.c, dz.dtype, stride, pi, pj, cin_first, cin)
             wp = cache.get((key, "dg", pi, pj, dz.dtype), weight, fn) if cache is not None else fn()
+            nr = len(range(pi, k, stride)) * len(range(pj, k, stride))  # taps of the forward kernel in this class
             conv_generic(dz, wp, cout_arg, kq, 1, kq - 1, dxp, 0, None, alpha, L.ACT_NONE, mask, mask_act,
-                         y_mul=stride, y_off_h=pi, y_off_w=pj)
+                         y_mul=stride, y_off_h=pi, y_off_w=pj, real_taps=nr)
 
 
 def conv_wgrad(x: NHWC, dz: NHWC, dw: torch.Tensor, k: int, stride: int, pad: int, cin_first: int = 0,
@@ -307,9 +336,17 @@ def conv_wgrad(x: NHWC, dz: NHWC, dw: torch.Tensor, k: int, stride: int, pad: in
     cout, cin_total = dw.shape[0], dw.shape[1]
     cin_n = (cin_total - cin_first) if cin is None else cin
     assert dw.is_cuda and dw.dtype == torch.float32 and dw.is_contiguous()
+    ev = _Counters.conv_events
+    if ev is not None:
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
     L.check(L.load().uegan_conv2d_wgrad(x.ref(), dz.ref(), cout, cin_n, cin_total, cin_first, k, stride, pad,
                                         dw.data_ptr(), alpha.data_ptr() if alpha is not None else None, float(scale),
                                         _stream()), "conv2d_wgrad")
+    if ev is not None:
+        s1.record()
+        real_cin = 3 if x.c == 4 else cin_n
+        ev.append((s0, s1, 2.0 * dz.n * dz.h * dz.w * cout * real_cin * k * k, x, cout, k, stride, "wgrad", x.dtype))
     _count(1)
 
 

@@ -142,6 +142,7 @@ class GANLoss(nn.Module):
             raise ValueError("Unexpected gan_mode {}".format(gan_mode))
         self.gan_mode = gan_mode
         self.real_label, self.fake_label, self.Tensor, self.opt = target_real_label, target_fake_label, tensor, opt
+        self.process_group = None  # set for data-parallel training: means / normalisation over the global batch
 
     def __call__(self, real_preds, fake_preds, target_is_real, for_real=None, for_fake=None, for_discriminator=True):
         if self.gan_mode not in K.GAN_MODES:
@@ -155,12 +156,12 @@ class GANLoss(nn.Module):
         mode = K.GAN_MODES[self.gan_mode]
         if torch.is_grad_enabled() and any(t.requires_grad for t in real + fake):
             from .autograd import gan_loss_apply
-            return gan_loss_apply(mode, bool(for_discriminator), real, fake)
+            return gan_loss_apply(mode, bool(for_discriminator), real, fake, self.process_group)
         real = [t.detach().contiguous().float() for t in real]
         fake = [t.detach().contiguous().float() for t in fake]
         ws = torch.empty(48, dtype=torch.float64, device=real[0].device)
         loss = torch.empty(1, dtype=torch.float32, device=real[0].device)
-        K.gan_loss_fwd(mode, bool(for_discriminator), real, fake, ws, loss)
+        K.gan_loss_fwd(mode, bool(for_discriminator), real, fake, ws, loss, self.process_group)
         return loss[0]
 
 

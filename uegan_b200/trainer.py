@@ -1,0 +1,239 @@
+"""Drop-in `trainer` module: `Trainer(loaders, args).train()` with the reference's step semantics
+(/root/reference/trainer.py:19-145, 313-354) on the native models / losses.
+
+The loop body of the reference (trainer.py:75-119) is factored into `train_step(real_raw, real_exp)`; everything the
+reference does around it that is not on the hot path (tensorboard, PSNR/SSIM/NIMA validation, sample dumps) is not
+re-implemented here -- use the reference's own trainer with `dropin/models.py` + `dropin/losses.py` for those.
+
+Data parallel: one process per GPU, batch sharded; two NCCL all-reduces per step (D gradients before
+`d_optimizer.step()`, G gradients before `g_optimizer.step()`, each ONE flat fp32 bucket) plus the two ~0.3 KB
+all-reduces per GAN-loss evaluation that keep the relativistic means global.
+"""
+from __future__ import annotations
+
+import os
+import random
+import time
+
+import torch
+import torch.nn as nn
+
+from .losses import GANLoss, MultiscaleRecLoss, PerceptualLoss
+from .models import Discriminator, Generator
+
+
+class ImagePool:
+    """History buffer of generated images (utils.py:23-50); pool_size=0 returns its input."""
+
+    def __init__(self, pool_size):
+        self.pool_size = pool_size
+        self.num_imgs, self.images = 0, []
+
+    def query(self, images):
+        if self.pool_size == 0:
+            return images
+        out = []
+        for image in images:
+            image = torch.unsqueeze(image.data, 0)
+            if self.num_imgs < self.pool_size:
+                self.num_imgs += 1
+                self.images.append(image)
+                out.append(image)
+            elif random.uniform(0, 1) > 0.5:
+                idx = random.randint(0, self.pool_size - 1)
+                out.append(self.images[idx].clone())
+                self.images[idx] = image
+            else:
+                out.append(image)
+        return torch.cat(out, 0)
+
+
+class _FlatGrads:
+    """All gradients of a module in ONE flat fp32 bucket (p.grad are views), so a step needs one all-reduce."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce(self, group):
+        import torch.distributed as dist
+        dist.all_reduce(self.flat, group=group)
+
+
+def init_weights(net, init_type="orthogonal", gain=0.02):
+    """trainer.py:357-390 (class-name matching on 'Conv')."""
+    def init_func(m):
+        classname = m.__class__.__name__
+        if hasattr(m, "weight") and (classname.find("Conv") != -1 or classname.find("Linear") != -1):
+            if init_type == "normal":
+                nn.init.normal_(m.weight.data, 0.0, gain)
+            elif init_type == "xavier":
+                nn.init.xavier_normal_(m.weight.data, gain=gain)
+            elif init_type == "xavier_uniform":
+                nn.init.xavier_uniform_(m.weight.data, gain=1.0)
+            elif init_type == "kaiming":
+                nn.init.kaiming_normal_(m.weight.data, a=0, mode="fan_in")
+            elif init_type == "kaiming_uniform":
+                nn.init.kaiming_uniform_(m.weight.data, a=0, mode="fan_in")
+            elif init_type == "orthogonal":
+                nn.init.orthogonal_(m.weight.data, gain=gain)
+            elif init_type == "none":
+                m.reset_parameters()
+            else:
+                raise NotImplementedError("Initialization method [{}] is not implemented".format(init_type))
+            if hasattr(m, "bias") and m.bias is not None:
+                nn.init.constant_(m.bias.data, 0.0)
+    net.apply(init_func)
+
+
+class Trainer(object):
+    def __init__(self, loaders, args, process_group=None, vgg_state_dict=None):
+        self.loaders, self.args = loaders, args
+        if not torch.cuda.is_available():
+            raise RuntimeError("uegan_b200.trainer.Trainer needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.group = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self.model_save_path = os.path.join(args.save_root_dir, args.version, args.model_save_path)
+        self.vgg_state_dict = vgg_state_dict
+        self.build_model()
+
+    # ------------------------------------------------------------------ trainer.py:313-354
+    def build_model(self):
+        a = self.args
+        self.G = Generator(a.g_conv_dim, a.g_norm_fun, a.g_act_fun, a.g_use_sn).to(self.device)
+        self.D = Discriminator(a.d_conv_dim, a.d_norm_fun, a.d_act_fun, a.d_use_sn, a.adv_loss_type).to(self.device)
+        if a.init_type:
+            init_weights(self.G, a.init_type, 0.02)
+            init_weights(self.D, a.init_type, 0.02)
+        if self.group is not None:  # identical replicas: broadcast rank 0's weights and spectral-norm buffers once
+            import torch.distributed as dist
+            for t in list(self.G.state_dict().values()) + list(self.D.state_dict().values()):
+                dist.broadcast(t, src=0, group=self.group)
+        if a.optimizer_type == "adam":
+            opt = lambda p, lr: torch.optim.Adam(params=p, lr=lr, betas=[a.beta1, a.beta2], weight_decay=0.0001)
+        elif a.optimizer_type == "rmsprop":
+            opt = lambda p, lr: torch.optim.RMSprop(params=p, lr=lr, alpha=a.alpha)
+        else:
+            raise NotImplementedError("=== Optimizer [{}] is not found ===".format(a.optimizer_type))
+        self.g_optimizer, self.d_optimizer = opt(self.G.parameters(), a.g_lr), opt(self.D.parameters(), a.d_lr)
+        if a.lr_decay:
+            rule = lambda epoch: 1.0 - max(0, epoch + 1 - a.lr_num_epochs_decay) / a.lr_decay_ratio
+            self.lr_scheduler_g = torch.optim.lr_scheduler.LambdaLR(self.g_optimizer, lr_lambda=rule)
+            self.lr_scheduler_d = torch.optim.lr_scheduler.LambdaLR(self.d_optimizer, lr_lambda=rule)
+        self.fake_exp_pool = ImagePool(a.pool_size)
+        self.g_grads, self.d_grads = _FlatGrads(self.G), _FlatGrads(self.D)
+        self.criterionPercep = PerceptualLoss(self.vgg_state_dict).to(self.device)
+        self.criterionIdt = MultiscaleRecLoss(scale=3, rec_loss_type=a.idt_loss_type, multiscale=True)
+        self.criterionGAN = GANLoss(a.adv_loss_type, tensor=torch.cuda.FloatTensor)
+        self.criterionGAN.process_group = self.group
+
+    # ------------------------------------------------------------------ trainer.py:75-119
+    def train_step(self, real_raw, real_exp, sync_scalars=True):
+        """One iteration on this rank's shard.  Returns the five loss values (python floats when sync_scalars, as
+        the reference's `.item()` calls; 0-d CUDA tensors otherwise, which keeps the step free of host syncs)."""
+        a, gan = self.args, self.criterionGAN
+        self.G.train(); self.D.train()
+        self.real_raw, self.real_exp = real_raw, real_exp
+        local = 1.0 / self.world  # mean-type losses are per-rank means; gradients are SUMMED across ranks
+        self.fake_exp = self.G(real_raw)
+        self.fake_exp_store = self.fake_exp_pool.query(self.fake_exp)
+        # ---- update D
+        self.d_grads.zero()
+        real_exp_preds = self.D(real_exp)
+        fake_exp_preds = self.D(self.fake_exp_store.detach())
+        d_loss = gan(real_exp_preds, fake_exp_preds, None, None, for_discriminator=True)
+        if a.adv_input:
+            input_preds = self.D(real_raw)
+            d_loss = d_loss + gan(real_exp_preds, input_preds, None, None, for_discriminator=True)
+        d_loss.backward()
+        if self.group is not None:
+            self.d_grads.all_reduce(self.group)
+        self.d_optimizer.step()
+        # ---- update G
+        self.g_grads.zero()
+        real_exp_preds = self.D(real_exp)
+        fake_exp_preds = self.D(self.fake_exp)
+        g_adv_loss = a.lambda_adv * gan(real_exp_preds, fake_exp_preds, None, None, for_discriminator=False)
+        g_percep_loss = a.lambda_percep * self.criterionPercep((self.fake_exp + 1.) / 2., (real_raw + 1.) / 2.)
+        self.real_exp_idt = self.G(real_exp)
+        g_idt_loss = a.lambda_idt * self.criterionIdt(self.real_exp_idt, real_exp)
+        g_loss = g_adv_loss + local * (g_percep_loss + g_idt_loss)
+        g_loss.backward()
+        if self.group is not None:
+            self.g_grads.all_reduce(self.group)
+        self.g_optimizer.step()
+        vals = dict(d_loss=d_loss, g_adv_loss=g_adv_loss, g_percep_loss=g_percep_loss, g_idt_loss=g_idt_loss,
+                    g_loss=g_adv_loss + g_percep_loss + g_idt_loss)
+        if sync_scalars:
+            vals = {k: float(v.detach()) for k, v in vals.items()}
+            for k, v in vals.items():
+                setattr(self, k, v)
+        return vals
+
+    # ------------------------------------------------------------------ trainer.py:40-145 (hot loop only)
+    def train(self):
+        a = self.args
+        loader = self.loaders.ref
+        steps_per_epoch = len(loader)
+        total_steps = int(a.total_epochs * steps_per_epoch)
+        start_step = 0
+        if a.pretrained_model:
+            start_step = int(a.pretrained_model * steps_per_epoch)
+            self.load_pretrained_model(a.pretrained_model)
+        save_step = max(1, int(a.model_save_epoch * steps_per_epoch))
+        it = iter(loader)
+        t0 = time.time()
+        for step in range(start_step, total_steps):
+            try:
+                x, y, _ = next(it)
+            except StopIteration:
+                it = iter(loader)
+                x, y, _ = next(it)
+            real_exp, real_raw = x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+            vals = self.train_step(real_raw, real_exp)
+            if (step + 1) % a.info_step == 0:
+                print("Elapse:{:>.8s}, D_Step:{:>6d}/{}, G_Step:{:>6d}/{}, D_loss:{:>.4f}, G_loss:{:>.4f}, "
+                      "G_percep_loss:{:>.4f}, G_adv_loss:{:>.4f}, G_idt_loss:{:>.4f}".format(
+                          str(time.time() - t0), step + 1, total_steps, step + 1, total_steps, vals["d_loss"],
+                          vals["g_loss"], vals["g_percep_loss"], vals["g_adv_loss"], vals["g_idt_loss"]))
+            if (step + 1) % save_step == 0:
+                self.save_checkpoint((step + 1) // steps_per_epoch)
+            if a.lr_decay and step % steps_per_epoch == 0:
+                epoch = step // steps_per_epoch
+                self.lr_scheduler_g.step(epoch=epoch)
+                self.lr_scheduler_d.step(epoch=epoch)
+
+    # ------------------------------------------------------------------ trainer.py:186-210, 402-423
+    def _ckpt_path(self, epoch):
+        return os.path.join(self.model_save_path, "{}_{}_{}.pth".format(self.args.version, self.args.adv_loss_type, epoch))
+
+    def save_checkpoint(self, epoch):
+        os.makedirs(self.model_save_path, exist_ok=True)
+        ck = {"G_net": self.G.state_dict(), "D_net": self.D.state_dict(), "epoch": epoch,
+              "g_optimizer": self.g_optimizer.state_dict(), "d_optimizer": self.d_optimizer.state_dict()}
+        if self.args.lr_decay:
+            ck["lr_scheduler_g"] = self.lr_scheduler_g.state_dict()
+            ck["lr_scheduler_d"] = self.lr_scheduler_d.state_dict()
+        torch.save(ck, self._ckpt_path(epoch))
+
+    def load_pretrained_model(self, resume_epochs):
+        ck = torch.load(self._ckpt_path(resume_epochs), map_location=self.device)
+        self.G.load_state_dict(ck["G_net"])
+        self.D.load_state_dict(ck["D_net"])
+        self.g_optimizer.load_state_dict(ck["g_optimizer"])
+        self.d_optimizer.load_state_dict(ck["d_optimizer"])
+        if self.args.lr_decay and "lr_scheduler_g" in ck:
+            self.lr_scheduler_g.load_state_dict(ck["lr_scheduler_g"])
+            self.lr_scheduler_d.load_state_dict(ck["lr_scheduler_d"])
