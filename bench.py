@@ -256,15 +256,17 @@ def run_native(args):
     ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 1))
 
     roof = None
-    if rank == 0:  # instrumented pass (rank 0 only, after the timed regions): CUDA events around every GEMM launch
-        reps = 2
-        K._Counters.conv_events = []
-        with ctx():
-            for _ in range(reps):
-                step_resident()
-        torch.cuda.synchronize()
-        ev = K._Counters.conv_events
-        K._Counters.conv_events = None
+    # instrumented pass after the timed regions: CUDA events around every GEMM launch.  Every rank runs it (the step
+    # contains collectives); rank 0 reports.
+    reps = 2
+    K._Counters.conv_events = []
+    with ctx():
+        for _ in range(reps):
+            step_resident()
+    barrier()
+    ev = K._Counters.conv_events
+    K._Counters.conv_events = None
+    if rank == 0:
         hbm, tf_burst, tf_sus, src = peaks()
         tot_ms = tot_fl = t_at_peak = 0.0
         per = {}
