@@ -101,7 +101,7 @@ def train_args(batch):
         g_lr=1e-4, d_lr=4e-4, beta1=0.5, beta2=0.999, alpha=0.9, lr_decay=False, pool_size=0, adv_input=True,
         lambda_adv=0.10, lambda_percep=1.0, lambda_idt=0.10, idt_loss_type="l1", save_root_dir="/tmp/uegan_b200",
         version="bench", model_save_path="models", train_batch_size=batch, total_epochs=1, pretrained_model=0.0,
-        model_save_epoch=1, info_step=100)
+        model_save_epoch=1, info_step=100, cuda_graph=False)
 
 
 # ------------------------------------------------------------------------------------------------ CPU (oracle port)
@@ -192,17 +192,32 @@ def run_native(args):
     x_host = x.cpu().pin_memory()
     if train:
         from uegan_b200.trainer import Trainer
-        T = Trainer(None, train_args(batch), process_group=group if world > 1 else None,
+        targs = train_args(batch)
+        targs.cuda_graph = bool(args.graph)
+        T = Trainer(None, targs, process_group=group if world > 1 else None,
                     vgg_state_dict=O.make_vgg_params())
         T.G.load_state_dict(O.make_generator_params(32, 0, "o1"))
         T.D.load_state_dict(O.make_discriminator_params(32, 1, "o1"))
         y = torch.rand(batch, 3, RES, RES, device="cuda", generator=gen) * 2 - 1
         y_host = y.cpu().pin_memory()
+        graphed = False
+        if args.graph:
+            try:
+                T.capture(x, y)
+                graphed = True
+            except Exception as e:  # noqa: BLE001 -- keep measuring (eagerly) if capture is not possible
+                sys.stderr.write(f"[bench] CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}\n")
+                torch.cuda.synchronize()
 
         def step_resident():
-            T.train_step(x, y, sync_scalars=False)
+            if graphed:
+                T.replay(x, y)
+            else:
+                T.train_step(x, y, sync_scalars=False)
 
         def step_e2e():
+            if graphed:  # H2D into the graph's static inputs, D2H of the five loss scalars
+                return T.replay(x_host, y_host, sync_scalars=True)
             xd, yd = x_host.cuda(non_blocking=True), y_host.cuda(non_blocking=True)
             return T.train_step(xd, yd, sync_scalars=True)  # 5 x .item(): the reference's D2H reads (trainer.py:98-119)
         h2d, d2h = 2 * x_host.numel() * 4, 5 * 4
@@ -225,11 +240,14 @@ def run_native(args):
         h2d, d2h = x_host.numel() * 4, x_host.numel() * 4
         gflop = G_GFLOP_PER_IMAGE
         ctx = torch.no_grad
+        graphed = False
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    host_ms = [0.0]
 
     def timed(fn, steps, warmup):
         with ctx():
@@ -239,8 +257,10 @@ def run_native(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             l0 = K.launches()
             e0.record()
+            h0 = time.perf_counter()
             for _ in range(steps):
                 fn()
+            host_ms[0] = (time.perf_counter() - h0) * 1e3 / steps  # time to ENQUEUE a step (no sync inside fn)
             e1.record()
             barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -252,6 +272,7 @@ def run_native(args):
     if sampler:
         sampler.start()
     ms_total, launches = timed(step_resident, args.steps, args.warmup)
+    host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if sampler else None
     ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 1))
 
@@ -262,20 +283,24 @@ def run_native(args):
     K._Counters.conv_events = []
     with ctx():
         for _ in range(reps):
-            step_resident()
+            if train:
+                T.train_step(x, y, sync_scalars=False)  # eager: events wrap individual launches
+            else:
+                step_resident()
     barrier()
     ev = K._Counters.conv_events
     K._Counters.conv_events = None
     if rank == 0:
         hbm, tf_burst, tf_sus, src = peaks()
         tot_ms = tot_fl = t_at_peak = 0.0
-        per = {}
+        per, groups = {}, {}
         for a, b, f, xt, cout, k, s, kind, dt in ev:
             ms = a.elapsed_time(b) / reps
             pk = tf_burst / 2 if dt == 0 else tf_burst
             tot_ms += ms; tot_fl += f / reps; t_at_peak += (f / reps) / (pk * 1e12)
             key = f"{kind} {'tf32' if dt == 0 else 'f16'} {xt.c}->{cout} k{k}s{s} @{xt.h}"
             e = per.setdefault(key, [0.0, 0.0]); e[0] += ms; e[1] += f / reps
+            g = groups.setdefault(f"{kind} {'tf32' if dt == 0 else 'f16'}", [0.0, 0.0]); g[0] += ms; g[1] += f / reps
         achieved = tot_fl / (tot_ms * 1e-3) / 1e12
         peak = tot_fl / t_at_peak / 1e12
         top = sorted(per.items(), key=lambda kv: -kv[1][0])[:24]
@@ -285,6 +310,7 @@ def run_native(args):
                 "gemm_ms_per_step": tot_ms, "step_ms": ms_total / args.steps, "gemm_launches_per_step": len(ev) // reps,
                 "gemm_share_of_step": tot_ms / (ms_total / args.steps),
                 "algorithmic_gflop_per_step_measured": tot_fl / 1e9,
+                "by_kind_ms_tflops": {k: [round(v[0], 2), round(v[1] / (v[0] * 1e-3) / 1e12, 1)] for k, v in groups.items()},
                 "top_layers_ms_tflops": {k: [round(v[0], 3), round(v[1] / (v[0] * 1e-3) / 1e12, 1)] for k, v in top}}
 
     if rank == 0:
@@ -303,6 +329,7 @@ def run_native(args):
             "config": {"workload": workload_name(args.workload), "batch_per_gpu": batch, "global_batch": world * batch,
                        "parallelism": (f"dp{world}: 2 flat NCCL grad all-reduces/step" if train else f"replicas x{world}"),
                        "l2": "per-step activation traffic (tens of GB) >> 126 MB L2; no flush needed",
+                       "host_enqueue_ms_per_step": host_enqueue_ms, "cuda_graph": bool(train and graphed),
                        "achieved_tflops_per_gpu": gflop * value / world / 1e3,
                        "frac_of_bf16_peak": gflop * value / world / 1e3 / tf_burst},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -323,6 +350,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "inference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 16 train / 32 inference)")
+    ap.add_argument("--graph", type=int, default=1, help="capture the training step into a CUDA graph (1) or run eagerly (0)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

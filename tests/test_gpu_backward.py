@@ -35,6 +35,12 @@ BWD_CASES = [
     ("k7s2_cin3", 2, 3, 96, 96, 32, 7, 2, "reflect"),
     ("k3_zero", 2, 64, 16, 16, 128, 3, 1, "zero"),
     ("big_c", 1, 512, 8, 8, 256, 3, 1, "reflect"),
+    # patch ("Toeplitz descriptor") wgrad: stride 1, Cout <= 64, C multiple of 32
+    ("patch_32_32_k3", 2, 32, 40, 24, 32, 3, 1, "reflect"),
+    ("patch_64_64_k3", 2, 64, 16, 32, 64, 3, 1, "reflect"),
+    ("patch_128_64_k3", 1, 128, 24, 16, 64, 3, 1, "reflect"),
+    ("patch_64_1_k7", 2, 64, 16, 24, 1, 7, 1, "reflect"),
+    ("patch_256_1_k5", 2, 256, 12, 16, 1, 5, 1, "reflect"),
 ]
 
 
@@ -58,7 +64,7 @@ def test_conv_dgrad_wgrad(K, case):
     c_x = 4 if cin == 3 else cin
     xt = fill_nhwc(K, x, c_x, pad, pm, L.F32)
     kq = (k + stride - 1) // stride
-    c_dz = 4 if cout == 3 else cout
+    c_dz = 4 if cout <= 4 else cout
     dz_d = fill_nhwc(K, dzv, c_dz, kq - 1, L.PAD_ZERO, L.F32)          # operand of dgrad (zero halo)
     # ---- dgrad -> gradient w.r.t. the padded input, then fold
     if cin != 3:

@@ -188,14 +188,33 @@ __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t tadd
     }
     if (p.mask) {
       const long long ko = (long long)mk_n * p.mask_img + (long long)mk_h * p.mask_row + (long long)mk_w * p.mask_pix + colbase + c0;
+      float t[16];
+      if (p.mask_kind == UEGAN_F32) {
+        const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.mask) + ko);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 qv = __ldg(mp + i);
+          t[4 * i] = qv.x; t[4 * i + 1] = qv.y; t[4 * i + 2] = qv.z; t[4 * i + 3] = qv.w;
+        }
+      } else {  // 16-bit mask: only the sign matters, which is bit 15 of either 16-bit format
+        const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.mask) + ko);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint4 qv = __ldg(mp + i);
+          const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t lo = w[j] & 0xFFFFu, hi = w[j] >> 16;
+            // value > 0  <=>  sign bit clear and not (+/-)zero
+            t[8 * i + 2 * j] = (lo != 0u && lo < 0x8000u) ? 1.f : 0.f;
+            t[8 * i + 2 * j + 1] = (hi != 0u && hi < 0x8000u) ? 1.f : 0.f;
+          }
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float t;
-        if (p.mask_kind == UEGAN_F32) t = __ldg(reinterpret_cast<const float*>(p.mask) + ko + i);
-        else if (p.mask_kind == UEGAN_F16) t = __half2float(reinterpret_cast<const __half*>(p.mask)[ko + i]);
-        else t = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.mask)[ko + i]);
-        if (p.mask_act == UEGAN_ACT_LRELU) v[i] *= (t > 0.f ? 1.f : 0.2f);
-        else v[i] = t > 0.f ? v[i] : 0.f;
+        if (p.mask_act == UEGAN_ACT_LRELU) v[i] *= (t[i] > 0.f ? 1.f : 0.2f);
+        else v[i] = t[i] > 0.f ? v[i] : 0.f;
       }
     }
     if (p.out_kind != UEGAN_F32) {

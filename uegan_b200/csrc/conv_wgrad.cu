@@ -179,6 +179,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // CUDA-core fallback for tiny spatial extents is not needed: TMA zero-fill covers partial tiles.
 // ------------------------------------------------------------------------------------------
 
+static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int cout, int cin, int cin_total,
+                              int cin_first, int k, int pad, float* dw, const float* alpha, float scale,
+                              cudaStream_t stream);
+
 }  // namespace uegan
 
 using namespace uegan;
@@ -196,6 +200,11 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   UEGAN_CHECK(cout <= dz->c && cin <= x->c && cin_first + cin <= cin_total, "conv2d_wgrad: channel mismatch");
   UEGAN_CHECK((dz->c * 4) % 128 == 0, "conv2d_wgrad: dz must store a multiple of 32 channels (got %d)", dz->c);
   const bool window = (x->c == 4);
+  if (stride == 1 && !window && k > 1) {
+    const int took = launch_wgrad_patch(x, dz, cout, cin, cin_total, cin_first, k, pad, dw_oihw, alpha_dev, scale,
+                                        static_cast<cudaStream_t>(stream));
+    if (took != 0) return took < 0 ? -1 : 0;
+  }
   UEGAN_CHECK(window || (x->c * 4) % 128 == 0, "conv2d_wgrad: x must store 4 or a multiple of 32 channels (got %d)", x->c);
 
   WgradParams p;
@@ -209,7 +218,8 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   p.taps = window ? k : k * k;
   p.cout = cout; p.cin = cin; p.cin_total = cin_total; p.cin_first = cin_first;
   p.m_tiles = (cout + 127) / 128;
-  const bool swap = !window && cout <= 16 && dz->c == 32;
+  // role swap pays whenever the output-channel side would leave MMA rows empty (Cout <= 32 of M = 128)
+  const bool swap = !window && cout <= 32 && dz->c == 32;
   p.swap_mode = swap;
   int N;
   if (swap) {
@@ -271,3 +281,227 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ==========================================================================================================
+// Patch ("Toeplitz descriptor") weight gradient for stride-1 convolutions of low-channel, high-resolution layers.
+//   D[(r, s, c)][o] = sum_pix x[pix + (r, s)][c] * dz[pix][o]      (roles swapped: M = taps x channels, N = dz channels)
+// One stage = an 8 x 8 tile of output pixels: per 32-channel chunk ONE halo'd patch of x ((8+k-1) rows x PW pixels, one
+// 128-byte row per pixel) and the dz tile.  For filter row r, tile row ks and tap group g (4 taps), the A operand is
+// read straight out of the patch by a descriptor whose M-group stride (LBO) is ONE PIXEL ROW (128 B): M-group j holds
+// the 32 channels of tap s = 4g + j, K row i the pixel x0 + i, so element (j, i) is patch pixel (ks + r, i + 4g + j) --
+// the sliding window is the descriptor, nothing is re-loaded per tap (k*k x less L2->SM traffic than one launch group
+// per tap).  Accumulators: one 128 x N block of TMEM per (r, g, chunk); groups of them are split over blockIdx.y.
+// ==========================================================================================================
+namespace uegan {
+
+struct WgradPatchParams {
+  int tiles_w, tiles_h, nimg, total_ktiles, ksplit;
+  int k, kgroups;              // kernel size, ceil(k / 4) tap groups
+  int chunks;                  // x.c / 32
+  int pw, ph;                  // patch width / height in pixels
+  int patch_bytes, dz_bytes, stage_bytes, num_stages;
+  int n_boxes;                 // N / 32
+  int acc_total, acc_per_cta;  // (r, g, chunk) triples in total / per blockIdx.y slice
+  int off;                     // halo - pad of x
+  int cout, cin, cin_total, cin_first;
+  float* dw;
+  const float* alpha;
+  float scale;
+  unsigned int* err_sink;
+};
+
+__global__ void __launch_bounds__(256, 1)
+conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ,
+                        const WgradPatchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[4];
+  __shared__ __align__(8) uint64_t empty_bar[4];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = (p.total_ktiles + p.ksplit - 1) / p.ksplit;
+  const int kt0 = blockIdx.x * per, kt1 = min(kt0 + per, p.total_ktiles);
+  const int acc0 = blockIdx.y * p.acc_per_cta, acc1 = min(acc0 + p.acc_per_cta, p.acc_total);
+  const int N = p.n_boxes * 32;
+  // accumulator index a -> (chunk, r, g):  a = (chunk * k + r) * kgroups + g.  The chunks this CTA touches:
+  const int ch_lo = acc0 / (p.k * p.kgroups), ch_hi = (acc1 - 1) / (p.k * p.kgroups);
+  const int nch = ch_hi - ch_lo + 1;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmZ);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (kt0 < kt1) {
+    if (warp == 0) {
+      if (elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx = nch * p.ph * p.pw * 128 + p.n_boxes * 64 * 128;
+        for (int kt = kt0; kt < kt1; ++kt) {
+          const int wo0 = (kt % p.tiles_w) * 8;
+          const int ho0 = ((kt / p.tiles_w) % p.tiles_h) * 8;
+          const int n = kt / (p.tiles_w * p.tiles_h);
+          mbar_wait(&empty_bar[stage], phase ^ 1, 0xA00 + stage, p.err_sink);
+          uint8_t* sp = smem + stage * p.stage_bytes;
+          uint8_t* sz = sp + nch * p.patch_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx);
+          for (int c = 0; c < nch; ++c)
+            tma_load_4d(&tmX, &full_bar[stage], sp + c * p.patch_bytes, (ch_lo + c) * 32, wo0 + p.off, ho0 + p.off, n);
+          for (int g = 0; g < p.n_boxes; ++g)
+            tma_load_4d(&tmZ, &full_bar[stage], sz + g * 64 * 128, g * 32, wo0, ho0, n);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        const uint32_t idesc = make_instr_desc(UMMA_TF32, 128, N, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t first = 0;
+        for (int kt = kt0; kt < kt1; ++kt) {
+          mbar_wait(&full_bar[stage], phase, 0xB00 + stage, p.err_sink);
+          tcgen05_fence_after();
+          const uint32_t sp = smem_u32(smem + stage * p.stage_bytes);
+          const uint32_t sz = sp + nch * p.patch_bytes;
+          for (int a = acc0; a < acc1; ++a) {
+            const int g = a % p.kgroups, r = (a / p.kgroups) % p.k, c = a / (p.kgroups * p.k) - ch_lo;
+            const uint32_t d_tmem = tmem_base + (a - acc0) * N;
+            const uint32_t patch = sp + c * p.patch_bytes + (r * p.pw + 4 * g) * 128;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              // A: M-group stride (LBO) = one pixel row: the 4 taps of the group are the same rows shifted by 0..3 pixels
+              const uint64_t da = make_smem_desc(patch + ks * p.pw * 128, 128, 512, UMMA_LAYOUT_SW128_B32);
+              const uint64_t db = make_smem_desc(sz + ks * 1024, 64 * 128, 512, UMMA_LAYOUT_SW128_B32);
+              umma_ss<1>(d_tmem, da, db, idesc, (first | ks) != 0 ? 1u : 0u);
+            }
+          }
+          first = 1;
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&done_bar);
+      }
+    } else if (warp >= 4) {
+      const int q = warp & 3;
+      mbar_wait(&done_bar, 0, 0xC00, p.err_sink);
+      tcgen05_fence_after();
+      const int m = q * 32 + lane;        // row of D: tap j = m / 32 of the group, channel m % 32 of the chunk
+      const float sc = p.scale * (p.alpha ? __ldg(p.alpha) : 1.f);
+      const int kk = p.k * p.k;
+      for (int a = acc0; a < acc1; ++a) {
+        const int g = a % p.kgroups, r = (a / p.kgroups) % p.k, chunk = a / (p.kgroups * p.k);
+        const int s_ = 4 * g + (m >> 5), c = chunk * 32 + (m & 31);
+        for (int c0 = 0; c0 < N; c0 += 16) {
+          uint32_t rr[16];
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (a - acc0) * N + c0, rr);
+          tmem_ld_wait();
+          if (s_ >= p.k || c >= p.cin) continue;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int o = c0 + i;
+            if (o < p.cout)
+              atomicAdd(p.dw + ((long long)o * p.cin_total + p.cin_first + c) * kk + r * p.k + s_,
+                        __uint_as_float(rr[i]) * sc);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// returns 1 if the patch kernel took the job, 0 if the caller should use the generic kernel, -1 on error
+static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int cout, int cin, int cin_total,
+                              int cin_first, int k, int pad, float* dw, const float* alpha, float scale,
+                              cudaStream_t stream) {
+  const char* env = getenv("UEGAN_NO_WGRAD_PATCH");
+  if (env && env[0] == '1') return 0;
+  if (x->c % 32 != 0 || dz->c % 32 != 0 || cout > 64 || k > 8) return 0;
+  const int Ho = x->h + 2 * pad - k + 1, Wo = x->w + 2 * pad - k + 1;
+  if (Ho < 8 || Wo < 8) return 0;
+  WgradPatchParams p;
+  memset(&p, 0, sizeof(p));
+  const int N = (cout + 31) / 32 * 32;
+  p.n_boxes = N / 32;
+  p.k = k;
+  p.kgroups = (k + 3) / 4;
+  p.chunks = (cin + 31) / 32;
+  p.pw = 8 + 4 * p.kgroups - 1;
+  p.ph = 8 + k - 1;
+  p.patch_bytes = (p.ph * p.pw * 128 + 1023) / 1024 * 1024;
+  p.dz_bytes = p.n_boxes * 64 * 128;
+  p.acc_total = p.chunks * k * p.kgroups;
+  p.acc_per_cta = 512 / N;
+  // a CTA's accumulators should span as few channel chunks as possible: align the slice to whole chunks when it can
+  const int per_chunk = k * p.kgroups;
+  if (p.acc_per_cta >= per_chunk) p.acc_per_cta = (p.acc_per_cta / per_chunk) * per_chunk;
+  if (p.acc_per_cta > p.acc_total) p.acc_per_cta = p.acc_total;
+  const int slices = (p.acc_total + p.acc_per_cta - 1) / p.acc_per_cta;
+  const int max_nch = p.acc_per_cta >= per_chunk ? p.acc_per_cta / per_chunk : 2;
+  p.stage_bytes = max_nch * p.patch_bytes + p.dz_bytes;
+  p.num_stages = (200 * 1024) / p.stage_bytes;
+  if (p.num_stages > 4) p.num_stages = 4;
+  if (p.num_stages < 2) return 0;
+  p.tiles_w = (Wo + 7) / 8;
+  p.tiles_h = (Ho + 7) / 8;
+  p.nimg = x->n;
+  p.total_ktiles = p.tiles_w * p.tiles_h * p.nimg;
+  int ksplit = (2 * num_sms() + slices - 1) / slices;
+  if (ksplit > p.total_ktiles) ksplit = p.total_ktiles;
+  p.ksplit = ksplit < 1 ? 1 : ksplit;
+  p.off = x->halo - pad;
+  p.cout = cout; p.cin = cin; p.cin_total = cin_total; p.cin_first = cin_first;
+  p.dw = dw; p.alpha = alpha; p.scale = scale;
+  p.err_sink = error_sink_device();
+  CUtensorMap tmX, tmZ;
+  {  // x, padded extent: {c, w, h, n}
+    const uint64_t pix = (uint64_t)x->c * 4, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
+    uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)t_wp(*x), (uint64_t)t_hp(*x), (uint64_t)x->n};
+    uint64_t strides[3] = {pix, row, img};
+    uint32_t box[4] = {32u, (uint32_t)p.pw, (uint32_t)p.ph, 1u};
+    if (encode_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x->data, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return -1;
+  }
+  {  // dz interior: {c, wo, ho, n}
+    const uint64_t pix = (uint64_t)dz->c * 4, row = (uint64_t)t_wp(*dz) * pix, img = (uint64_t)t_hp(*dz) * row;
+    uint8_t* base = static_cast<uint8_t*>(dz->data) + (uint64_t)dz->halo * row + (uint64_t)dz->halo * pix;
+    uint64_t dims[4] = {(uint64_t)dz->c, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)dz->n};
+    uint64_t strides[3] = {pix, row, img};
+    uint32_t box[4] = {32u, 8u, 8u, 1u};
+    if (encode_tiled(&tmZ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return -1;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_wgrad_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
+        cudaSuccess)
+      return set_error("conv2d_wgrad: cudaFuncSetAttribute failed");
+    attr_set = true;
+  }
+  const int smem_bytes = p.num_stages * p.stage_bytes + 1024;
+  dim3 grid((unsigned)p.ksplit, (unsigned)slices, 1u);
+  conv_wgrad_patch_kernel<<<grid, 256, smem_bytes, stream>>>(tmX, tmZ, p);
+  if (cudaGetLastError() != cudaSuccess) return set_error("conv2d_wgrad: patch kernel launch failed");
+  return 1;
+}
+
+}  // namespace uegan

@@ -121,8 +121,10 @@ class Trainer(object):
             import torch.distributed as dist
             for t in list(self.G.state_dict().values()) + list(self.D.state_dict().values()):
                 dist.broadcast(t, src=0, group=self.group)
+        cap = bool(getattr(a, "cuda_graph", False))  # device-side step counters so that Adam.step() can be captured
         if a.optimizer_type == "adam":
-            opt = lambda p, lr: torch.optim.Adam(params=p, lr=lr, betas=[a.beta1, a.beta2], weight_decay=0.0001)
+            opt = lambda p, lr: torch.optim.Adam(params=p, lr=lr, betas=[a.beta1, a.beta2], weight_decay=0.0001,
+                                                 capturable=cap, foreach=True)
         elif a.optimizer_type == "rmsprop":
             opt = lambda p, lr: torch.optim.RMSprop(params=p, lr=lr, alpha=a.alpha)
         else:
@@ -181,6 +183,35 @@ class Trainer(object):
             for k, v in vals.items():
                 setattr(self, k, v)
         return vals
+
+    # ------------------------------------------------------------------ whole step as a CUDA graph
+    def capture(self, real_raw, real_exp, warmup=3):
+        """Captures train_step (2 G + 5 D + 2 VGG forwards, all backwards, both Adam steps, the NCCL all-reduces) into
+        one CUDA graph.  ~1000 kernel launches per step otherwise cost more host time than the GPU needs to run them.
+        Requires pool_size == 0 (ImagePool is host logic) and args.cuda_graph=True at construction (capturable Adam).
+        Afterwards `replay(real_raw, real_exp)` copies the batch into the static input buffers and launches the graph;
+        the five losses come back as 0-d CUDA tensors (no host sync)."""
+        assert self.args.pool_size == 0 and getattr(self.args, "cuda_graph", False)
+        self._gx, self._gy = real_raw.clone(), real_exp.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):  # allocates every workspace / scratch buffer and settles the weight-pack caches
+                self.train_step(self._gx, self._gy, sync_scalars=False)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._gout = self.train_step(self._gx, self._gy, sync_scalars=False)
+        return self._graph
+
+    def replay(self, real_raw, real_exp, sync_scalars=False):
+        self._gx.copy_(real_raw, non_blocking=True)
+        self._gy.copy_(real_exp, non_blocking=True)
+        self._graph.replay()
+        if sync_scalars:
+            return {k: float(v) for k, v in self._gout.items()}
+        return self._gout
 
     # ------------------------------------------------------------------ trainer.py:40-145 (hot loop only)
     def train(self):
