@@ -1,0 +1,4 @@
+"""Drop-in for the reference's `losses` module: `from losses import PerceptualLoss, GANLoss, MultiscaleRecLoss`
+(trainer.py:9)."""
+from uegan_b200.losses import *  # noqa: F401,F403
+from uegan_b200.losses import GANLoss, MultiscaleRecLoss, PerceptualLoss, VGG19_relu  # noqa: F401

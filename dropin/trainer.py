@@ -1,0 +1,2 @@
+"""Drop-in for the reference's `trainer` module: `from trainer import Trainer` (main.py:8)."""
+from uegan_b200.trainer import Trainer, ImagePool, init_weights  # noqa: F401
