@@ -175,6 +175,11 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, 
   d |= static_cast<uint64_t>(layout & 7) << 61;
   return d;
 }
+// Advance a descriptor's start address by `bytes` (multiple of 16; smem addresses < 256 KB never carry out of the
+// 14-bit field).  The single MMA-issuing thread is latency-bound on scalar code for small-N MMAs, so the issue loops
+// build one descriptor per operand and only ADD per MMA.
+__device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
 // Instruction descriptor (InstrDescriptor bit layout, same header):
 //   [4,6) c_format (1 = F32)  [7,10) a_format  [10,13) b_format (0 F16, 1 BF16, 2 TF32)
 //   [15] a_major  [16] b_major (0 = K-major, 1 = MN-major)  [17,23) N>>3  [24,29) M>>4

@@ -367,39 +367,43 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // profiles/r1_probe_umma_window.json), 8-row groups = one output row of 8 pixels, SBO = patch row pitch.
           const uint32_t w_addr = smem_u32(smem);
           const uint32_t sbo = p.patch_w * 128;
+          const uint64_t db0 = make_smem_desc(w_addr, 16, 1024, UMMA_LAYOUT_SW128);
           uint32_t first = 0;
           for (int c = 0; c < p.patch_nch; ++c) {
             mbar_wait(&full_bar[stage], phase, 0x300 + stage, p.err_sink);
             tcgen05_fence_after();
-            const uint32_t a_base = w_addr + p.w_total_bytes + stage * p.stage_bytes;
+            const uint64_t da0 = make_smem_desc(w_addr + p.w_total_bytes + stage * p.stage_bytes, 16, sbo, UMMA_LAYOUT_SW128);
+            uint32_t a_off = 0, b_off = c * p.w_tile_bytes;
+            const uint32_t b_step = p.patch_nch * p.w_tile_bytes;
             for (int r = 0; r < p.patch_k; ++r) {
+              uint32_t a_rs = a_off;
               for (int s_ = 0; s_ < p.patch_k; ++s_) {
-                const uint32_t a_addr = a_base + (r * p.patch_w + s_) * 128;
-                const uint32_t b_addr = w_addr + ((r * p.patch_k + s_) * p.patch_nch + c) * p.w_tile_bytes;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, UMMA_LAYOUT_SW128);
-                  const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-                  umma_ss<kTf32>(d_tmem, da, db, idesc, first);
-                  first = 1;
-                }
+                const uint64_t da = desc_adv(da0, a_rs), db = desc_adv(db0, b_off);
+                umma_ss<kTf32>(d_tmem, da, db, idesc, first);
+                umma_ss<kTf32>(d_tmem, da + 2, db + 2, idesc, 1u);
+                umma_ss<kTf32>(d_tmem, da + 4, db + 4, idesc, 1u);
+                umma_ss<kTf32>(d_tmem, da + 6, db + 6, idesc, 1u);
+                first = 1;
+                a_rs += 128;
+                b_off += b_step;
               }
+              a_off += sbo;
             }
             umma_commit(&empty_bar[stage]);
             if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
           }
         } else {
+          const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024, UMMA_LAYOUT_SW128);
+          uint32_t first = 0;
           for (int kc = 0; kc < p.num_k_chunks; ++kc) {
             mbar_wait(&full_bar[stage], phase, 0x300 + stage, p.err_sink);
             tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-            const uint32_t b_addr = a_addr + kABytes;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {  // 4 x (32 bytes of K) per 128-byte swizzle row
-              const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-              const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-              umma_ss<kTf32>(d_tmem, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
-            }
+            const uint64_t da = desc_adv(d0, stage * p.stage_bytes), db = da + (kABytes >> 4);
+            umma_ss<kTf32>(d_tmem, da, db, idesc, first);  // 4 x (32 bytes of K) per 128-byte swizzle row
+            umma_ss<kTf32>(d_tmem, da + 2, db + 2, idesc, 1u);
+            umma_ss<kTf32>(d_tmem, da + 4, db + 4, idesc, 1u);
+            umma_ss<kTf32>(d_tmem, da + 6, db + 6, idesc, 1u);
+            first = 1;
             umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
             if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
           }

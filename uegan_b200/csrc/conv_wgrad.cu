@@ -112,18 +112,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kt = kt0; kt < kt1; ++kt) {
           mbar_wait(&full_bar[stage], phase, 0x700 + stage, p.err_sink);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-          const uint32_t b_addr = a_addr + kWgABytes;
+          // MN-major tf32 operands exist only in the SWIZZLE_128B_BASE32B layout (32-byte chunks XORed with row & 3,
+          // 4-row atoms; cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem
+          // layout"): LBO = stride between 32-channel groups (one TMA box), SBO = stride between 4-row groups.
+          const uint64_t da0 = make_smem_desc(smem_u32(smem + stage * p.stage_bytes), kWgBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
+          const uint64_t db0 = da0 + (kWgABytes >> 4);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {  // 8 pixels (one 1024-byte atom of rows) per MMA
-            // MN-major tf32 operands exist only in the SWIZZLE_128B_BASE32B layout (32-byte chunks XORed with row & 3,
-            // 4-row atoms; cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem
-            // layout"): LBO = stride between 32-channel groups (one TMA box), SBO = stride between 4-row groups.
-            const uint64_t da = make_smem_desc(a_addr + ks * 1024, kWgBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
-            const uint64_t db = make_smem_desc(b_addr + ks * 1024, kWgBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
-            umma_ss<1>(tmem_base, da, db, idesc, first);
-            first = 1;
+          for (int ks = 0; ks < 8; ++ks) {  // 8 pixels (one 1024-byte group of rows) per MMA
+            umma_ss<1>(tmem_base, da0 + ks * 64, db0 + ks * 64, idesc, (first | ks) != 0 ? 1u : 0u);
           }
+          first = 1;
           umma_commit(&empty_bar[stage]);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
@@ -378,17 +376,21 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           tcgen05_fence_after();
           const uint32_t sp = smem_u32(smem + stage * p.stage_bytes);
           const uint32_t sz = sp + nch * p.patch_bytes;
+          // A: M-group stride (LBO) = one pixel row: the 4 taps of a group are the same rows shifted by 0..3 pixels
+          const uint64_t da0 = make_smem_desc(sp, 128, 512, UMMA_LAYOUT_SW128_B32);
+          const uint64_t db0 = make_smem_desc(sz, 64 * 128, 512, UMMA_LAYOUT_SW128_B32);
+          const uint32_t row_step = p.pw * 8;  // one patch row, in descriptor units of 16 bytes
+          int g = acc0 % p.kgroups, r = (acc0 / p.kgroups) % p.k, c = acc0 / (p.kgroups * p.k) - ch_lo;
+          uint32_t d_tmem = tmem_base;
           for (int a = acc0; a < acc1; ++a) {
-            const int g = a % p.kgroups, r = (a / p.kgroups) % p.k, c = a / (p.kgroups * p.k) - ch_lo;
-            const uint32_t d_tmem = tmem_base + (a - acc0) * N;
-            const uint32_t patch = sp + c * p.patch_bytes + (r * p.pw + 4 * g) * 128;
+            uint64_t da = da0 + (uint32_t)(c * (p.patch_bytes >> 4) + (r * p.pw + 4 * g) * 8);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
-              // A: M-group stride (LBO) = one pixel row: the 4 taps of the group are the same rows shifted by 0..3 pixels
-              const uint64_t da = make_smem_desc(patch + ks * p.pw * 128, 128, 512, UMMA_LAYOUT_SW128_B32);
-              const uint64_t db = make_smem_desc(sz + ks * 1024, 64 * 128, 512, UMMA_LAYOUT_SW128_B32);
-              umma_ss<1>(d_tmem, da, db, idesc, (first | ks) != 0 ? 1u : 0u);
+              umma_ss<1>(d_tmem, da, db0 + ks * 64, idesc, (first | ks) != 0 ? 1u : 0u);
+              da += row_step;
             }
+            d_tmem += N;
+            if (++g == p.kgroups) { g = 0; if (++r == p.k) { r = 0; ++c; } }
           }
           first = 1;
           umma_commit(&empty_bar[stage]);
