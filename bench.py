@@ -171,6 +171,66 @@ def workload_name(w):
             else "generator_inference_3x512x512_b32 (BASELINE.json configs[1])")
 
 
+# ------------------------------------------------------------------------------------------------ GPU: config 5
+def run_sweep(args):
+    """BASELINE.json configs[4]: mixed-resolution Generator inference sweep (short edge 256 / 512 / 1024, 2:3 aspect),
+    batch sized to fill HBM, one replica per GPU, no communication."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from oracle import uegan_oracle as O
+    from uegan_b200 import kernels as K
+    from uegan_b200.models import Generator
+    G = Generator(32, "none", "LeakyReLU", False)
+    G.load_state_dict(O.make_generator_params(32, 0, "o1"))
+    G = G.cuda().eval()
+    free, _ = torch.cuda.mem_get_info()
+    rows, tot_pix, tot_ms = [], 0.0, 0.0
+    for (h, w) in ((256, 384), (512, 768), (1024, 1536)):
+        per_img = 1500.0 * h * w  # bytes of activation buffers per image (all Generator tensors, fp32 NHWC)
+        b = int(min(256, max(1, 0.5 * free / per_img)))
+        x = torch.rand(b, 3, h, w, device="cuda") * 2 - 1
+        with torch.no_grad():
+            for _ in range(max(args.warmup, 3)):
+                G(x)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                G(x)
+            e1.record()
+            torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / args.steps
+        rows.append({"h": h, "w": w, "batch_per_gpu": b, "ms_per_step": ms, "images_per_s": world * b / (ms * 1e-3),
+                     "mpix_per_s": world * b * h * w / 1e6 / (ms * 1e-3)})
+        tot_pix += world * b * h * w / 1e6
+        tot_ms += ms
+        G._plans.clear()
+        del x
+        torch.cuda.empty_cache()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Generator inference megapixels/sec (mixed-resolution sweep)", "value": tot_pix / (tot_ms * 1e-3),
+            "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+            "data": "synthetic", "config": {"workload": "generator_inference_sweep_256_512_1024 (BASELINE.json configs[4])",
+                                            "parallelism": f"replicas x{world}", "sweep": rows},
+            "gpu_launches": K.launches()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ GPU (native)
 def run_native(args):
     import torch
@@ -357,11 +417,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "inference"])
+    ap.add_argument("--workload", default="train", choices=["train", "inference", "sweep"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 16 train / 32 inference)")
     ap.add_argument("--graph", type=int, default=1, help="capture the training step into a CUDA graph (1) or run eagerly (0)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "sweep":
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_native(args)

@@ -119,27 +119,27 @@ __device__ __forceinline__ float tap_load(const void* p, long long o, int dtype)
   if (dtype == UEGAN_F16) return __half2float(static_cast<const __half*>(p)[o]);
   return static_cast<const float*>(p)[o];
 }
-// accum[0] += sum ((x-mx)*rx - (y-my)*ry)^2
-__global__ void in_mse_kernel(TapGeom g, const float* __restrict__ mrx, const float* __restrict__ mry,
-                              double* __restrict__ accum) {
-  const long long total = (long long)g.n * g.h * g.w * g.c;
-  double s = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % g.c);
-    long long pix = i / g.c;
-    const int xx = (int)(pix % g.w);
-    pix /= g.w;
-    const int yy = (int)(pix % g.h);
-    const int n = (int)(pix / g.h);
-    const long long o = tap_off(g, n, yy, xx, c);
-    const long long si = ((long long)n * g.c + c) * 2;
-    const float a = (tap_load(g.x, o, g.dtype) - mrx[si]) * mrx[si + 1];
-    const float b = (tap_load(g.y, o, g.dtype) - mry[si]) * mry[si + 1];
-    const float d = a - b;
-    s += (double)d * d;
+// accum[0] += sum ((x-mx)*rx - (y-my)*ry)^2   (strip-reduce skeleton of elementwise.cu: 16-byte loads, one atomic per
+// (block, channel))
+template <typename T>
+struct InMseOp {
+  TGeom x, y;
+  const float* mrx;
+  const float* mry;
+  double* accum;
+  __device__ void acc(int n, int yy, int xx, int c, float (&a)[Vec<T>::N][1]) const {
+    float xv[Vec<T>::N], yv[Vec<T>::N];
+    Vec<T>::load(static_cast<const T*>(x.data) + toff(x, n, yy, xx, c), xv);
+    Vec<T>::load(static_cast<const T*>(y.data) + toff(y, n, yy, xx, c), yv);
+#pragma unroll
+    for (int k = 0; k < Vec<T>::N; ++k) {
+      const long long si = ((long long)n * x.c + c + k) * 2;
+      const float d = (xv[k] - mrx[si]) * mrx[si + 1] - (yv[k] - mry[si]) * mry[si + 1];
+      a[k][0] += d * d;
+    }
   }
-  block_atomic_add(s, accum);
-}
+  __device__ void flush(int n, int c, const float (&t)[1]) const { atomicAdd(accum, (double)t[0]); }
+};
 // loss += weight * accum / numel ; accum reset
 __global__ void scalar_axpy_kernel(double* accum, double scale, float* loss) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -309,14 +309,21 @@ int uegan_in_mse_fwd(const uegan_tensor* x, const uegan_tensor* y, const float* 
   UEGAN_CHECK(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c && x->halo == y->halo &&
                   x->dtype == y->dtype,
               "in_mse: x / y mismatch");
-  TapGeom g;
-  g.x = x->data; g.y = y->data; g.n = x->n; g.h = x->h; g.w = x->w; g.c = x->c; g.halo = x->halo;
-  g.wp = t_wp(*x); g.hp = t_hp(*x); g.dtype = x->dtype;
-  const long long total = (long long)g.n * g.h * g.w * g.c;
+  const TGeom gx = geom(*x), gy = geom(*y);
+  const long long total = (long long)gx.n * gx.h * gx.w * gx.c;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  in_mse_kernel<<<blocks, 256, 0, st>>>(g, mean_rstd_x, mean_rstd_y, accum);
+  const int vn = 16 / dtype_size(x->dtype);
+  UEGAN_CHECK(gx.c % vn == 0 && 256 % (gx.c / vn) == 0, "in_mse: unsupported channel count %d", gx.c);
+  if (x->dtype == UEGAN_F32) {
+    InMseOp<float> op{gx, gy, mean_rstd_x, mean_rstd_y, accum};
+    launch_strip_reduce<float, 1>(op, gx.c, gx.n, gx.h, gx.w, st);
+  } else if (x->dtype == UEGAN_BF16) {
+    InMseOp<__nv_bfloat16> op{gx, gy, mean_rstd_x, mean_rstd_y, accum};
+    launch_strip_reduce<__nv_bfloat16, 1>(op, gx.c, gx.n, gx.h, gx.w, st);
+  } else {
+    InMseOp<__half> op{gx, gy, mean_rstd_x, mean_rstd_y, accum};
+    launch_strip_reduce<__half, 1>(op, gx.c, gx.n, gx.h, gx.w, st);
+  }
   scalar_axpy_kernel<<<1, 32, 0, st>>>(accum, (double)weight / (double)total, loss_inout);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
