@@ -198,34 +198,40 @@ def test_backward_pieces_vs_oracle():
 
 
 def test_cuda_graph_replay_matches_eager():
-    """the whole step captured as one CUDA graph takes the same steps as the eager path."""
+    """the whole step captured as one CUDA graph takes the same steps as the eager path.
+    GAN training with the reference learning rates is chaotic on the scale of a few steps (d_loss moves by 5-10 % per
+    step here; two EAGER runs drift apart by ~10 % after 4 steps because fp32 atomics reorder the wgrad sums), so the
+    comparison uses a small learning rate: losses must agree to 1e-3, and the weights must have moved by the same
+    Adam steps (a capture that replayed stale packed weights or stale optimizer state would not)."""
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
-    import types
     from uegan_b200.trainer import Trainer
     from bench import train_args
     raw = O.make_images((2, 3, 128, 128), 40).cuda()
     exp = O.make_images((2, 3, 128, 128), 41).cuda()
+    lr = 1e-5
 
     def make(graph):
         a = train_args(2)
-        a.cuda_graph = graph
+        a.cuda_graph, a.g_lr, a.d_lr = graph, lr, lr
         T = Trainer(None, a, vgg_state_dict=O.make_vgg_params())
         T.G.load_state_dict(O.make_generator_params(32, 0, "o1"))
         T.D.load_state_dict(O.make_discriminator_params(32, 1, "o1"))
         return T
 
     Te, Tg = make(False), make(True)
+    w0 = Te.D.d3[0][1].weight_orig.detach().clone()
     le = [Te.train_step(raw, exp) for _ in range(5)]
-    Tg.capture(raw, exp, warmup=3)          # 3 eager warm-up steps + 1 captured (capture does not execute)
-    # Trajectories of two runs drift apart (fp32 atomics in the weight-gradient split-K change the summation order from
-    # run to run; Adam's sign-like early steps amplify that: ~0.3 % in d_loss after 4 steps between two EAGER runs too),
-    # so the graph is held to the eager run to a few percent, and to the same step-to-step movement -- a capture that
-    # replayed stale packed weights or stale optimizer state would stand still instead.
+    Tg.capture(raw, exp, warmup=3)          # 3 eager warm-up steps; the capture itself does not execute
     l3 = Tg.replay(raw, exp, sync_scalars=True)   # = step index 3
     l4 = Tg.replay(raw, exp, sync_scalars=True)   # = step index 4
     for k in le[3]:
-        assert abs(l3[k] - le[3][k]) / abs(le[3][k]) < 3e-2, (k, l3[k], le[3][k])
-        assert abs(l4[k] - le[4][k]) / abs(le[4][k]) < 3e-2, (k, l4[k], le[4][k])
-    move_e, move_g = le[4]["d_loss"] - le[3]["d_loss"], l4["d_loss"] - l3["d_loss"]
-    assert abs(move_g) > 1e-3 and move_e * move_g > 0 and abs(move_g - move_e) < 0.5 * abs(move_e), (move_e, move_g)
+        assert abs(l3[k] - le[3][k]) / abs(le[3][k]) < 1e-3, (k, l3[k], le[3][k])
+        assert abs(l4[k] - le[4][k]) / abs(le[4][k]) < 1e-3, (k, l4[k], le[4][k])
+    for get in (lambda T: T.D.d3[0][1].weight_orig, lambda T: T.G.dec2.main[1].weight):
+        we, wg = get(Te).detach(), get(Tg).detach()
+        moved = float((we - (w0 if we.shape == w0.shape else we * 0 + we)).abs().mean()) if we.shape == w0.shape else None
+        assert float((we - wg).abs().mean()) < 0.2 * 5 * lr, float((we - wg).abs().mean())
+        if moved is not None:
+            assert moved > 0.5 * 5 * lr, moved  # five Adam steps of ~lr each really happened
+    assert float((Tg.D.d3[0][1].weight_orig.detach() - w0).abs().mean()) > 0.5 * 5 * lr

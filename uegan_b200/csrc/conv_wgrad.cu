@@ -28,6 +28,8 @@ struct WgradParams {
   int num_stages, stage_bytes;
   int window_mode;                 // 1: small-Cin sliding-window B map
   int swap_mode;                   // 1: tiny Cout: M = 128 window elements (s, c) of one filter row, N = dz channels
+  int tap_group, taps_total;       // non-swap: T taps share one MMA (N = T * per-tap columns), blockIdx.y = tap group
+  int tap_boxes;                   // 32-column boxes per tap
   int cout, cin, cin_total, cin_first, x_c;
   int m_tiles, n_chunks;
   float* dw;                       // OIHW fp32
@@ -52,7 +54,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int per = (p.total_ktiles + p.ksplit - 1) / p.ksplit;
   const int kt0 = blockIdx.x * per;
   const int kt1 = min(kt0 + per, p.total_ktiles);
-  const int r = (p.window_mode || p.swap_mode) ? tap : tap / p.k, s_ = (p.window_mode || p.swap_mode) ? 0 : tap % p.k;
+  // swap mode: `tap` is the filter row.  Otherwise `tap` is a GROUP of up to tap_group taps (window mode: filter rows,
+  // else (r, s) pairs) whose B boxes sit side by side in smem so that one MMA covers all of them (N = n_boxes * 32).
+  const int r = tap;  // swap mode only
+  const int t_first = tap * p.tap_group;
+  const int t_count = p.swap_mode ? 1 : min(p.tap_group, p.taps_total - t_first);
   const int N = p.n_boxes * 32;
 
   if (warp == 0 && elect_one()) {
@@ -78,7 +84,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t tx = kWgABytes + p.n_boxes * kWgBoxBytes;
+        const uint32_t tx = kWgABytes + (p.swap_mode ? 1 : t_count * p.tap_boxes) * kWgBoxBytes;
         for (int kt = kt0; kt < kt1; ++kt) {
           const int wo0 = (kt % p.tiles_w) * 8;
           const int ho0 = ((kt / p.tiles_w) % p.tiles_h) * 8;
@@ -97,8 +103,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_load_4d(&tmA, &full_bar[stage], sa + g * kWgBoxBytes, mt * 128 + g * 32, wo0, ho0, n);
             // B map = the fprop sliding-window map {window, wo, r, ho, n}: tap column s and channel offset are both
             // positions inside the window of k*C contiguous (s, c) values that starts at the pixel
-            for (int g = 0; g < p.n_boxes; ++g)
-              tma_load_5d(&tmB, &full_bar[stage], sb + g * kWgBoxBytes, s_ * p.x_c + nc * N + g * 32, wo0, r, ho0, n);
+            for (int t = 0; t < t_count; ++t) {
+              const int tp = t_first + t;
+              const int tr = p.window_mode ? tp : tp / p.k, ts = p.window_mode ? 0 : tp % p.k;
+              for (int g = 0; g < p.tap_boxes; ++g)
+                tma_load_5d(&tmB, &full_bar[stage], sb + (t * p.tap_boxes + g) * kWgBoxBytes,
+                            ts * p.x_c + nc * p.tap_boxes * 32 + g * 32, wo0, tr, ho0, n);
+            }
           }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
@@ -154,15 +165,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           continue;
         }
         if (o >= p.cout) continue;
+        const int ncol = p.tap_boxes * 32;  // columns per tap
+        const int tl = c0 / ncol;           // a 16-column chunk never straddles taps (ncol is a multiple of 32)
+        if (tl >= t_count) continue;
+        const int tp = t_first + tl;
+        const int tr = p.window_mode ? tp : tp / p.k, ts = p.window_mode ? 0 : tp % p.k;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int j = c0 + i;
+          const int j = (c0 + i) - tl * ncol;
           int c, ss;
           if (p.window_mode) { ss = j >> 2; c = j & 3; }  // window column = (s, c) with 4 stored channels
-          else { ss = s_; c = nc * N + j; }
+          else { ss = ts; c = nc * ncol + j; }
           if (c < p.cin && ss < p.k) {
             const float v = __uint_as_float(rr[i]) * sc;
-            atomicAdd(p.dw + ((long long)o * p.cin_total + p.cin_first + c) * kk + r * p.k + ss, v);
+            atomicAdd(p.dw + ((long long)o * p.cin_total + p.cin_first + c) * kk + tr * p.k + ss, v);
           }
         }
       }
@@ -224,15 +240,27 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
     N = 32; p.n_chunks = 1;
     p.taps = k;
     p.m_tiles = (k * x->c + 127) / 128;
+    p.tap_group = 1; p.taps_total = k; p.tap_boxes = 1;
   } else if (window) {
-    UEGAN_CHECK(k * 4 <= 32, "conv2d_wgrad: window mode needs k*4 <= 32");
-    N = 32; p.n_chunks = 1;
+    // RGB input: one "tap" = a filter row (the 32 (s, c) window values); all k rows side by side: N = 32 k
+    UEGAN_CHECK(k * 4 <= 32 && k <= 8, "conv2d_wgrad: window mode needs k*4 <= 32");
+    p.taps_total = k;
+    p.tap_boxes = 1;
+    p.tap_group = k;
+    N = 32 * k; p.n_chunks = 1;
   } else {
+    // several taps per MMA while the per-tap width leaves room in N <= 256 (A = dz is then read once per GROUP)
     const int cpad = (cin + 31) / 32 * 32;
-    N = cpad < 256 ? cpad : 256;
-    p.n_chunks = (cpad + N - 1) / N;
+    const int ncol = cpad < 256 ? cpad : 256;
+    p.n_chunks = (cpad + ncol - 1) / ncol;
+    p.tap_boxes = ncol / 32;
+    p.taps_total = k * k;
+    p.tap_group = 256 / ncol;
+    if (p.tap_group > p.taps_total) p.tap_group = p.taps_total;
+    N = p.tap_group * ncol;
   }
   p.n_boxes = N / 32;
+  if (!swap) p.taps = (p.taps_total + p.tap_group - 1) / p.tap_group;
   p.stage_bytes = kWgABytes + p.n_boxes * kWgBoxBytes;
   p.num_stages = (200 * 1024) / p.stage_bytes;
   if (p.num_stages > 4) p.num_stages = 4;
