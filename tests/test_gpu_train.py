@@ -201,8 +201,9 @@ def test_cuda_graph_replay_matches_eager():
     """the whole step captured as one CUDA graph takes the same steps as the eager path.
     GAN training with the reference learning rates is chaotic on the scale of a few steps (d_loss moves by 5-10 % per
     step here; two EAGER runs drift apart by ~10 % after 4 steps because fp32 atomics reorder the wgrad sums), so the
-    comparison uses a small learning rate: losses must agree to 1e-3, and the weights must have moved by the same
-    Adam steps (a capture that replayed stale packed weights or stale optimizer state would not)."""
+    comparison uses a small learning rate: losses must agree to 1e-2, d_loss must MOVE from one replay to the next as
+    it does eagerly, and the weights must have moved by the same Adam steps (a capture that replayed stale packed
+    weights or stale optimizer state would not)."""
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
     from uegan_b200.trainer import Trainer
@@ -225,9 +226,13 @@ def test_cuda_graph_replay_matches_eager():
     Tg.capture(raw, exp, warmup=3)          # 3 eager warm-up steps; the capture itself does not execute
     l3 = Tg.replay(raw, exp, sync_scalars=True)   # = step index 3
     l4 = Tg.replay(raw, exp, sync_scalars=True)   # = step index 4
-    for k in le[3]:
-        assert abs(l3[k] - le[3][k]) / abs(le[3][k]) < 1e-3, (k, l3[k], le[3][k])
-        assert abs(l4[k] - le[4][k]) / abs(le[4][k]) < 1e-3, (k, l4[k], le[4][k])
+    for k in le[3]:  # run-to-run noise (atomics order -> Adam sign flips) is ~3e-3 on g_percep after 3 steps
+        assert abs(l3[k] - le[3][k]) / abs(le[3][k]) < 1e-2, (k, l3[k], le[3][k])
+        assert abs(l4[k] - le[4][k]) / abs(le[4][k]) < 1e-2, (k, l4[k], le[4][k])
+    # the step-to-step movement of d_loss is what a stale operand (e.g. a weight pack that a replay does not refresh)
+    # would destroy: D evaluated with last step's weights does not move
+    move_e, move_g = le[4]["d_loss"] - le[3]["d_loss"], l4["d_loss"] - l3["d_loss"]
+    assert abs(move_e) > 1e-3 and abs(move_g - move_e) < 0.3 * abs(move_e), (move_e, move_g)
     for get in (lambda T: T.D.d3[0][1].weight_orig, lambda T: T.G.dec2.main[1].weight):
         we, wg = get(Te).detach(), get(Tg).detach()
         moved = float((we - (w0 if we.shape == w0.shape else we * 0 + we)).abs().mean()) if we.shape == w0.shape else None

@@ -70,7 +70,7 @@ def _g_workspace(G, b, h, w, dev):
 
 def _gam_forward(G, name, ga, src, ch, z, dst, off, stats, ws):
     fuse = ga.fuse[0]
-    wp = G._wcache.get(name, fuse.weight, lambda: K.packed_weight(fuse.weight, src.c, F32, 0, ch))
+    wp = G._wcache.get(name, fuse.weight, lambda out=None: K.packed_weight(fuse.weight, src.c, F32, 0, ch, out=out))
     if K.fused_stats_ok(src.h, src.w):
         K.conv_fprop(src, wp, ch, 1, 1, 0, z, in_stats=stats)
         K.instance_norm_apply(z, dst, off, stats)
@@ -309,11 +309,11 @@ def _d_forward_train(D, x, ws):
             ws["u"].append(conv.weight_u.detach().clone())  # the values this forward used (later forwards move on)
             ws["v"].append(conv.weight_v.detach().clone())
         dst = ws["ds"][i - 1]
-        wp = D._wcache.get(f"d{i}", wgt, lambda: K.packed_weight(wgt, src.c, F32))
+        wp = D._wcache.get(f"d{i}", wgt, lambda out=None: K.packed_weight(wgt, src.c, F32, out=out))
         K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, D._act)
         K.halo_fill(dst)
         pred = torch.empty(x.shape[0], 1, dst.h, dst.w, dtype=torch.float32, device=x.device)
-        hp = D._wcache.get(f"p{i}", head.weight, lambda: K.packed_weight(head.weight, dst.c, F32))
+        hp = D._wcache.get(f"p{i}", head.weight, lambda out=None: K.packed_weight(head.weight, dst.c, F32, out=out))
         K.conv_fprop(dst, hp, 1, k, 1, pad, None, 0, None, None, D._head_act, None, pred)
         preds.append(pred)
         src = dst
@@ -321,7 +321,7 @@ def _d_forward_train(D, x, ws):
     return preds
 
 
-def _d_backward(D, x, dpreds, ws, need_dx):
+def _d_backward(D, x, dpreds, ws, need_dx, need_w=True):
     b, _, h, w = x.shape
     dev = x.device
     S = lambda name, hh, ww, c, halo=0: _scratch.get("D" + name, b, hh, ww, c, halo, F32, dev)
@@ -342,10 +342,12 @@ def _d_backward(D, x, dpreds, ws, need_dx):
             dp = torch.zeros_like(ws["preds"][i - 1])
         dp = dp.contiguous().float()
         K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzp)
-        K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzpw)
-        gw = _zeros_like(head.weight)
-        K.conv_wgrad(ds, dzpw, gw, k, 1, pad)
-        grads[f"d{i}_pred.0.1.weight"] = gw
+        if need_w:
+            K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzpw)
+        if need_w:
+            gw = _zeros_like(head.weight)
+            K.conv_wgrad(ds, dzpw, gw, k, 1, pad)
+            grads[f"d{i}_pred.0.1.weight"] = gw
         dxa = S(f"dxa{i}", ds.h + 2 * pad, ds.w + 2 * pad, ds.c)
         K.conv_dgrad(dzp, head.weight, k, 1, dxa, cache, f"p{i}")
         dz = S(f"dz{i}", ds.h, ds.w, ds.c, kq - 1)
@@ -358,17 +360,18 @@ def _d_backward(D, x, dpreds, ws, need_dx):
         # strided SN conv d_i: input srcs[i-1]
         xin = srcs[i - 1]
         alpha = ws["sig"][i - 1][1:2] if D.use_sn else None
-        gw = _zeros_like(wgt)
-        K.conv_wgrad(xin, dz, gw, k, 2, pad, alpha=alpha)
-        if D.use_sn:
-            K.spectral_bwd(gw, wgt, ws["u"][i - 1], ws["v"][i - 1], ws["sig"][i - 1],
-                           torch.empty(1, dtype=torch.float64, device=dev))
-            grads[f"d{i}.0.1.weight_orig"] = gw
-        else:
-            grads[f"d{i}.0.1.weight"] = gw
-        gb = torch.empty_like(conv.bias)
-        K.channel_sum(dz, gb)
-        grads[f"d{i}.0.1.bias"] = gb
+        if need_w:
+            gw = _zeros_like(wgt)
+            K.conv_wgrad(xin, dz, gw, k, 2, pad, alpha=alpha)
+            if D.use_sn:
+                K.spectral_bwd(gw, wgt, ws["u"][i - 1], ws["v"][i - 1], ws["sig"][i - 1],
+                               torch.empty(1, dtype=torch.float64, device=dev))
+                grads[f"d{i}.0.1.weight_orig"] = gw
+            else:
+                grads[f"d{i}.0.1.weight"] = gw
+            gb = torch.empty_like(conv.bias)
+            K.channel_sum(dz, gb)
+            grads[f"d{i}.0.1.bias"] = gb
         if i > 1:
             dxb = S(f"dxb{i}", xin.h + 2 * pad, xin.w + 2 * pad, xin.c)
             K.conv_dgrad(dz, wgt, k, 2, dxb, cache, f"d{i}", alpha=alpha)
@@ -401,10 +404,11 @@ class _DiscriminatorFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *dpreds):
         D = ctx.module
-        grads, dx = _d_backward(D, ctx.x, dpreds, ctx.ws, ctx.needs_input_grad[1])
+        need_w = any(ctx.needs_input_grad[2:])
+        grads, dx = _d_backward(D, ctx.x, dpreds, ctx.ws, ctx.needs_input_grad[1], need_w)
         D._train_pool[ctx.key].append(ctx.ws)
         names = [n for n, _ in D.named_parameters()]
-        return (None, dx) + tuple(grads[n] for n in names)
+        return (None, dx) + tuple(grads.get(n) for n in names)
 
 
 def discriminator_apply(module, x):

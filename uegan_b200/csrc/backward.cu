@@ -64,18 +64,15 @@ struct CombineArgs {
   TGeom mul; int mul_c_off; int has_mul;
   int cch;  // channels produced
 };
+// grid = (x-chunks of a padded row, padded rows, images): no per-thread divisions (cv is a power of two)
 template <typename T>
-__global__ void grad_combine_kernel(CombineArgs q, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+__global__ void grad_combine_kernel(CombineArgs q, int cv_log2) {
   constexpr int VN = Vec<T>::N;
-  const int cv = q.cch / VN;
-  const int c = (int)(i % cv) * VN;
-  long long pix = i / cv;
-  const int xp = (int)(pix % q.dst.wp);
-  pix /= q.dst.wp;
-  const int yp = (int)(pix % q.dst.hp);
-  const int n = (int)(pix / q.dst.hp);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int xp = t >> cv_log2;
+  if (xp >= (int)q.dst.wp) return;
+  const int c = (t & ((1 << cv_log2) - 1)) * VN;
+  const int yp = blockIdx.y, n = blockIdx.z;
   const int y = yp - q.dst.halo, x = xp - q.dst.halo;
   float v[VN];
 #pragma unroll
@@ -443,9 +440,14 @@ int uegan_grad_combine(const uegan_tensor* dst, int32_t dst_c_off, int32_t chann
   if (add_c) { if (chk(add_c, c_c_off, 0, "add_c")) return -1; q.c = geom(*add_c); q.c_c_off = c_c_off; q.has_c = 1; }
   if (mask) { if (chk(mask, mask_c_off, 0, "mask")) return -1; q.mask = geom(*mask); q.mask_c_off = mask_c_off; q.has_mask = 1; }
   if (mul) { if (chk(mul, mul_c_off, 0, "mul")) return -1; q.mul = geom(*mul); q.mul_c_off = mul_c_off; q.has_mul = 1; }
-  const long long total = (long long)q.dst.n * q.dst.hp * q.dst.wp * (channels / vn);
+  const int cv = channels / vn;
+  int cv_log2 = 0;
+  while ((1 << cv_log2) < cv) ++cv_log2;
+  UEGAN_CHECK((1 << cv_log2) == cv, "grad_combine: channels / vector width must be a power of two (got %d)", cv);
+  UEGAN_CHECK(q.dst.hp <= 65535 && q.dst.n <= 65535, "grad_combine: tensor too large for the launch grid");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  UEGAN_DISPATCH(dst->dtype, grad_combine_kernel, <<<nblk(total, 256), 256, 0, st>>>(q, total));
+  const dim3 grid(nblk((long long)q.dst.wp * cv, 256), (unsigned)q.dst.hp, (unsigned)q.dst.n);
+  UEGAN_DISPATCH(dst->dtype, grad_combine_kernel, <<<grid, 256, 0, st>>>(q, cv_log2));
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

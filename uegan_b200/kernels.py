@@ -62,8 +62,9 @@ class NHWC:
 
 
 def packed_weight(weight: torch.Tensor, cin_stored: int, dtype: int, cin_first: int = 0, cin: Optional[int] = None,
-                  transpose_flip: bool = False) -> torch.Tensor:
-    """nn.Conv2d.weight (OIHW fp32, CUDA) -> K-major packed operand of the implicit GEMM."""
+                  transpose_flip: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.Conv2d.weight (OIHW fp32, CUDA) -> K-major packed operand of the implicit GEMM.  `out`: re-pack in place
+    (the operand buffers must keep their addresses across optimizer steps for CUDA-graph replay)."""
     lib = L.load()
     w = weight.detach()
     assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
@@ -75,7 +76,8 @@ def packed_weight(weight: torch.Tensor, cin_stored: int, dtype: int, cin_first: 
     if transpose_flip:
         cin = o
     nbytes = lib.uegan_packed_weight_bytes(cout, cin_stored, k, dtype)
-    buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
+    buf = out if out is not None else torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
+    assert buf.numel() >= nbytes
     L.check(lib.uegan_pack_conv_weight(w.data_ptr(), buf.data_ptr(), cout, i_total, cin_first, cin, cin_stored, k,
                                        dtype, int(transpose_flip), _stream()), "pack_conv_weight")
     _count(1)
@@ -267,7 +269,7 @@ def msrec_loss(pred: torch.Tensor, gt: torch.Tensor, rec_type: int, scales: int,
 # backward
 # ------------------------------------------------------------------------------------------------
 def packed_weight_dgrad(weight: torch.Tensor, cout_stored: int, dtype: int, stride: int = 1, pi: int = 0, pj: int = 0,
-                        cin_first: int = 0, cin: Optional[int] = None) -> torch.Tensor:
+                        cin_first: int = 0, cin: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Operand of the data-gradient GEMM of a conv with `weight` (OIHW): see uegan_pack_conv_weight_dgrad."""
     lib = L.load()
     w = weight.detach()
@@ -277,7 +279,8 @@ def packed_weight_dgrad(weight: torch.Tensor, cout_stored: int, dtype: int, stri
         cin = i_total - cin_first
     kq = (k + stride - 1) // stride
     nbytes = lib.uegan_packed_weight_bytes(cin, cout_stored, kq, dtype)
-    buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
+    buf = out if out is not None else torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
+    assert buf.numel() >= nbytes
     L.check(lib.uegan_pack_conv_weight_dgrad(w.data_ptr(), buf.data_ptr(), o, i_total, cin_first, cin, cout_stored, k,
                                              stride, pi, pj, dtype, _stream()), "pack_conv_weight_dgrad")
     _count(1)
@@ -323,7 +326,7 @@ def conv_dgrad(dz: NHWC, weight: torch.Tensor, k: int, stride: int, dxp: NHWC, c
     assert dxp.c >= cout_arg
     for pi in range(stride):
         for pj in range(stride):
-            fn = lambda: packed_weight_dgrad(weight, dz.c, dz.dtype, stride, pi, pj, cin_first, cin)
+            fn = lambda out=None: packed_weight_dgrad(weight, dz.c, dz.dtype, stride, pi, pj, cin_first, cin, out=out)
             wp = cache.get((key, "dg", pi, pj, dz.dtype), weight, fn) if cache is not None else fn()
             nr = len(range(pi, k, stride)) * len(range(pj, k, stride))  # taps of the forward kernel in this class
             conv_generic(dz, wp, cout_arg, kq, 1, kq - 1, dxp, 0, None, alpha, L.ACT_NONE, mask, mask_act,

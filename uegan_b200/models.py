@@ -77,7 +77,9 @@ class _Interp(nn.Module):
 
 
 class _ParamCache:
-    """Re-packs a parameter into its kernel operand only when the parameter changed (optimizer step / load)."""
+    """Re-packs a parameter into its kernel operand only when the parameter changed (optimizer step / load).
+    The operand buffer of a key is allocated once and re-packed IN PLACE (`fn(out=buf)`): consumers captured in a
+    CUDA graph keep reading the same address, and a re-pack node later in the graph refreshes it for the next replay."""
 
     def __init__(self):
         self.store = {}
@@ -85,9 +87,13 @@ class _ParamCache:
     def get(self, key, param, fn):
         tag = (param.data_ptr(), param._version)
         hit = self.store.get(key)
-        if hit is None or hit[0] != tag:
+        if hit is None:
             hit = (tag, fn())
-            self.store[key] = hit
+        elif hit[0] != tag:
+            hit = (tag, fn(out=hit[1]))
+        else:
+            return hit[1]
+        self.store[key] = hit
         return hit[1]
 
 
@@ -132,7 +138,7 @@ class Generator(nn.Module):
     # ---------------------------------------------------------------- native forward
     def _w(self, name, conv, cin_stored, cin_first=0, cin=None):
         return self._wcache.get(name, conv.weight,
-                                lambda: K.packed_weight(conv.weight, cin_stored, L.F32, cin_first, cin))
+                                lambda out=None: K.packed_weight(conv.weight, cin_stored, L.F32, cin_first, cin, out=out))
 
     def _plan(self, b, h, w, device):
         key = (b, h, w, str(device))
@@ -194,7 +200,7 @@ class Generator(nn.Module):
             # GAM(x) == IN(conv1x1(x, fuse.weight[:, :C])): the attention branch and fuse bias are constant per
             # (n, c) and cancel in the InstanceNorm that follows (models.py:230-237; SURVEY.md 8a rewrite 1).
             fuse = ga.fuse[0]
-            wp = self._wcache.get(name, fuse.weight, lambda: K.packed_weight(fuse.weight, src.c, L.F32, 0, ch))
+            wp = self._wcache.get(name, fuse.weight, lambda out=None: K.packed_weight(fuse.weight, src.c, L.F32, 0, ch, out=out))
             if K.fused_stats_ok(src.h, src.w):  # statistics ride in the conv epilogue
                 K.conv_fprop(src, wp, ch, 1, 1, 0, z, in_stats=P["stats"])
                 K.instance_norm_apply(z, dst, off, P["stats"])
@@ -314,11 +320,11 @@ class Discriminator(nn.Module):
                 K.spectral_sigma(wgt, conv.weight_u, conv.weight_v, self.training, P["sig"][i - 1], P["ws"][i - 1])
                 alpha = P["sig"][i - 1][1:2]
             dst = P["ds"][i - 1]
-            wp = self._wcache.get(f"d{i}", wgt, lambda: K.packed_weight(wgt, src.c, L.F32))
+            wp = self._wcache.get(f"d{i}", wgt, lambda out=None: K.packed_weight(wgt, src.c, L.F32, out=out))
             K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, self._act)
             K.halo_fill(dst)
             pred = torch.empty(b, 1, dst.h, dst.w, dtype=torch.float32, device=x.device)
-            hp = self._wcache.get(f"p{i}", head.weight, lambda: K.packed_weight(head.weight, dst.c, L.F32))
+            hp = self._wcache.get(f"p{i}", head.weight, lambda out=None: K.packed_weight(head.weight, dst.c, L.F32, out=out))
             K.conv_fprop(dst, hp, 1, k, 1, pad, None, 0, None, None, self._head_act, None, pred)
             preds.append(pred)
             src = dst

@@ -165,8 +165,18 @@ class Trainer(object):
         self.d_optimizer.step()
         # ---- update G
         self.g_grads.zero()
-        real_exp_preds = self.D(real_exp)
-        fake_exp_preds = self.D(self.fake_exp)
+        # The reference lets g_loss.backward() also fill D's parameter gradients and then discards them at the next
+        # d_optimizer.zero_grad() (trainer.py:89).  Same result without the wasted weight-gradient
+        # GEMMs: D's parameters are frozen for these two forwards (the gradient w.r.t. fake_exp still flows).
+        d_params = [p for p in self.D.parameters() if p.requires_grad]
+        for p in d_params:
+            p.requires_grad_(False)
+        try:
+            real_exp_preds = self.D(real_exp)
+            fake_exp_preds = self.D(self.fake_exp)
+        finally:
+            for p in d_params:
+                p.requires_grad_(True)
         g_adv_loss = a.lambda_adv * gan(real_exp_preds, fake_exp_preds, None, None, for_discriminator=False)
         g_percep_loss = a.lambda_percep * self.criterionPercep((self.fake_exp + 1.) / 2., (real_raw + 1.) / 2.)
         self.real_exp_idt = self.G(real_exp)
