@@ -19,10 +19,16 @@ def _stream() -> int:
 class _Counters:
     launches = 0          # kernels of libuegan_sm100.so launched through this module
     conv_events = None    # when a list: (start, end, flops) CUDA-event triples around every conv launch
+    trace = None          # when a list: (description, launches) per wrapper call, in issue order (profiling only)
 
 
-def _count(n: int):
+def _count(n: int, what: str = "", *tensors):
     _Counters.launches += n
+    tr = _Counters.trace
+    if tr is not None:
+        dims = " ".join(f"{t.n}x{t.h}x{t.w}x{t.c}h{t.halo}{'f' if t.dtype == L.F32 else 'h'}" for t in tensors
+                        if t is not None)
+        tr.append((f"{what} {dims}".strip(), n))
 
 
 def launches() -> int:
@@ -80,7 +86,7 @@ def packed_weight(weight: torch.Tensor, cin_stored: int, dtype: int, cin_first: 
     assert buf.numel() >= nbytes
     L.check(lib.uegan_pack_conv_weight(w.data_ptr(), buf.data_ptr(), cout, i_total, cin_first, cin, cin_stored, k,
                                        dtype, int(transpose_flip), _stream()), "pack_conv_weight")
-    _count(1)
+    _count(1, "pack_weight")
     return buf
 
 
@@ -114,7 +120,7 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
         wo = (x.w + 2 * pad - k) // stride + 1
         cin = 3 if x.c * (4 if x.dtype == L.F32 else 2) == 16 else x.c
         ev.append((s0, s1, 2.0 * x.n * ho * wo * cout * k * k * cin, x, cout, k, stride, "fprop", x.dtype))
-    _count(1)
+    _count(1, f"fprop ->{cout} k{k}s{stride}{' +stats' if in_stats is not None else ''}", x)
 
 
 def pack_input(x_nchw: torch.Tensor, dst: NHWC, pad_mode: int = L.PAD_REFLECT, scale=None, shift=None):
@@ -122,19 +128,19 @@ def pack_input(x_nchw: torch.Tensor, dst: NHWC, pad_mode: int = L.PAD_REFLECT, s
     assert tuple(x_nchw.shape) == (dst.n, 3, dst.h, dst.w)
     L.check(L.load().uegan_pack_input(x_nchw.data_ptr(), dst.ref(), pad_mode, L.float3(scale), L.float3(shift),
                                       _stream()), "pack_input")
-    _count(1)
+    _count(1, "pack_input", dst)
 
 
 def halo_fill(t: NHWC, pad_mode: int = L.PAD_REFLECT):
     L.check(L.load().uegan_halo_fill(t.ref(), pad_mode, _stream()), "halo_fill")
-    _count(1)
+    _count(1, "halo_fill", t)
 
 
 def instance_norm(src: NHWC, dst: NHWC, dst_c_off: int, stats_ws: torch.Tensor, eps: float = 1e-5):
     assert stats_ws.dtype == torch.float64 and stats_ws.numel() >= 3 * src.n * src.c
     L.check(L.load().uegan_instance_norm(src.ref(), dst.ref(), dst_c_off, eps, stats_ws.data_ptr(), _stream()),
             "instance_norm")
-    _count(3)
+    _count(3, "instance_norm", src)
 
 
 def instance_norm_apply(src: NHWC, dst: NHWC, dst_c_off: int, stats_ws: torch.Tensor, eps: float = 1e-5):
@@ -142,7 +148,7 @@ def instance_norm_apply(src: NHWC, dst: NHWC, dst_c_off: int, stats_ws: torch.Te
     assert stats_ws.dtype == torch.float64 and stats_ws.numel() >= 3 * src.n * src.c
     L.check(L.load().uegan_instance_norm_apply(src.ref(), dst.ref(), dst_c_off, eps, stats_ws.data_ptr(), _stream()),
             "instance_norm_apply")
-    _count(2)
+    _count(2, "instance_norm_apply", src)
 
 
 def fused_stats_ok(ho: int, wo: int) -> bool:
@@ -157,17 +163,17 @@ def spectral_sigma(w: torch.Tensor, u: torch.Tensor, v: torch.Tensor, train: boo
     assert ws.numel() >= rows + cols + 8 and sigma_out.numel() >= 2
     L.check(L.load().uegan_spectral_sigma(w.data_ptr(), u.data_ptr(), v.data_ptr(), rows, cols, int(train),
                                           sigma_out.data_ptr(), ws.data_ptr(), _stream()), "spectral_sigma")
-    _count(6 if train else 2)
+    _count(6 if train else 2, "spectral_sigma")
 
 
 def upsample2x(src: NHWC, dst: NHWC, dst_c_off: int = 0):
     L.check(L.load().uegan_upsample2x(src.ref(), dst.ref(), dst_c_off, _stream()), "upsample2x")
-    _count(1)
+    _count(1, "upsample2x", src)
 
 
 def maxpool2x2(src: NHWC, dst: NHWC):
     L.check(L.load().uegan_maxpool2x2(src.ref(), dst.ref(), _stream()), "maxpool2x2")
-    _count(1)
+    _count(1, "maxpool2x2", src)
 
 
 def unpack_nchw(src: NHWC, c_off: int, c_count: int) -> torch.Tensor:
@@ -209,7 +215,7 @@ def gan_loss_fwd(mode: int, for_d: bool, real, fake, ws: torch.Tensor, loss_out:
     if group is None:
         L.check(lib.uegan_gan_loss_fwd(mode, int(for_d), len(real), _ptr_array(real), _ptr_array(fake), counts,
                                        ws.data_ptr(), loss_out.data_ptr(), _stream()), "gan_loss_fwd")
-        _count(3)
+        _count(3, "gan_loss_fwd")
         return 1
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -234,7 +240,7 @@ def gan_loss_bwd(mode: int, for_d: bool, real, fake, ws: torch.Tensor, d_real, d
                                         _ptr_array(d_fake) if d_fake is not None else None,
                                         gscale_dev.data_ptr() if gscale_dev is not None else None,
                                         -float(world) if world > 1 else 1.0, _stream()), "gan_loss_bwd")
-    _count(1)
+    _count(1, "gan_loss_bwd")
 
 
 def instance_norm_stats(src: NHWC, stats_ws: torch.Tensor, sums_ready: bool = False, eps: float = 1e-5) -> int:
@@ -243,14 +249,14 @@ def instance_norm_stats(src: NHWC, stats_ws: torch.Tensor, sums_ready: bool = Fa
     out = C.c_void_p()
     L.check(L.load().uegan_instance_norm_stats(src.ref(), eps, stats_ws.data_ptr(), int(sums_ready), C.byref(out),
                                                _stream()), "instance_norm_stats")
-    _count(1 if sums_ready else 2)
+    _count(1 if sums_ready else 2, "instance_norm_stats", src)
     return out.value
 
 
 def in_mse_fwd(x: NHWC, y: NHWC, mr_x: int, mr_y: int, weight: float, accum: torch.Tensor, loss: torch.Tensor):
     L.check(L.load().uegan_in_mse_fwd(x.ref(), y.ref(), mr_x, mr_y, float(weight), accum.data_ptr(), loss.data_ptr(),
                                       _stream()), "in_mse_fwd")
-    _count(2)
+    _count(2, "in_mse_fwd", x)
 
 
 def msrec_loss(pred: torch.Tensor, gt: torch.Tensor, rec_type: int, scales: int, accum: torch.Tensor,
@@ -262,7 +268,7 @@ def msrec_loss(pred: torch.Tensor, gt: torch.Tensor, rec_type: int, scales: int,
                                       loss.data_ptr(), grad.data_ptr() if grad is not None else None,
                                       float(grad_scale), gscale_dev.data_ptr() if gscale_dev is not None else None,
                                       _stream()), "msrec_loss")
-    _count(2)
+    _count(2, "msrec_loss")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -283,7 +289,7 @@ def packed_weight_dgrad(weight: torch.Tensor, cout_stored: int, dtype: int, stri
     assert buf.numel() >= nbytes
     L.check(lib.uegan_pack_conv_weight_dgrad(w.data_ptr(), buf.data_ptr(), o, i_total, cin_first, cin, cout_stored, k,
                                              stride, pi, pj, dtype, _stream()), "pack_conv_weight_dgrad")
-    _count(1)
+    _count(1, "pack_weight_dgrad")
     return buf
 
 
@@ -312,7 +318,7 @@ def conv_generic(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int
         taps = real_taps if real_taps is not None else k * k
         real_c = 3 if cout == 16 and y.c == 16 else cout
         ev.append((s0, s1, 2.0 * x.n * x.h * x.w * x.c * real_c * taps, x, cout, k, stride, "dgrad", x.dtype))
-    _count(1)
+    _count(1, f"dgrad ->{cout} k{k} ymul{y_mul}{' +mask' if mask is not None else ''}", x)
 
 
 def conv_dgrad(dz: NHWC, weight: torch.Tensor, k: int, stride: int, dxp: NHWC, cache=None, key=None, alpha=None,
@@ -350,14 +356,14 @@ def conv_wgrad(x: NHWC, dz: NHWC, dw: torch.Tensor, k: int, stride: int, pad: in
         s1.record()
         real_cin = 3 if x.c == 4 else cin_n
         ev.append((s0, s1, 2.0 * dz.n * dz.h * dz.w * cout * real_cin * k * k, x, cout, k, stride, "wgrad", x.dtype))
-    _count(1)
+    _count(1, f"wgrad cout{cout} cin{cin_n} k{k}s{stride}", x, dz)
 
 
 def head_bwd(dout: torch.Tensor, out: torch.Tensor, x, mode: int, dz: NHWC):
     assert dout.is_contiguous() and out.is_contiguous() and dout.dtype == torch.float32
     L.check(L.load().uegan_head_bwd(dout.data_ptr(), out.data_ptr(), x.data_ptr() if x is not None else None,
                                     dout.shape[1], mode, dz.ref(), _stream()), "head_bwd")
-    _count(1)
+    _count(1, "head_bwd", dz)
 
 
 def grad_combine(dst: NHWC, channels: int, src_a: Optional[NHWC] = None, pad_a: int = 0, pad_mode_a: int = L.PAD_REFLECT,
@@ -368,31 +374,33 @@ def grad_combine(dst: NHWC, channels: int, src_a: Optional[NHWC] = None, pad_a: 
     L.check(L.load().uegan_grad_combine(dst.ref(), dst_c_off, channels, r(src_a), a_c_off, pad_a, pad_mode_a, r(add_b),
                                         b_c_off, r(add_c), c_c_off, r(mask), mask_c_off, act, r(mul), mul_c_off,
                                         _stream()), "grad_combine")
-    _count(1)
+    _count(1, f"grad_combine c{channels} pad{pad_a if src_a is not None else '-'}"
+              f"{' +b' if add_b is not None else ''}{' +c' if add_c is not None else ''}"
+              f"{' mask' if mask is not None else ''}{' mul' if mul is not None else ''}", dst, src_a)
 
 
 def channel_sum(src: NHWC, out: torch.Tensor, c_off: int = 0, channels: Optional[int] = None):
     channels = out.numel() if channels is None else channels
     assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
     L.check(L.load().uegan_channel_sum(src.ref(), c_off, channels, out.data_ptr(), _stream()), "channel_sum")
-    _count(1)
+    _count(1, f"channel_sum c{channels}", src)
 
 
 def instance_norm_bwd(dout: NHWC, d_c_off: int, z: NHWC, mean_rstd: int, dz: NHWC, ws: torch.Tensor):
     assert ws.dtype == torch.float64 and ws.numel() >= 2 * z.n * z.c
     L.check(L.load().uegan_instance_norm_bwd(dout.ref(), d_c_off, z.ref(), mean_rstd, dz.ref(), ws.data_ptr(),
                                              _stream()), "instance_norm_bwd")
-    _count(2)
+    _count(2, "instance_norm_bwd", z)
 
 
 def upsample2x_bwd(dout: NHWC, d_c_off: int, dsrc: NHWC):
     L.check(L.load().uegan_upsample2x_bwd(dout.ref(), d_c_off, dsrc.ref(), _stream()), "upsample2x_bwd")
-    _count(1)
+    _count(1, "upsample2x_bwd", dout)
 
 
 def maxpool2x2_bwd(src: NHWC, dpool: NHWC, dsrc: NHWC):
     L.check(L.load().uegan_maxpool2x2_bwd(src.ref(), dpool.ref(), dsrc.ref(), _stream()), "maxpool2x2_bwd")
-    _count(1)
+    _count(1, "maxpool2x2_bwd", src)
 
 
 def in_mse_bwd(x: NHWC, y: NHWC, mr_x: int, mr_y: int, weight: float, gscale, deep: Optional[NHWC], dx: NHWC,
@@ -401,12 +409,12 @@ def in_mse_bwd(x: NHWC, y: NHWC, mr_x: int, mr_y: int, weight: float, gscale, de
                                       gscale.data_ptr() if gscale is not None else None,
                                       deep.ref() if deep is not None else None, dx.ref(), ws.data_ptr(), _stream()),
             "in_mse_bwd")
-    _count(2)
+    _count(2, f"in_mse_bwd{' +deep' if deep is not None else ''}", x)
 
 
 def unpack_input_grad(dx: NHWC, scale, out: torch.Tensor):
     L.check(L.load().uegan_unpack_input_grad(dx.ref(), L.float3(scale), out.data_ptr(), _stream()), "unpack_input_grad")
-    _count(1)
+    _count(1, "unpack_input_grad", dx)
 
 
 def spectral_bwd(grad: torch.Tensor, w: torch.Tensor, u: torch.Tensor, v: torch.Tensor, sigma: torch.Tensor,
@@ -414,4 +422,4 @@ def spectral_bwd(grad: torch.Tensor, w: torch.Tensor, u: torch.Tensor, v: torch.
     rows = w.shape[0]
     L.check(L.load().uegan_spectral_bwd(grad.data_ptr(), w.data_ptr(), u.data_ptr(), v.data_ptr(), sigma.data_ptr(),
                                         rows, w.numel() // rows, ws.data_ptr(), _stream()), "spectral_bwd")
-    _count(2)
+    _count(2, "spectral_bwd")
