@@ -100,6 +100,21 @@ int uegan_pack_conv_weight_dgrad(const float* w_oihw, void* w_packed, int32_t co
 
 int uegan_conv2d_fprop(const uegan_conv_desc* desc, void* stream);
 
+/* "Row-sum" variant of uegan_conv2d_fprop for stride-1 convolutions with a TINY output-channel count written as planar
+ * fp32 (desc->out_nchw): the Generator's last conv 32 -> 3, k7 + tanh + clamp(res + x) (models.py:34-35,72) and the
+ * Discriminator's prediction heads C -> 1, k7 / k5 (models.py:110-126).  The horizontal taps become GEMM columns
+ * (N = k*cout), only the vertical taps stay in the K loop, and the epilogue sums the k shifted columns with warp
+ * shuffles: k*C/8 MMAs per 128 PATCH pixels instead of k*k*C/8 per 128 output pixels.  tf32 only, x.c % 32 == 0,
+ * (k, cout) in {(7,3), (7,1), (5,1), (3,1)}.  desc->w_packed must come from uegan_pack_conv_weight_rowsum; y, mul, mask,
+ * in_stats, y_mul are not used.  uegan_conv2d_rowsum_supported() != 0 tells whether a shape qualifies (weights plus two
+ * patch stages must fit in shared memory). */
+int uegan_conv2d_rowsum_supported(int32_t cout, int32_t cin_stored, int32_t k, int32_t dtype);
+size_t uegan_packed_weight_rowsum_bytes(int32_t cout, int32_t cin_stored, int32_t k);
+/* OIHW fp32 -> [(s, o) rows padded to a multiple of 16][r][cin_stored] tf32. */
+int uegan_pack_conv_weight_rowsum(const float* w_oihw, void* w_packed, int32_t cout, int32_t cin_total, int32_t cin_first,
+                                  int32_t cin, int32_t cin_stored, int32_t k, void* stream);
+int uegan_conv2d_fprop_rowsum(const uegan_conv_desc* desc, void* stream);
+
 /* NCHW fp32 image batch -> NHWC tensor with halo (pad_mode) and per-channel affine  v = x*scale[c] + shift[c]
  * (scale/shift are HOST arrays of 3 floats or NULL).  Replaces the implicit layout of models.py:47 inputs, and
  * (x+1)/2 -> (x-mean)/std of trainer.py:108 + losses.py:26-27 for the VGG tower.  Channels >= 3 are zero. */

@@ -138,11 +138,16 @@ def test_elementwise_backward(K):
     td = fill_nhwc(K, dout, 2 * c, 0, L.PAD_ZERO, L.F32)
     ws = torch.empty(3 * n * c, dtype=torch.float64, device="cuda")
     mr = K.instance_norm_stats(tz, ws)
-    dz = K.NHWC(n, h, w, c, 0, L.F32, "cuda")
-    K.instance_norm_bwd(td, c, tz, mr, dz, torch.empty(2 * n * c, dtype=torch.float64, device="cuda"))
     zr = z.double().requires_grad_(True)
     F.instance_norm(zr, eps=1e-5).backward(dout[:, c:].double())
-    assert relerr(dz.interior_nchw(), zr.grad) < 1e-3
+    for halo in (0, 2):
+        dz = K.NHWC(n, h, w, c, halo, L.F32, "cuda")
+        dz.buf.fill_(5.0)
+        K.instance_norm_bwd(td, c, tz, mr, dz, torch.empty(2 * n * c, dtype=torch.float64, device="cuda"))
+        assert relerr(dz.interior_nchw(), zr.grad) < 1e-3
+        if halo:
+            pv = dz.padded_view()
+            assert float(pv[:, :halo].abs().max()) == 0.0 and float(pv[:, :, -halo:].abs().max()) == 0.0
     # upsample backward
     up = tf32(torch.randn(n, 2 * c, 2 * h, 2 * w, device="cuda", generator=g))
     tu = fill_nhwc(K, up, 2 * c, 0, L.PAD_ZERO, L.F32)

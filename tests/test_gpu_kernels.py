@@ -209,3 +209,76 @@ def test_elementwise(K, dtype_name):
     assert relerr(td.interior_nchw(), F.max_pool2d(ta.interior_nchw(), 2, 2)) < 1e-6
     assert relerr(K.unpack_nchw(ta, 8, 16), ta.interior_nchw()[:, 8:24]) < 1e-6
     assert K.device_error() == 0
+
+
+@pytest.mark.parametrize("case", [
+    # (n, cin, h, w, cout, k, residual)
+    (2, 32, 24, 40, 3, 7, True),     # G's last conv: N = 21 -> 32, ragged 26-column tiles, 16-row tiles
+    (1, 32, 37, 61, 1, 7, False),    # odd extents: partial tiles in both directions
+    (2, 64, 16, 32, 1, 7, False),    # two channel chunks per patch
+    (1, 128, 20, 28, 1, 7, False),   # four chunks
+    (2, 256, 12, 36, 1, 5, False),   # k5 head, weights force the 8-row tile variant
+    (1, 32, 8, 8, 1, 3, False),      # k3, image smaller than a tile
+])
+def test_conv_rowsum(K, case):
+    """Row-sum kernel (csrc/conv_rowsum.cu) vs fp64 conv2d on tf32-representable operands, with alpha / bias / tanh /
+    residual + clamp / aux exactly as the generic planar epilogue."""
+    from uegan_b200 import _lib as L
+    n, cin, h, w, cout, k, resid = case
+    g = torch.Generator(device="cuda").manual_seed(100 + cin + k)
+    assert K.rowsum_supported(cout, cin, k, L.F32)
+    x = tf32(torch.randn(n, cin, h, w, device="cuda", generator=g))
+    wgt = tf32(torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k))
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.1
+    alpha = torch.tensor([0.73], device="cuda")
+    pad = (k - 1) // 2
+    xt = fill_nhwc(K, x, cin, pad + 1, L.PAD_REFLECT, L.F32)  # halo larger than pad: exercises patch_off
+    out = torch.full((n, cout, h, w), 7.0, device="cuda")
+    aux = torch.full((n, cout, h, w), 7.0, device="cuda")
+    res = torch.rand(n, cout, h, w, device="cuda", generator=g) * 2 - 1 if resid else None
+
+    class Cache:
+        def get(self, key, param, fn):
+            return fn()
+    K.conv_planar(xt, wgt, Cache(), "t", k, pad, bias, alpha, L.ACT_TANH, out, res, aux)
+    assert K.device_error() == 0
+    ref = torch.tanh(0.73 * F.conv2d(F.pad(x, (pad,) * 4, mode="reflect").double(), wgt.double())
+                     + bias.double().view(1, -1, 1, 1)).float()
+    assert relerr(aux, ref) < 2e-5
+    if resid:
+        ref = torch.clamp(ref + res, -1, 1)
+    assert relerr(out, ref) < 2e-5
+
+
+def test_in_mse_bwd_direct(K):
+    """Gradient of weight * mean((IN(x) - IN(y))^2) w.r.t. fp16 features x (+ deep gradient, ReLU mask), zero halo."""
+    from uegan_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(21)
+    n, c, h, w = 2, 64, 12, 20
+    x = torch.relu(torch.randn(n, c, h, w, device="cuda", generator=g) + 0.3).half().float()
+    y = torch.relu(torch.randn(n, c, h, w, device="cuda", generator=g) + 0.3).half().float()
+    deep = (torch.randn(n, c, h, w, device="cuda", generator=g) * 0.1).half().float()
+    tx = fill_nhwc(K, x, c, 1, L.PAD_ZERO, L.F16)
+    ty = fill_nhwc(K, y, c, 1, L.PAD_ZERO, L.F16)
+    tdeep = fill_nhwc(K, deep, c, 1, L.PAD_ZERO, L.F16)
+    wsx = torch.empty(3 * n * c, dtype=torch.float64, device="cuda")
+    wsy = torch.empty(3 * n * c, dtype=torch.float64, device="cuda")
+    mx, my = K.instance_norm_stats(tx, wsx), K.instance_norm_stats(ty, wsy)
+    weight = 50.0
+    gs = torch.tensor([0.5], device="cuda")
+    for dp in (None, tdeep):
+        dx = K.NHWC(n, h, w, c, 1, L.F16, "cuda")
+        dx.buf.fill_(3.0)
+        K.in_mse_bwd(tx, ty, mx, my, weight, gs, dp, dx, torch.empty(2 * n * c, dtype=torch.float64, device="cuda"))
+        assert K.device_error() == 0
+        xr = x.double().requires_grad_(True)
+        loss = weight * 0.5 * F.mse_loss(F.instance_norm(xr, eps=1e-5), F.instance_norm(y.double(), eps=1e-5))
+        loss.backward()
+        ref = xr.grad
+        if dp is not None:
+            ref = ref + deep.double()
+        ref = torch.where(x > 0, ref, torch.zeros_like(ref))
+        assert relerr(dx.interior_nchw(), ref) < 2e-3
+        pv = dx.padded_view().float()
+        assert float(pv[:, 0].abs().max()) == 0.0 and float(pv[:, :, 0].abs().max()) == 0.0
+        assert float(pv[:, -1].abs().max()) == 0.0 and float(pv[:, :, -1].abs().max()) == 0.0

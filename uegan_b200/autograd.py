@@ -120,8 +120,7 @@ def _g_forward_train(G, x, ws):
     conv(P["y4m"], "dec5.0", G.dec5[0], d, 3, 1, P["t"]); K.halo_fill(P["t"])
     out = torch.empty_like(x)
     cv = G.dec5[1].conv
-    K.conv_fprop(P["t"], G._w("dec5.1", cv, d), 3, 7, 1, 3, None, 0, cv.bias, None, L.ACT_TANH, None, out, x,
-                 aux_nchw=P["res"])
+    K.conv_planar(P["t"], cv.weight, G._wcache, "dec5.1", 7, 3, cv.bias, None, L.ACT_TANH, out, x, aux_nchw=P["res"])
     return out
 
 
@@ -313,8 +312,7 @@ def _d_forward_train(D, x, ws):
         K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, D._act)
         K.halo_fill(dst)
         pred = torch.empty(x.shape[0], 1, dst.h, dst.w, dtype=torch.float32, device=x.device)
-        hp = D._wcache.get(f"p{i}", head.weight, lambda out=None: K.packed_weight(head.weight, dst.c, F32, out=out))
-        K.conv_fprop(dst, hp, 1, k, 1, pad, None, 0, None, None, D._head_act, None, pred)
+        K.conv_planar(dst, head.weight, D._wcache, f"p{i}", k, pad, None, None, D._head_act, pred)
         preds.append(pred)
         src = dst
     ws["preds"] = preds

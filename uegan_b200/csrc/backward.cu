@@ -174,84 +174,166 @@ struct InBwdStatsOp {
     atomicAdd(&sums[((long long)n * z.c + c) * 2 + 1], (double)t[1]);
   }
 };
-template <typename T>
-__global__ void in_bwd_apply_kernel(TGeom dsrc, int d_c_off, TGeom z, TGeom dst, const float* __restrict__ mr,
-                                    const double* __restrict__ sums, double inv_npix, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+// The "apply" pass of a normalisation backward needs six per-(n, c) statistics per element.  The block stages them for
+// its image in shared memory (prologue: one thread per channel), then streams ROWS padded rows of one x-chunk:
+// grid = (x-chunks, row groups, images), no per-element divisions, no per-element global statistics loads.  The
+// per-element arithmetic is unchanged (bit-identical to evaluating the formulas below from global memory):
+//   mode 0  InstanceNorm backward: a = dout, b = z:  xhat = (b - mean)*rstd ; dz = rstd*(a - m1 - xhat*m2)
+//   mode 1  VGG tap (InstanceNorm + MSE) backward: a = x, b = y:  xh, yh normalised ; e = xh - yh ;
+//           g = (cf*rstd_x)*(e - m1 - xh*m2) (+ deep), then the ReLU mask of x
+// with m1 = mean_p(g), m2 = mean_p(g * xhat) from the strip-reduce pass before.
+struct AffineArgs {
+  TGeom a; int a_c_off;
+  TGeom b;
+  TGeom deep; int has_deep;
+  TGeom dst;
+  const float* mra;   // (mean, rstd) pairs of the normalised tensor (mode 0: of b = z; mode 1: of a = x)
+  const float* mrb;   // mode 1: (mean, rstd) of y
+  const double* sums; // per-(n, c) { sum(g), sum(g * xhat) }
+  double inv_npix;
+  float coef;
+  const float* gscale;
+  int mode, cch, cv_log2;
+};
+template <typename T, typename TG, int ROWS>
+__global__ void __launch_bounds__(256) affine_apply_kernel(const AffineArgs q) {
+  extern __shared__ float s_coef[];  // [6][cch]: mean_a, rstd_a (or cf*rstd_x), mean_b, rstd_b, m1, m2
   constexpr int VN = Vec<T>::N;
-  const int cv = z.c / VN;
-  const int c = (int)(i % cv) * VN;
-  long long pix = i / cv;
-  const int xp = (int)(pix % dst.wp);
-  pix /= dst.wp;
-  const int yp = (int)(pix % dst.hp);
-  const int n = (int)(pix / dst.hp);
-  const int y = yp - dst.halo, x = xp - dst.halo;
-  float v[VN];
+  const int n = blockIdx.z, C = q.cch;
+  {
+    const float cf = q.coef * (q.gscale ? __ldg(q.gscale) : 1.f);
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      const long long si = ((long long)n * C + ch) * 2;
+      s_coef[ch] = q.mra[si];
+      s_coef[C + ch] = q.mra[si + 1];
+      s_coef[2 * C + ch] = q.mode == 1 ? q.mrb[si] : 0.f;
+      s_coef[3 * C + ch] = q.mode == 1 ? q.mrb[si + 1] : 0.f;
+      s_coef[4 * C + ch] = (float)(q.sums[si] * q.inv_npix);
+      s_coef[5 * C + ch] = (float)(q.sums[si + 1] * q.inv_npix);
+    }
+    if (threadIdx.x == 0) s_coef[6 * C] = cf;
+  }
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int xp = t >> q.cv_log2;
+  if (xp >= (int)q.dst.wp) return;
+  const int c = (t & ((1 << q.cv_log2) - 1)) * VN;
+  const int x = xp - q.dst.halo;
+  const bool xin = x >= 0 && x < q.dst.w;
+  const float cf = s_coef[6 * C];
+  float av[ROWS][VN], bv[ROWS][VN], dv[ROWS][VN];
+  bool in[ROWS];
 #pragma unroll
-  for (int k = 0; k < VN; ++k) v[k] = 0.f;
-  if (y >= 0 && y < dst.h && x >= 0 && x < dst.w) {
-    float g[VN], zz[VN];
-    Vec<T>::load(static_cast<const T*>(dsrc.data) + toff(dsrc, n, y, x, d_c_off + c), g);
-    Vec<T>::load(static_cast<const T*>(z.data) + toff(z, n, y, x, c), zz);
-#pragma unroll
-    for (int k = 0; k < VN; ++k) {
-      const long long si = ((long long)n * z.c + c + k) * 2;
-      const float mean = mr[si], rstd = mr[si + 1];
-      const float xh = (zz[k] - mean) * rstd;
-      const float m1 = (float)(sums[si] * inv_npix), m2 = (float)(sums[si + 1] * inv_npix);
-      v[k] = rstd * (g[k] - m1 - xh * m2);
+  for (int r = 0; r < ROWS; ++r) {  // all loads first (independent), then the arithmetic
+    const int y = (int)blockIdx.y * ROWS + r - q.dst.halo;
+    in[r] = xin && y >= 0 && y < q.dst.h;
+    if (in[r]) {
+      Vec<T>::load(static_cast<const T*>(q.a.data) + toff(q.a, n, y, x, q.a_c_off + c), av[r]);
+      Vec<T>::load(static_cast<const T*>(q.b.data) + toff(q.b, n, y, x, c), bv[r]);
+      if (q.has_deep) Vec<TG>::load(static_cast<const TG*>(q.deep.data) + toff(q.deep, n, y, x, c), dv[r]);
     }
   }
-  Vec<T>::store(static_cast<T*>(dst.data) + toff(dst, n, y, x, c), v);
+  float v[ROWS][VN];
+#pragma unroll
+  for (int k = 0; k < VN; ++k) {
+    const float ma = s_coef[c + k], ra = s_coef[C + c + k], mb = s_coef[2 * C + c + k], rb = s_coef[3 * C + c + k];
+    const float m1 = s_coef[4 * C + c + k], m2 = s_coef[5 * C + c + k];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      float g = 0.f;
+      if (in[r]) {
+        if (q.mode == 0) {
+          const float xh = (bv[r][k] - ma) * ra;
+          g = ra * (av[r][k] - m1 - xh * m2);
+        } else {
+          const float xh = (av[r][k] - ma) * ra;
+          const float yh = (bv[r][k] - mb) * rb;
+          const float e = xh - yh;
+          g = cf * ra * (e - m1 - xh * m2);
+          if (q.has_deep) g += dv[r][k];
+          g = av[r][k] > 0.f ? g : 0.f;  // ReLU mask of the tap
+        }
+      }
+      v[r][k] = g;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int yp = (int)blockIdx.y * ROWS + r;
+    if (yp >= (int)q.dst.hp) break;
+    Vec<TG>::store(static_cast<TG*>(q.dst.data) + toff(q.dst, n, yp - q.dst.halo, x, c), v[r]);
+  }
+}
+template <typename T, typename TG>
+static int launch_affine_apply(AffineArgs& q, cudaStream_t st) {
+  constexpr int VN = Vec<T>::N, ROWS = 2;
+  const int cv = q.cch / VN;
+  int lg = 0;
+  while ((1 << lg) < cv) ++lg;
+  UEGAN_CHECK((1 << lg) == cv, "normalisation backward: channels / vector width must be a power of two (got %d)", cv);
+  UEGAN_CHECK(q.dst.n <= 65535 && (q.dst.hp + ROWS - 1) / ROWS <= 65535, "normalisation backward: tensor too large");
+  q.cv_log2 = lg;
+  const dim3 grid((unsigned)((q.dst.wp * cv + 255) / 256), (unsigned)((q.dst.hp + ROWS - 1) / ROWS), (unsigned)q.dst.n);
+  affine_apply_kernel<T, TG, ROWS><<<grid, 256, (6 * q.cch + 1) * sizeof(float), st>>>(q);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------
 // bilinear x2 (align_corners) backward, gather form: exact adjoint of upsample2x_kernel
 // ------------------------------------------------------------------------------------------
+// For the x2 case only output rows 2*yi-2 .. 2*yi+3 can have floor(sy*yo) in {yi-1, yi} (1/sy = 2 + 1/(h-1)); the
+// weights are derived from the SAME float expression the forward kernel evaluates, so the pair is an exact adjoint.
+// grid = (x-chunks of an input row, input rows, images).
 template <typename T>
-__global__ void upsample2x_bwd_kernel(TGeom g, int g_c_off, TGeom d, float sy, float sx, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+__global__ void upsample2x_bwd_kernel(TGeom g, int g_c_off, TGeom d, float sy, float sx, int cv_log2) {
   constexpr int VN = Vec<T>::N;
-  const int cv = d.c / VN;
-  const int c = (int)(i % cv) * VN;
-  long long pix = i / cv;
-  const int xi = (int)(pix % d.w);
-  pix /= d.w;
-  const int yi = (int)(pix % d.h);
-  const int n = (int)(pix / d.h);
-  float acc[VN];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int xi = t >> cv_log2;
+  if (xi >= d.w) return;
+  const int c = (t & ((1 << cv_log2) - 1)) * VN;
+  const int yi = blockIdx.y, n = blockIdx.z;
+  float wy[6], wx[6];
 #pragma unroll
-  for (int k = 0; k < VN; ++k) acc[k] = 0.f;
-  // candidate output rows / cols whose 2-tap footprint can touch (yi, xi)
-  int yo0 = sy > 0.f ? (int)floorf((yi - 1) / sy) : 0, yo1 = sy > 0.f ? (int)ceilf((yi + 1) / sy) : g.h - 1;
-  int xo0 = sx > 0.f ? (int)floorf((xi - 1) / sx) : 0, xo1 = sx > 0.f ? (int)ceilf((xi + 1) / sx) : g.w - 1;
-  yo0 = max(yo0, 0); xo0 = max(xo0, 0); yo1 = min(yo1, g.h - 1); xo1 = min(xo1, g.w - 1);
-  const T* gb = static_cast<const T*>(g.data);
-  for (int yo = yo0; yo <= yo1; ++yo) {
-    const float fy = sy * yo;
-    const int y0 = (int)fy;
-    const int y1 = y0 + (y0 < d.h - 1 ? 1 : 0);
-    const float ly = fy - y0;
-    float wy = 0.f;
-    if (y0 == yi) wy += 1.f - ly;
-    if (y1 == yi) wy += ly;
-    if (wy == 0.f) continue;
-    for (int xo = xo0; xo <= xo1; ++xo) {
+  for (int j = 0; j < 6; ++j) {
+    const int yo = 2 * yi - 2 + j;
+    float w = 0.f;
+    if (yo >= 0 && yo < g.h) {
+      const float fy = sy * yo;
+      const int y0 = (int)fy;
+      const int y1 = y0 + (y0 < d.h - 1 ? 1 : 0);
+      const float ly = fy - y0;
+      if (y0 == yi) w += 1.f - ly;
+      if (y1 == yi) w += ly;
+    }
+    wy[j] = w;
+    const int xo = 2 * xi - 2 + j;
+    w = 0.f;
+    if (xo >= 0 && xo < g.w) {
       const float fx = sx * xo;
       const int x0 = (int)fx;
       const int x1 = x0 + (x0 < d.w - 1 ? 1 : 0);
       const float lx = fx - x0;
-      float wx = 0.f;
-      if (x0 == xi) wx += 1.f - lx;
-      if (x1 == xi) wx += lx;
-      if (wx == 0.f) continue;
-      float t[VN];
-      Vec<T>::load(gb + toff(g, n, yo, xo, g_c_off + c), t);
+      if (x0 == xi) w += 1.f - lx;
+      if (x1 == xi) w += lx;
+    }
+    wx[j] = w;
+  }
+  float acc[VN];
 #pragma unroll
-      for (int k = 0; k < VN; ++k) acc[k] += wy * wx * t[k];
+  for (int k = 0; k < VN; ++k) acc[k] = 0.f;
+  const T* gb = static_cast<const T*>(g.data);
+#pragma unroll
+  for (int jy = 0; jy < 6; ++jy) {
+    if (wy[jy] == 0.f) continue;
+    const T* gr = gb + toff(g, n, 2 * yi - 2 + jy, 2 * xi - 2, g_c_off + c);
+#pragma unroll
+    for (int jx = 0; jx < 6; ++jx) {
+      if (wx[jx] == 0.f) continue;
+      float tv[VN];
+      Vec<T>::load(gr + (long long)jx * g.c, tv);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) acc[k] += wy[jy] * wx[jx] * tv[k];  // same order as the scatter's adjoint sum
     }
   }
   Vec<T>::store(static_cast<T*>(d.data) + toff(d, n, yi, xi, c), acc);
@@ -330,45 +412,6 @@ struct TapBwdStatsOp {
     atomicAdd(&sums[((long long)n * x.c + c) * 2 + 1], (double)t[1]);
   }
 };
-template <typename T, typename TG>
-__global__ void tap_bwd_apply_kernel(TGeom x, TGeom y, TGeom deep, int has_deep, TGeom dst, const float* __restrict__ mrx,
-                                     const float* __restrict__ mry, const double* __restrict__ sums, double inv_npix,
-                                     float coef, const float* __restrict__ gscale, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  constexpr int VN = 8;
-  const int cv = x.c / VN;
-  const int c = (int)(i % cv) * VN;
-  long long pix = i / cv;
-  const int xp = (int)(pix % dst.wp);
-  pix /= dst.wp;
-  const int yp = (int)(pix % dst.hp);
-  const int n = (int)(pix / dst.hp);
-  const int yy = yp - dst.halo, xx = xp - dst.halo;
-  float v[VN];
-#pragma unroll
-  for (int k = 0; k < VN; ++k) v[k] = 0.f;
-  if (yy >= 0 && yy < dst.h && xx >= 0 && xx < dst.w) {
-    float xv[VN], yv[VN], dv[VN];
-    Vec<T>::load(static_cast<const T*>(x.data) + toff(x, n, yy, xx, c), xv);
-    Vec<T>::load(static_cast<const T*>(y.data) + toff(y, n, yy, xx, c), yv);
-    if (has_deep) Vec<TG>::load(static_cast<const TG*>(deep.data) + toff(deep, n, yy, xx, c), dv);
-    const float cf = coef * (gscale ? gscale[0] : 1.f);
-#pragma unroll
-    for (int k = 0; k < VN; ++k) {
-      const long long si = ((long long)n * x.c + c + k) * 2;
-      const float xh = (xv[k] - mrx[si]) * mrx[si + 1];
-      const float yh = (yv[k] - mry[si]) * mry[si + 1];
-      const float e = xh - yh;
-      const float m1 = (float)(sums[si] * inv_npix), m2 = (float)(sums[si + 1] * inv_npix);
-      float g = cf * mrx[si + 1] * (e - m1 - xh * m2);
-      if (has_deep) g += dv[k];
-      v[k] = xv[k] > 0.f ? g : 0.f;  // ReLU mask of the tap
-    }
-  }
-  Vec<TG>::store(static_cast<TG*>(dst.data) + toff(dst, n, yy, xx, c), v);
-}
-
 // gradient of the packed input: NHWC (c >= 3) -> NCHW fp32 (3 channels) times per-channel scale
 template <typename TG>
 __global__ void unpack_grad_kernel(TGeom s, float* __restrict__ dst, float s0, float s1, float s2, long long total) {
@@ -497,10 +540,14 @@ int uegan_instance_norm_bwd(const uegan_tensor* dout, int32_t d_c_off, const ueg
     InBwdStatsOp<__half> op{g, d_c_off, zz, mean_rstd, ws};
     launch_strip_reduce<__half, 2>(op, zz.c, zz.n, zz.h, zz.w, st);
   }
-  const int vn = 16 / dtype_size(z->dtype);
-  const long long total = (long long)d.n * d.hp * d.wp * (zz.c / vn);
-  UEGAN_DISPATCH(z->dtype, in_bwd_apply_kernel,
-                 <<<nblk(total, 256), 256, 0, st>>>(g, d_c_off, zz, d, mean_rstd, ws, 1.0 / (double)npix, total));
+  AffineArgs q;
+  memset(&q, 0, sizeof(q));
+  q.a = g; q.a_c_off = d_c_off; q.b = zz; q.deep = d; q.has_deep = 0; q.dst = d;
+  q.mra = mean_rstd; q.mrb = nullptr; q.sums = ws; q.inv_npix = 1.0 / (double)npix; q.coef = 1.f; q.gscale = nullptr;
+  q.mode = 0; q.cch = zz.c;
+  if (z->dtype == UEGAN_F32) { if (launch_affine_apply<float, float>(q, st)) return -1; }
+  else if (z->dtype == UEGAN_BF16) { if (launch_affine_apply<__nv_bfloat16, __nv_bfloat16>(q, st)) return -1; }
+  else { if (launch_affine_apply<__half, __half>(q, st)) return -1; }
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -514,9 +561,14 @@ int uegan_upsample2x_bwd(const uegan_tensor* dout, int32_t d_c_off, const uegan_
   const float sy = g.h > 1 ? (float)(d.h - 1) / (float)(g.h - 1) : 0.f;
   const float sx = g.w > 1 ? (float)(d.w - 1) / (float)(g.w - 1) : 0.f;
   const int vn = 16 / dtype_size(dsrc->dtype);
-  const long long total = (long long)d.n * d.h * d.w * (d.c / vn);
+  const int cv = d.c / vn;
+  int lg = 0;
+  while ((1 << lg) < cv) ++lg;
+  UEGAN_CHECK((1 << lg) == cv, "upsample2x_bwd: channels / vector width must be a power of two (got %d)", cv);
+  UEGAN_CHECK(d.h <= 65535 && d.n <= 65535, "upsample2x_bwd: tensor too large for the launch grid");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  UEGAN_DISPATCH(dsrc->dtype, upsample2x_bwd_kernel, <<<nblk(total, 256), 256, 0, st>>>(g, d_c_off, d, sy, sx, total));
+  const dim3 grid(nblk((long long)d.w * cv, 256), (unsigned)d.h, (unsigned)d.n);
+  UEGAN_DISPATCH(dsrc->dtype, upsample2x_bwd_kernel, <<<grid, 256, 0, st>>>(g, d_c_off, d, sy, sx, lg));
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -558,10 +610,12 @@ int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* 
     launch_strip_reduce<__half, 2>(op, gx.c, gx.n, gx.h, gx.w, st);
   }
   const double numel = (double)gx.n * gx.c * (double)npix;
-  const long long total = (long long)gd.n * gd.hp * gd.wp * (gx.c / 8);
-  tap_bwd_apply_kernel<__half, __half><<<nblk(total, 256), 256, 0, st>>>(
-      gx, gy, gdeep, deep ? 1 : 0, gd, mean_rstd_x, mean_rstd_y, ws, 1.0 / (double)npix, (float)(2.0 * weight / numel),
-      gscale_dev, total);
+  AffineArgs q;
+  memset(&q, 0, sizeof(q));
+  q.a = gx; q.a_c_off = 0; q.b = gy; q.deep = gdeep; q.has_deep = deep ? 1 : 0; q.dst = gd;
+  q.mra = mean_rstd_x; q.mrb = mean_rstd_y; q.sums = ws; q.inv_npix = 1.0 / (double)npix;
+  q.coef = (float)(2.0 * weight / numel); q.gscale = gscale_dev; q.mode = 1; q.cch = gx.c;
+  if (launch_affine_apply<__half, __half>(q, st)) return -1;
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

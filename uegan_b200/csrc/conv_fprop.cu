@@ -524,6 +524,17 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   p.tiles_img = (x.n + p.tn - 1) / p.tn;
   p.block_n = g.cout_pad <= 256 ? g.cout_pad : 256;
   p.n_tiles = (g.cout_pad + p.block_n - 1) / p.block_n;
+  {
+    // few-tile launches (deep layers at small batch: d5, its data gradient, ...): split N while the doubled tile count
+    // still fits one wave -- an N >= 64 MMA costs ~N/2 cycles, so halving N halves a CTA's time and doubles the CTAs
+    const char* env = getenv("UEGAN_NO_NSPLIT");
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_img;
+    if (!(env && env[0] == '1'))
+      while (p.block_n >= 128 && p.block_n % 32 == 0 && 2 * m_tiles * p.n_tiles <= num_sms()) {
+        p.block_n /= 2;
+        p.n_tiles = (g.cout_pad + p.block_n - 1) / p.block_n;
+      }
+  }
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_img * p.n_tiles;
   p.kh = d.k;
   p.chunks_per_row = g.chunks_per_row;

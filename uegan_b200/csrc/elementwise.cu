@@ -269,17 +269,14 @@ __global__ void in_apply_kernel(TGeom s, TGeom d, int dst_c_off, const float* __
 // ------------------------------------------------------------------------------------------
 // bilinear x2, align_corners=True
 // ------------------------------------------------------------------------------------------
+// grid = (x-chunks of an output row, output rows, images): no per-thread divisions (cv is a power of two)
 template <typename T>
-__global__ void upsample2x_kernel(TGeom s, TGeom d, int dst_c_off, float sy, float sx, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int cv = s.c / Vec<T>::N;
-  const int c = (int)(i % cv) * Vec<T>::N;
-  long long pix = i / cv;
-  const int xo = (int)(pix % d.w);
-  pix /= d.w;
-  const int yo = (int)(pix % d.h);
-  const int n = (int)(pix / d.h);
+__global__ void upsample2x_kernel(TGeom s, TGeom d, int dst_c_off, float sy, float sx, int cv_log2) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int xo = t >> cv_log2;
+  if (xo >= d.w) return;
+  const int c = (t & ((1 << cv_log2) - 1)) * Vec<T>::N;
+  const int yo = blockIdx.y, n = blockIdx.z;
   const float fy = sy * yo, fx = sx * xo;
   const int y0 = (int)fy, x0 = (int)fx;
   const int y1 = y0 + (y0 < s.h - 1 ? 1 : 0), x1 = x0 + (x0 < s.w - 1 ? 1 : 0);
@@ -468,14 +465,19 @@ int uegan_upsample2x(const uegan_tensor* src, const uegan_tensor* dst, int32_t d
   const float sy = d.h > 1 ? (float)(s.h - 1) / (float)(d.h - 1) : 0.f;
   const float sx = d.w > 1 ? (float)(s.w - 1) / (float)(d.w - 1) : 0.f;
   const int vn = 16 / dtype_size(src->dtype);
-  const long long total = (long long)d.n * d.h * d.w * (s.c / vn);
+  const int cv = s.c / vn;
+  int lg = 0;
+  while ((1 << lg) < cv) ++lg;
+  UEGAN_CHECK((1 << lg) == cv, "upsample2x: channels / vector width must be a power of two (got %d)", cv);
+  UEGAN_CHECK(d.h <= 65535 && d.n <= 65535, "upsample2x: tensor too large for the launch grid");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid(nblocks((long long)d.w * cv, 256), (unsigned)d.h, (unsigned)d.n);
   if (src->dtype == UEGAN_F32)
-    upsample2x_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, sy, sx, total);
+    upsample2x_kernel<float><<<grid, 256, 0, st>>>(s, d, dst_c_off, sy, sx, lg);
   else if (src->dtype == UEGAN_BF16)
-    upsample2x_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, sy, sx, total);
+    upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(s, d, dst_c_off, sy, sx, lg);
   else
-    upsample2x_kernel<__half><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, sy, sx, total);
+    upsample2x_kernel<__half><<<grid, 256, 0, st>>>(s, d, dst_c_off, sy, sx, lg);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

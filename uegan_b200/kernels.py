@@ -123,6 +123,57 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
     _count(1, f"fprop ->{cout} k{k}s{stride}{' +stats' if in_stats is not None else ''}", x)
 
 
+def rowsum_supported(cout: int, cin_stored: int, k: int, dtype: int) -> bool:
+    return bool(L.load().uegan_conv2d_rowsum_supported(cout, cin_stored, k, dtype))
+
+
+def packed_weight_rowsum(weight: torch.Tensor, cin_stored: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Operand of the row-sum kernel (csrc/conv_rowsum.cu): rows (s, o), columns (r, c), tf32."""
+    lib = L.load()
+    w = weight.detach()
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+    o, i_total, k, _ = w.shape
+    nbytes = lib.uegan_packed_weight_rowsum_bytes(o, cin_stored, k)
+    buf = out if out is not None else torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
+    assert buf.numel() >= nbytes
+    L.check(lib.uegan_pack_conv_weight_rowsum(w.data_ptr(), buf.data_ptr(), o, i_total, 0, i_total, cin_stored, k,
+                                              _stream()), "pack_conv_weight_rowsum")
+    _count(1, "pack_weight_rowsum")
+    return buf
+
+
+def conv_planar(x: NHWC, weight: torch.Tensor, cache, key, k: int, pad: int, bias, alpha, act: int,
+                out_nchw: torch.Tensor, residual_nchw: Optional[torch.Tensor] = None,
+                aux_nchw: Optional[torch.Tensor] = None):
+    """Stride-1 conv with a tiny output-channel count written as fp32 NCHW planes (G's last conv, D's heads): the
+    row-sum kernel when the shape qualifies, else the generic implicit GEMM."""
+    cout = weight.shape[0]
+    if rowsum_supported(cout, x.c, k, x.dtype):
+        wp = cache.get((key, "rowsum"), weight, lambda out=None: packed_weight_rowsum(weight, x.c, out=out))
+        d = L.ConvDesc()
+        d.x = x.ct
+        d.cout, d.k, d.stride, d.pad, d.act = cout, k, 1, pad, act
+        d.w_packed = wp.data_ptr()
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.alpha = alpha.data_ptr() if alpha is not None else None
+        d.out_nchw = out_nchw.data_ptr()
+        d.residual_nchw = residual_nchw.data_ptr() if residual_nchw is not None else None
+        d.aux_nchw = aux_nchw.data_ptr() if aux_nchw is not None else None
+        ev = _Counters.conv_events
+        if ev is not None:
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+        L.check(L.load().uegan_conv2d_fprop_rowsum(C.byref(d), _stream()), "conv2d_fprop_rowsum")
+        if ev is not None:
+            s1.record()
+            ho, wo = x.h + 2 * pad - k + 1, x.w + 2 * pad - k + 1
+            ev.append((s0, s1, 2.0 * x.n * ho * wo * cout * k * k * x.c, x, cout, k, 1, "fprop", x.dtype))
+        _count(1, f"fprop_rowsum ->{cout} k{k}", x)
+        return
+    wp = cache.get(key, weight, lambda out=None: packed_weight(weight, x.c, x.dtype, out=out))
+    conv_fprop(x, wp, cout, k, 1, pad, None, 0, bias, alpha, act, None, out_nchw, residual_nchw, aux_nchw=aux_nchw)
+
+
 def pack_input(x_nchw: torch.Tensor, dst: NHWC, pad_mode: int = L.PAD_REFLECT, scale=None, shift=None):
     assert x_nchw.is_cuda and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and x_nchw.shape[1] == 3
     assert tuple(x_nchw.shape) == (dst.n, 3, dst.h, dst.w)

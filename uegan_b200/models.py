@@ -226,7 +226,7 @@ class Generator(nn.Module):
         conv(P["y4m"], "dec5.0", self.dec5[0], d, 3, 1, P["t"]); K.halo_fill(P["t"])
         out = torch.empty_like(x)
         cv = c(self.dec5[1])
-        K.conv_fprop(P["t"], self._w("dec5.1", cv, d), 3, 7, 1, 3, None, 0, cv.bias, None, L.ACT_TANH, None, out, x)
+        K.conv_planar(P["t"], cv.weight, self._wcache, "dec5.1", 7, 3, cv.bias, None, L.ACT_TANH, out, x)
         if keep is not None:
             keep.update(P)
         return out
@@ -324,8 +324,7 @@ class Discriminator(nn.Module):
             K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, self._act)
             K.halo_fill(dst)
             pred = torch.empty(b, 1, dst.h, dst.w, dtype=torch.float32, device=x.device)
-            hp = self._wcache.get(f"p{i}", head.weight, lambda out=None: K.packed_weight(head.weight, dst.c, L.F32, out=out))
-            K.conv_fprop(dst, hp, 1, k, 1, pad, None, 0, None, None, self._head_act, None, pred)
+            K.conv_planar(dst, head.weight, self._wcache, f"p{i}", k, pad, None, None, self._head_act, pred)
             preds.append(pred)
             src = dst
         if keep is not None:
