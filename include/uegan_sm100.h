@@ -183,6 +183,13 @@ int uegan_instance_norm_stats(const uegan_tensor* src, float eps, double* stats_
 int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz, int32_t cout, int32_t cin, int32_t cin_total,
                        int32_t cin_first, int32_t k, int32_t stride, int32_t pad, float* dw_oihw,
                        const float* alpha_dev, float scale, void* stream);
+/* The same weight gradient for a stride-1 conv with a tiny output-channel count (G's last conv, D's prediction heads) from
+ * the stacked gradient e = uegan_dz_hstack(dz):  dW[o][c][r][s] += scale * alpha * sum_{y,q} xpad[y + r][q][c] * e[y][q][(s,o)]
+ * -- the wgrad of a k x 1 convolution with k*cout output channels: one accumulator per (32-channel chunk, 4 filter rows)
+ * instead of one per (chunk, row, 4 columns).  pad must be (k-1)/2 <= x.halo; k*cout <= 32. */
+int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tensor* e, int32_t cout, int32_t cin, int32_t cin_total,
+                              int32_t cin_first, int32_t k, int32_t pad, float* dw_oihw, const float* alpha_dev,
+                              float scale, void* stream);
 /* Gradient of the planar heads into a zero-haloed NHWC tensor: mode 0 tanh (models.py:178), 1 sigmoid, 2
  * clamp(tanh(z) + x, -1, 1) with out_nchw = tanh(z) (models.py:35,72). */
 int uegan_head_bwd(const float* dout_nchw, const float* out_nchw, const float* x_nchw, int32_t channels, int32_t mode,
@@ -194,6 +201,15 @@ int uegan_grad_combine(const uegan_tensor* dst, int32_t dst_c_off, int32_t chann
                        int32_t a_c_off, int32_t pad_a, int32_t pad_mode_a, const uegan_tensor* add_b, int32_t b_c_off,
                        const uegan_tensor* add_c, int32_t c_c_off, const uegan_tensor* mask, int32_t mask_c_off,
                        int32_t act, const uegan_tensor* mul, int32_t mul_c_off, void* stream);
+/* Adjoint of nn.ReflectionPad2d IN PLACE: t (halo = pad) holds the gradient w.r.t. the reflect-padded input of a conv
+ * (what the dgrad launches of uegan_conv2d_fprop write, extent (h + 2 pad) x (w + 2 pad)); interior pixels within `pad`
+ * of an edge receive their reflected halo copies, then the halo is zeroed.  Same result as uegan_grad_combine with src_a
+ * only, but touches O(perimeter) data; the tensor is afterwards a zero-haloed dgrad / wgrad operand. */
+int uegan_fold_inplace(const uegan_tensor* t, void* stream);
+/* Horizontally unrolled gradient of a tiny-Cout stride-1 conv (cout 1 or 3, k <= 7): dz = 4-channel fp32 NHWC with a zero
+ * halo >= k - 1 (uegan_head_bwd); e = 32-channel fp32 NHWC, halo 0, extent h x (w + k - 1):
+ * e[n, y, q, s*cout + o] = dz[n, y, q - s, o].  Operand of uegan_conv2d_wgrad_hstack. */
+int uegan_dz_hstack(const uegan_tensor* dz, int32_t cout, int32_t k, const uegan_tensor* e, void* stream);
 /* out[c] = sum over n, h, w of src[.., c_off + c]  (bias gradient). */
 int uegan_channel_sum(const uegan_tensor* src, int32_t c_off, int32_t channels, float* out, void* stream);
 /* InstanceNorm backward: dz = rstd * (dout - mean(dout) - xhat * mean(dout * xhat)); ws: 2*n*c doubles. */

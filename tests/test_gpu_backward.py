@@ -167,3 +167,66 @@ def test_elementwise_backward(K):
     assert relerr(dzt.interior_nchw()[:, :3], ref) < 1e-3
     assert float(dzt.padded_view()[:, :6].abs().max()) == 0.0 and float(dzt.interior_nchw()[:, 3].abs().max()) == 0.0
     assert K.device_error() == 0
+
+
+HSTACK_CASES = [
+    # n, cin, h, w, cout, k
+    (2, 32, 24, 40, 3, 7),    # G's last conv
+    (1, 32, 19, 29, 1, 7),    # ragged extents
+    (2, 64, 16, 24, 1, 7),    # two channel chunks
+    (1, 128, 16, 16, 1, 7),   # chunks split over two slices
+    (2, 256, 12, 16, 1, 5),   # k5 head
+    (1, 512, 8, 8, 1, 5),     # deepest head: 16 chunks, 6 slices
+]
+
+
+@pytest.mark.parametrize("case", HSTACK_CASES)
+def test_wgrad_hstack(K, case):
+    """Tiny-Cout weight gradient through the horizontally unrolled gradient (uegan_dz_hstack + vertical patch wgrad)."""
+    from uegan_b200 import _lib as L
+    n, cin, h, w, cout, k = case
+    g = torch.Generator(device="cuda").manual_seed(123 + cin)
+    pad = (k - 1) // 2
+    x = tf32(torch.randn(n, cin, h, w, device="cuda", generator=g))
+    wr = torch.zeros(cout, cin, k, k, device="cuda", dtype=torch.double, requires_grad=True)
+    dzv = tf32(torch.randn(n, cout, h, w, device="cuda", generator=g))
+    F.conv2d(F.pad(x.double(), (pad,) * 4, mode="reflect"), wr).backward(dzv.double())
+    xt = fill_nhwc(K, x, cin, pad + 1, L.PAD_REFLECT, L.F32)  # halo > pad exercises the patch offset
+    dz4 = fill_nhwc(K, dzv, 4, k - 1, L.PAD_ZERO, L.F32)
+    e = K.NHWC(n, h, w + k - 1, 32, 0, L.F32, "cuda")
+    e.buf.fill_(9.0)
+    K.dz_hstack(dz4, cout, k, e)
+    ev = e.interior_nchw()
+    for s in range(k):
+        for o in range(cout):
+            assert torch.equal(ev[:, s * cout + o, :, s:s + w], dzv[:, o])
+    assert float(ev[:, k * cout:].abs().max()) == 0.0
+    dw = torch.zeros(cout, cin, k, k, device="cuda")
+    alpha = torch.tensor([0.5], device="cuda")
+    K.conv_wgrad_hstack(xt, e, dw, k, pad, alpha=alpha, scale=2.0)
+    assert K.device_error() == 0
+    err = relerr(dw, wr.grad)
+    print(f"hstack wgrad {case}: rel err {err:.3e}")
+    assert err < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 24, 40, 3), (2, 64, 12, 20, 1), (1, 32, 8, 7, 3), (2, 128, 9, 33, 2)])
+def test_fold_inplace(K, shape):
+    """In-place reflect-pad adjoint == grad_combine(src_a) == autograd of F.pad(reflect); halo zeroed."""
+    from uegan_b200 import _lib as L
+    n, c, h, w, pad = shape
+    g = torch.Generator(device="cuda").manual_seed(31)
+    a = tf32(torch.randn(n, c, h + 2 * pad, w + 2 * pad, device="cuda", generator=g))
+    ta = fill_nhwc(K, a, c, 0, L.PAD_ZERO, L.F32)
+    ref_t = K.NHWC(n, h, w, c, 0, L.F32, "cuda")
+    K.grad_combine(ref_t, c, src_a=ta, pad_a=pad)
+    v = K.fold_inplace(ta, pad)
+    assert K.device_error() == 0
+    assert (v.n, v.h, v.w, v.halo) == (n, h, w, pad)
+    xin = torch.zeros(n, c, h, w, device="cuda", dtype=torch.double, requires_grad=True)
+    F.pad(xin, (pad,) * 4, mode="reflect").backward(a.double())
+    assert relerr(v.interior_nchw(), xin.grad) < 1e-3
+    assert torch.equal(v.interior_nchw(), ref_t.interior_nchw())  # same summation order, same tf32 rounding
+    pv = v.padded_view()
+    assert float(pv[:, :pad].abs().max()) == 0.0 and float(pv[:, -pad:].abs().max()) == 0.0
+    assert float(pv[:, :, :pad].abs().max()) == 0.0 and float(pv[:, :, -pad:].abs().max()) == 0.0

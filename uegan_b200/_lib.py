@@ -75,6 +75,10 @@ SYMBOLS = {
     "uegan_pack_conv_weight_dgrad": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 10 + [C.c_void_p]),
     "uegan_conv2d_wgrad": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor)] + [C.c_int32] * 7 +
                            [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "uegan_conv2d_wgrad_hstack": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor)] + [C.c_int32] * 6 +
+                                  [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "uegan_fold_inplace": (C.c_int, [C.POINTER(Tensor), C.c_void_p]),
+    "uegan_dz_hstack": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.POINTER(Tensor), C.c_void_p]),
     "uegan_head_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Tensor),
                                  C.c_void_p]),
     "uegan_grad_combine": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.POINTER(Tensor), C.c_int32, C.c_int32,

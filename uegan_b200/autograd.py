@@ -38,6 +38,7 @@ class _Scratch:
 
 
 _scratch = _Scratch()
+_FOLD_INPLACE = __import__("os").environ.get("UEGAN_NO_FOLD_INPLACE") != "1"
 
 
 def _zeros_like(p):
@@ -145,17 +146,28 @@ def _g_backward(G, x, out_grad, ws, need_dx):
 
     # ---- dec5.1 + tanh + clamp(res + x)   (models.py:34-35, 72)
     dz5 = S("dz5", h, w, 4, 6)
-    dz5w = S("dz5w", h, w, 32, 0)
     K.head_bwd(out_grad, P["res"], x, 2, dz5)
-    K.head_bwd(out_grad, P["res"], x, 2, dz5w)
     c51 = G.dec5[1].conv
-    wgrad("dec5.1.main.1", c51, P["t"], dz5w, 7, 1, 3)
+    if K.hstack_ok(3, d, 7):
+        # horizontal taps unrolled into the gradient's channels: the wgrad keeps only the 7 vertical taps
+        e5 = S("dz5e", h, w + 6, 32, 0)
+        K.dz_hstack(dz5, 3, 7, e5)
+        gw = _zeros_like(c51.weight)
+        K.conv_wgrad_hstack(P["t"], e5, gw, 7, 3)
+        grads["dec5.1.main.1.weight"] = gw
+    else:
+        dz5w = S("dz5w", h, w, 32, 0)
+        K.head_bwd(out_grad, P["res"], x, 2, dz5w)
+        wgrad("dec5.1.main.1", c51, P["t"], dz5w, 7, 1, 3)
     gb = torch.empty(4, dtype=torch.float32, device=dev); K.channel_sum(dz5, gb, 0, 4)
     grads["dec5.1.main.1.bias"] = gb[:3]
     dxp = S("dxp_t", h + 6, w + 6, d)
     K.conv_dgrad(dz5, c51.weight, 7, 1, dxp, cache, "dec5.1")
-    dt = S("dt", h, w, d, 2)
-    K.grad_combine(dt, d, src_a=dxp, pad_a=3)
+    if _FOLD_INPLACE:
+        dt = K.fold_inplace(dxp, 3)  # the padded gradient itself becomes dt (interior + zero halo 3)
+    else:
+        dt = S("dt", h, w, d, 2)
+        K.grad_combine(dt, d, src_a=dxp, pad_a=3)
     # ---- dec5.0 (no activation)
     c50 = G.dec5[0].conv
     wgrad("dec5.0.main.1", c50, P["y4m"], dt, 3, 1, 1, bias_from=dt)
@@ -178,8 +190,11 @@ def _g_backward(G, x, out_grad, ws, need_dx):
         wgrad(f"dec{i+1}.main.1", dec, P["cat"][i], dz, 3, 1, 1, bias_from=dz)
         dxpc = S(f"dxp_cat{i}", hh + 2, ww + 2, 2 * ch)
         K.conv_dgrad(dz, dec.weight, 3, 1, dxpc, cache, f"dec{i+1}")
-        dcat = S(f"dcat{i}", hh, ww, 2 * ch)
-        K.grad_combine(dcat, 2 * ch, src_a=dxpc, pad_a=1)
+        if _FOLD_INPLACE:
+            dcat = K.fold_inplace(dxpc, 1)
+        else:
+            dcat = S(f"dcat{i}", hh, ww, 2 * ch)
+            K.grad_combine(dcat, 2 * ch, src_a=dxpc, pad_a=1)
         # first half: bilinear x2 of the (hoisted) 1x1 conv
         du = S(f"du{i}", hh // 2, ww // 2, ch)
         K.upsample2x_bwd(dcat, 0, du)
@@ -334,24 +349,31 @@ def _d_backward(D, x, dpreds, ws, need_dx, need_w=True):
         ds = ws["ds"][i - 1]
         conv, head, wgt = D._conv(i), D._head(i), D._weight(i)
         dzp = S(f"dzp{i}", ds.h, ds.w, 4, k - 1)
-        dzpw = S(f"dzpw{i}", ds.h, ds.w, 32, 0)
         dp = dpreds[i - 1]
         if dp is None:
             dp = torch.zeros_like(ws["preds"][i - 1])
         dp = dp.contiguous().float()
         K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzp)
         if need_w:
-            K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzpw)
-        if need_w:
             gw = _zeros_like(head.weight)
-            K.conv_wgrad(ds, dzpw, gw, k, 1, pad)
+            if K.hstack_ok(1, ds.c, k):
+                ep = S(f"dzpe{i}", ds.h, ds.w + k - 1, 32, 0)
+                K.dz_hstack(dzp, 1, k, ep)
+                K.conv_wgrad_hstack(ds, ep, gw, k, pad)
+            else:
+                dzpw = S(f"dzpw{i}", ds.h, ds.w, 32, 0)
+                K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzpw)
+                K.conv_wgrad(ds, dzpw, gw, k, 1, pad)
             grads[f"d{i}_pred.0.1.weight"] = gw
         dxa = S(f"dxa{i}", ds.h + 2 * pad, ds.w + 2 * pad, ds.c)
         K.conv_dgrad(dzp, head.weight, k, 1, dxa, cache, f"p{i}")
         dz = S(f"dz{i}", ds.h, ds.w, ds.c, kq - 1)
         if carry is not None:
-            tmp = S(f"tmp{i}", ds.h, ds.w, ds.c)
-            K.grad_combine(tmp, ds.c, src_a=carry[0], pad_a=carry[1])
+            if _FOLD_INPLACE:
+                tmp = K.fold_inplace(carry[0], carry[1])
+            else:
+                tmp = S(f"tmp{i}", ds.h, ds.w, ds.c)
+                K.grad_combine(tmp, ds.c, src_a=carry[0], pad_a=carry[1])
             K.grad_combine(dz, ds.c, src_a=dxa, pad_a=pad, add_b=tmp, mask=ds, act=D._act)
         else:
             K.grad_combine(dz, ds.c, src_a=dxa, pad_a=pad, mask=ds, act=D._act)

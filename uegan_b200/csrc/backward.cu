@@ -131,6 +131,80 @@ __global__ void grad_combine_kernel(CombineArgs q, int cv_log2) {
 }
 
 // ------------------------------------------------------------------------------------------
+// fold_inplace: t (halo = pad) holds the gradient w.r.t. the reflect-PADDED input of a conv (what a dgrad launch writes:
+// extent (h + 2 pad) x (w + 2 pad)).  Adjoint of nn.ReflectionPad2d in place: every interior pixel within `pad` of an
+// edge adds the halo pixels that were reflected copies of it; the halo is zeroed afterwards (uegan_halo_fill), so the
+// tensor is at once the folded gradient and a zero-haloed dgrad / wgrad operand.  Sources are halo pixels only, targets
+// interior pixels only: race-free.  Touches O(perimeter) data instead of a full read + write pass (grad_combine).
+// grid = (1, h, n); a row inside the top / bottom band processes every column, any other row only its 2*pad edge columns.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void fold_inplace_kernel(TGeom t, int cv_log2) {
+  constexpr int VN = Vec<T>::N;
+  const int y = blockIdx.y, n = blockIdx.z, pa = t.halo;
+  const int cv = 1 << cv_log2;
+  int ys[2], ny = 0;
+  if (y >= 1 && y <= pa) ys[ny++] = -y;                                  // interior row coordinate of the reflected source
+  if (y <= t.h - 2 && y >= t.h - 1 - pa) ys[ny++] = 2 * (t.h - 1) - y;
+  const bool band = ny > 0 || t.w <= 2 * pa + 1;  // (narrow images: the two edge column sets would overlap)
+  const int ncols = band ? t.w : 2 * pa;
+  T* base = static_cast<T*>(t.data);
+  for (int i = threadIdx.x; i < ncols * cv; i += blockDim.x) {
+    const int xi = i >> cv_log2, c = (i & (cv - 1)) * VN;
+    // edge columns that receive reflected copies: 1 .. pa and w-1-pa .. w-2
+    const int x = band ? xi : (xi < pa ? xi + 1 : t.w - 1 - 2 * pa + xi);
+    int xs[2], nx = 0;
+    if (x >= 1 && x <= pa) xs[nx++] = -x;
+    if (x <= t.w - 2 && x >= t.w - 1 - pa) xs[nx++] = 2 * (t.w - 1) - x;
+    if (ny == 0 && nx == 0) continue;
+    float v[VN];
+    T* dst = base + toff(t, n, y, x, c);
+    Vec<T>::load(dst, v);
+    // same summation order as grad_combine: (y, x) first, then rows ascending, columns ascending
+    for (int iy = -1; iy < ny; ++iy)
+      for (int ix = -1; ix < nx; ++ix) {
+        if (iy < 0 && ix < 0) continue;
+        float s[VN];
+        Vec<T>::load(base + toff(t, n, iy < 0 ? y : ys[iy], ix < 0 ? x : xs[ix], c), s);
+#pragma unroll
+        for (int k = 0; k < VN; ++k) v[k] += s[k];
+      }
+    Vec<T>::store(dst, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// dz_hstack: E[n, y, q, s*cout + o] = dz[n, y, q - s, o] for s < k, q in [0, w + k - 1)   (zero where q - s leaves the
+// image: dz carries a zero halo >= k - 1).  The horizontally unrolled output gradient of a tiny-Cout conv: with it the
+// weight gradient dW[o][c][r][s] = sum_{y,q} xpad[y + r][q][c] * E[y][q][(s, o)] is the wgrad of a k x 1 convolution with
+// k*cout output channels -- k times fewer MMAs than one accumulator per (r, s) tap (conv_wgrad.cu, vertical patch mode).
+// ------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void dz_hstack_kernel(TGeom dz, TGeom e, int k, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int q = (int)(i % e.w);
+  const int y = (int)((i / e.w) % e.h);
+  const int n = (int)(i / ((long long)e.w * e.h));
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  const float* db = static_cast<const float*>(dz.data);
+#pragma unroll
+  for (int s = 0; s < 7; ++s) {
+    if (s < k) {
+      const float4 d = *reinterpret_cast<const float4*>(db + toff(dz, n, y, q - s, 0));
+      v[s * COUT] = d.x;
+      if (COUT > 1) v[s * COUT + 1] = d.y;
+      if (COUT > 2) v[s * COUT + 2] = d.z;
+    }
+  }
+  float* ep = static_cast<float*>(e.data) + toff(e, n, y, q, 0);
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(ep + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+
+// ------------------------------------------------------------------------------------------
 // per-channel sum over n, h, w (bias gradient): out[c] += sum
 // ------------------------------------------------------------------------------------------
 template <typename T>
@@ -138,6 +212,7 @@ struct ChannelSumOp {
   TGeom s;
   int c_off;
   float* out;
+  __device__ void prep(int, int) {}
   __device__ void acc(int n, int y, int x, int c, float (&a)[Vec<T>::N][1]) const {
     float v[Vec<T>::N];
     Vec<T>::load(static_cast<const T*>(s.data) + toff(s, n, y, x, c_off + c), v);
@@ -157,14 +232,21 @@ struct InBwdStatsOp {
   TGeom z;
   const float* mr;
   double* sums;
+  float mean[Vec<T>::N], rstd[Vec<T>::N];
+  __device__ void prep(int n, int c) {
+#pragma unroll
+    for (int k = 0; k < Vec<T>::N; ++k) {
+      const long long si = ((long long)n * z.c + c + k) * 2;
+      mean[k] = mr[si]; rstd[k] = mr[si + 1];
+    }
+  }
   __device__ void acc(int n, int y, int x, int c, float (&a)[Vec<T>::N][2]) const {
     float gv[Vec<T>::N], zv[Vec<T>::N];
     Vec<T>::load(static_cast<const T*>(g.data) + toff(g, n, y, x, d_c_off + c), gv);
     Vec<T>::load(static_cast<const T*>(z.data) + toff(z, n, y, x, c), zv);
 #pragma unroll
     for (int k = 0; k < Vec<T>::N; ++k) {
-      const long long si = ((long long)n * z.c + c + k) * 2;
-      const float xh = (zv[k] - mr[si]) * mr[si + 1];
+      const float xh = (zv[k] - mean[k]) * rstd[k];
       a[k][0] += gv[k];
       a[k][1] += gv[k] * xh;
     }
@@ -394,15 +476,22 @@ struct TapBwdStatsOp {
   const float* mrx;
   const float* mry;
   double* sums;
+  float mx[Vec<T>::N], rx[Vec<T>::N], my[Vec<T>::N], ry[Vec<T>::N];
+  __device__ void prep(int n, int c) {
+#pragma unroll
+    for (int k = 0; k < Vec<T>::N; ++k) {
+      const long long si = ((long long)n * x.c + c + k) * 2;
+      mx[k] = mrx[si]; rx[k] = mrx[si + 1]; my[k] = mry[si]; ry[k] = mry[si + 1];
+    }
+  }
   __device__ void acc(int n, int yy, int xx, int c, float (&a)[Vec<T>::N][2]) const {
     float xv[Vec<T>::N], yv[Vec<T>::N];
     Vec<T>::load(static_cast<const T*>(x.data) + toff(x, n, yy, xx, c), xv);
     Vec<T>::load(static_cast<const T*>(y.data) + toff(y, n, yy, xx, c), yv);
 #pragma unroll
     for (int k = 0; k < Vec<T>::N; ++k) {
-      const long long si = ((long long)n * x.c + c + k) * 2;
-      const float xh = (xv[k] - mrx[si]) * mrx[si + 1];
-      const float e = xh - (yv[k] - mry[si]) * mry[si + 1];
+      const float xh = (xv[k] - mx[k]) * rx[k];
+      const float e = xh - (yv[k] - my[k]) * ry[k];
       a[k][0] += e;
       a[k][1] += e * xh;
     }
@@ -491,6 +580,41 @@ int uegan_grad_combine(const uegan_tensor* dst, int32_t dst_c_off, int32_t chann
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(nblk((long long)q.dst.wp * cv, 256), (unsigned)q.dst.hp, (unsigned)q.dst.n);
   UEGAN_DISPATCH(dst->dtype, grad_combine_kernel, <<<grid, 256, 0, st>>>(q, cv_log2));
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_fold_inplace(const uegan_tensor* t, void* stream) {
+  UEGAN_CHECK(t && t->data, "fold_inplace: null pointer");
+  UEGAN_CHECK(dtype_ok(t->dtype) && (t->c * dtype_size(t->dtype)) % 16 == 0, "fold_inplace: bad tensor");
+  if (t->halo == 0) return 0;
+  UEGAN_CHECK(t->halo < t->h && t->halo < t->w, "fold_inplace: halo %d needs h, w > halo (got %dx%d)", t->halo, t->h, t->w);
+  const TGeom g = geom(*t);
+  const int vn = 16 / dtype_size(t->dtype);
+  const int cv = t->c / vn;
+  int lg = 0;
+  while ((1 << lg) < cv) ++lg;
+  UEGAN_CHECK((1 << lg) == cv, "fold_inplace: channels / vector width must be a power of two (got %d)", cv);
+  UEGAN_CHECK(g.h <= 65535 && g.n <= 65535, "fold_inplace: tensor too large for the launch grid");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid(1u, (unsigned)g.h, (unsigned)g.n);
+  UEGAN_DISPATCH(t->dtype, fold_inplace_kernel, <<<grid, 256, 0, st>>>(g, lg));
+  UEGAN_CUDA(cudaGetLastError());
+  return uegan_halo_fill(t, UEGAN_PAD_ZERO, stream);
+}
+
+int uegan_dz_hstack(const uegan_tensor* dz, int32_t cout, int32_t k, const uegan_tensor* e, void* stream) {
+  UEGAN_CHECK(dz && e && dz->data && e->data, "dz_hstack: null pointer");
+  UEGAN_CHECK(dz->dtype == UEGAN_F32 && e->dtype == UEGAN_F32 && dz->c == 4 && e->c == 32 && e->halo == 0,
+              "dz_hstack: expects a 4-channel fp32 dz and a 32-channel fp32 stack without halo");
+  UEGAN_CHECK((cout == 1 || cout == 3) && k >= 1 && k <= 7 && k * cout <= 21, "dz_hstack: unsupported cout %d / k %d", cout, k);
+  UEGAN_CHECK(dz->halo >= k - 1 && e->n == dz->n && e->h == dz->h && e->w == dz->w + k - 1,
+              "dz_hstack: dz needs a zero halo >= k - 1 and the stack must be %d x %d (got %d x %d)", dz->h, dz->w + k - 1,
+              e->h, e->w);
+  const TGeom d = geom(*dz), g = geom(*e);
+  const long long total = (long long)g.n * g.h * g.w;
+  if (cout == 1) dz_hstack_kernel<1><<<nblk(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, g, k, total);
+  else dz_hstack_kernel<3><<<nblk(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, g, k, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -330,6 +330,11 @@ struct WgradPatchParams {
   int acc_total, acc_per_cta;  // (r, g, chunk) triples in total / per blockIdx.y slice
   int off;                     // halo - pad of x
   int cout, cin, cin_total, cin_first;
+  // vertical ("h-stack") mode: dz is the horizontally unrolled gradient E[..][(s, o)] (uegan_dz_hstack) of a tiny-Cout
+  // conv, so only the k VERTICAL taps remain: M-group j of tap group g = filter row 4g + j (LBO = one patch ROW), one
+  // accumulator per (chunk, g), D[(r, c)][(s, o)] -> dW[o][c][r][s].  rk = taps enumerated by the accumulator index
+  // besides the groups: k (horizontal mode: filter rows) or 1.
+  int vert, rk, lbo_bytes;
   float* dw;
   const float* alpha;
   float scale;
@@ -351,7 +356,7 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const int acc0 = blockIdx.y * p.acc_per_cta, acc1 = min(acc0 + p.acc_per_cta, p.acc_total);
   const int N = p.n_boxes * 32;
   // accumulator index a -> (chunk, r, g):  a = (chunk * k + r) * kgroups + g.  The chunks this CTA touches:
-  const int ch_lo = acc0 / (p.k * p.kgroups), ch_hi = (acc1 - 1) / (p.k * p.kgroups);
+  const int ch_lo = acc0 / (p.rk * p.kgroups), ch_hi = (acc1 - 1) / (p.rk * p.kgroups);
   const int nch = ch_hi - ch_lo + 1;
 
   if (warp == 0 && elect_one()) {
@@ -405,20 +410,22 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           const uint32_t sp = smem_u32(smem + stage * p.stage_bytes);
           const uint32_t sz = sp + nch * p.patch_bytes;
           // A: M-group stride (LBO) = one pixel row: the 4 taps of a group are the same rows shifted by 0..3 pixels
-          const uint64_t da0 = make_smem_desc(sp, 128, 512, UMMA_LAYOUT_SW128_B32);
+          const uint64_t da0 = make_smem_desc(sp, (uint32_t)p.lbo_bytes, 512, UMMA_LAYOUT_SW128_B32);
           const uint64_t db0 = make_smem_desc(sz, 64 * 128, 512, UMMA_LAYOUT_SW128_B32);
           const uint32_t row_step = p.pw * 8;  // one patch row, in descriptor units of 16 bytes
-          int g = acc0 % p.kgroups, r = (acc0 / p.kgroups) % p.k, c = acc0 / (p.kgroups * p.k) - ch_lo;
+          int g = acc0 % p.kgroups, r = (acc0 / p.kgroups) % p.rk, c = acc0 / (p.kgroups * p.rk) - ch_lo;
           uint32_t d_tmem = tmem_base;
           for (int a = acc0; a < acc1; ++a) {
-            uint64_t da = da0 + (uint32_t)(c * (p.patch_bytes >> 4) + (r * p.pw + 4 * g) * 8);
+            // first tap of the group: (row r, column 4g) of the patch, or (row 4g, column 0) in vertical mode
+            const uint32_t tap0 = p.vert ? (uint32_t)(4 * g * p.pw) : (uint32_t)(r * p.pw + 4 * g);
+            uint64_t da = da0 + (uint32_t)(c * (p.patch_bytes >> 4)) + tap0 * 8;
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
               umma_ss<1>(d_tmem, da, db0 + ks * 64, idesc, (first | ks) != 0 ? 1u : 0u);
               da += row_step;
             }
             d_tmem += N;
-            if (++g == p.kgroups) { g = 0; if (++r == p.k) { r = 0; ++c; } }
+            if (++g == p.kgroups) { g = 0; if (++r == p.rk) { r = 0; ++c; } }
           }
           first = 1;
           umma_commit(&empty_bar[stage]);
@@ -434,13 +441,25 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       const float sc = p.scale * (p.alpha ? __ldg(p.alpha) : 1.f);
       const int kk = p.k * p.k;
       for (int a = acc0; a < acc1; ++a) {
-        const int g = a % p.kgroups, r = (a / p.kgroups) % p.k, chunk = a / (p.kgroups * p.k);
-        const int s_ = 4 * g + (m >> 5), c = chunk * 32 + (m & 31);
+        const int g = a % p.kgroups, r = (a / p.kgroups) % p.rk, chunk = a / (p.kgroups * p.rk);
+        const int s_ = 4 * g + (m >> 5), c = chunk * 32 + (m & 31);  // vertical mode: s_ is the filter ROW
         for (int c0 = 0; c0 < N; c0 += 16) {
           uint32_t rr[16];
           tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (a - acc0) * N + c0, rr);
           tmem_ld_wait();
           if (s_ >= p.k || c >= p.cin) continue;
+          if (p.vert) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int j = c0 + i;  // column (s, o) of the stacked gradient
+              if (j < p.k * p.cout) {
+                const int ss = j / p.cout, o = j - ss * p.cout;
+                atomicAdd(p.dw + ((long long)o * p.cin_total + p.cin_first + c) * kk + s_ * p.k + ss,
+                          __uint_as_float(rr[i]) * sc);
+              }
+            }
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int o = c0 + i;
@@ -477,6 +496,7 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
   p.ph = 8 + k - 1;
   p.patch_bytes = (p.ph * p.pw * 128 + 1023) / 1024 * 1024;
   p.dz_bytes = p.n_boxes * 64 * 128;
+  p.vert = 0; p.rk = k; p.lbo_bytes = 128;
   p.acc_total = p.chunks * k * p.kgroups;
   p.acc_per_cta = 512 / N;
   // a CTA's accumulators should span as few channel chunks as possible: align the slice to whole chunks when it can
@@ -535,3 +555,82 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
 }
 
 }  // namespace uegan
+
+// Weight gradient of a stride-1 conv with a tiny output-channel count from the horizontally unrolled gradient
+// E = uegan_dz_hstack(dz) (32 stored channels = (s, o) pairs): the patch kernel in vertical mode.
+extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tensor* e, int32_t cout, int32_t cin,
+                                         int32_t cin_total, int32_t cin_first, int32_t k, int32_t pad, float* dw_oihw,
+                                         const float* alpha_dev, float scale, void* stream) {
+  UEGAN_CHECK(x && e && x->data && e->data && dw_oihw, "conv2d_wgrad_hstack: null pointer");
+  UEGAN_CHECK(x->dtype == UEGAN_F32 && e->dtype == UEGAN_F32 && x->c % 32 == 0 && e->c == 32 && e->halo == 0,
+              "conv2d_wgrad_hstack: fp32 tensors, x.c %% 32 == 0, 32-channel stack without halo");
+  UEGAN_CHECK(k >= 1 && k <= 7 && (k & 1) && pad == (k - 1) / 2 && pad <= x->halo && k * cout <= 32,
+              "conv2d_wgrad_hstack: unsupported k %d / pad %d / cout %d", k, pad, cout);
+  UEGAN_CHECK(e->n == x->n && e->h == x->h && e->w == x->w + k - 1, "conv2d_wgrad_hstack: stack is %dx%dx%d, expected %dx%dx%d",
+              e->n, e->h, e->w, x->n, x->h, x->w + k - 1);
+  UEGAN_CHECK(cin <= x->c && cin_first + cin <= cin_total, "conv2d_wgrad_hstack: channel mismatch");
+  WgradPatchParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_boxes = 1;
+  p.k = k;
+  p.kgroups = (k + 3) / 4;
+  p.chunks = (cin + 31) / 32;
+  p.vert = 1; p.rk = 1;
+  p.pw = 8;
+  p.ph = 8 + 4 * p.kgroups - 1;       // rows 0 .. 7 + (4*kgroups - 1): M-group j of the last group stays inside
+  p.lbo_bytes = p.pw * 128;           // M-group stride = one patch row
+  p.patch_bytes = p.ph * p.pw * 128;  // a multiple of 1024
+  p.dz_bytes = 64 * 128;
+  p.acc_total = p.chunks * p.kgroups;
+  // channel chunks per CTA: at least 3 stages of (chunks * patch + stack tile) in 200 KB, at most 512 / 32 accumulators
+  int nch_max = ((200 * 1024) / 3 - p.dz_bytes) / p.patch_bytes;
+  if (nch_max > 16 / p.kgroups) nch_max = 16 / p.kgroups;
+  if (nch_max < 1) nch_max = 1;
+  const int slices = (p.chunks + nch_max - 1) / nch_max;
+  const int nch = (p.chunks + slices - 1) / slices;
+  p.acc_per_cta = nch * p.kgroups;
+  p.stage_bytes = nch * p.patch_bytes + p.dz_bytes;
+  p.num_stages = (200 * 1024) / p.stage_bytes;
+  if (p.num_stages > 4) p.num_stages = 4;
+  UEGAN_CHECK(p.num_stages >= 2, "conv2d_wgrad_hstack: stage too large");
+  p.tiles_w = (e->w + 7) / 8;
+  p.tiles_h = (e->h + 7) / 8;
+  p.nimg = x->n;
+  p.total_ktiles = p.tiles_w * p.tiles_h * p.nimg;
+  int ksplit = (2 * num_sms() + slices - 1) / slices;
+  if (ksplit > p.total_ktiles) ksplit = p.total_ktiles;
+  p.ksplit = ksplit < 1 ? 1 : ksplit;
+  p.off = x->halo - pad;
+  p.cout = cout; p.cin = cin; p.cin_total = cin_total; p.cin_first = cin_first;
+  p.dw = dw_oihw; p.alpha = alpha_dev; p.scale = scale;
+  p.err_sink = error_sink_device();
+  CUtensorMap tmX, tmZ;
+  {  // x, padded extent: {c, w, h, n}
+    const uint64_t pix = (uint64_t)x->c * 4, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
+    uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)t_wp(*x), (uint64_t)t_hp(*x), (uint64_t)x->n};
+    uint64_t strides[3] = {pix, row, img};
+    uint32_t box[4] = {32u, (uint32_t)p.pw, (uint32_t)p.ph, 1u};
+    if (encode_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x->data, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return -1;
+  }
+  {  // the stack: {32, w + k - 1, h, n}
+    const uint64_t pix = 128, row = (uint64_t)e->w * pix, img = (uint64_t)e->h * row;
+    uint64_t dims[4] = {32u, (uint64_t)e->w, (uint64_t)e->h, (uint64_t)e->n};
+    uint64_t strides[3] = {pix, row, img};
+    uint32_t box[4] = {32u, 8u, 8u, 1u};
+    if (encode_tiled(&tmZ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e->data, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return -1;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    UEGAN_CUDA(cudaFuncSetAttribute(conv_wgrad_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    attr_set = true;
+  }
+  const int smem_bytes = p.num_stages * p.stage_bytes + 1024;
+  dim3 grid((unsigned)p.ksplit, (unsigned)slices, 1u);
+  conv_wgrad_patch_kernel<<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmX, tmZ, p);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -96,7 +96,8 @@ __device__ __forceinline__ long long toff(const TGeom& g, int n, int y, int x, i
 // backward, bias gradients, the perceptual MSE): block = (`rows` image rows of image n), thread = (pixel lane,
 // 16-byte channel vector).  Loads are 16 B per thread, coalesced along C then W; integer division only per row;
 // fp32 partials per thread, one smem tree per block, then Op::flush (atomics) once per (block, channel).
-//   Op: void acc(int n, int y, int x, int c, float (&a)[VN][NACC])  -- add the contributions of channels c..c+VN-1
+//   Op: void prep(int n, int c)                                     -- cache what is constant per (n, channel vector)
+//       void acc(int n, int y, int x, int c, float (&a)[VN][NACC])  -- add the contributions of channels c..c+VN-1
 //       void flush(int n, int c, const float (&tot)[NACC])          -- publish one channel's block total
 // ------------------------------------------------------------------------------------------
 template <typename T, int NACC, typename Op>
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(256) strip_reduce_kernel(Op op, int cch, int h
 #pragma unroll
     for (int j = 0; j < NACC; ++j) a[k][j] = 0.f;
   if (lane < lanes) {
+    op.prep(n, c);  // per-(n, c) statistics of this thread's channel vector -> registers, once
     for (int y = y0; y < y1; ++y)
       for (int x = lane; x < w; x += lanes) op.acc(n, y, x, c, a);
   }
@@ -219,6 +221,7 @@ template <typename T>
 struct InStatsOp {
   TGeom s;
   double* stats;
+  __device__ void prep(int, int) {}
   __device__ void acc(int n, int y, int x, int c, float (&a)[Vec<T>::N][2]) const {
     float v[Vec<T>::N];
     Vec<T>::load(static_cast<const T*>(s.data) + toff(s, n, y, x, c), v);

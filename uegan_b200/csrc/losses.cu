@@ -127,14 +127,21 @@ struct InMseOp {
   const float* mrx;
   const float* mry;
   double* accum;
+  float mx[Vec<T>::N], rx[Vec<T>::N], my[Vec<T>::N], ry[Vec<T>::N];
+  __device__ void prep(int n, int c) {
+#pragma unroll
+    for (int k = 0; k < Vec<T>::N; ++k) {
+      const long long si = ((long long)n * x.c + c + k) * 2;
+      mx[k] = mrx[si]; rx[k] = mrx[si + 1]; my[k] = mry[si]; ry[k] = mry[si + 1];
+    }
+  }
   __device__ void acc(int n, int yy, int xx, int c, float (&a)[Vec<T>::N][1]) const {
     float xv[Vec<T>::N], yv[Vec<T>::N];
     Vec<T>::load(static_cast<const T*>(x.data) + toff(x, n, yy, xx, c), xv);
     Vec<T>::load(static_cast<const T*>(y.data) + toff(y, n, yy, xx, c), yv);
 #pragma unroll
     for (int k = 0; k < Vec<T>::N; ++k) {
-      const long long si = ((long long)n * x.c + c + k) * 2;
-      const float d = (xv[k] - mrx[si]) * mrx[si + 1] - (yv[k] - mry[si]) * mry[si + 1];
+      const float d = (xv[k] - mx[k]) * rx[k] - (yv[k] - my[k]) * ry[k];
       a[k][0] += d * d;
     }
   }

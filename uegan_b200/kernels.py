@@ -56,6 +56,16 @@ class NHWC:
     def ref(self):
         return C.byref(self.ct)
 
+    def as_haloed(self, halo: int) -> "NHWC":
+        """The same memory read as a tensor whose outer `halo` pixels are a halo: a halo-0 buffer of extent
+        (h + 2*halo) x (w + 2*halo) (the padded gradient a dgrad launch writes) becomes interior h x w + halo."""
+        assert self.halo == 0 and self.h > 2 * halo and self.w > 2 * halo
+        v = object.__new__(NHWC)
+        v.n, v.h, v.w, v.c, v.halo, v.dtype = self.n, self.h - 2 * halo, self.w - 2 * halo, self.c, halo, self.dtype
+        v.buf, v.elems = self.buf, self.elems
+        v.ct = L.Tensor(self.buf.data_ptr(), v.n, v.h, v.w, v.c, halo, self.dtype)
+        return v
+
     def padded_view(self) -> torch.Tensor:
         return self.buf[: self.elems].view(self.n, self.h + 2 * self.halo, self.w + 2 * self.halo, self.c)
 
@@ -428,6 +438,43 @@ def grad_combine(dst: NHWC, channels: int, src_a: Optional[NHWC] = None, pad_a: 
     _count(1, f"grad_combine c{channels} pad{pad_a if src_a is not None else '-'}"
               f"{' +b' if add_b is not None else ''}{' +c' if add_c is not None else ''}"
               f"{' mask' if mask is not None else ''}{' mul' if mul is not None else ''}", dst, src_a)
+
+
+def fold_inplace(dxp: NHWC, pad: int) -> NHWC:
+    """Reflect-pad adjoint in place on the padded gradient `dxp` (halo 0, extent (h+2p) x (w+2p)); returns the view
+    (interior h x w, ZERO halo p) that downstream wgrad / dgrad / elementwise kernels consume."""
+    v = dxp.as_haloed(pad)
+    L.check(L.load().uegan_fold_inplace(v.ref(), _stream()), "fold_inplace")
+    _count(2, "fold_inplace", v)
+    return v
+
+
+def dz_hstack(dz: NHWC, cout: int, k: int, e: NHWC):
+    L.check(L.load().uegan_dz_hstack(dz.ref(), cout, k, e.ref(), _stream()), "dz_hstack")
+    _count(1, "dz_hstack", e)
+
+
+def conv_wgrad_hstack(x: NHWC, e: NHWC, dw: torch.Tensor, k: int, pad: int, alpha=None, scale: float = 1.0):
+    """dw (OIHW fp32, pre-zeroed or accumulating) += wgrad from the stacked gradient e = dz_hstack(dz)."""
+    cout, cin_total = dw.shape[0], dw.shape[1]
+    assert dw.is_cuda and dw.dtype == torch.float32 and dw.is_contiguous()
+    ev = _Counters.conv_events
+    if ev is not None:
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+    L.check(L.load().uegan_conv2d_wgrad_hstack(x.ref(), e.ref(), cout, cin_total, cin_total, 0, k, pad, dw.data_ptr(),
+                                               alpha.data_ptr() if alpha is not None else None, float(scale), _stream()),
+            "conv2d_wgrad_hstack")
+    if ev is not None:
+        s1.record()
+        ev.append((s0, s1, 2.0 * x.n * x.h * x.w * cout * cin_total * k * k, x, cout, k, 1, "wgrad", x.dtype))
+    _count(1, f"wgrad_hstack cout{cout} cin{cin_total} k{k}", x, e)
+
+
+def hstack_ok(cout: int, cin_stored: int, k: int) -> bool:
+    import os
+    return (os.environ.get("UEGAN_NO_HSTACK") != "1" and cout in (1, 3) and k * cout <= 21 and k % 2 == 1
+            and cin_stored % 32 == 0)
 
 
 def channel_sum(src: NHWC, out: torch.Tensor, c_off: int = 0, channels: Optional[int] = None):
