@@ -374,7 +374,12 @@ def run_native(args):
         peak = tot_fl / t_at_peak / 1e12
         top = sorted(per.items(), key=lambda kv: -kv[1][0])[:24]
         roof = {"bound": "tensor", "kernel": "conv_fprop_kernel (fprop+dgrad) + conv_wgrad_kernel, all launches of a step",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                # DRAM bytes of these launches per step (dram__bytes_read.sum + dram__bytes_write.sum, ncu): measured once,
+                # profiles/r1d_train_step_launches.md (training, 330 of 349 GEMM launches of the r1d build); per-layer
+                # figures of the current kernels: profiles/r1g_ncu_full_layers.md
+                "traffic": 82.2e9 if train else None,
+                "traffic_source": "ncu, profiles/r1d_train_step_launches.md (bytes per step, r1d build)" if train else None,
                 "peak_source": f"{src}: FLOP-weighted mix of bf16_tflops {tf_burst} (fp16 launches) and half of it (tf32 launches)",
                 "gemm_ms_per_step": tot_ms, "step_ms": ms_total / args.steps, "gemm_launches_per_step": len(ev) // reps,
                 "gemm_share_of_step": tot_ms / (ms_total / args.steps),

@@ -74,14 +74,21 @@ CONV_CASES = [
     ("vgg_first", 2, 3, 32, 32, 64, 3, 1, "zero"),
     ("ragged", 3, 32, 40, 24, 48, 3, 1, "reflect"),
     ("tiny_2x2", 3, 64, 4, 4, 32, 3, 2, "reflect"),
+    # patch mode with STREAMED weights (weights do not fit next to >= 3 patch stages)
+    ("stream_128_64", 2, 128, 32, 24, 64, 3, 1, "reflect"),
+    ("stream_nsplit", 2, 256, 16, 16, 256, 3, 1, "zero"),      # few tiles: N split 256 -> 64, four N tiles per patch
+    ("stream_vgg2_1", 1, 64, 32, 32, 128, 3, 1, "zero"),
+    ("stream_k5", 1, 64, 20, 28, 48, 5, 1, "reflect"),
 ]
 
 
 @pytest.mark.parametrize("dtype_name", ["f32", "bf16", "f16"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv_fprop(K, case, dtype_name):
+def test_conv_fprop(K, case, dtype_name, monkeypatch):
     from uegan_b200 import _lib as L
     name, n, cin, h, w, cout, k, stride, pad_mode = case
+    if name.startswith("stream_"):
+        monkeypatch.setenv("UEGAN_STREAM_MAXN", "128")  # the streamed-weight patch mode is opt-in (read per launch)
     dtype = dt(dtype_name)
     pm = L.PAD_REFLECT if pad_mode == "reflect" else L.PAD_ZERO
     g = torch.Generator(device="cuda").manual_seed(1234)
@@ -282,3 +289,26 @@ def test_in_mse_bwd_direct(K):
         pv = dx.padded_view().float()
         assert float(pv[:, 0].abs().max()) == 0.0 and float(pv[:, :, 0].abs().max()) == 0.0
         assert float(pv[:, -1].abs().max()) == 0.0 and float(pv[:, :, -1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("case", [("f32", 64, 32, 1), ("f32", 32, 64, 3), ("f16", 64, 128, 3)])
+def test_conv_fused_instance_norm_stats(K, case):
+    """Per-(n, c) sum / sum of squares accumulated by the conv epilogue (in_stats), consumed by instance_norm_apply: the
+    opt-in alternative (UEGAN_FUSED_STATS) to a separate statistics pass."""
+    from uegan_b200 import _lib as L
+    dtype_name, cin, cout, k = case
+    dtype = dt(dtype_name)
+    g = torch.Generator(device="cuda").manual_seed(17)
+    n, h, w = 2, 16, 24
+    pad = (k - 1) // 2
+    x = quant(torch.randn(n, cin, h, w, device="cuda", generator=g), dtype)
+    wgt = quant(torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k), dtype)
+    xt = fill_nhwc(K, x, cin, pad, L.PAD_ZERO, dtype)
+    z = K.NHWC(n, h, w, cout, 0, dtype, "cuda")
+    dst = K.NHWC(n, h, w, cout, 0, dtype, "cuda")
+    stats = torch.empty(3 * n * cout, dtype=torch.float64, device="cuda")
+    K.conv_fprop(xt, K.packed_weight(wgt, cin, dtype), cout, k, 1, pad, z, in_stats=stats)
+    K.instance_norm_apply(z, dst, 0, stats)
+    assert K.device_error() == 0
+    ref = F.instance_norm(z.interior_nchw(), eps=1e-5)  # statistics of the STORED (rounded) conv output
+    assert relerr(dst.interior_nchw(), ref) < (2e-3 if dtype != L.F32 else 1e-3)

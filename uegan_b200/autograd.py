@@ -72,7 +72,7 @@ def _g_workspace(G, b, h, w, dev):
 def _gam_forward(G, name, ga, src, ch, z, dst, off, stats, ws):
     fuse = ga.fuse[0]
     wp = G._wcache.get(name, fuse.weight, lambda out=None: K.packed_weight(fuse.weight, src.c, F32, 0, ch, out=out))
-    if K.fused_stats_ok(src.h, src.w):
+    if K.fused_stats_ok(src.h, src.w, ch):
         K.conv_fprop(src, wp, ch, 1, 1, 0, z, in_stats=stats)
         K.instance_norm_apply(z, dst, off, stats)
         ws["mr"][name] = stats.data_ptr() + 2 * src.n * ch * 8

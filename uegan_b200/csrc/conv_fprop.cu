@@ -22,6 +22,7 @@
 namespace uegan {
 
 constexpr int kMaxStages = 8;
+constexpr int kMaxBSlots = 16;
 constexpr int kABytes = 128 * 128;  // 128 pixel rows x 128 B
 constexpr int kTmemCols = 512;      // 2 accumulator stages x 256 fp32 columns
 
@@ -38,6 +39,9 @@ struct ConvParams {
   // patch mode (stride-1, pixel = whole 128-byte chunks, weights resident in smem)
   int patch_w, patch_nch, patch_k, patch_off;  // patch width in pixels, chunks per pixel, kernel size, halo - pad
   int w_tile_bytes, w_total_bytes, stage_tx_bytes;
+  // patch mode with STREAMED weights (kPatch == 2): the weight tiles do not fit next to the patches (large C or N), so
+  // they flow through their own ring of b_slots x w_tile_bytes behind the A ring (b_ring_off bytes from the smem base)
+  int b_slots, b_ring_off;
   // epilogue
   int Wo, Ho, Nimg, cout;
   int act;
@@ -275,6 +279,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ __align__(8) uint64_t w_full;
+  __shared__ __align__(8) uint64_t fullB[kMaxBSlots];
+  __shared__ __align__(8) uint64_t emptyB[kMaxBSlots];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_stats[8 * 256];  // InstanceNorm partial sums: [epilogue warp][chunk slot][lane]
 
@@ -295,6 +301,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tmem_empty[i], 8);
     }
     mbar_init(&w_full, 1);
+    if constexpr (kPatch == 2) {
+      for (int i = 0; i < p.b_slots; ++i) {
+        mbar_init(&fullB[i], 1);
+        mbar_init(&emptyB[i], 1);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, kTmemCols);
@@ -308,7 +320,33 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      if constexpr (kPatch) {
+      if constexpr (kPatch == 2) {
+        // A: one patch per (tile, channel chunk); B: the k*k weight tiles of that chunk, each through the B ring.  The MMA
+        // warp consumes in exactly this order, so neither ring can starve the other.
+        uint8_t* sb0 = smem + p.b_ring_off;
+        int bs = 0;
+        uint32_t bphase = 0;
+        const int taps = p.patch_k * p.patch_k;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+          const TileCoord tc = decode_tile(p, t);
+          for (int c = 0; c < p.patch_nch; ++c) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 0x100 + stage, p.err_sink);
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_tx_bytes);
+            tma_load_4d(&tmA, &full_bar[stage], smem + stage * p.stage_bytes, c * p.chunk_elems, tc.wo0 + p.patch_off,
+                        tc.ho0 + p.patch_off, tc.n0);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+            int r = 0, s_ = 0;
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&emptyB[bs], bphase ^ 1, 0x180 + bs, p.err_sink);
+              mbar_arrive_expect_tx(&fullB[bs], (uint32_t)p.w_tile_bytes);
+              const int kofs = (r * p.chunks_per_row + s_ * p.patch_nch + c) * p.chunk_elems;
+              tma_load_2d(&tmB, &fullB[bs], sb0 + bs * p.w_tile_bytes, kofs, tc.nt * p.block_n);
+              if (++s_ == p.patch_k) { s_ = 0; ++r; }
+              if (++bs == p.b_slots) { bs = 0; bphase ^= 1; }
+            }
+          }
+        }
+      } else if constexpr (kPatch == 1) {
         // weights: all k*k*nch [block_n x 128 B] tiles once per CTA, resident behind the A ring
         uint8_t* sw = smem;
         mbar_arrive_expect_tx(&w_full, (uint32_t)p.w_total_bytes);
@@ -356,12 +394,46 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      if constexpr (kPatch) mbar_wait(&w_full, 0, 0x500, p.err_sink);
+      if constexpr (kPatch == 1) mbar_wait(&w_full, 0, 0x500, p.err_sink);
+      int bs = 0;
+      uint32_t bphase = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 0x200 + acc, p.err_sink);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        if constexpr (kPatch) {
+        if constexpr (kPatch == 2) {
+          // same descriptor-window taps as the resident-weight patch mode; the B tile of every (chunk, tap) arrives
+          // through the B ring and its slot is released by a commit right after the four MMAs that read it
+          const uint32_t w_addr = smem_u32(smem);
+          const uint32_t sbo = p.patch_w * 128;
+          const uint64_t db0 = make_smem_desc(w_addr + p.b_ring_off, 16, 1024, UMMA_LAYOUT_SW128);
+          uint32_t first = 0;
+          for (int c = 0; c < p.patch_nch; ++c) {
+            mbar_wait(&full_bar[stage], phase, 0x300 + stage, p.err_sink);
+            tcgen05_fence_after();
+            const uint64_t da0 = make_smem_desc(w_addr + stage * p.stage_bytes, 16, sbo, UMMA_LAYOUT_SW128);
+            uint32_t a_off = 0;
+            for (int r = 0; r < p.patch_k; ++r) {
+              uint32_t a_rs = a_off;
+              for (int s_ = 0; s_ < p.patch_k; ++s_) {
+                mbar_wait(&fullB[bs], bphase, 0x380 + bs, p.err_sink);
+                tcgen05_fence_after();
+                const uint64_t da = desc_adv(da0, a_rs), db = desc_adv(db0, (uint32_t)bs * p.w_tile_bytes);
+                umma_ss<kTf32>(d_tmem, da, db, idesc, first);
+                umma_ss<kTf32>(d_tmem, da + 2, db + 2, idesc, 1u);
+                umma_ss<kTf32>(d_tmem, da + 4, db + 4, idesc, 1u);
+                umma_ss<kTf32>(d_tmem, da + 6, db + 6, idesc, 1u);
+                umma_commit(&emptyB[bs]);
+                if (++bs == p.b_slots) { bs = 0; bphase ^= 1; }
+                first = 1;
+                a_rs += 128;
+              }
+              a_off += sbo;
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          }
+        } else if constexpr (kPatch == 1) {
           // one staged patch per 128-byte channel chunk; every filter tap (r, s) is the SAME smem patch read
           // through a descriptor window shifted by (r*patch_w + s) rows (tcgen05 swizzles on absolute address bits,
           // profiles/r1_probe_umma_window.json), 8-row groups = one output row of 8 pixels, SBO = patch row pitch.
@@ -614,15 +686,43 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   const uint64_t pix_b = (uint64_t)x.c * es;
   const uint64_t row_b = (uint64_t)t_wp(x) * pix_b;
   const uint64_t img_b = (uint64_t)t_hp(x) * row_b;
-  bool patch = false;
+  bool patch = false, stream_w = false;
   {
     const char* env = getenv("UEGAN_NO_PATCH");
+    const char* env2 = getenv("UEGAN_NO_STREAM");
     const int PH = 16 + d.k - 1, PW = 8 + d.k - 1;
     const long long a_stage = ((long long)PH * PW * 128 + 1023) / 1024 * 1024;
     const long long w_tile = (long long)p.block_n * 128;
     const long long w_total = w_tile * d.k * d.k * (pix_b / 128);
-    if (!(env && env[0] == '1') && d.stride == 1 && d.k > 1 && pix_b % 128 == 0 && p.n_tiles == 1 && Ho >= 16 &&
-        Wo >= 8 && w_total + 2 * a_stage <= 200 * 1024) {
+    const bool shape_ok = !(env && env[0] == '1') && d.stride == 1 && d.k > 1 && pix_b % 128 == 0 && Ho >= 16 && Wo >= 8;
+    const bool resident = shape_ok && p.n_tiles == 1 && w_total + 2 * a_stage <= 200 * 1024;
+    const bool resident_deep = resident && w_total + 3 * a_stage <= 200 * 1024;  // >= 3 patch stages in flight
+    // Weights that do not fit (or leave only two patch stages: the TMA latency of a patch is then exposed) are streamed
+    // through their own ring: the A operand is still fetched once per tile instead of once per tap.
+    // (N = 256 launches are MMA-bound in plain mode already: 85-97 % of the tensor peak; they stay there.)
+    const char* env3 = getenv("UEGAN_STREAM_MAXN");
+    const int stream_max_n = env3 ? atoi(env3) : 0;  // opt-in: measured 1-6 % SLOWER than plain mode
+    if (shape_ok && !resident_deep && !(env2 && env2[0] == '1') && p.block_n <= stream_max_n && w_tile % 1024 == 0 &&
+        3 * a_stage + 4 * w_tile <= 200 * 1024) {
+      stream_w = true;
+      p.tw = 8; p.th = 16; p.tn = 1; p.tw_log2 = 3; p.th_log2 = 4;
+      p.tiles_w = (Wo + 7) / 8;
+      p.tiles_h = (Ho + 15) / 16;
+      p.tiles_img = x.n;
+      p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_img * p.n_tiles;
+      p.patch_w = PW;
+      p.patch_nch = (int)(pix_b / 128);
+      p.patch_k = d.k;
+      p.patch_off = x.halo - d.pad;
+      p.w_tile_bytes = (int)w_tile;
+      p.w_total_bytes = 0;
+      p.stage_bytes = (int)a_stage;
+      p.stage_tx_bytes = PH * PW * 128;
+      p.num_stages = 3;
+      p.b_ring_off = p.num_stages * p.stage_bytes;
+      p.b_slots = (int)((200 * 1024 - p.b_ring_off) / w_tile);
+      if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
+    } else if (resident) {
       patch = true;
       p.tw = 8; p.th = 16; p.tn = 1; p.tw_log2 = 3; p.th_log2 = 4;
       p.tiles_w = (Wo + 7) / 8;
@@ -643,7 +743,7 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   }
   // ---- tensor maps
   CUtensorMap tmA, tmB;
-  if (patch) {
+  if (patch || stream_w) {
     uint64_t dims[4] = {(uint64_t)x.c, (uint64_t)t_wp(x), (uint64_t)t_hp(x), (uint64_t)x.n};
     uint64_t strides[3] = {pix_b, row_b, img_b};
     uint32_t box[4] = {(uint32_t)g.chunk_elems, (uint32_t)p.patch_w, (uint32_t)(16 + d.k - 1), 1u};
@@ -668,7 +768,8 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
     UEGAN_CHECK(p.tn == 1, "conv: in_stats needs tiles within one image (Ho*Wo >= 128); use uegan_instance_norm");
     UEGAN_CUDA(cudaMemsetAsync(d.in_stats, 0, sizeof(double) * 2 * (size_t)x.n * d.cout, stream));
   }
-  const int smem_bytes = (patch ? p.w_total_bytes : 0) + p.num_stages * p.stage_bytes + 1024;
+  const int smem_bytes = stream_w ? p.b_ring_off + p.b_slots * p.w_tile_bytes + 1024
+                                  : (patch ? p.w_total_bytes : 0) + p.num_stages * p.stage_bytes + 1024;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   {
     static bool attr_set = false;
@@ -677,14 +778,18 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
       UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
       UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
       UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
       attr_set = true;
     }
   }
   if (x.dtype == UEGAN_F32) {
-    if (patch) conv_fprop_kernel<1, 1><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    if (stream_w) conv_fprop_kernel<1, 2><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    else if (patch) conv_fprop_kernel<1, 1><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
     else conv_fprop_kernel<1, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
   } else {
-    if (patch) conv_fprop_kernel<0, 1><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    if (stream_w) conv_fprop_kernel<0, 2><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    else if (patch) conv_fprop_kernel<0, 1><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
     else conv_fprop_kernel<0, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
   }
   UEGAN_CUDA(cudaGetLastError());

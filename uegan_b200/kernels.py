@@ -212,9 +212,18 @@ def instance_norm_apply(src: NHWC, dst: NHWC, dst_c_off: int, stats_ws: torch.Te
     _count(2, "instance_norm_apply", src)
 
 
-def fused_stats_ok(ho: int, wo: int) -> bool:
-    """conv epilogue statistics need every 128-pixel tile inside one image."""
-    return ho * wo >= 128 and wo >= 8
+def fused_stats_ok(ho: int, wo: int, cout: Optional[int] = None) -> bool:
+    """Whether the InstanceNorm statistics ride in the producing conv's epilogue (conv_fprop(in_stats=...)); needs every
+    128-pixel tile inside one image.  Default: NO -- the epilogue's per-tile butterfly (~150 instructions per 16-column
+    chunk) makes the launch epilogue-bound, and a separate strip-reduce pass over the stored tensor at 5-7 TB/s is cheaper:
+    measured on B200 (r1h A/B, training step) all-fused 72.2 ms, none 70.5 ms, cout <= 32 only 70.6 ms; VGG fprop 8.25 ->
+    5.89 ms.  UEGAN_FUSED_STATS = all | none | <max cout> selects the policy."""
+    import os
+    mode = os.environ.get("UEGAN_FUSED_STATS", "none")
+    if mode == "none":
+        return False
+    limit = (1 << 30) if mode == "all" else int(mode)
+    return ho * wo >= 128 and wo >= 8 and (cout is None or cout <= limit)
 
 
 def spectral_sigma(w: torch.Tensor, u: torch.Tensor, v: torch.Tensor, train: bool, sigma_out: torch.Tensor,

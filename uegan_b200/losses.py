@@ -88,7 +88,7 @@ class VGG19_relu(nn.Module):
             idx, cin, cout = spec
             conv = self.features[idx]
             is_tap = idx in _TAP_IDX
-            fused = is_tap and K.fused_stats_ok(dst.h, dst.w)
+            fused = is_tap and K.fused_stats_ok(dst.h, dst.w, cout)
             K.conv_fprop(src, self._packed(idx, src.c), cout, 3, 1, 1, dst, 0, conv.bias, None, L.ACT_RELU,
                          in_stats=P["stats"][ti] if fused else None)
             if is_tap:

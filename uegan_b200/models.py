@@ -201,7 +201,7 @@ class Generator(nn.Module):
             # (n, c) and cancel in the InstanceNorm that follows (models.py:230-237; SURVEY.md 8a rewrite 1).
             fuse = ga.fuse[0]
             wp = self._wcache.get(name, fuse.weight, lambda out=None: K.packed_weight(fuse.weight, src.c, L.F32, 0, ch, out=out))
-            if K.fused_stats_ok(src.h, src.w):  # statistics ride in the conv epilogue
+            if K.fused_stats_ok(src.h, src.w, ch):  # statistics ride in the conv epilogue
                 K.conv_fprop(src, wp, ch, 1, 1, 0, z, in_stats=P["stats"])
                 K.instance_norm_apply(z, dst, off, P["stats"])
             else:
