@@ -116,8 +116,19 @@ __global__ void __launch_bounds__(256) strip_reduce_kernel(Op op, int cch, int h
     for (int j = 0; j < NACC; ++j) a[k][j] = 0.f;
   if (lane < lanes) {
     op.prep(n, c);  // per-(n, c) statistics of this thread's channel vector -> registers, once
-    for (int y = y0; y < y1; ++y)
-      for (int x = lane; x < w; x += lanes) op.acc(n, y, x, c, a);
+    for (int y = y0; y < y1; ++y) {
+      // four independent pixels per trip: the loads of a trip are issued back to back (the loop carries no stores), which
+      // is what a latency-bound 16-byte-per-thread reduction needs (1.9-2.7 TB/s -> HBM-bound)
+      int x = lane;
+      // (16-bit tensors only: measured r1i, the fp32 reductions lose occupancy to the extra registers)
+      for (; sizeof(T) == 2 && x + 3 * lanes < w; x += 4 * lanes) {
+        op.acc(n, y, x, c, a);
+        op.acc(n, y, x + lanes, c, a);
+        op.acc(n, y, x + 2 * lanes, c, a);
+        op.acc(n, y, x + 3 * lanes, c, a);
+      }
+      for (; x < w; x += lanes) op.acc(n, y, x, c, a);
+    }
   }
 #pragma unroll
   for (int k = 0; k < VN; ++k)
@@ -250,17 +261,14 @@ __global__ void in_finalize_kernel(const double* __restrict__ stats, float* __re
   mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// grid = (x-chunks of a row, rows, images): no per-thread divisions (cv is a power of two)
 template <typename T>
-__global__ void in_apply_kernel(TGeom s, TGeom d, int dst_c_off, const float* __restrict__ mr, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int cv = s.c / Vec<T>::N;
-  const int c = (int)(i % cv) * Vec<T>::N;
-  long long pix = i / cv;
-  const int x = (int)(pix % s.w);
-  pix /= s.w;
-  const int y = (int)(pix % s.h);
-  const int n = (int)(pix / s.h);
+__global__ void in_apply_kernel(TGeom s, TGeom d, int dst_c_off, const float* __restrict__ mr, int cv_log2) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = t >> cv_log2;
+  if (x >= s.w) return;
+  const int c = (t & ((1 << cv_log2) - 1)) * Vec<T>::N;
+  const int y = blockIdx.y, n = blockIdx.z;
   float v[Vec<T>::N];
   Vec<T>::load(static_cast<const T*>(s.data) + toff(s, n, y, x, c), v);
   const float* m = mr + ((long long)n * s.c + c) * 2;
@@ -414,13 +422,18 @@ static int instance_norm_impl(const uegan_tensor* src, const uegan_tensor* dst, 
   float* mr = reinterpret_cast<float*>(stats_ws + 2 * nc);  // finalised (mean, rstd) live after the raw sums
   in_finalize_kernel<<<nblocks(nc, 128), 128, 0, st>>>(stats_ws, mr, nc, 1.0 / (double)npix, eps);
   const int vn = 16 / dtype_size(src->dtype);
-  const long long total = (long long)s.n * npix * (s.c / vn);
+  const int cv = s.c / vn;
+  int lg = 0;
+  while ((1 << lg) < cv) ++lg;
+  UEGAN_CHECK((1 << lg) == cv, "instance_norm: channels / vector width must be a power of two (got %d)", cv);
+  UEGAN_CHECK(s.h <= 65535 && s.n <= 65535, "instance_norm: tensor too large for the launch grid");
+  const dim3 grid(nblocks((long long)s.w * cv, 256), (unsigned)s.h, (unsigned)s.n);
   if (src->dtype == UEGAN_F32)
-    in_apply_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, mr, total);
+    in_apply_kernel<float><<<grid, 256, 0, st>>>(s, d, dst_c_off, mr, lg);
   else if (src->dtype == UEGAN_BF16)
-    in_apply_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, mr, total);
+    in_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(s, d, dst_c_off, mr, lg);
   else
-    in_apply_kernel<__half><<<nblocks(total, 256), 256, 0, st>>>(s, d, dst_c_off, mr, total);
+    in_apply_kernel<__half><<<grid, 256, 0, st>>>(s, d, dst_c_off, mr, lg);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -233,7 +233,7 @@ def spectral_sigma(w: torch.Tensor, u: torch.Tensor, v: torch.Tensor, train: boo
     assert ws.numel() >= rows + cols + 8 and sigma_out.numel() >= 2
     L.check(L.load().uegan_spectral_sigma(w.data_ptr(), u.data_ptr(), v.data_ptr(), rows, cols, int(train),
                                           sigma_out.data_ptr(), ws.data_ptr(), _stream()), "spectral_sigma")
-    _count(6 if train else 2, "spectral_sigma")
+    _count(4 if train else 2, "spectral_sigma")
 
 
 def upsample2x(src: NHWC, dst: NHWC, dst_c_off: int = 0):
