@@ -445,3 +445,89 @@ def train_step(gp: Params, dp: Params, vp: Params, g_opt: AdamState, d_opt: Adam
 def rel_err(a: Tensor, b: Tensor, floor: float = 1e-6) -> float:
     """max |a-b| / max(|b|_max, floor): the "relative" of north_star's 1e-3 (scale of the tensor)."""
     return float((a.double() - b.double()).abs().max() / max(float(b.abs().max()), floor))
+
+
+# ----------------------------------------------------------------------------------------------
+# Algebra of the tiny-Cout kernels (csrc/conv_rowsum.cu, conv_wgrad.cu vertical mode), restated on the CPU so that the
+# transformation itself is pinned against F.conv2d / autograd independently of the GPU (tests/test_oracle.py).
+# ----------------------------------------------------------------------------------------------
+def conv_rowsum_restatement(xpad: Tensor, w: Tensor) -> Tensor:
+    """Valid conv of xpad (N,C,Hp,Wp) with w (O,C,k,k) computed the way conv_rowsum_kernel does: horizontal taps as GEMM
+    columns, D[n,(s,o),i,q] = sum_{r,c} xpad[n,c,i+r,q] * w[o,c,r,s]  (a k x 1 conv with k*O outputs), then the shifted sum
+    y[n,o,i,x] = sum_s D[n,(s,o),i,x+s]  (the epilogue's __shfl_down)."""
+    o, c, k, _ = w.shape
+    wv = w.permute(3, 0, 1, 2).reshape(k * o, c, k, 1)            # rows (s, o); only the vertical taps remain
+    d = F.conv2d(xpad, wv)                                        # (N, k*O, Hp-k+1, Wp)
+    wo = xpad.shape[3] - k + 1
+    return sum(d[:, s * o:(s + 1) * o, :, s:s + wo] for s in range(k))
+
+
+def dz_hstack_restatement(dz: Tensor, k: int) -> Tensor:
+    """uegan_dz_hstack: E[n,(s,o),y,q] = dz[n,o,y,q-s], q in [0, W+k-1) (zero outside the image)."""
+    n, o, h, w = dz.shape
+    e = dz.new_zeros(n, k * o, h, w + k - 1)
+    for s in range(k):
+        e[:, s * o:(s + 1) * o, :, s:s + w] = dz
+    return e
+
+
+def wgrad_hstack_restatement(xpad: Tensor, dz: Tensor, k: int) -> Tensor:
+    """Weight gradient of y = conv(xpad, w) (stride 1) from the stacked gradient:
+    dW[o,c,r,s] = sum_{n,y,q} xpad[n,c,y+r,q] * E[n,(s,o),y,q]  -- the wgrad of a k x 1 convolution with k*O outputs."""
+    n, c, hp, wp = xpad.shape
+    o = dz.shape[1]
+    e = dz_hstack_restatement(dz, k)                              # (N, k*O, H, Wp)
+    h = e.shape[2]
+    dw = xpad.new_zeros(o, c, k, k)
+    for r in range(k):
+        t = torch.einsum("ncyq,njyq->jc", xpad[:, :, r:r + h, :], e)   # (k*O, C)
+        dw[:, :, r, :] = t.reshape(k, o, c).permute(1, 2, 0)
+    return dw
+
+
+def fold_reflect_restatement(dxp: Tensor, pad: int) -> Tensor:
+    """uegan_fold_inplace: adjoint of nn.ReflectionPad2d(pad) applied to the gradient of the padded tensor."""
+    n, c, hp, wp = dxp.shape
+    h, w = hp - 2 * pad, wp - 2 * pad
+    g = dxp
+    # separable: fold rows, then columns
+    rows = g[:, :, pad:pad + h, :].clone()
+    for y in range(1, pad + 1):
+        rows[:, :, y, :] += g[:, :, pad - y, :]
+        rows[:, :, h - 1 - y, :] += g[:, :, pad + h - 1 + y, :]
+    out = rows[:, :, :, pad:pad + w].clone()
+    for x in range(1, pad + 1):
+        out[:, :, :, x] += rows[:, :, :, pad - x]
+        out[:, :, :, w - 1 - x] += rows[:, :, :, pad + w - 1 + x]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# SURVEY.md 8(f) "next" rows N3 / N4: the steps either side of the hot path (oracle only, for the next round's kernels)
+# ----------------------------------------------------------------------------------------------
+def to_tensor_normalize(img_u8_hwc: np.ndarray) -> Tensor:
+    """transforms.ToTensor() + Normalize(0.5, 0.5) on a uint8 HWC RGB image -> fp32 CHW in [-1, 1]
+    (/root/reference/data_loader.py:79-81, 100-103)."""
+    x = torch.from_numpy(np.ascontiguousarray(img_u8_hwc)).permute(2, 0, 1).to(torch.float32).div(255.0)
+    return (x - 0.5) / 0.5
+
+
+def denorm(x: Tensor) -> Tensor:
+    """/root/reference/utils.py:128-130."""
+    return ((x + 1) / 2.0).clamp(0, 1)
+
+
+def denorm_to_u8(x_chw: Tensor) -> np.ndarray:
+    """denorm followed by torchvision.utils.save_image's quantisation (mul(255).add_(0.5).clamp_(0,255) -> uint8 HWC),
+    the PNG the Tester writes (/root/reference/tester.py via utils.save_image)."""
+    y = denorm(x_chw).mul(255).add(0.5).clamp(0, 255)
+    return y.permute(1, 2, 0).to(torch.uint8).numpy()
+
+
+def calculate_psnr(img1: np.ndarray, img2: np.ndarray, data_range: float = 255.0) -> float:
+    """/root/reference/metrics/CalcPSNR.py:85-92 (inputs in [0, 255])."""
+    a, b = img1.astype(np.float64), img2.astype(np.float64)
+    mse = np.mean((a - b) ** 2, dtype=np.float64)
+    if mse == 0:
+        return float("inf")
+    return float(10 * np.log10((data_range ** 2) / mse))

@@ -124,3 +124,65 @@ def test_train_step_matches_reference():
     delta_close(dp0["d1.0.1.weight_orig"], dp["d1.0.1.weight_orig"], g["step_post_d1_w"], 8e-4)
     delta_close(dp0["d5_pred.0.1.weight"], dp["d5_pred.0.1.weight"], g["step_post_d5_pred_w"], 8e-4)
     close(dp["d1.0.1.weight_u"], g["step_post_d1_u"], 1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# algebra of the tiny-Cout kernels and of the in-place fold, pinned on the CPU against F.conv2d / autograd
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,k", [(8, 3, 7), (16, 1, 7), (8, 1, 5), (4, 1, 3)])
+def test_rowsum_and_hstack_algebra(cin, cout, k):
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    pad = (k - 1) // 2
+    x = torch.randn(2, cin, 13, 17, generator=g, dtype=torch.float64)
+    w = torch.randn(cout, cin, k, k, generator=g, dtype=torch.float64, requires_grad=True)
+    xpad = F.pad(x, (pad,) * 4, mode="reflect")
+    ref = F.conv2d(xpad, w)
+    close(O.conv_rowsum_restatement(xpad, w.detach()), ref.detach(), 1e-12)
+    dz = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    ref.backward(dz)
+    close(O.wgrad_hstack_restatement(xpad, dz, k), w.grad, 1e-12)
+    e = O.dz_hstack_restatement(dz, k)
+    assert e.shape == (2, k * cout, 13, 17 + k - 1)
+
+
+@pytest.mark.parametrize("pad", [1, 2, 3])
+def test_fold_reflect_algebra(pad):
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(6)
+    xin = torch.zeros(2, 4, 9, 11, dtype=torch.float64, requires_grad=True)
+    dxp = torch.randn(2, 4, 9 + 2 * pad, 11 + 2 * pad, generator=g, dtype=torch.float64)
+    F.pad(xin, (pad,) * 4, mode="reflect").backward(dxp)
+    close(O.fold_reflect_restatement(dxp, pad), xin.grad, 1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY.md 8(f) N3 / N4 groundwork: input / output conversion and PSNR against the reference's own functions
+# ---------------------------------------------------------------------------------------------------------------
+def test_io_and_psnr_match_reference():
+    import sys
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, size=(24, 40, 3), dtype=np.uint8)
+    x = O.to_tensor_normalize(img)
+    assert x.shape == (3, 24, 40) and float(x.min()) >= -1.0 and float(x.max()) <= 1.0
+    assert np.array_equal(O.denorm_to_u8(x), img)  # ToTensor/Normalize -> denorm -> save_image quantisation round trip
+    a = rng.integers(0, 256, size=(24, 40, 3)).astype(np.float64)
+    b = np.clip(a + rng.normal(0, 4, size=a.shape), 0, 255)
+    mine = O.calculate_psnr(a, b)
+    assert abs(mine - 10 * np.log10(255.0 ** 2 / np.mean((a - b) ** 2))) < 1e-12
+    assert O.calculate_psnr(a, a) == float("inf")
+    if os.path.isdir("/root/reference"):  # live pin in the build container (cv2 / torchvision present there)
+        sys.path.insert(0, "/root/reference")
+        try:
+            from metrics.CalcPSNR import calculate_psnr as ref_psnr
+            import utils as ref_utils  # noqa: F401  (needs tensorflow / skimage shims in some images)
+        except Exception:
+            ref_psnr = None
+        finally:
+            sys.path.pop(0)
+        if ref_psnr is not None:
+            assert abs(mine - ref_psnr(a, b)) < 1e-12
+        import torchvision.transforms as T
+        from PIL import Image
+        tf = T.Compose([T.ToTensor(), T.Normalize(mean=[0.5] * 3, std=[0.5] * 3)])  # data_loader.py:79-81
+        close(x, tf(Image.fromarray(img)), 1e-7)
