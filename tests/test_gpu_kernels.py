@@ -312,3 +312,33 @@ def test_conv_fused_instance_norm_stats(K, case):
     assert K.device_error() == 0
     ref = F.instance_norm(z.interior_nchw(), eps=1e-5)  # statistics of the STORED (rounded) conv output
     assert relerr(dst.interior_nchw(), ref) < (2e-3 if dtype != L.F32 else 1e-3)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("UEGAN_EXPERIMENTAL") != "1",
+                    reason="experimental kernel, not validated on hardware yet (DESIGN.md 7a): run with UEGAN_EXPERIMENTAL=1")
+@pytest.mark.parametrize("case", [(2, 64, 24, 40, 32, True), (1, 32, 37, 61, 32, False), (2, 32, 16, 32, 64, False)])
+def test_conv_rowsum_nhwc_experimental(K, case, monkeypatch):
+    """csrc/conv_rowsum_nhwc.cu (opt-in): k3 stride-1, cout 32 / 64, NHWC output with bias + LeakyReLU (+ mul)."""
+    from uegan_b200 import _lib as L
+    monkeypatch.setenv("UEGAN_ROWSUM_NHWC", "1")
+    n, cin, h, w, cout, use_mul = case
+    g = torch.Generator(device="cuda").manual_seed(300 + cin + cout)
+    x = tf32(torch.randn(n, cin, h, w, device="cuda", generator=g))
+    wgt = tf32(torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / math.sqrt(cin * 9))
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.1
+    m = tf32(torch.randn(n, cout, h, w, device="cuda", generator=g))
+    xt = fill_nhwc(K, x, cin, 2, L.PAD_REFLECT, L.F32)
+    mt = fill_nhwc(K, m, cout, 1, L.PAD_REFLECT, L.F32) if use_mul else None
+    y = K.NHWC(n, h, w, cout + 16, 1, L.F32, "cuda", zero=True)
+
+    class Cache:
+        def get(self, key, param, fn):
+            return fn()
+    assert K.conv3x3_rowsum_nhwc(xt, wgt, Cache(), "t", 1, y, 16, bias, L.ACT_LRELU, mt)
+    assert K.device_error() == 0
+    ref = F.leaky_relu(F.conv2d(F.pad(x, (1,) * 4, mode="reflect").double(), wgt.double(), bias.double()), 0.2).float()
+    if use_mul:
+        ref = ref * m
+    assert relerr(y.interior_nchw()[:, 16:], ref) < 6e-4
+    assert float(y.interior_nchw()[:, :16].abs().max()) == 0.0
+    assert float(y.padded_view()[:, 0].abs().max()) == 0.0

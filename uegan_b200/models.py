@@ -186,6 +186,9 @@ class Generator(nn.Module):
 
         def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE, off=0, mul=None, bias=True):
             cv = c(holder)
+            if k == 3 and stride == 1 and K.conv3x3_rowsum_nhwc(src, cv.weight, self._wcache, name, 1, dst, off,
+                                                                 cv.bias if bias else None, act_, mul):
+                return  # experimental opt-in path (UEGAN_ROWSUM_NHWC=1)
             K.conv_fprop(src, self._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, off,
                          cv.bias if bias else None, None, act_, mul)
 
