@@ -104,8 +104,20 @@ def train_args(batch):
         model_save_epoch=1, info_step=100, cuda_graph=False)
 
 
-# ------------------------------------------------------------------------------------------------ CPU (oracle port)
-def oracle_step_fn(workload, batch):
+# ------------------------------------------------------------------------------------------------ CPU / library baselines
+def reference_available():
+    from oracle.make_ref import ref_dir
+    return ref_dir() is not None
+
+
+def baseline_step_fn(workload, batch, device="cpu"):
+    """One iteration of the workload by the REFERENCE's own code (oracle/ref_step.py over the vendored oracle/_ref:
+    kind "reference"), or, if the vendored copy is missing, by the oracle port (kind "port", CPU only)."""
+    if reference_available():
+        from oracle import ref_step
+        return ref_step.make_step(workload, batch, device, RES), "reference"
+    if device != "cpu":
+        return None, None
     import torch
     from oracle import uegan_oracle as O
     gp = O.make_generator_params(32, 0, "o1")
@@ -114,27 +126,56 @@ def oracle_step_fn(workload, batch):
         def step():
             with torch.no_grad():
                 O.generator_forward(gp, x)
-        return step
+        return step, "port"
     dp, vp = O.make_discriminator_params(32, 1, "o1"), O.make_vgg_params()
     g_opt, d_opt = O.AdamState(O._trainable(gp)), O.AdamState(O._trainable(dp))
     y = O.make_images((batch, 3, RES, RES), 1)
 
     def step():
         O.train_step(gp, dp, vp, g_opt, d_opt, x, y)
-    return step
+    return step, "port"
 
 
 def cpu_rate(workload, batch, iters, threads, warm=0):
     import torch
     torch.set_num_threads(threads)
-    step = oracle_step_fn(workload, batch)
+    step, kind = baseline_step_fn(workload, batch)
     for _ in range(warm):
         step()
     t0 = time.perf_counter()
     for _ in range(iters):
         step()
     dt = time.perf_counter() - t0
-    return batch * iters / dt, dt
+    return batch * iters / dt, dt, kind
+
+
+def gpu_library_rate(workload, batch, iters=3, warm=2):
+    """The reference's own PyTorch code on THIS GPU: eager ATen + cuDNN, fp32 tensors with torch's default TF32 convolutions,
+    cudnn.benchmark=True (main.py:16) -- the existing kernels this repo has to beat on the same box."""
+    import torch
+    step, kind = baseline_step_fn(workload, batch, "cuda")
+    if step is None:
+        return None
+    try:
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        return {"value": batch / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "batch": batch, "kind": kind,
+                "what": "unmodified reference models.py/losses.py + torch.optim.Adam on cuda: eager PyTorch "
+                        f"{torch.__version__} + cuDNN {torch.backends.cudnn.version()}, cudnn.benchmark=True, "
+                        f"allow_tf32(conv)={torch.backends.cudnn.allow_tf32}, {iters} steps after {warm} warm-up"}
+    except Exception as e:  # noqa: BLE001 -- a baseline that cannot run must not take the native measurement down with it
+        return {"value": None, "error": f"{type(e).__name__}: {e}"[:300]}
+    finally:
+        del step
+        torch.cuda.empty_cache()
 
 
 def run_reference(args):
@@ -144,7 +185,7 @@ def run_reference(args):
     batch = 1 if args.workload == "train" else 2
     import torch
     torch.set_num_threads(threads)
-    step = oracle_step_fn(args.workload, batch)
+    step, kind = baseline_step_fn(args.workload, batch)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -154,14 +195,16 @@ def run_reference(args):
     ms = 1e3 * sum(times) / len(times)
     val = batch / (ms / 1e3)
     what = "training step (trainer.py:75-119)" if args.workload == "train" else "Generator.forward"
-    sample = f"oracle port of the {what}, {batch}x3x{RES}x{RES} per step, {threads} threads, fp32"
+    src = ("the unmodified reference modules (oracle/_ref: models.py, losses.py, torch.optim.Adam)" if kind == "reference"
+           else "oracle port")
+    sample = f"{src}, {what}, {batch}x3x{RES}x{RES} per step, {threads} threads, fp32"
     print(json.dumps({
         "impl": "reference", "metric": "512x512 training images/sec" if args.workload == "train" else "512x512 images/sec",
         "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": workload_name(args.workload), "batch_per_step": batch,
                                         "note": "CPU steps are a bounded sample of the GPU arm's per-step batch"},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -390,7 +433,9 @@ def run_native(args):
     if rank == 0:
         cpu_threads = os.cpu_count() or 1
         cpu_batch = 1 if train else 2
-        cpu_val, cpu_dt = cpu_rate(args.workload, cpu_batch, 1 if train else 2, cpu_threads, warm=0 if train else 1)
+        # the reference's own PyTorch/cuDNN path on this GPU (N = 1 runs only: the scaling runs stay short)
+        gpu_lib = gpu_library_rate(args.workload, batch) if (world == 1 and args.lib_baseline) else None
+        cpu_val, cpu_dt, cpu_kind = cpu_rate(args.workload, cpu_batch, 1 if train else 2, cpu_threads, warm=0 if train else 1)
         ms_step = ms_total / args.steps
         value = world * batch / (ms_step * 1e-3)
         e2e = world * batch / (ms_e2e / args.steps * 1e-3)
@@ -408,9 +453,11 @@ def run_native(args):
                        "frac_of_bf16_peak": gflop * value / world / 1e3 / tf_burst},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
-            "cpu_baseline": {"value": cpu_val, "unit": "images/s", "cores": cpu_threads, "kind": "port",
-                             "sample": f"oracle {'train_step' if train else 'Generator.forward'}, "
+            "cpu_baseline": {"value": cpu_val, "unit": "images/s", "cores": cpu_threads, "kind": cpu_kind,
+                             "sample": f"{'unmodified reference modules (oracle/_ref)' if cpu_kind == 'reference' else 'oracle port'}"
+                                       f" {'training step' if train else 'Generator.forward'}, "
                                        f"{1 if train else 2} iteration(s) of {cpu_batch}x3x512x512 ({cpu_dt:.1f} s)"},
+            "gpu_library_baseline": gpu_lib,
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -424,6 +471,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "inference", "sweep"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 16 train / 32 inference)")
+    ap.add_argument("--lib-baseline", dest="lib_baseline", type=int, default=1,
+                    help="also time the unmodified reference on the GPU (eager PyTorch + cuDNN), N = 1 only")
     ap.add_argument("--graph", type=int, default=1, help="capture the training step into a CUDA graph (1) or run eagerly (0)")
     args = ap.parse_args()
     if args.workload == "sweep":

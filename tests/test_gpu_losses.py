@@ -116,8 +116,8 @@ def test_perceptual_vs_golden_and_oracle():
     e = rel(loss, g["percep64"])
     print(f"perceptual 64x64: {float(loss):.6f} vs reference {float(g['percep64']):.6f} rel err {e:.3e}")
     assert e < 1e-3
-    e5 = rel(taps[4][0].interior_nchw(), g["vgg64_relu5_1"])
-    print(f"relu5_1 (bf16 tower) rel err {e5:.3e}")
+    e5 = rel(taps[4][0].interior_nchw() / P.vgg.tap_scale(4), g["vgg64_relu5_1"])  # stored = 2^k * true activation
+    print(f"relu5_1 (fp16 tower, stored scale {P.vgg.tap_scale(4):g}) rel err {e5:.3e}")
     assert e5 < 5e-2
     # larger size: exercises the statistics fused into the conv epilogue
     a = O.make_images((2, 3, 128, 160), 14)
@@ -128,3 +128,61 @@ def test_perceptual_vs_golden_and_oracle():
     e = rel(loss, ref)
     print(f"perceptual 128x160: {float(loss):.6f} vs oracle {float(ref):.6f} rel err {e:.3e}")
     assert e < 1e-3
+
+
+@pytest.mark.parametrize("factor", [16.0, 1.0 / 16.0, "alternating"])
+def test_perceptual_fp16_range_rescaled_tower(factor):
+    """the fp16 tower must not depend on the synthetic He-normal checkpoint's dynamic range.  Every conv
+    weight is multiplied by 16 (activations would reach 16^13 = 4.5e15 by relu5_1: far outside fp16), by 1/16 (2.2e-16:
+    flushed to zero), or alternately by 64 and 1/64; the power-of-two calibration (losses.VGG19_relu.calibrate) must keep
+    the loss, its image gradient and every tap within the same tolerances as the unscaled tower -- against the fp32 oracle
+    evaluated on the SAME rescaled weights (biases are rescaled with the cumulative factor so that the rescaled fp32
+    network is the original one up to per-layer scale; eps changes the loss only where s^2 * var ~ eps)."""
+    need_gpu()
+    from uegan_b200 import kernels as K
+    from uegan_b200.losses import PerceptualLoss
+    vp = {k: v.clone() for k, v in O.make_vgg_params().items()}
+    keys = sorted({int(k.split(".")[1]) for k in vp})
+    cum = 1.0
+    for j, idx in enumerate(keys):
+        f = factor if factor != "alternating" else (64.0 if j % 2 == 0 else 1.0 / 64.0)
+        cum *= f
+        vp[f"features.{idx}.weight"] *= f
+        vp[f"features.{idx}.bias"] *= cum
+    P = PerceptualLoss(vgg_state_dict=vp).cuda()
+    a = ((O.make_images((2, 3, 64, 64), 12) + 1) / 2)
+    b = ((O.make_images((2, 3, 64, 64), 13) + 1) / 2)
+    x = a.cuda().requires_grad_(True)
+    loss = P(x, b.cuda())
+    loss.backward()
+    assert K.device_error() == 0
+    taps, _ = P.vgg.run(a.cuda(), "x")
+    P.vgg.check_range(taps)  # the amax guard: must not raise on a calibrated tower
+    ad = a.double().clone().requires_grad_(True)
+    ref = O.perceptual_loss({k: v.double() for k, v in vp.items()}, ad, b.double())
+    ref.backward()
+    e = rel(loss, ref)
+    g_err = float((x.grad.double().cpu() - ad.grad).norm() / ad.grad.norm())
+    print(f"rescaled tower ({factor}): loss {float(loss):.6f} vs fp64 oracle {float(ref):.6f} rel {e:.2e}; "
+          f"dL/dx rel-L2 {g_err:.3f}; stored tap scales {[P.vgg.tap_scale(i) for i in range(5)]}")
+    assert torch.isfinite(loss) and torch.isfinite(x.grad).all()
+    assert e < 1e-3
+    assert g_err < 0.2  # same (mask-flip dominated) gate as the unscaled tower, tests/test_gpu_train.py
+
+
+def test_perceptual_amax_guard_raises():
+    """A tower whose activations left fp16's range after calibration (here: weights swapped under a stale calibration)
+    is reported by check_range instead of saturating silently."""
+    need_gpu()
+    from uegan_b200 import _lib
+    from uegan_b200.losses import PerceptualLoss
+    P = PerceptualLoss(vgg_state_dict=O.make_vgg_params()).cuda()
+    a = ((O.make_images((1, 3, 64, 64), 3) + 1) / 2).cuda()
+    taps, _ = P.vgg.run(a, "x")
+    P.vgg.check_range(taps)
+    c = P.vgg._calib[0]
+    P.vgg._calib[0] = (c[0], c[1], c[2] * 4096.0, c[3] * 4096.0, c[4])  # conv1_1 output x4096 -> overflow downstream
+    P.vgg._wcache.clear()
+    taps, _ = P.vgg.run(a, "x")
+    with pytest.raises(_lib.UeganError):
+        P.vgg.check_range(taps)

@@ -1,0 +1,212 @@
+"""Whole backward chains with the activation masks PINNED (ADVICE `tests/test_gpu_train.py:100`).
+
+Gradients of (Leaky)ReLU networks are discontinuous in the forward values: an element whose pre-activation lies within
+the forward rounding error of zero flips its mask, which is why the end-to-end gradient tests carry loose norm / cosine
+gates.  Here the discontinuity is removed instead: the native forward runs first, its activation SIGNS (and max-pool
+routes, and the output-clamp mask) are read back from its workspace, and the oracle chain is re-evaluated in fp64 with
+those masks as constants (`y = z * slope_mask` instead of `leaky_relu(z)`).  Both sides then differentiate the SAME
+piecewise-linear network, every remaining difference is arithmetic (tf32 / fp16 operand rounding, accumulation order),
+and a systematic error in any backward kernel (a wrong `local` factor, a missing term of grad_combine, the fixed VGG loss
+scale, ...) shows up at full size.  Gates: G and D (tf32) 2e-3 rel-L2 on EVERY parameter gradient and on dL/dx;
+VGG (fp16, 13 layers deep) 5e-3 on dL/dx.  Measured values are printed.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import uegan_oracle as O
+
+pytestmark = pytest.mark.gpu
+DT = torch.float64
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-300))
+
+
+def slope(native_act, neg=0.2):
+    """d act / d z as a constant tensor, from the sign of the native activation (LeakyReLU keeps the sign)."""
+    m = torch.where(native_act > 0, torch.ones_like(native_act), torch.full_like(native_act, neg))
+    return m.to(DT).cpu()
+
+
+def pin(z, mask):
+    return z * mask
+
+
+def rconv(x, w, b, stride=1):
+    pad = (w.shape[-1] - 1) // 2
+    if pad:
+        x = F.pad(x, (pad, pad, pad, pad), mode="reflect")
+    return F.conv2d(x, w, b, stride=stride)
+
+
+# ------------------------------------------------------------------------------------------------ Generator
+@pytest.mark.parametrize("regime", ["o1", "tiny"])
+def test_generator_backward_chain_pinned(regime):
+    from uegan_b200 import kernels as K
+    from uegan_b200.models import Generator
+    gp = O.make_generator_params(32, 0, regime)
+    G = Generator(32, "none", "LeakyReLU", False)
+    G.load_state_dict(gp)
+    G = G.cuda().train()
+    b, h, w = 2, 128, 128
+    x = O.make_images((b, 3, h, w), 7).cuda().requires_grad_(True)
+    gout = O.make_images((b, 3, h, w), 8).cuda()
+    out = G(x)
+    out.backward(gout)
+    assert K.device_error() == 0
+    ws = G._train_pool[(b, h, w, str(x.device))][-1]
+    A = lambda t: t.interior_nchw()
+    masks = dict(x1=slope(A(ws["x1"])), x2=slope(A(ws["x2"])), x3=slope(A(ws["x3"])), x4=slope(A(ws["x4"])),
+                 x5=slope(A(ws["x5"])), y1=slope(A(ws["y"][0])), y2=slope(A(ws["y"][1])), y3=slope(A(ws["y"][2])),
+                 y4=slope(A(ws["y"][3])))
+    res_native = ws["res"].detach().to(DT).cpu()
+    xin = x.detach().to(DT).cpu()
+    clamp_mask = ((res_native + xin).abs() <= 1.0).to(DT)  # head_bwd mode 2 / torch.clamp: inclusive
+
+    p = {k: v.to(DT).clone().requires_grad_(True) for k, v in gp.items()}
+    xo = xin.clone().requires_grad_(True)
+
+    def block(name, t, key, stride=1):
+        return pin(rconv(t, p[name + ".weight"], p[name + ".bias"], stride), masks[key])
+
+    def up(name, t):
+        t = F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True)
+        return F.conv2d(t, p[name + ".weight"], p[name + ".bias"])
+
+    def gam(pre, t):  # full form (models.py:230-237): the dead branch gets its (rounding-noise) gradient, unused below
+        c = t.shape[1]
+        z = F.conv2d(t, p[pre + ".fuse.0.weight"][:, :c])
+        mu = z.mean(dim=(2, 3), keepdim=True)
+        var = z.var(dim=(2, 3), unbiased=False, keepdim=True)
+        return (z - mu) / torch.sqrt(var + 1e-5)
+
+    x1 = block("enc1.main.1", xo, "x1")
+    x2 = block("enc2.main.1", x1, "x2", 2)
+    x3 = block("enc3.main.1", x2, "x3", 2)
+    x4 = block("enc4.main.1", x3, "x4", 2)
+    x5 = block("enc5.main.1", x4, "x5", 2)
+    x5 = gam("ga5", x5)
+    y1 = block("dec1.main.1", torch.cat([up("upsample1.1.main.1", x5), gam("ga4", x4)], 1), "y1")
+    y2 = block("dec2.main.1", torch.cat([up("upsample2.1.main.1", y1), gam("ga3", x3)], 1), "y2")
+    y3 = block("dec3.main.1", torch.cat([up("upsample3.1.main.1", y2), gam("ga2", x2)], 1), "y3")
+    y4 = block("dec4.main.1", torch.cat([up("upsample4.1.main.1", y3), gam("ga1", x1)], 1), "y4")
+    t = rconv(y4 * x1, p["dec5.0.main.1.weight"], p["dec5.0.main.1.bias"])
+    res = torch.tanh(rconv(t, p["dec5.1.main.1.weight"], p["dec5.1.main.1.bias"]))
+    # clamp(res + x, -1, 1) with the native clamp mask as a constant (models.py:72)
+    o = (res + xo) * clamp_mask
+    o.backward(gout.to(DT).cpu())
+
+    worst = ("", 0.0)
+    native = {n: q.grad for n, q in G.named_parameters()}
+    for name in gp:
+        if ".conv.0." in name or ".conv.2." in name or name.endswith("fuse.0.bias"):
+            assert float(native[name].abs().max()) == 0.0, name  # dead parameters: exact zero
+            continue
+        ref = p[name].grad
+        got = native[name].detach().to(DT).cpu()
+        if "fuse.0.weight" in name:  # only the live half [:, :C] carries gradient
+            c = ref.shape[1] // 2
+            assert float(got[:, c:].abs().max()) == 0.0, name
+            ref, got = ref[:, :c], got[:, :c]
+        e = rel_l2(got, ref)
+        if e > worst[1]:
+            worst = (name, e)
+        assert e < 2e-3, f"{regime} {name}: rel-L2 {e:.3e}"
+    e_dx = rel_l2(x.grad, xo.grad)
+    print(f"[{regime}] G pinned chain: worst parameter gradient {worst[0]} {worst[1]:.3e}; dL/dx {e_dx:.3e}")
+    assert e_dx < 2e-3, e_dx
+
+
+# ------------------------------------------------------------------------------------------------ Discriminator
+@pytest.mark.parametrize("regime", ["o1", "tiny"])
+def test_discriminator_backward_chain_pinned(regime):
+    from uegan_b200 import kernels as K
+    from uegan_b200.models import Discriminator
+    dp = O.make_discriminator_params(32, 1, regime)
+    D = Discriminator(32, "none", "LeakyReLU", True, "rahinge")
+    D.load_state_dict(dp)
+    D = D.cuda().train()
+    b, h, w = 2, 128, 128
+    x = O.make_images((b, 3, h, w), 9).cuda().requires_grad_(True)
+    preds = D(x)
+    gouts = [O.make_images(tuple(q.shape), 20 + i).cuda() for i, q in enumerate(preds)]
+    torch.autograd.backward(preds, gouts)
+    assert K.device_error() == 0
+    ws = D._train_pool[(b, h, w, str(x.device))][-1]
+    masks = [slope(t.interior_nchw()) for t in ws["ds"]]
+
+    p = {k: v.to(DT).clone() for k, v in dp.items()}
+    for k in p:
+        if not (k.endswith("weight_u") or k.endswith("weight_v")):
+            p[k].requires_grad_(True)
+    xo = x.detach().to(DT).cpu().clone().requires_grad_(True)
+    hcur, outs = xo, []
+    for k in range(1, 6):
+        wsn, u, v, _ = O.spectral_norm_weight(p[f"d{k}.0.1.weight_orig"], p[f"d{k}.0.1.weight_u"],
+                                              p[f"d{k}.0.1.weight_v"], True)
+        hcur = pin(rconv(hcur, wsn, p[f"d{k}.0.1.bias"], 2), masks[k - 1])
+        outs.append(torch.tanh(rconv(hcur, p[f"d{k}_pred.0.1.weight"], None)))
+    torch.autograd.backward(outs, [g.to(DT).cpu() for g in gouts])
+    worst = ("", 0.0)
+    for name, q in D.named_parameters():
+        e = rel_l2(q.grad, p[name].grad)
+        if e > worst[1]:
+            worst = (name, e)
+        assert e < 2e-3, f"{regime} {name}: rel-L2 {e:.3e}"
+    e_dx = rel_l2(x.grad, xo.grad)
+    print(f"[{regime}] D pinned chain: worst parameter gradient {worst[0]} {worst[1]:.3e}; dL/dx {e_dx:.3e}")
+    assert e_dx < 2e-3, e_dx
+
+
+# ------------------------------------------------------------------------------------------------ VGG / PerceptualLoss
+def test_perceptual_backward_chain_pinned():
+    from uegan_b200 import kernels as K
+    from uegan_b200.losses import _VGG_LAYERS, PerceptualLoss
+    vp = O.make_vgg_params()
+    P = PerceptualLoss(vgg_state_dict=vp).cuda()
+    b, h, w = 2, 128, 128
+    x = (O.make_images((b, 3, h, w), 11).cuda() * 0.5 + 0.5).requires_grad_(True)
+    y = O.make_images((b, 3, h, w), 12).cuda() * 0.5 + 0.5
+    loss = P(x, y)
+    loss.backward()
+    assert K.device_error() == 0
+    acts = P.vgg._plans[(b, h, w, str(x.device), "x")]["acts"]  # acts[li + 1] = output of _VGG_LAYERS[li]
+    nat = [a.interior_nchw() for a in acts]
+
+    mean = torch.tensor(O.IMAGENET_MEAN, dtype=DT).view(1, -1, 1, 1)
+    std = torch.tensor(O.IMAGENET_STD, dtype=DT).view(1, -1, 1, 1)
+    v64 = {k: t.to(DT) for k, t in vp.items()}
+
+    def tower(img, pinned):
+        hcur, taps = (img - mean) / std, []
+        for li, spec in enumerate(_VGG_LAYERS):
+            if spec == "M":
+                if pinned:  # route through the native arg-max positions
+                    _, idx = F.max_pool2d(nat[li].to(DT).cpu(), 2, 2, return_indices=True)
+                    flat = hcur.flatten(2)
+                    hcur = flat.gather(2, idx.flatten(2)).view(idx.shape)
+                else:
+                    hcur = F.max_pool2d(hcur, 2, 2)
+                continue
+            idx_, cin, cout = spec
+            z = F.conv2d(hcur, v64[f"features.{idx_}.weight"], v64[f"features.{idx_}.bias"], padding=1)
+            hcur = z * (nat[li + 1] > 0).to(DT).cpu() if pinned else F.relu(z)
+            if idx_ in (0, 5, 10, 19, 28):
+                taps.append(hcur)
+        return taps
+
+    xo = x.detach().to(DT).cpu().clone().requires_grad_(True)
+    tx, ty = tower(xo, True), tower(y.detach().to(DT).cpu(), False)
+    lo = 0
+    for wgt, a, c in zip([1.0 / 64, 1.0 / 64, 1.0 / 32, 1.0 / 32, 1.0], tx, ty):
+        lo = lo + wgt * F.mse_loss(O.instance_norm(a), O.instance_norm(c))
+    lo.backward()
+    e_loss = abs(float(loss) - float(lo)) / abs(float(lo))
+    e_dx = rel_l2(x.grad, xo.grad)
+    cos = float(F.cosine_similarity(x.grad.detach().double().cpu().flatten(), xo.grad.flatten(), dim=0))
+    print(f"VGG pinned chain: loss rel err {e_loss:.3e}; dL/dx rel-L2 {e_dx:.3e}, cosine {cos:.6f}")
+    assert e_loss < 1e-3
+    assert e_dx < 5e-3 and cos > 0.9999, (e_dx, cos)

@@ -75,3 +75,48 @@ def test_train_step_512_losses_vs_oracle():
     print(f"512x512 step: losses {['%.6f' % v for v in losses]} ref {['%.6f' % v for v in ref]} rel {['%.2e' % e for e in errs]}")
     assert all(np.isfinite(losses))
     assert max(errs) < 1e-3  # north_star: 1e-3 relative on loss scalars
+
+
+def test_config1_generator_inference_b32_512():
+    """BASELINE.json configs[1] at its FULL size: Generator inference on 32 x 3x512x512.  Images are independent through the
+    Generator, so the oracle checks a sample of the batch (first, middle, last) directly (1e-3 on pixels, north_star) and a
+    size-independent property covers the rest: every image of the big batch equals the same image run in a batch of its own."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from uegan_b200 import kernels as K
+    G = _generator()
+    x = O.make_images((32, 3, 512, 512), 23)
+    gp = O.make_generator_params(32, 0, "o1")
+    with torch.no_grad():
+        out = G(x.cuda()).clone()
+        for i in (0, 13, 31):
+            ref = O.generator_forward(gp, x[i:i + 1])
+            l2 = _rel_l2(out[i:i + 1].cpu(), ref)
+            print(f"configs[1] 32x3x512x512, image {i}: pixel rel-L2 vs oracle {l2:.3e}")
+            assert l2 < 1e-3
+        for i in (5, 20):
+            solo = G(x[i:i + 1].cuda())
+            assert float((solo - out[i:i + 1]).abs().max()) <= 1e-6, i
+    assert K.device_error() == 0
+
+
+def test_config4_generator_1024x1536_vs_oracle():
+    """BASELINE.json configs[4] (mixed-resolution sweep): its largest shape, 1024 x 1536 (non-square, 3x the pixels of a tile
+    grid the 512^2 cases exercise), against the oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from uegan_b200 import kernels as K
+    G = _generator()
+    x = O.make_images((1, 3, 1024, 1536), 24)
+    with torch.no_grad():
+        out = G(x.cuda()).cpu()
+        ref = O.generator_forward(O.make_generator_params(32, 0, "o1"), x)
+    assert K.device_error() == 0
+    l2 = _rel_l2(out, ref)
+    print(f"configs[4] 1x3x1024x1536: pixel rel-L2 {l2:.3e}")
+    assert l2 < 1e-3
+    x2 = O.make_images((3, 3, 256, 384), 25)
+    with torch.no_grad():
+        l2 = _rel_l2(G(x2.cuda()).cpu(), O.generator_forward(O.make_generator_params(32, 0, "o1"), x2))
+    print(f"configs[4] 3x3x256x384: pixel rel-L2 {l2:.3e}")
+    assert l2 < 1e-3

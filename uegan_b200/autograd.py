@@ -280,8 +280,12 @@ class _GeneratorFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         G = ctx.module
+        if ctx.ws is None:
+            raise RuntimeError("uegan_b200: second backward through the same Generator forward (its activation "
+                               "workspace has been recycled); run the forward again")
         grads, dx = _g_backward(G, ctx.x, gout.contiguous().float(), ctx.ws, ctx.needs_input_grad[1])
         G._train_pool[ctx.key].append(ctx.ws)
+        ctx.ws = None
         names = [n for n, _ in G.named_parameters()]
         return (None, dx) + tuple(grads[n] for n in names)
 
@@ -426,9 +430,13 @@ class _DiscriminatorFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *dpreds):
         D = ctx.module
+        if ctx.ws is None:
+            raise RuntimeError("uegan_b200: second backward through the same Discriminator forward (its activation "
+                               "workspace has been recycled); run the forward again")
         need_w = any(ctx.needs_input_grad[2:])
         grads, dx = _d_backward(D, ctx.x, dpreds, ctx.ws, ctx.needs_input_grad[1], need_w)
         D._train_pool[ctx.key].append(ctx.ws)
+        ctx.ws = None
         names = [n for n, _ in D.named_parameters()]
         return (None, dx) + tuple(grads.get(n) for n in names)
 
@@ -526,6 +534,9 @@ class _PerceptualFn(torch.autograd.Function):
         # far below fp16's range; S makes the deepest tap's gradient O(1) (the others are <= 2^-11 of that), and is
         # divided out when the image gradient is unpacked.  fp16 keeps 10 mantissa bits (bf16's 8 cost 12 % rel-L2).
         t5 = ctx.taps_x[4][0]
+        # (the stored tower -- power-of-two factors folded into the weights, losses.VGG19_relu -- computes the same loss as
+        # a function of the image, with O(1..32) activations at every layer whatever the checkpoint's own magnitudes are;
+        # its gradient w.r.t. the image IS the true one, so no factor rides along.)
         scale = float(t5.n * t5.c * t5.h * t5.w) / (2.0 * module.weights[4])
         # gradient buffers are zero-initialised once: nobody writes their halo, which is the dgrad's zero padding
         if "grads" not in P:
@@ -557,13 +568,11 @@ class _PerceptualFn(torch.autograd.Function):
                 dz = dzt
             else:
                 dz = G[out_idx]  # masked by the producer (dgrad epilogue mask or max-pool backward)
-            conv = vgg.features[idx]
             src = acts[li]
             key = ("vgg_dg", idx)
-            tag = (conv.weight.data_ptr(), conv.weight._version)
             hit = vgg._wcache.get(key)
-            if hit is None or hit[0] != tag:
-                hit = (tag, K.packed_weight_dgrad(conv.weight, dz.c, L.F16, 1, 0, 0))
+            if hit is None:
+                hit = (None, K.packed_weight_dgrad(vgg.layer(idx)[0], dz.c, L.F16, 1, 0, 0))
                 vgg._wcache[key] = hit
             # the producer of `src`: a conv (ReLU mask needed, unless it is a tap, masked later) or a pool / the input
             prev_is_conv = li > 0 and _VGG_LAYERS[li - 1] != "M"

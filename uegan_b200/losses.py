@@ -22,8 +22,18 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 
 class VGG19_relu(nn.Module):
     """Frozen VGG-19 feature tower up to relu5_1 (losses.py:39-164), fp16 storage / kind::f16 MMAs with fp32
-    accumulation (10-bit operands like tf32, at the full 16-bit tensor rate; bf16 misses the 1e-3 loss tolerance).  The reference also evaluates relu5_2..5_4,
-    whose outputs nothing reads (losses.py:30-34); they are not computed here."""
+    accumulation (10-bit operands like tf32, at the full 16-bit tensor rate; bf16 misses the 1e-3 loss tolerance).  The
+    reference also evaluates relu5_2..5_4, whose outputs nothing reads (losses.py:30-34); they are not computed here.
+
+    Range: fp16 has 11 significant bits but only 2^-14 .. 2^16 of normal range, and the magnitudes inside a VGG depend
+    on the checkpoint.  The tower is frozen and ReLU / max-pool are positively homogeneous, so every conv carries a
+    POWER-OF-TWO factor f_l folded into its packed weight and bias: stored activation = s_l * true activation with
+    s_l = f_1 ... f_l, chosen once (`calibrate`, first batch) so that each layer's largest stored value sits near 2^5.
+    Powers of two commute with fp16 / fp32 rounding, so stored values carry exactly the bits the unscaled fp32-range
+    computation would; InstanceNorm + MSE at the taps is scale-invariant except for eps, which becomes eps * s_l^2.
+    `check_range` is the guard: it raises when a tap left the safe window instead of letting fp16 saturate silently."""
+
+    TARGET_AMAX = 32.0
 
     def __init__(self, state_dict=None):
         super().__init__()
@@ -39,16 +49,85 @@ class VGG19_relu(nn.Module):
             p.requires_grad = False
         self._plans = {}
         self._wcache = {}
+        self._calib = None  # {features idx: (tag, factor f_l, cumulative scale s_l, f_l * weight, s_l * bias)}
+
+    # ---------------------------------------------------------------- power-of-two range folding
+    def _tag(self):
+        return tuple((self.features[spec[0]].weight.data_ptr(), self.features[spec[0]].weight._version)
+                     for spec in _VGG_LAYERS if spec != "M")
+
+    def layer(self, idx):
+        """(effective fp32 weight, effective bias, cumulative scale) of the conv at features[idx]."""
+        c = self._calib[idx]
+        return c[2], c[3], c[1]
+
+    def tap_scale(self, ti):
+        return self._calib[_TAP_IDX[ti]][1]
+
+    @torch.no_grad()
+    def calibrate(self, x01):
+        """Chooses the per-layer power-of-two factors on the batch x01 (layer by layer: run, read the largest stored
+        value back, adjust, re-run).  One-off host-synchronising work; the tower is frozen afterwards."""
+        import math
+        b, _, h, w = x01.shape
+        P = self._plan(b, h, w, x01.device, "x")
+        acts = P["acts"]
+        scale = [1.0 / s for s in IMAGENET_STD]
+        shift = [-m / s for m, s in zip(IMAGENET_MEAN, IMAGENET_STD)]
+        K.pack_input(x01.contiguous().float(), acts[0], L.PAD_ZERO, scale, shift)
+        calib, s_prev = {}, 1.0
+        for li, spec in enumerate(_VGG_LAYERS):
+            src, dst = acts[li], acts[li + 1]
+            if spec == "M":
+                K.maxpool2x2(src, dst)
+                continue
+            idx, cin, cout = spec
+            conv = self.features[idx]
+            f = 1.0
+            for attempt in range(24):
+                w_eff = (conv.weight.detach() * f).contiguous()
+                b_eff = (conv.bias.detach() * (s_prev * f)).contiguous()
+                wp = K.packed_weight(w_eff, src.c, L.F16)
+                K.conv_fprop(src, wp, cout, 3, 1, 1, dst, 0, b_eff, None, L.ACT_RELU)
+                amax = float(dst.padded_view().float().abs().max())
+                if not math.isfinite(amax) or amax > 2.0 ** 15:
+                    f *= 2.0 ** -8
+                elif amax == 0.0:
+                    if attempt >= 6:  # a dead layer: nothing to scale
+                        break
+                    f *= 2.0 ** 8
+                else:
+                    g = 2.0 ** round(math.log2(self.TARGET_AMAX / amax))
+                    if g == 1.0:
+                        break
+                    f *= g
+            else:
+                raise L.UeganError(f"VGG19_relu.calibrate: features[{idx}] does not settle in fp16 range")
+            calib[idx] = (None, s_prev * f, w_eff, b_eff, f)
+            s_prev *= f
+        self._calib, self._calib_tag = calib, self._tag()
+        self._wcache.clear()
+        for pl in self._plans.values():
+            pl.pop("grads", None)
+
+    @torch.no_grad()
+    def check_range(self, taps):
+        """Raises if a tap's largest stored value left [2^-6, 2^15): the amax guard against silent fp16 saturation /
+        underflow (host-synchronising; call it when a loss looks suspicious or periodically, not every step)."""
+        import math
+        for ti, (t, _) in enumerate(taps):
+            amax = float(t.padded_view().float().abs().max())
+            if not math.isfinite(amax) or amax >= 2.0 ** 15 or (0.0 < amax < 2.0 ** -6):
+                raise L.UeganError(f"VGG19_relu: tap relu{ti + 1}_1 has |max| = {amax:g} in fp16 storage "
+                                   f"(scale 2^{math.log2(self.tap_scale(ti)):.0f}); call calibrate() on a representative batch")
 
     def _packed(self, idx, cin_stored):
         key = (idx, cin_stored)
-        conv = self.features[idx]
-        tag = (conv.weight.data_ptr(), conv.weight._version)
         hit = self._wcache.get(key)
-        if hit is None or hit[0] != tag:
-            hit = (tag, K.packed_weight(conv.weight, cin_stored, L.F16))
+        if hit is None:
+            hit = K.packed_weight(self.layer(idx)[0], cin_stored, L.F16)
             self._wcache[key] = hit
-        return hit[1]
+        return hit
 
     def _plan(self, b, h, w, device, slot):
         key = (b, h, w, str(device), slot)
@@ -74,6 +153,8 @@ class VGG19_relu(nn.Module):
         b, _, h, w = x01.shape
         if h % 16 or w % 16:
             raise ValueError("PerceptualLoss needs H, W multiples of 16")
+        if self._calib is None or self._calib_tag != self._tag():
+            self.calibrate(x01)
         P = self._plan(b, h, w, x01.device, slot)
         acts = P["acts"]
         scale = [1.0 / s for s in IMAGENET_STD]
@@ -86,13 +167,14 @@ class VGG19_relu(nn.Module):
                 K.maxpool2x2(src, dst)
                 continue
             idx, cin, cout = spec
-            conv = self.features[idx]
+            _, b_eff, s_l = self.layer(idx)
             is_tap = idx in _TAP_IDX
             fused = is_tap and K.fused_stats_ok(dst.h, dst.w, cout)
-            K.conv_fprop(src, self._packed(idx, src.c), cout, 3, 1, 1, dst, 0, conv.bias, None, L.ACT_RELU,
+            K.conv_fprop(src, self._packed(idx, src.c), cout, 3, 1, 1, dst, 0, b_eff, None, L.ACT_RELU,
                          in_stats=P["stats"][ti] if fused else None)
             if is_tap:
-                mr = K.instance_norm_stats(dst, P["stats"][ti], sums_ready=fused, eps=eps)
+                # InstanceNorm of the TRUE activation: eps scales with the square of the stored scale
+                mr = K.instance_norm_stats(dst, P["stats"][ti], sums_ready=fused, eps=eps * s_l * s_l)
                 taps.append((dst, mr))
                 ti += 1
         return taps, P
@@ -115,7 +197,11 @@ class PerceptualLoss(nn.Module):
             x, y = x.repeat(1, 3, 1, 1), y.repeat(1, 3, 1, 1)
         if self.vgg.features[0].weight.device != x.device:
             self.vgg.to(x.device)
-        if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad):
+        if torch.is_grad_enabled() and y.requires_grad:
+            # the trainer compares fake_exp with the DETACHED input (trainer.py:108); a gradient w.r.t. the second
+            # argument is not implemented natively and must not be dropped silently
+            raise NotImplementedError("uegan_b200.losses.PerceptualLoss: the second argument must not require grad")
+        if torch.is_grad_enabled() and x.requires_grad:
             from .autograd import perceptual_apply
             return perceptual_apply(self, x, y)
         return self.forward_native(x, y)
@@ -181,6 +267,8 @@ class MultiscaleRecLoss(nn.Module):
     def forward(self, input, target):
         if not (input.is_cuda and target.is_cuda):
             raise L.UeganError("uegan_b200.losses.MultiscaleRecLoss runs on CUDA (sm_100a) only; no CPU fallback")
+        if torch.is_grad_enabled() and target.requires_grad:
+            raise NotImplementedError("uegan_b200.losses.MultiscaleRecLoss: the target must not require grad")
         if torch.is_grad_enabled() and input.requires_grad:
             from .autograd import msrec_apply
             return msrec_apply(self, input, target)
@@ -189,3 +277,18 @@ class MultiscaleRecLoss(nn.Module):
         loss = torch.empty(1, dtype=torch.float32, device=pred.device)
         K.msrec_loss(pred, gt, self.rec_type, self.scales, accum, loss)
         return loss[0]
+
+
+class TVLoss(nn.Module):
+    """losses.py:167-184.  Imported by tester.py:9 but called nowhere in the reference (not on the hot path, SURVEY.md 2);
+    kept so that `from losses import PerceptualLoss, TVLoss` resolves.  Plain tensor arithmetic on the caller's device."""
+
+    def __init__(self, tv_loss_weight=1):
+        super().__init__()
+        self.tv_loss_weight = tv_loss_weight
+
+    def forward(self, x):
+        b, c, h, w = x.shape
+        h_tv = (x[:, :, 1:, :] - x[:, :, :h - 1, :]).pow(2).sum()
+        w_tv = (x[:, :, :, 1:] - x[:, :, :, :w - 1]).pow(2).sum()
+        return self.tv_loss_weight * 2 * (h_tv / (c * (h - 1) * w) + w_tv / (c * h * (w - 1))) / b

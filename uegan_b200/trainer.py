@@ -254,7 +254,7 @@ class Trainer(object):
                           str(time.time() - t0), step + 1, total_steps, step + 1, total_steps, vals["d_loss"],
                           vals["g_loss"], vals["g_percep_loss"], vals["g_adv_loss"], vals["g_idt_loss"]))
             if (step + 1) % save_step == 0:
-                self.save_checkpoint((step + 1) // steps_per_epoch)
+                self.save_checkpoint((step + 1) / steps_per_epoch)  # float epoch, trainer.py:163,205
             if a.lr_decay and step % steps_per_epoch == 0:
                 epoch = step // steps_per_epoch
                 self.lr_scheduler_g.step(epoch=epoch)
