@@ -244,11 +244,30 @@ int uegan_unpack_input_grad(const uegan_tensor* dx, const float* scale_host, flo
 int uegan_spectral_bwd(float* grad_inout, const float* w, const float* u, const float* v, const float* sigma,
                        int32_t rows, int32_t cols, double* ws, void* stream);
 
-/* Hardware probe used by tests/DESIGN.md: runs a 128xNx(32*kchunks) tf32 GEMM whose A operand is read from a
- * shared-memory window shifted by `row_shift` 128-byte rows with the given descriptor base_offset; see
- * csrc/probe.cu.  out: 128*n floats. */
-int uegan_probe_umma_window(const float* a, const float* b, float* out, int32_t a_rows, int32_t n, int32_t kchunks,
-                            int32_t row_shift, int32_t base_offset, int32_t sbo_bytes, void* stream);
+/* ---- the conversions either side of the hot path -------------------------------------------------
+ * uint8 HWC RGB batch (n x h x w x 3, device memory) -> what transforms.ToTensor() + Normalize(mean, std) produce
+ * (data_loader.py:79-81,100-103: mean = std = 0.5; losses.py:26-27: ImageNet constants), bit for bit:
+ *   v = ((float)u8 / 255 - mean[c]) / std[c]
+ * written (a) into dst, an NHWC activation tensor whose halo is filled with pad_mode (the Generator / Discriminator / VGG
+ * input operand; channels >= 3 are zero; dst may be NULL) and (b) as fp32 NCHW planes x_nchw_out (the tensor the
+ * reference's loader yields: residual of models.py:72, target of the losses; may be NULL). */
+int uegan_pack_input_u8(const uint8_t* img_nhwc_u8, int32_t n, int32_t h, int32_t w, const uegan_tensor* dst,
+                        float* x_nchw_out, int32_t pad_mode, const float* mean_host, const float* std_host, void* stream);
+/* fp32 NCHW in [-1, 1] -> uint8 HWC as the Tester writes it: denorm (utils.py:128-130) = clamp((x + 1) / 2, 0, 1), then
+ * torchvision.utils.save_image's quantisation clamp(v * 255 + 0.5, 0, 255) -> uint8 (tester.py:70-75), bit for bit. */
+int uegan_unpack_output_u8(const float* x_nchw, uint8_t* out_nhwc_u8, int32_t n, int32_t c, int32_t h, int32_t w,
+                           void* stream);
+
+/* ---- validation metrics on uint8 HWC image pairs ----------------------------------------------------
+ * Sum of squared differences over the image minus a `crop`-pixel border, per image, as an exact integer
+ * (metrics/CalcPSNR.py:47-52,85-92: PSNR = 10 log10(255^2 / (sse / count)), count = (h-2crop)(w-2crop)c). */
+int uegan_sse_u8(const uint8_t* a_nhwc, const uint8_t* b_nhwc, int32_t n, int32_t h, int32_t w, int32_t c, int32_t crop,
+                 uint64_t* sse_out, void* stream);
+/* Sum over channels and valid pixels of the SSIM map of skimage.metrics.structural_similarity(multichannel=True,
+ * data_range=255) -- 7x7 uniform window, sample covariance, K1 = 0.01, K2 = 0.03 -- evaluated on the image minus a
+ * `crop`-pixel border (metrics/CalcSSIM.py:47-62); mssim = sum / ((h-2crop-6)(w-2crop-6)c).  fp64. */
+int uegan_ssim_u8(const uint8_t* a_nhwc, const uint8_t* b_nhwc, int32_t n, int32_t h, int32_t w, int32_t c, int32_t crop,
+                  double* ssim_sum_out, void* stream);
 
 #ifdef __cplusplus
 }

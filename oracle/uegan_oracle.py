@@ -531,3 +531,46 @@ def calculate_psnr(img1: np.ndarray, img2: np.ndarray, data_range: float = 255.0
     if mse == 0:
         return float("inf")
     return float(10 * np.log10((data_range ** 2) / mse))
+
+
+def structural_similarity(im1: np.ndarray, im2: np.ndarray, data_range: float = 255.0) -> float:
+    """skimage.metrics.structural_similarity(im1, im2, multichannel=True, data_range=255) as metrics/CalcSSIM.py:62 calls
+    it: the algorithm lives in the third-party dependency scikit-image (absent from /root/reference and from this image;
+    the reference README pins no version -- the `multichannel=` keyword fixes it to 0.16 <= v < 0.19), restated here from
+    its published source (skimage/metrics/_structural_similarity.py): win_size 7, uniform window through
+    scipy.ndimage.uniform_filter, use_sample_covariance=True, K1 = 0.01, K2 = 0.03, mean of the SSIM map cropped by
+    (win_size - 1) // 2, averaged over channels.  PARITY UNPINNED for this function (no skimage to run, the reference holds
+    no SSIM fixture); it is anchored by its closed-form properties in tests/test_oracle.py."""
+    from scipy.ndimage import uniform_filter
+    assert im1.shape == im2.shape and im1.ndim == 3
+    win, k1, k2 = 7, 0.01, 0.03
+    npix = win * win
+    cov_norm = npix / (npix - 1.0)
+    c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+    pad = (win - 1) // 2
+    vals = []
+    for ch in range(im1.shape[2]):
+        x, y = im1[..., ch].astype(np.float64), im2[..., ch].astype(np.float64)
+        ux, uy = uniform_filter(x, size=win), uniform_filter(y, size=win)
+        uxx, uyy, uxy = uniform_filter(x * x, size=win), uniform_filter(y * y, size=win), uniform_filter(x * y, size=win)
+        vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+        a1, a2, b1, b2 = 2 * ux * uy + c1, 2 * vxy + c2, ux ** 2 + uy ** 2 + c1, vx + vy + c2
+        s = (a1 * a2) / (b1 * b2)
+        vals.append(s[pad:-pad, pad:-pad].mean(dtype=np.float64))
+    return float(np.mean(vals))
+
+
+def psnr_ssim_pair(gen_u8_hwc: np.ndarray, gt_u8_hwc: np.ndarray, crop_border: int = 4) -> Tuple[float, float]:
+    """What calc_psnr / calc_ssim compute for one image pair (metrics/CalcPSNR.py:35-58, CalcSSIM.py:35-62): images / 255,
+    border crop, * 255, then the metric."""
+    a, b = gt_u8_hwc / 255., gen_u8_hwc / 255.
+    a, b = a[crop_border:-crop_border, crop_border:-crop_border, :], b[crop_border:-crop_border, crop_border:-crop_border, :]
+    return calculate_psnr(a * 255, b * 255), structural_similarity(a * 255, b * 255)
+
+
+def to_tensor_normalize_imagenet(img_u8_hwc: np.ndarray) -> Tensor:
+    """ToTensor() followed by the ImageNet normalisation PerceptualLoss applies to a [0, 1] image (losses.py:19-20,26-27)."""
+    x = torch.from_numpy(np.ascontiguousarray(img_u8_hwc)).permute(2, 0, 1).to(torch.float32).div(255.0)
+    mean = torch.tensor(IMAGENET_MEAN).view(-1, 1, 1)
+    std = torch.tensor(IMAGENET_STD).view(-1, 1, 1)
+    return (x - mean) / std

@@ -8,8 +8,8 @@
 // B: n x 32 fp32, canonical K-major SWIZZLE_128B at a 1024-aligned address.
 // D[m][j] = sum_k A[row(m)][k] * B[j][k],  row(m) = row_shift + (m / 8) * (sbo_bytes / 128) + m % 8  -- if the
 // hardware applies the swizzle to absolute address bits (or honours base_offset).
-#include "common.cuh"
-#include "host_util.h"
+#include "../../uegan_b200/csrc/common.cuh"
+#include "../../uegan_b200/csrc/host_util.h"
 
 namespace uegan {
 

@@ -10,20 +10,30 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def load_probe_lib():
+    """tests/native/libuegan_probe.so: test-only hardware probes (built by __graft_entry__.build())."""
+    import ctypes as C
+    from tests.native.build_probe import build
+    lib = C.CDLL(build())
+    lib.uegan_probe_umma_window.restype = C.c_int
+    lib.uegan_probe_umma_window.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]
+    lib.uegan_probe_device_error.restype = C.c_int
+    return lib
+
+
 def run_probe(lib, a, b, n, row_shift, base_offset, sbo):
     out = torch.zeros(128, n, device="cuda")
-    from uegan_b200 import _lib as L
-    L.check(lib.uegan_probe_umma_window(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.shape[0], n, 1, row_shift,
-                                        base_offset, sbo, torch.cuda.current_stream().cuda_stream), "probe")
-    assert lib.uegan_device_error() == 0
+    rc = lib.uegan_probe_umma_window(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.shape[0], n, 1, row_shift,
+                                     base_offset, sbo, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    assert lib.uegan_probe_device_error() == 0
     return out
 
 
 def test_probe_umma_window():
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
-    from uegan_b200 import _lib as L
-    lib = L.load()
+    lib = load_probe_lib()
     torch.backends.cuda.matmul.allow_tf32 = False
     g = torch.Generator(device="cuda").manual_seed(5)
     n = 32

@@ -186,3 +186,32 @@ def test_io_and_psnr_match_reference():
         from PIL import Image
         tf = T.Compose([T.ToTensor(), T.Normalize(mean=[0.5] * 3, std=[0.5] * 3)])  # data_loader.py:79-81
         close(x, tf(Image.fromarray(img)), 1e-7)
+
+
+def test_ssim_restatement_properties():
+    """structural_similarity (restated from scikit-image, parity unpinned: see its docstring) -- closed-form anchors."""
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, (40, 48, 3), dtype=np.uint8)
+    b = np.clip(a.astype(np.int32) + rng.integers(-20, 21, a.shape), 0, 255).astype(np.uint8)
+    assert abs(O.structural_similarity(a.astype(np.float64), a.astype(np.float64)) - 1.0) < 1e-12
+    s_ab, s_ba = O.structural_similarity(a.astype(np.float64), b.astype(np.float64)), O.structural_similarity(
+        b.astype(np.float64), a.astype(np.float64))
+    assert abs(s_ab - s_ba) < 1e-12 and 0.0 < s_ab < 1.0
+    # constant images: S = (2 ux uy + C1) / (ux^2 + uy^2 + C1) everywhere (variances and covariance vanish)
+    c1 = (0.01 * 255) ** 2
+    x, y = np.full((16, 16, 3), 100.0), np.full((16, 16, 3), 140.0)
+    assert abs(O.structural_similarity(x, y) - (2 * 100 * 140 + c1) / (100 ** 2 + 140 ** 2 + c1)) < 1e-12
+    # brute-force evaluation of the definition at one interior pixel
+    p, q = a[..., 0].astype(np.float64), b[..., 0].astype(np.float64)
+    wy, wx = 10, 17
+    P, Q = p[wy - 3:wy + 4, wx - 3:wx + 4], q[wy - 3:wy + 4, wx - 3:wx + 4]
+    ux, uy = P.mean(), Q.mean()
+    vx, vy, vxy = P.var(ddof=1), Q.var(ddof=1), ((P - ux) * (Q - uy)).sum() / 48.0
+    c2 = (0.03 * 255) ** 2
+    want = (2 * ux * uy + c1) * (2 * vxy + c2) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
+    from scipy.ndimage import uniform_filter
+    cn = 49.0 / 48.0
+    fx, fy = uniform_filter(p, 7), uniform_filter(q, 7)
+    got = ((2 * fx * fy + c1) * (2 * cn * (uniform_filter(p * q, 7) - fx * fy) + c2) /
+           ((fx ** 2 + fy ** 2 + c1) * (cn * (uniform_filter(p * p, 7) - fx * fx) + cn * (uniform_filter(q * q, 7) - fy * fy) + c2)))[wy, wx]
+    assert abs(got - want) < 1e-9

@@ -173,7 +173,8 @@ class Generator(nn.Module):
         return self.forward_native(x)
 
     @torch.no_grad()
-    def forward_native(self, x, keep=None):
+    def forward_native(self, x, keep=None, packed=False):
+        """packed=True: the plan's x0 operand already holds x (uegan_b200.io.pack_u8 wrote both from uint8)."""
         assert x.dim() == 4 and x.shape[1] == 3, "expected (B,3,H,W)"
         b, _, h, w = x.shape
         if h % 16 or w % 16 or h < 32 or w < 32:
@@ -192,7 +193,8 @@ class Generator(nn.Module):
             K.conv_fprop(src, self._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, off,
                          cv.bias if bias else None, None, act_, mul)
 
-        K.pack_input(x, P["x0"], L.PAD_REFLECT)
+        if not packed:
+            K.pack_input(x, P["x0"], L.PAD_REFLECT)
         conv(P["x0"], "enc1", self.enc1, d, 7, 1, P["x1"], act); K.halo_fill(P["x1"])
         conv(P["x1"], "enc2", self.enc2, 2 * d, 3, 2, P["x2"], act); K.halo_fill(P["x2"])
         conv(P["x2"], "enc3", self.enc3, 4 * d, 3, 2, P["x3"], act); K.halo_fill(P["x3"])
