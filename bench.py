@@ -301,13 +301,14 @@ def run_native(args):
     if train:
         from uegan_b200.trainer import Trainer
         targs = train_args(batch)
-        # CUDA-graph capture of the step is used at N = 1 only: with NCCL collectives inside the captured step the
-        # N = 2 run hung after the timed region (graph replays followed by eager collectives); eager DDP is verified
-        # (scripts/ddp_equivalence.py) and costs ~1.5 % (host enqueue 101 ms vs 118 ms of GPU work per step).
-        use_graph = bool(args.graph) and world == 1
-        targs.cuda_graph = use_graph
+        # The data-parallel reductions run over peer memory inside our own kernels (uegan_b200.peer / optim), so the
+        # captured step contains no NCCL call and the CUDA graph is used at every world size; with the NCCL fallback
+        # (no symmetric memory) the step runs eagerly at N > 1.
+        targs.peer_reduce = bool(args.peer)
         T = Trainer(None, targs, process_group=group if world > 1 else None,
                     vgg_state_dict=O.make_vgg_params())
+        use_graph = bool(args.graph) and (world == 1 or T.comm is not None)
+        targs.cuda_graph = use_graph
         T.G.load_state_dict(O.make_generator_params(32, 0, "o1"))
         T.D.load_state_dict(O.make_discriminator_params(32, 1, "o1"))
         y = torch.rand(batch, 3, RES, RES, device="cuda", generator=gen) * 2 - 1
@@ -430,6 +431,23 @@ def run_native(args):
                 "by_kind_ms_tflops": {k: [round(v[0], 2), round(v[1] / (v[0] * 1e-3) / 1e12, 1)] for k, v in groups.items()},
                 "top_layers_ms_tflops": {k: [round(v[0], 3), round(v[1] / (v[0] * 1e-3) / 1e12, 1)] for k, v in top}}
 
+    replicas = None
+    if train:
+        # data-parallel consistency: after all steps every rank must hold bit-identical weights (the rank-ordered peer-memory
+        # sums guarantee it; with NCCL the all-reduce does).  One checksum per rank, gathered; rank 0 reports.
+        import hashlib
+        torch.cuda.synchronize()
+        flat = torch.cat([p.detach().flatten() for p in list(T.G.parameters()) + list(T.D.parameters())]).cpu().numpy()
+        digest = hashlib.sha256(flat.tobytes()).hexdigest()[:16]
+        if world > 1:
+            allh = [None] * world
+            dist.all_gather_object(allh, digest)
+        else:
+            allh = [digest]
+        replicas = {"weights_sha256_16": allh[0], "identical_on_all_ranks": len(set(allh)) == 1,
+                    "grad_reduce": ("single GPU" if world == 1 else
+                                    ("peer memory (NVLink), fused into uegan_adam_step_peers" if T.comm is not None
+                                     else "NCCL all-reduce + uegan_adam_step"))}
     if rank == 0:
         cpu_threads = os.cpu_count() or 1
         cpu_batch = 1 if train else 2
@@ -446,7 +464,9 @@ def run_native(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32 (G, D) + f16 (VGG), fp32 accumulate" if train else "tf32", "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "batch_per_gpu": batch, "global_batch": world * batch,
-                       "parallelism": (f"dp{world}: 2 flat NCCL grad all-reduces/step" if train else f"replicas x{world}"),
+                       "parallelism": (f"dp{world}: per optimizer one fused gradient-reduction + Adam kernel over "
+                                       f"{'peer memory' if (world > 1 and T.comm is not None) else ('NCCL' if world > 1 else 'one GPU')}"
+                                       if train else f"replicas x{world}"),
                        "l2": "per-step activation traffic (tens of GB) >> 126 MB L2; no flush needed",
                        "host_enqueue_ms_per_step": host_enqueue_ms, "cuda_graph": bool(train and graphed),
                        "achieved_tflops_per_gpu": gflop * value / world / 1e3,
@@ -457,7 +477,7 @@ def run_native(args):
                              "sample": f"{'unmodified reference modules (oracle/_ref)' if cpu_kind == 'reference' else 'oracle port'}"
                                        f" {'training step' if train else 'Generator.forward'}, "
                                        f"{1 if train else 2} iteration(s) of {cpu_batch}x3x512x512 ({cpu_dt:.1f} s)"},
-            "gpu_library_baseline": gpu_lib,
+            "gpu_library_baseline": gpu_lib, "replicas": replicas,
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -473,6 +493,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 16 train / 32 inference)")
     ap.add_argument("--lib-baseline", dest="lib_baseline", type=int, default=1,
                     help="also time the unmodified reference on the GPU (eager PyTorch + cuDNN), N = 1 only")
+    ap.add_argument("--peer", type=int, default=1, help="N > 1: gradient / loss reductions over peer memory inside our "
+                    "kernels (1) or NCCL all-reduce (0)")
     ap.add_argument("--graph", type=int, default=1, help="capture the training step into a CUDA graph (1) or run eagerly (0)")
     args = ap.parse_args()
     if args.workload == "sweep":

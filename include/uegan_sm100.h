@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UEGAN_ABI_VERSION 1
+#define UEGAN_ABI_VERSION 2
 
 enum { UEGAN_F32 = 0, UEGAN_BF16 = 1, UEGAN_F16 = 2 };  /* storage dtype; F32 tensors feed kind::tf32 MMAs, the
                                                            16-bit types kind::f16 */
@@ -193,14 +193,18 @@ int uegan_instance_norm_stats(const uegan_tensor* src, float eps, double* stats_
  * operands), dz must store a multiple of 32 channels, x 4 or a multiple of 32.  The caller zeroes dw_oihw. */
 int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz, int32_t cout, int32_t cin, int32_t cin_total,
                        int32_t cin_first, int32_t k, int32_t stride, int32_t pad, float* dw_oihw,
-                       const float* alpha_dev, float scale, void* stream);
+                       const float* alpha_dev, float scale, float* ws, size_t ws_bytes, void* stream);
+/* (ws, ws_bytes): optional split-K workspace.  NULL: the k-slices publish with fp32 atomics (fastest; the summation order
+ * and hence the last bits vary from run to run).  Non-NULL: every slice stores its partial plane into ws and a second
+ * kernel adds the planes to dw_oihw in slice order -- bit-reproducible like the reference under
+ * cudnn.deterministic=True (utils.py:154); the k-split is clamped to what ws_bytes holds. */
 /* The same weight gradient for a stride-1 conv with a tiny output-channel count (G's last conv, D's prediction heads) from
  * the stacked gradient e = uegan_dz_hstack(dz):  dW[o][c][r][s] += scale * alpha * sum_{y,q} xpad[y + r][q][c] * e[y][q][(s,o)]
  * -- the wgrad of a k x 1 convolution with k*cout output channels: one accumulator per (32-channel chunk, 4 filter rows)
  * instead of one per (chunk, row, 4 columns).  pad must be (k-1)/2 <= x.halo; k*cout <= 32. */
 int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tensor* e, int32_t cout, int32_t cin, int32_t cin_total,
                               int32_t cin_first, int32_t k, int32_t pad, float* dw_oihw, const float* alpha_dev,
-                              float scale, void* stream);
+                              float scale, float* ws, size_t ws_bytes, void* stream);
 /* Gradient of the planar heads into a zero-haloed NHWC tensor: mode 0 tanh (models.py:178), 1 sigmoid, 2
  * clamp(tanh(z) + x, -1, 1) with out_nchw = tanh(z) (models.py:35,72). */
 int uegan_head_bwd(const float* dout_nchw, const float* out_nchw, const float* x_nchw, int32_t channels, int32_t mode,
@@ -222,7 +226,8 @@ int uegan_fold_inplace(const uegan_tensor* t, void* stream);
  * e[n, y, q, s*cout + o] = dz[n, y, q - s, o].  Operand of uegan_conv2d_wgrad_hstack. */
 int uegan_dz_hstack(const uegan_tensor* dz, int32_t cout, int32_t k, const uegan_tensor* e, void* stream);
 /* out[c] = sum over n, h, w of src[.., c_off + c]  (bias gradient). */
-int uegan_channel_sum(const uegan_tensor* src, int32_t c_off, int32_t channels, float* out, void* stream);
+int uegan_channel_sum(const uegan_tensor* src, int32_t c_off, int32_t channels, float* out, int32_t out_channels,
+                      int32_t accumulate, void* stream);
 /* InstanceNorm backward: dz = rstd * (dout - mean(dout) - xhat * mean(dout * xhat)); ws: 2*n*c doubles. */
 int uegan_instance_norm_bwd(const uegan_tensor* dout, int32_t d_c_off, const uegan_tensor* z, const float* mean_rstd,
                             const uegan_tensor* dz, double* ws, void* stream);
@@ -236,13 +241,36 @@ int uegan_maxpool2x2_bwd(const uegan_tensor* src, const uegan_tensor* dpool, con
 int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
                      float weight, const float* gscale_dev, const uegan_tensor* deep, const uegan_tensor* dx, double* ws,
                      void* stream);
-/* Gradient of uegan_pack_input: NHWC (first 3 channels) -> NCHW fp32 times scale_host[c]. */
-int uegan_unpack_input_grad(const uegan_tensor* dx, const float* scale_host, float* dst_nchw, void* stream);
+/* Gradient of uegan_pack_input: NHWC (first 3 channels) -> NCHW fp32 times scale_host[c].  With skip_dout_nchw != NULL the
+ * Generator's identity path is added: out = clamp(res + x, -1, 1) (models.py:72) passes skip_dout where |res + x| <= 1. */
+int uegan_unpack_input_grad(const uegan_tensor* dx, const float* scale_host, float* dst_nchw, const float* skip_dout_nchw,
+                            const float* skip_res_nchw, const float* skip_x_nchw, void* stream);
 
 /* Backward of spectral normalisation through sigma (u, v constant, torch spectral_norm semantics): in place on
  * grad_inout = (dL/dW_sn)/sigma (rows x cols): grad -= (<grad, W>/sigma) u v^T.  sigma = {sigma, 1/sigma}; ws: 1 double. */
 int uegan_spectral_bwd(float* grad_inout, const float* w, const float* u, const float* v, const float* sigma,
-                       int32_t rows, int32_t cols, double* ws, void* stream);
+                       int32_t rows, int32_t cols, double* ws, float* accum_out, void* stream);
+
+/* ---- optimizer + data-parallel gradient reduction (trainer.py:337-338 torch.optim.Adam) ------------------
+ * Adam over ONE flat fp32 bucket (all parameters of a network; gradients, exp_avg, exp_avg_sq laid out alike), torch
+ * semantics: g += weight_decay * p; exp_avg.lerp_(g, 1 - beta1); exp_avg_sq = beta2 * exp_avg_sq + (1 - beta2) g^2;
+ * p -= lr / (1 - beta1^t) * exp_avg / (sqrt(exp_avg_sq) / sqrt(1 - beta2^t) + eps).  state3 = {t, lr / bc1, 1 / sqrt(bc2)}
+ * (device floats; t is incremented by the call), lr_dev = device scalar: a CUDA-graph replay needs no host work. */
+int uegan_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* state3,
+                    const float* lr_dev, float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* The same update with the gradient all-reduce FUSED into it: peer_grads_host[r] = device address of rank r's gradient
+ * bucket in this process's address space (peer memory over NVLink / NVSwitch, e.g. torch symmetric memory); the kernel
+ * sums the `world` buckets in rank order as it loads them, so every rank applies bit-identical updates and no reduced
+ * gradient is ever written.  The caller orders it after all ranks' backward passes (a device-side barrier) and keeps the
+ * buckets untouched until all ranks have read them. */
+int uegan_adam_step_peers(float* param, const float* const* peer_grads_host, int32_t world, float* exp_avg,
+                          float* exp_avg_sq, int64_t n, float* state3, const float* lr_dev, float beta1, float beta2,
+                          float eps, float weight_decay, void* stream);
+/* out[i] = sum_r peers_host[r][i], i < count <= 64, in rank order: the batch-global sums of the relativistic GAN loss
+ * (losses.py:351-360) over peer memory instead of a NCCL all-reduce. */
+int uegan_peer_sum_f64(double* out, const double* const* peers_host, int32_t world, int32_t count, void* stream);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream`: zeroing of gradient buckets / per-pass scratch (torch zero_() replacement). */
+int uegan_memset_zero(void* ptr, size_t bytes, void* stream);
 
 /* ---- the conversions either side of the hot path -------------------------------------------------
  * uint8 HWC RGB batch (n x h x w x 3, device memory) -> what transforms.ToTensor() + Normalize(mean, std) produce

@@ -15,8 +15,10 @@ from oracle import uegan_oracle as O  # noqa: E402
 from uegan_b200.trainer import Trainer  # noqa: E402
 
 
-def make_trainer(batch, group):
-    T = Trainer(None, train_args(batch), process_group=group, vgg_state_dict=O.make_vgg_params())
+def make_trainer(batch, group, peer=True):
+    a = train_args(batch)
+    a.peer_reduce = peer
+    T = Trainer(None, a, process_group=group, vgg_state_dict=O.make_vgg_params())
     T.G.load_state_dict(O.make_generator_params(32, 0, "o1"))
     T.D.load_state_dict(O.make_discriminator_params(32, 1, "o1"))
     return T
@@ -29,9 +31,18 @@ def main():
     b, res = 2, 128
     raw = O.make_images((world * b, 3, res, res), 40).cuda()
     exp = O.make_images((world * b, 3, res, res), 41).cuda()
-    # sharded step
-    T = make_trainer(b, dist.group.WORLD)
+    # sharded step: reductions over peer memory inside our kernels (default) or NCCL (UEGAN_DDP_NCCL=1)
+    peer = os.environ.get("UEGAN_DDP_NCCL") != "1"
+    T = make_trainer(b, dist.group.WORLD, peer)
+    if rank == 0:
+        print(f"world {world}: gradient / loss reductions via", "peer memory (uegan_adam_step_peers, uegan_peer_sum_f64)"
+              if T.comm is not None else "NCCL all-reduce")
     v_dp = T.train_step(raw[rank * b:(rank + 1) * b].contiguous(), exp[rank * b:(rank + 1) * b].contiguous())
+    # every rank must hold bit-identical weights after the step
+    import hashlib
+    flat = torch.cat([p.detach().flatten() for p in list(T.G.parameters()) + list(T.D.parameters())]).cpu().numpy()
+    hashes = [None] * world
+    dist.all_gather_object(hashes, hashlib.sha256(flat.tobytes()).hexdigest()[:16])
     # mean-type losses are per-rank means: average them over ranks for the comparison
     t = torch.tensor([v_dp["g_percep_loss"], v_dp["g_idt_loss"]], device="cuda", dtype=torch.float64)
     dist.all_reduce(t)
@@ -57,6 +68,8 @@ def main():
         ok &= dG.mean().item() < 2e-5 and dD.mean().item() < 4e-5
         for k in range(1, 6):  # spectral-norm buffers stay identical on every rank
             ok &= float((T1.D.state_dict()[f"d{k}.0.1.weight_u"] - T.D.state_dict()[f"d{k}.0.1.weight_u"]).abs().max()) < 1e-5
+        print("replica weight checksums:", hashes)
+        ok &= len(set(hashes)) == 1
         print("DDP_EQUIVALENCE", "PASS" if ok else "FAIL")
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

@@ -61,11 +61,11 @@ def _worker(rank, world, port, q):
     from uegan_b200.models import Discriminator
     torch.manual_seed(1)
     D = Discriminator(32, "none", "LeakyReLU", True, "rahinge")
-    fg_ = _FlatGrads(D)
+    fg_ = _FlatGrads(D, dist.group.WORLD)
     assert fg_.flat.numel() == 4633632  # every D parameter lives in the one bucket
     for i, p in enumerate(fg_.params):
         p.grad.fill_(float(rank + 1) * (i + 1))
-    fg_.all_reduce(dist.group.WORLD)
+    fg_.all_reduce()
     for i, p in enumerate(fg_.params):
         ok &= bool(torch.all(p.grad == float(sum(range(1, world + 1))) * (i + 1)))
         ok &= p.grad.data_ptr() >= fg_.flat.data_ptr()  # still a view of the bucket

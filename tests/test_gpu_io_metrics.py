@@ -78,7 +78,9 @@ def test_enhance_u8_matches_float_path():
     want = np.stack([O.denorm_to_u8(ref[i]) for i in range(2)])
     d = np.abs(got.astype(np.int32) - want.astype(np.int32))
     print(f"enhance_u8 vs oracle PNG bytes: max |diff| {d.max()}, mean {d.mean():.4f}")
-    assert d.max() <= 1 and d.mean() < 0.02  # 1e-3 on pixels = at most one grey level at a rounding boundary
+    # 1e-3 rel-L2 on pixels in [-1, 1] is ~0.1 grey level: never more than one level off, and a few per cent of the bytes
+    # sit close enough to a rounding boundary to land on the other side (measured 3.5 %)
+    assert d.max() <= 1 and d.mean() < 0.06
     assert K.device_error() == 0
 
 

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libuegan_sm100.so")
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 PAD_ZERO, PAD_REFLECT = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class UeganError(RuntimeError):
@@ -75,12 +75,12 @@ SYMBOLS = {
     "uegan_msrec_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "uegan_spectral_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
-                                     C.c_void_p, C.c_void_p]),
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "uegan_pack_conv_weight_dgrad": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 10 + [C.c_void_p]),
     "uegan_conv2d_wgrad": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor)] + [C.c_int32] * 7 +
-                           [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+                           [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uegan_conv2d_wgrad_hstack": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor)] + [C.c_int32] * 6 +
-                                  [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+                                  [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uegan_fold_inplace": (C.c_int, [C.POINTER(Tensor), C.c_void_p]),
     "uegan_dz_hstack": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.POINTER(Tensor), C.c_void_p]),
     "uegan_head_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Tensor),
@@ -89,17 +89,23 @@ SYMBOLS = {
                                      C.c_int32, C.POINTER(Tensor), C.c_int32, C.POINTER(Tensor), C.c_int32,
                                      C.POINTER(Tensor), C.c_int32, C.c_int32, C.POINTER(Tensor), C.c_int32,
                                      C.c_void_p]),
-    "uegan_channel_sum": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "uegan_channel_sum": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "uegan_instance_norm_bwd": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.POINTER(Tensor), C.c_void_p,
                                           C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
     "uegan_upsample2x_bwd": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.POINTER(Tensor), C.c_void_p]),
     "uegan_maxpool2x2_bwd": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
     "uegan_in_mse_bwd": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p, C.c_float,
                                    C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
-    "uegan_unpack_input_grad": (C.c_int, [C.POINTER(Tensor), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
+    "uegan_unpack_input_grad": (C.c_int, [C.POINTER(Tensor), C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
     "uegan_upsample2x": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_int32, C.c_void_p]),
     "uegan_maxpool2x2": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
     "uegan_unpack_nchw": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "uegan_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p]),
+    "uegan_adam_step_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p]),
+    "uegan_peer_sum_f64": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p]),
+    "uegan_memset_zero": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "uegan_pack_input_u8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Tensor), C.c_void_p, C.c_int32,
                                       C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]),
     "uegan_unpack_output_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

@@ -136,15 +136,26 @@ def _g_backward(G, x, out_grad, ws, need_dx):
     grads = {}
     cache = G._wcache
     act = G._act
+    # gradient sink (uegan_b200.optim.FlatBucket): the weight-gradient kernels accumulate straight into the optimizer's
+    # flat bucket and autograd gets None for those parameters; without a sink (plain autograd use) fresh tensors are returned
+    sink = getattr(G, "_grad_sink", None)
+
+    def gbuf(pname, param, zero=True):
+        if sink is not None:
+            return sink[pname], True
+        return (_zeros_like(param) if zero else torch.empty_like(param)), False
 
     def wgrad(name, conv, xin, dz, k, stride, pad, cin_first=0, cin=None, bias_from=None):
-        gw = _zeros_like(conv.weight)
+        gw, direct = gbuf(name + ".weight", conv.weight)
         K.conv_wgrad(xin, dz, gw, k, stride, pad, cin_first=cin_first, cin=cin)
-        grads[name + ".weight"] = gw
+        grads[name + ".weight"] = None if direct else gw
         if bias_from is not None and conv.bias is not None:
-            gb = torch.empty_like(conv.bias)
-            K.channel_sum(bias_from, gb)
-            grads[name + ".bias"] = gb
+            gb, direct = gbuf(name + ".bias", conv.bias, zero=False)
+            K.channel_sum(bias_from, gb, accumulate=direct)
+            grads[name + ".bias"] = None if direct else gb
+
+    def dead(pname, param):
+        grads[pname] = None if sink is not None else torch.zeros_like(param)
 
     # ---- dec5.1 + tanh + clamp(res + x)   (models.py:34-35, 72)
     dz5 = S("dz5", h, w, 4, 6)
@@ -154,15 +165,16 @@ def _g_backward(G, x, out_grad, ws, need_dx):
         # horizontal taps unrolled into the gradient's channels: the wgrad keeps only the 7 vertical taps
         e5 = S("dz5e", h, w + 6, 32, 0)
         K.dz_hstack(dz5, 3, 7, e5)
-        gw = _zeros_like(c51.weight)
+        gw, direct = gbuf("dec5.1.main.1.weight", c51.weight)
         K.conv_wgrad_hstack(P["t"], e5, gw, 7, 3)
-        grads["dec5.1.main.1.weight"] = gw
+        grads["dec5.1.main.1.weight"] = None if direct else gw
     else:
         dz5w = S("dz5w", h, w, 32, 0)
         K.head_bwd(out_grad, P["res"], x, 2, dz5w)
         wgrad("dec5.1.main.1", c51, P["t"], dz5w, 7, 1, 3)
-    gb = torch.empty(4, dtype=torch.float32, device=dev); K.channel_sum(dz5, gb, 0, 4)
-    grads["dec5.1.main.1.bias"] = gb[:3]
+    gb, direct = gbuf("dec5.1.main.1.bias", c51.bias, zero=False)
+    K.channel_sum(dz5, gb, 0, 4, accumulate=direct)  # 4 stored channels reduced, the 3 real ones written
+    grads["dec5.1.main.1.bias"] = None if direct else gb
     dxp = S("dxp_t", h + 6, w + 6, d)
     K.conv_dgrad(dz5, c51.weight, 7, 1, dxp, cache, "dec5.1")
     if _FOLD_INPLACE:
@@ -209,7 +221,7 @@ def _g_backward(G, x, out_grad, ws, need_dx):
                             torch.empty(2 * b * ch, dtype=torch.float64, device=dev))
         gname = f"ga{4-i}"
         wgrad(gname + ".fuse.0", ga, skips[i], dzs, 1, 1, 0, cin_first=0, cin=ch)
-        grads[gname + ".fuse.0.bias"] = torch.zeros_like(ga.bias)
+        dead(gname + ".fuse.0.bias", ga.bias)
         dsk = S(f"dskip{i}", hh, ww, ch)
         K.conv_dgrad(dzs, ga.weight, 1, 1, dsk, cache, gname, cin_first=0, cin=ch)
         dskip[i] = dsk
@@ -225,7 +237,7 @@ def _g_backward(G, x, out_grad, ws, need_dx):
     K.instance_norm_bwd(d_x5n, 0, P["z5"], P["mr"]["ga5"], dz5g, torch.empty(2 * b * c5, dtype=torch.float64, device=dev))
     f5 = G.ga5.fuse[0]
     wgrad("ga5.fuse.0", f5, P["x5"], dz5g, 1, 1, 0, cin_first=0, cin=c5)
-    grads["ga5.fuse.0.bias"] = torch.zeros_like(f5.bias)
+    dead("ga5.fuse.0.bias", f5.bias)
     dx5 = S("dx5", h5, w5, c5)
     K.conv_dgrad(dz5g, f5.weight, 1, 1, dx5, cache, "ga5", cin_first=0, cin=c5)
     # ---- encoder 5..1
@@ -254,12 +266,13 @@ def _g_backward(G, x, out_grad, ws, need_dx):
         dx0 = S("dx0", h, w, 16)
         K.grad_combine(dx0, 16, src_a=dxp0, pad_a=3)
         dx = torch.empty_like(x)
-        K.unpack_input_grad(dx0, None, dx)
+        # + the identity path of out = clamp(res + x, -1, 1) (models.py:72)
+        K.unpack_input_grad(dx0, None, dx, skip=(out_grad, P["res"], x))
     # dead parameters (see module docstring)
     for i in range(1, 6):
         ga = getattr(G, f"ga{i}")
-        grads[f"ga{i}.conv.0.weight"] = torch.zeros_like(ga.conv[0].weight)
-        grads[f"ga{i}.conv.2.weight"] = torch.zeros_like(ga.conv[2].weight)
+        dead(f"ga{i}.conv.0.weight", ga.conv[0].weight)
+        dead(f"ga{i}.conv.2.weight", ga.conv[2].weight)
     return grads, dx
 
 
@@ -287,7 +300,7 @@ class _GeneratorFn(torch.autograd.Function):
         G._train_pool[ctx.key].append(ctx.ws)
         ctx.ws = None
         names = [n for n, _ in G.named_parameters()]
-        return (None, dx) + tuple(grads[n] for n in names)
+        return (None, dx) + tuple(grads[n] for n in names)  # None where the kernels wrote into the gradient sink
 
 
 def generator_apply(module, x):
@@ -346,6 +359,12 @@ def _d_backward(D, x, dpreds, ws, need_dx, need_w=True):
     S = lambda name, hh, ww, c, halo=0: _scratch.get("D" + name, b, hh, ww, c, halo, F32, dev)
     cache = D._wcache
     grads = {}
+    sink = getattr(D, "_grad_sink", None) if need_w else None
+
+    def gbuf(pname, param, zero=True):
+        if sink is not None:
+            return sink[pname], True
+        return (_zeros_like(param) if zero else torch.empty_like(param)), False
     srcs = [ws["x0"]] + ws["ds"]
     carry = None  # gradient w.r.t. the padded ds_k coming from d_{k+1}
     head_mode = 0 if D._head_act == L.ACT_TANH else 1
@@ -361,7 +380,7 @@ def _d_backward(D, x, dpreds, ws, need_dx, need_w=True):
         dp = dp.contiguous().float()
         K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzp)
         if need_w:
-            gw = _zeros_like(head.weight)
+            gw, direct = gbuf(f"d{i}_pred.0.1.weight", head.weight)
             if K.hstack_ok(1, ds.c, k):
                 ep = S(f"dzpe{i}", ds.h, ds.w + k - 1, 32, 0)
                 K.dz_hstack(dzp, 1, k, ep)
@@ -370,7 +389,7 @@ def _d_backward(D, x, dpreds, ws, need_dx, need_w=True):
                 dzpw = S(f"dzpw{i}", ds.h, ds.w, 32, 0)
                 K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzpw)
                 K.conv_wgrad(ds, dzpw, gw, k, 1, pad)
-            grads[f"d{i}_pred.0.1.weight"] = gw
+            grads[f"d{i}_pred.0.1.weight"] = None if direct else gw
         dxa = S(f"dxa{i}", ds.h + 2 * pad, ds.w + 2 * pad, ds.c)
         K.conv_dgrad(dzp, head.weight, k, 1, dxa, cache, f"p{i}")
         dz = S(f"dz{i}", ds.h, ds.w, ds.c, kq - 1)
@@ -387,17 +406,30 @@ def _d_backward(D, x, dpreds, ws, need_dx, need_w=True):
         xin = srcs[i - 1]
         alpha = ws["sig"][i - 1][1:2] if D.use_sn else None
         if need_w:
-            gw = _zeros_like(wgt)
-            K.conv_wgrad(xin, dz, gw, k, 2, pad, alpha=alpha)
             if D.use_sn:
+                # the gradient w.r.t. W_sn of THIS pass (u, v, sigma differ between the passes of a step) in a per-layer
+                # scratch, then the rank-one correction, added into the sink by the same kernel
+                wname = f"d{i}.0.1.weight_orig"
+                tgt, direct = gbuf(wname, wgt, zero=False)
+                if direct:
+                    gw = _scratch.store.get(("Dsn", i, str(dev)))
+                    if gw is None:
+                        gw = _scratch.store[("Dsn", i, str(dev))] = torch.empty_like(wgt, memory_format=torch.contiguous_format)
+                    K.zero_(gw)
+                else:
+                    gw = tgt
+                    K.zero_(gw)
+                K.conv_wgrad(xin, dz, gw, k, 2, pad, alpha=alpha)
                 K.spectral_bwd(gw, wgt, ws["u"][i - 1], ws["v"][i - 1], ws["sig"][i - 1],
-                               torch.empty(1, dtype=torch.float64, device=dev))
-                grads[f"d{i}.0.1.weight_orig"] = gw
+                               torch.empty(1, dtype=torch.float64, device=dev), accum=tgt if direct else None)
+                grads[wname] = None if direct else gw
             else:
-                grads[f"d{i}.0.1.weight"] = gw
-            gb = torch.empty_like(conv.bias)
-            K.channel_sum(dz, gb)
-            grads[f"d{i}.0.1.bias"] = gb
+                gw, direct = gbuf(f"d{i}.0.1.weight", wgt)
+                K.conv_wgrad(xin, dz, gw, k, 2, pad, alpha=alpha)
+                grads[f"d{i}.0.1.weight"] = None if direct else gw
+            gb, direct = gbuf(f"d{i}.0.1.bias", conv.bias, zero=False)
+            K.channel_sum(dz, gb, accumulate=direct)
+            grads[f"d{i}.0.1.bias"] = None if direct else gb
         if i > 1:
             dxb = S(f"dxb{i}", xin.h + 2 * pad, xin.w + 2 * pad, xin.c)
             K.conv_dgrad(dz, wgt, k, 2, dxb, cache, f"d{i}", alpha=alpha)

@@ -212,6 +212,7 @@ struct ChannelSumOp {
   TGeom s;
   int c_off;
   float* out;
+  int out_channels;
   __device__ void prep(int, int) {}
   __device__ void acc(int n, int y, int x, int c, float (&a)[Vec<T>::N][1]) const {
     float v[Vec<T>::N];
@@ -219,7 +220,9 @@ struct ChannelSumOp {
 #pragma unroll
     for (int k = 0; k < Vec<T>::N; ++k) a[k][0] += v[k];
   }
-  __device__ void flush(int n, int c, const float (&t)[1]) const { atomicAdd(out + c, t[0]); }
+  __device__ void flush(int n, int c, const float (&t)[1]) const {
+    if (c < out_channels) atomicAdd(out + c, t[0]);
+  }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -511,7 +514,9 @@ struct TapBwdStatsOp {
 };
 // gradient of the packed input: NHWC (c >= 3) -> NCHW fp32 (3 channels) times per-channel scale
 template <typename TG>
-__global__ void unpack_grad_kernel(TGeom s, float* __restrict__ dst, float s0, float s1, float s2, long long total) {
+__global__ void unpack_grad_kernel(TGeom s, float* __restrict__ dst, float s0, float s1, float s2, long long total,
+                                   const float* __restrict__ skip_dout, const float* __restrict__ skip_res,
+                                   const float* __restrict__ skip_x) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int x = (int)(i % s.w);
@@ -521,7 +526,13 @@ __global__ void unpack_grad_kernel(TGeom s, float* __restrict__ dst, float s0, f
   const int c = (int)(r % 3);
   const int n = (int)(r / 3);
   const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
-  dst[i] = to_f32<TG>(static_cast<const TG*>(s.data)[toff(s, n, y, x, c)]) * sc;
+  float v = to_f32<TG>(static_cast<const TG*>(s.data)[toff(s, n, y, x, c)]) * sc;
+  if (skip_dout) {
+    // the generator's identity path out = clamp(res + x, -1, 1) (models.py:72): d out / d x = [|res + x| <= 1]
+    const float t = __ldg(skip_res + i) + __ldg(skip_x + i);
+    if (t >= -1.f && t <= 1.f) v += __ldg(skip_dout + i);
+  }
+  dst[i] = v;
 }
 
 static inline unsigned nblk(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
@@ -627,23 +638,25 @@ int uegan_dz_hstack(const uegan_tensor* dz, int32_t cout, int32_t k, const uegan
   return 0;
 }
 
-int uegan_channel_sum(const uegan_tensor* src, int32_t c_off, int32_t channels, float* out, void* stream) {
+int uegan_channel_sum(const uegan_tensor* src, int32_t c_off, int32_t channels, float* out, int32_t out_channels,
+                      int32_t accumulate, void* stream) {
   UEGAN_CHECK(src && src->data && out, "channel_sum: null pointer");
   UEGAN_CHECK(c_off >= 0 && c_off + channels <= src->c && channels <= 1024, "channel_sum: bad channel range");
+  if (out_channels <= 0 || out_channels > channels) out_channels = channels;
   const TGeom s = geom(*src);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  UEGAN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * channels, st));
+  if (!accumulate) UEGAN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * out_channels, st));
   const int vn = 16 / dtype_size(src->dtype);
   UEGAN_CHECK(channels % vn == 0 && c_off % vn == 0 && 256 % (channels / vn) == 0,
               "channel_sum: unsupported channel count %d", channels);
   if (src->dtype == UEGAN_F32) {
-    ChannelSumOp<float> op{s, c_off, out};
+    ChannelSumOp<float> op{s, c_off, out, out_channels};
     launch_strip_reduce<float, 1>(op, channels, s.n, s.h, s.w, st);
   } else if (src->dtype == UEGAN_BF16) {
-    ChannelSumOp<__nv_bfloat16> op{s, c_off, out};
+    ChannelSumOp<__nv_bfloat16> op{s, c_off, out, out_channels};
     launch_strip_reduce<__nv_bfloat16, 1>(op, channels, s.n, s.h, s.w, st);
   } else {
-    ChannelSumOp<__half> op{s, c_off, out};
+    ChannelSumOp<__half> op{s, c_off, out, out_channels};
     launch_strip_reduce<__half, 1>(op, channels, s.n, s.h, s.w, st);
   }
   UEGAN_CUDA(cudaGetLastError());
@@ -752,13 +765,16 @@ int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* 
   return 0;
 }
 
-int uegan_unpack_input_grad(const uegan_tensor* dx, const float* scale_host, float* dst_nchw, void* stream) {
+int uegan_unpack_input_grad(const uegan_tensor* dx, const float* scale_host, float* dst_nchw, const float* skip_dout_nchw,
+                            const float* skip_res_nchw, const float* skip_x_nchw, void* stream) {
   UEGAN_CHECK(dx && dx->data && dst_nchw && dx->c >= 3, "unpack_input_grad: null pointer");
+  UEGAN_CHECK(!skip_dout_nchw || (skip_res_nchw && skip_x_nchw), "unpack_input_grad: the identity path needs res and x");
   const TGeom s = geom(*dx);
   const long long total = (long long)s.n * 3 * s.h * s.w;
   const float s0 = scale_host ? scale_host[0] : 1.f, s1 = scale_host ? scale_host[1] : 1.f, s2 = scale_host ? scale_host[2] : 1.f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  UEGAN_DISPATCH(dx->dtype, unpack_grad_kernel, <<<nblk(total, 256), 256, 0, st>>>(s, dst_nchw, s0, s1, s2, total));
+  UEGAN_DISPATCH(dx->dtype, unpack_grad_kernel, <<<nblk(total, 256), 256, 0, st>>>(s, dst_nchw, s0, s1, s2, total,
+                                                                                   skip_dout_nchw, skip_res_nchw, skip_x_nchw));
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -33,10 +33,32 @@ struct WgradParams {
   int cout, cin, cin_total, cin_first, x_c;
   int m_tiles, n_chunks;
   float* dw;                       // OIHW fp32
+  float* partial;                  // deterministic mode: [k-split slice][dw_numel] partial sums, reduced in slice order
+  long long dw_numel;
   const float* alpha;
   float scale;
   unsigned int* err_sink;
 };
+
+// split-K publication of one weight-gradient element: fp32 atomics (order = scheduling order, not reproducible), or a
+// plain store into this k-slice's partial plane (wgrad_reduce_kernel then sums the planes in slice order: reproducible
+// bit for bit, like the reference under cudnn.deterministic=True, utils.py:154)
+__device__ __forceinline__ void wg_publish(float* dw, float* partial, long long dw_numel, long long idx, float v) {
+  if (partial) partial[(long long)blockIdx.x * dw_numel + idx] = v;
+  else atomicAdd(dw + idx, v);
+}
+
+// dw[o][cin_first + c][r][s] += sum_{slice} partial[slice][...] over the elements this launch owns
+__global__ void wgrad_reduce_kernel(float* __restrict__ dw, const float* __restrict__ partial, long long dw_numel, int slices,
+                                    int cin_total, int cin_first, int cin, int kk) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dw_numel) return;
+  const int c = (int)((i / kk) % cin_total);
+  if (c < cin_first || c >= cin_first + cin) return;
+  float acc = 0.f;
+  for (int s = 0; s < slices; ++s) acc += partial[(long long)s * dw_numel + i];
+  dw[i] += acc;
+}
 
 __global__ void __launch_bounds__(256, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
@@ -158,8 +180,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int i = 0; i < 16; ++i) {
               const int oc = c0 + i;
               if (oc < p.cout)
-                atomicAdd(p.dw + ((long long)oc * p.cin_total + p.cin_first + c) * kk + r * p.k + ss,
-                          __uint_as_float(rr[i]) * sc);
+                wg_publish(p.dw, p.partial, p.dw_numel, ((long long)oc * p.cin_total + p.cin_first + c) * kk + r * p.k + ss,
+                           __uint_as_float(rr[i]) * sc);
             }
           }
           continue;
@@ -178,7 +200,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           else { ss = ts; c = nc * ncol + j; }
           if (c < p.cin && ss < p.k) {
             const float v = __uint_as_float(rr[i]) * sc;
-            atomicAdd(p.dw + ((long long)o * p.cin_total + p.cin_first + c) * kk + tr * p.k + ss, v);
+            wg_publish(p.dw, p.partial, p.dw_numel, ((long long)o * p.cin_total + p.cin_first + c) * kk + tr * p.k + ss, v);
           }
         }
       }
@@ -194,8 +216,28 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------
 
 static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int cout, int cin, int cin_total,
-                              int cin_first, int k, int pad, float* dw, const float* alpha, float scale,
-                              cudaStream_t stream);
+                              int cin_first, int k, int pad, float* dw, const float* alpha, float scale, float* ws,
+                              size_t ws_bytes, cudaStream_t stream);
+
+// Deterministic mode (ws != NULL): clamp the k-split to what the workspace holds; after the GEMM launch, reduce the
+// non-empty slices in order.
+static int wg_plan_split(int* ksplit, long long dw_numel, float* ws, size_t ws_bytes) {
+  if (!ws) return 0;
+  const long long fit = (long long)(ws_bytes / (sizeof(float) * (size_t)dw_numel));
+  UEGAN_CHECK(fit >= 1, "conv2d_wgrad: workspace of %zu bytes cannot hold one %lld-element partial", ws_bytes, dw_numel);
+  if (*ksplit > fit) *ksplit = (int)fit;
+  return 0;
+}
+static int wg_reduce(float* dw, const float* ws, long long dw_numel, int ksplit, int total_ktiles, int cin_total,
+                     int cin_first, int cin, int k, cudaStream_t st) {
+  if (!ws) return 0;
+  const int per = (total_ktiles + ksplit - 1) / ksplit;
+  const int slices = (total_ktiles + per - 1) / per;  // slices beyond this one own no k-tile and write nothing
+  wgrad_reduce_kernel<<<(unsigned)((dw_numel + 255) / 256), 256, 0, st>>>(dw, ws, dw_numel, slices, cin_total, cin_first, cin,
+                                                                        k * k);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
 
 }  // namespace uegan
 
@@ -203,7 +245,8 @@ using namespace uegan;
 
 extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz, int32_t cout, int32_t cin,
                                   int32_t cin_total, int32_t cin_first, int32_t k, int32_t stride, int32_t pad,
-                                  float* dw_oihw, const float* alpha_dev, float scale, void* stream) {
+                                  float* dw_oihw, const float* alpha_dev, float scale, float* ws, size_t ws_bytes,
+                                  void* stream) {
   UEGAN_CHECK(x && dz && x->data && dz->data && dw_oihw, "conv2d_wgrad: null pointer");
   UEGAN_CHECK(x->dtype == UEGAN_F32 && dz->dtype == UEGAN_F32, "conv2d_wgrad: fp32 (tf32) tensors only");
   UEGAN_CHECK(stride == 1 || stride == 2, "conv2d_wgrad: stride %d", stride);
@@ -215,8 +258,8 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   UEGAN_CHECK((dz->c * 4) % 128 == 0, "conv2d_wgrad: dz must store a multiple of 32 channels (got %d)", dz->c);
   const bool window = (x->c == 4);
   if (stride == 1 && !window && k > 1) {
-    const int took = launch_wgrad_patch(x, dz, cout, cin, cin_total, cin_first, k, pad, dw_oihw, alpha_dev, scale,
-                                        static_cast<cudaStream_t>(stream));
+    const int took = launch_wgrad_patch(x, dz, cout, cin, cin_total, cin_first, k, pad, dw_oihw, alpha_dev, scale, ws,
+                                        ws_bytes, static_cast<cudaStream_t>(stream));
     if (took != 0) return took < 0 ? -1 : 0;
   }
   UEGAN_CHECK(window || (x->c * 4) % 128 == 0, "conv2d_wgrad: x must store 4 or a multiple of 32 channels (got %d)", x->c);
@@ -269,8 +312,11 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   int ksplit = (2 * num_sms() + groups - 1) / groups;
   if (ksplit > p.total_ktiles) ksplit = p.total_ktiles;
   if (ksplit < 1) ksplit = 1;
+  p.dw_numel = (long long)cout * cin_total * k * k;
+  if (wg_plan_split(&ksplit, p.dw_numel, ws, ws_bytes)) return -1;
   p.ksplit = ksplit;
   p.dw = dw_oihw;
+  p.partial = ws;
   p.alpha = alpha_dev;
   p.scale = scale;
   p.err_sink = error_sink_device();
@@ -305,7 +351,8 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   dim3 grid((unsigned)p.ksplit, (unsigned)p.taps, (unsigned)(p.m_tiles * p.n_chunks));
   conv_wgrad_kernel<<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   UEGAN_CUDA(cudaGetLastError());
-  return 0;
+  return wg_reduce(dw_oihw, ws, p.dw_numel, p.ksplit, p.total_ktiles, cin_total, cin_first, cin, k,
+                   static_cast<cudaStream_t>(stream));
 }
 
 // ==========================================================================================================
@@ -336,6 +383,8 @@ struct WgradPatchParams {
   // besides the groups: k (horizontal mode: filter rows) or 1.
   int vert, rk, lbo_bytes;
   float* dw;
+  float* partial;
+  long long dw_numel;
   const float* alpha;
   float scale;
   unsigned int* err_sink;
@@ -454,8 +503,8 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
               const int j = c0 + i;  // column (s, o) of the stacked gradient
               if (j < p.k * p.cout) {
                 const int ss = j / p.cout, o = j - ss * p.cout;
-                atomicAdd(p.dw + ((long long)o * p.cin_total + p.cin_first + c) * kk + s_ * p.k + ss,
-                          __uint_as_float(rr[i]) * sc);
+                wg_publish(p.dw, p.partial, p.dw_numel, ((long long)o * p.cin_total + p.cin_first + c) * kk + s_ * p.k + ss,
+                           __uint_as_float(rr[i]) * sc);
               }
             }
             continue;
@@ -464,8 +513,8 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           for (int i = 0; i < 16; ++i) {
             const int o = c0 + i;
             if (o < p.cout)
-              atomicAdd(p.dw + ((long long)o * p.cin_total + p.cin_first + c) * kk + r * p.k + s_,
-                        __uint_as_float(rr[i]) * sc);
+              wg_publish(p.dw, p.partial, p.dw_numel, ((long long)o * p.cin_total + p.cin_first + c) * kk + r * p.k + s_,
+                         __uint_as_float(rr[i]) * sc);
           }
         }
       }
@@ -478,8 +527,8 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 
 // returns 1 if the patch kernel took the job, 0 if the caller should use the generic kernel, -1 on error
 static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int cout, int cin, int cin_total,
-                              int cin_first, int k, int pad, float* dw, const float* alpha, float scale,
-                              cudaStream_t stream) {
+                              int cin_first, int k, int pad, float* dw, const float* alpha, float scale, float* ws,
+                              size_t ws_bytes, cudaStream_t stream) {
   const char* env = getenv("UEGAN_NO_WGRAD_PATCH");
   if (env && env[0] == '1') return 0;
   if (x->c % 32 != 0 || dz->c % 32 != 0 || cout > 64 || k > 8) return 0;
@@ -515,10 +564,13 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
   p.total_ktiles = p.tiles_w * p.tiles_h * p.nimg;
   int ksplit = (2 * num_sms() + slices - 1) / slices;
   if (ksplit > p.total_ktiles) ksplit = p.total_ktiles;
-  p.ksplit = ksplit < 1 ? 1 : ksplit;
+  if (ksplit < 1) ksplit = 1;
+  p.dw_numel = (long long)cout * cin_total * k * k;
+  if (wg_plan_split(&ksplit, p.dw_numel, ws, ws_bytes)) return -1;
+  p.ksplit = ksplit;
   p.off = x->halo - pad;
   p.cout = cout; p.cin = cin; p.cin_total = cin_total; p.cin_first = cin_first;
-  p.dw = dw; p.alpha = alpha; p.scale = scale;
+  p.dw = dw; p.partial = ws; p.alpha = alpha; p.scale = scale;
   p.err_sink = error_sink_device();
   CUtensorMap tmX, tmZ;
   {  // x, padded extent: {c, w, h, n}
@@ -551,6 +603,7 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
   dim3 grid((unsigned)p.ksplit, (unsigned)slices, 1u);
   conv_wgrad_patch_kernel<<<grid, 256, smem_bytes, stream>>>(tmX, tmZ, p);
   if (cudaGetLastError() != cudaSuccess) return set_error("conv2d_wgrad: patch kernel launch failed");
+  if (wg_reduce(dw, ws, p.dw_numel, p.ksplit, p.total_ktiles, cin_total, cin_first, cin, k, stream)) return -1;
   return 1;
 }
 
@@ -560,7 +613,7 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
 // E = uegan_dz_hstack(dz) (32 stored channels = (s, o) pairs): the patch kernel in vertical mode.
 extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tensor* e, int32_t cout, int32_t cin,
                                          int32_t cin_total, int32_t cin_first, int32_t k, int32_t pad, float* dw_oihw,
-                                         const float* alpha_dev, float scale, void* stream) {
+                                         const float* alpha_dev, float scale, float* ws, size_t ws_bytes, void* stream) {
   UEGAN_CHECK(x && e && x->data && e->data && dw_oihw, "conv2d_wgrad_hstack: null pointer");
   UEGAN_CHECK(x->dtype == UEGAN_F32 && e->dtype == UEGAN_F32 && x->c % 32 == 0 && e->c == 32 && e->halo == 0,
               "conv2d_wgrad_hstack: fp32 tensors, x.c %% 32 == 0, 32-channel stack without halo");
@@ -599,10 +652,13 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
   p.total_ktiles = p.tiles_w * p.tiles_h * p.nimg;
   int ksplit = (2 * num_sms() + slices - 1) / slices;
   if (ksplit > p.total_ktiles) ksplit = p.total_ktiles;
-  p.ksplit = ksplit < 1 ? 1 : ksplit;
+  if (ksplit < 1) ksplit = 1;
+  p.dw_numel = (long long)cout * cin_total * k * k;
+  if (wg_plan_split(&ksplit, p.dw_numel, ws, ws_bytes)) return -1;
+  p.ksplit = ksplit;
   p.off = x->halo - pad;
   p.cout = cout; p.cin = cin; p.cin_total = cin_total; p.cin_first = cin_first;
-  p.dw = dw_oihw; p.alpha = alpha_dev; p.scale = scale;
+  p.dw = dw_oihw; p.partial = ws; p.alpha = alpha_dev; p.scale = scale;
   p.err_sink = error_sink_device();
   CUtensorMap tmX, tmZ;
   {  // x, padded extent: {c, w, h, n}
@@ -632,5 +688,6 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
   dim3 grid((unsigned)p.ksplit, (unsigned)slices, 1u);
   conv_wgrad_patch_kernel<<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmX, tmZ, p);
   UEGAN_CUDA(cudaGetLastError());
-  return 0;
+  return wg_reduce(dw_oihw, ws, p.dw_numel, p.ksplit, p.total_ktiles, cin_total, cin_first, cin, k,
+                   static_cast<cudaStream_t>(stream));
 }

@@ -93,11 +93,14 @@ __global__ void sn_dot_kernel(const float* __restrict__ a, const float* __restri
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 __global__ void sn_rank1_kernel(float* __restrict__ a, const float* __restrict__ u, const float* __restrict__ v,
-                                const double* __restrict__ dot, const float* __restrict__ sigma, int rows, int cols) {
+                                const double* __restrict__ dot, const float* __restrict__ sigma, int rows, int cols,
+                                float* __restrict__ accum) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)rows * cols) return;
   const float coef = (float)(dot[0]) * sigma[1];  // <A, W> / sigma
-  a[i] -= coef * u[i / cols] * v[i % cols];
+  const float r = a[i] - coef * u[i / cols] * v[i % cols];
+  if (accum) accum[i] += r;  // straight into the optimizer's gradient bucket (a stays the per-pass scratch)
+  else a[i] = r;
 }
 
 }  // namespace uegan
@@ -128,7 +131,7 @@ extern "C" int uegan_spectral_sigma(const float* w, float* u, float* v, int32_t 
 }
 
 extern "C" int uegan_spectral_bwd(float* grad_inout, const float* w, const float* u, const float* v, const float* sigma,
-                                  int32_t rows, int32_t cols, double* ws, void* stream) {
+                                  int32_t rows, int32_t cols, double* ws, float* accum_out, void* stream) {
   UEGAN_CHECK(grad_inout && w && u && v && sigma && ws, "spectral_bwd: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long n = (long long)rows * cols;
@@ -136,7 +139,7 @@ extern "C" int uegan_spectral_bwd(float* grad_inout, const float* w, const float
   int blocks = (int)((n + 1023) / 1024);
   if (blocks > 256) blocks = 256;
   sn_dot_kernel<<<blocks, 256, 0, st>>>(grad_inout, w, n, ws);
-  sn_rank1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grad_inout, u, v, ws, sigma, rows, cols);
+  sn_rank1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grad_inout, u, v, ws, sigma, rows, cols, accum_out);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -289,6 +289,11 @@ def unpack_nchw(src: NHWC, c_off: int, c_count: int) -> torch.Tensor:
     return out
 
 
+def zero_(t: torch.Tensor):
+    """cudaMemsetAsync on the current stream (a memset node in a captured graph, not an ATen fill kernel)."""
+    L.check(L.load().uegan_memset_zero(t.data_ptr(), t.numel() * t.element_size(), _stream()), "memset_zero")
+
+
 def device_error() -> int:
     """Synchronises and returns the watchdog word (0 = no bounded wait expired)."""
     return L.load().uegan_device_error()
@@ -324,15 +329,20 @@ def gan_loss_fwd(mode: int, for_d: bool, real, fake, ws: torch.Tensor, loss_out:
                                        ws.data_ptr(), loss_out.data_ptr(), _stream()), "gan_loss_fwd")
         _count(3, "gan_loss_fwd")
         return 1
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
     rp, fp = _ptr_array(real), _ptr_array(fake)
+    if hasattr(group, "reduce"):  # uegan_b200.peer.PeerComm: sums over peer memory, no NCCL call
+        world = group.world
+        red = lambda lo, hi: group.reduce(ws, lo, hi)
+    else:
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        red = lambda lo, hi: dist.all_reduce(ws[lo:hi], group=group)
     L.check(lib.uegan_gan_loss_phase(0, mode, int(for_d), len(real), rp, fp, counts, world, ws.data_ptr(), None,
                                      _stream()), "gan_loss_phase0")
-    dist.all_reduce(ws[:16], group=group)
+    red(0, 16)
     L.check(lib.uegan_gan_loss_phase(1, mode, int(for_d), len(real), rp, fp, counts, world, ws.data_ptr(), None,
                                      _stream()), "gan_loss_phase1")
-    dist.all_reduce(ws[16:48], group=group)
+    red(16, 48)
     L.check(lib.uegan_gan_loss_phase(2, mode, int(for_d), len(real), rp, fp, counts, world, ws.data_ptr(),
                                      loss_out.data_ptr(), _stream()), "gan_loss_phase2")
     _count(3)
@@ -446,6 +456,25 @@ def conv_dgrad(dz: NHWC, weight: torch.Tensor, k: int, stride: int, dxp: NHWC, c
                          y_mul=stride, y_off_h=pi, y_off_w=pj, real_taps=nr)
 
 
+class _WgradWs:
+    """Split-K workspace of the weight-gradient kernels.  UEGAN_DETERMINISTIC=1 (default): every k-slice stores its partial
+    plane here and a second kernel sums the planes in slice order -- bit-reproducible runs, as the reference asks of cuDNN
+    (utils.py:154 cudnn.deterministic=True).  UEGAN_DETERMINISTIC=0: fp32 atomics, no workspace."""
+    BYTES = 96 << 20
+    buf = {}
+
+    @classmethod
+    def get(cls, device):
+        import os
+        if os.environ.get("UEGAN_DETERMINISTIC", "1") == "0":
+            return None, 0
+        key = str(device)
+        b = cls.buf.get(key)
+        if b is None:
+            b = cls.buf[key] = torch.empty(cls.BYTES // 4, dtype=torch.float32, device=device)
+        return b.data_ptr(), cls.BYTES
+
+
 def conv_wgrad(x: NHWC, dz: NHWC, dw: torch.Tensor, k: int, stride: int, pad: int, cin_first: int = 0,
                cin: Optional[int] = None, alpha=None, scale: float = 1.0):
     """dw (OIHW fp32, pre-zeroed or accumulating) += scale * alpha * wgrad(x, dz)."""
@@ -458,12 +487,12 @@ def conv_wgrad(x: NHWC, dz: NHWC, dw: torch.Tensor, k: int, stride: int, pad: in
         s0.record()
     L.check(L.load().uegan_conv2d_wgrad(x.ref(), dz.ref(), cout, cin_n, cin_total, cin_first, k, stride, pad,
                                         dw.data_ptr(), alpha.data_ptr() if alpha is not None else None, float(scale),
-                                        _stream()), "conv2d_wgrad")
+                                        *_WgradWs.get(dw.device), _stream()), "conv2d_wgrad")
     if ev is not None:
         s1.record()
         real_cin = 3 if x.c == 4 else cin_n
         ev.append((s0, s1, 2.0 * dz.n * dz.h * dz.w * cout * real_cin * k * k, x, cout, k, stride, "wgrad", x.dtype))
-    _count(1, f"wgrad cout{cout} cin{cin_n} k{k}s{stride}", x, dz)
+    _count(2 if _WgradWs.buf else 1, f"wgrad cout{cout} cin{cin_n} k{k}s{stride}", x, dz)
 
 
 def head_bwd(dout: torch.Tensor, out: torch.Tensor, x, mode: int, dz: NHWC):
@@ -509,12 +538,13 @@ def conv_wgrad_hstack(x: NHWC, e: NHWC, dw: torch.Tensor, k: int, pad: int, alph
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
     L.check(L.load().uegan_conv2d_wgrad_hstack(x.ref(), e.ref(), cout, cin_total, cin_total, 0, k, pad, dw.data_ptr(),
-                                               alpha.data_ptr() if alpha is not None else None, float(scale), _stream()),
+                                               alpha.data_ptr() if alpha is not None else None, float(scale),
+                                               *_WgradWs.get(dw.device), _stream()),
             "conv2d_wgrad_hstack")
     if ev is not None:
         s1.record()
         ev.append((s0, s1, 2.0 * x.n * x.h * x.w * cout * cin_total * k * k, x, cout, k, 1, "wgrad", x.dtype))
-    _count(1, f"wgrad_hstack cout{cout} cin{cin_total} k{k}", x, e)
+    _count(2 if _WgradWs.buf else 1, f"wgrad_hstack cout{cout} cin{cin_total} k{k}", x, e)
 
 
 def hstack_ok(cout: int, cin_stored: int, k: int) -> bool:
@@ -523,10 +553,13 @@ def hstack_ok(cout: int, cin_stored: int, k: int) -> bool:
             and cin_stored % 32 == 0)
 
 
-def channel_sum(src: NHWC, out: torch.Tensor, c_off: int = 0, channels: Optional[int] = None):
+def channel_sum(src: NHWC, out: torch.Tensor, c_off: int = 0, channels: Optional[int] = None, accumulate: bool = False):
+    """out[c] (+)= sum over pixels of src[.., c_off + c]; `channels` stored channels are reduced, the first out.numel()
+    of them are written."""
     channels = out.numel() if channels is None else channels
-    assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
-    L.check(L.load().uegan_channel_sum(src.ref(), c_off, channels, out.data_ptr(), _stream()), "channel_sum")
+    assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() <= channels
+    L.check(L.load().uegan_channel_sum(src.ref(), c_off, channels, out.data_ptr(), out.numel(), int(accumulate),
+                                       _stream()), "channel_sum")
     _count(1, f"channel_sum c{channels}", src)
 
 
@@ -556,14 +589,19 @@ def in_mse_bwd(x: NHWC, y: NHWC, mr_x: int, mr_y: int, weight: float, gscale, de
     _count(2, f"in_mse_bwd{' +deep' if deep is not None else ''}", x)
 
 
-def unpack_input_grad(dx: NHWC, scale, out: torch.Tensor):
-    L.check(L.load().uegan_unpack_input_grad(dx.ref(), L.float3(scale), out.data_ptr(), _stream()), "unpack_input_grad")
+def unpack_input_grad(dx: NHWC, scale, out: torch.Tensor, skip=None):
+    """skip = (dout, res, x) fp32 NCHW: adds the Generator's identity path clamp(res + x) (models.py:72)."""
+    sk = [t.data_ptr() for t in skip] if skip is not None else [None, None, None]
+    L.check(L.load().uegan_unpack_input_grad(dx.ref(), L.float3(scale), out.data_ptr(), *sk, _stream()),
+            "unpack_input_grad")
     _count(1, "unpack_input_grad", dx)
 
 
 def spectral_bwd(grad: torch.Tensor, w: torch.Tensor, u: torch.Tensor, v: torch.Tensor, sigma: torch.Tensor,
-                 ws: torch.Tensor):
+                 ws: torch.Tensor, accum: Optional[torch.Tensor] = None):
+    """In place on `grad`, or (accum given) accum += result with `grad` left as the per-pass scratch."""
     rows = w.shape[0]
     L.check(L.load().uegan_spectral_bwd(grad.data_ptr(), w.data_ptr(), u.data_ptr(), v.data_ptr(), sigma.data_ptr(),
-                                        rows, w.numel() // rows, ws.data_ptr(), _stream()), "spectral_bwd")
+                                        rows, w.numel() // rows, ws.data_ptr(),
+                                        accum.data_ptr() if accum is not None else None, _stream()), "spectral_bwd")
     _count(2, "spectral_bwd")

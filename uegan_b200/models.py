@@ -83,9 +83,14 @@ class _ParamCache:
 
     def __init__(self):
         self.store = {}
+        self.epoch = 0
+
+    def bump(self):
+        """The parameters were rewritten by a kernel torch does not see (uegan_adam_step): every operand is stale."""
+        self.epoch += 1
 
     def get(self, key, param, fn):
-        tag = (param.data_ptr(), param._version)
+        tag = (param.data_ptr(), param._version, self.epoch)
         hit = self.store.get(key)
         if hit is None:
             hit = (tag, fn())

@@ -50,9 +50,11 @@ class ImagePool:
 
 
 class _FlatGrads:
-    """All gradients of a module in ONE flat fp32 bucket (p.grad are views), so a step needs one all-reduce."""
+    """All gradients of a module in ONE flat fp32 bucket (p.grad are views), so a step needs one all-reduce (RMSprop
+    branch; the Adam branch uses uegan_b200.optim.FlatBucket / FlatAdam)."""
 
-    def __init__(self, module):
+    def __init__(self, module, group=None):
+        self.group = group
         self.params = [p for p in module.parameters() if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
@@ -61,12 +63,13 @@ class _FlatGrads:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
 
-    def zero(self):
+    def zero_grad(self):
         self.flat.zero_()
 
-    def all_reduce(self, group):
-        import torch.distributed as dist
-        dist.all_reduce(self.flat, group=group)
+    def all_reduce(self):
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat, group=self.group)
 
 
 def init_weights(net, init_type="orthogonal", gain=0.02):
@@ -122,25 +125,48 @@ class Trainer(object):
             import torch.distributed as dist
             for t in list(self.G.state_dict().values()) + list(self.D.state_dict().values()):
                 dist.broadcast(t, src=0, group=self.group)
-        cap = bool(getattr(a, "cuda_graph", False))  # device-side step counters so that Adam.step() can be captured
+        # Data-parallel reductions over peer memory (NVLink / NVSwitch): gradient buckets and the GAN-loss partial sums
+        # live in symmetric memory and are summed inside our own kernels; NCCL remains the fallback
+        # (args.peer_reduce=False, or no symmetric-memory support).
+        self.comm = None
+        if self.group is not None and getattr(a, "peer_reduce", True):
+            try:
+                from .peer import PeerComm
+                self.comm = PeerComm(self.group)
+            except Exception as e:  # noqa: BLE001
+                import warnings
+                warnings.warn(f"uegan_b200: peer-memory reductions unavailable ({type(e).__name__}: {e}); using NCCL")
         if a.optimizer_type == "adam":
-            opt = lambda p, lr: torch.optim.Adam(params=p, lr=lr, betas=[a.beta1, a.beta2], weight_decay=0.0001,
-                                                 capturable=cap, foreach=True)
+            from .optim import FlatAdam, FlatBucket
+            galloc = self.comm.alloc if self.comm is not None else None
+            self.g_grads, self.d_grads = FlatBucket(self.G, galloc), FlatBucket(self.D, galloc)
+
+            def opt(bucket, lr, net):
+                before = after = peers = None
+                if self.comm is not None:
+                    peers, before, after = self.comm.peer_ptrs(bucket.grad), self.comm.barrier, self.comm.barrier
+                elif self.group is not None:
+                    import torch.distributed as dist
+                    before = lambda: dist.all_reduce(bucket.grad, group=self.group)
+                return FlatAdam(bucket, lr=lr, betas=[a.beta1, a.beta2], weight_decay=0.0001, peers=peers,
+                                before_step=before, after_step=after, on_update=net._wcache.bump)
+            self.g_optimizer, self.d_optimizer = opt(self.g_grads, a.g_lr, self.G), opt(self.d_grads, a.d_lr, self.D)
         elif a.optimizer_type == "rmsprop":
-            opt = lambda p, lr: torch.optim.RMSprop(params=p, lr=lr, alpha=a.alpha)
+            # non-default branch (trainer.py:340-342): torch's RMSprop on flat gradient buckets, NCCL all-reduce
+            self.g_grads, self.d_grads = _FlatGrads(self.G, self.group), _FlatGrads(self.D, self.group)
+            self.g_optimizer = torch.optim.RMSprop(params=self.G.parameters(), lr=a.g_lr, alpha=a.alpha)
+            self.d_optimizer = torch.optim.RMSprop(params=self.D.parameters(), lr=a.d_lr, alpha=a.alpha)
         else:
             raise NotImplementedError("=== Optimizer [{}] is not found ===".format(a.optimizer_type))
-        self.g_optimizer, self.d_optimizer = opt(self.G.parameters(), a.g_lr), opt(self.D.parameters(), a.d_lr)
         if a.lr_decay:
             rule = lambda epoch: 1.0 - max(0, epoch + 1 - a.lr_num_epochs_decay) / a.lr_decay_ratio
             self.lr_scheduler_g = torch.optim.lr_scheduler.LambdaLR(self.g_optimizer, lr_lambda=rule)
             self.lr_scheduler_d = torch.optim.lr_scheduler.LambdaLR(self.d_optimizer, lr_lambda=rule)
         self.fake_exp_pool = ImagePool(a.pool_size)
-        self.g_grads, self.d_grads = _FlatGrads(self.G), _FlatGrads(self.D)
         self.criterionPercep = PerceptualLoss(self.vgg_state_dict).to(self.device)
         self.criterionIdt = MultiscaleRecLoss(scale=3, rec_loss_type=a.idt_loss_type, multiscale=True)
         self.criterionGAN = GANLoss(a.adv_loss_type, tensor=torch.cuda.FloatTensor)
-        self.criterionGAN.process_group = self.group
+        self.criterionGAN.process_group = self.comm if self.comm is not None else self.group
 
     # ------------------------------------------------------------------ trainer.py:75-119
     def train_step(self, real_raw, real_exp, sync_scalars=True):
@@ -153,7 +179,7 @@ class Trainer(object):
         self.fake_exp = self.G(real_raw)
         self.fake_exp_store = self.fake_exp_pool.query(self.fake_exp)
         # ---- update D
-        self.d_grads.zero()
+        self.d_grads.zero_grad()
         real_exp_preds = self.D(real_exp)
         fake_exp_preds = self.D(self.fake_exp_store.detach())
         d_loss = gan(real_exp_preds, fake_exp_preds, None, None, for_discriminator=True)
@@ -161,11 +187,11 @@ class Trainer(object):
             input_preds = self.D(real_raw)
             d_loss = d_loss + gan(real_exp_preds, input_preds, None, None, for_discriminator=True)
         d_loss.backward()
-        if self.group is not None:
-            self.d_grads.all_reduce(self.group)
-        self.d_optimizer.step()
+        if isinstance(self.d_grads, _FlatGrads):
+            self.d_grads.all_reduce()
+        self.d_optimizer.step()  # FlatAdam: gradient reduction (peer memory or NCCL) + Adam, trainer.py:97
         # ---- update G
-        self.g_grads.zero()
+        self.g_grads.zero_grad()
         # The reference lets g_loss.backward() also fill D's parameter gradients and then discards them at the next
         # d_optimizer.zero_grad() (trainer.py:89).  Same result without the wasted weight-gradient
         # GEMMs: D's parameters are frozen for these two forwards (the gradient w.r.t. fake_exp still flows).
@@ -184,8 +210,8 @@ class Trainer(object):
         g_idt_loss = a.lambda_idt * self.criterionIdt(self.real_exp_idt, real_exp)
         g_loss = g_adv_loss + local * (g_percep_loss + g_idt_loss)
         g_loss.backward()
-        if self.group is not None:
-            self.g_grads.all_reduce(self.group)
+        if isinstance(self.g_grads, _FlatGrads):
+            self.g_grads.all_reduce()
         self.g_optimizer.step()
         vals = dict(d_loss=d_loss, g_adv_loss=g_adv_loss, g_percep_loss=g_percep_loss, g_idt_loss=g_idt_loss,
                     g_loss=g_adv_loss + g_percep_loss + g_idt_loss)
@@ -197,12 +223,15 @@ class Trainer(object):
 
     # ------------------------------------------------------------------ whole step as a CUDA graph
     def capture(self, real_raw, real_exp, warmup=3):
-        """Captures train_step (2 G + 5 D + 2 VGG forwards, all backwards, both Adam steps, the NCCL all-reduces) into
-        one CUDA graph.  ~1000 kernel launches per step otherwise cost more host time than the GPU needs to run them.
-        Requires pool_size == 0 (ImagePool is host logic) and args.cuda_graph=True at construction (capturable Adam).
+        """Captures train_step (2 G + 5 D + 2 VGG forwards, all backwards, both fused reduce+Adam steps) into one CUDA
+        graph.  ~1000 kernel launches per step otherwise cost more host time than the GPU needs to run them.  With the
+        peer-memory reductions there is no NCCL call inside the step, so the capture works at any world size.
+        Requires pool_size == 0 (ImagePool is host logic).
         Afterwards `replay(real_raw, real_exp)` copies the batch into the static input buffers and launches the graph;
         the five losses come back as 0-d CUDA tensors (no host sync)."""
-        assert self.args.pool_size == 0 and getattr(self.args, "cuda_graph", False)
+        assert self.args.pool_size == 0
+        if self.group is not None and self.comm is None:
+            raise RuntimeError("CUDA-graph capture at world size > 1 needs the peer-memory reductions (NCCL fallback active)")
         self._gx, self._gy = real_raw.clone(), real_exp.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -219,6 +248,9 @@ class Trainer(object):
         return self._graph
 
     def replay(self, real_raw, real_exp, sync_scalars=False):
+        for o in (self.g_optimizer, self.d_optimizer):
+            if hasattr(o, "sync_lr"):
+                o.sync_lr()  # a scheduler may have changed the learning rate: host -> device scalar, outside the graph
         self._gx.copy_(real_raw, non_blocking=True)
         self._gy.copy_(real_exp, non_blocking=True)
         self._graph.replay()
