@@ -341,16 +341,22 @@ def run_native(args):
         G = Generator(32, "none", "LeakyReLU", False)
         G.load_state_dict(O.make_generator_params(32, 0, "o1"))
         G = G.cuda().eval()
-        out_host = torch.empty_like(x_host).pin_memory()
+        # e2e = the deployment path: uint8 HWC images in pinned host memory -> H2D -> uegan_pack_input_u8 -> Generator ->
+        # uegan_unpack_output_u8 -> D2H, double-buffered so that the copies overlap the compute (uegan_b200.io.U8Pipeline;
+        # SURVEY.md 8f N3).  Every step moves a fresh batch in and its result out inside the timed region.
+        from uegan_b200 import io as IO
+        img_host = ((x_host + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory()
+        out_host = [torch.empty_like(img_host).pin_memory() for _ in range(2)]
+        pipe = IO.U8Pipeline(G)
+        e2e_i = [0]
 
         def step_resident():
             return G(x)
 
         def step_e2e():
-            out = G(x_host.cuda(non_blocking=True))
-            out_host.copy_(out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        h2d, d2h = x_host.numel() * 4, x_host.numel() * 4
+            pipe.submit(img_host, out_host[e2e_i[0] % 2])
+            e2e_i[0] += 1
+        h2d, d2h = img_host.numel(), img_host.numel()
         gflop = G_GFLOP_PER_IMAGE
         ctx = torch.no_grad
         graphed = False
@@ -362,7 +368,7 @@ def run_native(args):
 
     host_ms = [0.0]
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, finish=None):
         with ctx():
             for _ in range(warmup):
                 fn()
@@ -374,6 +380,8 @@ def run_native(args):
             for _ in range(steps):
                 fn()
             host_ms[0] = (time.perf_counter() - h0) * 1e3 / steps  # time to ENQUEUE a step (no sync inside fn)
+            if finish is not None:
+                finish()  # e.g. the timing stream waits for the last device->host copy of a pipelined run
             e1.record()
             barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -387,7 +395,8 @@ def run_native(args):
     ms_total, launches = timed(step_resident, args.steps, args.warmup)
     host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if sampler else None
-    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 1))
+    fin = None if train else (lambda: torch.cuda.current_stream().wait_stream(pipe.s_out))
+    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 1), finish=fin)
 
     roof = None
     # instrumented pass after the timed regions: CUDA events around every GEMM launch.  Every rank runs it (the step
@@ -448,6 +457,8 @@ def run_native(args):
                     "grad_reduce": ("single GPU" if world == 1 else
                                     ("peer memory (NVLink), fused into uegan_adam_step_peers" if T.comm is not None
                                      else "NCCL all-reduce + uegan_adam_step"))}
+    gd_prec = (T.G.precision if train else G.precision)
+    gd_prec = "f16 operands with per-tensor 2^k scales" if gd_prec == "f16" else "tf32"
     if rank == 0:
         cpu_threads = os.cpu_count() or 1
         cpu_batch = 1 if train else 2
@@ -462,7 +473,7 @@ def run_native(args):
             "metric": "512x512 training images/sec" if train else "512x512 images/sec", "value": value,
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 (G, D) + f16 (VGG), fp32 accumulate" if train else "tf32", "data": "synthetic",
+            "dtype": (f"{gd_prec} (G, D) + f16 (VGG), fp32 accumulate" if train else gd_prec), "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "batch_per_gpu": batch, "global_batch": world * batch,
                        "parallelism": (f"dp{world}: per optimizer one fused gradient-reduction + Adam kernel over "
                                        f"{'peer memory' if (world > 1 and T.comm is not None) else ('NCCL' if world > 1 else 'one GPU')}"

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UEGAN_ABI_VERSION 2
+#define UEGAN_ABI_VERSION 3
 
 enum { UEGAN_F32 = 0, UEGAN_BF16 = 1, UEGAN_F16 = 2 };  /* storage dtype; F32 tensors feed kind::tf32 MMAs, the
                                                            16-bit types kind::f16 */
@@ -37,6 +37,11 @@ typedef struct uegan_tensor {
   int32_t c;       /* stored channels per pixel (c * sizeof(dtype) must be a multiple of 16) */
   int32_t halo;    /* halo pixels on each side */
   int32_t dtype;   /* UEGAN_F32 | UEGAN_BF16 | UEGAN_F16 */
+  const float* scale; /* NULL, or a DEVICE scalar s > 0 (a power of two): the stored values are s * the true values.
+                         fp16 tensors of the Generator / Discriminator carry one (their magnitudes follow the weights: 3e-9
+                         after five layers of the reference's orthogonal(0.02) init, far below fp16's range); every kernel
+                         divides it out of what it loads and multiplies its output by the destination's scale, exactly
+                         (powers of two), so results are those of the unscaled arithmetic.  uegan_scale_update maintains it. */
 } uegan_tensor;
 
 /* One implicit-GEMM convolution (tcgen05.mma + TMA), forward.
@@ -57,6 +62,7 @@ typedef struct uegan_conv_desc {
   int32_t pad;          /* (k-1)/2 in the reference, must be <= x.halo */
   int32_t act;          /* UEGAN_ACT_* */
   const void* w_packed; /* from uegan_pack_conv_weight, same dtype as x */
+  const float* w_scale; /* NULL, or the device scalar the packed weight was multiplied by (uegan_pack_conv_weight_scaled) */
   const float* bias;    /* [cout] fp32 or NULL */
   const float* alpha;   /* device scalar (1/sigma of spectral norm, models.py:185-188) or NULL (=1) */
   const uegan_tensor* mul;     /* optional: y *= mul[n,ho,wo,co] after the activation (y4.mul(x1), models.py:70) */
@@ -97,6 +103,32 @@ int uegan_pack_conv_weight(const float* w_oihw, void* w_packed, int32_t cout, in
 int uegan_pack_conv_weight_dgrad(const float* w_oihw, void* w_packed, int32_t cout_orig, int32_t cin_total,
                                  int32_t cin_first, int32_t cin, int32_t cout_stored, int32_t k_orig, int32_t stride,
                                  int32_t pi, int32_t pj, int32_t dtype, void* stream);
+/* Both packers with a scale: the packed values are w * (*w_scale_dev) (a device scalar maintained by
+ * uegan_scale_update on the fp32 master weight); pass the same pointer as conv_desc.w_scale. */
+int uegan_pack_conv_weight_scaled(const float* w_oihw, void* w_packed, int32_t cout, int32_t cin_total, int32_t cin_first,
+                                  int32_t cin, int32_t cin_stored, int32_t k, int32_t dtype, const float* w_scale_dev,
+                                  void* stream);
+int uegan_pack_conv_weight_dgrad_scaled(const float* w_oihw, void* w_packed, int32_t cout_orig, int32_t cin_total,
+                                        int32_t cin_first, int32_t cin, int32_t cout_stored, int32_t k_orig,
+                                        int32_t stride, int32_t pi, int32_t pj, int32_t dtype, const float* w_scale_dev,
+                                        void* stream);
+
+/* Per-tensor power-of-two scales (uegan_tensor.scale), maintained on the device so that CUDA-graph replays need no host
+ * work.  One entry per tensor: the kernel samples up to `max_samples` stored values evenly across the buffer, takes
+ * their largest magnitude, and sets  *scale = 2^floor(log2(target / (amax_stored / *scale)))  -- the scale the NEXT
+ * pass uses (delayed scaling: magnitudes drift slowly, `target` = 2^10 leaves a 64x margin below fp16's 65504).  A sample
+ * that overflowed (inf / nan) divides the scale by 2^8; an all-zero 16-bit sample multiplies it by 2^8 (underflow: the next
+ * pass measures again), an all-zero fp32 sample leaves it unchanged.  dtype F32 entries are
+ * fp32 buffers (master weights: their scale is what the packers multiply by). */
+typedef struct uegan_scale_entry {
+  const void* data;   /* device buffer */
+  int64_t numel;      /* elements in the buffer */
+  int32_t dtype;      /* UEGAN_F32 | UEGAN_F16 | UEGAN_BF16 */
+  int32_t reserved;   /* 0: the buffer holds stored (= scale * true) values; 1: it holds TRUE values (fp32 master weights whose
+                         scale is what uegan_pack_conv_weight*_scaled multiplies by) */
+  float* scale;       /* device scalar to update */
+} uegan_scale_entry;
+int uegan_scale_update(const uegan_scale_entry* entries_dev, int32_t count, float target, int32_t max_samples, void* stream);
 
 int uegan_conv2d_fprop(const uegan_conv_desc* desc, void* stream);
 
@@ -113,6 +145,11 @@ size_t uegan_packed_weight_rowsum_bytes(int32_t cout, int32_t cin_stored, int32_
 /* OIHW fp32 -> [(s, o) rows padded to a multiple of 16][r][cin_stored] tf32. */
 int uegan_pack_conv_weight_rowsum(const float* w_oihw, void* w_packed, int32_t cout, int32_t cin_total, int32_t cin_first,
                                   int32_t cin, int32_t cin_stored, int32_t k, void* stream);
+/* The same operand multiplied by a device scalar and stored as `dtype` (UEGAN_F32: tf32-rounded; UEGAN_F16: rows padded to
+ * whole 64-channel chunks) -- the fp16 row-sum path; pass the scalar as conv_desc.w_scale. */
+int uegan_pack_conv_weight_rowsum_scaled(const float* w_oihw, void* w_packed, int32_t cout, int32_t cin_total,
+                                         int32_t cin_first, int32_t cin, int32_t cin_stored, int32_t k, int32_t dtype,
+                                         const float* w_scale_dev, void* stream);
 int uegan_conv2d_fprop_rowsum(const uegan_conv_desc* desc, void* stream);
 
 /* EXPERIMENTAL, opt-in (environment UEGAN_ROWSUM_NHWC=1; otherwise ..._supported() returns 0 and nothing below is used):
@@ -271,6 +308,9 @@ int uegan_adam_step_peers(float* param, const float* const* peer_grads_host, int
 int uegan_peer_sum_f64(double* out, const double* const* peers_host, int32_t world, int32_t count, void* stream);
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream`: zeroing of gradient buckets / per-pass scratch (torch zero_() replacement). */
 int uegan_memset_zero(void* ptr, size_t bytes, void* stream);
+/* cudaStreamIsCapturing(stream): 0 = not capturing, 1 = capture active, 2 = capture invalidated (debug aid: which call broke
+ * a CUDA-graph capture), -1 = query failed. */
+int uegan_capture_status(void* stream);
 
 /* ---- the conversions either side of the hot path -------------------------------------------------
  * uint8 HWC RGB batch (n x h x w x 3, device memory) -> what transforms.ToTensor() + Normalize(mean, std) produce

@@ -91,7 +91,8 @@ def test_shape_policy_entry_points_without_gpu(monkeypatch):
     assert lib.uegan_conv2d_rowsum_supported(3, 32, 7, L.F32) == 1
     assert lib.uegan_conv2d_rowsum_supported(1, 256, 5, L.F32) == 1
     assert lib.uegan_conv2d_rowsum_supported(1, 512, 5, L.F32) == 0
-    assert lib.uegan_conv2d_rowsum_supported(3, 32, 7, L.F16) == 0
+    assert lib.uegan_conv2d_rowsum_supported(3, 32, 7, L.F16) == 1  # fp16 operands: 64-channel chunks
+    assert lib.uegan_conv2d_rowsum_supported(1, 512, 5, L.F16) == 1  # half the bytes: the deepest head fits too
     assert lib.uegan_conv2d_rowsum_supported(32, 32, 3, L.F32) == 0
     monkeypatch.setenv("UEGAN_NO_ROWSUM", "1")
     assert lib.uegan_conv2d_rowsum_supported(3, 32, 7, L.F32) == 0
@@ -106,7 +107,7 @@ def test_shape_policy_entry_points_without_gpu(monkeypatch):
     assert lib.uegan_conv2d_rowsum_nhwc_supported(64, 128, 3, L.F32) == 0  # dec3: weights do not fit
     assert lib.uegan_conv2d_rowsum_nhwc_supported(32, 64, 7, L.F32) == 0
     assert lib.uegan_packed_weight_rowsum_nhwc_bytes(32, 64) == 3 * 32 * 3 * 64 * 4
-    assert lib.uegan_packed_weight_rowsum_bytes(3, 32, 7) == 32 * 7 * 32 * 4
+    assert lib.uegan_packed_weight_rowsum_bytes(3, 32, 7) == 32 * 7 * 64 * 4  # sized for fp32 rows or fp16 rows padded to 64 channels
     # statistics policy (kernels.fused_stats_ok): separate pass by default
     monkeypatch.delenv("UEGAN_FUSED_STATS", raising=False)
     assert K.fused_stats_ok(512, 512, 64) is False

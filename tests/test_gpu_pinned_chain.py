@@ -52,13 +52,15 @@ def rconv(x, w, b, stride=1):
 
 
 # ------------------------------------------------------------------------------------------------ Generator
+@pytest.mark.parametrize("precision", ["tf32", "f16"])
 @pytest.mark.parametrize("regime", ["o1", "tiny"])
-def test_generator_backward_chain_pinned(regime):
+def test_generator_backward_chain_pinned(regime, precision):
     from uegan_b200 import kernels as K
     from uegan_b200.models import Generator
     gp = O.make_generator_params(32, 0, regime)
     G = Generator(32, "none", "LeakyReLU", False)
     G.load_state_dict(gp)
+    G.precision = precision
     G = G.cuda().train()
     b, h, w = 2, 128, 128
     x = O.make_images((b, 3, h, w), 7).cuda().requires_grad_(True)
@@ -66,7 +68,7 @@ def test_generator_backward_chain_pinned(regime):
     out = G(x)
     out.backward(gout)
     assert K.device_error() == 0
-    ws = G._train_pool[(b, h, w, str(x.device))][-1]
+    ws = G._train_pool[(b, h, w, str(x.device), precision)][-1]
     A = lambda t: t.interior_nchw()
     nat = dict(x1=A(ws["x1"]), x2=A(ws["x2"]), x3=A(ws["x3"]), x4=A(ws["x4"]), x5=A(ws["x5"]), y1=A(ws["y"][0]),
                y2=A(ws["y"][1]), y3=A(ws["y"][2]), y4=A(ws["y"][3]), t=A(ws["t"]))
@@ -126,18 +128,20 @@ def test_generator_backward_chain_pinned(regime):
             worst = (name, e)
         assert e < 2e-3, f"{regime} {name}: rel-L2 {e:.3e}"
     e_dx = rel_l2(x.grad, xo.grad)
-    print(f"[{regime}] G pinned chain: worst parameter gradient {worst[0]} {worst[1]:.3e}; dL/dx {e_dx:.3e}")
+    print(f"[{regime} {precision}] G pinned chain: worst parameter gradient {worst[0]} {worst[1]:.3e}; dL/dx {e_dx:.3e}")
     assert e_dx < 2e-3, e_dx
 
 
 # ------------------------------------------------------------------------------------------------ Discriminator
+@pytest.mark.parametrize("precision", ["tf32", "f16"])
 @pytest.mark.parametrize("regime", ["o1", "tiny"])
-def test_discriminator_backward_chain_pinned(regime):
+def test_discriminator_backward_chain_pinned(regime, precision):
     from uegan_b200 import kernels as K
     from uegan_b200.models import Discriminator
     dp = O.make_discriminator_params(32, 1, regime)
     D = Discriminator(32, "none", "LeakyReLU", True, "rahinge")
     D.load_state_dict(dp)
+    D.precision = precision
     D = D.cuda().train()
     b, h, w = 2, 128, 128
     x = O.make_images((b, 3, h, w), 9).cuda().requires_grad_(True)
@@ -145,7 +149,7 @@ def test_discriminator_backward_chain_pinned(regime):
     gouts = [O.make_images(tuple(q.shape), 20 + i).cuda() for i, q in enumerate(preds)]
     torch.autograd.backward(preds, gouts)
     assert K.device_error() == 0
-    ws = D._train_pool[(b, h, w, str(x.device))][-1]
+    ws = D._train_pool[(b, h, w, str(x.device), precision)][-1]
     nat = [t.interior_nchw() for t in ws["ds"]]
     masks = [slope(t) for t in nat]
 
@@ -168,7 +172,7 @@ def test_discriminator_backward_chain_pinned(regime):
             worst = (name, e)
         assert e < 2e-3, f"{regime} {name}: rel-L2 {e:.3e}"
     e_dx = rel_l2(x.grad, xo.grad)
-    print(f"[{regime}] D pinned chain: worst parameter gradient {worst[0]} {worst[1]:.3e}; dL/dx {e_dx:.3e}")
+    print(f"[{regime} {precision}] D pinned chain: worst parameter gradient {worst[0]} {worst[1]:.3e}; dL/dx {e_dx:.3e}")
     assert e_dx < 2e-3, e_dx
 
 

@@ -117,6 +117,28 @@ def test_train_step_vs_golden():
     assert rel(dsd["d1.0.1.weight_u"], g["step_post_d1_u"]) < 1e-2
 
 
+def test_train_step_f16_vs_golden():
+    """The same reference-shaped loop with fp16 operands in G and D (per-tensor power-of-two scales, kind::f16 fprop / dgrad /
+    wgrad): step-0 losses against the reference's golden run at the north-star tolerance."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from uegan_b200 import kernels as K
+    g = np.load(os.path.join(GOLD, "golden_o1.npz"))
+    G, D, P, gl, ms = build()
+    G.precision = D.precision = "f16"
+    g_opt = torch.optim.Adam(G.parameters(), lr=1e-4, betas=[0.5, 0.999], weight_decay=0.0001)
+    d_opt = torch.optim.Adam(D.parameters(), lr=4e-4, betas=[0.5, 0.999], weight_decay=0.0001)
+    raw = O.make_images((2, 3, 128, 128), 40).cuda()
+    exp = O.make_images((2, 3, 128, 128), 41).cuda()
+    for step in range(2):
+        losses = train_step(G, D, P, gl, ms, g_opt, d_opt, raw, exp)
+        assert K.device_error() == 0
+        ref = g[f"step{step}_losses"]
+        errs = [abs(a - b) / abs(b) for a, b in zip(losses, ref)]
+        print(f"[f16] step {step}: losses {['%.6f' % v for v in losses]} ref {['%.6f' % v for v in ref]} rel {['%.2e' % e for e in errs]}")
+        assert max(errs) < (1e-3 if step == 0 else 3e-2)
+
+
 def test_backward_pieces_vs_oracle():
     """Gradients of each stack separately against torch.autograd on the CPU oracle (localises a failing kernel)."""
     if not torch.cuda.is_available():

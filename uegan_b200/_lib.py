@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libuegan_sm100.so")
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 PAD_ZERO, PAD_REFLECT = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class UeganError(RuntimeError):
@@ -23,13 +23,18 @@ class UeganError(RuntimeError):
 
 class Tensor(C.Structure):
     _fields_ = [("data", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
-                ("halo", C.c_int32), ("dtype", C.c_int32)]
+                ("halo", C.c_int32), ("dtype", C.c_int32), ("scale", C.c_void_p)]
+
+
+class ScaleEntry(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("numel", C.c_int64), ("dtype", C.c_int32), ("reserved", C.c_int32),
+                ("scale", C.c_void_p)]
 
 
 class ConvDesc(C.Structure):
     _fields_ = [("x", Tensor), ("y", Tensor), ("y_c_off", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32),
                 ("stride", C.c_int32), ("pad", C.c_int32), ("act", C.c_int32), ("w_packed", C.c_void_p),
-                ("bias", C.c_void_p), ("alpha", C.c_void_p), ("mul", C.POINTER(Tensor)), ("out_nchw", C.c_void_p),
+                ("w_scale", C.c_void_p), ("bias", C.c_void_p), ("alpha", C.c_void_p), ("mul", C.POINTER(Tensor)), ("out_nchw", C.c_void_p),
                 ("residual_nchw", C.c_void_p), ("aux_nchw", C.c_void_p), ("y_mul", C.c_int32), ("y_off_h", C.c_int32), ("y_off_w", C.c_int32),
                 ("mask", C.POINTER(Tensor)), ("mask_act", C.c_int32), ("in_stats", C.c_void_p)]
 
@@ -42,10 +47,14 @@ SYMBOLS = {
     "uegan_packed_weight_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "uegan_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "uegan_pack_conv_weight_scaled": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p, C.c_void_p]),
+    "uegan_pack_conv_weight_dgrad_scaled": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 10 + [C.c_void_p, C.c_void_p]),
+    "uegan_scale_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "uegan_conv2d_fprop": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "uegan_conv2d_rowsum_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "uegan_packed_weight_rowsum_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "uegan_pack_conv_weight_rowsum": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
+    "uegan_pack_conv_weight_rowsum_scaled": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p, C.c_void_p]),
     "uegan_conv2d_fprop_rowsum": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "uegan_conv2d_rowsum_nhwc_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "uegan_packed_weight_rowsum_nhwc_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
@@ -105,6 +114,7 @@ SYMBOLS = {
     "uegan_adam_step_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p]),
     "uegan_peer_sum_f64": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p]),
+    "uegan_capture_status": (C.c_int, [C.c_void_p]),
     "uegan_memset_zero": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "uegan_pack_input_u8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Tensor), C.c_void_p, C.c_int32,
                                       C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]),
@@ -135,10 +145,20 @@ def load():
     return lib
 
 
+_DEBUG_CAPTURE = os.environ.get("UEGAN_DEBUG_CAPTURE") == "1"
+_last_ok = [""]
+
+
 def check(rc: int, what: str = ""):
     if rc != 0:
         msg = load().uegan_last_error()
         raise UeganError(f"{what}: {msg.decode() if msg else rc}")
+    if _DEBUG_CAPTURE:  # pinpoints the call after which a CUDA-graph capture turned invalid
+        import torch
+        st = load().uegan_capture_status(torch.cuda.current_stream().cuda_stream)
+        if st == 2 or st < 0:
+            raise UeganError(f"capture invalid (status {st}) after `{what}` (last good call: `{_last_ok[0]}`)")
+        _last_ok[0] = what
 
 
 def float3(v):

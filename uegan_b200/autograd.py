@@ -23,16 +23,24 @@ F32 = L.F32
 
 
 class _Scratch:
-    """Gradient scratch buffers, reused across calls (backward passes run one at a time)."""
+    """Gradient scratch buffers, reused across calls (backward passes run one at a time).  With a ScaleBook every buffer
+    gets its own power-of-two scale slot (fp16 gradients); `share` makes a buffer use another buffer's slot."""
 
-    def __init__(self):
+    def __init__(self, book=None):
         self.store = {}
+        self.book = book
 
-    def get(self, name, n, h, w, c, halo=0, dtype=F32, device="cuda", zero=False):
+    def get(self, name, n, h, w, c, halo=0, dtype=F32, device="cuda", zero=False, share=None):
         key = (name, n, h, w, c, halo, dtype, str(device))
         t = self.store.get(key)
         if t is None:
-            t = K.NHWC(n, h, w, c, halo, dtype, device, zero=zero)
+            scale = None
+            if self.book is not None and dtype != F32:
+                scale = share.scale if share is not None else self.book.slot()
+                zero = True
+            t = K.NHWC(n, h, w, c, halo, dtype, device, zero=zero, scale=scale)
+            if scale is not None and share is None:
+                self.book.track_nhwc(t)
             self.store[key] = t
         return t
 
@@ -50,12 +58,23 @@ def _zeros_like(p):
 # =================================================================================================
 def _g_workspace(G, b, h, w, dev):
     d = G.conv_dim
-    T = lambda hh, ww, c, halo=0, zero=False: K.NHWC(b, hh, ww, c, halo, F32, dev, zero)
+    dt = G._dtype
+    book = K.ScaleBook(dev) if dt != F32 else None
+
+    def T(hh, ww, c, halo=0, zero=False, scaled=True):
+        if book is None:
+            return K.NHWC(b, hh, ww, c, halo, F32, dev, zero)
+        t = K.NHWC(b, hh, ww, c, halo, dt, dev, True, scale=book.slot() if scaled else None)
+        if scaled:
+            book.track_nhwc(t)
+        return t
     f64 = lambda n: torch.empty(n, dtype=torch.float64, device=dev)
     chs = [8 * d, 4 * d, 2 * d, d]
     res = [(h // 8, w // 8), (h // 4, w // 4), (h // 2, w // 2), (h, w)]
+    bwd_book = K.ScaleBook(dev) if dt != F32 else None
     return dict(
-        x0=T(h, w, 4, 3, True), x1=T(h, w, d, 1), x2=T(h // 2, w // 2, 2 * d, 1), x3=T(h // 4, w // 4, 4 * d, 1),
+        book=book, bwd_book=bwd_book, scratch=_Scratch(bwd_book) if dt != F32 else None, dtype=dt,
+        x0=T(h, w, 4 if dt == F32 else 8, 3, True, scaled=False), x1=T(h, w, d, 1), x2=T(h // 2, w // 2, 2 * d, 1), x3=T(h // 4, w // 4, 4 * d, 1),
         x4=T(h // 8, w // 8, 8 * d, 1), x5=T(h // 16, w // 16, 16 * d),
         z5=T(h // 16, w // 16, 16 * d), x5n=T(h // 16, w // 16, 16 * d), st5=f64(3 * b * 16 * d),
         u=[T(r[0] // 2, r[1] // 2, c) for r, c in zip(res, chs)],
@@ -71,13 +90,16 @@ def _g_workspace(G, b, h, w, dev):
 
 def _gam_forward(G, name, ga, src, ch, z, dst, off, stats, ws):
     fuse = ga.fuse[0]
-    wp = G._wcache.get(name, fuse.weight, lambda out=None: K.packed_weight(fuse.weight, src.c, F32, 0, ch, out=out))
-    if K.fused_stats_ok(src.h, src.w, ch):
+    dt = G._dtype
+    wsc = G._wscale(name, fuse)
+    wp = G._wcache.get((name, dt), fuse.weight,
+                       lambda out=None: K.packed_weight(fuse.weight, src.c, dt, 0, ch, out=out, w_scale=wsc))
+    if dt == F32 and K.fused_stats_ok(src.h, src.w, ch):
         K.conv_fprop(src, wp, ch, 1, 1, 0, z, in_stats=stats)
         K.instance_norm_apply(z, dst, off, stats)
         ws["mr"][name] = stats.data_ptr() + 2 * src.n * ch * 8
     else:
-        K.conv_fprop(src, wp, ch, 1, 1, 0, z)
+        K.conv_fprop(src, wp, ch, 1, 1, 0, z, w_scale=wsc)
         K.instance_norm(z, dst, off, stats)
         ws["mr"][name] = stats.data_ptr() + 2 * src.n * ch * 8
 
@@ -90,16 +112,44 @@ def _g_layers(G):
     return d, ups, gas, decs
 
 
+def _settle(book, run, max_iter=48):
+    """First use of an fp16 workspace: repeat `run()` + scale update until no per-tensor scale changes any more (every
+    pass fixes at least the next layer of the chain; host-synchronising, one-off, happens before any graph capture)."""
+    prev = None
+    for _ in range(max_iter):
+        run()
+        book.update()
+        cur = book.values()
+        if prev is not None and torch.equal(cur, prev):
+            return
+        prev = cur
+
+
 def _g_forward_train(G, x, ws):
+    if ws["book"] is not None:
+        if not ws.get("fwd_settled"):
+            ws["fwd_settled"] = True
+            _settle(ws["book"], lambda: _g_forward_pass(G, x, ws))
+        else:
+            ws["book"].update()  # delayed scaling: this pass stores with the magnitudes the previous pass measured
+    return _g_forward_pass(G, x, ws)
+
+
+def _g_forward_pass(G, x, ws):
     d, ups, gas, decs = _g_layers(G)
     act = G._act
     P = ws
+    if G._dtype != F32:
+        for name, holder in G._conv_table():
+            G._wscale(name, holder)
+        G._update_weight_scales()
 
     def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE):
         cv = holder.conv
         if k == 3 and stride == 1 and K.conv3x3_rowsum_nhwc(src, cv.weight, G._wcache, name, 1, dst, 0, cv.bias, act_):
             return  # experimental opt-in path (UEGAN_ROWSUM_NHWC=1)
-        K.conv_fprop(src, G._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, 0, cv.bias, None, act_)
+        K.conv_fprop(src, G._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, 0, cv.bias, None, act_,
+                     w_scale=G._wscale(name, cv))
 
     K.pack_input(x, P["x0"], L.PAD_REFLECT)
     conv(P["x0"], "enc1", G.enc1, d, 7, 1, P["x1"], act); K.halo_fill(P["x1"])
@@ -123,16 +173,33 @@ def _g_forward_train(G, x, ws):
     conv(P["y4m"], "dec5.0", G.dec5[0], d, 3, 1, P["t"]); K.halo_fill(P["t"])
     out = torch.empty_like(x)
     cv = G.dec5[1].conv
-    K.conv_planar(P["t"], cv.weight, G._wcache, "dec5.1", 7, 3, cv.bias, None, L.ACT_TANH, out, x, aux_nchw=P["res"])
+    K.conv_planar(P["t"], cv.weight, G._wcache, "dec5.1", 7, 3, cv.bias, None, L.ACT_TANH, out, x, aux_nchw=P["res"],
+                  w_scale=G._wscale("dec5.1", cv))
     return out
 
 
 def _g_backward(G, x, out_grad, ws, need_dx):
+    if ws.get("bwd_book") is not None:
+        if not ws.get("bwd_settled"):
+            ws["bwd_settled"] = True
+            _settle(ws["bwd_book"], lambda: _g_backward_pass(G, x, out_grad, ws, need_dx, dry=True))
+        else:
+            ws["bwd_book"].update()
+    return _g_backward_pass(G, x, out_grad, ws, need_dx)
+
+
+def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
+    """dry=True: the data-gradient chain only (settling the gradient scales of a new fp16 workspace): no weight / bias
+    gradient is accumulated."""
     d, ups, gas, decs = _g_layers(G)
     P = ws
     b, _, h, w = x.shape
     dev = x.device
-    S = lambda name, hh, ww, c, halo=0: _scratch.get(name, b, hh, ww, c, halo, F32, dev)
+    dty = ws.get("dtype", F32)
+    f16 = dty != F32
+    scr = ws["scratch"] if f16 else _scratch
+    S = lambda name, hh, ww, c, halo=0, share=None: scr.get(name, b, hh, ww, c, halo, dty, dev, share=share)
+    rgb_c = 8 if f16 else 4  # stored channels of a 3-channel tensor: one 16-byte vector
     grads = {}
     cache = G._wcache
     act = G._act
@@ -146,6 +213,8 @@ def _g_backward(G, x, out_grad, ws, need_dx):
         return (_zeros_like(param) if zero else torch.empty_like(param)), False
 
     def wgrad(name, conv, xin, dz, k, stride, pad, cin_first=0, cin=None, bias_from=None):
+        if dry:
+            return
         gw, direct = gbuf(name + ".weight", conv.weight)
         K.conv_wgrad(xin, dz, gw, k, stride, pad, cin_first=cin_first, cin=cin)
         grads[name + ".weight"] = None if direct else gw
@@ -158,25 +227,29 @@ def _g_backward(G, x, out_grad, ws, need_dx):
         grads[pname] = None if sink is not None else torch.zeros_like(param)
 
     # ---- dec5.1 + tanh + clamp(res + x)   (models.py:34-35, 72)
-    dz5 = S("dz5", h, w, 4, 6)
+    dz5 = S("dz5", h, w, rgb_c, 6)
     K.head_bwd(out_grad, P["res"], x, 2, dz5)
     c51 = G.dec5[1].conv
-    if K.hstack_ok(3, d, 7):
+    if dry:
+        pass
+    elif K.hstack_ok(3, d, 7):
         # horizontal taps unrolled into the gradient's channels: the wgrad keeps only the 7 vertical taps
-        e5 = S("dz5e", h, w + 6, 32, 0)
+        e5 = S("dz5e", h, w + 6, 32, 0, share=dz5)
         K.dz_hstack(dz5, 3, 7, e5)
         gw, direct = gbuf("dec5.1.main.1.weight", c51.weight)
         K.conv_wgrad_hstack(P["t"], e5, gw, 7, 3)
         grads["dec5.1.main.1.weight"] = None if direct else gw
     else:
-        dz5w = S("dz5w", h, w, 32, 0)
+        dz5w = S("dz5w", h, w, 32, 0, share=dz5)  # the same gradient with 32 stored channels (wgrad operand)
         K.head_bwd(out_grad, P["res"], x, 2, dz5w)
         wgrad("dec5.1.main.1", c51, P["t"], dz5w, 7, 1, 3)
-    gb, direct = gbuf("dec5.1.main.1.bias", c51.bias, zero=False)
-    K.channel_sum(dz5, gb, 0, 4, accumulate=direct)  # 4 stored channels reduced, the 3 real ones written
-    grads["dec5.1.main.1.bias"] = None if direct else gb
+    if not dry:
+        gb, direct = gbuf("dec5.1.main.1.bias", c51.bias, zero=False)
+        K.channel_sum(dz5, gb, 0, rgb_c, accumulate=direct)  # one stored vector reduced, the 3 real channels written
+        grads["dec5.1.main.1.bias"] = None if direct else gb
+    wsc = lambda name, conv: G._wscale(name, conv)
     dxp = S("dxp_t", h + 6, w + 6, d)
-    K.conv_dgrad(dz5, c51.weight, 7, 1, dxp, cache, "dec5.1")
+    K.conv_dgrad(dz5, c51.weight, 7, 1, dxp, cache, "dec5.1", w_scale=wsc("dec5.1", c51))
     if _FOLD_INPLACE:
         dt = K.fold_inplace(dxp, 3)  # the padded gradient itself becomes dt (interior + zero halo 3)
     else:
@@ -186,7 +259,7 @@ def _g_backward(G, x, out_grad, ws, need_dx):
     c50 = G.dec5[0].conv
     wgrad("dec5.0.main.1", c50, P["y4m"], dt, 3, 1, 1, bias_from=dt)
     dxp2 = S("dxp_y4m", h + 2, w + 2, d)
-    K.conv_dgrad(dt, c50.weight, 3, 1, dxp2, cache, "dec5.0")
+    K.conv_dgrad(dt, c50.weight, 3, 1, dxp2, cache, "dec5.0", w_scale=wsc("dec5.0", c50))
     # y4m = y4 * x1 ;  y4 = act(z4)
     dz = S("dz_dec3", h, w, d, 2)
     K.grad_combine(dz, d, src_a=dxp2, pad_a=1, mul=P["x1"], mask=P["y"][3], act=act)
@@ -203,7 +276,7 @@ def _g_backward(G, x, out_grad, ws, need_dx):
         dec, up, ga = decs[i].conv, ups[i].conv, gas[i].fuse[0]
         wgrad(f"dec{i+1}.main.1", dec, P["cat"][i], dz, 3, 1, 1, bias_from=dz)
         dxpc = S(f"dxp_cat{i}", hh + 2, ww + 2, 2 * ch)
-        K.conv_dgrad(dz, dec.weight, 3, 1, dxpc, cache, f"dec{i+1}")
+        K.conv_dgrad(dz, dec.weight, 3, 1, dxpc, cache, f"dec{i+1}", w_scale=wsc(f"dec{i+1}", dec))
         if _FOLD_INPLACE:
             dcat = K.fold_inplace(dxpc, 1)
         else:
@@ -214,7 +287,7 @@ def _g_backward(G, x, out_grad, ws, need_dx):
         K.upsample2x_bwd(dcat, 0, du)
         wgrad(f"upsample{i+1}.1.main.1", up, srcs[i], du, 1, 1, 0, bias_from=du)
         dsrc = S(f"dsrc{i}", hh // 2, ww // 2, 2 * ch)
-        K.conv_dgrad(du, up.weight, 1, 1, dsrc, cache, f"upsample{i+1}")
+        K.conv_dgrad(du, up.weight, 1, 1, dsrc, cache, f"upsample{i+1}", w_scale=wsc(f"upsample{i+1}", up))
         # second half: InstanceNorm(conv1x1(skip, fuse.weight[:, :ch]))
         dzs = S(f"dzs{i}", hh, ww, ch)
         K.instance_norm_bwd(dcat, ch, P["z"][i], P["mr"][f"ga{4-i}"], dzs,
@@ -223,7 +296,7 @@ def _g_backward(G, x, out_grad, ws, need_dx):
         wgrad(gname + ".fuse.0", ga, skips[i], dzs, 1, 1, 0, cin_first=0, cin=ch)
         dead(gname + ".fuse.0.bias", ga.bias)
         dsk = S(f"dskip{i}", hh, ww, ch)
-        K.conv_dgrad(dzs, ga.weight, 1, 1, dsk, cache, gname, cin_first=0, cin=ch)
+        K.conv_dgrad(dzs, ga.weight, 1, 1, dsk, cache, gname, cin_first=0, cin=ch, w_scale=wsc(gname, ga))
         dskip[i] = dsk
         if i > 0:
             dz = S(f"dz_dec{i-1}", hh // 2, ww // 2, 2 * ch, 2)
@@ -239,7 +312,7 @@ def _g_backward(G, x, out_grad, ws, need_dx):
     wgrad("ga5.fuse.0", f5, P["x5"], dz5g, 1, 1, 0, cin_first=0, cin=c5)
     dead("ga5.fuse.0.bias", f5.bias)
     dx5 = S("dx5", h5, w5, c5)
-    K.conv_dgrad(dz5g, f5.weight, 1, 1, dx5, cache, "ga5", cin_first=0, cin=c5)
+    K.conv_dgrad(dz5g, f5.weight, 1, 1, dx5, cache, "ga5", cin_first=0, cin=c5, w_scale=wsc("ga5", f5))
     # ---- encoder 5..1
     encs = [G.enc1, G.enc2, G.enc3, G.enc4, G.enc5]
     xs = [P["x0"], P["x1"], P["x2"], P["x3"], P["x4"], P["x5"]]
@@ -250,7 +323,7 @@ def _g_backward(G, x, out_grad, ws, need_dx):
         xin = xs[li - 1]
         wgrad(f"enc{li}.main.1", conv, xin, dze, 3, 2, 1, bias_from=dze)
         dxpe = S(f"dxp_x{li-1}", xin.h + 2, xin.w + 2, xin.c)
-        K.conv_dgrad(dze, conv.weight, 3, 2, dxpe, cache, f"enc{li}")
+        K.conv_dgrad(dze, conv.weight, 3, 2, dxpe, cache, f"enc{li}", w_scale=wsc(f"enc{li}", conv))
         halo = 1 if li > 2 else 3  # next dz feeds the dgrad of a k3s2 conv (halo 1); enc1's dz only feeds wgrad
         nxt = S(f"dz_e{li-1}", xin.h, xin.w, xin.c, halo if li > 2 else 0)
         K.grad_combine(nxt, xin.c, src_a=dxpe, pad_a=1, add_b=dskip[5 - li], add_c=dx1a if li == 2 else None,
@@ -262,7 +335,7 @@ def _g_backward(G, x, out_grad, ws, need_dx):
         dxp0 = S("dxp_x0", h + 6, w + 6, 16)
         dze3 = S("dz_e1h", h, w, d, 6)
         K.grad_combine(dze3, d, add_b=dze)
-        K.conv_dgrad(dze3, G.enc1.conv.weight, 7, 1, dxp0, cache, "enc1")
+        K.conv_dgrad(dze3, G.enc1.conv.weight, 7, 1, dxp0, cache, "enc1", w_scale=wsc("enc1", G.enc1.conv))
         dx0 = S("dx0", h, w, 16)
         K.grad_combine(dx0, 16, src_a=dxp0, pad_a=3)
         dx = torch.empty_like(x)
@@ -283,7 +356,7 @@ class _GeneratorFn(torch.autograd.Function):
         if module.conv_dim % 32:
             raise NotImplementedError("training kernels need conv_dim to be a multiple of 32 (wgrad operand rows)")
         x = x.detach().contiguous().float()
-        key = (b, h, w, str(x.device))
+        key = (b, h, w, str(x.device), module.precision)
         pool = module._train_pool.setdefault(key, [])
         ws = pool.pop() if pool else _g_workspace(module, b, h, w, x.device)
         out = _g_forward_train(module, x, ws)
@@ -317,18 +390,28 @@ def generator_apply(module, x):
 # Discriminator
 # =================================================================================================
 def _d_workspace(D, b, h, w, dev):
-    d = D.conv_dim
-    chans = [d, 2 * d, 4 * d, 8 * d, 16 * d]
-    ws = dict(x0=K.NHWC(b, h, w, 4, 3, F32, dev, zero=True), ds=[], sig=[], u=[], v=[], preds=[])
-    hh, ww = h, w
-    for i in range(5):
-        hh, ww = (hh + 1) // 2, (ww + 1) // 2
-        ws["ds"].append(K.NHWC(b, hh, ww, chans[i], 3 if i < 3 else 2, F32, dev))
-        ws["sig"].append(torch.ones(2, dtype=torch.float32, device=dev))
+    ws = D._act_buffers(b, h, w, dev)  # x0, ds[5], book, dtype
+    dt = ws["dtype"]
+    bwd_book = K.ScaleBook(dev) if dt != F32 else None
+    ws.update(sig=[torch.ones(2, dtype=torch.float32, device=dev) for _ in range(5)], u=[], v=[], preds=[],
+              bwd_book=bwd_book, scratch=_Scratch(bwd_book) if dt != F32 else None)
     return ws
 
 
 def _d_forward_train(D, x, ws):
+    if ws["book"] is not None:
+        if not ws.get("fwd_settled"):
+            ws["fwd_settled"] = True
+            # eval-mode passes while the scales settle: the spectral-norm power iteration must advance exactly once
+            _settle(ws["book"], lambda: _d_forward_pass(D, x, ws, False))
+        else:
+            ws["book"].update()
+    return _d_forward_pass(D, x, ws, D.training)
+
+
+def _d_forward_pass(D, x, ws, training):
+    D._register_weight_scales()
+    dt = D._dtype
     K.pack_input(x, ws["x0"], L.PAD_REFLECT)
     src, preds = ws["x0"], []
     ws["u"], ws["v"] = [], []
@@ -337,16 +420,18 @@ def _d_forward_train(D, x, ws):
         alpha = None
         if D.use_sn:
             scratch = torch.empty(wgt.shape[0] + wgt.numel() // wgt.shape[0] + 8, dtype=torch.float32, device=x.device)
-            K.spectral_sigma(wgt, conv.weight_u, conv.weight_v, D.training, ws["sig"][i - 1], scratch)
+            K.spectral_sigma(wgt, conv.weight_u, conv.weight_v, training, ws["sig"][i - 1], scratch)
             alpha = ws["sig"][i - 1][1:2]
             ws["u"].append(conv.weight_u.detach().clone())  # the values this forward used (later forwards move on)
             ws["v"].append(conv.weight_v.detach().clone())
         dst = ws["ds"][i - 1]
-        wp = D._wcache.get(f"d{i}", wgt, lambda out=None: K.packed_weight(wgt, src.c, F32, out=out))
-        K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, D._act)
+        wsc = D._wscale(f"d{i}", wgt)
+        wp = D._wcache.get((f"d{i}", dt), wgt, lambda out=None: K.packed_weight(wgt, src.c, dt, out=out, w_scale=wsc))
+        K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, D._act, w_scale=wsc)
         K.halo_fill(dst)
         pred = torch.empty(x.shape[0], 1, dst.h, dst.w, dtype=torch.float32, device=x.device)
-        K.conv_planar(dst, head.weight, D._wcache, f"p{i}", k, pad, None, None, D._head_act, pred)
+        K.conv_planar(dst, head.weight, D._wcache, f"p{i}", k, pad, None, None, D._head_act, pred,
+                      w_scale=D._wscale(f"p{i}", head.weight))
         preds.append(pred)
         src = dst
     ws["preds"] = preds
@@ -354,12 +439,28 @@ def _d_forward_train(D, x, ws):
 
 
 def _d_backward(D, x, dpreds, ws, need_dx, need_w=True):
+    if ws.get("bwd_book") is not None:
+        if not ws.get("bwd_settled"):
+            ws["bwd_settled"] = True
+            _settle(ws["bwd_book"], lambda: _d_backward_pass(D, x, dpreds, ws, need_dx, False))
+        else:
+            ws["bwd_book"].update()
+    return _d_backward_pass(D, x, dpreds, ws, need_dx, need_w)
+
+
+def _d_backward_pass(D, x, dpreds, ws, need_dx, need_w=True):
     b, _, h, w = x.shape
     dev = x.device
-    S = lambda name, hh, ww, c, halo=0: _scratch.get("D" + name, b, hh, ww, c, halo, F32, dev)
+    dty = ws.get("dtype", F32)
+    f16 = dty != F32
+    scr = ws["scratch"] if f16 else _scratch
+    S = lambda name, hh, ww, c, halo=0, share=None: scr.get("D" + name, b, hh, ww, c, halo, dty, dev, share=share)
+    rgb_c = 8 if f16 else 4
     cache = D._wcache
     grads = {}
     sink = getattr(D, "_grad_sink", None) if need_w else None
+    wsc = lambda i: D._wscale(f"d{i}", D._weight(i))
+    wsp = lambda i: D._wscale(f"p{i}", D._head(i).weight)
 
     def gbuf(pname, param, zero=True):
         if sink is not None:
@@ -373,7 +474,7 @@ def _d_backward(D, x, dpreds, ws, need_dx, need_w=True):
         kq = (k + 1) // 2
         ds = ws["ds"][i - 1]
         conv, head, wgt = D._conv(i), D._head(i), D._weight(i)
-        dzp = S(f"dzp{i}", ds.h, ds.w, 4, k - 1)
+        dzp = S(f"dzp{i}", ds.h, ds.w, rgb_c, k - 1)
         dp = dpreds[i - 1]
         if dp is None:
             dp = torch.zeros_like(ws["preds"][i - 1])
@@ -382,16 +483,16 @@ def _d_backward(D, x, dpreds, ws, need_dx, need_w=True):
         if need_w:
             gw, direct = gbuf(f"d{i}_pred.0.1.weight", head.weight)
             if K.hstack_ok(1, ds.c, k):
-                ep = S(f"dzpe{i}", ds.h, ds.w + k - 1, 32, 0)
+                ep = S(f"dzpe{i}", ds.h, ds.w + k - 1, 32, 0, share=dzp)
                 K.dz_hstack(dzp, 1, k, ep)
                 K.conv_wgrad_hstack(ds, ep, gw, k, pad)
             else:
-                dzpw = S(f"dzpw{i}", ds.h, ds.w, 32, 0)
+                dzpw = S(f"dzpw{i}", ds.h, ds.w, 32, 0, share=dzp)
                 K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzpw)
                 K.conv_wgrad(ds, dzpw, gw, k, 1, pad)
             grads[f"d{i}_pred.0.1.weight"] = None if direct else gw
         dxa = S(f"dxa{i}", ds.h + 2 * pad, ds.w + 2 * pad, ds.c)
-        K.conv_dgrad(dzp, head.weight, k, 1, dxa, cache, f"p{i}")
+        K.conv_dgrad(dzp, head.weight, k, 1, dxa, cache, f"p{i}", w_scale=wsp(i))
         dz = S(f"dz{i}", ds.h, ds.w, ds.c, kq - 1)
         if carry is not None:
             if _FOLD_INPLACE:
@@ -432,11 +533,11 @@ def _d_backward(D, x, dpreds, ws, need_dx, need_w=True):
             grads[f"d{i}.0.1.bias"] = None if direct else gb
         if i > 1:
             dxb = S(f"dxb{i}", xin.h + 2 * pad, xin.w + 2 * pad, xin.c)
-            K.conv_dgrad(dz, wgt, k, 2, dxb, cache, f"d{i}", alpha=alpha)
+            K.conv_dgrad(dz, wgt, k, 2, dxb, cache, f"d{i}", alpha=alpha, w_scale=wsc(i))
             carry = (dxb, pad)
         elif need_dx:
             dxb = S("dxb1", h + 2 * pad, w + 2 * pad, 16)
-            K.conv_dgrad(dz, wgt, k, 2, dxb, cache, "d1", alpha=alpha)
+            K.conv_dgrad(dz, wgt, k, 2, dxb, cache, "d1", alpha=alpha, w_scale=wsc(1))
             dx0 = S("dx0", h, w, 16)
             K.grad_combine(dx0, 16, src_a=dxb, pad_a=pad)
             dx = torch.empty_like(x)
@@ -452,7 +553,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         if module.conv_dim % 32:
             raise NotImplementedError("training kernels need conv_dim to be a multiple of 32 (wgrad operand rows)")
         x = x.detach().contiguous().float()
-        key = (b, h, w, str(x.device))
+        key = (b, h, w, str(x.device), module.precision)
         pool = module._train_pool.setdefault(key, [])
         ws = pool.pop() if pool else _d_workspace(module, b, h, w, x.device)
         preds = _d_forward_train(module, x, ws)
@@ -469,8 +570,15 @@ class _DiscriminatorFn(torch.autograd.Function):
         grads, dx = _d_backward(D, ctx.x, dpreds, ctx.ws, ctx.needs_input_grad[1], need_w)
         D._train_pool[ctx.key].append(ctx.ws)
         ctx.ws = None
-        names = [n for n, _ in D.named_parameters()]
-        return (None, dx) + tuple(grads.get(n) for n in names)
+        named = list(D.named_parameters())
+        out = [grads.get(n) for n, _ in named]
+        if need_w and dx is None and all(g is None for g in out):
+            # every gradient went straight into the sink.  A backward node that hands autograd NOTHING invalidates an
+            # ongoing CUDA-graph capture (measured r2: capture fails iff all outputs are None); one zero gradient for the
+            # smallest parameter keeps a leaf on the device queue.  `p.grad += 0` is exact.
+            j = min(range(len(named)), key=lambda i: named[i][1].numel())
+            out[j] = torch.zeros_like(named[j][1])
+        return (None, dx) + tuple(out)
 
 
 def discriminator_apply(module, x):

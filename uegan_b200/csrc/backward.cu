@@ -29,6 +29,7 @@ __global__ void head_bwd_kernel(const float* __restrict__ dout, const float* __r
   for (int k = 0; k < Vec<T>::N; ++k) v[k] = 0.f;
   if (y >= 0 && y < d.h && x >= 0 && x < d.w) {
     const long long plane = (long long)d.h * d.w;
+    const float so = tscale(d);
     for (int c = 0; c < cch; ++c) {
       const long long o = ((long long)n * cch + c) * plane + (long long)y * d.w + x;
       const float g = __ldg(dout + o), r = __ldg(outv + o);
@@ -39,7 +40,7 @@ __global__ void head_bwd_kernel(const float* __restrict__ dout, const float* __r
         const float s = r + __ldg(xin + o);
         dz = (s >= -1.f && s <= 1.f) ? g * (1.f - r * r) : 0.f;
       }
-      v[c] = dz;
+      v[c] = dz * so;
     }
   }
   T* dp = static_cast<T*>(d.data) + i * d.c;
@@ -79,6 +80,9 @@ __global__ void grad_combine_kernel(CombineArgs q, int cv_log2) {
   for (int k = 0; k < VN; ++k) v[k] = 0.f;
   const bool interior = (y >= 0 && y < q.dst.h && x >= 0 && x < q.dst.w);
   if (interior) {
+    // per-tensor power-of-two scales: every addend is brought to the destination's scale (exact multiplications)
+    const float so = tscale(q.dst);
+    const float fa = q.has_a ? so * tinv(q.a) : 1.f, fb = q.has_b ? so * tinv(q.b) : 1.f, fc = q.has_c ? so * tinv(q.c) : 1.f;
     if (q.has_a) {
       const T* ab = static_cast<const T*>(q.a.data);
       // positions of the padded tensor that map to (y, x)
@@ -96,26 +100,27 @@ __global__ void grad_combine_kernel(CombineArgs q, int cv_log2) {
           float t[VN];
           Vec<T>::load(ab + toff(q.a, n, ys[iy], xs[ix], q.a_c_off + c), t);
 #pragma unroll
-          for (int k = 0; k < VN; ++k) v[k] += t[k];
+          for (int k = 0; k < VN; ++k) v[k] += t[k] * fa;
         }
     }
     if (q.has_b) {
       float t[VN];
       Vec<T>::load(static_cast<const T*>(q.b.data) + toff(q.b, n, y, x, q.b_c_off + c), t);
 #pragma unroll
-      for (int k = 0; k < VN; ++k) v[k] += t[k];
+      for (int k = 0; k < VN; ++k) v[k] += t[k] * fb;
     }
     if (q.has_c) {
       float t[VN];
       Vec<T>::load(static_cast<const T*>(q.c.data) + toff(q.c, n, y, x, q.c_c_off + c), t);
 #pragma unroll
-      for (int k = 0; k < VN; ++k) v[k] += t[k];
+      for (int k = 0; k < VN; ++k) v[k] += t[k] * fc;
     }
     if (q.has_mul) {
       float t[VN];
+      const float fm = tinv(q.mul);
       Vec<T>::load(static_cast<const T*>(q.mul.data) + toff(q.mul, n, y, x, q.mul_c_off + c), t);
 #pragma unroll
-      for (int k = 0; k < VN; ++k) v[k] *= t[k];
+      for (int k = 0; k < VN; ++k) v[k] *= t[k] * fm;
     }
     if (q.has_mask) {
       float t[VN];
@@ -179,8 +184,9 @@ __global__ void fold_inplace_kernel(TGeom t, int cv_log2) {
 // weight gradient dW[o][c][r][s] = sum_{y,q} xpad[y + r][q][c] * E[y][q][(s, o)] is the wgrad of a k x 1 convolution with
 // k*cout output channels -- k times fewer MMAs than one accumulator per (r, s) tap (conv_wgrad.cu, vertical patch mode).
 // ------------------------------------------------------------------------------------------
-template <int COUT>
+template <typename T, int COUT>
 __global__ void dz_hstack_kernel(TGeom dz, TGeom e, int k, long long total) {
+  constexpr int VN = Vec<T>::N;  // dz stores one 16-byte vector per pixel (4 fp32 / 8 fp16 channels, COUT real ones)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int q = (int)(i % e.w);
@@ -189,19 +195,26 @@ __global__ void dz_hstack_kernel(TGeom dz, TGeom e, int k, long long total) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = 0.f;
-  const float* db = static_cast<const float*>(dz.data);
+  const T* db = static_cast<const T*>(dz.data);
 #pragma unroll
   for (int s = 0; s < 7; ++s) {
     if (s < k) {
-      const float4 d = *reinterpret_cast<const float4*>(db + toff(dz, n, y, q - s, 0));
-      v[s * COUT] = d.x;
-      if (COUT > 1) v[s * COUT + 1] = d.y;
-      if (COUT > 2) v[s * COUT + 2] = d.z;
+      float d[VN];
+      Vec<T>::load(db + toff(dz, n, y, q - s, 0), d);
+      v[s * COUT] = d[0];
+      if (COUT > 1) v[s * COUT + 1] = d[1];
+      if (COUT > 2) v[s * COUT + 2] = d[2];
     }
   }
-  float* ep = static_cast<float*>(e.data) + toff(e, n, y, q, 0);
+  // (the stack shares dz's scale: a pure copy; Vec<float>::store re-rounds tf32 values to themselves)
+  T* ep = static_cast<T*>(e.data) + toff(e, n, y, q, 0);
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(ep + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  for (int j = 0; j < 32; j += VN) {
+    float o[VN];
+#pragma unroll
+    for (int t = 0; t < VN; ++t) o[t] = v[j + t];
+    Vec<T>::store(ep + j, o);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -221,7 +234,7 @@ struct ChannelSumOp {
     for (int k = 0; k < Vec<T>::N; ++k) a[k][0] += v[k];
   }
   __device__ void flush(int n, int c, const float (&t)[1]) const {
-    if (c < out_channels) atomicAdd(out + c, t[0]);
+    if (c < out_channels) atomicAdd(out + c, t[0] * tinv(s));  // the bias gradient is a true-scale fp32 value
   }
 };
 
@@ -278,6 +291,7 @@ struct AffineArgs {
   double inv_npix;
   float coef;
   const float* gscale;
+  const float *s_num0, *s_num1, *s_den;  // optional per-tensor scales folded into the coefficient: * s_num0 * s_num1 / s_den
   int mode, cch, cv_log2;
 };
 // row groups per block: the statistics prologue is paid once per ROWS * kAffineIters rows (fp32: 4 trips measured faster,
@@ -289,7 +303,8 @@ __global__ void __launch_bounds__(256) affine_apply_kernel(const AffineArgs q) {
   constexpr int VN = Vec<T>::N;
   const int n = blockIdx.z, C = q.cch;
   {
-    const float cf = q.coef * (q.gscale ? __ldg(q.gscale) : 1.f);
+    const float cf = q.coef * (q.gscale ? __ldg(q.gscale) : 1.f) * (q.s_num0 ? __ldg(q.s_num0) : 1.f) *
+                     (q.s_num1 ? __ldg(q.s_num1) : 1.f) / (q.s_den ? __ldg(q.s_den) : 1.f);
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
       const long long si = ((long long)n * C + ch) * 2;
       s_coef[ch] = q.mra[si];
@@ -334,8 +349,10 @@ __global__ void __launch_bounds__(256) affine_apply_kernel(const AffineArgs q) {
       float g = 0.f;
       if (in[r]) {
         if (q.mode == 0) {
+          // stored tensors: xh is the true normalised value (ra = rstd / s_z), the bracket is in dout's stored units;
+          // s_coef[6 * C] (= cf) carries s_z * s_dz / s_dout, which turns ra * bracket into dz's stored units
           const float xh = (bv[r][k] - ma) * ra;
-          g = ra * (av[r][k] - m1 - xh * m2);
+          g = cf * ra * (av[r][k] - m1 - xh * m2);
         } else {
           const float xh = (av[r][k] - ma) * ra;
           const float yh = (bv[r][k] - mb) * rb;
@@ -429,6 +446,9 @@ __global__ void upsample2x_bwd_kernel(TGeom g, int g_c_off, TGeom d, float sy, f
       for (int k = 0; k < VN; ++k) acc[k] += wy[jy] * wx[jx] * tv[k];  // same order as the scatter's adjoint sum
     }
   }
+  const float rs = tscale(d) * tinv(g);
+#pragma unroll
+  for (int k = 0; k < VN; ++k) acc[k] *= rs;
   Vec<T>::store(static_cast<T*>(d.data) + toff(d, n, yi, xi, c), acc);
 }
 
@@ -526,7 +546,7 @@ __global__ void unpack_grad_kernel(TGeom s, float* __restrict__ dst, float s0, f
   const int c = (int)(r % 3);
   const int n = (int)(r / 3);
   const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
-  float v = to_f32<TG>(static_cast<const TG*>(s.data)[toff(s, n, y, x, c)]) * sc;
+  float v = to_f32<TG>(static_cast<const TG*>(s.data)[toff(s, n, y, x, c)]) * sc * tinv(s);
   if (skip_dout) {
     // the generator's identity path out = clamp(res + x, -1, 1) (models.py:72): d out / d x = [|res + x| <= 1]
     const float t = __ldg(skip_res + i) + __ldg(skip_x + i);
@@ -624,16 +644,23 @@ int uegan_fold_inplace(const uegan_tensor* t, void* stream) {
 
 int uegan_dz_hstack(const uegan_tensor* dz, int32_t cout, int32_t k, const uegan_tensor* e, void* stream) {
   UEGAN_CHECK(dz && e && dz->data && e->data, "dz_hstack: null pointer");
-  UEGAN_CHECK(dz->dtype == UEGAN_F32 && e->dtype == UEGAN_F32 && dz->c == 4 && e->c == 32 && e->halo == 0,
-              "dz_hstack: expects a 4-channel fp32 dz and a 32-channel fp32 stack without halo");
+  UEGAN_CHECK(dz->dtype == e->dtype && (dz->dtype == UEGAN_F32 || dz->dtype == UEGAN_F16) &&
+                  dz->c * dtype_size(dz->dtype) == 16 && e->c == 32 && e->halo == 0,
+              "dz_hstack: expects a one-vector (16-byte) dz and a 32-channel stack without halo, both fp32 or both fp16");
   UEGAN_CHECK((cout == 1 || cout == 3) && k >= 1 && k <= 7 && k * cout <= 21, "dz_hstack: unsupported cout %d / k %d", cout, k);
   UEGAN_CHECK(dz->halo >= k - 1 && e->n == dz->n && e->h == dz->h && e->w == dz->w + k - 1,
               "dz_hstack: dz needs a zero halo >= k - 1 and the stack must be %d x %d (got %d x %d)", dz->h, dz->w + k - 1,
               e->h, e->w);
   const TGeom d = geom(*dz), g = geom(*e);
   const long long total = (long long)g.n * g.h * g.w;
-  if (cout == 1) dz_hstack_kernel<1><<<nblk(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, g, k, total);
-  else dz_hstack_kernel<3><<<nblk(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, g, k, total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dz->dtype == UEGAN_F32) {
+    if (cout == 1) dz_hstack_kernel<float, 1><<<nblk(total, 256), 256, 0, st>>>(d, g, k, total);
+    else dz_hstack_kernel<float, 3><<<nblk(total, 256), 256, 0, st>>>(d, g, k, total);
+  } else {
+    if (cout == 1) dz_hstack_kernel<__half, 1><<<nblk(total, 256), 256, 0, st>>>(d, g, k, total);
+    else dz_hstack_kernel<__half, 3><<<nblk(total, 256), 256, 0, st>>>(d, g, k, total);
+  }
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -690,6 +717,7 @@ int uegan_instance_norm_bwd(const uegan_tensor* dout, int32_t d_c_off, const ueg
   q.a = g; q.a_c_off = d_c_off; q.b = zz; q.deep = d; q.has_deep = 0; q.dst = d;
   q.mra = mean_rstd; q.mrb = nullptr; q.sums = ws; q.inv_npix = 1.0 / (double)npix; q.coef = 1.f; q.gscale = nullptr;
   q.mode = 0; q.cch = zz.c;
+  q.s_num0 = zz.scale; q.s_num1 = d.scale; q.s_den = g.scale;
   if (z->dtype == UEGAN_F32) { if (launch_affine_apply<float, float>(q, st)) return -1; }
   else if (z->dtype == UEGAN_BF16) { if (launch_affine_apply<__nv_bfloat16, __nv_bfloat16>(q, st)) return -1; }
   else { if (launch_affine_apply<__half, __half>(q, st)) return -1; }

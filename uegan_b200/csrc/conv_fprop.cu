@@ -51,6 +51,11 @@ struct ConvParams {
   long long out_pix, out_row, out_img;  // strides in elements
   const float* bias;
   const float* alpha;
+  // per-tensor power-of-two scales (uegan_tensor.scale; NULL = 1): stored = scale * true
+  const float* sx;    // input activations
+  const float* sw;    // packed weights
+  const float* sy;    // NHWC output (planar fp32 outputs are true values)
+  const float* smul;  // the `mul` operand
   const void* mul;  // same dtype as out
   long long mul_pix, mul_row, mul_img;
   const void* mask;  // activation-derivative mask from a forward tensor (dgrad epilogue); dtype mask_kind
@@ -111,8 +116,8 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
 // NHWC epilogue of one warp: its 32 rows x the 16-column chunks {half, half+2, ...} of the tile.
 template <int ACT>
 __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t taddr, int colbase, int half, long long o,
-                                              long long mo, bool valid, float alpha, float* stat_slice, int mk_n, int mk_h,
-                                              int mk_w) {
+                                              long long mo, bool valid, float alpha, float bmul, float* stat_slice,
+                                              int mk_n, int mk_h, int mk_w) {
   for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
     uint32_t rr[16];
     tmem_ld16(taddr + c0, rr);
@@ -126,7 +131,7 @@ __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t tadd
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float x = __uint_as_float(rr[i]) * alpha;
-        if (p.bias) x += __ldg(p.bias + col0 + i);
+        if (p.bias) x += __ldg(p.bias + col0 + i) * bmul;
         x = act_t<ACT>(x, p.act);
         x = round_store(x, p.out_kind);
         x = valid ? x : 0.f;
@@ -152,10 +157,11 @@ __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t tadd
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 b = __ldg(bp + i);
-        v[4 * i + 0] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 0]), alpha, b.x), p.act);
-        v[4 * i + 1] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 1]), alpha, b.y), p.act);
-        v[4 * i + 2] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 2]), alpha, b.z), p.act);
-        v[4 * i + 3] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 3]), alpha, b.w), p.act);
+        // (bmul = 1 unless the output carries a scale: a power of two, so b * bmul is exact)
+        v[4 * i + 0] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 0]), alpha, b.x * bmul), p.act);
+        v[4 * i + 1] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 1]), alpha, b.y * bmul), p.act);
+        v[4 * i + 2] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 2]), alpha, b.z * bmul), p.act);
+        v[4 * i + 3] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 3]), alpha, b.w * bmul), p.act);
       }
     } else {
 #pragma unroll
@@ -490,7 +496,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3;          // TMEM lane quarter this warp may read
     const int half = (warp - 4) >> 2;  // interleaved 16-column chunks: half, half + 2, ...
     const int m = q * 32 + lane;
-    const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+    // alpha = (1/sigma) * s_y / (s_x * s_w * s_mul): the accumulator is in stored units of x and w, the output in stored
+    // units of y (LeakyReLU / ReLU are positively homogeneous; tanh / sigmoid heads write true values: s_y = s_mul = 1)
+    const float bmul = (p.sy ? __ldg(p.sy) : 1.0f) / (p.smul ? __ldg(p.smul) : 1.0f);
+    const float alpha = (p.alpha ? __ldg(p.alpha) : 1.0f) * bmul / ((p.sx ? __ldg(p.sx) : 1.0f) * (p.sw ? __ldg(p.sw) : 1.0f));
     const int mw = m & (p.tw - 1), mh = (m >> p.tw_log2) & (p.th - 1), mn = m >> (p.tw_log2 + p.th_log2);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -528,10 +537,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const long long o = (long long)n * p.out_img + (long long)ho * p.out_row + (long long)wo * p.out_pix + colbase;
         const long long mo = (long long)n * p.mul_img + (long long)ho * p.mul_row + (long long)wo * p.mul_pix + colbase;
         switch (p.act) {
-          case UEGAN_ACT_LRELU: epilogue_nhwc<UEGAN_ACT_LRELU>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice, n, ho, wo); break;
-          case UEGAN_ACT_RELU: epilogue_nhwc<UEGAN_ACT_RELU>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice, n, ho, wo); break;
-          case UEGAN_ACT_NONE: epilogue_nhwc<UEGAN_ACT_NONE>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice, n, ho, wo); break;
-          default: epilogue_nhwc<-1>(p, taddr, colbase, half, o, mo, valid, alpha, stat_slice, n, ho, wo); break;
+          case UEGAN_ACT_LRELU: epilogue_nhwc<UEGAN_ACT_LRELU>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo); break;
+          case UEGAN_ACT_RELU: epilogue_nhwc<UEGAN_ACT_RELU>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo); break;
+          case UEGAN_ACT_NONE: epilogue_nhwc<UEGAN_ACT_NONE>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo); break;
+          default: epilogue_nhwc<-1>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo); break;
         }
       }
       tcgen05_fence_before();
@@ -620,6 +629,8 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   p.ab_fmt = x.dtype == UEGAN_F32 ? UMMA_TF32 : (x.dtype == UEGAN_BF16 ? UMMA_BF16 : UMMA_F16);
   p.bias = d.bias;
   p.alpha = d.alpha;
+  p.sx = x.scale;
+  p.sw = d.w_scale;
   p.out_nchw = d.out_nchw;
   p.residual_nchw = d.residual_nchw;
   p.aux_nchw = d.aux_nchw;
@@ -647,6 +658,11 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
     UEGAN_CHECK((y.c * dtype_size(y.dtype)) % 16 == 0, "conv: y.c misaligned");
     UEGAN_CHECK(dtype_ok(y.dtype), "conv: bad y dtype %d", y.dtype);
     p.out_kind = y.dtype;
+    p.sy = y.scale;
+    UEGAN_CHECK(!(y.scale || (d.mul && d.mul->scale)) || d.act == UEGAN_ACT_NONE || d.act == UEGAN_ACT_LRELU ||
+                    d.act == UEGAN_ACT_RELU,
+                "conv: a scaled output needs a positively homogeneous activation (none / LeakyReLU / ReLU)");
+    UEGAN_CHECK(!(y.scale && d.in_stats), "conv: in_stats is not available with a scaled output");
     p.out_pix = y.c;
     p.out_row = t_wp(y) * y.c;
     p.out_img = t_hp(y) * p.out_row;
@@ -676,6 +692,7 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
       p.mul_img = t_hp(mt) * p.mul_row;
       const long long moff = (long long)mt.halo * p.mul_row + (long long)mt.halo * p.mul_pix;
       p.mul = static_cast<const uint8_t*>(mt.data) + moff * dtype_size(mt.dtype);
+      p.smul = mt.scale;
     }
   }
 
@@ -806,7 +823,8 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin_total,
                                    int cin_first, int cin, int cin_stored, int k, int row_pad, int cout_pad,
-                                   int mode, int k_orig, int q, int pi, int pj, long long total) {
+                                   int mode, int k_orig, int q, int pi, int pj, long long total,
+                                   const float* __restrict__ wscale) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int x = (int)(i % row_pad);
@@ -823,6 +841,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
         v = w[(((long long)c * cin_total + cin_first + o) * k_orig + rr) * k_orig + ss];
     }
   }
+  if (wscale) v *= __ldg(wscale);
   if constexpr (sizeof(T) == 4) {
     out[i] = round_tf32(v);
   } else if constexpr (std::is_same<T, __half>::value) {
@@ -844,7 +863,8 @@ size_t uegan_packed_weight_bytes(int32_t cout, int32_t cin_stored, int32_t k, in
 }
 
 static int pack_impl(const float* w_oihw, void* w_packed, int cout, int cin_total, int cin_first, int cin,
-                     int cin_stored, int k, int dtype, int mode, int k_orig, int q, int pi, int pj, void* stream) {
+                     int cin_stored, int k, int dtype, int mode, int k_orig, int q, int pi, int pj, void* stream,
+                     const float* wscale = nullptr) {
   UEGAN_CHECK(w_oihw && w_packed, "pack_conv_weight: null pointer");
   UEGAN_CHECK(cin <= cin_stored, "pack_conv_weight: cin %d > stored %d", cin, cin_stored);
   UEGAN_CHECK(dtype_ok(dtype), "pack_conv_weight: bad dtype");
@@ -856,15 +876,15 @@ static int pack_impl(const float* w_oihw, void* w_packed, int cout, int cin_tota
   if (dtype == UEGAN_F32)
     pack_weight_kernel<float><<<blocks, threads, 0, st>>>(w_oihw, static_cast<float*>(w_packed), cout, cin_total,
                                                           cin_first, cin, cin_stored, k, g.row_pad, g.cout_pad, mode,
-                                                          k_orig, q, pi, pj, total);
+                                                          k_orig, q, pi, pj, total, wscale);
   else if (dtype == UEGAN_BF16)
     pack_weight_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), cout,
                                                                    cin_total, cin_first, cin, cin_stored, k, g.row_pad,
-                                                                   g.cout_pad, mode, k_orig, q, pi, pj, total);
+                                                                   g.cout_pad, mode, k_orig, q, pi, pj, total, wscale);
   else
     pack_weight_kernel<__half><<<blocks, threads, 0, st>>>(w_oihw, static_cast<__half*>(w_packed), cout, cin_total,
                                                            cin_first, cin, cin_stored, k, g.row_pad, g.cout_pad, mode,
-                                                           k_orig, q, pi, pj, total);
+                                                           k_orig, q, pi, pj, total, wscale);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -887,6 +907,25 @@ int uegan_pack_conv_weight_dgrad(const float* w_oihw, void* w_packed, int32_t co
   // original output channels (stored count cout_stored in the dz tensor)
   return pack_impl(w_oihw, w_packed, cin, cin_total, cin_first, cout_orig, cout_stored, k, dtype, 1, k_orig, stride, pi,
                    pj, stream);
+}
+
+int uegan_pack_conv_weight_scaled(const float* w_oihw, void* w_packed, int32_t cout, int32_t cin_total, int32_t cin_first,
+                                  int32_t cin, int32_t cin_stored, int32_t k, int32_t dtype, const float* w_scale_dev,
+                                  void* stream) {
+  UEGAN_CHECK(cin_first + cin <= cin_total, "pack_conv_weight_scaled: channel range out of bounds");
+  return pack_impl(w_oihw, w_packed, cout, cin_total, cin_first, cin, cin_stored, k, dtype, 0, k, 1, 0, 0, stream,
+                   w_scale_dev);
+}
+
+int uegan_pack_conv_weight_dgrad_scaled(const float* w_oihw, void* w_packed, int32_t cout_orig, int32_t cin_total,
+                                        int32_t cin_first, int32_t cin, int32_t cout_stored, int32_t k_orig,
+                                        int32_t stride, int32_t pi, int32_t pj, int32_t dtype, const float* w_scale_dev,
+                                        void* stream) {
+  UEGAN_CHECK(stride == 1 || stride == 2, "pack_conv_weight_dgrad_scaled: stride %d", stride);
+  UEGAN_CHECK(cin_first + cin <= cin_total, "pack_conv_weight_dgrad_scaled: channel range out of bounds");
+  const int k = (k_orig + stride - 1) / stride;
+  return pack_impl(w_oihw, w_packed, cin, cin_total, cin_first, cout_orig, cout_stored, k, dtype, 1, k_orig, stride, pi,
+                   pj, stream, w_scale_dev);
 }
 
 int uegan_conv2d_fprop(const uegan_conv_desc* desc, void* stream) {

@@ -23,7 +23,9 @@ constexpr int kRsRowBytes = 32 * 128;  // one patch row: 32 pixels x 128 B
 
 struct RowsumParams {
   int k, cout, nb;        // nb: N of the MMA = k*cout rounded up to 16
-  int nch, cs;            // 32-channel chunks per pixel, stored channels
+  int nch, cs, cb;        // 128-byte channel chunks per pixel, stored channels, channels per chunk (32 tf32 / 64 fp16)
+  int csp;                // nch * cb: channels per pixel of the packed weight rows (zero beyond cs)
+  const float *sx, *sw;   // per-tensor scales of x and of the packed weight (NULL = 1)
   int th, msub, two;      // output rows per tile (16 / 8), M tiles per patch (th / 4), output columns per tile
   int tiles_w, tiles_h, total_tiles;
   int patch_off, ph;
@@ -89,6 +91,7 @@ __device__ __forceinline__ void rowsum_epilogue(const RowsumParams& p, uint32_t 
   }
 }
 
+template <int kF16>
 __global__ void __launch_bounds__(384, 1)
 conv_rowsum_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const RowsumParams p) {
@@ -133,7 +136,7 @@ conv_rowsum_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_arrive_expect_tx(&w_full, (uint32_t)p.w_total_bytes);
       for (int wi = 0; wi < p.k * p.nch; ++wi) {  // weight tile (r, chunk): [nb rows x 128 B], resident
         const int r = wi / p.nch, c = wi % p.nch;
-        tma_load_2d(&tmB, &w_full, smem + wi * p.w_tile_bytes, r * p.cs + c * 32, 0);
+        tma_load_2d(&tmB, &w_full, smem + wi * p.w_tile_bytes, r * p.csp + c * p.cb, 0);
       }
       uint8_t* sa0 = smem + p.w_total_bytes;
       int stage = 0;
@@ -144,7 +147,7 @@ conv_rowsum_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int c = 0; c < p.nch; ++c) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 0xD00 + stage, p.err_sink);
           mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_tx);
-          tma_load_4d(&tmA, &full_bar[stage], sa0 + stage * p.stage_bytes, c * 32, wo0 + p.patch_off, ho0 + p.patch_off, n);
+          tma_load_4d(&tmA, &full_bar[stage], sa0 + stage * p.stage_bytes, c * p.cb, wo0 + p.patch_off, ho0 + p.patch_off, n);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -152,7 +155,7 @@ conv_rowsum_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     if (elect_one()) {
       // ===================== MMA issuer =====================
-      const uint32_t idesc = make_instr_desc(UMMA_TF32, 128, p.nb);
+      const uint32_t idesc = make_instr_desc(kF16 ? UMMA_F16 : UMMA_TF32, 128, p.nb);
       const uint32_t w_addr = smem_u32(smem);
       const uint64_t db0 = make_smem_desc(w_addr, 16, 1024, UMMA_LAYOUT_SW128);
       int stage = 0;
@@ -173,10 +176,11 @@ conv_rowsum_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             uint64_t db = desc_adv(db0, (uint32_t)c * p.w_tile_bytes);
             const uint32_t b_step = (uint32_t)(p.nch * p.w_tile_bytes) >> 4;
             for (int r = 0; r < p.k; ++r) {
-              umma_ss<1>(d_tmem, da, db, idesc, (c | r) != 0 ? 1u : 0u);
-              umma_ss<1>(d_tmem, da + 2, db + 2, idesc, 1u);
-              umma_ss<1>(d_tmem, da + 4, db + 4, idesc, 1u);
-              umma_ss<1>(d_tmem, da + 6, db + 6, idesc, 1u);
+              // 4 MMAs per 128-byte row: 32 bytes of K each (8 tf32 / 16 fp16 values)
+              umma_ss<kF16 ? 0 : 1>(d_tmem, da, db, idesc, (c | r) != 0 ? 1u : 0u);
+              umma_ss<kF16 ? 0 : 1>(d_tmem, da + 2, db + 2, idesc, 1u);
+              umma_ss<kF16 ? 0 : 1>(d_tmem, da + 4, db + 4, idesc, 1u);
+              umma_ss<kF16 ? 0 : 1>(d_tmem, da + 6, db + 6, idesc, 1u);
               da += kRsRowBytes >> 4;
               db += b_step;
             }
@@ -193,7 +197,8 @@ conv_rowsum_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===================== epilogue: lane quarter q = patch row within the M tile, half = M tiles {half, half + 2} ====
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
-    const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+    // planar fp32 outputs are true values: the accumulator is in stored units of x and w
+    const float alpha = (p.alpha ? __ldg(p.alpha) : 1.0f) / ((p.sx ? __ldg(p.sx) : 1.0f) * (p.sw ? __ldg(p.sw) : 1.0f));
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -223,18 +228,25 @@ conv_rowsum_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
-// out[n][r][c] (n = s*cout + o, nb rows; k*cs columns) = tf32(w[o][cin_first + c][r][s]), zero elsewhere
-__global__ void pack_weight_rowsum_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin_total,
-                                          int cin_first, int cin, int cs, int k, int nb) {
+// out[n][r][c] (n = s*cout + o, nb rows; k*csp columns, csp = stored channels padded to whole 128-byte chunks)
+//   = round(w[o][cin_first + c][r][s] * (*wscale)), zero elsewhere; tf32-rounded fp32 or fp16
+template <typename T>
+__global__ void pack_weight_rowsum_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin_total,
+                                          int cin_first, int cin, int csp, int k, int nb, const float* __restrict__ wscale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nb * k * cs) return;
-  const int c = i % cs, r = (i / cs) % k, nrow = i / (cs * k);
+  if (i >= nb * k * csp) return;
+  const int c = i % csp, r = (i / csp) % k, nrow = i / (csp * k);
   const int s = nrow / cout, o = nrow % cout;
   float v = 0.f;
   if (s < k && c < cin) v = w[(((long long)o * cin_total + cin_first + c) * k + r) * k + s];
-  uint32_t t;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
-  out[i] = __uint_as_float(t);
+  if (wscale) v *= __ldg(wscale);
+  if constexpr (sizeof(T) == 4) {
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+    out[i] = __uint_as_float(t);
+  } else {
+    out[i] = __float2half_rn(v);
+  }
 }
 
 static bool rowsum_shape_ok(int cout, int k) {
@@ -242,9 +254,11 @@ static bool rowsum_shape_ok(int cout, int k) {
 }
 static int rowsum_nb(int cout, int k) { return (k * cout + 15) / 16 * 16; }
 
+static int rowsum_cb(int dtype) { return dtype == UEGAN_F32 ? 32 : 64; }
 // picks th (16, then 8) so that the resident weights and >= 2 patch stages fit; 0 if neither does
-static int rowsum_plan(int cout, int k, int cs, RowsumParams* p) {
-  const int nb = rowsum_nb(cout, k), nch = cs / 32;
+static int rowsum_plan(int cout, int k, int cs, int dtype, RowsumParams* p) {
+  const int cb = rowsum_cb(dtype);
+  const int nb = rowsum_nb(cout, k), nch = (cs + cb - 1) / cb;
   const long long w_total = (long long)k * nch * nb * 128;
   for (int th = 16; th >= 8; th -= 8) {
     const long long stage = (long long)(th + k - 1) * kRsRowBytes;
@@ -255,7 +269,7 @@ static int rowsum_plan(int cout, int k, int cs, RowsumParams* p) {
         p->stage_bytes = (int)stage; p->stage_tx = (int)stage;
         p->num_stages = (int)(room / stage) < kRsStages ? (int)(room / stage) : kRsStages;
         p->w_tile_bytes = nb * 128; p->w_total_bytes = (int)w_total;
-        p->nb = nb; p->nch = nch; p->cs = cs; p->k = k; p->cout = cout; p->two = 32 - k + 1;
+        p->nb = nb; p->nch = nch; p->cs = cs; p->cb = cb; p->csp = nch * cb; p->k = k; p->cout = cout; p->two = 32 - k + 1;
       }
       return th;
     }
@@ -270,27 +284,46 @@ using namespace uegan;
 extern "C" {
 
 int uegan_conv2d_rowsum_supported(int32_t cout, int32_t cin_stored, int32_t k, int32_t dtype) {
-  if (dtype != UEGAN_F32 || cin_stored % 32 != 0 || !rowsum_shape_ok(cout, k)) return 0;
+  if ((dtype != UEGAN_F32 && dtype != UEGAN_F16) || cin_stored % 32 != 0 || !rowsum_shape_ok(cout, k)) return 0;
   const char* env = getenv("UEGAN_NO_ROWSUM");
   if (env && env[0] == '1') return 0;
-  return rowsum_plan(cout, k, cin_stored, nullptr) != 0;
+  return rowsum_plan(cout, k, cin_stored, dtype, nullptr) != 0;
 }
 
 size_t uegan_packed_weight_rowsum_bytes(int32_t cout, int32_t cin_stored, int32_t k) {
-  return (size_t)rowsum_nb(cout, k) * k * cin_stored * sizeof(float);
+  // (sized for either operand type: fp32 rows of cin_stored values >= fp16 rows padded to whole 64-channel chunks)
+  return (size_t)rowsum_nb(cout, k) * k * ((cin_stored + 63) / 64 * 64) * sizeof(float);
+}
+
+static int pack_rowsum_impl(const float* w_oihw, void* w_packed, int cout, int cin_total, int cin_first, int cin,
+                            int cin_stored, int k, int dtype, const float* wscale, void* stream) {
+  UEGAN_CHECK(w_oihw && w_packed, "pack_conv_weight_rowsum: null pointer");
+  UEGAN_CHECK(cin <= cin_stored && cin_first + cin <= cin_total && rowsum_shape_ok(cout, k),
+              "pack_conv_weight_rowsum: unsupported shape (cout %d, k %d)", cout, k);
+  UEGAN_CHECK(dtype == UEGAN_F32 || dtype == UEGAN_F16, "pack_conv_weight_rowsum: fp32 (tf32) or fp16 operands");
+  const int nb = rowsum_nb(cout, k), cb = rowsum_cb(dtype);
+  const int csp = (cin_stored + cb - 1) / cb * cb;
+  const int total = nb * k * csp;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == UEGAN_F32)
+    pack_weight_rowsum_kernel<float><<<(total + 255) / 256, 256, 0, st>>>(w_oihw, static_cast<float*>(w_packed), cout,
+                                                                         cin_total, cin_first, cin, csp, k, nb, wscale);
+  else
+    pack_weight_rowsum_kernel<__half><<<(total + 255) / 256, 256, 0, st>>>(w_oihw, static_cast<__half*>(w_packed), cout,
+                                                                          cin_total, cin_first, cin, csp, k, nb, wscale);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int uegan_pack_conv_weight_rowsum(const float* w_oihw, void* w_packed, int32_t cout, int32_t cin_total, int32_t cin_first,
                                   int32_t cin, int32_t cin_stored, int32_t k, void* stream) {
-  UEGAN_CHECK(w_oihw && w_packed, "pack_conv_weight_rowsum: null pointer");
-  UEGAN_CHECK(cin <= cin_stored && cin_first + cin <= cin_total && rowsum_shape_ok(cout, k),
-              "pack_conv_weight_rowsum: unsupported shape (cout %d, k %d)", cout, k);
-  const int nb = rowsum_nb(cout, k);
-  const int total = nb * k * cin_stored;
-  pack_weight_rowsum_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w_oihw, static_cast<float*>(w_packed), cout, cin_total, cin_first, cin, cin_stored, k, nb);
-  UEGAN_CUDA(cudaGetLastError());
-  return 0;
+  return pack_rowsum_impl(w_oihw, w_packed, cout, cin_total, cin_first, cin, cin_stored, k, UEGAN_F32, nullptr, stream);
+}
+
+int uegan_pack_conv_weight_rowsum_scaled(const float* w_oihw, void* w_packed, int32_t cout, int32_t cin_total,
+                                         int32_t cin_first, int32_t cin, int32_t cin_stored, int32_t k, int32_t dtype,
+                                         const float* w_scale_dev, void* stream) {
+  return pack_rowsum_impl(w_oihw, w_packed, cout, cin_total, cin_first, cin, cin_stored, k, dtype, w_scale_dev, stream);
 }
 
 int uegan_conv2d_fprop_rowsum(const uegan_conv_desc* desc, void* stream) {
@@ -298,13 +331,17 @@ int uegan_conv2d_fprop_rowsum(const uegan_conv_desc* desc, void* stream) {
   const uegan_conv_desc& d = *desc;
   const uegan_tensor& x = d.x;
   UEGAN_CHECK(x.data && d.w_packed && d.out_nchw, "conv2d_fprop_rowsum: null pointer (planar fp32 output only)");
-  UEGAN_CHECK(x.dtype == UEGAN_F32 && x.c % 32 == 0 && d.stride == 1 && rowsum_shape_ok(d.cout, d.k) && !d.mul && !d.mask &&
-                  !d.in_stats && d.y_mul <= 1,
+  const bool f16 = x.dtype == UEGAN_F16;
+  const int es = f16 ? 2 : 4;
+  UEGAN_CHECK((x.dtype == UEGAN_F32 || f16) && x.c % 32 == 0 && d.stride == 1 && rowsum_shape_ok(d.cout, d.k) && !d.mul &&
+                  !d.mask && !d.in_stats && d.y_mul <= 1,
               "conv2d_fprop_rowsum: unsupported convolution (cout %d, k %d, stride %d, c %d)", d.cout, d.k, d.stride, x.c);
   UEGAN_CHECK(d.pad <= x.halo, "conv2d_fprop_rowsum: pad %d exceeds input halo %d", d.pad, x.halo);
   RowsumParams p;
   memset(&p, 0, sizeof(p));
-  UEGAN_CHECK(rowsum_plan(d.cout, d.k, x.c, &p) != 0, "conv2d_fprop_rowsum: weights do not fit in shared memory (c %d)", x.c);
+  UEGAN_CHECK(rowsum_plan(d.cout, d.k, x.c, x.dtype, &p) != 0,
+              "conv2d_fprop_rowsum: weights do not fit in shared memory (c %d)", x.c);
+  p.sx = x.scale; p.sw = d.w_scale;
   const int Ho = x.h + 2 * d.pad - d.k + 1, Wo = x.w + 2 * d.pad - d.k + 1;
   UEGAN_CHECK(Ho >= 1 && Wo >= 1, "conv2d_fprop_rowsum: empty output");
   p.Ho = Ho; p.Wo = Wo; p.act = d.act;
@@ -317,30 +354,30 @@ int uegan_conv2d_fprop_rowsum(const uegan_conv_desc* desc, void* stream) {
   p.err_sink = error_sink_device();
   CUtensorMap tmA, tmB;
   {  // x, padded extent: {c, w, h, n}; box = one patch of 32 channels (coordinates beyond the tensor are zero-filled)
-    const uint64_t pix = (uint64_t)x.c * 4, row = (uint64_t)t_wp(x) * pix, img = (uint64_t)t_hp(x) * row;
+    // (fp16 tensors with 32 stored channels: the 64-channel box reads 32 real channels, the rest is zero-fill)
+    const CUtensorMapDataType tdt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const uint64_t pix = (uint64_t)x.c * es, row = (uint64_t)t_wp(x) * pix, img = (uint64_t)t_hp(x) * row;
     uint64_t dims[4] = {(uint64_t)x.c, (uint64_t)t_wp(x), (uint64_t)t_hp(x), (uint64_t)x.n};
     uint64_t strides[3] = {pix, row, img};
-    uint32_t box[4] = {32u, 32u, (uint32_t)p.ph, 1u};
-    if (encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x.data, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
-      return -1;
-  }
-  {
-    const uint64_t ktot = (uint64_t)d.k * x.c;
-    uint64_t dims[2] = {ktot, (uint64_t)p.nb};
-    uint64_t strides[1] = {ktot * 4};
-    uint32_t box[2] = {32u, (uint32_t)p.nb};
-    if (encode_tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(d.w_packed), dims, strides, box,
-                     CU_TENSOR_MAP_SWIZZLE_128B))
+    uint32_t box[4] = {(uint32_t)p.cb, 32u, (uint32_t)p.ph, 1u};
+    if (encode_tiled(&tmA, tdt, 4, x.data, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    const uint64_t ktot = (uint64_t)d.k * p.csp;
+    uint64_t wdims[2] = {ktot, (uint64_t)p.nb};
+    uint64_t wstrides[1] = {ktot * es};
+    uint32_t wbox[2] = {(uint32_t)p.cb, (uint32_t)p.nb};
+    if (encode_tiled(&tmB, tdt, 2, const_cast<void*>(d.w_packed), wdims, wstrides, wbox, CU_TENSOR_MAP_SWIZZLE_128B))
       return -1;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    UEGAN_CUDA(cudaFuncSetAttribute(conv_rowsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    UEGAN_CUDA(cudaFuncSetAttribute(conv_rowsum_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    UEGAN_CUDA(cudaFuncSetAttribute(conv_rowsum_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_set = true;
   }
   const int smem_bytes = p.w_total_bytes + p.num_stages * p.stage_bytes + 1024;
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_rowsum_kernel<<<grid, 384, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  if (f16) conv_rowsum_kernel<1><<<grid, 384, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  else conv_rowsum_kernel<0><<<grid, 384, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -17,8 +17,14 @@
 namespace uegan {
 
 constexpr int kWgStageRows = 64;                      // pixels per K stage
-constexpr int kWgBoxBytes = kWgStageRows * 128;       // one {32 ch x 64 px} box
-constexpr int kWgABytes = 4 * kWgBoxBytes;            // M = 128 channels
+constexpr int kWgBoxBytes = kWgStageRows * 128;       // one {128 bytes of channels x 64 px} box: 32 tf32 / 64 fp16 channels
+// M = 128 channels: 4 boxes of 32 tf32 channels, 2 boxes of 64 fp16 channels
+template <int kF16> struct WgT {
+  static constexpr int CB = kF16 ? 64 : 32;           // channels per box (one 128-byte swizzle row)
+  static constexpr int MBOX = 128 / CB;               // boxes of the M operand
+  static constexpr int ABYTES = MBOX * kWgBoxBytes;
+  static constexpr int KROWS = kF16 ? 16 : 8;         // pixels (K) per MMA
+};
 
 struct WgradParams {
   int tiles_w, tiles_h, nimg;      // 8x8 pixel tiles over (wo, ho, n)
@@ -32,10 +38,12 @@ struct WgradParams {
   int tap_boxes;                   // 32-column boxes per tap
   int cout, cin, cin_total, cin_first, x_c;
   int m_tiles, n_chunks;
+  int a_bytes;                     // bytes of the M operand per stage (WgT::ABYTES)
   float* dw;                       // OIHW fp32
   float* partial;                  // deterministic mode: [k-split slice][dw_numel] partial sums, reduced in slice order
   long long dw_numel;
   const float* alpha;
+  const float *sx, *sdz;           // per-tensor scales of x and dz (NULL = 1): the weight gradient is a true-scale value
   float scale;
   unsigned int* err_sink;
 };
@@ -60,8 +68,10 @@ __global__ void wgrad_reduce_kernel(float* __restrict__ dw, const float* __restr
   dw[i] += acc;
 }
 
+template <int kF16>
 __global__ void __launch_bounds__(256, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
+  constexpr int CB = WgT<kF16>::CB, MBOX = WgT<kF16>::MBOX, kWgABytes = WgT<kF16>::ABYTES, KROWS = WgT<kF16>::KROWS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[4];
@@ -81,7 +91,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int r = tap;  // swap mode only
   const int t_first = tap * p.tap_group;
   const int t_count = p.swap_mode ? 1 : min(p.tap_group, p.taps_total - t_first);
-  const int N = p.n_boxes * 32;
+  const int N = p.n_boxes * CB;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -117,12 +127,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           if (p.swap_mode) {
             // M operand = 128 consecutive window elements (s, c) of filter row r, N operand = the 32 stored dz channels
-            for (int g = 0; g < 4; ++g)
-              tma_load_5d(&tmB, &full_bar[stage], sa + g * kWgBoxBytes, mt * 128 + g * 32, wo0, r, ho0, n);
+            for (int g = 0; g < MBOX; ++g)
+              tma_load_5d(&tmB, &full_bar[stage], sa + g * kWgBoxBytes, mt * 128 + g * CB, wo0, r, ho0, n);
             tma_load_4d(&tmA, &full_bar[stage], sb, 0, wo0, ho0, n);
           } else {
-            for (int g = 0; g < 4; ++g)
-              tma_load_4d(&tmA, &full_bar[stage], sa + g * kWgBoxBytes, mt * 128 + g * 32, wo0, ho0, n);
+            for (int g = 0; g < MBOX; ++g)
+              tma_load_4d(&tmA, &full_bar[stage], sa + g * kWgBoxBytes, mt * 128 + g * CB, wo0, ho0, n);
             // B map = the fprop sliding-window map {window, wo, r, ho, n}: tap column s and channel offset are both
             // positions inside the window of k*C contiguous (s, c) values that starts at the pixel
             for (int t = 0; t < t_count; ++t) {
@@ -130,7 +140,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const int tr = p.window_mode ? tp : tp / p.k, ts = p.window_mode ? 0 : tp % p.k;
               for (int g = 0; g < p.tap_boxes; ++g)
                 tma_load_5d(&tmB, &full_bar[stage], sb + (t * p.tap_boxes + g) * kWgBoxBytes,
-                            ts * p.x_c + nc * p.tap_boxes * 32 + g * 32, wo0, tr, ho0, n);
+                            ts * p.x_c + nc * p.tap_boxes * CB + g * CB, wo0, tr, ho0, n);
             }
           }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
@@ -138,7 +148,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     } else if (warp == 1) {
       if (elect_one()) {
-        const uint32_t idesc = make_instr_desc(UMMA_TF32, 128, N, /*a_mn_major=*/1, /*b_mn_major=*/1);
+        const uint32_t idesc = make_instr_desc(kF16 ? UMMA_F16 : UMMA_TF32, 128, N, /*a_mn_major=*/1, /*b_mn_major=*/1);
         int stage = 0;
         uint32_t phase = 0;
         uint32_t first = 0;
@@ -148,11 +158,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // MN-major tf32 operands exist only in the SWIZZLE_128B_BASE32B layout (32-byte chunks XORed with row & 3,
           // 4-row atoms; cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem
           // layout"): LBO = stride between 32-channel groups (one TMA box), SBO = stride between 4-row groups.
-          const uint64_t da0 = make_smem_desc(smem_u32(smem + stage * p.stage_bytes), kWgBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
+          // MN-major fp16 operands: the plain SWIZZLE_128B layout, ((64 ch, n), (8 px, k)) : ((1, LBO), (128 B, SBO)):
+          // 8-row atoms of 128-byte rows, SBO = 1024 bytes between them, LBO = one box between 64-channel groups.
+          const uint64_t da0 = kF16 ? make_smem_desc(smem_u32(smem + stage * p.stage_bytes), kWgBoxBytes, 1024, UMMA_LAYOUT_SW128)
+                                    : make_smem_desc(smem_u32(smem + stage * p.stage_bytes), kWgBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
           const uint64_t db0 = da0 + (kWgABytes >> 4);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {  // 8 pixels (one 1024-byte group of rows) per MMA
-            umma_ss<1>(tmem_base, da0 + ks * 64, db0 + ks * 64, idesc, (first | ks) != 0 ? 1u : 0u);
+          for (int ks = 0; ks < kWgStageRows / KROWS; ++ks) {  // KROWS pixels (KROWS x 128 bytes of rows) per MMA
+            umma_ss<kF16 ? 0 : 1>(tmem_base, da0 + ks * (KROWS * 8), db0 + ks * (KROWS * 8), idesc,
+                                  (first | ks) != 0 ? 1u : 0u);
           }
           first = 1;
           umma_commit(&empty_bar[stage]);
@@ -166,7 +180,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&done_bar, 0, 0x800, p.err_sink);
       tcgen05_fence_after();
       const int o = mt * 128 + q * 32 + lane;
-      const float sc = p.scale * (p.alpha ? __ldg(p.alpha) : 1.f);
+      const float sc = p.scale * (p.alpha ? __ldg(p.alpha) : 1.f) /
+                       ((p.sx ? __ldg(p.sx) : 1.f) * (p.sdz ? __ldg(p.sdz) : 1.f));
       const int kk = p.k * p.k;
       for (int c0 = 0; c0 < N; c0 += 16) {
         uint32_t rr[16];
@@ -187,7 +202,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           continue;
         }
         if (o >= p.cout) continue;
-        const int ncol = p.tap_boxes * 32;  // columns per tap
+        const int ncol = p.tap_boxes * CB;  // columns per tap
         const int tl = c0 / ncol;           // a 16-column chunk never straddles taps (ncol is a multiple of 32)
         if (tl >= t_count) continue;
         const int tp = t_first + tl;
@@ -196,7 +211,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int i = 0; i < 16; ++i) {
           const int j = (c0 + i) - tl * ncol;
           int c, ss;
-          if (p.window_mode) { ss = j >> 2; c = j & 3; }  // window column = (s, c) with 4 stored channels
+          if (p.window_mode) { ss = j / p.x_c; c = j - ss * p.x_c; }  // window column = (s, c), x_c stored channels (RGB)
           else { ss = ts; c = nc * ncol + j; }
           if (c < p.cin && ss < p.k) {
             const float v = __uint_as_float(rr[i]) * sc;
@@ -248,21 +263,29 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
                                   float* dw_oihw, const float* alpha_dev, float scale, float* ws, size_t ws_bytes,
                                   void* stream) {
   UEGAN_CHECK(x && dz && x->data && dz->data && dw_oihw, "conv2d_wgrad: null pointer");
-  UEGAN_CHECK(x->dtype == UEGAN_F32 && dz->dtype == UEGAN_F32, "conv2d_wgrad: fp32 (tf32) tensors only");
+  UEGAN_CHECK(x->dtype == dz->dtype && (x->dtype == UEGAN_F32 || x->dtype == UEGAN_F16),
+              "conv2d_wgrad: x and dz must both be fp32 (kind::tf32) or both fp16 (kind::f16)");
+  const bool f16 = x->dtype == UEGAN_F16;
+  const int es = f16 ? 2 : 4, CB = f16 ? 64 : 32;  // element size, channels per 128-byte box
+  const int a_bytes = (128 / CB) * kWgBoxBytes;
   UEGAN_CHECK(stride == 1 || stride == 2, "conv2d_wgrad: stride %d", stride);
   UEGAN_CHECK(pad <= x->halo && k >= 1 && k <= 7, "conv2d_wgrad: bad pad/k");
   const int Ho = (x->h + 2 * pad - k) / stride + 1, Wo = (x->w + 2 * pad - k) / stride + 1;
   UEGAN_CHECK(dz->n == x->n && dz->h == Ho && dz->w == Wo, "conv2d_wgrad: dz is %dx%dx%d, expected %dx%dx%d", dz->n,
               dz->h, dz->w, x->n, Ho, Wo);
   UEGAN_CHECK(cout <= dz->c && cin <= x->c && cin_first + cin <= cin_total, "conv2d_wgrad: channel mismatch");
-  UEGAN_CHECK((dz->c * 4) % 128 == 0, "conv2d_wgrad: dz must store a multiple of 32 channels (got %d)", dz->c);
-  const bool window = (x->c == 4);
+  // (channels beyond a tensor's extent are TMA zero-fill: any channel count whose pixel is a multiple of 16 bytes works;
+  // whole 128-byte boxes are the efficient case)
+  UEGAN_CHECK((dz->c * es) % 16 == 0 && (f16 || (dz->c * es) % 128 == 0),
+              "conv2d_wgrad: unsupported dz channel count %d", dz->c);
+  const bool window = (x->c * es == 16);  // RGB input stored as one 16-byte pixel
   if (stride == 1 && !window && k > 1) {
     const int took = launch_wgrad_patch(x, dz, cout, cin, cin_total, cin_first, k, pad, dw_oihw, alpha_dev, scale, ws,
                                         ws_bytes, static_cast<cudaStream_t>(stream));
     if (took != 0) return took < 0 ? -1 : 0;
   }
-  UEGAN_CHECK(window || (x->c * 4) % 128 == 0, "conv2d_wgrad: x must store 4 or a multiple of 32 channels (got %d)", x->c);
+  UEGAN_CHECK(window || (f16 ? (x->c * es) % 16 == 0 : (x->c * 4) % 128 == 0),
+              "conv2d_wgrad: unsupported x channel count %d", x->c);
 
   WgradParams p;
   memset(&p, 0, sizeof(p));
@@ -280,31 +303,32 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   p.swap_mode = swap;
   int N;
   if (swap) {
-    N = 32; p.n_chunks = 1;
+    N = CB; p.n_chunks = 1;  // the (<= 32) dz channels: one box, zero-filled beyond the tensor
     p.taps = k;
     p.m_tiles = (k * x->c + 127) / 128;
     p.tap_group = 1; p.taps_total = k; p.tap_boxes = 1;
   } else if (window) {
-    // RGB input: one "tap" = a filter row (the 32 (s, c) window values); all k rows side by side: N = 32 k
-    UEGAN_CHECK(k * 4 <= 32 && k <= 8, "conv2d_wgrad: window mode needs k*4 <= 32");
+    // RGB input: one "tap" = a filter row (the (s, c) window values of one box); rows side by side while N <= 256
+    UEGAN_CHECK(k * x->c <= CB && k <= 8, "conv2d_wgrad: window mode needs k * stored channels <= %d", CB);
     p.taps_total = k;
     p.tap_boxes = 1;
-    p.tap_group = k;
-    N = 32 * k; p.n_chunks = 1;
+    p.tap_group = k < 256 / CB ? k : 256 / CB;
+    N = CB * p.tap_group; p.n_chunks = 1;
   } else {
     // several taps per MMA while the per-tap width leaves room in N <= 256 (A = dz is then read once per GROUP)
-    const int cpad = (cin + 31) / 32 * 32;
+    const int cpad = (cin + CB - 1) / CB * CB;
     const int ncol = cpad < 256 ? cpad : 256;
     p.n_chunks = (cpad + ncol - 1) / ncol;
-    p.tap_boxes = ncol / 32;
+    p.tap_boxes = ncol / CB;
     p.taps_total = k * k;
     p.tap_group = 256 / ncol;
     if (p.tap_group > p.taps_total) p.tap_group = p.taps_total;
     N = p.tap_group * ncol;
   }
-  p.n_boxes = N / 32;
+  p.n_boxes = N / CB;
   if (!swap) p.taps = (p.taps_total + p.tap_group - 1) / p.tap_group;
-  p.stage_bytes = kWgABytes + p.n_boxes * kWgBoxBytes;
+  p.a_bytes = a_bytes;
+  p.stage_bytes = a_bytes + p.n_boxes * kWgBoxBytes;
   p.num_stages = (200 * 1024) / p.stage_bytes;
   if (p.num_stages > 4) p.num_stages = 4;
   UEGAN_CHECK(p.num_stages >= 2, "conv2d_wgrad: stage too large");
@@ -319,37 +343,41 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   p.partial = ws;
   p.alpha = alpha_dev;
   p.scale = scale;
+  p.sx = x->scale;
+  p.sdz = dz->scale;
   p.err_sink = error_sink_device();
 
   p.x_c = x->c;
   CUtensorMap tmA, tmB;
+  const CUtensorMapDataType tdt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle tsw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   {  // dz interior: {c, wo, ho, n}; coordinates beyond the interior / beyond Cout are zero-filled
-    const uint64_t pix = (uint64_t)dz->c * 4, row = (uint64_t)t_wp(*dz) * pix, img = (uint64_t)t_hp(*dz) * row;
+    const uint64_t pix = (uint64_t)dz->c * es, row = (uint64_t)t_wp(*dz) * pix, img = (uint64_t)t_hp(*dz) * row;
     uint8_t* base = static_cast<uint8_t*>(dz->data) + (uint64_t)dz->halo * row + (uint64_t)dz->halo * pix;
     uint64_t dims[4] = {(uint64_t)dz->c, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)dz->n};
     uint64_t strides[3] = {pix, row, img};
-    uint32_t box[4] = {32u, 8u, 8u, 1u};
-    if (encode_tiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-      return -1;
+    uint32_t box[4] = {(uint32_t)CB, 8u, 8u, 1u};
+    if (encode_tiled(&tmA, tdt, 4, base, dims, strides, box, tsw)) return -1;
   }
   {  // x: sliding-window map {window, wo, r, ho, n} (conv_fprop.cu)
-    const uint64_t pix = (uint64_t)x->c * 4, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
+    const uint64_t pix = (uint64_t)x->c * es, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
     uint8_t* base = static_cast<uint8_t*>(x->data) + (uint64_t)(x->halo - pad) * row + (uint64_t)(x->halo - pad) * pix;
-    const uint64_t win = window ? 32u : (uint64_t)k * x->c;
+    const uint64_t win = window ? (uint64_t)CB : (uint64_t)k * x->c;
     uint64_t dims[5] = {win, (uint64_t)Wo, (uint64_t)k, (uint64_t)Ho, (uint64_t)x->n};
     uint64_t strides[4] = {(uint64_t)stride * pix, row, (uint64_t)stride * row, img};
-    uint32_t box[5] = {32u, 8u, 1u, 8u, 1u};
-    if (encode_tiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-      return -1;
+    uint32_t box[5] = {(uint32_t)CB, 8u, 1u, 8u, 1u};
+    if (encode_tiled(&tmB, tdt, 5, base, dims, strides, box, tsw)) return -1;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    UEGAN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    UEGAN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    UEGAN_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_set = true;
   }
   const int smem_bytes = p.num_stages * p.stage_bytes + 1024;
   dim3 grid((unsigned)p.ksplit, (unsigned)p.taps, (unsigned)(p.m_tiles * p.n_chunks));
-  conv_wgrad_kernel<<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  if (f16) conv_wgrad_kernel<1><<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  else conv_wgrad_kernel<0><<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   UEGAN_CUDA(cudaGetLastError());
   return wg_reduce(dw_oihw, ws, p.dw_numel, p.ksplit, p.total_ktiles, cin_total, cin_first, cin, k,
                    static_cast<cudaStream_t>(stream));
@@ -386,13 +414,19 @@ struct WgradPatchParams {
   float* partial;
   long long dw_numel;
   const float* alpha;
+  const float *sx, *sdz;  // per-tensor scales of x and dz (NULL = 1)
   float scale;
   unsigned int* err_sink;
 };
 
+// kF16: fp16 operands -- 64-channel chunks (one 128-byte row per pixel), M = 128 = TWO taps x 64 channels per group, K = 16
+// pixels per MMA = two tile rows (K-atom stride SBO = one patch row for A, 1024 B for the dz tile).
+template <int kF16>
 __global__ void __launch_bounds__(256, 1)
 conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ,
                         const WgradPatchParams p) {
+  constexpr int CB = kF16 ? 64 : 32;       // channels per chunk
+  constexpr int TPG = 128 / CB;            // taps per M = 128 group (4 tf32, 2 fp16)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[4];
@@ -403,7 +437,7 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const int per = (p.total_ktiles + p.ksplit - 1) / p.ksplit;
   const int kt0 = blockIdx.x * per, kt1 = min(kt0 + per, p.total_ktiles);
   const int acc0 = blockIdx.y * p.acc_per_cta, acc1 = min(acc0 + p.acc_per_cta, p.acc_total);
-  const int N = p.n_boxes * 32;
+  const int N = p.n_boxes * CB;
   // accumulator index a -> (chunk, r, g):  a = (chunk * k + r) * kgroups + g.  The chunks this CTA touches:
   const int ch_lo = acc0 / (p.rk * p.kgroups), ch_hi = (acc1 - 1) / (p.rk * p.kgroups);
   const int nch = ch_hi - ch_lo + 1;
@@ -441,15 +475,15 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           uint8_t* sz = sp + nch * p.patch_bytes;
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           for (int c = 0; c < nch; ++c)
-            tma_load_4d(&tmX, &full_bar[stage], sp + c * p.patch_bytes, (ch_lo + c) * 32, wo0 + p.off, ho0 + p.off, n);
+            tma_load_4d(&tmX, &full_bar[stage], sp + c * p.patch_bytes, (ch_lo + c) * CB, wo0 + p.off, ho0 + p.off, n);
           for (int g = 0; g < p.n_boxes; ++g)
-            tma_load_4d(&tmZ, &full_bar[stage], sz + g * 64 * 128, g * 32, wo0, ho0, n);
+            tma_load_4d(&tmZ, &full_bar[stage], sz + g * 64 * 128, g * CB, wo0, ho0, n);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
     } else if (warp == 1) {
       if (elect_one()) {
-        const uint32_t idesc = make_instr_desc(UMMA_TF32, 128, N, 1, 1);
+        const uint32_t idesc = make_instr_desc(kF16 ? UMMA_F16 : UMMA_TF32, 128, N, 1, 1);
         int stage = 0;
         uint32_t phase = 0;
         uint32_t first = 0;
@@ -458,20 +492,25 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           tcgen05_fence_after();
           const uint32_t sp = smem_u32(smem + stage * p.stage_bytes);
           const uint32_t sz = sp + nch * p.patch_bytes;
-          // A: M-group stride (LBO) = one pixel row: the 4 taps of a group are the same rows shifted by 0..3 pixels
-          const uint64_t da0 = make_smem_desc(sp, (uint32_t)p.lbo_bytes, 512, UMMA_LAYOUT_SW128_B32);
-          const uint64_t db0 = make_smem_desc(sz, 64 * 128, 512, UMMA_LAYOUT_SW128_B32);
+          // A: M-group stride (LBO) = one pixel row: the taps of a group are the same rows shifted by 0, 1, .. pixels.
+          // tf32: 4-row K atoms inside one tile row (SBO 512); fp16: 8-row K atoms, the second one is the NEXT tile row
+          // of the patch (SBO = patch row pitch; tcgen05 swizzles on absolute address bits, so any 128-byte multiple works)
+          const uint64_t da0 = kF16 ? make_smem_desc(sp, (uint32_t)p.lbo_bytes, (uint32_t)p.pw * 128, UMMA_LAYOUT_SW128)
+                                    : make_smem_desc(sp, (uint32_t)p.lbo_bytes, 512, UMMA_LAYOUT_SW128_B32);
+          const uint64_t db0 = kF16 ? make_smem_desc(sz, 64 * 128, 1024, UMMA_LAYOUT_SW128)
+                                    : make_smem_desc(sz, 64 * 128, 512, UMMA_LAYOUT_SW128_B32);
           const uint32_t row_step = p.pw * 8;  // one patch row, in descriptor units of 16 bytes
           int g = acc0 % p.kgroups, r = (acc0 / p.kgroups) % p.rk, c = acc0 / (p.kgroups * p.rk) - ch_lo;
           uint32_t d_tmem = tmem_base;
           for (int a = acc0; a < acc1; ++a) {
-            // first tap of the group: (row r, column 4g) of the patch, or (row 4g, column 0) in vertical mode
-            const uint32_t tap0 = p.vert ? (uint32_t)(4 * g * p.pw) : (uint32_t)(r * p.pw + 4 * g);
+            // first tap of the group: (row r, column TPG*g) of the patch, or (row TPG*g, column 0) in vertical mode
+            const uint32_t tap0 = p.vert ? (uint32_t)(TPG * g * p.pw) : (uint32_t)(r * p.pw + TPG * g);
             uint64_t da = da0 + (uint32_t)(c * (p.patch_bytes >> 4)) + tap0 * 8;
+            constexpr int KSTEPS = kF16 ? 4 : 8;  // MMAs per 8x8 pixel tile: K = 8 (one tile row) or 16 (two tile rows)
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              umma_ss<1>(d_tmem, da, db0 + ks * 64, idesc, (first | ks) != 0 ? 1u : 0u);
-              da += row_step;
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+              umma_ss<kF16 ? 0 : 1>(d_tmem, da, db0 + ks * (kF16 ? 128 : 64), idesc, (first | ks) != 0 ? 1u : 0u);
+              da += kF16 ? 2 * row_step : row_step;
             }
             d_tmem += N;
             if (++g == p.kgroups) { g = 0; if (++r == p.rk) { r = 0; ++c; } }
@@ -486,12 +525,13 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       const int q = warp & 3;
       mbar_wait(&done_bar, 0, 0xC00, p.err_sink);
       tcgen05_fence_after();
-      const int m = q * 32 + lane;        // row of D: tap j = m / 32 of the group, channel m % 32 of the chunk
-      const float sc = p.scale * (p.alpha ? __ldg(p.alpha) : 1.f);
+      const int m = q * 32 + lane;        // row of D: tap j = m / CB of the group, channel m % CB of the chunk
+      const float sc = p.scale * (p.alpha ? __ldg(p.alpha) : 1.f) /
+                       ((p.sx ? __ldg(p.sx) : 1.f) * (p.sdz ? __ldg(p.sdz) : 1.f));
       const int kk = p.k * p.k;
       for (int a = acc0; a < acc1; ++a) {
         const int g = a % p.kgroups, r = (a / p.kgroups) % p.rk, chunk = a / (p.kgroups * p.rk);
-        const int s_ = 4 * g + (m >> 5), c = chunk * 32 + (m & 31);  // vertical mode: s_ is the filter ROW
+        const int s_ = TPG * g + m / CB, c = chunk * CB + (m % CB);  // vertical mode: s_ is the filter ROW
         for (int c0 = 0; c0 < N; c0 += 16) {
           uint32_t rr[16];
           tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (a - acc0) * N + c0, rr);
@@ -526,22 +566,36 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 }
 
 // returns 1 if the patch kernel took the job, 0 if the caller should use the generic kernel, -1 on error
+template <int kF16>
+static int wgrad_patch_set_attr() {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_wgrad_patch_kernel<kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
+        cudaSuccess)
+      return set_error("conv2d_wgrad: cudaFuncSetAttribute failed");
+    attr_set = true;
+  }
+  return 0;
+}
+
 static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int cout, int cin, int cin_total,
                               int cin_first, int k, int pad, float* dw, const float* alpha, float scale, float* ws,
                               size_t ws_bytes, cudaStream_t stream) {
   const char* env = getenv("UEGAN_NO_WGRAD_PATCH");
   if (env && env[0] == '1') return 0;
+  const bool f16 = x->dtype == UEGAN_F16;
+  const int es = f16 ? 2 : 4, CB = f16 ? 64 : 32, TPG = 128 / CB;
   if (x->c % 32 != 0 || dz->c % 32 != 0 || cout > 64 || k > 8) return 0;
   const int Ho = x->h + 2 * pad - k + 1, Wo = x->w + 2 * pad - k + 1;
   if (Ho < 8 || Wo < 8) return 0;
   WgradPatchParams p;
   memset(&p, 0, sizeof(p));
-  const int N = (cout + 31) / 32 * 32;
-  p.n_boxes = N / 32;
+  const int N = (cout + CB - 1) / CB * CB;
+  p.n_boxes = N / CB;
   p.k = k;
-  p.kgroups = (k + 3) / 4;
-  p.chunks = (cin + 31) / 32;
-  p.pw = 8 + 4 * p.kgroups - 1;
+  p.kgroups = (k + TPG - 1) / TPG;
+  p.chunks = (cin + CB - 1) / CB;
+  p.pw = 8 + TPG * p.kgroups - 1;
   p.ph = 8 + k - 1;
   p.patch_bytes = (p.ph * p.pw * 128 + 1023) / 1024 * 1024;
   p.dz_bytes = p.n_boxes * 64 * 128;
@@ -571,37 +625,35 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
   p.off = x->halo - pad;
   p.cout = cout; p.cin = cin; p.cin_total = cin_total; p.cin_first = cin_first;
   p.dw = dw; p.partial = ws; p.alpha = alpha; p.scale = scale;
+  p.sx = x->scale; p.sdz = dz->scale;
   p.err_sink = error_sink_device();
+  const CUtensorMapDataType tdt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle tsw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX, tmZ;
   {  // x, padded extent: {c, w, h, n}
-    const uint64_t pix = (uint64_t)x->c * 4, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
+    const uint64_t pix = (uint64_t)x->c * es, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
     uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)t_wp(*x), (uint64_t)t_hp(*x), (uint64_t)x->n};
     uint64_t strides[3] = {pix, row, img};
-    uint32_t box[4] = {32u, (uint32_t)p.pw, (uint32_t)p.ph, 1u};
-    if (encode_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x->data, dims, strides, box,
-                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-      return -1;
+    uint32_t box[4] = {(uint32_t)CB, (uint32_t)p.pw, (uint32_t)p.ph, 1u};
+    if (encode_tiled(&tmX, tdt, 4, x->data, dims, strides, box, tsw)) return -1;
   }
   {  // dz interior: {c, wo, ho, n}
-    const uint64_t pix = (uint64_t)dz->c * 4, row = (uint64_t)t_wp(*dz) * pix, img = (uint64_t)t_hp(*dz) * row;
+    const uint64_t pix = (uint64_t)dz->c * es, row = (uint64_t)t_wp(*dz) * pix, img = (uint64_t)t_hp(*dz) * row;
     uint8_t* base = static_cast<uint8_t*>(dz->data) + (uint64_t)dz->halo * row + (uint64_t)dz->halo * pix;
     uint64_t dims[4] = {(uint64_t)dz->c, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)dz->n};
     uint64_t strides[3] = {pix, row, img};
-    uint32_t box[4] = {32u, 8u, 8u, 1u};
-    if (encode_tiled(&tmZ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box,
-                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-      return -1;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_wgrad_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) !=
-        cudaSuccess)
-      return set_error("conv2d_wgrad: cudaFuncSetAttribute failed");
-    attr_set = true;
+    uint32_t box[4] = {(uint32_t)CB, 8u, 8u, 1u};
+    if (encode_tiled(&tmZ, tdt, 4, base, dims, strides, box, tsw)) return -1;
   }
   const int smem_bytes = p.num_stages * p.stage_bytes + 1024;
   dim3 grid((unsigned)p.ksplit, (unsigned)slices, 1u);
-  conv_wgrad_patch_kernel<<<grid, 256, smem_bytes, stream>>>(tmX, tmZ, p);
+  if (f16) {
+    if (wgrad_patch_set_attr<1>()) return -1;
+    conv_wgrad_patch_kernel<1><<<grid, 256, smem_bytes, stream>>>(tmX, tmZ, p);
+  } else {
+    if (wgrad_patch_set_attr<0>()) return -1;
+    conv_wgrad_patch_kernel<0><<<grid, 256, smem_bytes, stream>>>(tmX, tmZ, p);
+  }
   if (cudaGetLastError() != cudaSuccess) return set_error("conv2d_wgrad: patch kernel launch failed");
   if (wg_reduce(dw, ws, p.dw_numel, p.ksplit, p.total_ktiles, cin_total, cin_first, cin, k, stream)) return -1;
   return 1;
@@ -615,8 +667,11 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
                                          int32_t cin_total, int32_t cin_first, int32_t k, int32_t pad, float* dw_oihw,
                                          const float* alpha_dev, float scale, float* ws, size_t ws_bytes, void* stream) {
   UEGAN_CHECK(x && e && x->data && e->data && dw_oihw, "conv2d_wgrad_hstack: null pointer");
-  UEGAN_CHECK(x->dtype == UEGAN_F32 && e->dtype == UEGAN_F32 && x->c % 32 == 0 && e->c == 32 && e->halo == 0,
-              "conv2d_wgrad_hstack: fp32 tensors, x.c %% 32 == 0, 32-channel stack without halo");
+  UEGAN_CHECK(x->dtype == e->dtype && (x->dtype == UEGAN_F32 || x->dtype == UEGAN_F16) && x->c % 32 == 0 && e->c == 32 &&
+                  e->halo == 0,
+              "conv2d_wgrad_hstack: fp32 or fp16 tensors, x.c %% 32 == 0, 32-channel stack without halo");
+  const bool f16 = x->dtype == UEGAN_F16;
+  const int es = f16 ? 2 : 4, CB = f16 ? 64 : 32, TPG = 128 / CB;
   UEGAN_CHECK(k >= 1 && k <= 7 && (k & 1) && pad == (k - 1) / 2 && pad <= x->halo && k * cout <= 32,
               "conv2d_wgrad_hstack: unsupported k %d / pad %d / cout %d", k, pad, cout);
   UEGAN_CHECK(e->n == x->n && e->h == x->h && e->w == x->w + k - 1, "conv2d_wgrad_hstack: stack is %dx%dx%d, expected %dx%dx%d",
@@ -624,20 +679,21 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
   UEGAN_CHECK(cin <= x->c && cin_first + cin <= cin_total, "conv2d_wgrad_hstack: channel mismatch");
   WgradPatchParams p;
   memset(&p, 0, sizeof(p));
-  p.n_boxes = 1;
+  p.n_boxes = 1;  // the 32 (s, o) columns of the stack: one box (fp16: zero-filled beyond the 32 stored channels)
   p.k = k;
-  p.kgroups = (k + 3) / 4;
-  p.chunks = (cin + 31) / 32;
+  p.kgroups = (k + TPG - 1) / TPG;
+  p.chunks = (cin + CB - 1) / CB;
   p.vert = 1; p.rk = 1;
   p.pw = 8;
-  p.ph = 8 + 4 * p.kgroups - 1;       // rows 0 .. 7 + (4*kgroups - 1): M-group j of the last group stays inside
+  p.ph = 8 + TPG * p.kgroups - 1;     // rows 0 .. 7 + (TPG*kgroups - 1): M-group j of the last group stays inside
   p.lbo_bytes = p.pw * 128;           // M-group stride = one patch row
   p.patch_bytes = p.ph * p.pw * 128;  // a multiple of 1024
   p.dz_bytes = 64 * 128;
   p.acc_total = p.chunks * p.kgroups;
-  // channel chunks per CTA: at least 3 stages of (chunks * patch + stack tile) in 200 KB, at most 512 / 32 accumulators
+  const int N = CB;
+  // channel chunks per CTA: at least 3 stages of (chunks * patch + stack tile) in 200 KB, at most 512 / N accumulators
   int nch_max = ((200 * 1024) / 3 - p.dz_bytes) / p.patch_bytes;
-  if (nch_max > 16 / p.kgroups) nch_max = 16 / p.kgroups;
+  if (nch_max > (512 / N) / p.kgroups) nch_max = (512 / N) / p.kgroups;
   if (nch_max < 1) nch_max = 1;
   const int slices = (p.chunks + nch_max - 1) / nch_max;
   const int nch = (p.chunks + slices - 1) / slices;
@@ -659,34 +715,34 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
   p.off = x->halo - pad;
   p.cout = cout; p.cin = cin; p.cin_total = cin_total; p.cin_first = cin_first;
   p.dw = dw_oihw; p.partial = ws; p.alpha = alpha_dev; p.scale = scale;
+  p.sx = x->scale; p.sdz = e->scale;
   p.err_sink = error_sink_device();
+  const CUtensorMapDataType tdt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle tsw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX, tmZ;
   {  // x, padded extent: {c, w, h, n}
-    const uint64_t pix = (uint64_t)x->c * 4, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
+    const uint64_t pix = (uint64_t)x->c * es, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
     uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)t_wp(*x), (uint64_t)t_hp(*x), (uint64_t)x->n};
     uint64_t strides[3] = {pix, row, img};
-    uint32_t box[4] = {32u, (uint32_t)p.pw, (uint32_t)p.ph, 1u};
-    if (encode_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x->data, dims, strides, box,
-                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-      return -1;
+    uint32_t box[4] = {(uint32_t)CB, (uint32_t)p.pw, (uint32_t)p.ph, 1u};
+    if (encode_tiled(&tmX, tdt, 4, x->data, dims, strides, box, tsw)) return -1;
   }
   {  // the stack: {32, w + k - 1, h, n}
-    const uint64_t pix = 128, row = (uint64_t)e->w * pix, img = (uint64_t)e->h * row;
+    const uint64_t pix = 32 * es, row = (uint64_t)e->w * pix, img = (uint64_t)e->h * row;
     uint64_t dims[4] = {32u, (uint64_t)e->w, (uint64_t)e->h, (uint64_t)e->n};
     uint64_t strides[3] = {pix, row, img};
-    uint32_t box[4] = {32u, 8u, 8u, 1u};
-    if (encode_tiled(&tmZ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e->data, dims, strides, box,
-                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-      return -1;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    UEGAN_CUDA(cudaFuncSetAttribute(conv_wgrad_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    attr_set = true;
+    uint32_t box[4] = {(uint32_t)CB, 8u, 8u, 1u};
+    if (encode_tiled(&tmZ, tdt, 4, e->data, dims, strides, box, tsw)) return -1;
   }
   const int smem_bytes = p.num_stages * p.stage_bytes + 1024;
   dim3 grid((unsigned)p.ksplit, (unsigned)slices, 1u);
-  conv_wgrad_patch_kernel<<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmX, tmZ, p);
+  if (f16) {
+    if (wgrad_patch_set_attr<1>()) return -1;
+    conv_wgrad_patch_kernel<1><<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmX, tmZ, p);
+  } else {
+    if (wgrad_patch_set_attr<0>()) return -1;
+    conv_wgrad_patch_kernel<0><<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmX, tmZ, p);
+  }
   UEGAN_CUDA(cudaGetLastError());
   return wg_reduce(dw_oihw, ws, p.dw_numel, p.ksplit, p.total_ktiles, cin_total, cin_first, cin, k,
                    static_cast<cudaStream_t>(stream));

@@ -79,13 +79,18 @@ struct TGeom {  // device-side view of a uegan_tensor
   void* data;
   int n, h, w, c, halo;
   long long wp, hp;
+  const float* scale;  // uegan_tensor.scale: stored = scale * true (NULL = 1)
 };
 static TGeom geom(const uegan_tensor& t) {
   TGeom g;
   g.data = t.data; g.n = t.n; g.h = t.h; g.w = t.w; g.c = t.c; g.halo = t.halo;
   g.wp = t_wp(t); g.hp = t_hp(t);
+  g.scale = t.scale;
   return g;
 }
+// the tensor's scale / its reciprocal (powers of two: exact)
+__device__ __forceinline__ float tscale(const TGeom& g) { return g.scale ? __ldg(g.scale) : 1.f; }
+__device__ __forceinline__ float tinv(const TGeom& g) { return g.scale ? 1.f / __ldg(g.scale) : 1.f; }
 // element offset of (n, y, x, c) with y, x in interior coordinates (may be negative into the halo)
 __device__ __forceinline__ long long toff(const TGeom& g, int n, int y, int x, int c) {
   return (((long long)n * g.hp + (y + g.halo)) * g.wp + (x + g.halo)) * g.c + c;
@@ -175,9 +180,10 @@ __global__ void pack_input_kernel(const float* __restrict__ src, TGeom d, int re
     x = reflect_idx(x, d.w);
     const long long plane = (long long)d.h * d.w;
     const float* s = src + (long long)n * 3 * plane + (long long)y * d.w + x;
-    v[0] = __ldg(s) * s0 + b0;
-    v[1] = __ldg(s + plane) * s1 + b1;
-    v[2] = __ldg(s + 2 * plane) * s2 + b2;
+    const float so = tscale(d);
+    v[0] = (__ldg(s) * s0 + b0) * so;
+    v[1] = (__ldg(s + plane) * s1 + b1) * so;
+    v[2] = (__ldg(s + 2 * plane) * s2 + b2) * so;
   }
   T* dp = static_cast<T*>(d.data) + i * d.c;
   Vec<T>::store(dp, v);
@@ -250,15 +256,18 @@ static void run_in_stats(const TGeom& s, double* stats, cudaStream_t st) {
   launch_strip_reduce<T, 2>(op, s.c, s.n, s.h, s.w, st);
 }
 
+// (mean, rstd) of the STORED values: with stored = s * true, mean_st = s * mean and rstd_st = 1 / sqrt(s^2 var + s^2 eps)
+// = rstd / s, so that (stored - mean_st) * rstd_st is the true normalised value.
 __global__ void in_finalize_kernel(const double* __restrict__ stats, float* __restrict__ mr, int total, double inv_npix,
-                                   float eps) {
+                                   float eps, const float* __restrict__ src_scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
+  const double s = src_scale ? (double)__ldg(src_scale) : 1.0;
   const double mean = stats[2 * i] * inv_npix;
   double var = stats[2 * i + 1] * inv_npix - mean * mean;  // biased variance (InstanceNorm2d)
   if (var < 0.0) var = 0.0;
   mr[2 * i] = (float)mean;
-  mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps * s * s));
 }
 
 // grid = (x-chunks of a row, rows, images): no per-thread divisions (cv is a power of two)
@@ -272,8 +281,9 @@ __global__ void in_apply_kernel(TGeom s, TGeom d, int dst_c_off, const float* __
   float v[Vec<T>::N];
   Vec<T>::load(static_cast<const T*>(s.data) + toff(s, n, y, x, c), v);
   const float* m = mr + ((long long)n * s.c + c) * 2;
+  const float so = tscale(d);
 #pragma unroll
-  for (int k = 0; k < Vec<T>::N; ++k) v[k] = (v[k] - m[2 * k]) * m[2 * k + 1];
+  for (int k = 0; k < Vec<T>::N; ++k) v[k] = (v[k] - m[2 * k]) * (m[2 * k + 1] * so);
   Vec<T>::store(static_cast<T*>(d.data) + toff(d, n, y, x, dst_c_off + c), v);
 }
 
@@ -298,9 +308,10 @@ __global__ void upsample2x_kernel(TGeom s, TGeom d, int dst_c_off, float sy, flo
   Vec<T>::load(base + toff(s, n, y0, x1, c), b);
   Vec<T>::load(base + toff(s, n, y1, x0, c), e);
   Vec<T>::load(base + toff(s, n, y1, x1, c), f);
+  const float rs = tscale(d) * tinv(s);  // re-scale from the source's to the destination's power-of-two scale
 #pragma unroll
   for (int k = 0; k < Vec<T>::N; ++k)
-    o[k] = (1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * e[k] + lx * f[k]);
+    o[k] = ((1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * e[k] + lx * f[k])) * rs;
   Vec<T>::store(static_cast<T*>(d.data) + toff(d, n, yo, xo, dst_c_off + c), o);
 }
 
@@ -420,7 +431,7 @@ static int instance_norm_impl(const uegan_tensor* src, const uegan_tensor* dst, 
     else run_in_stats<__half>(s, stats_ws, st);
   }
   float* mr = reinterpret_cast<float*>(stats_ws + 2 * nc);  // finalised (mean, rstd) live after the raw sums
-  in_finalize_kernel<<<nblocks(nc, 128), 128, 0, st>>>(stats_ws, mr, nc, 1.0 / (double)npix, eps);
+  in_finalize_kernel<<<nblocks(nc, 128), 128, 0, st>>>(stats_ws, mr, nc, 1.0 / (double)npix, eps, src->scale);
   const int vn = 16 / dtype_size(src->dtype);
   const int cv = s.c / vn;
   int lg = 0;
@@ -455,7 +466,7 @@ int uegan_instance_norm_stats(const uegan_tensor* src, float eps, double* stats_
     else run_in_stats<__half>(s, stats_ws, st);
   }
   float* mr = reinterpret_cast<float*>(stats_ws + 2 * nc);
-  in_finalize_kernel<<<nblocks(nc, 128), 128, 0, st>>>(stats_ws, mr, nc, 1.0 / (double)npix, eps);
+  in_finalize_kernel<<<nblocks(nc, 128), 128, 0, st>>>(stats_ws, mr, nc, 1.0 / (double)npix, eps, src->scale);
   *mean_rstd_out = mr;
   UEGAN_CUDA(cudaGetLastError());
   return 0;

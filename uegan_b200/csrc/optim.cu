@@ -150,6 +150,12 @@ int uegan_memset_zero(void* ptr, size_t bytes, void* stream) {
   return 0;
 }
 
+int uegan_capture_status(void* stream) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(static_cast<cudaStream_t>(stream), &st) != cudaSuccess) return -1;
+  return (int)st;  // 0 none, 1 active, 2 invalidated
+}
+
 int uegan_peer_sum_f64(double* out, const double* const* peers_host, int32_t world, int32_t count, void* stream) {
   UEGAN_CHECK(out && peers_host && world >= 1 && world <= kMaxPeers && count >= 1 && count <= 64,
               "peer_sum_f64: bad arguments (world %d, count %d)", world, count);

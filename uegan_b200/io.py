@@ -65,3 +65,53 @@ def enhance_u8(G, img_u8: torch.Tensor, out: Optional[torch.Tensor] = None) -> t
     pack_u8(img_u8, P["x0"], planes_out=x)
     y = G.forward_native(x, packed=True)
     return unpack_u8(y, out)
+
+
+class U8Pipeline:
+    """Double-buffered uint8 -> Generator -> uint8 inference from / to PINNED host memory: the H2D copy of batch i+1 and
+    the D2H copy of batch i-1 run on their own streams while batch i computes, so the end-to-end rate approaches the
+    resident rate (3 bytes per pixel cross PCIe each way instead of the 12 + 12 of fp32 NCHW staging).
+
+        pipe = U8Pipeline(G)                       # G: uegan_b200.models.Generator in eval mode
+        for src, dst in batches:                   # pinned uint8 (N, H, W, 3) tensors
+            pipe.submit(src, dst)
+        pipe.drain()                               # dst of every submitted batch is complete
+    """
+
+    def __init__(self, G, depth: int = 2):
+        self.G, self.depth = G, depth
+        self.slots, self.i = [], 0
+        self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def _slot(self, shape, device):
+        if len(self.slots) < self.depth:
+            self.slots.append(dict(inp=torch.empty(shape, dtype=torch.uint8, device=device),
+                                   out=torch.empty(shape, dtype=torch.uint8, device=device),
+                                   e_in=torch.cuda.Event(), e_comp=torch.cuda.Event(), e_out=torch.cuda.Event(), used=False))
+        return self.slots[self.i % self.depth]
+
+    @torch.no_grad()
+    def submit(self, src_host: torch.Tensor, dst_host: torch.Tensor):
+        assert src_host.is_pinned() and dst_host.is_pinned() and src_host.dtype == torch.uint8
+        main = torch.cuda.current_stream()
+        sl = self._slot(tuple(src_host.shape), main.device)
+        self.i += 1
+        with torch.cuda.stream(self.s_in):
+            if sl["used"]:
+                self.s_in.wait_event(sl["e_comp"])   # the slot's previous batch has been consumed by the pack kernel
+            sl["inp"].copy_(src_host, non_blocking=True)
+            sl["e_in"].record(self.s_in)
+        main.wait_event(sl["e_in"])
+        if sl["used"]:
+            main.wait_event(sl["e_out"])             # the slot's previous output has left for the host
+        enhance_u8(self.G, sl["inp"], out=sl["out"])
+        sl["e_comp"].record(main)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(sl["e_comp"])
+            dst_host.copy_(sl["out"], non_blocking=True)
+            sl["e_out"].record(self.s_out)
+        sl["used"] = True
+
+    def drain(self):
+        self.s_out.synchronize()
+        torch.cuda.current_stream().synchronize()

@@ -41,7 +41,8 @@ class NHWC:
 
     SLACK = 512
 
-    def __init__(self, n, h, w, c, halo=0, dtype=L.F32, device="cuda", zero=False):
+    def __init__(self, n, h, w, c, halo=0, dtype=L.F32, device="cuda", zero=False, scale=None):
+        """scale: optional 1-element fp32 CUDA tensor (a ScaleBook slot): stored values = scale * true values."""
         es = 4 if dtype == L.F32 else 2
         assert (c * es) % 16 == 0, "channel vector must be a multiple of 16 bytes"
         self.n, self.h, self.w, self.c, self.halo, self.dtype = n, h, w, c, halo, dtype
@@ -51,7 +52,8 @@ class NHWC:
         if not zero:
             self.buf[elems:].zero_()
         self.elems = elems
-        self.ct = L.Tensor(self.buf.data_ptr(), n, h, w, c, halo, dtype)
+        self.scale = scale
+        self.ct = L.Tensor(self.buf.data_ptr(), n, h, w, c, halo, dtype, scale.data_ptr() if scale is not None else None)
 
     def ref(self):
         return C.byref(self.ct)
@@ -62,25 +64,77 @@ class NHWC:
         assert self.halo == 0 and self.h > 2 * halo and self.w > 2 * halo
         v = object.__new__(NHWC)
         v.n, v.h, v.w, v.c, v.halo, v.dtype = self.n, self.h - 2 * halo, self.w - 2 * halo, self.c, halo, self.dtype
-        v.buf, v.elems = self.buf, self.elems
-        v.ct = L.Tensor(self.buf.data_ptr(), v.n, v.h, v.w, v.c, halo, self.dtype)
+        v.buf, v.elems, v.scale = self.buf, self.elems, self.scale
+        v.ct = L.Tensor(self.buf.data_ptr(), v.n, v.h, v.w, v.c, halo, self.dtype,
+                        self.scale.data_ptr() if self.scale is not None else None)
         return v
 
     def padded_view(self) -> torch.Tensor:
         return self.buf[: self.elems].view(self.n, self.h + 2 * self.halo, self.w + 2 * self.halo, self.c)
 
     def interior_nchw(self) -> torch.Tensor:
-        """Interior as a float32 NCHW torch tensor (test/debug readback; not on the hot path)."""
+        """Interior as a float32 NCHW torch tensor of TRUE values (test/debug readback; not on the hot path)."""
         v = self.padded_view()
         p = self.halo
         v = v[:, p:p + self.h, p:p + self.w, :]
-        return v.permute(0, 3, 1, 2).float().contiguous()
+        v = v.permute(0, 3, 1, 2).float().contiguous()
+        return v / self.scale if self.scale is not None else v
+
+
+class ScaleBook:
+    """Device-resident power-of-two scales (uegan_tensor.scale) of a set of tensors and the table uegan_scale_update walks.
+    `slot()` hands out 1-element views of one fp32 buffer (all 1.0 initially); `track()` registers the buffer whose stored
+    values a slot describes; `update()` is ONE launch that re-derives every tracked slot from a strided sample."""
+
+    TARGET = 1024.0      # 2^10: 64x below fp16's 65504 (samples underestimate the maximum; magnitudes drift between passes)
+    SAMPLES = 1 << 16
+
+    def __init__(self, device, capacity=512):
+        self.buf = torch.ones(capacity, dtype=torch.float32, device=device)
+        self.n = 0
+        self.entries = []
+        self.table = None
+
+    def slot(self) -> torch.Tensor:
+        assert self.n < self.buf.numel(), "ScaleBook capacity"
+        t = self.buf[self.n:self.n + 1]
+        self.n += 1
+        return t
+
+    def track(self, data_ptr: int, numel: int, dtype: int, slot: torch.Tensor, true_values: bool = False):
+        """true_values: the buffer holds unscaled values (fp32 master weights); the slot is the scale their packed copy gets."""
+        self.entries.append((int(data_ptr), int(numel), int(dtype), slot.data_ptr(), 1 if true_values else 0))
+        self.table = None
+
+    def track_nhwc(self, t: "NHWC"):
+        self.track(t.buf.data_ptr(), t.elems, t.dtype, t.scale)
+
+    def clear_tracked(self):
+        self.entries, self.table = [], None
+
+    def update(self):
+        if not self.entries:
+            return
+        if self.table is None:
+            arr = (L.ScaleEntry * len(self.entries))()
+            for i, (ptr, numel, dtype, sl, tv) in enumerate(self.entries):
+                arr[i].data, arr[i].numel, arr[i].dtype, arr[i].reserved, arr[i].scale = ptr, numel, dtype, tv, sl
+            raw = bytes(arr)
+            self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.buf.device)
+        L.check(L.load().uegan_scale_update(self.table.data_ptr(), len(self.entries), self.TARGET, self.SAMPLES, _stream()),
+                "scale_update")
+        _count(1, "scale_update")
+
+    def values(self) -> torch.Tensor:
+        return self.buf[:self.n].detach().cpu()
 
 
 def packed_weight(weight: torch.Tensor, cin_stored: int, dtype: int, cin_first: int = 0, cin: Optional[int] = None,
-                  transpose_flip: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  transpose_flip: bool = False, out: Optional[torch.Tensor] = None,
+                  w_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """nn.Conv2d.weight (OIHW fp32, CUDA) -> K-major packed operand of the implicit GEMM.  `out`: re-pack in place
-    (the operand buffers must keep their addresses across optimizer steps for CUDA-graph replay)."""
+    (the operand buffers must keep their addresses across optimizer steps for CUDA-graph replay).  w_scale: device scalar
+    the values are multiplied by (fp16 operands of weights whose magnitude is far from 1; pass it to the conv as well)."""
     lib = L.load()
     w = weight.detach()
     assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
@@ -94,8 +148,13 @@ def packed_weight(weight: torch.Tensor, cin_stored: int, dtype: int, cin_first: 
     nbytes = lib.uegan_packed_weight_bytes(cout, cin_stored, k, dtype)
     buf = out if out is not None else torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
     assert buf.numel() >= nbytes
-    L.check(lib.uegan_pack_conv_weight(w.data_ptr(), buf.data_ptr(), cout, i_total, cin_first, cin, cin_stored, k,
-                                       dtype, int(transpose_flip), _stream()), "pack_conv_weight")
+    if w_scale is not None:
+        assert not transpose_flip
+        L.check(lib.uegan_pack_conv_weight_scaled(w.data_ptr(), buf.data_ptr(), cout, i_total, cin_first, cin, cin_stored, k,
+                                                  dtype, w_scale.data_ptr(), _stream()), "pack_conv_weight_scaled")
+    else:
+        L.check(lib.uegan_pack_conv_weight(w.data_ptr(), buf.data_ptr(), cout, i_total, cin_first, cin, cin_stored, k,
+                                           dtype, int(transpose_flip), _stream()), "pack_conv_weight")
     _count(1, "pack_weight")
     return buf
 
@@ -104,7 +163,7 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
                y_c_off: int = 0, bias: Optional[torch.Tensor] = None, alpha: Optional[torch.Tensor] = None,
                act: int = L.ACT_NONE, mul: Optional[NHWC] = None, out_nchw: Optional[torch.Tensor] = None,
                residual_nchw: Optional[torch.Tensor] = None, in_stats: Optional[torch.Tensor] = None,
-               aux_nchw: Optional[torch.Tensor] = None):
+               aux_nchw: Optional[torch.Tensor] = None, w_scale: Optional[torch.Tensor] = None):
     lib = L.load()
     d = L.ConvDesc()
     d.x = x.ct
@@ -112,6 +171,7 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
         d.y = y.ct
     d.y_c_off, d.cout, d.k, d.stride, d.pad, d.act = y_c_off, cout, k, stride, pad, act
     d.w_packed = w_packed.data_ptr()
+    d.w_scale = w_scale.data_ptr() if w_scale is not None else None
     d.bias = bias.data_ptr() if bias is not None else None
     d.alpha = alpha.data_ptr() if alpha is not None else None
     d.mul = C.pointer(mul.ct) if mul is not None else None
@@ -137,8 +197,9 @@ def rowsum_supported(cout: int, cin_stored: int, k: int, dtype: int) -> bool:
     return bool(L.load().uegan_conv2d_rowsum_supported(cout, cin_stored, k, dtype))
 
 
-def packed_weight_rowsum(weight: torch.Tensor, cin_stored: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Operand of the row-sum kernel (csrc/conv_rowsum.cu): rows (s, o), columns (r, c), tf32."""
+def packed_weight_rowsum(weight: torch.Tensor, cin_stored: int, out: Optional[torch.Tensor] = None, dtype: int = L.F32,
+                         w_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Operand of the row-sum kernel (csrc/conv_rowsum.cu): rows (s, o), columns (r, c); tf32, or fp16 times *w_scale."""
     lib = L.load()
     w = weight.detach()
     assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
@@ -146,24 +207,31 @@ def packed_weight_rowsum(weight: torch.Tensor, cin_stored: int, out: Optional[to
     nbytes = lib.uegan_packed_weight_rowsum_bytes(o, cin_stored, k)
     buf = out if out is not None else torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
     assert buf.numel() >= nbytes
-    L.check(lib.uegan_pack_conv_weight_rowsum(w.data_ptr(), buf.data_ptr(), o, i_total, 0, i_total, cin_stored, k,
-                                              _stream()), "pack_conv_weight_rowsum")
+    if dtype != L.F32 or w_scale is not None:
+        L.check(lib.uegan_pack_conv_weight_rowsum_scaled(w.data_ptr(), buf.data_ptr(), o, i_total, 0, i_total, cin_stored, k,
+                                                         dtype, w_scale.data_ptr() if w_scale is not None else None,
+                                                         _stream()), "pack_conv_weight_rowsum_scaled")
+    else:
+        L.check(lib.uegan_pack_conv_weight_rowsum(w.data_ptr(), buf.data_ptr(), o, i_total, 0, i_total, cin_stored, k,
+                                                  _stream()), "pack_conv_weight_rowsum")
     _count(1, "pack_weight_rowsum")
     return buf
 
 
 def conv_planar(x: NHWC, weight: torch.Tensor, cache, key, k: int, pad: int, bias, alpha, act: int,
                 out_nchw: torch.Tensor, residual_nchw: Optional[torch.Tensor] = None,
-                aux_nchw: Optional[torch.Tensor] = None):
+                aux_nchw: Optional[torch.Tensor] = None, w_scale: Optional[torch.Tensor] = None):
     """Stride-1 conv with a tiny output-channel count written as fp32 NCHW planes (G's last conv, D's heads): the
     row-sum kernel when the shape qualifies, else the generic implicit GEMM."""
     cout = weight.shape[0]
     if rowsum_supported(cout, x.c, k, x.dtype):
-        wp = cache.get((key, "rowsum"), weight, lambda out=None: packed_weight_rowsum(weight, x.c, out=out))
+        wp = cache.get((key, "rowsum", x.dtype), weight,
+                       lambda out=None: packed_weight_rowsum(weight, x.c, out=out, dtype=x.dtype, w_scale=w_scale))
         d = L.ConvDesc()
         d.x = x.ct
         d.cout, d.k, d.stride, d.pad, d.act = cout, k, 1, pad, act
         d.w_packed = wp.data_ptr()
+        d.w_scale = w_scale.data_ptr() if w_scale is not None else None
         d.bias = bias.data_ptr() if bias is not None else None
         d.alpha = alpha.data_ptr() if alpha is not None else None
         d.out_nchw = out_nchw.data_ptr()
@@ -180,8 +248,9 @@ def conv_planar(x: NHWC, weight: torch.Tensor, cache, key, k: int, pad: int, bia
             ev.append((s0, s1, 2.0 * x.n * ho * wo * cout * k * k * x.c, x, cout, k, 1, "fprop", x.dtype))
         _count(1, f"fprop_rowsum ->{cout} k{k}", x)
         return
-    wp = cache.get(key, weight, lambda out=None: packed_weight(weight, x.c, x.dtype, out=out))
-    conv_fprop(x, wp, cout, k, 1, pad, None, 0, bias, alpha, act, None, out_nchw, residual_nchw, aux_nchw=aux_nchw)
+    wp = cache.get((key, x.dtype), weight, lambda out=None: packed_weight(weight, x.c, x.dtype, out=out, w_scale=w_scale))
+    conv_fprop(x, wp, cout, k, 1, pad, None, 0, bias, alpha, act, None, out_nchw, residual_nchw, aux_nchw=aux_nchw,
+               w_scale=w_scale)
 
 
 def conv3x3_rowsum_nhwc(x: NHWC, weight: torch.Tensor, cache, key, pad: int, y: NHWC, y_c_off: int = 0, bias=None,
@@ -392,7 +461,8 @@ def msrec_loss(pred: torch.Tensor, gt: torch.Tensor, rec_type: int, scales: int,
 # backward
 # ------------------------------------------------------------------------------------------------
 def packed_weight_dgrad(weight: torch.Tensor, cout_stored: int, dtype: int, stride: int = 1, pi: int = 0, pj: int = 0,
-                        cin_first: int = 0, cin: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                        cin_first: int = 0, cin: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                        w_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Operand of the data-gradient GEMM of a conv with `weight` (OIHW): see uegan_pack_conv_weight_dgrad."""
     lib = L.load()
     w = weight.detach()
@@ -404,21 +474,28 @@ def packed_weight_dgrad(weight: torch.Tensor, cout_stored: int, dtype: int, stri
     nbytes = lib.uegan_packed_weight_bytes(cin, cout_stored, kq, dtype)
     buf = out if out is not None else torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
     assert buf.numel() >= nbytes
-    L.check(lib.uegan_pack_conv_weight_dgrad(w.data_ptr(), buf.data_ptr(), o, i_total, cin_first, cin, cout_stored, k,
-                                             stride, pi, pj, dtype, _stream()), "pack_conv_weight_dgrad")
+    if w_scale is not None:
+        L.check(lib.uegan_pack_conv_weight_dgrad_scaled(w.data_ptr(), buf.data_ptr(), o, i_total, cin_first, cin,
+                                                        cout_stored, k, stride, pi, pj, dtype, w_scale.data_ptr(),
+                                                        _stream()), "pack_conv_weight_dgrad_scaled")
+    else:
+        L.check(lib.uegan_pack_conv_weight_dgrad(w.data_ptr(), buf.data_ptr(), o, i_total, cin_first, cin, cout_stored, k,
+                                                 stride, pi, pj, dtype, _stream()), "pack_conv_weight_dgrad")
     _count(1, "pack_weight_dgrad")
     return buf
 
 
 def conv_generic(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, pad: int, y: NHWC, y_c_off: int = 0,
                  bias=None, alpha=None, act: int = L.ACT_NONE, mask: Optional[NHWC] = None, mask_act: int = L.ACT_NONE,
-                 y_mul: int = 1, y_off_h: int = 0, y_off_w: int = 0, real_taps: Optional[int] = None):
+                 y_mul: int = 1, y_off_h: int = 0, y_off_w: int = 0, real_taps: Optional[int] = None,
+                 w_scale: Optional[torch.Tensor] = None):
     """conv_fprop with the dgrad-only options (activation-derivative mask, strided output view)."""
     lib = L.load()
     d = L.ConvDesc()
     d.x, d.y = x.ct, y.ct
     d.y_c_off, d.cout, d.k, d.stride, d.pad, d.act = y_c_off, cout, k, stride, pad, act
     d.w_packed = w_packed.data_ptr()
+    d.w_scale = w_scale.data_ptr() if w_scale is not None else None
     d.bias = bias.data_ptr() if bias is not None else None
     d.alpha = alpha.data_ptr() if alpha is not None else None
     d.mask = C.pointer(mask.ct) if mask is not None else None
@@ -439,7 +516,8 @@ def conv_generic(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int
 
 
 def conv_dgrad(dz: NHWC, weight: torch.Tensor, k: int, stride: int, dxp: NHWC, cache=None, key=None, alpha=None,
-               cin_first: int = 0, cin: Optional[int] = None, mask: Optional[NHWC] = None, mask_act: int = L.ACT_NONE):
+               cin_first: int = 0, cin: Optional[int] = None, mask: Optional[NHWC] = None, mask_act: int = L.ACT_NONE,
+               w_scale: Optional[torch.Tensor] = None):
     """Data gradient of y = conv(xpad, weight, stride) w.r.t. the PADDED input: dxp (extent of xpad, halo 0).
     dz: output gradient with a zero halo of ceil(k/stride) - 1.  stride 2 = four parity-class launches."""
     kq = (k + stride - 1) // stride
@@ -449,11 +527,12 @@ def conv_dgrad(dz: NHWC, weight: torch.Tensor, k: int, stride: int, dxp: NHWC, c
     assert dxp.c >= cout_arg
     for pi in range(stride):
         for pj in range(stride):
-            fn = lambda out=None: packed_weight_dgrad(weight, dz.c, dz.dtype, stride, pi, pj, cin_first, cin, out=out)
-            wp = cache.get((key, "dg", pi, pj, dz.dtype), weight, fn) if cache is not None else fn()
+            fn = lambda out=None: packed_weight_dgrad(weight, dz.c, dz.dtype, stride, pi, pj, cin_first, cin, out=out,
+                                                      w_scale=w_scale)
+            wp = cache.get((key, "dg", pi, pj, dz.dtype, dz.c), weight, fn) if cache is not None else fn()
             nr = len(range(pi, k, stride)) * len(range(pj, k, stride))  # taps of the forward kernel in this class
             conv_generic(dz, wp, cout_arg, kq, 1, kq - 1, dxp, 0, None, alpha, L.ACT_NONE, mask, mask_act,
-                         y_mul=stride, y_off_h=pi, y_off_w=pj, real_taps=nr)
+                         y_mul=stride, y_off_h=pi, y_off_w=pj, real_taps=nr, w_scale=w_scale)
 
 
 class _WgradWs:
@@ -490,7 +569,7 @@ def conv_wgrad(x: NHWC, dz: NHWC, dw: torch.Tensor, k: int, stride: int, pad: in
                                         *_WgradWs.get(dw.device), _stream()), "conv2d_wgrad")
     if ev is not None:
         s1.record()
-        real_cin = 3 if x.c == 4 else cin_n
+        real_cin = 3 if x.c * (4 if x.dtype == L.F32 else 2) == 16 else cin_n
         ev.append((s0, s1, 2.0 * dz.n * dz.h * dz.w * cout * real_cin * k * k, x, cout, k, stride, "wgrad", x.dtype))
     _count(2 if _WgradWs.buf else 1, f"wgrad cout{cout} cin{cin_n} k{k}s{stride}", x, dz)
 

@@ -102,7 +102,56 @@ class _ParamCache:
         return hit[1]
 
 
-class Generator(nn.Module):
+class _ScaledNet:
+    """Operand precision of a network's convolutions and, for fp16, the device-resident power-of-two scales of its master
+    weights.  precision = "tf32": fp32 storage, kind::tf32 MMAs (the reference's own default GPU arithmetic).
+    precision = "f16": fp16 storage / kind::f16 MMAs with per-tensor scales maintained on the device (uegan_scale_update):
+    the same 11 significant bits at twice the tensor rate and half the bytes per pass."""
+
+    def _init_precision(self):
+        self.precision = __import__("os").environ.get("UEGAN_GD_DTYPE", "tf32")
+        self._wbook = None  # ScaleBook of the master weights (f16 mode)
+
+    @property
+    def _dtype(self):
+        if self.precision not in ("tf32", "f16"):
+            raise ValueError("precision must be 'tf32' or 'f16'")
+        return L.F16 if self.precision == "f16" else L.F32
+
+    def _wscale(self, name, conv):
+        """Device scalar the packed fp16 weight of `conv` is multiplied by (None in tf32 mode)."""
+        if self._dtype == L.F32:
+            return None
+        w = conv if isinstance(conv, torch.Tensor) else conv.weight
+        wb = self._wbook
+        if wb is None or wb.buf.device != w.device:
+            wb = self._wbook = K.ScaleBook(w.device)
+            wb.items = {}
+        it = wb.items.get(name)
+        if it is None or it[0] is not w:
+            it = wb.items[name] = (w, it[1] if it is not None else wb.slot())
+        return it[1]
+
+    def _update_weight_scales(self):
+        """One launch: every weight's scale from its CURRENT fp32 master values (exact, not delayed); skipped while the
+        parameters are unchanged (inference).  The table is rebuilt when a parameter moved (FlatBucket, .to())."""
+        wb = self._wbook
+        if wb is None or not wb.items:
+            return
+        ptrs = tuple(w.data_ptr() for w, _ in wb.items.values())
+        if getattr(wb, "ptrs", None) != ptrs:
+            wb.clear_tracked()
+            for w, sl in wb.items.values():
+                wb.track(w.data_ptr(), w.numel(), L.F32, sl, true_values=True)
+            wb.ptrs, wb.tag = ptrs, None
+        tag = tuple(w._version for w, _ in wb.items.values()) + (self._wcache.epoch,)
+        if wb.tag != tag:
+            wb.update()
+            wb.tag = tag
+
+
+
+class Generator(nn.Module, _ScaledNet):
     """Generator network (reference: models.py:10-74).  forward: (B,3,H,W) fp32 in [-1,1], H,W % 16 == 0."""
 
     def __init__(self, conv_dim, norm_fun, act_fun, use_sn):
@@ -139,20 +188,34 @@ class Generator(nn.Module):
         self.ga1 = _GAMHolder(d)
         self._plans = {}
         self._wcache = _ParamCache()
+        self._init_precision()
 
     # ---------------------------------------------------------------- native forward
     def _w(self, name, conv, cin_stored, cin_first=0, cin=None):
-        return self._wcache.get(name, conv.weight,
-                                lambda out=None: K.packed_weight(conv.weight, cin_stored, L.F32, cin_first, cin, out=out))
+        dt = self._dtype
+        ws = self._wscale(name, conv)
+        return self._wcache.get((name, dt), conv.weight,
+                                lambda out=None: K.packed_weight(conv.weight, cin_stored, dt, cin_first, cin, out=out,
+                                                                 w_scale=ws))
 
     def _plan(self, b, h, w, device):
-        key = (b, h, w, str(device))
+        key = (b, h, w, str(device), self.precision)
         pl = self._plans.get(key)
         if pl is None:
             d = self.conv_dim
-            T = lambda hh, ww, c, halo=0, zero=False: K.NHWC(b, hh, ww, c, halo, L.F32, device, zero)
+            dt = self._dtype
+            book = K.ScaleBook(device) if dt != L.F32 else None
+
+            def T(hh, ww, c, halo=0, zero=False, scaled=True):
+                if book is None:
+                    return K.NHWC(b, hh, ww, c, halo, L.F32, device, zero)
+                t = K.NHWC(b, hh, ww, c, halo, dt, device, True, scale=book.slot() if scaled else None)
+                if scaled:
+                    book.track_nhwc(t)
+                return t
             pl = dict(
-                x0=T(h, w, 4, 3, zero=True),
+                book=book,
+                x0=T(h, w, 4 if dt == L.F32 else 8, 3, zero=True, scaled=False),
                 x1=T(h, w, d, 1), x2=T(h // 2, w // 2, 2 * d, 1), x3=T(h // 4, w // 4, 4 * d, 1),
                 x4=T(h // 8, w // 8, 8 * d, 1), x5=T(h // 16, w // 16, 16 * d),
                 z5=T(h // 16, w // 16, 16 * d), x5n=T(h // 16, w // 16, 16 * d),
@@ -187,8 +250,36 @@ class Generator(nn.Module):
         if self._act is None:
             raise NotImplementedError("activation function [%s] has no sm_100a epilogue" % self.act_fun)
         x = x.contiguous().float()
-        d, act, P = self.conv_dim, self._act, self._plan(b, h, w, x.device)
+        P = self._plan(b, h, w, x.device)
+        book = P["book"]
+        if book is not None and not P.get("calibrated"):
+            # fp16 storage: settle the per-tensor scales on this batch (each pass fixes at least the next layer; the
+            # activations of the reference's orthogonal(0.02) init need scales up to 2^40).  One-off per shape.
+            prev = None
+            for it in range(48):
+                self._forward_pass(x, P, packed and it == 0)
+                book.update()
+                cur = book.values()
+                if prev is not None and torch.equal(cur, prev):
+                    break
+                prev = cur
+            P["calibrated"] = True
+            packed = True  # x0 is in place
+        elif book is not None:
+            book.update()  # delayed scaling: this pass uses the magnitudes the previous pass stored
+        out = self._forward_pass(x, P, packed)
+        if keep is not None:
+            keep.update(P)
+        return out
+
+    def _forward_pass(self, x, P, packed):
+        d, act = self.conv_dim, self._act
         c = lambda holder: holder.conv
+        if self._dtype != L.F32:
+            # register every weight's scale slot, then ONE launch refreshes them all from the fp32 masters
+            for name, holder in self._conv_table():
+                self._wscale(name, holder)
+            self._update_weight_scales()
 
         def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE, off=0, mul=None, bias=True):
             cv = c(holder)
@@ -196,7 +287,7 @@ class Generator(nn.Module):
                                                                  cv.bias if bias else None, act_, mul):
                 return  # experimental opt-in path (UEGAN_ROWSUM_NHWC=1)
             K.conv_fprop(src, self._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, off,
-                         cv.bias if bias else None, None, act_, mul)
+                         cv.bias if bias else None, None, act_, mul, w_scale=self._wscale(name, cv))
 
         if not packed:
             K.pack_input(x, P["x0"], L.PAD_REFLECT)
@@ -210,12 +301,15 @@ class Generator(nn.Module):
             # GAM(x) == IN(conv1x1(x, fuse.weight[:, :C])): the attention branch and fuse bias are constant per
             # (n, c) and cancel in the InstanceNorm that follows (models.py:230-237; SURVEY.md 8a rewrite 1).
             fuse = ga.fuse[0]
-            wp = self._wcache.get(name, fuse.weight, lambda out=None: K.packed_weight(fuse.weight, src.c, L.F32, 0, ch, out=out))
-            if K.fused_stats_ok(src.h, src.w, ch):  # statistics ride in the conv epilogue
+            dt = self._dtype
+            ws_ = self._wscale(name, fuse)
+            wp = self._wcache.get((name, dt), fuse.weight,
+                                  lambda out=None: K.packed_weight(fuse.weight, src.c, dt, 0, ch, out=out, w_scale=ws_))
+            if dt == L.F32 and K.fused_stats_ok(src.h, src.w, ch):  # statistics ride in the conv epilogue
                 K.conv_fprop(src, wp, ch, 1, 1, 0, z, in_stats=P["stats"])
                 K.instance_norm_apply(z, dst, off, P["stats"])
             else:
-                K.conv_fprop(src, wp, ch, 1, 1, 0, z)
+                K.conv_fprop(src, wp, ch, 1, 1, 0, z, w_scale=ws_)
                 K.instance_norm(z, dst, off, P["stats"])
 
         gam("ga5", self.ga5, P["x5"], 16 * d, P["z5"], P["x5n"], 0)
@@ -236,13 +330,21 @@ class Generator(nn.Module):
         conv(P["y4m"], "dec5.0", self.dec5[0], d, 3, 1, P["t"]); K.halo_fill(P["t"])
         out = torch.empty_like(x)
         cv = c(self.dec5[1])
-        K.conv_planar(P["t"], cv.weight, self._wcache, "dec5.1", 7, 3, cv.bias, None, L.ACT_TANH, out, x)
-        if keep is not None:
-            keep.update(P)
+        K.conv_planar(P["t"], cv.weight, self._wcache, "dec5.1", 7, 3, cv.bias, None, L.ACT_TANH, out, x,
+                      w_scale=self._wscale("dec5.1", cv))
         return out
 
+    def _conv_table(self):
+        """(cache name, module holding .weight) of every convolution the native plan runs."""
+        t = [("enc1", self.enc1.conv), ("enc2", self.enc2.conv), ("enc3", self.enc3.conv), ("enc4", self.enc4.conv),
+             ("enc5", self.enc5.conv), ("dec1", self.dec1.conv), ("dec2", self.dec2.conv), ("dec3", self.dec3.conv),
+             ("dec4", self.dec4.conv), ("dec5.0", self.dec5[0].conv), ("dec5.1", self.dec5[1].conv)]
+        t += [(f"upsample{i}", getattr(self, f"upsample{i}")[1].conv) for i in range(1, 5)]
+        t += [(f"ga{i}", getattr(self, f"ga{i}").fuse[0]) for i in range(1, 6)]
+        return t
 
-class Discriminator(nn.Module):
+
+class Discriminator(nn.Module, _ScaledNet):
     """Multi-scale PatchGAN discriminator (reference: models.py:104-182): five spectrally-normalised strided convs,
     each followed by a Cout=1 prediction head; forward returns the list of five (B,1,H/2^k,W/2^k) maps."""
 
@@ -272,6 +374,7 @@ class Discriminator(nn.Module):
             setattr(self, f"d{i}_pred", nn.Sequential(head))
         self._plans = {}
         self._wcache = _ParamCache()
+        self._init_precision()
 
     def _conv(self, i):
         return getattr(self, f"d{i}")[0][1]
@@ -283,18 +386,39 @@ class Discriminator(nn.Module):
         c = self._conv(i)
         return c.weight_orig if self.use_sn else c.weight
 
+    def _register_weight_scales(self):
+        if self._dtype != L.F32:
+            for i in range(1, 6):
+                self._wscale(f"d{i}", self._weight(i))
+                self._wscale(f"p{i}", self._head(i).weight)
+            self._update_weight_scales()
+
+    def _act_buffers(self, b, h, w, device):
+        """x0 + the five activation tensors (+ their ScaleBook in f16 mode) of one forward pass."""
+        d = self.conv_dim
+        dt = self._dtype
+        chans = [d, 2 * d, 4 * d, 8 * d, 16 * d]
+        book = K.ScaleBook(device) if dt != L.F32 else None
+        out = dict(book=book, dtype=dt, x0=K.NHWC(b, h, w, 4 if dt == L.F32 else 8, 3, dt, device, zero=True), ds=[])
+        hh, ww = h, w
+        for i in range(5):
+            hh, ww = (hh + 1) // 2, (ww + 1) // 2
+            halo = 3 if i < 3 else 2
+            if book is None:
+                t = K.NHWC(b, hh, ww, chans[i], halo, L.F32, device)
+            else:
+                t = K.NHWC(b, hh, ww, chans[i], halo, dt, device, True, scale=book.slot())
+                book.track_nhwc(t)
+            out["ds"].append(t)
+        return out
+
     def _plan(self, b, h, w, device):
-        key = (b, h, w, str(device))
+        key = (b, h, w, str(device), self.precision)
         pl = self._plans.get(key)
         if pl is None:
-            d = self.conv_dim
-            chans = [d, 2 * d, 4 * d, 8 * d, 16 * d]
-            pl = dict(x0=K.NHWC(b, h, w, 4, 3, L.F32, device, zero=True), ds=[], sig=[], ws=[])
-            hh, ww = h, w
+            pl = self._act_buffers(b, h, w, device)
+            pl.update(sig=[], ws=[])
             for i in range(5):
-                hh, ww = (hh + 1) // 2, (ww + 1) // 2
-                halo = 3 if i < 3 else 2
-                pl["ds"].append(K.NHWC(b, hh, ww, chans[i], halo, L.F32, device))
                 wgt = self._weight(i + 1)
                 pl["sig"].append(torch.ones(2, dtype=torch.float32, device=device))
                 pl["ws"].append(torch.empty(wgt.shape[0] + wgt.numel() // wgt.shape[0] + 8, dtype=torch.float32,
@@ -320,6 +444,33 @@ class Discriminator(nn.Module):
             raise NotImplementedError("activation function [%s] has no sm_100a epilogue" % self.act_fun)
         x = x.contiguous().float()
         P = self._plan(b, h, w, x.device)
+        book = P["book"]
+        if book is not None and not P.get("calibrated"):
+            # settle the per-tensor scales (see Generator.forward_native); eval-mode passes: the spectral-norm buffers
+            # must not advance during calibration
+            P["calibrated"] = True
+            was = self.training
+            self.training = False
+            prev = None
+            for _ in range(48):
+                self._forward_pass(x, P)
+                book.update()
+                cur = book.values()
+                if prev is not None and torch.equal(cur, prev):
+                    break
+                prev = cur
+            self.training = was
+        elif book is not None:
+            book.update()
+        preds = self._forward_pass(x, P)
+        if keep is not None:
+            keep.update(P)
+        return preds
+
+    def _forward_pass(self, x, P):
+        b = x.shape[0]
+        self._register_weight_scales()
+        dt = self._dtype
         K.pack_input(x, P["x0"], L.PAD_REFLECT)
         src, preds = P["x0"], []
         for i, (k, pad) in enumerate(self._SPEC, start=1):
@@ -330,13 +481,14 @@ class Discriminator(nn.Module):
                 K.spectral_sigma(wgt, conv.weight_u, conv.weight_v, self.training, P["sig"][i - 1], P["ws"][i - 1])
                 alpha = P["sig"][i - 1][1:2]
             dst = P["ds"][i - 1]
-            wp = self._wcache.get(f"d{i}", wgt, lambda out=None: K.packed_weight(wgt, src.c, L.F32, out=out))
-            K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, self._act)
+            wsc = self._wscale(f"d{i}", wgt)
+            wp = self._wcache.get((f"d{i}", dt), wgt,
+                                  lambda out=None: K.packed_weight(wgt, src.c, dt, out=out, w_scale=wsc))
+            K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, self._act, w_scale=wsc)
             K.halo_fill(dst)
             pred = torch.empty(b, 1, dst.h, dst.w, dtype=torch.float32, device=x.device)
-            K.conv_planar(dst, head.weight, self._wcache, f"p{i}", k, pad, None, None, self._head_act, pred)
+            K.conv_planar(dst, head.weight, self._wcache, f"p{i}", k, pad, None, None, self._head_act, pred,
+                          w_scale=self._wscale(f"p{i}", head.weight))
             preds.append(pred)
             src = dst
-        if keep is not None:
-            keep.update(P)
         return preds
