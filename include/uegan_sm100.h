@@ -152,17 +152,6 @@ int uegan_pack_conv_weight_rowsum_scaled(const float* w_oihw, void* w_packed, in
                                          const float* w_scale_dev, void* stream);
 int uegan_conv2d_fprop_rowsum(const uegan_conv_desc* desc, void* stream);
 
-/* EXPERIMENTAL, opt-in (environment UEGAN_ROWSUM_NHWC=1; otherwise ..._supported() returns 0 and nothing below is used):
- * the row-sum formulation for k3 stride-1 convolutions with cout = 32 / 64 and an NHWC output (G's dec4 / dec5.0,
- * models.py:31,33): N = 3*cout GEMM columns, the three horizontal taps summed in the epilogue.  Written after round 1's GPU
- * budget was spent: compiles, not yet validated on hardware.  desc: x, y (+ y_c_off), cout, k = 3, stride 1,
- * pad, act (none / LReLU / ReLU), bias, alpha, mul; w_packed from uegan_pack_conv_weight_rowsum_nhwc. */
-int uegan_conv2d_rowsum_nhwc_supported(int32_t cout, int32_t cin_stored, int32_t k, int32_t dtype);
-size_t uegan_packed_weight_rowsum_nhwc_bytes(int32_t cout, int32_t cin_stored);
-int uegan_pack_conv_weight_rowsum_nhwc(const float* w_oihw, void* w_packed, int32_t cout, int32_t cin_total,
-                                       int32_t cin_first, int32_t cin, int32_t cin_stored, void* stream);
-int uegan_conv2d_fprop_rowsum_nhwc(const uegan_conv_desc* desc, void* stream);
-
 /* NCHW fp32 image batch -> NHWC tensor with halo (pad_mode) and per-channel affine  v = x*scale[c] + shift[c]
  * (scale/shift are HOST arrays of 3 floats or NULL).  Replaces the implicit layout of models.py:47 inputs, and
  * (x+1)/2 -> (x-mean)/std of trainer.py:108 + losses.py:26-27 for the VGG tower.  Channels >= 3 are zero. */

@@ -79,13 +79,11 @@ def test_product_never_imports_oracle():
 
 def test_shape_policy_entry_points_without_gpu(monkeypatch):
     """Host-only policy functions of the C ABI (no CUDA calls): which convolutions take the row-sum kernels.  The
-    experimental NHWC variant must stay OFF unless UEGAN_ROWSUM_NHWC=1, and the Python hook in front of every 3x3
-    stride-1 Generator conv must fall through without touching CUDA."""
+    deepest head fits in fp16 only."""
     import types
     from uegan_b200 import _lib as L
     from uegan_b200 import kernels as K
     lib = L.load()
-    monkeypatch.delenv("UEGAN_ROWSUM_NHWC", raising=False)
     monkeypatch.delenv("UEGAN_NO_ROWSUM", raising=False)
     # tiny-Cout row-sum (validated on B200): G's last conv and D's heads qualify, the deepest head's weights do not fit
     assert lib.uegan_conv2d_rowsum_supported(3, 32, 7, L.F32) == 1
@@ -96,17 +94,6 @@ def test_shape_policy_entry_points_without_gpu(monkeypatch):
     assert lib.uegan_conv2d_rowsum_supported(32, 32, 3, L.F32) == 0
     monkeypatch.setenv("UEGAN_NO_ROWSUM", "1")
     assert lib.uegan_conv2d_rowsum_supported(3, 32, 7, L.F32) == 0
-    # experimental NHWC variant: off by default
-    assert lib.uegan_conv2d_rowsum_nhwc_supported(32, 64, 3, L.F32) == 0
-    fake_x = types.SimpleNamespace(c=64, dtype=L.F32)
-    w = torch.zeros(32, 64, 3, 3)
-    assert K.conv3x3_rowsum_nhwc(fake_x, w, None, "dec4", 1, None) is False  # returns before any CUDA work
-    monkeypatch.setenv("UEGAN_ROWSUM_NHWC", "1")
-    assert lib.uegan_conv2d_rowsum_nhwc_supported(32, 64, 3, L.F32) == 1   # dec4
-    assert lib.uegan_conv2d_rowsum_nhwc_supported(32, 32, 3, L.F32) == 1   # dec5.0
-    assert lib.uegan_conv2d_rowsum_nhwc_supported(64, 128, 3, L.F32) == 0  # dec3: weights do not fit
-    assert lib.uegan_conv2d_rowsum_nhwc_supported(32, 64, 7, L.F32) == 0
-    assert lib.uegan_packed_weight_rowsum_nhwc_bytes(32, 64) == 3 * 32 * 3 * 64 * 4
     assert lib.uegan_packed_weight_rowsum_bytes(3, 32, 7) == 32 * 7 * 64 * 4  # sized for fp32 rows or fp16 rows padded to 64 channels
     # statistics policy (kernels.fused_stats_ok): separate pass by default
     monkeypatch.delenv("UEGAN_FUSED_STATS", raising=False)

@@ -23,6 +23,7 @@ def build_generator(regime, conv_dim=32):
     from uegan_b200.models import Generator
     G = Generator(conv_dim, "none", "LeakyReLU", False)
     G.load_state_dict(O.make_generator_params(conv_dim, 0, regime), strict=True)
+    G.precision = "tf32"  # this file pins the tf32 path; tests/test_gpu_generator_f16.py the fp16 default
     return G.cuda().eval()
 
 

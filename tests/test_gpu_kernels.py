@@ -314,31 +314,40 @@ def test_conv_fused_instance_norm_stats(K, case):
     assert relerr(dst.interior_nchw(), ref) < (2e-3 if dtype != L.F32 else 1e-3)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("UEGAN_EXPERIMENTAL") != "1",
-                    reason="experimental kernel, not validated on hardware yet (DESIGN.md 7a): run with UEGAN_EXPERIMENTAL=1")
-@pytest.mark.parametrize("case", [(2, 64, 24, 40, 32, True), (1, 32, 37, 61, 32, False), (2, 32, 16, 32, 64, False)])
-def test_conv_rowsum_nhwc_experimental(K, case, monkeypatch):
-    """csrc/conv_rowsum_nhwc.cu (opt-in): k3 stride-1, cout 32 / 64, NHWC output with bias + LeakyReLU (+ mul)."""
+@pytest.mark.parametrize("case", [
+    # (n, cin, h, w, cout, k)
+    (2, 32, 24, 40, 3, 7),      # G's last conv: 32 stored channels = half of a 64-channel fp16 chunk (zero-filled)
+    (2, 64, 16, 32, 1, 7),
+    (2, 256, 12, 36, 1, 5),
+    (2, 256, 8, 8, 1, 5),       # the p4 head at 128x128 input
+    (2, 512, 16, 16, 1, 5),     # the deepest head (fits in fp16 only): 8 chunks, 8-row tiles
+    (2, 512, 4, 4, 1, 5),       # ... at 128x128 input: image smaller than one tile
+])
+def test_conv_rowsum_f16(K, case):
+    """fp16 row-sum kernel with scaled operands (x stored = 2^a x, packed w = 2^b w) vs fp64 conv2d on fp16-representable
+    operands: the planar output is the TRUE value."""
     from uegan_b200 import _lib as L
-    monkeypatch.setenv("UEGAN_ROWSUM_NHWC", "1")
-    n, cin, h, w, cout, use_mul = case
-    g = torch.Generator(device="cuda").manual_seed(300 + cin + cout)
-    x = tf32(torch.randn(n, cin, h, w, device="cuda", generator=g))
-    wgt = tf32(torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / math.sqrt(cin * 9))
+    n, cin, h, w, cout, k = case
+    g = torch.Generator(device="cuda").manual_seed(200 + cin + k + h)
+    assert K.rowsum_supported(cout, cin, k, L.F16)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g).half().float()
+    wgt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k)).half().float()
     bias = torch.randn(cout, device="cuda", generator=g) * 0.1
-    m = tf32(torch.randn(n, cout, h, w, device="cuda", generator=g))
-    xt = fill_nhwc(K, x, cin, 2, L.PAD_REFLECT, L.F32)
-    mt = fill_nhwc(K, m, cout, 1, L.PAD_REFLECT, L.F32) if use_mul else None
-    y = K.NHWC(n, h, w, cout + 16, 1, L.F32, "cuda", zero=True)
+    alpha = torch.tensor([0.73], device="cuda")
+    pad = (k - 1) // 2
+    sx = torch.tensor([4.0], device="cuda")
+    sw = torch.tensor([16.0], device="cuda")
+    xt = K.NHWC(n, h, w, cin, pad, L.F16, "cuda", zero=True, scale=sx)
+    xt.padded_view()[..., :cin] = (F.pad(x, (pad,) * 4, mode="reflect") * 4.0).permute(0, 2, 3, 1).half()
+    out = torch.full((n, cout, h, w), 7.0, device="cuda")
 
     class Cache:
         def get(self, key, param, fn):
             return fn()
-    assert K.conv3x3_rowsum_nhwc(xt, wgt, Cache(), "t", 1, y, 16, bias, L.ACT_LRELU, mt)
+    K.conv_planar(xt, wgt, Cache(), "t", k, pad, bias, alpha, L.ACT_TANH, out, None, None, w_scale=sw)
     assert K.device_error() == 0
-    ref = F.leaky_relu(F.conv2d(F.pad(x, (1,) * 4, mode="reflect").double(), wgt.double(), bias.double()), 0.2).float()
-    if use_mul:
-        ref = ref * m
-    assert relerr(y.interior_nchw()[:, 16:], ref) < 6e-4
-    assert float(y.interior_nchw()[:, :16].abs().max()) == 0.0
-    assert float(y.padded_view()[:, 0].abs().max()) == 0.0
+    ref = torch.tanh(0.73 * F.conv2d(F.pad(x, (pad,) * 4, mode="reflect").double(), wgt.double())
+                     + bias.double().view(1, -1, 1, 1)).float()
+    e = relerr(out, ref)
+    print(f"rowsum f16 {case}: rel err {e:.3e}")
+    assert e < 2e-5

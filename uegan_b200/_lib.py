@@ -56,10 +56,6 @@ SYMBOLS = {
     "uegan_pack_conv_weight_rowsum": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
     "uegan_pack_conv_weight_rowsum_scaled": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p, C.c_void_p]),
     "uegan_conv2d_fprop_rowsum": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
-    "uegan_conv2d_rowsum_nhwc_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
-    "uegan_packed_weight_rowsum_nhwc_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
-    "uegan_pack_conv_weight_rowsum_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]),
-    "uegan_conv2d_fprop_rowsum_nhwc": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "uegan_pack_input": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.c_int32, C.POINTER(C.c_float),
                                    C.POINTER(C.c_float), C.c_void_p]),
     "uegan_halo_fill": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_void_p]),

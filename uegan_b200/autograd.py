@@ -146,8 +146,6 @@ def _g_forward_pass(G, x, ws):
 
     def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE):
         cv = holder.conv
-        if k == 3 and stride == 1 and K.conv3x3_rowsum_nhwc(src, cv.weight, G._wcache, name, 1, dst, 0, cv.bias, act_):
-            return  # experimental opt-in path (UEGAN_ROWSUM_NHWC=1)
         K.conv_fprop(src, G._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, 0, cv.bias, None, act_,
                      w_scale=G._wscale(name, cv))
 

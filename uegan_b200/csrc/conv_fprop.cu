@@ -234,8 +234,9 @@ __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t tadd
         if (p.out_kind == UEGAN_BF16) {
           __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
           pk[i] = *reinterpret_cast<uint32_t*>(&h);
-        } else {
-          __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        } else {  // saturating (see Vec<__half>::store)
+          __half2 h = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f),
+                                        fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
           pk[i] = *reinterpret_cast<uint32_t*>(&h);
         }
       }

@@ -60,11 +60,14 @@ template <> struct Vec<__half> {
       v[2 * i + 1] = __high2float(h);
     }
   }
+  // saturating: a value beyond fp16's range is stored as +-65504, never as inf (a scale that lags by more than its 64x
+  // margin then costs precision for one pass -- uegan_scale_update sees the saturated sample and backs off -- instead of
+  // poisoning the step with inf - inf = nan)
   __device__ static void store(__half* p, const float (&v)[8]) {
     uint32_t w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      __half2 h = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f), fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
       w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);

@@ -30,8 +30,9 @@ __global__ void __launch_bounds__(256) scale_update_kernel(const uegan_scale_ent
       } else if (e.dtype == UEGAN_F16) {
         const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
         const float a = fabsf(__low2float(h)), b = fabsf(__high2float(h));
-        if (a <= 65504.f) amax = fmaxf(amax, a); else bad = 1;
-        if (b <= 65504.f) amax = fmaxf(amax, b); else bad = 1;
+        // (stores saturate at 65504: a sample at the limit counts as overflow)
+        if (a < 65504.f) amax = fmaxf(amax, a); else bad = 1;
+        if (b < 65504.f) amax = fmaxf(amax, b); else bad = 1;
       } else {
         const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
         const float a = fabsf(__low2float(h)), b = fabsf(__high2float(h));

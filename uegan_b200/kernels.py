@@ -253,43 +253,6 @@ def conv_planar(x: NHWC, weight: torch.Tensor, cache, key, k: int, pad: int, bia
                w_scale=w_scale)
 
 
-def conv3x3_rowsum_nhwc(x: NHWC, weight: torch.Tensor, cache, key, pad: int, y: NHWC, y_c_off: int = 0, bias=None,
-                        act: int = L.ACT_NONE, mul: Optional[NHWC] = None) -> bool:
-    """EXPERIMENTAL opt-in (UEGAN_ROWSUM_NHWC=1, csrc/conv_rowsum_nhwc.cu): k3 stride-1 conv with cout 32 / 64 through the
-    row-sum formulation.  Returns False (nothing launched) unless the library reports the shape as supported, which it never
-    does by default."""
-    lib = L.load()
-    cout, cin_total, k, _ = weight.shape
-    if k != 3 or not lib.uegan_conv2d_rowsum_nhwc_supported(cout, x.c, k, x.dtype):
-        return False
-
-    def pack(out=None):
-        w = weight.detach()
-        nbytes = lib.uegan_packed_weight_rowsum_nhwc_bytes(cout, x.c)
-        buf = out if out is not None else torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
-        L.check(lib.uegan_pack_conv_weight_rowsum_nhwc(w.data_ptr(), buf.data_ptr(), cout, cin_total, 0, cin_total, x.c,
-                                                       _stream()), "pack_conv_weight_rowsum_nhwc")
-        _count(1, "pack_weight_rowsum_nhwc")
-        return buf
-    wp = cache.get((key, "rowsum_nhwc"), weight, pack)
-    d = L.ConvDesc()
-    d.x, d.y = x.ct, y.ct
-    d.y_c_off, d.cout, d.k, d.stride, d.pad, d.act = y_c_off, cout, 3, 1, pad, act
-    d.w_packed = wp.data_ptr()
-    d.bias = bias.data_ptr() if bias is not None else None
-    d.mul = C.pointer(mul.ct) if mul is not None else None
-    ev = _Counters.conv_events
-    if ev is not None:
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-    L.check(lib.uegan_conv2d_fprop_rowsum_nhwc(C.byref(d), _stream()), "conv2d_fprop_rowsum_nhwc")
-    if ev is not None:
-        s1.record()
-        ev.append((s0, s1, 2.0 * x.n * y.h * y.w * cout * 9 * x.c, x, cout, 3, 1, "fprop", x.dtype))
-    _count(1, f"fprop_rowsum_nhwc ->{cout} k3", x)
-    return True
-
-
 def pack_input(x_nchw: torch.Tensor, dst: NHWC, pad_mode: int = L.PAD_REFLECT, scale=None, shift=None):
     assert x_nchw.is_cuda and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and x_nchw.shape[1] == 3
     assert tuple(x_nchw.shape) == (dst.n, 3, dst.h, dst.w)
