@@ -38,6 +38,58 @@ TRAIN_GFLOP_PER_IMAGE = 1098.9  # algorithmic conv FLOPs of one training step pe
 RES = 512
 
 
+def _conv_tables():
+    """(cin, cout, h_in, h_out) of every convolution on the path at 512 x 512 (1x1 up-convs hoisted before the
+    bilinear x2, GAM fuse with its live half only -- the forms this implementation executes)."""
+    G = [(3, 32, 512, 512), (32, 64, 512, 256), (64, 128, 256, 128), (128, 256, 128, 64), (256, 512, 64, 32),
+         (512, 512, 32, 32),                                                     # ga5.fuse (live half)
+         (512, 256, 32, 32), (256, 256, 64, 64), (512, 256, 64, 64),             # upsample1 conv, ga4.fuse, dec1
+         (256, 128, 64, 64), (128, 128, 128, 128), (256, 128, 128, 128),         # upsample2, ga3, dec2
+         (128, 64, 128, 128), (64, 64, 256, 256), (128, 64, 256, 256),           # upsample3, ga2, dec3
+         (64, 32, 256, 256), (32, 32, 512, 512), (64, 32, 512, 512),             # upsample4, ga1, dec4
+         (32, 32, 512, 512), (32, 3, 512, 512)]                                  # dec5.0, dec5.1
+    D = [(3, 32, 512, 256), (32, 64, 256, 128), (64, 128, 128, 64), (128, 256, 64, 32), (256, 512, 32, 16),
+         (32, 1, 256, 256), (64, 1, 128, 128), (128, 1, 64, 64), (256, 1, 32, 32), (512, 1, 16, 16)]
+    V = [(3, 64, 512, 512), (64, 64, 512, 512), (64, 128, 256, 256), (128, 128, 256, 256), (128, 256, 128, 128),
+         (256, 256, 128, 128), (256, 256, 128, 128), (256, 256, 128, 128), (256, 512, 64, 64), (512, 512, 64, 64),
+         (512, 512, 64, 64), (512, 512, 64, 64), (512, 512, 32, 32)]
+    return G, D, V
+
+
+def training_step_algorithmic_bytes(bytes_per_elem=2):
+    """Algorithmic HBM bytes of ONE training step per image at 512 x 512: every GEMM reads its two activation-sized
+    operands / writes its output exactly once at 16-bit storage (fprop: x + y; dgrad: dz + dx; wgrad: x + dz), everything
+    else (padding, activations, norms, up/down-sampling, losses) fused away, weights (35 MB per step, not per image)
+    excluded.  Passes per step (trainer.py:75-119): G 2 fprop, 2 wgrad, 2 dgrad (no dgrad into the image); D 5 fprop,
+    3 wgrad + 3 dgrad without the input layer (D step), 1 full dgrad (G step); VGG 2 fprop, 1 dgrad."""
+    G, D, V = _conv_tables()
+    io = lambda t: sum(ci * hi * hi + co * ho * ho for ci, co, hi, ho in t)
+    first = lambda t: t[0][0] * t[0][2] ** 2 + t[0][1] * t[0][3] ** 2
+    g = io(G) * (2 + 2) + (io(G) - first(G)) * 2
+    d = io(D) * (5 + 3) + (io(D) - first(D)) * 3 + io(D) * 1
+    v = io(V) * (2 + 1)
+    return (g + d + v) * bytes_per_elem
+
+
+def generator_algorithmic_bytes(bytes_per_elem=2):
+    return sum(ci * hi * hi + co * ho * ho for ci, co, hi, ho in _conv_tables()[0]) * bytes_per_elem
+
+
+def measured_traffic(train, precision):
+    """DRAM bytes per step of the GEMM launches, from the committed ncu pass of THIS build
+    (profiles/r2_step_traffic.json, written by scripts/ncu_traffic.py from the per-launch CSV: dram__bytes_read.sum +
+    dram__bytes_write.sum); None when no capture of this workload / precision is committed."""
+    p = os.path.join(ROOT, "profiles", "r2_step_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    e = d.get(f"{'train' if train else 'inference'}_{precision}")
+    if not e:
+        return None, None
+    return e.get("gemm_dram_bytes_per_step"), e.get("source")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -425,14 +477,17 @@ def run_native(args):
             g = groups.setdefault(f"{kind} {'tf32' if dt == 0 else 'f16'}", [0.0, 0.0]); g[0] += ms; g[1] += f / reps
         achieved = tot_fl / (tot_ms * 1e-3) / 1e12
         peak = tot_fl / t_at_peak / 1e12
+        prec = "f16" if (T.G.precision if train else G.precision) == "f16" else "tf32"
+        traffic, traffic_src = measured_traffic(train, prec)
+        alg_bytes = batch * (training_step_algorithmic_bytes() if train else generator_algorithmic_bytes())
         top = sorted(per.items(), key=lambda kv: -kv[1][0])[:24]
         roof = {"bound": "tensor", "kernel": "conv_fprop_kernel (fprop+dgrad) + conv_wgrad_kernel, all launches of a step",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                # DRAM bytes of these launches per step (dram__bytes_read.sum + dram__bytes_write.sum, ncu): measured once,
-                # profiles/r1d_train_step_launches.md (training, 330 of 349 GEMM launches of the r1d build); per-layer
-                # figures of the current kernels: profiles/r1g_ncu_full_layers.md
-                "traffic": 82.2e9 if train else None,
-                "traffic_source": "ncu, profiles/r1d_train_step_launches.md (bytes per step, r1d build)" if train else None,
+                # DRAM bytes of these launches per step (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu
+                # pass of this build, next to the algorithmic bytes of the same step
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes": alg_bytes,
+                "traffic_over_algorithmic": (traffic / alg_bytes) if (traffic and alg_bytes) else None,
                 "peak_source": f"{src}: FLOP-weighted mix of bf16_tflops {tf_burst} (fp16 launches) and half of it (tf32 launches)",
                 "gemm_ms_per_step": tot_ms, "step_ms": ms_total / args.steps, "gemm_launches_per_step": len(ev) // reps,
                 "gemm_share_of_step": tot_ms / (ms_total / args.steps),
