@@ -31,6 +31,7 @@ class _Scratch:
         self.book = book
 
     def get(self, name, n, h, w, c, halo=0, dtype=F32, device="cuda", zero=False, share=None):
+        """zero=True: allocated zeroed (a halo that only ever holds zeros: the buffer's producers write the interior only)."""
         key = (name, n, h, w, c, halo, dtype, str(device))
         t = self.store.get(key)
         if t is None:
@@ -196,7 +197,8 @@ def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
     dty = ws.get("dtype", F32)
     f16 = dty != F32
     scr = ws["scratch"] if f16 else _scratch
-    S = lambda name, hh, ww, c, halo=0, share=None: scr.get(name, b, hh, ww, c, halo, dty, dev, share=share)
+    S = lambda name, hh, ww, c, halo=0, share=None, zero=False: scr.get(name, b, hh, ww, c, halo, dty, dev, share=share,
+                                                                        zero=zero)
     rgb_c = 8 if f16 else 4  # stored channels of a 3-channel tensor: one 16-byte vector
     grads = {}
     cache = G._wcache
@@ -284,8 +286,15 @@ def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
         du = S(f"du{i}", hh // 2, ww // 2, ch)
         K.upsample2x_bwd(dcat, 0, du)
         wgrad(f"upsample{i+1}.1.main.1", up, srcs[i], du, 1, 1, 0, bias_from=du)
-        dsrc = S(f"dsrc{i}", hh // 2, ww // 2, 2 * ch)
-        K.conv_dgrad(du, up.weight, 1, 1, dsrc, cache, f"upsample{i+1}", w_scale=wsc(f"upsample{i+1}", up))
+        if i > 0:
+            # the data gradient of the 1x1 up-conv IS the gradient of y_{i-1} = act(z): the LeakyReLU mask rides in the
+            # dgrad epilogue and the result lands in the (zero-haloed) operand of the next decoder stage directly
+            dz_next = S(f"dz_dec{i-1}", hh // 2, ww // 2, 2 * ch, 2, zero=True)
+            K.conv_dgrad(du, up.weight, 1, 1, dz_next, cache, f"upsample{i+1}", w_scale=wsc(f"upsample{i+1}", up),
+                         mask=P["y"][i - 1], mask_act=act)
+        else:
+            dsrc = S(f"dsrc{i}", hh // 2, ww // 2, 2 * ch)
+            K.conv_dgrad(du, up.weight, 1, 1, dsrc, cache, f"upsample{i+1}", w_scale=wsc(f"upsample{i+1}", up))
         # second half: InstanceNorm(conv1x1(skip, fuse.weight[:, :ch]))
         dzs = S(f"dzs{i}", hh, ww, ch)
         K.instance_norm_bwd(dcat, ch, P["z"][i], P["mr"][f"ga{4-i}"], dzs,
@@ -297,8 +306,7 @@ def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
         K.conv_dgrad(dzs, ga.weight, 1, 1, dsk, cache, gname, cin_first=0, cin=ch, w_scale=wsc(gname, ga))
         dskip[i] = dsk
         if i > 0:
-            dz = S(f"dz_dec{i-1}", hh // 2, ww // 2, 2 * ch, 2)
-            K.grad_combine(dz, 2 * ch, add_b=dsrc, mask=P["y"][i - 1], act=act)
+            dz = dz_next
         else:
             d_x5n = dsrc
     # ---- ga5 on x5
@@ -309,13 +317,12 @@ def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
     f5 = G.ga5.fuse[0]
     wgrad("ga5.fuse.0", f5, P["x5"], dz5g, 1, 1, 0, cin_first=0, cin=c5)
     dead("ga5.fuse.0.bias", f5.bias)
-    dx5 = S("dx5", h5, w5, c5)
-    K.conv_dgrad(dz5g, f5.weight, 1, 1, dx5, cache, "ga5", cin_first=0, cin=c5, w_scale=wsc("ga5", f5))
+    dze = S("dz_e5", h5, w5, c5, 1, zero=True)  # = mask(x5) * dgrad, straight from the epilogue
+    K.conv_dgrad(dz5g, f5.weight, 1, 1, dze, cache, "ga5", cin_first=0, cin=c5, w_scale=wsc("ga5", f5),
+                 mask=P["x5"], mask_act=act)
     # ---- encoder 5..1
     encs = [G.enc1, G.enc2, G.enc3, G.enc4, G.enc5]
     xs = [P["x0"], P["x1"], P["x2"], P["x3"], P["x4"], P["x5"]]
-    dze = S("dz_e5", h5, w5, c5, 1)
-    K.grad_combine(dze, c5, add_b=dx5, mask=P["x5"], act=act)
     for li in (5, 4, 3, 2):  # enc{li}: x_{li-1} -> x_li, k3 s2
         conv = encs[li - 1].conv
         xin = xs[li - 1]
@@ -400,11 +407,25 @@ def _d_forward_train(D, x, ws):
     if ws["book"] is not None:
         if not ws.get("fwd_settled"):
             ws["fwd_settled"] = True
-            # eval-mode passes while the scales settle: the spectral-norm power iteration must advance exactly once
+            # The spectral-norm power iteration must advance exactly once, and the scales must settle on the sigma the
+            # real pass uses (from a random u, sigma moves by a large factor in the first iteration, which compounds over
+            # the five layers): advance u / v first, then settle AND run with u / v held (sigma = u.(W v) is then the very
+            # value the train-mode pass would have computed).
+            if D.training and D.use_sn:
+                _d_advance_sn(D, x.device)
             _settle(ws["book"], lambda: _d_forward_pass(D, x, ws, False))
-        else:
-            ws["book"].update()
+            return _d_forward_pass(D, x, ws, False)
+        ws["book"].update()
     return _d_forward_pass(D, x, ws, D.training)
+
+
+def _d_advance_sn(D, dev):
+    """One power iteration of every spectrally-normalised conv (what a train-mode forward does, models.py:185-188)."""
+    sig = torch.empty(2, dtype=torch.float32, device=dev)
+    for i in range(1, 6):
+        conv, wgt = D._conv(i), D._weight(i)
+        scratch = torch.empty(wgt.shape[0] + wgt.numel() // wgt.shape[0] + 8, dtype=torch.float32, device=dev)
+        K.spectral_sigma(wgt, conv.weight_u, conv.weight_v, True, sig, scratch)
 
 
 def _d_forward_pass(D, x, ws, training):

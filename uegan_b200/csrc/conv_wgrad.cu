@@ -56,16 +56,31 @@ __device__ __forceinline__ void wg_publish(float* dw, float* partial, long long 
   else atomicAdd(dw + idx, v);
 }
 
-// dw[o][cin_first + c][r][s] += sum_{slice} partial[slice][...] over the elements this launch owns
-__global__ void wgrad_reduce_kernel(float* __restrict__ dw, const float* __restrict__ partial, long long dw_numel, int slices,
-                                    int cin_total, int cin_first, int cin, int kk) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= dw_numel) return;
-  const int c = (int)((i / kk) % cin_total);
-  if (c < cin_first || c >= cin_first + cin) return;
+// dw[o][cin_first + c][r][s] += sum_{slice} partial[slice][...] over the elements this launch owns.
+// Block = 32 elements x 8 slice lanes: lane l sums the slices l, l + 8, ... in order, then the 8 lane sums are added in
+// lane order -- a FIXED association (bit-reproducible) with an 8x shorter dependent-load chain than one thread per element.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(float* __restrict__ dw, const float* __restrict__ partial,
+                                                           long long dw_numel, int slices, int cin_total, int cin_first,
+                                                           int cin, int kk) {
+  __shared__ float sh[8][33];
+  const int e = threadIdx.x & 31, l = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + e;
   float acc = 0.f;
-  for (int s = 0; s < slices; ++s) acc += partial[(long long)s * dw_numel + i];
-  dw[i] += acc;
+  bool own = false;
+  if (i < dw_numel) {
+    const int c = (int)((i / kk) % cin_total);
+    own = c >= cin_first && c < cin_first + cin;
+    if (own)
+      for (int s = l; s < slices; s += 8) acc += partial[(long long)s * dw_numel + i];
+  }
+  sh[l][e] = acc;
+  __syncthreads();
+  if (l == 0 && own) {
+    float t = sh[0][e];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sh[k][e];
+    dw[i] += t;
+  }
 }
 
 template <int kF16>
@@ -248,8 +263,8 @@ static int wg_reduce(float* dw, const float* ws, long long dw_numel, int ksplit,
   if (!ws) return 0;
   const int per = (total_ktiles + ksplit - 1) / ksplit;
   const int slices = (total_ktiles + per - 1) / per;  // slices beyond this one own no k-tile and write nothing
-  wgrad_reduce_kernel<<<(unsigned)((dw_numel + 255) / 256), 256, 0, st>>>(dw, ws, dw_numel, slices, cin_total, cin_first, cin,
-                                                                        k * k);
+  wgrad_reduce_kernel<<<(unsigned)((dw_numel + 31) / 32), 256, 0, st>>>(dw, ws, dw_numel, slices, cin_total, cin_first, cin,
+                                                                      k * k);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

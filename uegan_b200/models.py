@@ -444,20 +444,30 @@ class Discriminator(nn.Module, _ScaledNet):
         P = self._plan(b, h, w, x.device)
         book = P["book"]
         if book is not None and not P.get("calibrated"):
-            # settle the per-tensor scales (see Generator.forward_native); eval-mode passes: the spectral-norm buffers
-            # must not advance during calibration
+            # settle the per-tensor scales (see Generator.forward_native) on the sigma the real pass uses: advance the
+            # spectral-norm power iteration ONCE (if in train mode), then settle and run with u / v held (see
+            # autograd._d_forward_train)
             P["calibrated"] = True
             was = self.training
+            if was and self.use_sn:
+                from .autograd import _d_advance_sn
+                _d_advance_sn(self, x.device)
             self.training = False
-            prev = None
-            for _ in range(48):
-                self._forward_pass(x, P)
-                book.update()
-                cur = book.values()
-                if prev is not None and torch.equal(cur, prev):
-                    break
-                prev = cur
-            self.training = was
+            try:
+                prev = None
+                for _ in range(48):
+                    self._forward_pass(x, P)
+                    book.update()
+                    cur = book.values()
+                    if prev is not None and torch.equal(cur, prev):
+                        break
+                    prev = cur
+                preds = self._forward_pass(x, P)
+            finally:
+                self.training = was
+            if keep is not None:
+                keep.update(P)
+            return preds
         elif book is not None:
             book.update()
         preds = self._forward_pass(x, P)
