@@ -266,6 +266,14 @@ def workload_name(w):
             else "generator_inference_3x512x512_b32 (BASELINE.json configs[1])")
 
 
+def _claim_stdout():
+    """Returns a duplicate of the original stdout and points fd 1 at stderr for the rest of the process."""
+    sys.stdout.flush()
+    fd = os.dup(1)
+    os.dup2(2, 1)
+    return fd
+
+
 # ------------------------------------------------------------------------------------------------ GPU: config 5
 def run_sweep(args):
     """BASELINE.json configs[4]: mixed-resolution Generator inference sweep (short edge 256 / 512 / 1024, 2:3 aspect),
@@ -276,8 +284,10 @@ def run_sweep(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    json_fd = _claim_stdout()
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from oracle import uegan_oracle as O
     from uegan_b200 import kernels as K
@@ -288,7 +298,7 @@ def run_sweep(args):
     free, _ = torch.cuda.mem_get_info()
     rows, tot_pix, tot_ms = [], 0.0, 0.0
     for (h, w) in ((256, 384), (512, 768), (1024, 1536)):
-        per_img = 1500.0 * h * w  # bytes of activation buffers per image (all Generator tensors, fp32 NHWC)
+        per_img = (1500.0 if G.precision == "tf32" else 800.0) * h * w  # bytes of activation buffers per image (all Generator tensors)
         b = int(min(256, max(1, 0.5 * free / per_img)))
         x = torch.rand(b, 3, h, w, device="cuda") * 2 - 1
         with torch.no_grad():
@@ -315,13 +325,13 @@ def run_sweep(args):
         del x
         torch.cuda.empty_cache()
     if rank == 0:
-        print(json.dumps({
+        os.write(json_fd, (json.dumps({
             "metric": "Generator inference megapixels/sec (mixed-resolution sweep)", "value": tot_pix / (tot_ms * 1e-3),
             "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+            "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": G.precision,
             "data": "synthetic", "config": {"workload": "generator_inference_sweep_256_512_1024 (BASELINE.json configs[4])",
                                             "parallelism": f"replicas x{world}", "sweep": rows},
-            "gpu_launches": K.launches()}))
+            "gpu_launches": K.launches()}) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
@@ -335,11 +345,13 @@ def run_native(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     group = None
+    # stdout carries exactly ONE JSON line: native libraries (NCCL's "NCCL version ..." banner, symmetric-memory init) write
+    # to file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
+    # duplicate of the original stdout at the end
+    json_fd = _claim_stdout()
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
-        else:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("VERSION", "INFO", "TRACE"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         group = dist.group.WORLD
@@ -524,7 +536,8 @@ def run_native(args):
         value = world * batch / (ms_step * 1e-3)
         e2e = world * batch / (ms_e2e / args.steps * 1e-3)
         hbm, tf_burst, tf_sus, src = peaks()
-        print(json.dumps({
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps({
             "metric": "512x512 training images/sec" if train else "512x512 images/sec", "value": value,
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -544,7 +557,7 @@ def run_native(args):
                                        f" {'training step' if train else 'Generator.forward'}, "
                                        f"{1 if train else 2} iteration(s) of {cpu_batch}x3x512x512 ({cpu_dt:.1f} s)"},
             "gpu_library_baseline": gpu_lib, "replicas": replicas,
-        }))
+        }) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

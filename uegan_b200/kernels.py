@@ -362,7 +362,7 @@ def gan_loss_fwd(mode: int, for_d: bool, real, fake, ws: torch.Tensor, loss_out:
         _count(3, "gan_loss_fwd")
         return 1
     rp, fp = _ptr_array(real), _ptr_array(fake)
-    if hasattr(group, "reduce"):  # uegan_b200.peer.PeerComm: sums over peer memory, no NCCL call
+    if hasattr(group, "peer_ptrs"):  # uegan_b200.peer.PeerComm: sums over peer memory, no NCCL call
         world = group.world
         red = lambda lo, hi: group.reduce(ws, lo, hi)
     else:
