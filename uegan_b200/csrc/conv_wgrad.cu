@@ -57,28 +57,38 @@ __device__ __forceinline__ void wg_publish(float* dw, float* partial, long long 
 }
 
 // dw[o][cin_first + c][r][s] += sum_{slice} partial[slice][...] over the elements this launch owns.
-// Block = 32 elements x 8 slice lanes: lane l sums the slices l, l + 8, ... in order, then the 8 lane sums are added in
-// lane order -- a FIXED association (bit-reproducible) with an 8x shorter dependent-load chain than one thread per element.
+// Block = E elements x L slice lanes (E * L = 256, L = 2^lanes_log2): lane l sums the slices l, l + L, ... in order (the
+// loads of four slices are issued back to back), then the L lane sums are added in lane order -- a FIXED association
+// (bit-reproducible) whose dependent-load chain is slices / (4 L) long: with up to 296 slices of a few thousand
+// elements (1x1 convs) the one-thread-per-element version was pure latency (25-50 us per launch, 1.4 ms per step).
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(float* __restrict__ dw, const float* __restrict__ partial,
                                                            long long dw_numel, int slices, int cin_total, int cin_first,
-                                                           int cin, int kk) {
-  __shared__ float sh[8][33];
-  const int e = threadIdx.x & 31, l = threadIdx.x >> 5;
-  const long long i = (long long)blockIdx.x * 32 + e;
+                                                           int cin, int kk, int lanes_log2) {
+  __shared__ float sh[256];
+  const int L = 1 << lanes_log2, E = 256 >> lanes_log2;
+  const int e = threadIdx.x & (E - 1), l = threadIdx.x >> (8 - lanes_log2);
+  const long long i = (long long)blockIdx.x * E + e;
   float acc = 0.f;
   bool own = false;
   if (i < dw_numel) {
     const int c = (int)((i / kk) % cin_total);
     own = c >= cin_first && c < cin_first + cin;
-    if (own)
-      for (int s = l; s < slices; s += 8) acc += partial[(long long)s * dw_numel + i];
+    if (own) {
+      const float* src = partial + i;
+      int s = l;
+      for (; s + 3 * L < slices; s += 4 * L) {
+        const float a0 = __ldg(src + (long long)s * dw_numel), a1 = __ldg(src + (long long)(s + L) * dw_numel);
+        const float a2 = __ldg(src + (long long)(s + 2 * L) * dw_numel), a3 = __ldg(src + (long long)(s + 3 * L) * dw_numel);
+        acc = (((acc + a0) + a1) + a2) + a3;
+      }
+      for (; s < slices; s += L) acc += __ldg(src + (long long)s * dw_numel);
+    }
   }
-  sh[l][e] = acc;
+  sh[l * E + e] = acc;
   __syncthreads();
   if (l == 0 && own) {
-    float t = sh[0][e];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) t += sh[k][e];
+    float t = sh[e];
+    for (int k = 1; k < L; ++k) t += sh[k * E + e];
     dw[i] += t;
   }
 }
@@ -129,36 +139,53 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (kt0 < kt1) {
     if (warp == 0) {
       if (elect_one()) {
+        // The producer is ONE thread: everything that does not change from stage to stage (box coordinates of every
+        // tap / channel group) is computed before the loop, and the tile counters advance by increments -- measured
+        // r2j (ncu source page): with the coordinate arithmetic (divisions per box) inside the loop the MMA warp sat in
+        // its full_bar wait for 80 % of its samples while this thread issued ~600 instructions per stage.
+        constexpr int MAXB = 256 / CB;  // N-operand boxes per stage
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t tx = kWgABytes + (p.swap_mode ? 1 : t_count * p.tap_boxes) * kWgBoxBytes;
+        const int nB = p.swap_mode ? 1 : t_count * p.tap_boxes;
+        const uint32_t tx = kWgABytes + nB * kWgBoxBytes;
+        int bc[MAXB], br[MAXB];
+#pragma unroll
+        for (int j = 0; j < MAXB; ++j) {
+          const int t = j / p.tap_boxes, g = j - t * p.tap_boxes;
+          const int tp = t_first + t;
+          const int tr = p.window_mode ? tp : tp / p.k, ts = p.window_mode ? 0 : tp - (tp / p.k) * p.k;
+          bc[j] = ts * p.x_c + nc * p.tap_boxes * CB + g * CB;
+          br[j] = tr;
+        }
+        int tw_i = kt0 % p.tiles_w, th_i = (kt0 / p.tiles_w) % p.tiles_h, n = kt0 / (p.tiles_w * p.tiles_h);
+        const int m0 = mt * 128;
         for (int kt = kt0; kt < kt1; ++kt) {
-          const int wo0 = (kt % p.tiles_w) * 8;
-          const int ho0 = ((kt / p.tiles_w) % p.tiles_h) * 8;
-          const int n = kt / (p.tiles_w * p.tiles_h);
+          const int wo0 = tw_i * 8, ho0 = th_i * 8;
           mbar_wait(&empty_bar[stage], phase ^ 1, 0x600 + stage, p.err_sink);
           uint8_t* sa = smem + stage * p.stage_bytes;
           uint8_t* sb = sa + kWgABytes;
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           if (p.swap_mode) {
             // M operand = 128 consecutive window elements (s, c) of filter row r, N operand = the 32 stored dz channels
+#pragma unroll
             for (int g = 0; g < MBOX; ++g)
-              tma_load_5d(&tmB, &full_bar[stage], sa + g * kWgBoxBytes, mt * 128 + g * CB, wo0, r, ho0, n);
+              tma_load_5d(&tmB, &full_bar[stage], sa + g * kWgBoxBytes, m0 + g * CB, wo0, r, ho0, n);
             tma_load_4d(&tmA, &full_bar[stage], sb, 0, wo0, ho0, n);
           } else {
+#pragma unroll
             for (int g = 0; g < MBOX; ++g)
-              tma_load_4d(&tmA, &full_bar[stage], sa + g * kWgBoxBytes, mt * 128 + g * CB, wo0, ho0, n);
+              tma_load_4d(&tmA, &full_bar[stage], sa + g * kWgBoxBytes, m0 + g * CB, wo0, ho0, n);
             // B map = the fprop sliding-window map {window, wo, r, ho, n}: tap column s and channel offset are both
             // positions inside the window of k*C contiguous (s, c) values that starts at the pixel
-            for (int t = 0; t < t_count; ++t) {
-              const int tp = t_first + t;
-              const int tr = p.window_mode ? tp : tp / p.k, ts = p.window_mode ? 0 : tp % p.k;
-              for (int g = 0; g < p.tap_boxes; ++g)
-                tma_load_5d(&tmB, &full_bar[stage], sb + (t * p.tap_boxes + g) * kWgBoxBytes,
-                            ts * p.x_c + nc * p.tap_boxes * CB + g * CB, wo0, tr, ho0, n);
-            }
+#pragma unroll
+            for (int j = 0; j < MAXB; ++j)
+              if (j < nB) tma_load_5d(&tmB, &full_bar[stage], sb + j * kWgBoxBytes, bc[j], wo0, br[j], ho0, n);
           }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          if (++tw_i == p.tiles_w) {
+            tw_i = 0;
+            if (++th_i == p.tiles_h) { th_i = 0; ++n; }
+          }
         }
       }
     } else if (warp == 1) {
@@ -263,8 +290,10 @@ static int wg_reduce(float* dw, const float* ws, long long dw_numel, int ksplit,
   if (!ws) return 0;
   const int per = (total_ktiles + ksplit - 1) / ksplit;
   const int slices = (total_ktiles + per - 1) / per;  // slices beyond this one own no k-tile and write nothing
-  wgrad_reduce_kernel<<<(unsigned)((dw_numel + 31) / 32), 256, 0, st>>>(dw, ws, dw_numel, slices, cin_total, cin_first, cin,
-                                                                      k * k);
+  const int lanes_log2 = slices >= 48 ? 5 : (slices >= 12 ? 4 : 3);
+  const int E = 256 >> lanes_log2;
+  wgrad_reduce_kernel<<<(unsigned)((dw_numel + E - 1) / E), 256, 0, st>>>(dw, ws, dw_numel, slices, cin_total, cin_first, cin,
+                                                                         k * k, lanes_log2);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -348,8 +377,10 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   if (p.num_stages > 4) p.num_stages = 4;
   UEGAN_CHECK(p.num_stages >= 2, "conv2d_wgrad: stage too large");
   const int groups = p.taps * p.m_tiles * p.n_chunks;
-  int ksplit = (2 * num_sms() + groups - 1) / groups;
-  if (ksplit > p.total_ktiles) ksplit = p.total_ktiles;
+  int ksplit = (2 * num_sms()) / groups;  // two full waves of single-CTA SMs (rounding UP left a third, mostly empty wave)
+  // every CTA pays a fixed prologue + a 128 x N epilogue (and one more partial plane for the reduction): keep >= 16
+  // K stages per CTA even when that leaves SMs idle (deep layers: few pixels, large dW)
+  if (ksplit > p.total_ktiles / 16) ksplit = p.total_ktiles / 16;
   if (ksplit < 1) ksplit = 1;
   p.dw_numel = (long long)cout * cin_total * k * k;
   if (wg_plan_split(&ksplit, p.dw_numel, ws, ws_bytes)) return -1;
@@ -481,10 +512,13 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t tx = nch * p.ph * p.pw * 128 + p.n_boxes * 64 * 128;
+        int tw_i = kt0 % p.tiles_w, th_i = (kt0 / p.tiles_w) % p.tiles_h, n_i = kt0 / (p.tiles_w * p.tiles_h);
         for (int kt = kt0; kt < kt1; ++kt) {
-          const int wo0 = (kt % p.tiles_w) * 8;
-          const int ho0 = ((kt / p.tiles_w) % p.tiles_h) * 8;
-          const int n = kt / (p.tiles_w * p.tiles_h);
+          const int wo0 = tw_i * 8, ho0 = th_i * 8, n = n_i;
+          if (++tw_i == p.tiles_w) {
+            tw_i = 0;
+            if (++th_i == p.tiles_h) { th_i = 0; ++n_i; }
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1, 0xA00 + stage, p.err_sink);
           uint8_t* sp = smem + stage * p.stage_bytes;
           uint8_t* sz = sp + nch * p.patch_bytes;
@@ -631,7 +665,7 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
   p.tiles_h = (Ho + 7) / 8;
   p.nimg = x->n;
   p.total_ktiles = p.tiles_w * p.tiles_h * p.nimg;
-  int ksplit = (2 * num_sms() + slices - 1) / slices;
+  int ksplit = (2 * num_sms()) / slices;
   if (ksplit > p.total_ktiles) ksplit = p.total_ktiles;
   if (ksplit < 1) ksplit = 1;
   p.dw_numel = (long long)cout * cin_total * k * k;
@@ -721,7 +755,7 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
   p.tiles_h = (e->h + 7) / 8;
   p.nimg = x->n;
   p.total_ktiles = p.tiles_w * p.tiles_h * p.nimg;
-  int ksplit = (2 * num_sms() + slices - 1) / slices;
+  int ksplit = (2 * num_sms()) / slices;
   if (ksplit > p.total_ktiles) ksplit = p.total_ktiles;
   if (ksplit < 1) ksplit = 1;
   p.dw_numel = (long long)cout * cin_total * k * k;
