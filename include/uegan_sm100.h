@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UEGAN_ABI_VERSION 3
+#define UEGAN_ABI_VERSION 4
 
 enum { UEGAN_F32 = 0, UEGAN_BF16 = 1, UEGAN_F16 = 2 };  /* storage dtype; F32 tensors feed kind::tf32 MMAs, the
                                                            16-bit types kind::f16 */
@@ -78,6 +78,11 @@ typedef struct uegan_conv_desc {
   double* in_stats;            /* optional [n][cout][2]: the epilogue accumulates sum / sum of squares of the stored
                                   outputs per (n, c) (zeroed by the call); consumed by uegan_instance_norm_apply.
                                   Needs Ho*Wo >= 128 (tiles within one image). */
+  int32_t y_cls_c;             /* 0, or (with y_mul = 2, y_off = 0) ALL FOUR parity classes of a stride-2 data gradient in
+                                  one launch: cout = 4 * y_cls_c output columns, column (pi*2 + pj) * y_cls_c + c is
+                                  channel c of the output pixel (2a + pi, 2b + pj); w_packed = the four class operands
+                                  of uegan_pack_conv_weight_dgrad back to back (class = pi*2 + pj).  Small-Cin layers
+                                  get 4x wider MMAs, deep ones one grid instead of four quarter-filled ones. */
 } uegan_conv_desc;
 
 int uegan_abi_version(void);
@@ -231,6 +236,19 @@ int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz, int32_t co
 int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tensor* e, int32_t cout, int32_t cin, int32_t cin_total,
                               int32_t cin_first, int32_t k, int32_t pad, float* dw_oihw, const float* alpha_dev,
                               float scale, float* ws, size_t ws_bytes, void* stream);
+/* The same stride-1 weight gradient with the stack read as a SLIDING WINDOW over dz itself (no uegan_dz_hstack pass, no
+ * stack tensor): dz (fp16) must carry a ZERO halo of >= k - 1 pixels; the k * dz.c contiguous values starting k - 1 pixels
+ * left of a pixel are its stack row.  Any Cout <= dz.c with k * dz.c <= 256 columns (tiny heads: dz.c = 8; the 32- and
+ * 64-channel full-resolution decoder layers of G with k = 3), x.c a multiple of 32, k odd, pad = (k-1)/2.
+ * Replaces autograd's aten::convolution_backward (weight half) for models.py:94 (dec3, dec4, dec5) and :174 (heads). */
+int uegan_conv2d_wgrad_zwin_supported(int32_t cout, int32_t dz_c, int32_t dz_halo, int32_t x_c, int32_t k, int32_t stride,
+                                      int32_t dtype);
+int uegan_conv2d_wgrad_zwin(const uegan_tensor* x, const uegan_tensor* dz, int32_t cout, int32_t cin, int32_t cin_total,
+                            int32_t cin_first, int32_t k, int32_t pad, float* dw_oihw, const float* alpha_dev, float scale,
+                            float* ws, size_t ws_bytes, void* stream);
+/* Kernels launched by the calling thread's last uegan_conv2d_wgrad* call: 1 (k-split of one, or atomics) or 2 (GEMM +
+ * ordered reduction of the partial planes).  Launch accounting only. */
+int uegan_wgrad_last_launches(void);
 /* Gradient of the planar heads into a zero-haloed NHWC tensor: mode 0 tanh (models.py:178), 1 sigmoid, 2
  * clamp(tanh(z) + x, -1, 1) with out_nchw = tanh(z) (models.py:35,72). */
 int uegan_head_bwd(const float* dout_nchw, const float* out_nchw, const float* x_nchw, int32_t channels, int32_t mode,
@@ -267,6 +285,17 @@ int uegan_maxpool2x2_bwd(const uegan_tensor* src, const uegan_tensor* dpool, con
 int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
                      float weight, const float* gscale_dev, const uegan_tensor* deep, const uegan_tensor* dx, double* ws,
                      void* stream);
+/* One PerceptualLoss term in ONE pass over the two feature maps (losses.py:22-36: InstanceNorm2d of both taps + MSE): the
+ * five raw moments per (n, c) -- sum x, x^2, y, y^2, xy -- give the (mean, rstd) pairs of both maps, the loss term
+ * (loss_inout += weight * mean((IN(x) - IN(y))^2); accum: one zeroed double of scratch) and the two per-(n, c) sums the
+ * backward pass needs, all in closed form.  ws: 9 * n * c doubles; *mrx_out / *mry_out / *sums_out point into it and feed
+ * uegan_in_mse_bwd_apply.  eps is the InstanceNorm eps in units of the stored values (times x.scale^2 if x carries one). */
+int uegan_in_mse_joint(const uegan_tensor* x, const uegan_tensor* y, float eps, float weight, double* ws, double* accum,
+                       float* loss_inout, float** mrx_out, float** mry_out, double** sums_out, void* stream);
+/* uegan_in_mse_bwd without its statistics pass: `sums` = the per-(n, c) {sum e, sum e * xhat} from uegan_in_mse_joint. */
+int uegan_in_mse_bwd_apply(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
+                           float weight, const float* gscale_dev, const uegan_tensor* deep, const uegan_tensor* dx,
+                           const double* sums, void* stream);
 /* Gradient of uegan_pack_input: NHWC (first 3 channels) -> NCHW fp32 times scale_host[c].  With skip_dout_nchw != NULL the
  * Generator's identity path is added: out = clamp(res + x, -1, 1) (models.py:72) passes skip_dout where |res + x| <= 1. */
 int uegan_unpack_input_grad(const uegan_tensor* dx, const float* scale_host, float* dst_nchw, const float* skip_dout_nchw,

@@ -29,6 +29,9 @@ WGRAD = [
     ("D.d1  3->32 k7s2", 3, 512, 32, 7, 2, 3), ("D.d2 32->64 k7s2", 32, 256, 64, 7, 2, 3),
     ("D.d3 64->128 k7s2", 64, 128, 128, 7, 2, 3), ("D.d4 128->256 k5s2", 128, 64, 256, 5, 2, 3),
     ("D.d5 256->512 k5s2", 256, 32, 512, 5, 2, 3),
+    ("G.dec5.1 32->3 k7s1", 32, 512, 3, 7, 1, 2), ("D.p1 32->1 k7s1", 32, 256, 1, 7, 1, 3),
+    ("D.p2 64->1 k7s1", 64, 128, 1, 7, 1, 3), ("D.p3 128->1 k7s1", 128, 64, 1, 7, 1, 3),
+    ("D.p4 256->1 k5s1", 256, 32, 1, 5, 1, 3), ("D.p5 512->1 k5s1", 512, 16, 1, 5, 1, 3),
 ]
 # stride-2 data gradients: name, cin (dx channels), h of x, cout (dz channels), k, launches per step
 DGRAD = [
@@ -76,16 +79,18 @@ def run_wgrad():
         pad = (k - 1) // 2
         g = torch.Generator(device=dev).manual_seed(7)
         cx = 8 if cin == 3 else cin
-        cdz = (cout + 31) // 32 * 32
+        zw = stride == 1 and k > 1          # dgrad operands: zero halo of k - 1 (the sliding-window stack path)
+        cdz = 8 if cout <= 8 else (cout + 31) // 32 * 32
+        zh = k - 1 if zw else 0
         halo = max(pad, 1)
         # correctness at n = 2 on a reduced extent (same channel structure, same code path)
         hs = min(h, 64)
         x = torch.randn(2, cin, hs, hs, device=dev, generator=g).half().float()
         ho = (hs + 2 * pad - k) // stride + 1
         dz = torch.randn(2, cout, ho, ho, device=dev, generator=g).half().float()
-        xt, dzt = fill(x, cx, halo, True), fill(dz, cdz, 0, False)
+        xt, dzt = fill(x, cx, halo, True), fill(dz, cdz, zh, False)
         dw = torch.zeros(cout, cin, k, k, device=dev)
-        K.conv_wgrad(xt, dzt, dw, k, stride, pad)
+        K.conv_wgrad(xt, dzt, dw, k, stride, pad, dz_zero_halo=zw)
         xpad = F.pad(x, (pad,) * 4, mode="reflect") if pad else x
         ref = torch.nn.grad.conv2d_weight(xpad.double(), (cout, cin, k, k), dz.double(), stride=stride)
         err = relerr(dw, ref)
@@ -93,9 +98,10 @@ def run_wgrad():
         # timing at the step's shape
         xb = K.NHWC(B, h, h, cx, halo, L.F16, dev); xb.buf.normal_()
         hob = (h + 2 * pad - k) // stride + 1
-        dzb = K.NHWC(B, hob, hob, cdz, 0, L.F16, dev); dzb.buf.normal_()
+        dzb = K.NHWC(B, hob, hob, cdz, zh, L.F16, dev, zero=True)
+        dzb.padded_view()[:, zh:zh + hob, zh:zh + hob, :].normal_()
         dwb = torch.zeros(cout, cin, k, k, device=dev)
-        tmin, tmed = timeit(lambda: K.conv_wgrad(xb, dzb, dwb, k, stride, pad))
+        tmin, tmed = timeit(lambda: K.conv_wgrad(xb, dzb, dwb, k, stride, pad, dz_zero_halo=zw))
         gf = 2.0 * B * hob * hob * cout * cin * k * k / 1e9
         tot += tmed * per_step
         print(f"wgrad {name:24s} err {err:.2e}  min {tmin:.3f} med {tmed:.3f} ms  {gf / tmed:7.1f} TF/s  x{per_step} = {tmed * per_step:.3f} ms", flush=True)

@@ -210,6 +210,50 @@ def test_wgrad_hstack(K, case):
     assert err < 1e-4
 
 
+ZWIN_CASES = [
+    # n, cin, h, w, cout, dz stored channels, k
+    (2, 32, 24, 40, 3, 8, 7),      # G's last conv: dz is the 8-channel head gradient
+    (1, 32, 19, 29, 1, 8, 7),      # ragged extents, D head
+    (2, 256, 12, 16, 1, 8, 5),     # k5 head, four channel chunks
+    (1, 512, 8, 8, 1, 8, 5),       # deepest head
+    (2, 32, 40, 24, 32, 32, 3),    # dec5.0: N = 96
+    (2, 64, 16, 32, 32, 32, 3),    # dec4
+    (1, 128, 24, 16, 64, 64, 3),   # dec3: N = 192, two slices of channel chunks
+]
+
+
+@pytest.mark.parametrize("case", ZWIN_CASES)
+def test_wgrad_zwin_f16(K, case):
+    """Weight gradient with the horizontally stacked gradient read as a sliding TMA window over the zero-haloed dz
+    (uegan_conv2d_wgrad_zwin) == torch's conv2d weight gradient on the same fp16-quantised operands; the alpha / scale
+    factors and a per-tensor scale on both operands ride along."""
+    from uegan_b200 import _lib as L
+    n, cin, h, w, cout, cdz, k = case
+    g = torch.Generator(device="cuda").manual_seed(321 + cin + cout)
+    pad = (k - 1) // 2
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g).half().float()
+    dzv = torch.randn(n, cout, h, w, device="cuda", generator=g).half().float()
+    wr = torch.zeros(cout, cin, k, k, device="cuda", dtype=torch.double, requires_grad=True)
+    F.conv2d(F.pad(x.double(), (pad,) * 4, mode="reflect"), wr).backward(dzv.double())
+    sx, sz = torch.tensor([4.0], device="cuda"), torch.tensor([0.25], device="cuda")
+    xt = K.NHWC(n, h, w, cin, pad + 1, L.F16, "cuda", zero=True, scale=sx)  # halo > pad exercises the patch offset
+    xt.padded_view()[...] = (F.pad(x, (pad + 1,) * 4, mode="reflect") * 4.0).permute(0, 2, 3, 1).half()
+    dzt = K.NHWC(n, h, w, cdz, k - 1, L.F16, "cuda", zero=True, scale=sz)
+    dzt.padded_view()[:, k - 1:k - 1 + h, k - 1:k - 1 + w, :cout] = (dzv * 0.25).permute(0, 2, 3, 1).half()
+    assert K.zwin_ok(cout, xt, dzt, k)
+    dw = torch.full((cout, cin, k, k), 1.0, device="cuda")  # accumulates
+    alpha = torch.tensor([0.5], device="cuda")
+    K.conv_wgrad(xt, dzt, dw, k, 1, pad, alpha=alpha, scale=2.0, dz_zero_halo=True)
+    assert K.device_error() == 0
+    err = relerr(dw - 1.0, wr.grad)
+    print(f"zwin wgrad {case}: rel err {err:.3e}")
+    assert err < 1e-4
+    # bit-reproducible, and equal to the generic path within fp32 summation order
+    dw2 = torch.full((cout, cin, k, k), 1.0, device="cuda")
+    K.conv_wgrad(xt, dzt, dw2, k, 1, pad, alpha=alpha, scale=2.0, dz_zero_halo=True)
+    assert torch.equal(dw, dw2)
+
+
 @pytest.mark.parametrize("shape", [(2, 32, 24, 40, 3), (2, 64, 12, 20, 1), (1, 32, 8, 7, 3), (2, 128, 9, 33, 2)])
 def test_fold_inplace(K, shape):
     """In-place reflect-pad adjoint == grad_combine(src_a) == autograd of F.pad(reflect); halo zeroed."""

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libuegan_sm100.so")
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 PAD_ZERO, PAD_REFLECT = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class UeganError(RuntimeError):
@@ -36,7 +36,7 @@ class ConvDesc(C.Structure):
                 ("stride", C.c_int32), ("pad", C.c_int32), ("act", C.c_int32), ("w_packed", C.c_void_p),
                 ("w_scale", C.c_void_p), ("bias", C.c_void_p), ("alpha", C.c_void_p), ("mul", C.POINTER(Tensor)), ("out_nchw", C.c_void_p),
                 ("residual_nchw", C.c_void_p), ("aux_nchw", C.c_void_p), ("y_mul", C.c_int32), ("y_off_h", C.c_int32), ("y_off_w", C.c_int32),
-                ("mask", C.POINTER(Tensor)), ("mask_act", C.c_int32), ("in_stats", C.c_void_p)]
+                ("mask", C.POINTER(Tensor)), ("mask_act", C.c_int32), ("in_stats", C.c_void_p), ("y_cls_c", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/uegan_sm100.h declares
@@ -86,6 +86,10 @@ SYMBOLS = {
                            [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uegan_conv2d_wgrad_hstack": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor)] + [C.c_int32] * 6 +
                                   [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "uegan_wgrad_last_launches": (C.c_int, []),
+    "uegan_conv2d_wgrad_zwin_supported": (C.c_int, [C.c_int32] * 7),
+    "uegan_conv2d_wgrad_zwin": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor)] + [C.c_int32] * 6 +
+                                [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
     "uegan_fold_inplace": (C.c_int, [C.POINTER(Tensor), C.c_void_p]),
     "uegan_dz_hstack": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.POINTER(Tensor), C.c_void_p]),
     "uegan_head_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Tensor),
@@ -101,6 +105,11 @@ SYMBOLS = {
     "uegan_maxpool2x2_bwd": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
     "uegan_in_mse_bwd": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p, C.c_float,
                                    C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
+    "uegan_in_mse_joint": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.c_void_p]),
+    "uegan_in_mse_bwd_apply": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p, C.c_float,
+                                         C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.c_void_p]),
     "uegan_unpack_input_grad": (C.c_int, [C.POINTER(Tensor), C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
     "uegan_upsample2x": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_int32, C.c_void_p]),

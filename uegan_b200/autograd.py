@@ -212,11 +212,12 @@ def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
             return sink[pname], True
         return (_zeros_like(param) if zero else torch.empty_like(param)), False
 
-    def wgrad(name, conv, xin, dz, k, stride, pad, cin_first=0, cin=None, bias_from=None):
+    def wgrad(name, conv, xin, dz, k, stride, pad, cin_first=0, cin=None, bias_from=None, zero_halo=False):
+        """zero_halo: dz's halo holds zeros (every dgrad operand here), which the sliding-window stack path needs."""
         if dry:
             return
         gw, direct = gbuf(name + ".weight", conv.weight)
-        K.conv_wgrad(xin, dz, gw, k, stride, pad, cin_first=cin_first, cin=cin)
+        K.conv_wgrad(xin, dz, gw, k, stride, pad, cin_first=cin_first, cin=cin, dz_zero_halo=zero_halo)
         grads[name + ".weight"] = None if direct else gw
         if bias_from is not None and conv.bias is not None:
             gb, direct = gbuf(name + ".bias", conv.bias, zero=False)
@@ -232,6 +233,11 @@ def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
     c51 = G.dec5[1].conv
     if dry:
         pass
+    elif K.zwin_ok(3, P["t"], dz5, 7):
+        # the horizontal taps are a sliding window over the zero-haloed dz5 itself: only the 7 vertical taps are enumerated
+        gw, direct = gbuf("dec5.1.main.1.weight", c51.weight)
+        K.conv_wgrad(P["t"], dz5, gw, 7, 1, 3, dz_zero_halo=True)
+        grads["dec5.1.main.1.weight"] = None if direct else gw
     elif K.hstack_ok(3, d, 7):
         # horizontal taps unrolled into the gradient's channels: the wgrad keeps only the 7 vertical taps
         e5 = S("dz5e", h, w + 6, 32, 0, share=dz5)
@@ -257,7 +263,7 @@ def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
         K.grad_combine(dt, d, src_a=dxp, pad_a=3)
     # ---- dec5.0 (no activation)
     c50 = G.dec5[0].conv
-    wgrad("dec5.0.main.1", c50, P["y4m"], dt, 3, 1, 1, bias_from=dt)
+    wgrad("dec5.0.main.1", c50, P["y4m"], dt, 3, 1, 1, bias_from=dt, zero_halo=True)
     dxp2 = S("dxp_y4m", h + 2, w + 2, d)
     K.conv_dgrad(dt, c50.weight, 3, 1, dxp2, cache, "dec5.0", w_scale=wsc("dec5.0", c50))
     # y4m = y4 * x1 ;  y4 = act(z4)
@@ -274,7 +280,7 @@ def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
         ch = P["u"][i].c
         hh, ww = P["y"][i].h, P["y"][i].w
         dec, up, ga = decs[i].conv, ups[i].conv, gas[i].fuse[0]
-        wgrad(f"dec{i+1}.main.1", dec, P["cat"][i], dz, 3, 1, 1, bias_from=dz)
+        wgrad(f"dec{i+1}.main.1", dec, P["cat"][i], dz, 3, 1, 1, bias_from=dz, zero_halo=True)
         dxpc = S(f"dxp_cat{i}", hh + 2, ww + 2, 2 * ch)
         K.conv_dgrad(dz, dec.weight, 3, 1, dxpc, cache, f"dec{i+1}", w_scale=wsc(f"dec{i+1}", dec))
         if _FOLD_INPLACE:
@@ -501,7 +507,9 @@ def _d_backward_pass(D, x, dpreds, ws, need_dx, need_w=True):
         K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzp)
         if need_w:
             gw, direct = gbuf(f"d{i}_pred.0.1.weight", head.weight)
-            if K.hstack_ok(1, ds.c, k):
+            if K.zwin_ok(1, ds, dzp, k):
+                K.conv_wgrad(ds, dzp, gw, k, 1, pad, dz_zero_halo=True)
+            elif K.hstack_ok(1, ds.c, k):
                 ep = S(f"dzpe{i}", ds.h, ds.w + k - 1, 32, 0, share=dzp)
                 K.dz_hstack(dzp, 1, k, ep)
                 K.conv_wgrad_hstack(ds, ep, gw, k, pad)

@@ -760,9 +760,9 @@ int uegan_maxpool2x2_bwd(const uegan_tensor* src, const uegan_tensor* dpool, con
   return 0;
 }
 
-int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
-                     float weight, const float* gscale_dev, const uegan_tensor* deep, const uegan_tensor* dx, double* ws,
-                     void* stream) {
+static int in_mse_bwd_impl(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
+                           float weight, const float* gscale_dev, const uegan_tensor* deep, const uegan_tensor* dx, double* ws,
+                           bool sums_ready, void* stream) {
   UEGAN_CHECK(x && y && dx && mean_rstd_x && mean_rstd_y && ws, "in_mse_bwd: null pointer");
   UEGAN_CHECK(x->dtype == UEGAN_F16 && y->dtype == UEGAN_F16 && dx->dtype == UEGAN_F16 && x->c % 8 == 0 && x->c <= 1024,
               "in_mse_bwd: expects fp16 features and a (loss-scaled) fp16 gradient");
@@ -775,10 +775,10 @@ int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* 
   if (deep) gdeep = geom(*deep);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nc = gx.n * gx.c;
-  UEGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * nc, st));
   const long long npix = (long long)gx.h * gx.w;
   UEGAN_CHECK(256 % (gx.c / 8) == 0, "in_mse_bwd: unsupported channel count %d", gx.c);
-  {
+  if (!sums_ready) {
+    UEGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * nc, st));
     TapBwdStatsOp<__half> op{gx, gy, mean_rstd_x, mean_rstd_y, ws};
     launch_strip_reduce<__half, 2>(op, gx.c, gx.n, gx.h, gx.w, st);
   }
@@ -791,6 +791,18 @@ int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* 
   if (launch_affine_apply<__half, __half>(q, st)) return -1;
   UEGAN_CUDA(cudaGetLastError());
   return 0;
+}
+
+int uegan_in_mse_bwd(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
+                     float weight, const float* gscale_dev, const uegan_tensor* deep, const uegan_tensor* dx, double* ws,
+                     void* stream) {
+  return in_mse_bwd_impl(x, y, mean_rstd_x, mean_rstd_y, weight, gscale_dev, deep, dx, ws, false, stream);
+}
+
+int uegan_in_mse_bwd_apply(const uegan_tensor* x, const uegan_tensor* y, const float* mean_rstd_x, const float* mean_rstd_y,
+                           float weight, const float* gscale_dev, const uegan_tensor* deep, const uegan_tensor* dx,
+                           const double* sums, void* stream) {
+  return in_mse_bwd_impl(x, y, mean_rstd_x, mean_rstd_y, weight, gscale_dev, deep, dx, const_cast<double*>(sums), true, stream);
 }
 
 int uegan_unpack_input_grad(const uegan_tensor* dx, const float* scale_host, float* dst_nchw, const float* skip_dout_nchw,

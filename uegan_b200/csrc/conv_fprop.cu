@@ -66,6 +66,10 @@ struct ConvParams {
   float* aux_nchw;  // optional: activation before the residual/clamp
   unsigned int* err_sink;  // host-mapped watchdog word
   double* in_stats;        // optional [Nimg][cout][2] sum / sum-of-squares of the stored outputs (InstanceNorm)
+  // merged parity classes of a stride-2 data gradient (uegan_conv_desc.y_cls_c): column = (class, channel), class
+  // (pi, pj) lands at output pixel (2a + pi, 2b + pj); cls_row / cls_pix = element strides of ONE output row / pixel
+  int cls_c, cls_h, cls_w;
+  long long cls_row, cls_pix;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -124,6 +128,13 @@ __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t tadd
     tmem_ld_wait();
     const int col0 = colbase + c0;
     if (col0 >= p.cout) continue;  // warp-uniform
+    long long oc = o + c0;
+    bool vc = valid;
+    if (p.cls_c) {
+      const int cls = col0 / p.cls_c, ch = col0 - cls * p.cls_c, pi = cls >> 1, pj = cls & 1;
+      oc = o - colbase + pi * p.cls_row + pj * p.cls_pix + ch;
+      vc = valid && (2 * mk_h + pi < p.cls_h) && (2 * mk_w + pj < p.cls_w);
+    }
     if (p.in_stats) {
       // per-(n, c) sum and sum of squares over this warp's 32 rows (all rows of a tile share n when tn == 1):
       // recursive-halving butterfly, 31 shuffles for 32 values; lane L ends with the total of element L.
@@ -150,7 +161,7 @@ __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t tadd
       }
       stat_slice[(c0 >> 5) * 32 + (threadIdx.x & 31)] += a[0];  // private to this lane; flushed when n changes
     }
-    if (!valid) continue;
+    if (!vc) continue;
     float v[16];
     if (p.bias) {
       const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
@@ -240,11 +251,11 @@ __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t tadd
           pk[i] = *reinterpret_cast<uint32_t*>(&h);
         }
       }
-      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + o + c0);
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + oc);
       op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     } else {
-      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o + c0);
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + oc);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         op[i] = make_float4(round_tf32(v[4 * i]), round_tf32(v[4 * i + 1]), round_tf32(v[4 * i + 2]),
@@ -655,7 +666,8 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
       if (p.Wo > wv) p.Wo = wv;
     }
     UEGAN_CHECK(d.cout % 16 == 0, "conv: NHWC output needs cout %% 16 == 0 (got %d)", d.cout);
-    UEGAN_CHECK(d.y_c_off >= 0 && d.y_c_off + d.cout <= y.c && d.y_c_off % 8 == 0, "conv: bad channel slice");
+    UEGAN_CHECK(d.y_c_off >= 0 && d.y_c_off + (d.y_cls_c > 0 ? d.y_cls_c : d.cout) <= y.c && d.y_c_off % 8 == 0,
+                "conv: bad channel slice");
     UEGAN_CHECK((y.c * dtype_size(y.dtype)) % 16 == 0, "conv: y.c misaligned");
     UEGAN_CHECK(dtype_ok(y.dtype), "conv: bad y dtype %d", y.dtype);
     p.out_kind = y.dtype;
@@ -669,6 +681,13 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
     p.out_img = t_hp(y) * p.out_row;
     const long long off = (long long)(y.halo + d.y_off_h) * p.out_row + (long long)(y.halo + d.y_off_w) * p.out_pix +
                           d.y_c_off;
+    if (d.y_cls_c > 0) {
+      UEGAN_CHECK(ymul == 2 && d.y_off_h == 0 && d.y_off_w == 0 && d.cout == 4 * d.y_cls_c && d.y_cls_c % 16 == 0 &&
+                      d.y_c_off + d.y_cls_c <= y.c && !d.mask && !d.mul && !d.bias && !d.in_stats,
+                  "conv: merged parity classes need y_mul 2, no offsets, cout = 4 * y_cls_c, no bias / mask / mul / stats");
+      p.cls_c = d.y_cls_c; p.cls_h = y.h; p.cls_w = y.w;
+      p.cls_row = p.out_row; p.cls_pix = p.out_pix;
+    }
     p.out_pix *= ymul;
     p.out_row *= ymul;
     p.out = static_cast<uint8_t*>(y.data) + off * dtype_size(y.dtype);

@@ -67,11 +67,12 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(float* __restrict__ d
   __shared__ float sh[256];
   const int L = 1 << lanes_log2, E = 256 >> lanes_log2;
   const int e = threadIdx.x & (E - 1), l = threadIdx.x >> (8 - lanes_log2);
-  const long long i = (long long)blockIdx.x * E + e;
+  // (32-bit index arithmetic: 64-bit divisions here cost more than the loads -- 130 us for D's d5, r2l)
+  const unsigned i = blockIdx.x * (unsigned)E + (unsigned)e;
   float acc = 0.f;
   bool own = false;
-  if (i < dw_numel) {
-    const int c = (int)((i / kk) % cin_total);
+  if (i < (unsigned)dw_numel) {
+    const int c = (int)((i / (unsigned)kk) % (unsigned)cin_total);
     own = c >= cin_first && c < cin_first + cin;
     if (own) {
       const float* src = partial + i;
@@ -278,15 +279,22 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
 
 // Deterministic mode (ws != NULL): clamp the k-split to what the workspace holds; after the GEMM launch, reduce the
 // non-empty slices in order.
-static int wg_plan_split(int* ksplit, long long dw_numel, float* ws, size_t ws_bytes) {
-  if (!ws) return 0;
-  const long long fit = (long long)(ws_bytes / (sizeof(float) * (size_t)dw_numel));
-  UEGAN_CHECK(fit >= 1, "conv2d_wgrad: workspace of %zu bytes cannot hold one %lld-element partial", ws_bytes, dw_numel);
-  if (*ksplit > fit) *ksplit = (int)fit;
+// A launch whose k-split ends up 1 needs neither: every dW element then has exactly ONE contributing thread, so the
+// accumulation into dW itself (atomicAdd, *ws = NULL) is already reproducible.
+static int wg_plan_split(int* ksplit, long long dw_numel, float** ws, size_t ws_bytes) {
+  if (*ws) {
+    UEGAN_CHECK(dw_numel < (1ll << 31), "conv2d_wgrad: weight tensor too large");
+    const long long fit = (long long)(ws_bytes / (sizeof(float) * (size_t)dw_numel));
+    UEGAN_CHECK(fit >= 1, "conv2d_wgrad: workspace of %zu bytes cannot hold one %lld-element partial", ws_bytes, dw_numel);
+    if (*ksplit > fit) *ksplit = (int)fit;
+    if (*ksplit == 1) *ws = nullptr;
+  }
   return 0;
 }
+static thread_local int g_wgrad_launches = 0;  // kernels launched by the last weight-gradient call of this thread
 static int wg_reduce(float* dw, const float* ws, long long dw_numel, int ksplit, int total_ktiles, int cin_total,
                      int cin_first, int cin, int k, cudaStream_t st) {
+  g_wgrad_launches = ws ? 2 : 1;
   if (!ws) return 0;
   const int per = (total_ktiles + ksplit - 1) / ksplit;
   const int slices = (total_ktiles + per - 1) / per;  // slices beyond this one own no k-tile and write nothing
@@ -377,13 +385,15 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   if (p.num_stages > 4) p.num_stages = 4;
   UEGAN_CHECK(p.num_stages >= 2, "conv2d_wgrad: stage too large");
   const int groups = p.taps * p.m_tiles * p.n_chunks;
-  int ksplit = (2 * num_sms()) / groups;  // two full waves of single-CTA SMs (rounding UP left a third, mostly empty wave)
+  // two full waves of single-CTA SMs (rounding UP left a third, mostly empty wave); launches that fill half the SMs by
+  // themselves are not split at all (no partial planes, no reduction pass)
+  int ksplit = 2 * groups >= num_sms() ? 1 : (2 * num_sms()) / groups;
   // every CTA pays a fixed prologue + a 128 x N epilogue (and one more partial plane for the reduction): keep >= 16
   // K stages per CTA even when that leaves SMs idle (deep layers: few pixels, large dW)
   if (ksplit > p.total_ktiles / 16) ksplit = p.total_ktiles / 16;
   if (ksplit < 1) ksplit = 1;
   p.dw_numel = (long long)cout * cin_total * k * k;
-  if (wg_plan_split(&ksplit, p.dw_numel, ws, ws_bytes)) return -1;
+  if (wg_plan_split(&ksplit, p.dw_numel, &ws, ws_bytes)) return -1;
   p.ksplit = ksplit;
   p.dw = dw_oihw;
   p.partial = ws;
@@ -456,6 +466,9 @@ struct WgradPatchParams {
   // accumulator per (chunk, g), D[(r, c)][(s, o)] -> dW[o][c][r][s].  rk = taps enumerated by the accumulator index
   // besides the groups: k (horizontal mode: filter rows) or 1.
   int vert, rk, lbo_bytes;
+  // columns of D: n_cols of them (a multiple of 16), column j = (j / col_c, j % col_c) = (horizontal tap, output channel);
+  // col_rev: the tap index runs backwards (the stack is a sliding WINDOW over dz itself, see uegan_conv2d_wgrad_zwin)
+  int n_cols, col_c, col_rev;
   float* dw;
   float* partial;
   long long dw_numel;
@@ -475,15 +488,15 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   constexpr int TPG = 128 / CB;            // taps per M = 128 group (4 tf32, 2 fp16)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full_bar[4];
-  __shared__ __align__(8) uint64_t empty_bar[4];
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t tmem_base_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (p.total_ktiles + p.ksplit - 1) / p.ksplit;
   const int kt0 = blockIdx.x * per, kt1 = min(kt0 + per, p.total_ktiles);
   const int acc0 = blockIdx.y * p.acc_per_cta, acc1 = min(acc0 + p.acc_per_cta, p.acc_total);
-  const int N = p.n_boxes * CB;
+  const int N = p.n_cols;
   // accumulator index a -> (chunk, r, g):  a = (chunk * k + r) * kgroups + g.  The chunks this CTA touches:
   const int ch_lo = acc0 / (p.rk * p.kgroups), ch_hi = (acc1 - 1) / (p.rk * p.kgroups);
   const int nch = ch_hi - ch_lo + 1;
@@ -590,8 +603,9 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int j = c0 + i;  // column (s, o) of the stacked gradient
-              if (j < p.k * p.cout) {
-                const int ss = j / p.cout, o = j - ss * p.cout;
+              const int sj = j / p.col_c, o = j - sj * p.col_c;
+              if (sj < p.k && o < p.cout) {
+                const int ss = p.col_rev ? p.k - 1 - sj : sj;
                 wg_publish(p.dw, p.partial, p.dw_numel, ((long long)o * p.cin_total + p.cin_first + c) * kk + s_ * p.k + ss,
                            __uint_as_float(rr[i]) * sc);
               }
@@ -649,6 +663,7 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
   p.patch_bytes = (p.ph * p.pw * 128 + 1023) / 1024 * 1024;
   p.dz_bytes = p.n_boxes * 64 * 128;
   p.vert = 0; p.rk = k; p.lbo_bytes = 128;
+  p.n_cols = N; p.col_c = cout; p.col_rev = 0;
   p.acc_total = p.chunks * k * p.kgroups;
   p.acc_per_cta = 512 / N;
   // a CTA's accumulators should span as few channel chunks as possible: align the slice to whole chunks when it can
@@ -669,7 +684,7 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
   if (ksplit > p.total_ktiles) ksplit = p.total_ktiles;
   if (ksplit < 1) ksplit = 1;
   p.dw_numel = (long long)cout * cin_total * k * k;
-  if (wg_plan_split(&ksplit, p.dw_numel, ws, ws_bytes)) return -1;
+  if (wg_plan_split(&ksplit, p.dw_numel, &ws, ws_bytes)) return -1;
   p.ksplit = ksplit;
   p.off = x->halo - pad;
   p.cout = cout; p.cin = cin; p.cin_total = cin_total; p.cin_first = cin_first;
@@ -733,6 +748,7 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
   p.kgroups = (k + TPG - 1) / TPG;
   p.chunks = (cin + CB - 1) / CB;
   p.vert = 1; p.rk = 1;
+  p.n_cols = CB; p.col_c = cout; p.col_rev = 0;
   p.pw = 8;
   p.ph = 8 + TPG * p.kgroups - 1;     // rows 0 .. 7 + (TPG*kgroups - 1): M-group j of the last group stays inside
   p.lbo_bytes = p.pw * 128;           // M-group stride = one patch row
@@ -759,7 +775,7 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
   if (ksplit > p.total_ktiles) ksplit = p.total_ktiles;
   if (ksplit < 1) ksplit = 1;
   p.dw_numel = (long long)cout * cin_total * k * k;
-  if (wg_plan_split(&ksplit, p.dw_numel, ws, ws_bytes)) return -1;
+  if (wg_plan_split(&ksplit, p.dw_numel, &ws, ws_bytes)) return -1;
   p.ksplit = ksplit;
   p.off = x->halo - pad;
   p.cout = cout; p.cin = cin; p.cin_total = cin_total; p.cin_first = cin_first;
@@ -796,3 +812,98 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
   return wg_reduce(dw_oihw, ws, p.dw_numel, p.ksplit, p.total_ktiles, cin_total, cin_first, cin, k,
                    static_cast<cudaStream_t>(stream));
 }
+
+// Weight gradient of a stride-1 conv from a SLIDING WINDOW over dz itself (no materialised stack): with a zero halo of
+// >= k - 1 pixels around dz, the k * Cs contiguous values that start at pixel q - (k - 1) of a dz row ARE the stack row
+//   E[q][(s', o)] = dz[q - (k - 1) + s'][o] = dz[q - s][o],  s = k - 1 - s',  q in [0, W + k - 1)
+// (Cs = stored channels of dz), so one overlapping-stride TMA map delivers the N operand of the vertical patch mode:
+//   D[(r, c)][(s', o)] = sum_{y, q} xpad[y + r][q][c] * E[y][q][(s', o)] = dW[o][c][r][k - 1 - s'].
+// Only the k VERTICAL taps are enumerated on the M side (k x fewer MMAs than one accumulator per (r, s), each k x wider:
+// Cout = 32, k = 3 runs N = 96 instead of 6 MMAs of N = 64 per K step).  Needs k * Cs <= 256 columns.
+extern "C" int uegan_conv2d_wgrad_zwin_supported(int32_t cout, int32_t dz_c, int32_t dz_halo, int32_t x_c, int32_t k,
+                                                 int32_t stride, int32_t dtype) {
+  const int ncols = (k * dz_c + 15) / 16 * 16;
+  return dtype == UEGAN_F16 && stride == 1 && k >= 3 && k <= 7 && (k & 1) && dz_halo >= k - 1 && dz_c % 8 == 0 &&
+         cout <= dz_c && ncols <= 256 && x_c % 32 == 0;
+}
+
+extern "C" int uegan_conv2d_wgrad_zwin(const uegan_tensor* x, const uegan_tensor* dz, int32_t cout, int32_t cin,
+                                       int32_t cin_total, int32_t cin_first, int32_t k, int32_t pad, float* dw_oihw,
+                                       const float* alpha_dev, float scale, float* ws, size_t ws_bytes, void* stream) {
+  UEGAN_CHECK(x && dz && x->data && dz->data && dw_oihw, "conv2d_wgrad_zwin: null pointer");
+  UEGAN_CHECK(x->dtype == UEGAN_F16 && dz->dtype == UEGAN_F16, "conv2d_wgrad_zwin: fp16 tensors only");
+  UEGAN_CHECK(uegan_conv2d_wgrad_zwin_supported(cout, dz->c, dz->halo, x->c, k, 1, x->dtype),
+              "conv2d_wgrad_zwin: unsupported shape (cout %d, dz.c %d, dz.halo %d, x.c %d, k %d)", cout, dz->c, dz->halo, x->c, k);
+  UEGAN_CHECK(pad == (k - 1) / 2 && pad <= x->halo, "conv2d_wgrad_zwin: pad %d (k %d, x.halo %d)", pad, k, x->halo);
+  UEGAN_CHECK(dz->n == x->n && dz->h == x->h && dz->w == x->w, "conv2d_wgrad_zwin: dz is %dx%dx%d, expected %dx%dx%d", dz->n,
+              dz->h, dz->w, x->n, x->h, x->w);
+  UEGAN_CHECK(cin <= x->c && cin_first + cin <= cin_total, "conv2d_wgrad_zwin: channel mismatch");
+  constexpr int es = 2, CB = 64, TPG = 2;
+  WgradPatchParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_cols = (k * dz->c + 15) / 16 * 16;
+  p.n_boxes = (p.n_cols + CB - 1) / CB;
+  p.col_c = dz->c; p.col_rev = 1;
+  p.k = k;
+  p.kgroups = (k + TPG - 1) / TPG;
+  p.chunks = (cin + CB - 1) / CB;
+  p.vert = 1; p.rk = 1;
+  p.pw = 8;
+  p.ph = 8 + TPG * p.kgroups - 1;
+  p.lbo_bytes = p.pw * 128;
+  p.patch_bytes = p.ph * p.pw * 128;
+  p.dz_bytes = p.n_boxes * 64 * 128;
+  p.acc_total = p.chunks * p.kgroups;
+  const int N = p.n_cols;
+  int nch_max = ((200 * 1024) / 3 - p.dz_bytes) / p.patch_bytes;
+  if (nch_max > (512 / N) / p.kgroups) nch_max = (512 / N) / p.kgroups;
+  UEGAN_CHECK(nch_max >= 1, "conv2d_wgrad_zwin: %d columns x %d tap groups do not fit the accumulator memory", N, p.kgroups);
+  const int slices = (p.chunks + nch_max - 1) / nch_max;
+  const int nch = (p.chunks + slices - 1) / slices;
+  p.acc_per_cta = nch * p.kgroups;
+  p.stage_bytes = nch * p.patch_bytes + p.dz_bytes;
+  p.num_stages = (200 * 1024) / p.stage_bytes;
+  if (p.num_stages > 6) p.num_stages = 6;
+  UEGAN_CHECK(p.num_stages >= 2, "conv2d_wgrad_zwin: stage too large");
+  const int We = dz->w + k - 1;
+  p.tiles_w = (We + 7) / 8;
+  p.tiles_h = (dz->h + 7) / 8;
+  p.nimg = x->n;
+  p.total_ktiles = p.tiles_w * p.tiles_h * p.nimg;
+  int ksplit = 2 * slices >= num_sms() ? 1 : (2 * num_sms()) / slices;
+  if (ksplit > p.total_ktiles / 16) ksplit = p.total_ktiles / 16;
+  if (ksplit < 1) ksplit = 1;
+  p.dw_numel = (long long)cout * cin_total * k * k;
+  if (wg_plan_split(&ksplit, p.dw_numel, &ws, ws_bytes)) return -1;
+  p.ksplit = ksplit;
+  p.off = x->halo - pad;
+  p.cout = cout; p.cin = cin; p.cin_total = cin_total; p.cin_first = cin_first;
+  p.dw = dw_oihw; p.partial = ws; p.alpha = alpha_dev; p.scale = scale;
+  p.sx = x->scale; p.sdz = dz->scale;
+  p.err_sink = error_sink_device();
+  CUtensorMap tmX, tmZ;
+  {  // x, padded extent: {c, w, h, n}
+    const uint64_t pix = (uint64_t)x->c * es, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
+    uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)t_wp(*x), (uint64_t)t_hp(*x), (uint64_t)x->n};
+    uint64_t strides[3] = {pix, row, img};
+    uint32_t box[4] = {(uint32_t)CB, (uint32_t)p.pw, (uint32_t)p.ph, 1u};
+    if (encode_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x->data, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+  }
+  {  // the window map over dz: {window element, q, y, n}, q = 0 is the window that starts k - 1 pixels left of the interior
+    const uint64_t pix = (uint64_t)dz->c * es, row = (uint64_t)t_wp(*dz) * pix, img = (uint64_t)t_hp(*dz) * row;
+    uint8_t* base = static_cast<uint8_t*>(dz->data) + (uint64_t)dz->halo * row + (uint64_t)(dz->halo - (k - 1)) * pix;
+    uint64_t dims[4] = {(uint64_t)p.n_boxes * CB, (uint64_t)We, (uint64_t)dz->h, (uint64_t)dz->n};
+    uint64_t strides[3] = {pix, row, img};
+    uint32_t box[4] = {(uint32_t)CB, 8u, 8u, 1u};
+    if (encode_tiled(&tmZ, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+  }
+  const int smem_bytes = p.num_stages * p.stage_bytes + 1024;
+  dim3 grid((unsigned)p.ksplit, (unsigned)slices, 1u);
+  if (wgrad_patch_set_attr<1>()) return -1;
+  conv_wgrad_patch_kernel<1><<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmX, tmZ, p);
+  UEGAN_CUDA(cudaGetLastError());
+  return wg_reduce(dw_oihw, ws, p.dw_numel, p.ksplit, p.total_ktiles, cin_total, cin_first, cin, k,
+                   static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int uegan_wgrad_last_launches(void) { return uegan::g_wgrad_launches; }

@@ -147,6 +147,77 @@ struct InMseOp {
   }
   __device__ void flush(int n, int c, const float (&t)[1]) const { atomicAdd(accum, (double)t[0]); }
 };
+// ------------------------------------------------------------------------------------------
+// VGG tap, joint pass: the five raw moments per (n, c) of the two feature maps -- sum x, sum x^2, sum y, sum y^2, sum xy --
+// in ONE read of x and y.  Everything the tap needs follows in closed form (in_joint_finalize_kernel): the InstanceNorm
+// statistics of both maps, the MSE of the normalised maps, and the two per-(n, c) sums of the backward pass.  Replaces
+// four passes (statistics of x, of y, the MSE pass, the backward statistics pass: 6 tensor reads) by one (2 reads).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct JointMomentsOp {
+  TGeom x, y;
+  double* mom;
+  __device__ void prep(int, int) {}
+  __device__ void acc(int n, int yy, int xx, int c, float (&a)[Vec<T>::N][5]) const {
+    float xv[Vec<T>::N], yv[Vec<T>::N];
+    Vec<T>::load(static_cast<const T*>(x.data) + toff(x, n, yy, xx, c), xv);
+    Vec<T>::load(static_cast<const T*>(y.data) + toff(y, n, yy, xx, c), yv);
+#pragma unroll
+    for (int k = 0; k < Vec<T>::N; ++k) {
+      a[k][0] += xv[k];
+      a[k][1] = fmaf(xv[k], xv[k], a[k][1]);
+      a[k][2] += yv[k];
+      a[k][3] = fmaf(yv[k], yv[k], a[k][3]);
+      a[k][4] = fmaf(xv[k], yv[k], a[k][4]);
+    }
+  }
+  __device__ void flush(int n, int c, const float (&t)[5]) const {
+    double* m = mom + ((long long)n * x.c + c) * 5;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) atomicAdd(m + j, (double)t[j]);
+  }
+};
+// One thread per (n, c).  With N pixels and the fp32-rounded (mean, rstd) pairs the apply pass will use (mx, rx, my, ry):
+//   sum xh     = rx (Sx - N mx)                      sum xh^2  = rx^2 (Sxx - 2 mx Sx + N mx^2)
+//   sum xh yh  = rx ry (Sxy - mx Sy - my Sx + N mx my)
+//   sums[0] = sum (xh - yh), sums[1] = sum (xh - yh) xh      (what TapBwdStatsOp measured in its own pass)
+//   accum  += sum (xh - yh)^2 = sum xh^2 + sum yh^2 - 2 sum xh yh
+__global__ void __launch_bounds__(256) in_joint_finalize_kernel(const double* __restrict__ mom, int nc, double npix, float eps,
+                                                                const float* __restrict__ src_scale, float* __restrict__ mrx,
+                                                                float* __restrict__ mry, double* __restrict__ sums,
+                                                                double* __restrict__ accum) {
+  __shared__ double sh[256];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double contrib = 0.0;
+  if (i < nc) {
+    const double s = src_scale ? (double)__ldg(src_scale) : 1.0;
+    const double e = (double)eps * s * s;
+    const double Sx = mom[5 * i], Sxx = mom[5 * i + 1], Sy = mom[5 * i + 2], Syy = mom[5 * i + 3], Sxy = mom[5 * i + 4];
+    const double inv = 1.0 / npix;
+    double vx = Sxx * inv - (Sx * inv) * (Sx * inv), vy = Syy * inv - (Sy * inv) * (Sy * inv);
+    if (vx < 0.0) vx = 0.0;
+    if (vy < 0.0) vy = 0.0;
+    const float mxf = (float)(Sx * inv), rxf = (float)(1.0 / sqrt(vx + e));
+    const float myf = (float)(Sy * inv), ryf = (float)(1.0 / sqrt(vy + e));
+    mrx[2 * i] = mxf; mrx[2 * i + 1] = rxf;
+    mry[2 * i] = myf; mry[2 * i + 1] = ryf;
+    const double mx = mxf, rx = rxf, my = myf, ry = ryf;
+    const double sxh = rx * (Sx - npix * mx), syh = ry * (Sy - npix * my);
+    const double sxx = rx * rx * (Sxx - 2.0 * mx * Sx + npix * mx * mx);
+    const double syy = ry * ry * (Syy - 2.0 * my * Sy + npix * my * my);
+    const double sxy = rx * ry * (Sxy - mx * Sy - my * Sx + npix * mx * my);
+    sums[2 * i] = sxh - syh;
+    sums[2 * i + 1] = sxx - sxy;
+    contrib = sxx + syy - 2.0 * sxy;
+  }
+  sh[threadIdx.x] = contrib;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(accum, sh[0]);
+}
 // loss += weight * accum / numel ; accum reset
 __global__ void scalar_axpy_kernel(double* accum, double scale, float* loss) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -333,6 +404,39 @@ int uegan_in_mse_fwd(const uegan_tensor* x, const uegan_tensor* y, const float* 
   }
   scalar_axpy_kernel<<<1, 32, 0, st>>>(accum, (double)weight / (double)total, loss_inout);
   UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_in_mse_joint(const uegan_tensor* x, const uegan_tensor* y, float eps, float weight, double* ws, double* accum,
+                       float* loss_inout, float** mrx_out, float** mry_out, double** sums_out, void* stream) {
+  UEGAN_CHECK(x && y && ws && accum && loss_inout && mrx_out && mry_out && sums_out, "in_mse_joint: null pointer");
+  UEGAN_CHECK(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c && x->dtype == y->dtype && x->scale == y->scale,
+              "in_mse_joint: x / y mismatch");
+  const TGeom gx = geom(*x), gy = geom(*y);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int vn = 16 / dtype_size(x->dtype);
+  UEGAN_CHECK(gx.c % vn == 0 && 256 % (gx.c / vn) == 0, "in_mse_joint: unsupported channel count %d", gx.c);
+  const int nc = gx.n * gx.c;
+  const double npix = (double)gx.h * gx.w;
+  double* mom = ws;
+  double* sums = ws + 5 * (size_t)nc;
+  float* mrx = reinterpret_cast<float*>(ws + 7 * (size_t)nc);
+  float* mry = mrx + 2 * (size_t)nc;
+  UEGAN_CUDA(cudaMemsetAsync(mom, 0, sizeof(double) * 5 * nc, st));
+  if (x->dtype == UEGAN_F32) {
+    JointMomentsOp<float> op{gx, gy, mom};
+    launch_strip_reduce<float, 5>(op, gx.c, gx.n, gx.h, gx.w, st);
+  } else if (x->dtype == UEGAN_BF16) {
+    JointMomentsOp<__nv_bfloat16> op{gx, gy, mom};
+    launch_strip_reduce<__nv_bfloat16, 5>(op, gx.c, gx.n, gx.h, gx.w, st);
+  } else {
+    JointMomentsOp<__half> op{gx, gy, mom};
+    launch_strip_reduce<__half, 5>(op, gx.c, gx.n, gx.h, gx.w, st);
+  }
+  in_joint_finalize_kernel<<<(nc + 255) / 256, 256, 0, st>>>(mom, nc, npix, eps, x->scale, mrx, mry, sums, accum);
+  scalar_axpy_kernel<<<1, 32, 0, st>>>(accum, (double)weight / ((double)nc * npix), loss_inout);
+  UEGAN_CUDA(cudaGetLastError());
+  *mrx_out = mrx; *mry_out = mry; *sums_out = sums;
   return 0;
 }
 

@@ -408,6 +408,26 @@ def in_mse_fwd(x: NHWC, y: NHWC, mr_x: int, mr_y: int, weight: float, accum: tor
     _count(2, "in_mse_fwd", x)
 
 
+def in_mse_joint(x: NHWC, y: NHWC, eps: float, weight: float, ws: torch.Tensor, accum: torch.Tensor, loss: torch.Tensor):
+    """One PerceptualLoss term from ONE pass over the taps x, y (InstanceNorm statistics of both + MSE + backward sums).
+    Returns the device addresses (mean/rstd of x, mean/rstd of y, backward sums) inside ws (>= 9 * n * c doubles)."""
+    assert ws.dtype == torch.float64 and ws.numel() >= 9 * x.n * x.c
+    mx, my, sm = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    L.check(L.load().uegan_in_mse_joint(x.ref(), y.ref(), float(eps), float(weight), ws.data_ptr(), accum.data_ptr(),
+                                        loss.data_ptr(), C.byref(mx), C.byref(my), C.byref(sm), _stream()), "in_mse_joint")
+    _count(3, "in_mse_joint", x)
+    return mx.value, my.value, sm.value
+
+
+def in_mse_bwd_apply(x: NHWC, y: NHWC, mr_x: int, mr_y: int, weight: float, gscale, deep: Optional[NHWC], dx: NHWC,
+                     sums: int):
+    L.check(L.load().uegan_in_mse_bwd_apply(x.ref(), y.ref(), mr_x, mr_y, float(weight),
+                                            gscale.data_ptr() if gscale is not None else None,
+                                            deep.ref() if deep is not None else None, dx.ref(), sums, _stream()),
+            "in_mse_bwd_apply")
+    _count(1, f"in_mse_bwd_apply{' +deep' if deep is not None else ''}", x)
+
+
 def msrec_loss(pred: torch.Tensor, gt: torch.Tensor, rec_type: int, scales: int, accum: torch.Tensor,
                loss: torch.Tensor, grad: Optional[torch.Tensor] = None, grad_scale: float = 1.0, gscale_dev=None):
     assert pred.shape == gt.shape and pred.is_cuda and pred.dtype == torch.float32
@@ -451,7 +471,7 @@ def packed_weight_dgrad(weight: torch.Tensor, cout_stored: int, dtype: int, stri
 def conv_generic(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, pad: int, y: NHWC, y_c_off: int = 0,
                  bias=None, alpha=None, act: int = L.ACT_NONE, mask: Optional[NHWC] = None, mask_act: int = L.ACT_NONE,
                  y_mul: int = 1, y_off_h: int = 0, y_off_w: int = 0, real_taps: Optional[int] = None,
-                 w_scale: Optional[torch.Tensor] = None):
+                 w_scale: Optional[torch.Tensor] = None, y_cls_c: int = 0):
     """conv_fprop with the dgrad-only options (activation-derivative mask, strided output view)."""
     lib = L.load()
     d = L.ConvDesc()
@@ -463,7 +483,7 @@ def conv_generic(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int
     d.alpha = alpha.data_ptr() if alpha is not None else None
     d.mask = C.pointer(mask.ct) if mask is not None else None
     d.mask_act = mask_act
-    d.y_mul, d.y_off_h, d.y_off_w = y_mul, y_off_h, y_off_w
+    d.y_mul, d.y_off_h, d.y_off_w, d.y_cls_c = y_mul, y_off_h, y_off_w, y_cls_c
     ev = _Counters.conv_events
     if ev is not None:
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -471,11 +491,13 @@ def conv_generic(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int
     L.check(lib.uegan_conv2d_fprop(C.byref(d), _stream()), "conv2d (dgrad)")
     if ev is not None:
         s1.record()
-        # algorithmic MACs of a data-gradient launch = its share of the forward conv's MACs (real taps only)
+        # algorithmic MACs of a data-gradient launch = its share of the forward conv's MACs (real taps only; a merged
+        # launch covers all four parity classes: real_taps = the forward kernel's k*k, channels = one class)
         taps = real_taps if real_taps is not None else k * k
-        real_c = 3 if cout == 16 and y.c == 16 else cout
-        ev.append((s0, s1, 2.0 * x.n * x.h * x.w * x.c * real_c * taps, x, cout, k, stride, "dgrad", x.dtype))
-    _count(1, f"dgrad ->{cout} k{k} ymul{y_mul}{' +mask' if mask is not None else ''}", x)
+        cc = y_cls_c if y_cls_c else cout
+        real_c = 3 if cc == 16 and y.c == 16 else cc
+        ev.append((s0, s1, 2.0 * x.n * x.h * x.w * x.c * real_c * taps, x, cc, k, stride, "dgrad", x.dtype))
+    _count(1, f"dgrad ->{cout} k{k} ymul{y_mul}{' x4cls' if y_cls_c else ''}{' +mask' if mask is not None else ''}", x)
 
 
 def conv_dgrad(dz: NHWC, weight: torch.Tensor, k: int, stride: int, dxp: NHWC, cache=None, key=None, alpha=None,
@@ -483,11 +505,26 @@ def conv_dgrad(dz: NHWC, weight: torch.Tensor, k: int, stride: int, dxp: NHWC, c
                w_scale: Optional[torch.Tensor] = None):
     """Data gradient of y = conv(xpad, weight, stride) w.r.t. the PADDED input: dxp (extent of xpad, halo 0).
     dz: output gradient with a zero halo of ceil(k/stride) - 1.  stride 2 = four parity-class launches."""
+    import os
     kq = (k + stride - 1) // stride
     assert dz.halo >= kq - 1, "dz needs a zero halo of ceil(k/stride)-1"
     cin_n = (weight.shape[1] - cin_first) if cin is None else cin
     cout_arg = (cin_n + 15) // 16 * 16  # RGB input (3 channels): the packed operand's rows 3..15 are zero
     assert dxp.c >= cout_arg
+    if stride == 2 and mask is None and os.environ.get("UEGAN_NO_DGRAD_MERGE") != "1":
+        # all four parity classes in ONE launch: N = 4 * cout_arg columns (class, channel) over the shared kq x kq window
+        def fn4(out=None):
+            lib = L.load()
+            cb = lib.uegan_packed_weight_bytes(cin_n, dz.c, kq, dz.dtype)
+            buf = out if out is not None else torch.empty(4 * cb + 256, dtype=torch.uint8, device=weight.device)
+            for cls in range(4):
+                packed_weight_dgrad(weight, dz.c, dz.dtype, 2, cls >> 1, cls & 1, cin_first, cin,
+                                    out=buf[cls * cb:], w_scale=w_scale)
+            return buf
+        wp = cache.get((key, "dg4", dz.dtype, dz.c), weight, fn4) if cache is not None else fn4()
+        conv_generic(dz, wp, 4 * cout_arg, kq, 1, kq - 1, dxp, 0, None, alpha, L.ACT_NONE, None, L.ACT_NONE, y_mul=2,
+                     real_taps=k * k, w_scale=w_scale, y_cls_c=cout_arg)
+        return
     for pi in range(stride):
         for pj in range(stride):
             fn = lambda out=None: packed_weight_dgrad(weight, dz.c, dz.dtype, stride, pi, pj, cin_first, cin, out=out,
@@ -517,24 +554,40 @@ class _WgradWs:
         return b.data_ptr(), cls.BYTES
 
 
+def zwin_ok(cout: int, x: NHWC, dz: NHWC, k: int, stride: int = 1) -> bool:
+    """Whether the weight gradient of (x, dz) can read the stacked gradient as a sliding window over a ZERO-haloed dz."""
+    import os
+    return (os.environ.get("UEGAN_NO_ZWIN") != "1" and x.dtype == dz.dtype and dz.h == x.h and dz.w == x.w
+            and bool(L.load().uegan_conv2d_wgrad_zwin_supported(cout, dz.c, dz.halo, x.c, k, stride, x.dtype)))
+
+
 def conv_wgrad(x: NHWC, dz: NHWC, dw: torch.Tensor, k: int, stride: int, pad: int, cin_first: int = 0,
-               cin: Optional[int] = None, alpha=None, scale: float = 1.0):
-    """dw (OIHW fp32, pre-zeroed or accumulating) += scale * alpha * wgrad(x, dz)."""
+               cin: Optional[int] = None, alpha=None, scale: float = 1.0, dz_zero_halo: bool = False):
+    """dw (OIHW fp32, pre-zeroed or accumulating) += scale * alpha * wgrad(x, dz).
+    dz_zero_halo: the caller guarantees that dz's halo holds zeros (a dgrad operand); stride-1 layers with few output
+    channels then read the horizontally stacked gradient as a sliding window over dz (uegan_conv2d_wgrad_zwin)."""
     cout, cin_total = dw.shape[0], dw.shape[1]
     cin_n = (cin_total - cin_first) if cin is None else cin
     assert dw.is_cuda and dw.dtype == torch.float32 and dw.is_contiguous()
+    lib = L.load()
+    zwin = dz_zero_halo and pad == (k - 1) // 2 and zwin_ok(cout, x, dz, k, stride)
     ev = _Counters.conv_events
     if ev is not None:
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-    L.check(L.load().uegan_conv2d_wgrad(x.ref(), dz.ref(), cout, cin_n, cin_total, cin_first, k, stride, pad,
-                                        dw.data_ptr(), alpha.data_ptr() if alpha is not None else None, float(scale),
-                                        *_WgradWs.get(dw.device), _stream()), "conv2d_wgrad")
+    if zwin:
+        L.check(lib.uegan_conv2d_wgrad_zwin(x.ref(), dz.ref(), cout, cin_n, cin_total, cin_first, k, pad, dw.data_ptr(),
+                                            alpha.data_ptr() if alpha is not None else None, float(scale),
+                                            *_WgradWs.get(dw.device), _stream()), "conv2d_wgrad_zwin")
+    else:
+        L.check(lib.uegan_conv2d_wgrad(x.ref(), dz.ref(), cout, cin_n, cin_total, cin_first, k, stride, pad,
+                                       dw.data_ptr(), alpha.data_ptr() if alpha is not None else None, float(scale),
+                                       *_WgradWs.get(dw.device), _stream()), "conv2d_wgrad")
     if ev is not None:
         s1.record()
         real_cin = 3 if x.c * (4 if x.dtype == L.F32 else 2) == 16 else cin_n
         ev.append((s0, s1, 2.0 * dz.n * dz.h * dz.w * cout * real_cin * k * k, x, cout, k, stride, "wgrad", x.dtype))
-    _count(2 if _WgradWs.buf else 1, f"wgrad cout{cout} cin{cin_n} k{k}s{stride}", x, dz)
+    _count(lib.uegan_wgrad_last_launches(), f"wgrad{'_zwin' if zwin else ''} cout{cout} cin{cin_n} k{k}s{stride}", x, dz)
 
 
 def head_bwd(dout: torch.Tensor, out: torch.Tensor, x, mode: int, dz: NHWC):
@@ -586,7 +639,7 @@ def conv_wgrad_hstack(x: NHWC, e: NHWC, dw: torch.Tensor, k: int, pad: int, alph
     if ev is not None:
         s1.record()
         ev.append((s0, s1, 2.0 * x.n * x.h * x.w * cout * cin_total * k * k, x, cout, k, 1, "wgrad", x.dtype))
-    _count(2 if _WgradWs.buf else 1, f"wgrad_hstack cout{cout} cin{cin_total} k{k}", x, e)
+    _count(L.load().uegan_wgrad_last_launches(), f"wgrad_hstack cout{cout} cin{cin_total} k{k}", x, e)
 
 
 def hstack_ok(cout: int, cin_stored: int, k: int) -> bool:
