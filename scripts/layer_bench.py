@@ -146,6 +146,45 @@ def run_dgrad():
     print(f"stride-2 dgrad total per step (listed launches): {tot:.3f} ms")
 
 
+# stride-1 forward-kernel launches on low-channel full-resolution tensors: name, stored cin, h, cout, k, launches per step
+FPROP = [
+    ("G.enc1 8->32 k7", 8, 512, 32, 7, 2), ("G.dec5.0 32->32 k3", 32, 512, 32, 3, 2), ("G.dgrad dec4 32->64 k3", 32, 512, 64, 3, 2),
+    ("G.dgrad dec5.1 8->32 k7", 8, 512, 32, 7, 2), ("VGG conv1_1 8->64 k3", 8, 512, 64, 3, 2), ("G.dec4 64->32 k3", 64, 512, 32, 3, 2),
+    ("VGG conv1_2 64->64 k3", 64, 512, 64, 3, 2),
+]
+
+
+def run_fprop():
+    tot = 0.0
+    for name, cin, h, cout, k, per_step in FPROP:
+        if flt and flt not in name:
+            continue
+        pad = (k - 1) // 2
+        g = torch.Generator(device=dev).manual_seed(5)
+        real_cin = 3 if cin == 8 else cin
+        hs = 64
+        x = torch.randn(2, real_cin, hs, hs, device=dev, generator=g).half().float()
+        wgt = (torch.randn(cout, real_cin, k, k, device=dev, generator=g) / math.sqrt(real_cin * k * k)).half().float()
+        xt = fill(x, cin, pad, True)
+        y = K.NHWC(2, hs, hs, cout, 0, L.F16, dev, zero=True)
+        wp = K.packed_weight(wgt, cin, L.F16)
+        K.conv_fprop(xt, wp, cout, k, 1, pad, y, act=L.ACT_LRELU)
+        ref = F.leaky_relu(F.conv2d(F.pad(x, (pad,) * 4, mode="reflect").double(), wgt.double()), 0.2)
+        err = relerr(y.interior_nchw(), ref)
+        assert K.device_error() == 0
+        xb = K.NHWC(B, h, h, cin, pad, L.F16, dev); xb.buf.normal_()
+        yb = K.NHWC(B, h, h, cout, 0, L.F16, dev)
+        tmin, tmed = timeit(lambda: K.conv_fprop(xb, wp, cout, k, 1, pad, yb, act=L.ACT_LRELU))
+        gf = 2.0 * B * h * h * cout * real_cin * k * k / 1e9
+        gb = B * h * h * (cin + cout) * 2 / 1e9
+        tot += tmed * per_step
+        print(f"fprop {name:26s} err {err:.2e}  min {tmin:.3f} med {tmed:.3f} ms  {gf / tmed:7.1f} TF/s  {gb / tmed * 1e3:6.0f} GB/s  x{per_step} = {tmed * per_step:.3f} ms", flush=True)
+        del xb, yb
+    print(f"low-channel fprop-kernel total per step (listed launches): {tot:.3f} ms")
+
+
+if what in ("fprop", "all"):
+    run_fprop()
 if what in ("wgrad", "all"):
     run_wgrad()
 if what in ("dgrad", "all"):

@@ -291,6 +291,59 @@ def test_in_mse_bwd_direct(K):
         assert float(pv[:, -1].abs().max()) == 0.0 and float(pv[:, :, -1].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 12, 20), (1, 128, 33, 17), (2, 512, 4, 4)])
+def test_in_mse_joint(K, shape):
+    """The joint tap pass (five raw moments per (n, c) in one read of x and y) == torch's
+    weight * mse(instance_norm(x), instance_norm(y)) and, through uegan_in_mse_bwd_apply, its gradient; channels with a
+    tiny variance next to a large mean (the conditioning risk of raw moments) and dead channels included."""
+    from uegan_b200 import _lib as L
+    n, c, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(77 + c)
+    x = torch.relu(torch.randn(n, c, h, w, device="cuda", generator=g) + 0.3)
+    y = torch.relu(torch.randn(n, c, h, w, device="cuda", generator=g) + 0.3)
+    x[:, 1] = 3.0 + 0.05 * x[:, 1]   # low variance on a large mean
+    y[:, 1] = 2.0 + 0.05 * y[:, 1]
+    x[:, 2] = 0.0                    # a dead channel in one map, in both
+    x[:, 3] = 0.0
+    y[:, 3] = 0.0
+    x, y = x.half().float(), y.half().float()
+    tx = fill_nhwc(K, x, c, 1, L.PAD_ZERO, L.F16)
+    ty = fill_nhwc(K, y, c, 1, L.PAD_ZERO, L.F16)
+    weight, eps = 0.75, 1e-5
+    ws = torch.empty(9 * n * c, dtype=torch.float64, device="cuda")
+    accum = torch.zeros(1, dtype=torch.float64, device="cuda")
+    loss = torch.full((1,), 2.0, dtype=torch.float32, device="cuda")  # accumulates
+    mx, my, sm = K.in_mse_joint(tx, ty, eps, weight, ws, accum, loss)
+    assert K.device_error() == 0
+    xr = x.double().requires_grad_(True)
+    ref = weight * F.mse_loss(F.instance_norm(xr, eps=eps), F.instance_norm(y.double(), eps=eps))
+    ref.backward()
+    e = abs(float(loss[0]) - 2.0 - float(ref)) / float(ref)
+    print(f"in_mse_joint {shape}: loss rel err {e:.2e}")
+    assert e < 2e-5
+    assert float(accum[0]) == 0.0  # scratch handed back zeroed
+    # the separate-pass path computes the same numbers
+    wsx = torch.empty(3 * n * c, dtype=torch.float64, device="cuda")
+    wsy = torch.empty(3 * n * c, dtype=torch.float64, device="cuda")
+    mx2, my2 = K.instance_norm_stats(tx, wsx, eps=eps), K.instance_norm_stats(ty, wsy, eps=eps)
+    loss2 = torch.zeros(1, dtype=torch.float32, device="cuda")
+    K.in_mse_fwd(tx, ty, mx2, my2, weight, accum, loss2)
+    assert abs(float(loss2[0]) - (float(loss[0]) - 2.0)) / float(ref) < 2e-5
+    # gradient: joint sums + apply  vs  autograd, and vs the statistics-pass variant
+    scale = 4096.0
+    gs = torch.tensor([0.5], device="cuda")
+    dx = K.NHWC(n, h, w, c, 1, L.F16, "cuda", zero=True)
+    K.in_mse_bwd_apply(tx, ty, mx, my, weight * scale, gs, None, dx, sm)
+    dx2 = K.NHWC(n, h, w, c, 1, L.F16, "cuda", zero=True)
+    K.in_mse_bwd(tx, ty, mx2, my2, weight * scale, gs, None, dx2, torch.empty(2 * n * c, dtype=torch.float64, device="cuda"))
+    assert K.device_error() == 0
+    refg = torch.where(x > 0, xr.grad * (scale * 0.5), torch.zeros_like(xr.grad))
+    eg = relerr(dx.interior_nchw(), refg)
+    eg2 = relerr(dx2.interior_nchw(), refg)
+    print(f"in_mse_joint {shape}: grad rel err {eg:.2e} (separate passes {eg2:.2e})")
+    assert eg < 2e-3 and eg <= 1.5 * eg2 + 1e-4
+
+
 @pytest.mark.parametrize("case", [("f32", 64, 32, 1), ("f32", 32, 64, 3), ("f16", 64, 128, 3)])
 def test_conv_fused_instance_norm_stats(K, case):
     """Per-(n, c) sum / sum of squares accumulated by the conv epilogue (in_stats), consumed by instance_norm_apply: the

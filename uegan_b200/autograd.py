@@ -679,13 +679,19 @@ class _PerceptualFn(torch.autograd.Function):
         x = x.detach().contiguous().float()
         y = y.detach().contiguous().float()
         vgg = module.vgg
-        taps_x, Px = vgg.run(x, "x", module.eps)
-        taps_y, _ = vgg.run(y, "y", module.eps)
+        joint = module.joint_taps()
+        taps_x, Px = vgg.run(x, "x", module.eps, stats=not joint)
+        taps_y, _ = vgg.run(y, "y", module.eps, stats=not joint)
         loss = torch.zeros((), dtype=torch.float32, device=x.device)
-        if module._accum is None or module._accum.device != x.device:
-            module._accum = torch.zeros(1, dtype=torch.float64, device=x.device)
-        for wgt, (tx, mx), (ty, my) in zip(module.weights, taps_x, taps_y):
-            K.in_mse_fwd(tx, ty, mx, my, wgt, module._accum, loss)
+        ctx.joint = None
+        if joint:
+            # statistics of both towers' taps, the MSE and the backward sums from ONE pass per tap
+            ctx.joint = module.tap_terms(taps_x, taps_y, Px, loss)
+        else:
+            if module._accum is None or module._accum.device != x.device:
+                module._accum = torch.zeros(1, dtype=torch.float64, device=x.device)
+            for wgt, (tx, mx), (ty, my) in zip(module.weights, taps_x, taps_y):
+                K.in_mse_fwd(tx, ty, mx, my, wgt, module._accum, loss)
         ctx.module, ctx.taps_x, ctx.taps_y, ctx.Px, ctx.shape = module, taps_x, taps_y, Px, x.shape
         return loss
 
@@ -731,7 +737,11 @@ class _PerceptualFn(torch.autograd.Function):
                 (tx, mx), (ty, my) = ctx.taps_x[t], ctx.taps_y[t]
                 deep = G[out_idx] if have[out_idx] else None
                 dzt = _scratch.get(f"vgg_dz{out_idx}", tx.n, tx.h, tx.w, tx.c, 1, L.F16, dev, zero=True)
-                K.in_mse_bwd(tx, ty, mx, my, module.weights[t] * scale, g, deep, dzt, P["gws"])
+                if ctx.joint is not None:
+                    jx, jy, jsums = ctx.joint[t]
+                    K.in_mse_bwd_apply(tx, ty, jx, jy, module.weights[t] * scale, g, deep, dzt, jsums)
+                else:
+                    K.in_mse_bwd(tx, ty, mx, my, module.weights[t] * scale, g, deep, dzt, P["gws"])
                 dz = dzt
             else:
                 dz = G[out_idx]  # masked by the producer (dgrad epilogue mask or max-pool backward)

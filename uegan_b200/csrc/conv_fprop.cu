@@ -38,6 +38,9 @@ struct ConvParams {
   int num_stages, stage_bytes;
   // patch mode (stride-1, pixel = whole 128-byte chunks, weights resident in smem)
   int patch_w, patch_nch, patch_k, patch_off;  // patch width in pixels, chunks per pixel, kernel size, halo - pad
+  // patch-mode operand rows: 128 bytes (SWIZZLE_128B, 4 MMAs of K = 32 bytes per tap) or, for 32-channel 16-bit tensors,
+  // 64 bytes = one pixel (SWIZZLE_64B, 2 MMAs per tap); weight-tile K offset = (r * patch_cpr + s * patch_nch + c) * patch_ce
+  int patch_row_bytes, patch_kmma, patch_layout, patch_cpr, patch_ce;
   int w_tile_bytes, w_total_bytes, stage_tx_bytes;
   // patch mode with STREAMED weights (kPatch == 2): the weight tiles do not fit next to the patches (large C or N), so
   // they flow through their own ring of b_slots x w_tile_bytes behind the A ring (b_ring_off bytes from the smem base)
@@ -108,6 +111,33 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   return c;
 }
 
+// The tiles a persistent CTA visits (t = blockIdx.x, += gridDim.x) without a division per tile: the stride is decomposed
+// once into its (n-tile, w, h, image) digits and added with carries.  The epilogue warps are bound by their own
+// instruction latency on small-N layers (r2r: ~340 warp instructions per 128 x 32 tile, 90 of them three integer
+// divisions), so every instruction per tile counts there.
+struct TileIter {
+  int i_nt, i_w, i_h, i_n;  // current digits
+  int s_nt, s_w, s_h, s_n;  // digits of the stride
+  __device__ __forceinline__ void init(const ConvParams& p, int t0, int step) {
+    i_nt = t0 % p.n_tiles; int m = t0 / p.n_tiles;
+    i_w = m % p.tiles_w; m /= p.tiles_w;
+    i_h = m % p.tiles_h; i_n = m / p.tiles_h;
+    s_nt = step % p.n_tiles; m = step / p.n_tiles;
+    s_w = m % p.tiles_w; m /= p.tiles_w;
+    s_h = m % p.tiles_h; s_n = m / p.tiles_h;
+  }
+  __device__ __forceinline__ void next(const ConvParams& p) {
+    i_nt += s_nt; int c = i_nt >= p.n_tiles; i_nt -= c ? p.n_tiles : 0;
+    i_w += s_w + c; c = i_w >= p.tiles_w; i_w -= c ? p.tiles_w : 0;
+    i_h += s_h + c; c = i_h >= p.tiles_h; i_h -= c ? p.tiles_h : 0;
+    i_n += s_n + c;
+  }
+  __device__ __forceinline__ TileCoord coord(const ConvParams& p) const {
+    TileCoord c;
+    c.nt = i_nt; c.wo0 = i_w * p.tw; c.ho0 = i_h * p.th; c.n0 = i_n * p.tn;
+    return c;
+  }
+};
 
 template <int ACT>
 __device__ __forceinline__ float act_t(float v, int act_rt) {
@@ -121,7 +151,7 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
 template <int ACT>
 __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t taddr, int colbase, int half, long long o,
                                               long long mo, bool valid, float alpha, float bmul, float* stat_slice,
-                                              int mk_n, int mk_h, int mk_w) {
+                                              int mk_n, int mk_h, int mk_w, const float* s_bias) {
   for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
     uint32_t rr[16];
     tmem_ld16(taddr + c0, rr);
@@ -164,15 +194,16 @@ __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t tadd
     if (!vc) continue;
     float v[16];
     if (p.bias) {
-      const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+      // bias * bmul staged in shared memory once per CTA (bmul = 1 unless the output carries a scale: a power of two, so
+      // the product is exact); a global load per tile sat on the epilogue's critical path
+      const float4* bp = reinterpret_cast<const float4*>(s_bias + col0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 b = __ldg(bp + i);
-        // (bmul = 1 unless the output carries a scale: a power of two, so b * bmul is exact)
-        v[4 * i + 0] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 0]), alpha, b.x * bmul), p.act);
-        v[4 * i + 1] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 1]), alpha, b.y * bmul), p.act);
-        v[4 * i + 2] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 2]), alpha, b.z * bmul), p.act);
-        v[4 * i + 3] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 3]), alpha, b.w * bmul), p.act);
+        const float4 b = bp[i];
+        v[4 * i + 0] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 0]), alpha, b.x), p.act);
+        v[4 * i + 1] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 1]), alpha, b.y), p.act);
+        v[4 * i + 2] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 2]), alpha, b.z), p.act);
+        v[4 * i + 3] = act_t<ACT>(fmaf(__uint_as_float(rr[4 * i + 3]), alpha, b.w), p.act);
       }
     } else {
 #pragma unroll
@@ -245,10 +276,8 @@ __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t tadd
         if (p.out_kind == UEGAN_BF16) {
           __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
           pk[i] = *reinterpret_cast<uint32_t*>(&h);
-        } else {  // saturating (see Vec<__half>::store)
-          __half2 h = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f),
-                                        fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
-          pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        } else {  // saturating (see Vec<__half>::store): one F2FP.SATFINITE instead of four FMNMX + F2FP per pair
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
         }
       }
       uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + oc);
@@ -301,6 +330,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ __align__(8) uint64_t emptyB[kMaxBSlots];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_stats[8 * 256];  // InstanceNorm partial sums: [epilogue warp][chunk slot][lane]
+  __shared__ __align__(16) float s_bias[512];  // bias * (s_y / s_mul), padded with zeros to the 16-column chunks
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -328,6 +358,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, kTmemCols);
+  if (p.bias && !p.out_nchw) {
+    const float bm = (p.sy ? __ldg(p.sy) : 1.0f) / (p.smul ? __ldg(p.smul) : 1.0f);
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_bias[i] = i < p.cout ? __ldg(p.bias + i) * bm : 0.f;
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -368,11 +402,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // weights: all k*k*nch [block_n x 128 B] tiles once per CTA, resident behind the A ring
         uint8_t* sw = smem;
         mbar_arrive_expect_tx(&w_full, (uint32_t)p.w_total_bytes);
-        const int ntiles_w = p.patch_k * p.patch_k * p.patch_nch;
+        // 16-byte pixels: one box per filter row, landing as [K chunk of 8][cout][8 values] = unswizzled core matrices
+        const int ntiles_w = p.patch_layout == UMMA_LAYOUT_NONE ? 0 : p.patch_k * p.patch_k * p.patch_nch;
+        if (p.patch_layout == UMMA_LAYOUT_NONE)
+          for (int r = 0; r < p.patch_k; ++r) tma_load_4d(&tmB, &w_full, sw + r * p.w_tile_bytes, 0, 0, 0, r);
         for (int wi = 0; wi < ntiles_w; ++wi) {
           const int c = wi % p.patch_nch, tap = wi / p.patch_nch;
           const int r = tap / p.patch_k, s_ = tap % p.patch_k;
-          const int kofs = (r * p.chunks_per_row + s_ * p.patch_nch + c) * p.chunk_elems;
+          const int kofs = (r * p.patch_cpr + s_ * p.patch_nch + c) * p.patch_ce;
           tma_load_2d(&tmB, &w_full, sw + wi * p.w_tile_bytes, kofs, 0);
         }
         uint8_t* sa0 = smem + p.w_total_bytes;
@@ -381,7 +418,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int c = 0; c < p.patch_nch; ++c) {
             mbar_wait(&empty_bar[stage], phase ^ 1, 0x100 + stage, p.err_sink);
             mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_tx_bytes);
-            tma_load_4d(&tmA, &full_bar[stage], sa0 + stage * p.stage_bytes, c * p.chunk_elems, tc.wo0 + p.patch_off,
+            tma_load_4d(&tmA, &full_bar[stage], sa0 + stage * p.stage_bytes, c * p.patch_ce, tc.wo0 + p.patch_off,
                         tc.ho0 + p.patch_off, tc.n0);
             if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
           }
@@ -455,14 +492,47 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // one staged patch per 128-byte channel chunk; every filter tap (r, s) is the SAME smem patch read
           // through a descriptor window shifted by (r*patch_w + s) rows (tcgen05 swizzles on absolute address bits,
           // profiles/r1_probe_umma_window.json), 8-row groups = one output row of 8 pixels, SBO = patch row pitch.
+          // (64-byte rows: a 32-channel 16-bit pixel IS the operand row, SWIZZLE_64B atoms of 8 rows x 64 B, two MMAs per tap)
           const uint32_t w_addr = smem_u32(smem);
-          const uint32_t sbo = p.patch_w * 128;
-          const uint64_t db0 = make_smem_desc(w_addr, 16, 1024, UMMA_LAYOUT_SW128);
+          if (p.patch_layout == UMMA_LAYOUT_NONE) {
+            // 16-byte pixels (RGB stored as 8 fp16 channels), UNSWIZZLED operands: a core matrix (8 rows x 16 B) is 8
+            // consecutive pixels of a patch row; the K-adjacent core matrix (LBO) is the SAME memory one pixel further, so
+            // the horizontal taps of a filter row are the K dimension of the MMA with no replication at all: one MMA
+            // (K = 16) = two taps x 8 channels, its 8-row groups (SBO) are the tile's 16 rows.
+            mbar_wait(&full_bar[stage], phase, 0x300 + stage, p.err_sink);
+            tcgen05_fence_after();
+            const uint32_t sbo = p.patch_w * 16;
+            const uint64_t da0 = make_smem_desc(w_addr + p.w_total_bytes + stage * p.stage_bytes, 16, sbo, UMMA_LAYOUT_NONE);
+            const uint64_t db0 = make_smem_desc(w_addr, p.block_n * 16, 128, UMMA_LAYOUT_NONE);
+            const uint32_t b_mma = p.block_n * 32;  // two K chunks of [cout x 16 B]
+            uint32_t first = 0, a_off = 0, b_off = 0;
+            for (int r = 0; r < p.patch_k; ++r) {
+              uint64_t da = desc_adv(da0, a_off), db = desc_adv(db0, b_off);
+              for (int j = 0; j < p.patch_kmma; ++j) {
+                umma_ss<kTf32>(d_tmem, da, db, idesc, first);
+                first = 1;
+                da += 2;
+                db += b_mma >> 4;
+              }
+              a_off += sbo;
+              b_off += p.w_tile_bytes;
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+            umma_commit(&tmem_full[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+            continue;
+          }
+          const uint32_t rb = p.patch_row_bytes;
+          const uint32_t sbo = p.patch_w * rb;
+          const uint64_t db0 = make_smem_desc(w_addr, 16, 8 * rb, p.patch_layout);
+          const bool four = p.patch_kmma == 4;
           uint32_t first = 0;
           for (int c = 0; c < p.patch_nch; ++c) {
             mbar_wait(&full_bar[stage], phase, 0x300 + stage, p.err_sink);
             tcgen05_fence_after();
-            const uint64_t da0 = make_smem_desc(w_addr + p.w_total_bytes + stage * p.stage_bytes, 16, sbo, UMMA_LAYOUT_SW128);
+            const uint64_t da0 = make_smem_desc(w_addr + p.w_total_bytes + stage * p.stage_bytes, 16, sbo, p.patch_layout);
             uint32_t a_off = 0, b_off = c * p.w_tile_bytes;
             const uint32_t b_step = p.patch_nch * p.w_tile_bytes;
             for (int r = 0; r < p.patch_k; ++r) {
@@ -471,10 +541,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint64_t da = desc_adv(da0, a_rs), db = desc_adv(db0, b_off);
                 umma_ss<kTf32>(d_tmem, da, db, idesc, first);
                 umma_ss<kTf32>(d_tmem, da + 2, db + 2, idesc, 1u);
-                umma_ss<kTf32>(d_tmem, da + 4, db + 4, idesc, 1u);
-                umma_ss<kTf32>(d_tmem, da + 6, db + 6, idesc, 1u);
+                if (four) {
+                  umma_ss<kTf32>(d_tmem, da + 4, db + 4, idesc, 1u);
+                  umma_ss<kTf32>(d_tmem, da + 6, db + 6, idesc, 1u);
+                }
                 first = 1;
-                a_rs += 128;
+                a_rs += rb;
                 b_off += b_step;
               }
               a_off += sbo;
@@ -531,8 +603,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           atomicAdd(p.in_stats + ((long long)n_img * p.cout + col) * 2 + (lane >> 4), (double)v);
       }
     };
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(p, t);
+    TileIter it;
+    it.init(p, blockIdx.x, gridDim.x);
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, it.next(p)) {
+      const TileCoord tc = it.coord(p);
       if (p.in_stats && tc.n0 * p.n_tiles + tc.nt != stat_n) {
         if (stat_n >= 0) flush_stats(stat_n);
         stat_n = tc.n0 * p.n_tiles + tc.nt;
@@ -547,12 +621,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (half == 0) epilogue_planar(p, taddr, colbase, n, ho, wo, valid, alpha);
       } else {
         const long long o = (long long)n * p.out_img + (long long)ho * p.out_row + (long long)wo * p.out_pix + colbase;
-        const long long mo = (long long)n * p.mul_img + (long long)ho * p.mul_row + (long long)wo * p.mul_pix + colbase;
+        const long long mo = p.mul ? (long long)n * p.mul_img + (long long)ho * p.mul_row + (long long)wo * p.mul_pix + colbase : 0;
         switch (p.act) {
-          case UEGAN_ACT_LRELU: epilogue_nhwc<UEGAN_ACT_LRELU>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo); break;
-          case UEGAN_ACT_RELU: epilogue_nhwc<UEGAN_ACT_RELU>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo); break;
-          case UEGAN_ACT_NONE: epilogue_nhwc<UEGAN_ACT_NONE>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo); break;
-          default: epilogue_nhwc<-1>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo); break;
+          case UEGAN_ACT_LRELU: epilogue_nhwc<UEGAN_ACT_LRELU>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo, s_bias); break;
+          case UEGAN_ACT_RELU: epilogue_nhwc<UEGAN_ACT_RELU>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo, s_bias); break;
+          case UEGAN_ACT_NONE: epilogue_nhwc<UEGAN_ACT_NONE>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo, s_bias); break;
+          default: epilogue_nhwc<-1>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo, s_bias); break;
         }
       }
       tcgen05_fence_before();
@@ -666,6 +740,7 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
       if (p.Wo > wv) p.Wo = wv;
     }
     UEGAN_CHECK(d.cout % 16 == 0, "conv: NHWC output needs cout %% 16 == 0 (got %d)", d.cout);
+    UEGAN_CHECK(!d.bias || d.cout <= 512, "conv: a bias needs cout <= 512 (staged in shared memory; got %d)", d.cout);
     UEGAN_CHECK(d.y_c_off >= 0 && d.y_c_off + (d.y_cls_c > 0 ? d.y_cls_c : d.cout) <= y.c && d.y_c_off % 8 == 0,
                 "conv: bad channel slice");
     UEGAN_CHECK((y.c * dtype_size(y.dtype)) % 16 == 0, "conv: y.c misaligned");
@@ -727,11 +802,23 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   {
     const char* env = getenv("UEGAN_NO_PATCH");
     const char* env2 = getenv("UEGAN_NO_STREAM");
-    const int PH = 16 + d.k - 1, PW = 8 + d.k - 1;
-    const long long a_stage = ((long long)PH * PW * 128 + 1023) / 1024 * 1024;
-    const long long w_tile = (long long)p.block_n * 128;
-    const long long w_total = w_tile * d.k * d.k * (pix_b / 128);
-    const bool shape_ok = !(env && env[0] == '1') && d.stride == 1 && d.k > 1 && pix_b % 128 == 0 && Ho >= 16 && Wo >= 8;
+    const int PH = 16 + d.k - 1;
+    int PW = 8 + d.k - 1;
+    // 64-byte pixels (32 channels of a 16-bit type): the same patch mode on SWIZZLE_64B rows -- the plain mode's
+    // overlapping 128-byte windows re-fetch every input byte ~12 times through L2 and bound those layers (r2p)
+    const char* env64 = getenv("UEGAN_NO_PATCH64");
+    const bool row64 = pix_b == 64 && es == 2 && !(env64 && env64[0] == '1');
+    // 16-byte pixels (RGB as 8 channels of a 16-bit type): unswizzled operands, the taps of a filter row are the MMA's K
+    const char* env16 = getenv("UEGAN_NO_PATCH16");
+    const bool row16 = pix_b == 16 && es == 2 && !(env16 && env16[0] == '1');
+    const int kpad = (d.k + 1) / 2 * 2;  // taps per filter row, rounded to whole K = 16 MMAs (the extra tap has zero weights)
+    const int rb = row16 ? 16 : (row64 ? 64 : 128);
+    if (row16) PW = 8 + kpad - 1;
+    const long long a_stage = ((long long)PH * PW * rb + 1023) / 1024 * 1024;
+    const long long w_tile = row16 ? (long long)kpad * p.block_n * 16 : (long long)p.block_n * rb;
+    const long long w_total = row16 ? (w_tile * d.k + 1023) / 1024 * 1024 : w_tile * d.k * d.k * (row64 ? 1 : pix_b / 128);
+    const bool shape_ok = !(env && env[0] == '1') && d.stride == 1 && d.k > 1 && (pix_b % 128 == 0 || row64 || row16) &&
+                          Ho >= 16 && Wo >= 8 && (!row64 || w_total % 1024 == 0) && (!row16 || g.cout_pad <= 256);
     const bool resident = shape_ok && p.n_tiles == 1 && w_total + 2 * a_stage <= 200 * 1024;
     const bool resident_deep = resident && w_total + 3 * a_stage <= 200 * 1024;  // >= 3 patch stages in flight
     // Weights that do not fit (or leave only two patch stages: the TMA latency of a patch is then exposed) are streamed
@@ -739,7 +826,7 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
     // (N = 256 launches are MMA-bound in plain mode already: 85-97 % of the tensor peak; they stay there.)
     const char* env3 = getenv("UEGAN_STREAM_MAXN");
     const int stream_max_n = env3 ? atoi(env3) : 0;  // opt-in: measured 1-6 % SLOWER than plain mode
-    if (shape_ok && !resident_deep && !(env2 && env2[0] == '1') && p.block_n <= stream_max_n && w_tile % 1024 == 0 &&
+    if (shape_ok && !row64 && !row16 && !resident_deep && !(env2 && env2[0] == '1') && p.block_n <= stream_max_n && w_tile % 1024 == 0 &&
         3 * a_stage + 4 * w_tile <= 200 * 1024) {
       stream_w = true;
       p.tw = 8; p.th = 16; p.tn = 1; p.tw_log2 = 3; p.th_log2 = 4;
@@ -767,24 +854,34 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
       p.tiles_img = x.n;
       p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_img;
       p.patch_w = PW;
-      p.patch_nch = (int)(pix_b / 128);
+      p.patch_nch = (row64 || row16) ? 1 : (int)(pix_b / 128);
       p.patch_k = d.k;
       p.patch_off = x.halo - d.pad;
+      p.patch_row_bytes = rb;
+      p.patch_kmma = row16 ? kpad / 2 : rb / 32;
+      p.patch_layout = row16 ? UMMA_LAYOUT_NONE : (row64 ? UMMA_LAYOUT_SW64 : UMMA_LAYOUT_SW128);
+      p.patch_ce = rb / es;
+      p.patch_cpr = g.row_pad / p.patch_ce;
       p.w_tile_bytes = (int)w_tile;
       p.w_total_bytes = (int)w_total;
       p.stage_bytes = (int)a_stage;
-      p.stage_tx_bytes = PH * PW * 128;
+      p.stage_tx_bytes = PH * PW * rb;
       p.num_stages = (int)((200 * 1024 - w_total) / a_stage);
       if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
     }
   }
   // ---- tensor maps
   CUtensorMap tmA, tmB;
+  const bool patch64 = patch && p.patch_row_bytes == 64, patch16 = patch && p.patch_row_bytes == 16;
   if (patch || stream_w) {
     uint64_t dims[4] = {(uint64_t)x.c, (uint64_t)t_wp(x), (uint64_t)t_hp(x), (uint64_t)x.n};
     uint64_t strides[3] = {pix_b, row_b, img_b};
-    uint32_t box[4] = {(uint32_t)g.chunk_elems, (uint32_t)p.patch_w, (uint32_t)(16 + d.k - 1), 1u};
-    if (encode_tiled(&tmA, dt, 4, x.data, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    uint32_t box[4] = {(uint32_t)(patch16 ? 8 : (patch64 ? 32 : g.chunk_elems)), (uint32_t)p.patch_w,
+                       (uint32_t)(16 + d.k - 1), 1u};
+    if (encode_tiled(&tmA, dt, 4, x.data, dims, strides, box,
+                     patch16 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                             : (patch64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)))
+      return -1;
   } else {
     uint8_t* a_base = static_cast<uint8_t*>(x.data) + (uint64_t)(x.halo - d.pad) * row_b + (uint64_t)(x.halo - d.pad) * pix_b;
     uint64_t dims[5] = {(uint64_t)g.row_pad, (uint64_t)Wo, (uint64_t)d.k, (uint64_t)Ho, (uint64_t)x.n};
@@ -792,12 +889,21 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
     uint32_t box[5] = {(uint32_t)g.chunk_elems, (uint32_t)p.tw, 1u, (uint32_t)p.th, (uint32_t)p.tn};
     if (encode_tiled(&tmA, dt, 5, a_base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
   }
-  {
+  if (patch16) {
+    // weights [cout_pad][k][row_pad] read as {8 values, cout, K chunk, filter row}: the box {8, cout, kpad / .., 1} lands as
+    // [K chunk][cout][8 values] -- core matrices of 8 output channels x 16 B, K-adjacent ones cout * 16 B apart
+    const uint64_t ktot = (uint64_t)d.k * g.row_pad;
+    uint64_t dims[4] = {8u, (uint64_t)g.cout_pad, (uint64_t)(g.row_pad / 8), (uint64_t)d.k};
+    uint64_t strides[3] = {ktot * es, 16u, (uint64_t)g.row_pad * es};
+    uint32_t box[4] = {8u, (uint32_t)p.block_n, (uint32_t)(2 * p.patch_kmma), 1u};
+    if (encode_tiled(&tmB, dt, 4, const_cast<void*>(d.w_packed), dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+  } else {
     const uint64_t ktot = (uint64_t)d.k * g.row_pad;
     uint64_t dims[2] = {ktot, (uint64_t)g.cout_pad};
     uint64_t strides[1] = {ktot * es};
-    uint32_t box[2] = {(uint32_t)g.chunk_elems, (uint32_t)p.block_n};
-    if (encode_tiled(&tmB, dt, 2, const_cast<void*>(d.w_packed), dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+    uint32_t box[2] = {(uint32_t)(patch64 ? 32 : g.chunk_elems), (uint32_t)p.block_n};
+    if (encode_tiled(&tmB, dt, 2, const_cast<void*>(d.w_packed), dims, strides, box,
+                     patch64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B))
       return -1;
   }
   if (d.in_stats) {

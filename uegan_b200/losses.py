@@ -148,8 +148,10 @@ class VGG19_relu(nn.Module):
         return pl
 
     @torch.no_grad()
-    def run(self, x01, slot="x", eps=1e-5):
-        """x01: (B,3,H,W) fp32 in [0,1].  Returns (taps, plan): taps = list of (NHWC activation, mean/rstd address)."""
+    def run(self, x01, slot="x", eps=1e-5, stats=True):
+        """x01: (B,3,H,W) fp32 in [0,1].  Returns (taps, plan): taps = list of (NHWC activation, mean/rstd address).
+        stats=False: no InstanceNorm statistics pass (address None): the caller measures both towers' taps jointly
+        (kernels.in_mse_joint)."""
         b, _, h, w = x01.shape
         if h % 16 or w % 16:
             raise ValueError("PerceptualLoss needs H, W multiples of 16")
@@ -169,12 +171,12 @@ class VGG19_relu(nn.Module):
             idx, cin, cout = spec
             _, b_eff, s_l = self.layer(idx)
             is_tap = idx in _TAP_IDX
-            fused = is_tap and K.fused_stats_ok(dst.h, dst.w, cout)
+            fused = is_tap and stats and K.fused_stats_ok(dst.h, dst.w, cout)
             K.conv_fprop(src, self._packed(idx, src.c), cout, 3, 1, 1, dst, 0, b_eff, None, L.ACT_RELU,
                          in_stats=P["stats"][ti] if fused else None)
             if is_tap:
                 # InstanceNorm of the TRUE activation: eps scales with the square of the stored scale
-                mr = K.instance_norm_stats(dst, P["stats"][ti], sums_ready=fused, eps=eps * s_l * s_l)
+                mr = K.instance_norm_stats(dst, P["stats"][ti], sums_ready=fused, eps=eps * s_l * s_l) if stats else None
                 taps.append((dst, mr))
                 ti += 1
         return taps, P
@@ -206,11 +208,35 @@ class PerceptualLoss(nn.Module):
             return perceptual_apply(self, x, y)
         return self.forward_native(x, y)
 
+    @staticmethod
+    def joint_taps():
+        """One joint pass per tap over both towers' feature maps (uegan_in_mse_joint) instead of separate statistics,
+        MSE and backward-statistics passes; UEGAN_NO_JOINT_TAP=1 selects the separate passes."""
+        import os
+        return os.environ.get("UEGAN_NO_JOINT_TAP") != "1"
+
+    def tap_terms(self, taps_x, taps_y, Px, loss):
+        """loss += sum_k w_k MSE(IN(x_k), IN(y_k)) from the joint pass; returns per tap (mean/rstd x, mean/rstd y, sums)."""
+        dev = loss.device
+        if self._accum is None or self._accum.device != dev:
+            self._accum = torch.zeros(1, dtype=torch.float64, device=dev)
+        if "joint_ws" not in Px:
+            Px["joint_ws"] = [torch.empty(9 * t.n * t.c, dtype=torch.float64, device=dev) for t, _ in taps_x]
+        out = []
+        for ti, (wgt, (tx, _), (ty, _)) in enumerate(zip(self.weights, taps_x, taps_y)):
+            s_l = self.vgg.tap_scale(ti)
+            out.append(K.in_mse_joint(tx, ty, self.eps * s_l * s_l, wgt, Px["joint_ws"][ti], self._accum, loss))
+        return out
+
     @torch.no_grad()
     def forward_native(self, x, y):
-        taps_x, _ = self.vgg.run(x, "x", self.eps)
-        taps_y, _ = self.vgg.run(y, "y", self.eps)
+        joint = self.joint_taps()
+        taps_x, Px = self.vgg.run(x, "x", self.eps, stats=not joint)
+        taps_y, _ = self.vgg.run(y, "y", self.eps, stats=not joint)
         loss = torch.zeros(1, dtype=torch.float32, device=x.device)
+        if joint:
+            self.tap_terms(taps_x, taps_y, Px, loss)
+            return loss[0]
         if self._accum is None or self._accum.device != x.device:
             self._accum = torch.zeros(1, dtype=torch.float64, device=x.device)
         for wgt, (tx, mx), (ty, my) in zip(self.weights, taps_x, taps_y):
