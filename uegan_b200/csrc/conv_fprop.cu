@@ -1,7 +1,7 @@
 // Implicit-GEMM convolution, forward, for sm_100a: TMA-staged NHWC tiles -> tcgen05.mma (TMEM accumulators)
 // -> fused epilogue.  One persistent CTA per SM, warp-specialised:
 //   warp 0   TMA producer   (one elected lane)
-//   warp 1   MMA issuer     (one elected lane)
+//   warp 1   MMA issuer     (one elected lane; warp 3 is a second issuer on small-N launches)
 //   warp 2   TMEM allocator
 //   warps 4-11 epilogue     (TMEM -> registers -> alpha/bias/activation/mul -> global)
 //
@@ -41,6 +41,7 @@ struct ConvParams {
   // patch-mode operand rows: 128 bytes (SWIZZLE_128B, 4 MMAs of K = 32 bytes per tap) or, for 32-channel 16-bit tensors,
   // 64 bytes = one pixel (SWIZZLE_64B, 2 MMAs per tap); weight-tile K offset = (r * patch_cpr + s * patch_nch + c) * patch_ce
   int patch_row_bytes, patch_kmma, patch_layout, patch_cpr, patch_ce;
+  int n_issuers;  // 1, or 2: warps 1 and 3 both issue MMAs, alternating tiles (small-N launches)
   int w_tile_bytes, w_total_bytes, stage_tx_bytes;
   // patch mode with STREAMED weights (kPatch == 2): the weight tiles do not fit next to the patches (large C or N), so
   // they flow through their own ring of b_slots x w_tile_bytes behind the A ring (b_ring_off bytes from the smem base)
@@ -441,18 +442,35 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers =====================
+    // The issue loop is ONE thread's scalar instruction stream (descriptor arithmetic, R2UR moves into the uniform
+    // registers tcgen05.mma reads): on small-N layers (N <= 64: 18 - 50 cheap MMAs per 128-pixel tile) that stream, not the
+    // tensor pipe, was the launch's critical path (r2t: the issuing warp never waits; doing the same work on all 32 lanes
+    // made the layers 30 % slower).  With n_iss = 2, warp 3 is a SECOND issuer: issuer i owns the CTA's tiles i, i + 2, ...
+    // and the accumulator stage i; each walks the smem ring in tile order, skipping the other's stages.
+    const int iss = warp == 3 ? 1 : 0;
+    const int n_iss = (kPatch != 2 && p.n_issuers == 2) ? 2 : 1;
+    if (iss < n_iss && elect_one()) {
       const uint32_t idesc = make_instr_desc(p.ab_fmt, 128, p.block_n);
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
+      int acc = iss;
       uint32_t acc_phase = 0;
+      const int per_tile = kPatch == 1 ? p.patch_nch : p.num_k_chunks;  // smem stages one tile consumes
+      auto skip_tile = [&]() {
+        for (int i = 0; i < per_tile; ++i)
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+      };
+      auto next_acc = [&]() {
+        if (n_iss == 2) { acc_phase ^= 1; skip_tile(); }
+        else { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
+      };
+      if (iss) skip_tile();
       if constexpr (kPatch == 1) mbar_wait(&w_full, 0, 0x500, p.err_sink);
       int bs = 0;
       uint32_t bphase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x + iss * gridDim.x; t < p.total_tiles; t += n_iss * gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 0x200 + acc, p.err_sink);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
@@ -520,8 +538,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             umma_commit(&empty_bar[stage]);
             if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
             umma_commit(&tmem_full[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            next_acc();
             continue;
           }
           const uint32_t rb = p.patch_row_bytes;
@@ -571,8 +588,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        next_acc();
       }
     }
   } else if (warp >= 4) {
@@ -910,6 +926,16 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
     UEGAN_CHECK(!d.out_nchw && !d.mul, "conv: in_stats needs a plain NHWC epilogue");
     UEGAN_CHECK(p.tn == 1, "conv: in_stats needs tiles within one image (Ho*Wo >= 128); use uegan_instance_norm");
     UEGAN_CUDA(cudaMemsetAsync(d.in_stats, 0, sizeof(double) * 2 * (size_t)x.n * d.cout, stream));
+  }
+  {
+    // two MMA issuers when a tile's MMAs are cheap (N <= 64: the issuing thread's instruction stream is the bottleneck)
+    const char* env = getenv("UEGAN_ISSUERS");
+    const int per_tile = patch ? p.patch_nch : p.num_k_chunks;
+    p.n_issuers = env ? atoi(env) : (p.block_n <= 64 ? 2 : 1);
+    // An issuer SKIPS the other's stages without waiting on them, and mbarrier parity waits only tell phases apart that
+    // are at most one ring pass away: the ring must hold two whole tiles, or a skipped-ahead wait would pass on a stale
+    // phase (measured: launch failure with 72-chunk tiles on an 8-stage ring).
+    if (stream_w || p.n_issuers != 2 || p.num_stages < 2 * per_tile) p.n_issuers = 1;
   }
   const int smem_bytes = stream_w ? p.b_ring_off + p.b_slots * p.w_tile_bytes + 1024
                                   : (patch ? p.w_total_bytes : 0) + p.num_stages * p.stage_bytes + 1024;
