@@ -469,6 +469,7 @@ struct WgradPatchParams {
   // columns of D: n_cols of them (a multiple of 16), column j = (j / col_c, j % col_c) = (horizontal tap, output channel);
   // col_rev: the tap index runs backwards (the stack is a sliding WINDOW over dz itself, see uegan_conv2d_wgrad_zwin)
   int n_cols, col_c, col_rev;
+  int two_issuers;  // warps 1 and 3 both issue MMAs (alternate accumulators)
   float* dw;
   float* partial;
   long long dw_numel;
@@ -497,6 +498,7 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const int kt0 = blockIdx.x * per, kt1 = min(kt0 + per, p.total_ktiles);
   const int acc0 = blockIdx.y * p.acc_per_cta, acc1 = min(acc0 + p.acc_per_cta, p.acc_total);
   const int N = p.n_cols;
+  const int n_iss = (p.two_issuers && acc1 - acc0 >= 2) ? 2 : 1;
   // accumulator index a -> (chunk, r, g):  a = (chunk * k + r) * kgroups + g.  The chunks this CTA touches:
   const int ch_lo = acc0 / (p.rk * p.kgroups), ch_hi = (acc1 - 1) / (p.rk * p.kgroups);
   const int nch = ch_hi - ch_lo + 1;
@@ -508,9 +510,9 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < p.num_stages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], n_iss);
     }
-    mbar_init(&done_bar, 1);
+    mbar_init(&done_bar, n_iss);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
@@ -543,8 +545,13 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1) {
-      if (elect_one()) {
+    } else if (warp == 1 || warp == 3) {
+      // Two MMA issuers (warp 3 joins when the CTA owns >= 2 accumulators): issuer i takes every second accumulator of
+      // EVERY stage, so both walk the ring in lock step (each arrives once on empty_bar / done_bar) and no accumulator is
+      // shared.  The one-thread issue loop (descriptor arithmetic + uniform-register moves per MMA), not the tensor pipe,
+      // bounds these N <= 192 launches.
+      const int iss = warp == 3 ? 1 : 0;
+      if (iss < n_iss && elect_one()) {
         const uint32_t idesc = make_instr_desc(kF16 ? UMMA_F16 : UMMA_TF32, 128, N, 1, 1);
         int stage = 0;
         uint32_t phase = 0;
@@ -569,10 +576,12 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             const uint32_t tap0 = p.vert ? (uint32_t)(TPG * g * p.pw) : (uint32_t)(r * p.pw + TPG * g);
             uint64_t da = da0 + (uint32_t)(c * (p.patch_bytes >> 4)) + tap0 * 8;
             constexpr int KSTEPS = kF16 ? 4 : 8;  // MMAs per 8x8 pixel tile: K = 8 (one tile row) or 16 (two tile rows)
+            if (((a - acc0) & (n_iss - 1)) == iss) {
 #pragma unroll
-            for (int ks = 0; ks < KSTEPS; ++ks) {
-              umma_ss<kF16 ? 0 : 1>(d_tmem, da, db0 + ks * (kF16 ? 128 : 64), idesc, (first | ks) != 0 ? 1u : 0u);
-              da += kF16 ? 2 * row_step : row_step;
+              for (int ks = 0; ks < KSTEPS; ++ks) {
+                umma_ss<kF16 ? 0 : 1>(d_tmem, da, db0 + ks * (kF16 ? 128 : 64), idesc, (first | ks) != 0 ? 1u : 0u);
+                da += kF16 ? 2 * row_step : row_step;
+              }
             }
             d_tmem += N;
             if (++g == p.kgroups) { g = 0; if (++r == p.rk) { r = 0; ++c; } }
@@ -691,6 +700,7 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
   p.dw = dw; p.partial = ws; p.alpha = alpha; p.scale = scale;
   p.sx = x->scale; p.sdz = dz->scale;
   p.err_sink = error_sink_device();
+  { const char* e2 = getenv("UEGAN_WGRAD_ISSUERS"); p.two_issuers = !(e2 && e2[0] == '1'); }
   const CUtensorMapDataType tdt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapSwizzle tsw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX, tmZ;
@@ -782,6 +792,7 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
   p.dw = dw_oihw; p.partial = ws; p.alpha = alpha_dev; p.scale = scale;
   p.sx = x->scale; p.sdz = e->scale;
   p.err_sink = error_sink_device();
+  { const char* e2 = getenv("UEGAN_WGRAD_ISSUERS"); p.two_issuers = !(e2 && e2[0] == '1'); }
   const CUtensorMapDataType tdt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapSwizzle tsw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX, tmZ;
@@ -881,6 +892,7 @@ extern "C" int uegan_conv2d_wgrad_zwin(const uegan_tensor* x, const uegan_tensor
   p.dw = dw_oihw; p.partial = ws; p.alpha = alpha_dev; p.scale = scale;
   p.sx = x->scale; p.sdz = dz->scale;
   p.err_sink = error_sink_device();
+  { const char* e2 = getenv("UEGAN_WGRAD_ISSUERS"); p.two_issuers = !(e2 && e2[0] == '1'); }
   CUtensorMap tmX, tmZ;
   {  // x, padded extent: {c, w, h, n}
     const uint64_t pix = (uint64_t)x->c * es, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
