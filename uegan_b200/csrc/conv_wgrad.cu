@@ -381,10 +381,17 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   if (!swap) p.taps = (p.taps_total + p.tap_group - 1) / p.tap_group;
   p.a_bytes = a_bytes;
   p.stage_bytes = a_bytes + p.n_boxes * kWgBoxBytes;
-  p.num_stages = (200 * 1024) / p.stage_bytes;
+  // Two CTAs per SM (each with half the smem ring and 256 of the 512 TMEM columns) when two stages still fit: the
+  // launches are latency-bound (one TMA thread, one MMA thread, a short epilogue), and a second resident CTA overlaps them.
+  const char* occ_env = getenv("UEGAN_WGRAD_OCC");
+  const int occ = occ_env ? atoi(occ_env) : 2;
+  const int groups = p.taps * p.m_tiles * p.n_chunks;
+  // (only launches that are split into two waves' worth of CTAs anyway: a one-wave launch wants the deep ring; measured
+  // r2z: D's d5 0.089 -> 0.118 ms with the halved ring, every two-wave launch 5 - 20 % faster)
+  const int budget = (occ >= 2 && 2 * p.stage_bytes <= 100 * 1024 && 2 * groups < num_sms()) ? 100 * 1024 : 200 * 1024;
+  p.num_stages = budget / p.stage_bytes;
   if (p.num_stages > 4) p.num_stages = 4;
   UEGAN_CHECK(p.num_stages >= 2, "conv2d_wgrad: stage too large");
-  const int groups = p.taps * p.m_tiles * p.n_chunks;
   // two full waves of single-CTA SMs (rounding UP left a third, mostly empty wave); launches that fill half the SMs by
   // themselves are not split at all (no partial planes, no reduction pass)
   int ksplit = 2 * groups >= num_sms() ? 1 : (2 * num_sms()) / groups;
@@ -470,6 +477,7 @@ struct WgradPatchParams {
   // col_rev: the tap index runs backwards (the stack is a sliding WINDOW over dz itself, see uegan_conv2d_wgrad_zwin)
   int n_cols, col_c, col_rev;
   int two_issuers;  // warps 1 and 3 both issue MMAs (alternate accumulators)
+  int tmem_cols;    // TMEM columns the CTA allocates: 512, or 256 when its accumulators fit (two CTAs per SM then)
   float* dw;
   float* partial;
   long long dw_numel;
@@ -515,7 +523,7 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     mbar_init(&done_bar, n_iss);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  if (warp == 2) tmem_alloc(&tmem_base_smem, p.tmem_cols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -634,7 +642,7 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 // returns 1 if the patch kernel took the job, 0 if the caller should use the generic kernel, -1 on error
@@ -701,6 +709,7 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
   p.sx = x->scale; p.sdz = dz->scale;
   p.err_sink = error_sink_device();
   { const char* e2 = getenv("UEGAN_WGRAD_ISSUERS"); p.two_issuers = !(e2 && e2[0] == '1'); }
+  if (p.tmem_cols == 0) p.tmem_cols = 512;
   const CUtensorMapDataType tdt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapSwizzle tsw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX, tmZ;
@@ -793,6 +802,7 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
   p.sx = x->scale; p.sdz = e->scale;
   p.err_sink = error_sink_device();
   { const char* e2 = getenv("UEGAN_WGRAD_ISSUERS"); p.two_issuers = !(e2 && e2[0] == '1'); }
+  if (p.tmem_cols == 0) p.tmem_cols = 512;
   const CUtensorMapDataType tdt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapSwizzle tsw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX, tmZ;
@@ -873,7 +883,14 @@ extern "C" int uegan_conv2d_wgrad_zwin(const uegan_tensor* x, const uegan_tensor
   const int nch = (p.chunks + slices - 1) / slices;
   p.acc_per_cta = nch * p.kgroups;
   p.stage_bytes = nch * p.patch_bytes + p.dz_bytes;
-  p.num_stages = (200 * 1024) / p.stage_bytes;
+  {
+    // two CTAs per SM when the accumulators fit half the TMEM and three stages fit half the shared memory
+    const char* occ_env = getenv("UEGAN_WGRAD_OCC");
+    const int occ = occ_env ? atoi(occ_env) : 2;
+    const bool two = occ >= 2 && p.acc_per_cta * N <= 256 && 3 * p.stage_bytes <= 100 * 1024;
+    p.tmem_cols = two ? 256 : 512;
+    p.num_stages = (two ? 100 * 1024 : 200 * 1024) / p.stage_bytes;
+  }
   if (p.num_stages > 6) p.num_stages = 6;
   UEGAN_CHECK(p.num_stages >= 2, "conv2d_wgrad_zwin: stage too large");
   const int We = dz->w + k - 1;
@@ -893,6 +910,7 @@ extern "C" int uegan_conv2d_wgrad_zwin(const uegan_tensor* x, const uegan_tensor
   p.sx = x->scale; p.sdz = dz->scale;
   p.err_sink = error_sink_device();
   { const char* e2 = getenv("UEGAN_WGRAD_ISSUERS"); p.two_issuers = !(e2 && e2[0] == '1'); }
+  if (p.tmem_cols == 0) p.tmem_cols = 512;
   CUtensorMap tmX, tmZ;
   {  // x, padded extent: {c, w, h, n}
     const uint64_t pix = (uint64_t)x->c * es, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
