@@ -78,6 +78,8 @@ typedef struct uegan_conv_desc {
   double* in_stats;            /* optional [n][cout][2]: the epilogue accumulates sum / sum of squares of the stored
                                   outputs per (n, c) (zeroed by the call); consumed by uegan_instance_norm_apply.
                                   Needs Ho*Wo >= 128 (tiles within one image). */
+  const uegan_tensor* y_premul; /* optional, with `mul` (16-bit tensors): the output BEFORE the multiplication is stored here
+                                  as well (own scale) -- training keeps y4 next to y4.mul(x1), models.py:70 */
   int32_t y_cls_c;             /* 0, or (with y_mul = 2, y_off = 0) ALL FOUR parity classes of a stride-2 data gradient in
                                   one launch: cout = 4 * y_cls_c output columns, column (pi*2 + pj) * y_cls_c + c is
                                   channel c of the output pixel (2a + pi, 2b + pj); w_packed = the four class operands
@@ -184,6 +186,13 @@ int uegan_unpack_nchw(const uegan_tensor* src, int32_t c_off, int32_t c_count, f
  * ws: rows + cols + 8 floats of scratch. */
 int uegan_spectral_sigma(const float* w, float* u, float* v, int32_t rows, int32_t cols, int32_t train,
                          float* sigma_out, float* ws, void* stream);
+/* The same for `count` (<= 8) independent layers at once -- one launch per phase for the whole Discriminator (models.py:139-
+ * 155: five spectrally-normalised convs per pass) instead of four per layer.  Tables are HOST arrays of device pointers;
+ * ws[l] as above.  u_used / v_used (optional, may hold NULLs): copies of the u / v the pass ends with, which the backward
+ * of THIS pass needs after later passes have moved u / v on. */
+int uegan_spectral_sigma_batch(int32_t count, const float* const* w, float* const* u, float* const* v, const int32_t* rows,
+                               const int32_t* cols, int32_t train, float* const* sigma_out, float* const* ws,
+                               float* const* u_used, float* const* v_used, void* stream);
 
 /* Relativistic average GAN loss summed over `nscales` prediction maps (GANLoss.__call__, losses.py:393-409 with
  * gan_mode 'rahinge' (mode 0, losses.py:348-362) or 'rals' (mode 1, :363-377)).  real[i] / fake[i]: fp32 maps of
@@ -260,6 +269,13 @@ int uegan_grad_combine(const uegan_tensor* dst, int32_t dst_c_off, int32_t chann
                        int32_t a_c_off, int32_t pad_a, int32_t pad_mode_a, const uegan_tensor* add_b, int32_t b_c_off,
                        const uegan_tensor* add_c, int32_t c_c_off, const uegan_tensor* mask, int32_t mask_c_off,
                        int32_t act, const uegan_tensor* mul, int32_t mul_c_off, void* stream);
+/* The same with a second output from the same pass: dst2 (halo 0) = mul2 * ( fold(src_a) + add_b + add_c ), i.e. the sum
+ * before mask / mul.  Both factors of y4.mul(x1) (models.py:70) get their gradients from ONE read of the incoming one. */
+int uegan_grad_combine2(const uegan_tensor* dst, int32_t dst_c_off, int32_t channels, const uegan_tensor* src_a,
+                        int32_t a_c_off, int32_t pad_a, int32_t pad_mode_a, const uegan_tensor* add_b, int32_t b_c_off,
+                        const uegan_tensor* add_c, int32_t c_c_off, const uegan_tensor* mask, int32_t mask_c_off,
+                        int32_t act, const uegan_tensor* mul, int32_t mul_c_off, const uegan_tensor* dst2,
+                        int32_t dst2_c_off, const uegan_tensor* mul2, int32_t mul2_c_off, void* stream);
 /* Adjoint of nn.ReflectionPad2d IN PLACE: t (halo = pad) holds the gradient w.r.t. the reflect-padded input of a conv
  * (what the dgrad launches of uegan_conv2d_fprop write, extent (h + 2 pad) x (w + 2 pad)); interior pixels within `pad`
  * of an edge receive their reflected halo copies, then the halo is zeroed.  Same result as uegan_grad_combine with src_a

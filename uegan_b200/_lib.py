@@ -36,7 +36,7 @@ class ConvDesc(C.Structure):
                 ("stride", C.c_int32), ("pad", C.c_int32), ("act", C.c_int32), ("w_packed", C.c_void_p),
                 ("w_scale", C.c_void_p), ("bias", C.c_void_p), ("alpha", C.c_void_p), ("mul", C.POINTER(Tensor)), ("out_nchw", C.c_void_p),
                 ("residual_nchw", C.c_void_p), ("aux_nchw", C.c_void_p), ("y_mul", C.c_int32), ("y_off_h", C.c_int32), ("y_off_w", C.c_int32),
-                ("mask", C.POINTER(Tensor)), ("mask_act", C.c_int32), ("in_stats", C.c_void_p), ("y_cls_c", C.c_int32)]
+                ("mask", C.POINTER(Tensor)), ("mask_act", C.c_int32), ("in_stats", C.c_void_p), ("y_premul", C.POINTER(Tensor)), ("y_cls_c", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/uegan_sm100.h declares
@@ -65,6 +65,9 @@ SYMBOLS = {
                                             C.c_void_p]),
     "uegan_spectral_sigma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uegan_spectral_sigma_batch": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p),
+                                             C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "uegan_instance_norm_stats": (C.c_int, [C.POINTER(Tensor), C.c_float, C.c_void_p, C.c_int32,
                                             C.POINTER(C.c_void_p), C.c_void_p]),
     "uegan_gan_loss_fwd": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
@@ -98,6 +101,10 @@ SYMBOLS = {
                                      C.c_int32, C.POINTER(Tensor), C.c_int32, C.POINTER(Tensor), C.c_int32,
                                      C.POINTER(Tensor), C.c_int32, C.c_int32, C.POINTER(Tensor), C.c_int32,
                                      C.c_void_p]),
+    "uegan_grad_combine2": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.POINTER(Tensor), C.c_int32, C.c_int32,
+                                      C.c_int32, C.POINTER(Tensor), C.c_int32, C.POINTER(Tensor), C.c_int32,
+                                      C.POINTER(Tensor), C.c_int32, C.c_int32, C.POINTER(Tensor), C.c_int32,
+                                      C.POINTER(Tensor), C.c_int32, C.POINTER(Tensor), C.c_int32, C.c_void_p]),
     "uegan_channel_sum": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "uegan_instance_norm_bwd": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.POINTER(Tensor), C.c_void_p,
                                           C.POINTER(Tensor), C.c_void_p, C.c_void_p]),

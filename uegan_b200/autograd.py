@@ -145,11 +145,12 @@ def _g_forward_pass(G, x, ws):
             G._wscale(name, holder)
         G._update_weight_scales()
 
-    def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE):
+    def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE, mul=None, premul=None):
         cv = holder.conv
-        K.conv_fprop(src, G._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, 0, cv.bias, None, act_,
-                     w_scale=G._wscale(name, cv))
+        K.conv_fprop(src, G._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, 0, cv.bias, None, act_, mul=mul,
+                     w_scale=G._wscale(name, cv), premul=premul)
 
+    f16_premul = G._dtype != F32 and __import__("os").environ.get("UEGAN_NO_PREMUL") != "1"
     K.pack_input(x, P["x0"], L.PAD_REFLECT)
     conv(P["x0"], "enc1", G.enc1, d, 7, 1, P["x1"], act); K.halo_fill(P["x1"])
     conv(P["x1"], "enc2", G.enc2, 2 * d, 3, 2, P["x2"], act); K.halo_fill(P["x2"])
@@ -165,9 +166,14 @@ def _g_forward_pass(G, x, ws):
         K.upsample2x(P["u"][i], P["cat"][i], 0)
         _gam_forward(G, f"ga{4-i}", gas[i], skips[i], ch, P["z"][i], P["cat"][i], ch, P["st"][i], ws)
         K.halo_fill(P["cat"][i])
-        conv(P["cat"][i], f"dec{i+1}", decs[i], ch, 3, 1, P["y"][i], act)
+        if i == 3 and f16_premul:
+            # y4.mul(x1), models.py:70, in dec4's epilogue; y4 itself (kept for backward) is its second output
+            conv(P["cat"][i], f"dec{i+1}", decs[i], ch, 3, 1, P["y4m"], act, mul=P["x1"], premul=P["y"][i])
+        else:
+            conv(P["cat"][i], f"dec{i+1}", decs[i], ch, 3, 1, P["y"][i], act)
         src = P["y"][i]
-    K.grad_combine(P["y4m"], d, add_b=P["y"][3], mul=P["x1"])  # y4.mul(x1), models.py:70 (y4 itself is kept for backward)
+    if not f16_premul:
+        K.grad_combine(P["y4m"], d, add_b=P["y"][3], mul=P["x1"])  # y4.mul(x1) (y4 itself is kept for backward)
     K.halo_fill(P["y4m"])
     conv(P["y4m"], "dec5.0", G.dec5[0], d, 3, 1, P["t"]); K.halo_fill(P["t"])
     out = torch.empty_like(x)
@@ -268,9 +274,8 @@ def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
     K.conv_dgrad(dt, c50.weight, 3, 1, dxp2, cache, "dec5.0", w_scale=wsc("dec5.0", c50))
     # y4m = y4 * x1 ;  y4 = act(z4)
     dz = S("dz_dec3", h, w, d, 2)
-    K.grad_combine(dz, d, src_a=dxp2, pad_a=1, mul=P["x1"], mask=P["y"][3], act=act)
     dx1a = S("dx1a", h, w, d)
-    K.grad_combine(dx1a, d, src_a=dxp2, pad_a=1, mul=P["y"][3])
+    K.grad_combine(dz, d, src_a=dxp2, pad_a=1, mul=P["x1"], mask=P["y"][3], act=act, dst2=dx1a, mul2=P["y"][3])
     # ---- decoder stages 4..1
     skips = [P["x4"], P["x3"], P["x2"], P["x1"]]
     dskip = [None] * 4
@@ -427,11 +432,11 @@ def _d_forward_train(D, x, ws):
 
 def _d_advance_sn(D, dev):
     """One power iteration of every spectrally-normalised conv (what a train-mode forward does, models.py:185-188)."""
-    sig = torch.empty(2, dtype=torch.float32, device=dev)
-    for i in range(1, 6):
-        conv, wgt = D._conv(i), D._weight(i)
-        scratch = torch.empty(wgt.shape[0] + wgt.numel() // wgt.shape[0] + 8, dtype=torch.float32, device=dev)
-        K.spectral_sigma(wgt, conv.weight_u, conv.weight_v, True, sig, scratch)
+    wl = [D._weight(i) for i in range(1, 6)]
+    sigs = [torch.empty(2, dtype=torch.float32, device=dev) for _ in wl]
+    scr = [torch.empty(w_.shape[0] + w_.numel() // w_.shape[0] + 8, dtype=torch.float32, device=dev) for w_ in wl]
+    K.spectral_sigma_batch(wl, [D._conv(i).weight_u for i in range(1, 6)], [D._conv(i).weight_v for i in range(1, 6)],
+                           True, sigs, scr)
 
 
 def _d_forward_pass(D, x, ws, training):
@@ -439,16 +444,22 @@ def _d_forward_pass(D, x, ws, training):
     dt = D._dtype
     K.pack_input(x, ws["x0"], L.PAD_REFLECT)
     src, preds = ws["x0"], []
-    ws["u"], ws["v"] = [], []
+    if D.use_sn:
+        # all five layers' power iterations in one launch per phase (the layers are independent); the kernels also leave
+        # copies of the u / v this forward used in the workspace (later forwards move the module's buffers on)
+        nl = len(D._SPEC)
+        wl = [D._weight(i) for i in range(1, nl + 1)]
+        if "sn_scratch" not in ws:
+            f32 = lambda n: torch.empty(n, dtype=torch.float32, device=x.device)
+            ws["sn_scratch"] = [f32(w_.shape[0] + w_.numel() // w_.shape[0] + 8) for w_ in wl]
+            ws["u"] = [f32(w_.shape[0]) for w_ in wl]
+            ws["v"] = [f32(w_.numel() // w_.shape[0]) for w_ in wl]
+        K.spectral_sigma_batch(wl, [D._conv(i).weight_u for i in range(1, nl + 1)],
+                               [D._conv(i).weight_v for i in range(1, nl + 1)], training, ws["sig"], ws["sn_scratch"],
+                               ws["u"], ws["v"])
     for i, (k, pad) in enumerate(D._SPEC, start=1):
         conv, head, wgt = D._conv(i), D._head(i), D._weight(i)
-        alpha = None
-        if D.use_sn:
-            scratch = torch.empty(wgt.shape[0] + wgt.numel() // wgt.shape[0] + 8, dtype=torch.float32, device=x.device)
-            K.spectral_sigma(wgt, conv.weight_u, conv.weight_v, training, ws["sig"][i - 1], scratch)
-            alpha = ws["sig"][i - 1][1:2]
-            ws["u"].append(conv.weight_u.detach().clone())  # the values this forward used (later forwards move on)
-            ws["v"].append(conv.weight_v.detach().clone())
+        alpha = ws["sig"][i - 1][1:2] if D.use_sn else None
         dst = ws["ds"][i - 1]
         wsc = D._wscale(f"d{i}", wgt)
         wp = D._wcache.get((f"d{i}", dt), wgt, lambda out=None: K.packed_weight(wgt, src.c, dt, out=out, w_scale=wsc))

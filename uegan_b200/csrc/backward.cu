@@ -63,6 +63,10 @@ struct CombineArgs {
   TGeom c; int c_c_off; int has_c;
   TGeom mask; int mask_c_off; int act; int has_mask;
   TGeom mul; int mul_c_off; int has_mul;
+  // optional second output (halo 0): dst2 = mul2 * ( fold(src_a) + add_b + add_c ) -- the same sum before mask / mul
+  // (the two factors of y4.mul(x1), models.py:70, get their gradients from one read of the incoming gradient)
+  TGeom dst2; int dst2_c_off; int has_dst2;
+  TGeom mul2; int mul2_c_off;
   int cch;  // channels produced
 };
 // grid = (x-chunks of a padded row, padded rows, images): no per-thread divisions (cv is a power of two)
@@ -114,6 +118,14 @@ __global__ void grad_combine_kernel(CombineArgs q, int cv_log2) {
       Vec<T>::load(static_cast<const T*>(q.c.data) + toff(q.c, n, y, x, q.c_c_off + c), t);
 #pragma unroll
       for (int k = 0; k < VN; ++k) v[k] += t[k] * fc;
+    }
+    if (q.has_dst2) {
+      float t[VN], o2[VN];
+      const float f2 = tscale(q.dst2) * tinv(q.mul2) / so;  // the sum is in dst's scale: powers of two, exact
+      Vec<T>::load(static_cast<const T*>(q.mul2.data) + toff(q.mul2, n, y, x, q.mul2_c_off + c), t);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) o2[k] = v[k] * (t[k] * f2);
+      Vec<T>::store(static_cast<T*>(q.dst2.data) + toff(q.dst2, n, y, x, q.dst2_c_off + c), o2);
     }
     if (q.has_mul) {
       float t[VN];
@@ -585,10 +597,11 @@ int uegan_head_bwd(const float* dout_nchw, const float* out_nchw, const float* x
   return 0;
 }
 
-int uegan_grad_combine(const uegan_tensor* dst, int32_t dst_c_off, int32_t channels, const uegan_tensor* src_a,
-                       int32_t a_c_off, int32_t pad_a, int32_t pad_mode_a, const uegan_tensor* add_b, int32_t b_c_off,
-                       const uegan_tensor* add_c, int32_t c_c_off, const uegan_tensor* mask, int32_t mask_c_off,
-                       int32_t act, const uegan_tensor* mul, int32_t mul_c_off, void* stream) {
+static int grad_combine_impl(const uegan_tensor* dst, int32_t dst_c_off, int32_t channels, const uegan_tensor* src_a,
+                             int32_t a_c_off, int32_t pad_a, int32_t pad_mode_a, const uegan_tensor* add_b, int32_t b_c_off,
+                             const uegan_tensor* add_c, int32_t c_c_off, const uegan_tensor* mask, int32_t mask_c_off,
+                             int32_t act, const uegan_tensor* mul, int32_t mul_c_off, const uegan_tensor* dst2,
+                             int32_t dst2_c_off, const uegan_tensor* mul2, int32_t mul2_c_off, void* stream) {
   UEGAN_CHECK(dst && dst->data && (src_a || add_b || add_c), "grad_combine: null pointer");
   CombineArgs q;
   memset(&q, 0, sizeof(q));
@@ -611,6 +624,12 @@ int uegan_grad_combine(const uegan_tensor* dst, int32_t dst_c_off, int32_t chann
   if (add_c) { if (chk(add_c, c_c_off, 0, "add_c")) return -1; q.c = geom(*add_c); q.c_c_off = c_c_off; q.has_c = 1; }
   if (mask) { if (chk(mask, mask_c_off, 0, "mask")) return -1; q.mask = geom(*mask); q.mask_c_off = mask_c_off; q.has_mask = 1; }
   if (mul) { if (chk(mul, mul_c_off, 0, "mul")) return -1; q.mul = geom(*mul); q.mul_c_off = mul_c_off; q.has_mul = 1; }
+  if (dst2) {
+    UEGAN_CHECK(mul2 && dst2->halo == 0, "grad_combine2: the second output needs its factor mul2 and a halo of 0");
+    if (chk(dst2, dst2_c_off, 0, "dst2") || chk(mul2, mul2_c_off, 0, "mul2")) return -1;
+    q.dst2 = geom(*dst2); q.dst2_c_off = dst2_c_off; q.has_dst2 = 1;
+    q.mul2 = geom(*mul2); q.mul2_c_off = mul2_c_off;
+  }
   const int cv = channels / vn;
   int cv_log2 = 0;
   while ((1 << cv_log2) < cv) ++cv_log2;
@@ -621,6 +640,24 @@ int uegan_grad_combine(const uegan_tensor* dst, int32_t dst_c_off, int32_t chann
   UEGAN_DISPATCH(dst->dtype, grad_combine_kernel, <<<grid, 256, 0, st>>>(q, cv_log2));
   UEGAN_CUDA(cudaGetLastError());
   return 0;
+}
+
+int uegan_grad_combine(const uegan_tensor* dst, int32_t dst_c_off, int32_t channels, const uegan_tensor* src_a,
+                       int32_t a_c_off, int32_t pad_a, int32_t pad_mode_a, const uegan_tensor* add_b, int32_t b_c_off,
+                       const uegan_tensor* add_c, int32_t c_c_off, const uegan_tensor* mask, int32_t mask_c_off,
+                       int32_t act, const uegan_tensor* mul, int32_t mul_c_off, void* stream) {
+  return grad_combine_impl(dst, dst_c_off, channels, src_a, a_c_off, pad_a, pad_mode_a, add_b, b_c_off, add_c, c_c_off, mask,
+                           mask_c_off, act, mul, mul_c_off, nullptr, 0, nullptr, 0, stream);
+}
+
+int uegan_grad_combine2(const uegan_tensor* dst, int32_t dst_c_off, int32_t channels, const uegan_tensor* src_a,
+                        int32_t a_c_off, int32_t pad_a, int32_t pad_mode_a, const uegan_tensor* add_b, int32_t b_c_off,
+                        const uegan_tensor* add_c, int32_t c_c_off, const uegan_tensor* mask, int32_t mask_c_off,
+                        int32_t act, const uegan_tensor* mul, int32_t mul_c_off, const uegan_tensor* dst2,
+                        int32_t dst2_c_off, const uegan_tensor* mul2, int32_t mul2_c_off, void* stream) {
+  UEGAN_CHECK(dst2 && mul2, "grad_combine2: null second output");
+  return grad_combine_impl(dst, dst_c_off, channels, src_a, a_c_off, pad_a, pad_mode_a, add_b, b_c_off, add_c, c_c_off, mask,
+                           mask_c_off, act, mul, mul_c_off, dst2, dst2_c_off, mul2, mul2_c_off, stream);
 }
 
 int uegan_fold_inplace(const uegan_tensor* t, void* stream) {

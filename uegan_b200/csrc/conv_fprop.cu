@@ -62,6 +62,10 @@ struct ConvParams {
   const float* smul;  // the `mul` operand
   const void* mul;  // same dtype as out
   long long mul_pix, mul_row, mul_img;
+  // optional second NHWC output: the values BEFORE `mul` (training keeps y4 next to y4 * x1, models.py:70), own scale
+  void* premul;
+  long long pre_pix, pre_row, pre_img;
+  const float* spre;
   const void* mask;  // activation-derivative mask from a forward tensor (dgrad epilogue); dtype mask_kind
   long long mask_pix, mask_row, mask_img;
   int mask_kind, mask_act;
@@ -149,11 +153,12 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
 }
 
 // NHWC epilogue of one warp: its 32 rows x the 16-column chunks {half, half+2, ...} of the tile.
-template <int ACT>
+template <int ACT, int NH>
 __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t taddr, int colbase, int half, long long o,
                                               long long mo, bool valid, float alpha, float bmul, float* stat_slice,
-                                              int mk_n, int mk_h, int mk_w, const float* s_bias) {
-  for (int c0 = half * 16; c0 < p.block_n; c0 += 32) {
+                                              int mk_n, int mk_h, int mk_w, const float* s_bias, long long po,
+                                              float pre_scale) {
+  for (int c0 = half * 16; c0 < p.block_n; c0 += 16 * NH) {
     uint32_t rr[16];
     tmem_ld16(taddr + c0, rr);
     tmem_ld_wait();
@@ -209,6 +214,21 @@ __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t tadd
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = act_t<ACT>(__uint_as_float(rr[i]) * alpha, p.act);
+    }
+    if (p.premul) {  // 16-bit outputs only (checked on the host)
+      uint32_t pk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (p.out_kind == UEGAN_BF16) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i] * pre_scale, v[2 * i + 1] * pre_scale);
+          pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        } else {
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(v[2 * i + 1] * pre_scale), "f"(v[2 * i] * pre_scale));
+        }
+      }
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.premul) + po + c0);
+      op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
     if (p.mul) {
       if (p.out_kind != UEGAN_F32) {
@@ -316,10 +336,16 @@ __device__ __forceinline__ void epilogue_planar(const ConvParams& p, uint32_t ta
   }
 }
 
-template <int kTf32, int kPatch>
-__global__ void __launch_bounds__(384, 1)
+// kOcc2: the two-CTAs-per-SM build for small-N launches (block_n <= 128): 256 threads (4 epilogue warps instead of 8),
+// <= 128 registers, 256 TMEM columns (2 accumulator stages x 128), <= ~100 KB of shared memory.  Those launches are bound
+// by the latencies of their one-thread producer / issuer and of the per-tile epilogue chain, not by any throughput; a
+// second resident CTA is a second, independent tile pipeline on the same SM.
+template <int kTf32, int kPatch, int kOcc2>
+__global__ void __launch_bounds__(kOcc2 ? 256 : 384, kOcc2 ? 2 : 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const ConvParams p) {
+  constexpr int kAccCols = kOcc2 ? 128 : 256;      // TMEM columns per accumulator stage
+  constexpr int kEpiWarps = kOcc2 ? 4 : 8;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -347,7 +373,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], kEpiWarps);
     }
     mbar_init(&w_full, 1);
     if constexpr (kPatch == 2) {
@@ -358,7 +384,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, kTmemCols);
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 2 * kAccCols);
   if (p.bias && !p.out_nchw) {
     const float bm = (p.sy ? __ldg(p.sy) : 1.0f) / (p.smul ? __ldg(p.smul) : 1.0f);
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_bias[i] = i < p.cout ? __ldg(p.bias + i) * bm : 0.f;
@@ -473,7 +499,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int t = blockIdx.x + iss * gridDim.x; t < p.total_tiles; t += n_iss * gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 0x200 + acc, p.err_sink);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
+        const uint32_t d_tmem = tmem_base + acc * kAccCols;
         if constexpr (kPatch == 2) {
           // same descriptor-window taps as the resident-weight patch mode; the B tile of every (chunk, tap) arrives
           // through the B ring and its slot is released by a commit right after the four MMAs that read it
@@ -594,12 +620,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps: lane quarter = warp & 3, column half = (warp - 4) >> 2) ==========
     const int q = warp & 3;          // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;  // interleaved 16-column chunks: half, half + 2, ...
+    const int half = (warp - 4) >> 2;  // interleaved 16-column chunks: half, half + 2, ... (kOcc2: one warp per quarter)
     const int m = q * 32 + lane;
     // alpha = (1/sigma) * s_y / (s_x * s_w * s_mul): the accumulator is in stored units of x and w, the output in stored
     // units of y (LeakyReLU / ReLU are positively homogeneous; tanh / sigmoid heads write true values: s_y = s_mul = 1)
     const float bmul = (p.sy ? __ldg(p.sy) : 1.0f) / (p.smul ? __ldg(p.smul) : 1.0f);
     const float alpha = (p.alpha ? __ldg(p.alpha) : 1.0f) * bmul / ((p.sx ? __ldg(p.sx) : 1.0f) * (p.sw ? __ldg(p.sw) : 1.0f));
+    // pre-mul output in its own scale: the accumulator times alpha is s_y / s_mul times the true value
+    const float pre_scale = p.premul ? (p.spre ? __ldg(p.spre) : 1.0f) / bmul : 1.0f;
     const int mw = m & (p.tw - 1), mh = (m >> p.tw_log2) & (p.th - 1), mn = m >> (p.tw_log2 + p.th_log2);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -631,18 +659,19 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool valid = (wo < p.Wo) && (ho < p.Ho) && (n < p.Nimg);
       mbar_wait(&tmem_full[acc], acc_phase, 0x400 + acc, p.err_sink);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols;
       const int colbase = tc.nt * p.block_n;
       if (p.out_nchw) {
         if (half == 0) epilogue_planar(p, taddr, colbase, n, ho, wo, valid, alpha);
       } else {
         const long long o = (long long)n * p.out_img + (long long)ho * p.out_row + (long long)wo * p.out_pix + colbase;
         const long long mo = p.mul ? (long long)n * p.mul_img + (long long)ho * p.mul_row + (long long)wo * p.mul_pix + colbase : 0;
+        const long long po = p.premul ? (long long)n * p.pre_img + (long long)ho * p.pre_row + (long long)wo * p.pre_pix + colbase : 0;
         switch (p.act) {
-          case UEGAN_ACT_LRELU: epilogue_nhwc<UEGAN_ACT_LRELU>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo, s_bias); break;
-          case UEGAN_ACT_RELU: epilogue_nhwc<UEGAN_ACT_RELU>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo, s_bias); break;
-          case UEGAN_ACT_NONE: epilogue_nhwc<UEGAN_ACT_NONE>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo, s_bias); break;
-          default: epilogue_nhwc<-1>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo, s_bias); break;
+          case UEGAN_ACT_LRELU: epilogue_nhwc<UEGAN_ACT_LRELU, kOcc2 ? 1 : 2>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo, s_bias, po, pre_scale); break;
+          case UEGAN_ACT_RELU: epilogue_nhwc<UEGAN_ACT_RELU, kOcc2 ? 1 : 2>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo, s_bias, po, pre_scale); break;
+          case UEGAN_ACT_NONE: epilogue_nhwc<UEGAN_ACT_NONE, kOcc2 ? 1 : 2>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo, s_bias, po, pre_scale); break;
+          default: epilogue_nhwc<-1, kOcc2 ? 1 : 2>(p, taddr, colbase, half, o, mo, valid, alpha, bmul, stat_slice, n, ho, wo, s_bias, po, pre_scale); break;
         }
       }
       tcgen05_fence_before();
@@ -656,7 +685,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * kAccCols);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -724,7 +753,16 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   p.chunk_elems = g.chunk_elems;
   p.num_k_chunks = d.k * g.chunks_per_row;
   p.stage_bytes = kABytes + ((p.block_n * 128 + 1023) / 1024) * 1024;
-  p.num_stages = (200 * 1024) / p.stage_bytes;
+  // Two CTAs per SM (conv_fprop_kernel<.., .., 1>) for small-N launches with at least two waves of tiles: budget ~98 KB
+  bool occ2 = false;
+  {
+    const char* env = getenv("UEGAN_CONV_OCC");
+    const int want = env ? atoi(env) : 2;
+    occ2 = want >= 2 && p.block_n <= 128 && !d.in_stats && p.total_tiles >= 2 * num_sms();
+  }
+  long long budget = occ2 ? 98 * 1024 : 200 * 1024;
+  if (occ2 && budget / p.stage_bytes < 3) { occ2 = false; budget = 200 * 1024; }  // (re-checked for the patch modes below)
+  p.num_stages = (int)(budget / p.stage_bytes);
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   p.Wo = Wo; p.Ho = Ho; p.Nimg = x.n; p.cout = d.cout;
   p.act = d.act;
@@ -805,6 +843,18 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
       p.mul = static_cast<const uint8_t*>(mt.data) + moff * dtype_size(mt.dtype);
       p.smul = mt.scale;
     }
+    if (d.y_premul) {
+      const uegan_tensor& pt = *d.y_premul;
+      UEGAN_CHECK(d.mul && pt.data && pt.dtype == y.dtype && y.dtype != UEGAN_F32 && pt.n == y.n && pt.h == y.h && pt.w == y.w &&
+                      pt.c >= d.cout && (pt.c * dtype_size(pt.dtype)) % 16 == 0 && !d.in_stats,
+                  "conv: y_premul needs `mul`, a 16-bit tensor of y's extent and no in_stats");
+      p.pre_pix = pt.c;
+      p.pre_row = t_wp(pt) * pt.c;
+      p.pre_img = t_hp(pt) * p.pre_row;
+      const long long poff = (long long)pt.halo * p.pre_row + (long long)pt.halo * p.pre_pix;
+      p.premul = static_cast<uint8_t*>(pt.data) + poff * dtype_size(pt.dtype);
+      p.spre = pt.scale;
+    }
   }
 
   // ---- patch mode?  stride 1, k > 1, pixel = whole 128-byte chunks, single N tile, weights fit next to >= 2 A stages
@@ -835,15 +885,24 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
     const long long w_total = row16 ? (w_tile * d.k + 1023) / 1024 * 1024 : w_tile * d.k * d.k * (row64 ? 1 : pix_b / 128);
     const bool shape_ok = !(env && env[0] == '1') && d.stride == 1 && d.k > 1 && (pix_b % 128 == 0 || row64 || row16) &&
                           Ho >= 16 && Wo >= 8 && (!row64 || w_total % 1024 == 0) && (!row16 || g.cout_pad <= 256);
-    const bool resident = shape_ok && p.n_tiles == 1 && w_total + 2 * a_stage <= 200 * 1024;
-    const bool resident_deep = resident && w_total + 3 * a_stage <= 200 * 1024;  // >= 3 patch stages in flight
+    bool resident = shape_ok && p.n_tiles == 1 && w_total + 2 * a_stage <= budget;
+    if (occ2 && shape_ok && p.n_tiles == 1 && w_total + 2 * a_stage > budget && w_total + 2 * a_stage <= 200 * 1024) {
+      // the resident-weight patch mode needs the whole SM's shared memory here: it beats plain mode at two CTAs per SM
+      // (two patch stages per CTA are enough at two CTAs per SM: dec4 forward 0.274 -> 0.219 ms, r3c)
+      occ2 = false;
+      budget = 200 * 1024;
+      p.num_stages = (int)(budget / p.stage_bytes);
+      if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+      resident = true;
+    }
+    const bool resident_deep = resident && w_total + 3 * a_stage <= budget;  // >= 3 patch stages in flight
     // Weights that do not fit (or leave only two patch stages: the TMA latency of a patch is then exposed) are streamed
     // through their own ring: the A operand is still fetched once per tile instead of once per tap.
     // (N = 256 launches are MMA-bound in plain mode already: 85-97 % of the tensor peak; they stay there.)
     const char* env3 = getenv("UEGAN_STREAM_MAXN");
     const int stream_max_n = env3 ? atoi(env3) : 0;  // opt-in: measured 1-6 % SLOWER than plain mode
-    if (shape_ok && !row64 && !row16 && !resident_deep && !(env2 && env2[0] == '1') && p.block_n <= stream_max_n && w_tile % 1024 == 0 &&
-        3 * a_stage + 4 * w_tile <= 200 * 1024) {
+    if (shape_ok && !occ2 && !row64 && !row16 && !resident_deep && !(env2 && env2[0] == '1') && p.block_n <= stream_max_n && w_tile % 1024 == 0 &&
+        3 * a_stage + 4 * w_tile <= budget) {
       stream_w = true;
       p.tw = 8; p.th = 16; p.tn = 1; p.tw_log2 = 3; p.th_log2 = 4;
       p.tiles_w = (Wo + 7) / 8;
@@ -860,7 +919,7 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
       p.stage_tx_bytes = PH * PW * 128;
       p.num_stages = 3;
       p.b_ring_off = p.num_stages * p.stage_bytes;
-      p.b_slots = (int)((200 * 1024 - p.b_ring_off) / w_tile);
+      p.b_slots = (int)((budget - p.b_ring_off) / w_tile);
       if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
     } else if (resident) {
       patch = true;
@@ -882,7 +941,7 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
       p.w_total_bytes = (int)w_total;
       p.stage_bytes = (int)a_stage;
       p.stage_tx_bytes = PH * PW * rb;
-      p.num_stages = (int)((200 * 1024 - w_total) / a_stage);
+      p.num_stages = (int)((budget - w_total) / a_stage);
       if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
     }
   }
@@ -939,27 +998,41 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   }
   const int smem_bytes = stream_w ? p.b_ring_off + p.b_slots * p.w_tile_bytes + 1024
                                   : (patch ? p.w_total_bytes : 0) + p.num_stages * p.stage_bytes + 1024;
-  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  const int max_ctas = occ2 ? 2 * num_sms() : num_sms();
+  int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
   {
     static bool attr_set = false;
     if (!attr_set) {
-      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      UEGAN_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr_set = true;
     }
   }
-  if (x.dtype == UEGAN_F32) {
-    if (stream_w) conv_fprop_kernel<1, 2><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
-    else if (patch) conv_fprop_kernel<1, 1><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
-    else conv_fprop_kernel<1, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+  UEGAN_CHECK(!occ2 || smem_bytes <= 100 * 1024, "conv: internal: two-CTA build with %d bytes of shared memory", smem_bytes);
+  if (occ2) {
+    if (x.dtype == UEGAN_F32) {
+      if (patch) conv_fprop_kernel<1, 1, 1><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+      else conv_fprop_kernel<1, 0, 1><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+    } else {
+      if (patch) conv_fprop_kernel<0, 1, 1><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+      else conv_fprop_kernel<0, 0, 1><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+    }
+  } else if (x.dtype == UEGAN_F32) {
+    if (stream_w) conv_fprop_kernel<1, 2, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    else if (patch) conv_fprop_kernel<1, 1, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    else conv_fprop_kernel<1, 0, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
   } else {
-    if (stream_w) conv_fprop_kernel<0, 2><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
-    else if (patch) conv_fprop_kernel<0, 1><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
-    else conv_fprop_kernel<0, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    if (stream_w) conv_fprop_kernel<0, 2, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    else if (patch) conv_fprop_kernel<0, 1, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    else conv_fprop_kernel<0, 0, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
   }
   UEGAN_CUDA(cudaGetLastError());
   return 0;

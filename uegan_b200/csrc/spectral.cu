@@ -103,9 +103,144 @@ __global__ void sn_rank1_kernel(float* __restrict__ a, const float* __restrict__
   else a[i] = r;
 }
 
+// ---- all spectrally-normalised layers of a network in one launch per phase (the layers are independent; only the four
+// phases of one layer depend on each other): 4 launches per Discriminator pass instead of 20.
+constexpr int kSnMaxLayers = 8;
+struct SnBatch {
+  const float* w[kSnMaxLayers];
+  float* u[kSnMaxLayers];
+  float* v[kSnMaxLayers];
+  float* u_used[kSnMaxLayers];  // optional copies of the u / v this pass ends with (what its backward needs)
+  float* v_used[kSnMaxLayers];
+  float* t[kSnMaxLayers];
+  float* wv[kSnMaxLayers];
+  double* sumsq[kSnMaxLayers];
+  float* out[kSnMaxLayers];
+  int rows[kSnMaxLayers], cols[kSnMaxLayers];
+  int train;
+  float eps;
+};
+__global__ void sn_wt_u_batch_kernel(const SnBatch b, int rows_per_block) {
+  const int l = blockIdx.z, rows = b.rows[l], cols = b.cols[l];
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block;
+  if (col >= cols || r0 >= rows) return;
+  const int r1 = min(r0 + rows_per_block, rows);
+  const float* __restrict__ w = b.w[l];
+  const float* __restrict__ u = b.u[l];
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc += __ldg(w + (long long)r * cols + col) * __ldg(u + r);
+  atomicAdd(b.t[l] + col, acc);
+}
+__global__ void sn_sumsq_batch_kernel(const SnBatch b) {
+  const int l = blockIdx.y, n = b.cols[l];
+  const float* __restrict__ t = b.t[l];
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += (double)t[i] * t[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(b.sumsq[l], acc);
+}
+__global__ void sn_w_v_batch_kernel(const SnBatch b) {
+  const int l = blockIdx.y, rows = b.rows[l], cols = b.cols[l];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  float inv = 1.f;
+  if (b.train) inv = 1.f / fmaxf((float)sqrt(*b.sumsq[l]), b.eps);
+  const float* __restrict__ src = b.train ? b.t[l] : b.v[l];
+  const float* __restrict__ w = b.w[l];
+  float acc = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const float vv = src[c] * inv;
+    acc += __ldg(w + (long long)warp * cols + c) * vv;
+    if (warp == 0) {  // row 0's warp also publishes the new v (and the copy this pass's backward reads)
+      if (b.train) b.v[l][c] = vv;
+      if (b.v_used[l]) b.v_used[l][c] = vv;
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) b.wv[l][warp] = acc;
+}
+__global__ void sn_finalize_batch_kernel(const SnBatch b) {
+  __shared__ double sh[32];
+  __shared__ float s_inv;
+  const int l = blockIdx.x, rows = b.rows[l];
+  const float* __restrict__ wv = b.wv[l];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) acc += (double)wv[i] * wv[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
+    s_inv = 1.f / fmaxf((float)sqrt(s), b.eps);
+  }
+  __syncthreads();
+  double dot = 0.0;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    const float ui = b.train ? wv[i] * s_inv : b.u[l][i];
+    if (b.train) b.u[l][i] = ui;
+    if (b.u_used[l]) b.u_used[l][i] = ui;
+    dot += (double)ui * wv[i];
+  }
+  dot = warp_sum(dot);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
+    b.out[l][0] = (float)s;
+    b.out[l][1] = (float)(1.0 / s);
+  }
+}
+
 }  // namespace uegan
 
 using namespace uegan;
+
+extern "C" int uegan_spectral_sigma_batch(int32_t count, const float* const* w, float* const* u, float* const* v,
+                                          const int32_t* rows, const int32_t* cols, int32_t train, float* const* sigma_out,
+                                          float* const* ws, float* const* u_used, float* const* v_used, void* stream) {
+  UEGAN_CHECK(count >= 1 && count <= kSnMaxLayers && w && u && v && rows && cols && sigma_out && ws,
+              "spectral_sigma_batch: 1..%d layers, non-null tables", kSnMaxLayers);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SnBatch b;
+  memset(&b, 0, sizeof(b));
+  int max_rows = 0, max_cols = 0;
+  for (int l = 0; l < count; ++l) {
+    UEGAN_CHECK(w[l] && u[l] && v[l] && sigma_out[l] && ws[l], "spectral_sigma_batch: null pointer (layer %d)", l);
+    b.w[l] = w[l]; b.u[l] = u[l]; b.v[l] = v[l]; b.out[l] = sigma_out[l];
+    b.u_used[l] = u_used ? u_used[l] : nullptr;
+    b.v_used[l] = v_used ? v_used[l] : nullptr;
+    b.rows[l] = rows[l]; b.cols[l] = cols[l];
+    // ws layout as uegan_spectral_sigma: t[cols] | wv[rows] | sumsq (double, 8-byte aligned)
+    b.t[l] = ws[l];
+    b.wv[l] = ws[l] + cols[l];
+    b.sumsq[l] = reinterpret_cast<double*>(ws[l] + ((cols[l] + rows[l] + 1) / 2) * 2);
+    if (rows[l] > max_rows) max_rows = rows[l];
+    if (cols[l] > max_cols) max_cols = cols[l];
+    if (train) {
+      UEGAN_CUDA(cudaMemsetAsync(b.t[l], 0, sizeof(float) * cols[l], st));
+      UEGAN_CUDA(cudaMemsetAsync(b.sumsq[l], 0, sizeof(double), st));
+    }
+  }
+  b.train = train;
+  b.eps = 1e-12f;
+  if (train) {
+    const int rpb = 32;
+    dim3 grid((max_cols + 127) / 128, (max_rows + rpb - 1) / rpb, count);
+    sn_wt_u_batch_kernel<<<grid, 128, 0, st>>>(b, rpb);
+    int sb = (max_cols + 1023) / 1024;
+    if (sb > 32) sb = 32;
+    sn_sumsq_batch_kernel<<<dim3(sb, count), 256, 0, st>>>(b);
+  }
+  sn_w_v_batch_kernel<<<dim3((max_rows * 32 + 255) / 256, count), 256, 0, st>>>(b);
+  sn_finalize_batch_kernel<<<count, 256, 0, st>>>(b);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int uegan_spectral_sigma(const float* w, float* u, float* v, int32_t rows, int32_t cols, int32_t train,
                                     float* sigma_out, float* ws, void* stream) {

@@ -163,10 +163,13 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
                y_c_off: int = 0, bias: Optional[torch.Tensor] = None, alpha: Optional[torch.Tensor] = None,
                act: int = L.ACT_NONE, mul: Optional[NHWC] = None, out_nchw: Optional[torch.Tensor] = None,
                residual_nchw: Optional[torch.Tensor] = None, in_stats: Optional[torch.Tensor] = None,
-               aux_nchw: Optional[torch.Tensor] = None, w_scale: Optional[torch.Tensor] = None):
+               aux_nchw: Optional[torch.Tensor] = None, w_scale: Optional[torch.Tensor] = None,
+               premul: Optional[NHWC] = None):
+    """premul: with `mul`, the output before the multiplication is stored there as well."""
     lib = L.load()
     d = L.ConvDesc()
     d.x = x.ct
+    d.y_premul = C.pointer(premul.ct) if premul is not None else None
     if y is not None:
         d.y = y.ct
     d.y_c_off, d.cout, d.k, d.stride, d.pad, d.act = y_c_off, cout, k, stride, pad, act
@@ -303,6 +306,22 @@ def spectral_sigma(w: torch.Tensor, u: torch.Tensor, v: torch.Tensor, train: boo
     L.check(L.load().uegan_spectral_sigma(w.data_ptr(), u.data_ptr(), v.data_ptr(), rows, cols, int(train),
                                           sigma_out.data_ptr(), ws.data_ptr(), _stream()), "spectral_sigma")
     _count(4 if train else 2, "spectral_sigma")
+
+
+def spectral_sigma_batch(ws_list, us, vs, train: bool, sigma_outs, scratches, u_used=None, v_used=None):
+    """spectral_sigma for several independent layers in one launch per phase (4 launches, or 2 in eval mode).
+    u_used / v_used: optional per-layer fp32 buffers that receive the u / v this pass ends with."""
+    n = len(ws_list)
+    rows = (C.c_int32 * n)(*[w.shape[0] for w in ws_list])
+    cols = (C.c_int32 * n)(*[w.numel() // w.shape[0] for w in ws_list])
+    for w, sg, sc in zip(ws_list, sigma_outs, scratches):
+        assert sc.numel() >= w.shape[0] + w.numel() // w.shape[0] + 8 and sg.numel() >= 2
+    L.check(L.load().uegan_spectral_sigma_batch(n, _ptr_array(ws_list), _ptr_array(us), _ptr_array(vs), rows, cols, int(train),
+                                                _ptr_array(sigma_outs), _ptr_array(scratches),
+                                                _ptr_array(u_used) if u_used is not None else None,
+                                                _ptr_array(v_used) if v_used is not None else None, _stream()),
+            "spectral_sigma_batch")
+    _count(4 if train else 2, "spectral_sigma_batch")
 
 
 def upsample2x(src: NHWC, dst: NHWC, dst_c_off: int = 0):
@@ -600,11 +619,18 @@ def head_bwd(dout: torch.Tensor, out: torch.Tensor, x, mode: int, dz: NHWC):
 def grad_combine(dst: NHWC, channels: int, src_a: Optional[NHWC] = None, pad_a: int = 0, pad_mode_a: int = L.PAD_REFLECT,
                  add_b: Optional[NHWC] = None, add_c: Optional[NHWC] = None, mask: Optional[NHWC] = None,
                  act: int = L.ACT_NONE, mul: Optional[NHWC] = None, dst_c_off: int = 0, a_c_off: int = 0, b_c_off: int = 0,
-                 c_c_off: int = 0, mask_c_off: int = 0, mul_c_off: int = 0):
+                 c_c_off: int = 0, mask_c_off: int = 0, mul_c_off: int = 0, dst2: Optional[NHWC] = None,
+                 mul2: Optional[NHWC] = None):
+    """dst2 / mul2: optional second output (halo 0) = mul2 * (the sum before mask / mul), from the same pass."""
     r = lambda t: t.ref() if t is not None else None
-    L.check(L.load().uegan_grad_combine(dst.ref(), dst_c_off, channels, r(src_a), a_c_off, pad_a, pad_mode_a, r(add_b),
-                                        b_c_off, r(add_c), c_c_off, r(mask), mask_c_off, act, r(mul), mul_c_off,
-                                        _stream()), "grad_combine")
+    if dst2 is not None:
+        L.check(L.load().uegan_grad_combine2(dst.ref(), dst_c_off, channels, r(src_a), a_c_off, pad_a, pad_mode_a, r(add_b),
+                                             b_c_off, r(add_c), c_c_off, r(mask), mask_c_off, act, r(mul), mul_c_off,
+                                             dst2.ref(), 0, mul2.ref(), 0, _stream()), "grad_combine2")
+    else:
+        L.check(L.load().uegan_grad_combine(dst.ref(), dst_c_off, channels, r(src_a), a_c_off, pad_a, pad_mode_a, r(add_b),
+                                            b_c_off, r(add_c), c_c_off, r(mask), mask_c_off, act, r(mul), mul_c_off,
+                                            _stream()), "grad_combine")
     _count(1, f"grad_combine c{channels} pad{pad_a if src_a is not None else '-'}"
               f"{' +b' if add_b is not None else ''}{' +c' if add_c is not None else ''}"
               f"{' mask' if mask is not None else ''}{' mul' if mul is not None else ''}", dst, src_a)
