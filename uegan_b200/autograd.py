@@ -50,6 +50,41 @@ _scratch = _Scratch()
 _FOLD_INPLACE = __import__("os").environ.get("UEGAN_NO_FOLD_INPLACE") != "1"
 
 
+class _Side:
+    """Weight gradients (+ their split-K reductions, bias sums, spectral-norm corrections) are off the critical path of a
+    backward pass: only the optimizer reads them.  They run on ONE side stream, forked after the kernel that produced
+    their gradient operand and joined at the end of the pass, so the data-gradient chain and its HBM-bound elementwise
+    passes overlap with them (in a captured step: parallel branches of the CUDA graph).  Used only with a gradient sink
+    (the trainer's flat buckets): every buffer involved is then persistent, so no allocation crosses streams.  All
+    weight-gradient work shares the side stream, which also serialises the shared split-K workspace.
+    UEGAN_SIDE_STREAM=0 runs everything on the current stream."""
+    enabled = __import__("os").environ.get("UEGAN_SIDE_STREAM", "1") != "0"
+    streams = {}
+
+    @classmethod
+    def get(cls, dev):
+        key = str(dev)
+        st = cls.streams.get(key)
+        if st is None:
+            st = cls.streams[key] = torch.cuda.Stream(device=dev)
+        return st
+
+    @classmethod
+    def run(cls, dev, on, fn):
+        if not (on and cls.enabled):
+            fn()
+            return
+        side = cls.get(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            fn()
+
+    @classmethod
+    def join(cls, dev, on):
+        if on and cls.enabled:
+            torch.cuda.current_stream(dev).wait_stream(cls.get(dev))
+
+
 def _zeros_like(p):
     return torch.zeros_like(p, memory_format=torch.contiguous_format)
 
@@ -150,7 +185,8 @@ def _g_forward_pass(G, x, ws):
         K.conv_fprop(src, G._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, 0, cv.bias, None, act_, mul=mul,
                      w_scale=G._wscale(name, cv), premul=premul)
 
-    f16_premul = G._dtype != F32 and __import__("os").environ.get("UEGAN_NO_PREMUL") != "1"
+    # opt-in (UEGAN_PREMUL=1): measured r3e it moves the multiply's 0.4 ms into dec4's epilogue-bound launch, no net gain
+    f16_premul = G._dtype != F32 and __import__("os").environ.get("UEGAN_PREMUL") == "1"
     K.pack_input(x, P["x0"], L.PAD_REFLECT)
     conv(P["x0"], "enc1", G.enc1, d, 7, 1, P["x1"], act); K.halo_fill(P["x1"])
     conv(P["x1"], "enc2", G.enc2, 2 * d, 3, 2, P["x2"], act); K.halo_fill(P["x2"])
@@ -218,17 +254,24 @@ def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
             return sink[pname], True
         return (_zeros_like(param) if zero else torch.empty_like(param)), False
 
+    side = sink is not None and not dry
+
     def wgrad(name, conv, xin, dz, k, stride, pad, cin_first=0, cin=None, bias_from=None, zero_halo=False):
         """zero_halo: dz's halo holds zeros (every dgrad operand here), which the sliding-window stack path needs."""
         if dry:
             return
         gw, direct = gbuf(name + ".weight", conv.weight)
-        K.conv_wgrad(xin, dz, gw, k, stride, pad, cin_first=cin_first, cin=cin, dz_zero_halo=zero_halo)
         grads[name + ".weight"] = None if direct else gw
+        gb = None
         if bias_from is not None and conv.bias is not None:
-            gb, direct = gbuf(name + ".bias", conv.bias, zero=False)
-            K.channel_sum(bias_from, gb, accumulate=direct)
-            grads[name + ".bias"] = None if direct else gb
+            gb, direct_b = gbuf(name + ".bias", conv.bias, zero=False)
+            grads[name + ".bias"] = None if direct_b else gb
+
+        def run():
+            K.conv_wgrad(xin, dz, gw, k, stride, pad, cin_first=cin_first, cin=cin, dz_zero_halo=zero_halo)
+            if gb is not None:
+                K.channel_sum(bias_from, gb, accumulate=direct_b)
+        _Side.run(dev, side, run)
 
     def dead(pname, param):
         grads[pname] = None if sink is not None else torch.zeros_like(param)
@@ -242,23 +285,24 @@ def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
     elif K.zwin_ok(3, P["t"], dz5, 7):
         # the horizontal taps are a sliding window over the zero-haloed dz5 itself: only the 7 vertical taps are enumerated
         gw, direct = gbuf("dec5.1.main.1.weight", c51.weight)
-        K.conv_wgrad(P["t"], dz5, gw, 7, 1, 3, dz_zero_halo=True)
+        _Side.run(dev, side, lambda: K.conv_wgrad(P["t"], dz5, gw, 7, 1, 3, dz_zero_halo=True))
         grads["dec5.1.main.1.weight"] = None if direct else gw
     elif K.hstack_ok(3, d, 7):
         # horizontal taps unrolled into the gradient's channels: the wgrad keeps only the 7 vertical taps
         e5 = S("dz5e", h, w + 6, 32, 0, share=dz5)
         K.dz_hstack(dz5, 3, 7, e5)
         gw, direct = gbuf("dec5.1.main.1.weight", c51.weight)
-        K.conv_wgrad_hstack(P["t"], e5, gw, 7, 3)
+        _Side.run(dev, side, lambda: K.conv_wgrad_hstack(P["t"], e5, gw, 7, 3))
         grads["dec5.1.main.1.weight"] = None if direct else gw
     else:
         dz5w = S("dz5w", h, w, 32, 0, share=dz5)  # the same gradient with 32 stored channels (wgrad operand)
         K.head_bwd(out_grad, P["res"], x, 2, dz5w)
         wgrad("dec5.1.main.1", c51, P["t"], dz5w, 7, 1, 3)
     if not dry:
-        gb, direct = gbuf("dec5.1.main.1.bias", c51.bias, zero=False)
-        K.channel_sum(dz5, gb, 0, rgb_c, accumulate=direct)  # one stored vector reduced, the 3 real channels written
-        grads["dec5.1.main.1.bias"] = None if direct else gb
+        gb51, direct51 = gbuf("dec5.1.main.1.bias", c51.bias, zero=False)
+        # one stored vector reduced, the 3 real channels written
+        _Side.run(dev, side, lambda: K.channel_sum(dz5, gb51, 0, rgb_c, accumulate=direct51))
+        grads["dec5.1.main.1.bias"] = None if direct51 else gb51
     wsc = lambda name, conv: G._wscale(name, conv)
     dxp = S("dxp_t", h + 6, w + 6, d)
     K.conv_dgrad(dz5, c51.weight, 7, 1, dxp, cache, "dec5.1", w_scale=wsc("dec5.1", c51))
@@ -362,6 +406,7 @@ def _g_backward_pass(G, x, out_grad, ws, need_dx, dry=False):
         ga = getattr(G, f"ga{i}")
         dead(f"ga{i}.conv.0.weight", ga.conv[0].weight)
         dead(f"ga{i}.conv.2.weight", ga.conv[2].weight)
+    _Side.join(dev, side)
     return grads, dx
 
 
@@ -502,6 +547,7 @@ def _d_backward_pass(D, x, dpreds, ws, need_dx, need_w=True):
         if sink is not None:
             return sink[pname], True
         return (_zeros_like(param) if zero else torch.empty_like(param)), False
+    side = sink is not None  # weight-gradient work on the side stream (see _Side)
     srcs = [ws["x0"]] + ws["ds"]
     carry = None  # gradient w.r.t. the padded ds_k coming from d_{k+1}
     head_mode = 0 if D._head_act == L.ACT_TANH else 1
@@ -519,15 +565,16 @@ def _d_backward_pass(D, x, dpreds, ws, need_dx, need_w=True):
         if need_w:
             gw, direct = gbuf(f"d{i}_pred.0.1.weight", head.weight)
             if K.zwin_ok(1, ds, dzp, k):
-                K.conv_wgrad(ds, dzp, gw, k, 1, pad, dz_zero_halo=True)
+                _Side.run(dev, side, lambda ds=ds, dzp=dzp, gw=gw, k=k, pad=pad:
+                          K.conv_wgrad(ds, dzp, gw, k, 1, pad, dz_zero_halo=True))
             elif K.hstack_ok(1, ds.c, k):
                 ep = S(f"dzpe{i}", ds.h, ds.w + k - 1, 32, 0, share=dzp)
                 K.dz_hstack(dzp, 1, k, ep)
-                K.conv_wgrad_hstack(ds, ep, gw, k, pad)
+                _Side.run(dev, side, lambda ds=ds, ep=ep, gw=gw, k=k, pad=pad: K.conv_wgrad_hstack(ds, ep, gw, k, pad))
             else:
                 dzpw = S(f"dzpw{i}", ds.h, ds.w, 32, 0, share=dzp)
                 K.head_bwd(dp, ws["preds"][i - 1], None, head_mode, dzpw)
-                K.conv_wgrad(ds, dzpw, gw, k, 1, pad)
+                _Side.run(dev, side, lambda ds=ds, dzpw=dzpw, gw=gw, k=k, pad=pad: K.conv_wgrad(ds, dzpw, gw, k, 1, pad))
             grads[f"d{i}_pred.0.1.weight"] = None if direct else gw
         dxa = S(f"dxa{i}", ds.h + 2 * pad, ds.w + 2 * pad, ds.c)
         K.conv_dgrad(dzp, head.weight, k, 1, dxa, cache, f"p{i}", w_scale=wsp(i))
@@ -554,20 +601,26 @@ def _d_backward_pass(D, x, dpreds, ws, need_dx, need_w=True):
                     gw = _scratch.store.get(("Dsn", i, str(dev)))
                     if gw is None:
                         gw = _scratch.store[("Dsn", i, str(dev))] = torch.empty_like(wgt, memory_format=torch.contiguous_format)
-                    K.zero_(gw)
                 else:
                     gw = tgt
+                dot_ws = _scratch.store.get(("Dsn_dot", i, str(dev)))
+                if dot_ws is None:
+                    dot_ws = _scratch.store[("Dsn_dot", i, str(dev))] = torch.empty(1, dtype=torch.float64, device=dev)
+
+                def run_w(gw=gw, tgt=tgt, direct=direct, xin=xin, dz=dz, k=k, pad=pad, alpha=alpha, wgt=wgt, i=i, dot_ws=dot_ws):
                     K.zero_(gw)
-                K.conv_wgrad(xin, dz, gw, k, 2, pad, alpha=alpha)
-                K.spectral_bwd(gw, wgt, ws["u"][i - 1], ws["v"][i - 1], ws["sig"][i - 1],
-                               torch.empty(1, dtype=torch.float64, device=dev), accum=tgt if direct else None)
+                    K.conv_wgrad(xin, dz, gw, k, 2, pad, alpha=alpha)
+                    K.spectral_bwd(gw, wgt, ws["u"][i - 1], ws["v"][i - 1], ws["sig"][i - 1], dot_ws,
+                                   accum=tgt if direct else None)
+                _Side.run(dev, side, run_w)
                 grads[wname] = None if direct else gw
             else:
                 gw, direct = gbuf(f"d{i}.0.1.weight", wgt)
-                K.conv_wgrad(xin, dz, gw, k, 2, pad, alpha=alpha)
+                _Side.run(dev, side, lambda gw=gw, xin=xin, dz=dz, k=k, pad=pad, alpha=alpha:
+                          K.conv_wgrad(xin, dz, gw, k, 2, pad, alpha=alpha))
                 grads[f"d{i}.0.1.weight"] = None if direct else gw
             gb, direct = gbuf(f"d{i}.0.1.bias", conv.bias, zero=False)
-            K.channel_sum(dz, gb, accumulate=direct)
+            _Side.run(dev, side, lambda dz=dz, gb=gb, direct=direct: K.channel_sum(dz, gb, accumulate=direct))
             grads[f"d{i}.0.1.bias"] = None if direct else gb
         if i > 1:
             dxb = S(f"dxb{i}", xin.h + 2 * pad, xin.w + 2 * pad, xin.c)
@@ -580,7 +633,9 @@ def _d_backward_pass(D, x, dpreds, ws, need_dx, need_w=True):
             K.grad_combine(dx0, 16, src_a=dxb, pad_a=pad)
             dx = torch.empty_like(x)
             K.unpack_input_grad(dx0, None, dx)
+            _Side.join(dev, side)
             return grads, dx
+    _Side.join(dev, side)
     return grads, None
 
 

@@ -140,26 +140,34 @@ __global__ void sn_sumsq_batch_kernel(const SnBatch b) {
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(b.sumsq[l], acc);
 }
-__global__ void sn_w_v_batch_kernel(const SnBatch b) {
+// one BLOCK per row (a warp per row walked d5's 6400 columns in 200 dependent trips: 100 us, latency-bound)
+__global__ void __launch_bounds__(256) sn_w_v_batch_kernel(const SnBatch b) {
+  __shared__ float sh[8];
   const int l = blockIdx.y, rows = b.rows[l], cols = b.cols[l];
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  const int row = blockIdx.x;
+  if (row >= rows) return;
   float inv = 1.f;
   if (b.train) inv = 1.f / fmaxf((float)sqrt(*b.sumsq[l]), b.eps);
   const float* __restrict__ src = b.train ? b.t[l] : b.v[l];
-  const float* __restrict__ w = b.w[l];
+  const float* __restrict__ w = b.w[l] + (long long)row * cols;
   float acc = 0.f;
-  for (int c = lane; c < cols; c += 32) {
+  for (int c = threadIdx.x; c < cols; c += 256) {
     const float vv = src[c] * inv;
-    acc += __ldg(w + (long long)warp * cols + c) * vv;
-    if (warp == 0) {  // row 0's warp also publishes the new v (and the copy this pass's backward reads)
+    acc += __ldg(w + c) * vv;
+    if (row == 0) {  // row 0's block also publishes the new v (and the copy this pass's backward reads)
       if (b.train) b.v[l][c] = vv;
       if (b.v_used[l]) b.v_used[l][c] = vv;
     }
   }
   acc = warp_sum(acc);
-  if (lane == 0) b.wv[l][warp] = acc;
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = sh[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += sh[i];
+    b.wv[l][row] = t;
+  }
 }
 __global__ void sn_finalize_batch_kernel(const SnBatch b) {
   __shared__ double sh[32];
@@ -236,7 +244,7 @@ extern "C" int uegan_spectral_sigma_batch(int32_t count, const float* const* w, 
     if (sb > 32) sb = 32;
     sn_sumsq_batch_kernel<<<dim3(sb, count), 256, 0, st>>>(b);
   }
-  sn_w_v_batch_kernel<<<dim3((max_rows * 32 + 255) / 256, count), 256, 0, st>>>(b);
+  sn_w_v_batch_kernel<<<dim3(max_rows, count), 256, 0, st>>>(b);
   sn_finalize_batch_kernel<<<count, 256, 0, st>>>(b);
   UEGAN_CUDA(cudaGetLastError());
   return 0;

@@ -481,13 +481,16 @@ class Discriminator(nn.Module, _ScaledNet):
         dt = self._dtype
         K.pack_input(x, P["x0"], L.PAD_REFLECT)
         src, preds = P["x0"], []
+        if self.use_sn:
+            # one power iteration per train-mode forward, in place on the weight_u / weight_v buffers; the five layers are
+            # independent, so each phase is one launch for all of them
+            nl = len(self._SPEC)
+            K.spectral_sigma_batch([self._weight(i) for i in range(1, nl + 1)],
+                                   [self._conv(i).weight_u for i in range(1, nl + 1)],
+                                   [self._conv(i).weight_v for i in range(1, nl + 1)], self.training, P["sig"], P["ws"])
         for i, (k, pad) in enumerate(self._SPEC, start=1):
             conv, head, wgt = self._conv(i), self._head(i), self._weight(i)
-            alpha = None
-            if self.use_sn:
-                # one power iteration per train-mode forward, in place on the weight_u / weight_v buffers
-                K.spectral_sigma(wgt, conv.weight_u, conv.weight_v, self.training, P["sig"][i - 1], P["ws"][i - 1])
-                alpha = P["sig"][i - 1][1:2]
+            alpha = P["sig"][i - 1][1:2] if self.use_sn else None
             dst = P["ds"][i - 1]
             wsc = self._wscale(f"d{i}", wgt)
             wp = self._wcache.get((f"d{i}", dt), wgt,
