@@ -1,0 +1,7 @@
+#!/bin/bash
+python -m pytest tests/test_gpu_kernels.py tests/test_gpu_generator_f16.py tests/test_gpu_generator.py tests/test_gpu_losses.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -1
+for m in "UEGAN_NO_ROWSUM64=1 UEGAN_ROWSUM_OCC=1" "UEGAN_ROWSUM_OCC=1" ""; do
+echo "== $m"
+env $m python bench.py --workload inference --steps 30 --warmup 5 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('infer', d['value'], d['ms_per_step'], d['e2e']['value'])"
+done
+python bench.py --steps 10 --warmup 3 --lib-baseline 0 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('train', d['value'], d['ms_per_step'], d['e2e']['value'])"

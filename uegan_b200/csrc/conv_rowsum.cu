@@ -19,7 +19,6 @@
 namespace uegan {
 
 constexpr int kRsStages = 4;
-constexpr int kRsRowBytes = 32 * 128;  // one patch row: 32 pixels x 128 B
 
 struct RowsumParams {
   int k, cout, nb;        // nb: N of the MMA = k*cout rounded up to 16
@@ -31,6 +30,10 @@ struct RowsumParams {
   int patch_off, ph;
   int stage_bytes, num_stages, stage_tx;
   int w_tile_bytes, w_total_bytes;
+  int row_bytes;          // one patch row: 32 pixels x 128 B, or x 64 B (32-channel fp16 pixels: SWIZZLE_64B rows, row64)
+  int row64;
+  int w_tx_bytes;         // exact bytes of the resident weights (w_total_bytes is their 1 KB-rounded smem reservation)
+  int occ2;               // planned for two CTAs per SM
   int Wo, Ho, act;
   const float* bias;
   const float* alpha;
@@ -133,7 +136,7 @@ conv_rowsum_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0) {
     if (elect_one()) {
       // ===================== TMA producer =====================
-      mbar_arrive_expect_tx(&w_full, (uint32_t)p.w_total_bytes);
+      mbar_arrive_expect_tx(&w_full, (uint32_t)p.w_tx_bytes);
       for (int wi = 0; wi < p.k * p.nch; ++wi) {  // weight tile (r, chunk): [nb rows x 128 B], resident
         const int r = wi / p.nch, c = wi % p.nch;
         tma_load_2d(&tmB, &w_full, smem + wi * p.w_tile_bytes, r * p.csp + c * p.cb, 0);
@@ -157,7 +160,9 @@ conv_rowsum_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // ===================== MMA issuer =====================
       const uint32_t idesc = make_instr_desc(kF16 ? UMMA_F16 : UMMA_TF32, 128, p.nb);
       const uint32_t w_addr = smem_u32(smem);
-      const uint64_t db0 = make_smem_desc(w_addr, 16, 1024, UMMA_LAYOUT_SW128);
+      const uint32_t lay = p.row64 ? UMMA_LAYOUT_SW64 : UMMA_LAYOUT_SW128;
+      const uint32_t sbo = p.row64 ? 512 : 1024;
+      const uint64_t db0 = make_smem_desc(w_addr, 16, sbo, lay);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -169,19 +174,21 @@ conv_rowsum_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int c = 0; c < p.nch; ++c) {
           mbar_wait(&full_bar[stage], phase, 0xE20 + stage, p.err_sink);
           tcgen05_fence_after();
-          const uint64_t da0 = make_smem_desc(w_addr + p.w_total_bytes + stage * p.stage_bytes, 16, 1024, UMMA_LAYOUT_SW128);
+          const uint64_t da0 = make_smem_desc(w_addr + p.w_total_bytes + stage * p.stage_bytes, 16, sbo, lay);
           for (int j = 0; j < p.msub; ++j) {
             const uint32_t d_tmem = tmem_base + acc * 128 + j * 32;
-            uint64_t da = desc_adv(da0, (uint32_t)(4 * j) * kRsRowBytes);
+            uint64_t da = desc_adv(da0, (uint32_t)(4 * j) * p.row_bytes);
             uint64_t db = desc_adv(db0, (uint32_t)c * p.w_tile_bytes);
             const uint32_t b_step = (uint32_t)(p.nch * p.w_tile_bytes) >> 4;
             for (int r = 0; r < p.k; ++r) {
-              // 4 MMAs per 128-byte row: 32 bytes of K each (8 tf32 / 16 fp16 values)
+              // 4 MMAs per 128-byte row (2 per 64-byte row): 32 bytes of K each (8 tf32 / 16 fp16 values)
               umma_ss<kF16 ? 0 : 1>(d_tmem, da, db, idesc, (c | r) != 0 ? 1u : 0u);
               umma_ss<kF16 ? 0 : 1>(d_tmem, da + 2, db + 2, idesc, 1u);
-              umma_ss<kF16 ? 0 : 1>(d_tmem, da + 4, db + 4, idesc, 1u);
-              umma_ss<kF16 ? 0 : 1>(d_tmem, da + 6, db + 6, idesc, 1u);
-              da += kRsRowBytes >> 4;
+              if (!p.row64) {
+                umma_ss<kF16 ? 0 : 1>(d_tmem, da + 4, db + 4, idesc, 1u);
+                umma_ss<kF16 ? 0 : 1>(d_tmem, da + 6, db + 6, idesc, 1u);
+              }
+              da += p.row_bytes >> 4;
               db += b_step;
             }
           }
@@ -259,19 +266,31 @@ static int rowsum_cb(int dtype) { return dtype == UEGAN_F32 ? 32 : 64; }
 static int rowsum_plan(int cout, int k, int cs, int dtype, RowsumParams* p) {
   const int cb = rowsum_cb(dtype);
   const int nb = rowsum_nb(cout, k), nch = (cs + cb - 1) / cb;
-  const long long w_total = (long long)k * nch * nb * 128;
-  for (int th = 16; th >= 8; th -= 8) {
-    const long long stage = (long long)(th + k - 1) * kRsRowBytes;
-    const long long room = 200 * 1024 - w_total;
-    if (room >= 2 * stage) {
-      if (p) {
-        p->th = th; p->msub = th / 4; p->ph = th + k - 1;
-        p->stage_bytes = (int)stage; p->stage_tx = (int)stage;
-        p->num_stages = (int)(room / stage) < kRsStages ? (int)(room / stage) : kRsStages;
-        p->w_tile_bytes = nb * 128; p->w_total_bytes = (int)w_total;
-        p->nb = nb; p->nch = nch; p->cs = cs; p->cb = cb; p->csp = nch * cb; p->k = k; p->cout = cout; p->two = 32 - k + 1;
+  // 32-channel fp16 pixels are 64 bytes: SWIZZLE_64B rows (half the smem, TMA bytes and MMAs of a half-empty 128-byte row)
+  const char* e64 = getenv("UEGAN_NO_ROWSUM64");
+  const bool row64 = dtype == UEGAN_F16 && cs == 32 && !(e64 && e64[0] == '1');
+  const int rb = row64 ? 64 : 128;
+  const long long w_total = ((long long)k * nch * nb * rb + 1023) / 1024 * 1024;
+  const char* eocc = getenv("UEGAN_ROWSUM_OCC");
+  const int occ = eocc ? atoi(eocc) : 2;
+  // first choice: two CTAs per SM (<= 98 KB each: th = 8, >= 3 stages); else one CTA with the whole shared memory
+  for (int pass = (occ >= 2 ? 0 : 1); pass < 2; ++pass) {
+    const long long budget = pass == 0 ? 98 * 1024 : 200 * 1024;
+    for (int th = (pass == 0 ? 8 : 16); th >= 8; th -= 8) {
+      const long long stage = (long long)(th + k - 1) * 32 * rb;
+      const long long room = budget - w_total;
+      if (room >= (pass == 0 ? 3 : 2) * stage) {
+        if (p) {
+          p->th = th; p->msub = th / 4; p->ph = th + k - 1;
+          p->stage_bytes = (int)stage; p->stage_tx = (int)stage;
+          p->num_stages = (int)(room / stage) < kRsStages ? (int)(room / stage) : kRsStages;
+          p->w_tile_bytes = nb * rb; p->w_total_bytes = (int)w_total;
+          p->row_bytes = 32 * rb; p->row64 = row64 ? 1 : 0;
+          p->w_tx_bytes = k * nch * nb * rb; p->occ2 = pass == 0 ? 1 : 0;
+          p->nb = nb; p->nch = nch; p->cs = cs; p->cb = cb; p->csp = nch * cb; p->k = k; p->cout = cout; p->two = 32 - k + 1;
+        }
+        return th;
       }
-      return th;
     }
   }
   return 0;
@@ -359,14 +378,15 @@ int uegan_conv2d_fprop_rowsum(const uegan_conv_desc* desc, void* stream) {
     const uint64_t pix = (uint64_t)x.c * es, row = (uint64_t)t_wp(x) * pix, img = (uint64_t)t_hp(x) * row;
     uint64_t dims[4] = {(uint64_t)x.c, (uint64_t)t_wp(x), (uint64_t)t_hp(x), (uint64_t)x.n};
     uint64_t strides[3] = {pix, row, img};
-    uint32_t box[4] = {(uint32_t)p.cb, 32u, (uint32_t)p.ph, 1u};
-    if (encode_tiled(&tmA, tdt, 4, x.data, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    const CUtensorMapSwizzle swz = p.row64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const uint32_t bc = p.row64 ? 32u : (uint32_t)p.cb;  // channels per operand row
+    uint32_t box[4] = {bc, 32u, (uint32_t)p.ph, 1u};
+    if (encode_tiled(&tmA, tdt, 4, x.data, dims, strides, box, swz)) return -1;
     const uint64_t ktot = (uint64_t)d.k * p.csp;
     uint64_t wdims[2] = {ktot, (uint64_t)p.nb};
     uint64_t wstrides[1] = {ktot * es};
-    uint32_t wbox[2] = {(uint32_t)p.cb, (uint32_t)p.nb};
-    if (encode_tiled(&tmB, tdt, 2, const_cast<void*>(d.w_packed), wdims, wstrides, wbox, CU_TENSOR_MAP_SWIZZLE_128B))
-      return -1;
+    uint32_t wbox[2] = {bc, (uint32_t)p.nb};
+    if (encode_tiled(&tmB, tdt, 2, const_cast<void*>(d.w_packed), wdims, wstrides, wbox, swz)) return -1;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -375,7 +395,8 @@ int uegan_conv2d_fprop_rowsum(const uegan_conv_desc* desc, void* stream) {
     attr_set = true;
   }
   const int smem_bytes = p.w_total_bytes + p.num_stages * p.stage_bytes + 1024;
-  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  const int max_ctas = p.occ2 ? 2 * num_sms() : num_sms();
+  const int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
   if (f16) conv_rowsum_kernel<1><<<grid, 384, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   else conv_rowsum_kernel<0><<<grid, 384, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
   UEGAN_CUDA(cudaGetLastError());
