@@ -259,7 +259,9 @@ def test_cuda_graph_replay_matches_eager():
     le = [Te.train_step(raw, exp) for _ in range(5)]
     Tg.capture(raw, exp, warmup=3)          # 3 eager warm-up steps; the capture itself does not execute
     l3 = Tg.replay(raw, exp, sync_scalars=True)   # = step index 3
-    l4 = Tg.replay(raw, exp, sync_scalars=True)   # = step index 4
+    # step index 4 through the one-batch-ahead input pipeline: pinned host batch -> prefetch (copy stream) -> replay(None, None)
+    Tg.prefetch(raw.cpu().pin_memory(), exp.cpu().pin_memory())
+    l4 = Tg.replay(None, None, sync_scalars=True)
     for k in le[3]:  # run-to-run noise (atomics order -> Adam sign flips) is ~3e-3 on g_percep after 3 steps
         assert abs(l3[k] - le[3][k]) / abs(le[3][k]) < 1e-2, (k, l3[k], le[3][k])
         assert abs(l4[k] - le[4][k]) / abs(le[4][k]) < 1e-2, (k, l4[k], le[4][k])
