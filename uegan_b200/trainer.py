@@ -5,9 +5,11 @@ The loop body of the reference (trainer.py:75-119) is factored into `train_step(
 reference does around it that is not on the hot path (tensorboard, PSNR/SSIM/NIMA validation, sample dumps) is not
 re-implemented here -- use the reference's own trainer with `dropin/models.py` + `dropin/losses.py` for those.
 
-Data parallel: one process per GPU, batch sharded; two NCCL all-reduces per step (D gradients before
-`d_optimizer.step()`, G gradients before `g_optimizer.step()`, each ONE flat fp32 bucket) plus the two ~0.3 KB
-all-reduces per GAN-loss evaluation that keep the relativistic means global.
+Data parallel: one process per GPU, batch sharded.  Each network's gradients live in ONE flat fp32 bucket in
+symmetric (peer-mapped) memory; `uegan_adam_step_peers` sums the ranks' buckets in rank order while it applies Adam (D before
+`d_optimizer.step()`, G before `g_optimizer.step()`), and the 16 / 32 doubles per GAN-loss evaluation that keep the
+relativistic means global go through `uegan_peer_sum_f64` -- no NCCL call on the step, so it is captured as one CUDA graph at
+any world size.  NCCL all-reduces of the same buckets are the fallback (`peer_reduce=False`).
 """
 from __future__ import annotations
 
