@@ -176,6 +176,11 @@ int uegan_instance_norm_apply(const uegan_tensor* src, const uegan_tensor* dst, 
                               double* stats_ws, void* stream);
 /* F.interpolate(scale_factor=2, mode='bilinear', align_corners=True) (models.py:191-201) into a channel slice. */
 int uegan_upsample2x(const uegan_tensor* src, const uegan_tensor* dst, int32_t dst_c_off, void* stream);
+/* One decoder concat of the Generator in a single pass (models.py:55-67 `torch.cat([upsample(y), GAM(skip)], 1)`):
+ * dst[.., 0:C) = bilinear x2 (align_corners=True) of u, dst[.., C:2C) = (z - mean) * rstd with the finalised pairs of
+ * uegan_instance_norm_stats(z).  Whole 2C-channel pixels are written (the two separate passes wrote half lines). */
+int uegan_cat_build(const uegan_tensor* u, const uegan_tensor* z, const float* mean_rstd, const uegan_tensor* dst,
+                    void* stream);
 /* nn.MaxPool2d(2,2) of torchvision vgg19.features (losses.py:43). */
 int uegan_maxpool2x2(const uegan_tensor* src, const uegan_tensor* dst, void* stream);
 /* NHWC tensor interior channels [c_off, c_off+c_count) -> NCHW fp32 (test / debug readback). */

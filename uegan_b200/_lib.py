@@ -120,6 +120,7 @@ SYMBOLS = {
     "uegan_unpack_input_grad": (C.c_int, [C.POINTER(Tensor), C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
     "uegan_upsample2x": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_int32, C.c_void_p]),
+    "uegan_cat_build": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p, C.POINTER(Tensor), C.c_void_p]),
     "uegan_maxpool2x2": (C.c_int, [C.POINTER(Tensor), C.POINTER(Tensor), C.c_void_p]),
     "uegan_unpack_nchw": (C.c_int, [C.POINTER(Tensor), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "uegan_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p]),

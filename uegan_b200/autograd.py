@@ -124,12 +124,17 @@ def _g_workspace(G, b, h, w, dev):
     )
 
 
-def _gam_forward(G, name, ga, src, ch, z, dst, off, stats, ws):
+def _gam_forward(G, name, ga, src, ch, z, dst, off, stats, ws, up=None):
+    """up: the low-resolution tensor whose bilinear x2 fills dst[.., 0:ch): the concat is then built in one pass."""
     fuse = ga.fuse[0]
     dt = G._dtype
     wsc = G._wscale(name, fuse)
     wp = G._wcache.get((name, dt), fuse.weight,
                        lambda out=None: K.packed_weight(fuse.weight, src.c, dt, 0, ch, out=out, w_scale=wsc))
+    if up is not None:
+        K.conv_fprop(src, wp, ch, 1, 1, 0, z, w_scale=wsc)
+        ws["mr"][name] = K.cat_build(up, z, stats, dst)
+        return
     if dt == F32 and K.fused_stats_ok(src.h, src.w, ch):
         K.conv_fprop(src, wp, ch, 1, 1, 0, z, in_stats=stats)
         K.instance_norm_apply(z, dst, off, stats)
@@ -199,8 +204,11 @@ def _g_forward_pass(G, x, ws):
     for i in range(4):
         ch = P["u"][i].c
         conv(src, f"upsample{i+1}", ups[i], ch, 1, 1, P["u"][i])
-        K.upsample2x(P["u"][i], P["cat"][i], 0)
-        _gam_forward(G, f"ga{4-i}", gas[i], skips[i], ch, P["z"][i], P["cat"][i], ch, P["st"][i], ws)
+        if K.cat_build_ok():  # [bilinear x2 of u | IN(conv1x1(skip))] written as whole pixels by one kernel
+            _gam_forward(G, f"ga{4-i}", gas[i], skips[i], ch, P["z"][i], P["cat"][i], ch, P["st"][i], ws, up=P["u"][i])
+        else:
+            K.upsample2x(P["u"][i], P["cat"][i], 0)
+            _gam_forward(G, f"ga{4-i}", gas[i], skips[i], ch, P["z"][i], P["cat"][i], ch, P["st"][i], ws)
         K.halo_fill(P["cat"][i])
         if i == 3 and f16_premul:
             # y4.mul(x1), models.py:70, in dec4's epilogue; y4 itself (kept for backward) is its second output

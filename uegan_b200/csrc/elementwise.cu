@@ -318,6 +318,47 @@ __global__ void upsample2x_kernel(TGeom s, TGeom d, int dst_c_off, float sy, flo
   Vec<T>::store(static_cast<T*>(d.data) + toff(d, n, yo, xo, dst_c_off + c), o);
 }
 
+// ------------------------------------------------------------------------------------------
+// Decoder concat in ONE pass: cat[.., 0:C) = bilinear x2 (align_corners) of u, cat[.., C:2C) = InstanceNorm(z) from the
+// finalised (mean, rstd) pairs (models.py:55-67: torch.cat([upsample(y), GAM(skip)], 1)).  Written as whole pixels: the
+// two separate passes each wrote HALF of every 128-byte line of cat and ran at 1.8 - 2.7 TB/s (r3h).
+// grid = (x-chunks of an output row, output rows, images); a thread owns one 16-byte vector of the 2C-channel pixel.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void cat_build_kernel(TGeom u, TGeom z, TGeom d, const float* __restrict__ mr, float sy, float sx, int cv_log2) {
+  constexpr int VN = Vec<T>::N;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int xo = t >> cv_log2;
+  if (xo >= d.w) return;
+  const int c = (t & ((1 << cv_log2) - 1)) * VN;  // channel of cat
+  const int yo = blockIdx.y, n = blockIdx.z;
+  float o[VN];
+  if (c < u.c) {
+    const float fy = sy * yo, fx = sx * xo;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < u.h - 1 ? 1 : 0), x1 = x0 + (x0 < u.w - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0;
+    const T* base = static_cast<const T*>(u.data);
+    float a[VN], b[VN], e[VN], f[VN];
+    Vec<T>::load(base + toff(u, n, y0, x0, c), a);
+    Vec<T>::load(base + toff(u, n, y0, x1, c), b);
+    Vec<T>::load(base + toff(u, n, y1, x0, c), e);
+    Vec<T>::load(base + toff(u, n, y1, x1, c), f);
+    const float rs = tscale(d) * tinv(u);
+#pragma unroll
+    for (int k = 0; k < VN; ++k)
+      o[k] = ((1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * e[k] + lx * f[k])) * rs;
+  } else {
+    const int cz = c - u.c;
+    Vec<T>::load(static_cast<const T*>(z.data) + toff(z, n, yo, xo, cz), o);
+    const float* m = mr + ((long long)n * z.c + cz) * 2;
+    const float so = tscale(d);
+#pragma unroll
+    for (int k = 0; k < VN; ++k) o[k] = (o[k] - m[2 * k]) * (m[2 * k + 1] * so);
+  }
+  Vec<T>::store(static_cast<T*>(d.data) + toff(d, n, yo, xo, c), o);
+}
+
 template <typename T>
 __global__ void maxpool2x2_kernel(TGeom s, TGeom d, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -508,6 +549,31 @@ int uegan_upsample2x(const uegan_tensor* src, const uegan_tensor* dst, int32_t d
     upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(s, d, dst_c_off, sy, sx, lg);
   else
     upsample2x_kernel<__half><<<grid, 256, 0, st>>>(s, d, dst_c_off, sy, sx, lg);
+  UEGAN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uegan_cat_build(const uegan_tensor* u, const uegan_tensor* z, const float* mean_rstd, const uegan_tensor* dst,
+                    void* stream) {
+  UEGAN_CHECK(u && z && dst && mean_rstd, "cat_build: null pointer");
+  if (check_vec(*u, "cat_build u") || check_vec(*z, "cat_build z") || check_vec(*dst, "cat_build dst")) return -1;
+  UEGAN_CHECK(u->dtype == dst->dtype && z->dtype == dst->dtype && u->n == dst->n && z->n == dst->n && dst->h == 2 * u->h &&
+                  dst->w == 2 * u->w && z->h == dst->h && z->w == dst->w && u->c == z->c && dst->c == 2 * u->c,
+              "cat_build: u (n,h/2,w/2,C), z (n,h,w,C) and dst (n,h,w,2C) expected");
+  const TGeom gu = geom(*u), gz = geom(*z), gd = geom(*dst);
+  const float sy = gd.h > 1 ? (float)(gu.h - 1) / (float)(gd.h - 1) : 0.f;
+  const float sx = gd.w > 1 ? (float)(gu.w - 1) / (float)(gd.w - 1) : 0.f;
+  const int vn = 16 / dtype_size(dst->dtype);
+  const int cv = gd.c / vn;
+  int lg = 0;
+  while ((1 << lg) < cv) ++lg;
+  UEGAN_CHECK((1 << lg) == cv && gu.c % vn == 0, "cat_build: channels / vector width must be a power of two (got %d)", cv);
+  UEGAN_CHECK(gd.h <= 65535 && gd.n <= 65535, "cat_build: tensor too large for the launch grid");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid(nblocks((long long)gd.w * cv, 256), (unsigned)gd.h, (unsigned)gd.n);
+  if (dst->dtype == UEGAN_F32) cat_build_kernel<float><<<grid, 256, 0, st>>>(gu, gz, gd, mean_rstd, sy, sx, lg);
+  else if (dst->dtype == UEGAN_BF16) cat_build_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(gu, gz, gd, mean_rstd, sy, sx, lg);
+  else cat_build_kernel<__half><<<grid, 256, 0, st>>>(gu, gz, gd, mean_rstd, sy, sx, lg);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -329,6 +329,22 @@ def upsample2x(src: NHWC, dst: NHWC, dst_c_off: int = 0):
     _count(1, "upsample2x", src)
 
 
+def cat_build(u: NHWC, z: NHWC, stats_ws: torch.Tensor, dst: NHWC, eps: float = 1e-5) -> int:
+    """dst = [bilinear x2 of u | InstanceNorm(z)] in one pass over whole pixels; statistics of z are computed here.
+    Returns the device address of z's (mean, rstd) pairs inside stats_ws (kept for the backward pass)."""
+    mr = instance_norm_stats(z, stats_ws, eps=eps)
+    L.check(L.load().uegan_cat_build(u.ref(), z.ref(), mr, dst.ref(), _stream()), "cat_build")
+    _count(1, "cat_build", dst)
+    return mr
+
+
+def cat_build_ok() -> bool:
+    """Opt-in (UEGAN_CAT_BUILD=1): measured r3p the one-pass concat is SLOWER than the two half-line passes (inference 6031 ->
+    5522 img/s, training 40.6 -> 41.3 ms): its warps diverge between the 4-load bilinear half and the 1-load normalise half."""
+    import os
+    return os.environ.get("UEGAN_CAT_BUILD") == "1"
+
+
 def maxpool2x2(src: NHWC, dst: NHWC):
     L.check(L.load().uegan_maxpool2x2(src.ref(), dst.ref(), _stream()), "maxpool2x2")
     _count(1, "maxpool2x2", src)

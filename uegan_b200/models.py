@@ -295,14 +295,19 @@ class Generator(nn.Module, _ScaledNet):
         conv(P["x3"], "enc4", self.enc4, 8 * d, 3, 2, P["x4"], act); K.halo_fill(P["x4"])
         conv(P["x4"], "enc5", self.enc5, 16 * d, 3, 2, P["x5"], act)
 
-        def gam(name, ga, src, ch, z, dst, off):
+        def gam(name, ga, src, ch, z, dst, off, up=None):
             # GAM(x) == IN(conv1x1(x, fuse.weight[:, :C])): the attention branch and fuse bias are constant per
             # (n, c) and cancel in the InstanceNorm that follows (models.py:230-237; SURVEY.md 8a rewrite 1).
+            # up: the low-resolution tensor whose bilinear x2 is the other half of dst: one kernel then writes whole pixels
             fuse = ga.fuse[0]
             dt = self._dtype
             ws_ = self._wscale(name, fuse)
             wp = self._wcache.get((name, dt), fuse.weight,
                                   lambda out=None: K.packed_weight(fuse.weight, src.c, dt, 0, ch, out=out, w_scale=ws_))
+            if up is not None:
+                K.conv_fprop(src, wp, ch, 1, 1, 0, z, w_scale=ws_)
+                K.cat_build(up, z, P["stats"], dst)
+                return
             if dt == L.F32 and K.fused_stats_ok(src.h, src.w, ch):  # statistics ride in the conv epilogue
                 K.conv_fprop(src, wp, ch, 1, 1, 0, z, in_stats=P["stats"])
                 K.instance_norm_apply(z, dst, off, P["stats"])
@@ -319,8 +324,11 @@ class Generator(nn.Module, _ScaledNet):
             # conv1x1 then bilinear x2 == bilinear x2 then conv1x1 (both linear, lerp weights sum to 1): run the
             # 1x1 at low resolution (models.py:23-26; SURVEY.md 8a rewrite 2)
             conv(P[src], un, up[1], ch, 1, 1, P[u])
-            K.upsample2x(P[u], P[cat], 0)
-            gam(gn, ga, P[skip], ch, P[z], P[cat], ch)
+            if K.cat_build_ok():
+                gam(gn, ga, P[skip], ch, P[z], P[cat], ch, up=P[u])
+            else:
+                K.upsample2x(P[u], P[cat], 0)
+                gam(gn, ga, P[skip], ch, P[z], P[cat], ch)
             K.halo_fill(P[cat])
             last = dn == "dec4"
             conv(P[cat], dn, dec, ch, 3, 1, P[y], act, 0, P["x1"] if last else None)  # dec4 fuses y4.mul(x1)
