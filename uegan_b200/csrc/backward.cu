@@ -121,7 +121,7 @@ __global__ void grad_combine_kernel(CombineArgs q, int cv_log2) {
     }
     if (q.has_dst2) {
       float t[VN], o2[VN];
-      const float f2 = tscale(q.dst2) * tinv(q.mul2) / so;  // the sum is in dst's scale: powers of two, exact
+      const float f2 = tscale(q.dst2) * tinv(q.mul2) * pow2_rcp(so);  // the sum is in dst's scale: powers of two, exact
       Vec<T>::load(static_cast<const T*>(q.mul2.data) + toff(q.mul2, n, y, x, q.mul2_c_off + c), t);
 #pragma unroll
       for (int k = 0; k < VN; ++k) o2[k] = v[k] * (t[k] * f2);

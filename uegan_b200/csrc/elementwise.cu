@@ -91,10 +91,18 @@ static TGeom geom(const uegan_tensor& t) {
 }
 // the tensor's scale / its reciprocal (powers of two: exact)
 __device__ __forceinline__ float tscale(const TGeom& g) { return g.scale ? __ldg(g.scale) : 1.f; }
-__device__ __forceinline__ float tinv(const TGeom& g) { return g.scale ? 1.f / __ldg(g.scale) : 1.f; }
+// (the scale is a power of two by contract, include/uegan_sm100.h: its reciprocal is an exponent flip -- one integer
+// subtraction instead of MUFU.RCP + the IEEE fix-up sequence that every THREAD of the elementwise kernels executed for up to
+// five tensors: ~50 of grad_combine's ~200 instructions per 16-byte vector, r3r)
+__device__ __forceinline__ float pow2_rcp(float s) { return __int_as_float(0x7F000000 - __float_as_int(s)); }
+__device__ __forceinline__ float tinv(const TGeom& g) { return g.scale ? pow2_rcp(__ldg(g.scale)) : 1.f; }
 // element offset of (n, y, x, c) with y, x in interior coordinates (may be negative into the halo)
+// (row index in 32 bits -- n * hp + y never leaves them --, one widening multiply for the pixel index, one 64 x 32 multiply
+// for the element offset: the all-64-bit form cost ~15 instructions per operand of every elementwise thread)
 __device__ __forceinline__ long long toff(const TGeom& g, int n, int y, int x, int c) {
-  return (((long long)n * g.hp + (y + g.halo)) * g.wp + (x + g.halo)) * g.c + c;
+  const int row = n * (int)g.hp + y + g.halo;
+  const long long pix = (long long)row * (int)g.wp + (x + g.halo);
+  return pix * g.c + c;
 }
 
 // ------------------------------------------------------------------------------------------
