@@ -291,6 +291,33 @@ def test_in_mse_bwd_direct(K):
         assert float(pv[:, -1].abs().max()) == 0.0 and float(pv[:, :, -1].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 12, 20), (1, 128, 9, 7)])
+def test_cat_build(K, shape):
+    """uegan_cat_build (one-pass decoder concat, opt-in) == uegan_upsample2x into the first half + uegan_instance_norm into
+    the second half, bit for bit, and both == torch's bilinear x2 (align_corners) / instance_norm."""
+    from uegan_b200 import _lib as L
+    n, c, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(5 + c)
+    u = torch.randn(n, c, h, w, device="cuda", generator=g).half().float()
+    z = (torch.randn(n, c, 2 * h, 2 * w, device="cuda", generator=g) * 3 + 1).half().float()
+    su, sz, sd = (torch.tensor([v], device="cuda") for v in (2.0, 0.5, 4.0))
+    tu = K.NHWC(n, h, w, c, 0, L.F16, "cuda", zero=True, scale=su)
+    tu.padded_view()[...] = (u * 2.0).permute(0, 2, 3, 1).half()
+    tz = K.NHWC(n, 2 * h, 2 * w, c, 0, L.F16, "cuda", zero=True, scale=sz)
+    tz.padded_view()[...] = (z * 0.5).permute(0, 2, 3, 1).half()
+    a = K.NHWC(n, 2 * h, 2 * w, 2 * c, 1, L.F16, "cuda", zero=True, scale=sd)
+    b = K.NHWC(n, 2 * h, 2 * w, 2 * c, 1, L.F16, "cuda", zero=True, scale=sd)
+    st = torch.empty(3 * n * c, dtype=torch.float64, device="cuda")
+    K.cat_build(tu, tz, st, a)
+    K.upsample2x(tu, b, 0)
+    K.instance_norm(tz, b, c, st)
+    assert K.device_error() == 0
+    assert torch.equal(a.padded_view(), b.padded_view())
+    ref = torch.cat([F.interpolate(u.double(), scale_factor=2, mode="bilinear", align_corners=True),
+                     F.instance_norm(z.double(), eps=1e-5)], 1)
+    assert relerr(a.interior_nchw(), ref) < 2e-3
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 12, 20), (1, 128, 33, 17), (2, 512, 4, 4)])
 def test_in_mse_joint(K, shape):
     """The joint tap pass (five raw moments per (n, c) in one read of x and y) == torch's

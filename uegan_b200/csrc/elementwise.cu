@@ -348,27 +348,32 @@ __global__ void cat_build_kernel(TGeom u, TGeom z, TGeom d, const float* __restr
   const int yo = blockIdx.y, n = blockIdx.z;
   float o[VN];
   if (c < u.c) {
+    // (the arithmetic of upsample2x_kernel, operation for operation: the two paths agree bit for bit)
     const float fy = sy * yo, fx = sx * xo;
     const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < u.h - 1 ? 1 : 0), x1 = x0 + (x0 < u.w - 1 ? 1 : 0);
     const float ly = fy - y0, lx = fx - x0;
-    const T* base = static_cast<const T*>(u.data);
+    const T* p00 = static_cast<const T*>(u.data) + toff(u, n, y0, x0, c);
+    const long long dx = x0 < u.w - 1 ? u.c : 0, dy = y0 < u.h - 1 ? u.wp * u.c : 0;
     float a[VN], b[VN], e[VN], f[VN];
-    Vec<T>::load(base + toff(u, n, y0, x0, c), a);
-    Vec<T>::load(base + toff(u, n, y0, x1, c), b);
-    Vec<T>::load(base + toff(u, n, y1, x0, c), e);
-    Vec<T>::load(base + toff(u, n, y1, x1, c), f);
+    Vec<T>::load(p00, a);
+    Vec<T>::load(p00 + dx, b);
+    Vec<T>::load(p00 + dy, e);
+    Vec<T>::load(p00 + dy + dx, f);
     const float rs = tscale(d) * tinv(u);
+    const float w00 = (1.f - ly) * (1.f - lx) * rs, w01 = (1.f - ly) * lx * rs, w10 = ly * (1.f - lx) * rs, w11 = ly * lx * rs;
 #pragma unroll
-    for (int k = 0; k < VN; ++k)
-      o[k] = ((1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * e[k] + lx * f[k])) * rs;
+    for (int k = 0; k < VN; ++k) o[k] = fmaf(w11, f[k], fmaf(w10, e[k], fmaf(w01, b[k], w00 * a[k])));
   } else {
     const int cz = c - u.c;
     Vec<T>::load(static_cast<const T*>(z.data) + toff(z, n, yo, xo, cz), o);
-    const float* m = mr + ((long long)n * z.c + cz) * 2;
+    const float4* m4 = reinterpret_cast<const float4*>(mr + ((long long)n * z.c + cz) * 2);
     const float so = tscale(d);
 #pragma unroll
-    for (int k = 0; k < VN; ++k) o[k] = (o[k] - m[2 * k]) * (m[2 * k + 1] * so);
+    for (int k = 0; k < VN; k += 2) {
+      const float4 q = __ldg(m4 + (k >> 1));
+      o[k] = (o[k] - q.x) * (q.y * so);
+      o[k + 1] = (o[k + 1] - q.z) * (q.w * so);
+    }
   }
   Vec<T>::store(static_cast<T*>(d.data) + toff(d, n, yo, xo, c), o);
 }
