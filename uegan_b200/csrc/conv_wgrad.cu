@@ -481,6 +481,10 @@ struct WgradPatchParams {
   int n_cols, col_c, col_rev;
   int two_issuers;  // warps 1 and 3 both issue MMAs (alternate accumulators)
   int tmem_cols;    // TMEM columns the CTA allocates: 512, or 256 when its accumulators fit (two CTAs per SM then)
+  // M-side operand rows: 128 bytes (cbm = CB channels, tpg = 128 / CB taps per M group), or -- 32-channel fp16 tensors,
+  // vertical mode -- 64 bytes = one pixel (SWIZZLE_64B atoms of 32 channels: cbm = 32, tpg = 4 filter rows per M group:
+  // no half-empty rows, half the MMAs)
+  int cbm, tpg, a_row_bytes;
   float* dw;
   float* partial;
   long long dw_numel;
@@ -537,7 +541,7 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       if (elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t tx = nch * p.ph * p.pw * 128 + p.n_boxes * 64 * 128;
+        const uint32_t tx = nch * p.ph * p.pw * p.a_row_bytes + p.n_boxes * 64 * 128;
         int tw_i = kt0 % p.tiles_w, th_i = (kt0 / p.tiles_w) % p.tiles_h, n_i = kt0 / (p.tiles_w * p.tiles_h);
         for (int kt = kt0; kt < kt1; ++kt) {
           const int wo0 = tw_i * 8, ho0 = th_i * 8, n = n_i;
@@ -550,7 +554,7 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           uint8_t* sz = sp + nch * p.patch_bytes;
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           for (int c = 0; c < nch; ++c)
-            tma_load_4d(&tmX, &full_bar[stage], sp + c * p.patch_bytes, (ch_lo + c) * CB, wo0 + p.off, ho0 + p.off, n);
+            tma_load_4d(&tmX, &full_bar[stage], sp + c * p.patch_bytes, (ch_lo + c) * p.cbm, wo0 + p.off, ho0 + p.off, n);
           for (int g = 0; g < p.n_boxes; ++g)
             tma_load_4d(&tmZ, &full_bar[stage], sz + g * 64 * 128, g * CB, wo0, ho0, n);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
@@ -575,17 +579,18 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           // A: M-group stride (LBO) = one pixel row: the taps of a group are the same rows shifted by 0, 1, .. pixels.
           // tf32: 4-row K atoms inside one tile row (SBO 512); fp16: 8-row K atoms, the second one is the NEXT tile row
           // of the patch (SBO = patch row pitch; tcgen05 swizzles on absolute address bits, so any 128-byte multiple works)
-          const uint64_t da0 = kF16 ? make_smem_desc(sp, (uint32_t)p.lbo_bytes, (uint32_t)p.pw * 128, UMMA_LAYOUT_SW128)
+          const uint64_t da0 = kF16 ? make_smem_desc(sp, (uint32_t)p.lbo_bytes, (uint32_t)(p.pw * p.a_row_bytes),
+                                                     p.a_row_bytes == 64 ? UMMA_LAYOUT_SW64 : UMMA_LAYOUT_SW128)
                                     : make_smem_desc(sp, (uint32_t)p.lbo_bytes, 512, UMMA_LAYOUT_SW128_B32);
           const uint64_t db0 = kF16 ? make_smem_desc(sz, 64 * 128, 1024, UMMA_LAYOUT_SW128)
                                     : make_smem_desc(sz, 64 * 128, 512, UMMA_LAYOUT_SW128_B32);
-          const uint32_t row_step = p.pw * 8;  // one patch row, in descriptor units of 16 bytes
+          const uint32_t row_step = (uint32_t)(p.pw * p.a_row_bytes) >> 4;  // one patch row, in descriptor units of 16 bytes
           int g = acc0 % p.kgroups, r = (acc0 / p.kgroups) % p.rk, c = acc0 / (p.kgroups * p.rk) - ch_lo;
           uint32_t d_tmem = tmem_base;
           for (int a = acc0; a < acc1; ++a) {
             // first tap of the group: (row r, column TPG*g) of the patch, or (row TPG*g, column 0) in vertical mode
-            const uint32_t tap0 = p.vert ? (uint32_t)(TPG * g * p.pw) : (uint32_t)(r * p.pw + TPG * g);
-            uint64_t da = da0 + (uint32_t)(c * (p.patch_bytes >> 4)) + tap0 * 8;
+            const uint32_t tap0 = p.vert ? (uint32_t)(p.tpg * g * p.pw) : (uint32_t)(r * p.pw + p.tpg * g);
+            uint64_t da = da0 + (uint32_t)(c * (p.patch_bytes >> 4)) + tap0 * (uint32_t)(p.a_row_bytes >> 4);
             constexpr int KSTEPS = kF16 ? 4 : 8;  // MMAs per 8x8 pixel tile: K = 8 (one tile row) or 16 (two tile rows)
             if (((a - acc0) & (n_iss - 1)) == iss) {
 #pragma unroll
@@ -613,7 +618,7 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       const int kk = p.k * p.k;
       for (int a = acc0; a < acc1; ++a) {
         const int g = a % p.kgroups, r = (a / p.kgroups) % p.rk, chunk = a / (p.kgroups * p.rk);
-        const int s_ = TPG * g + m / CB, c = chunk * CB + (m % CB);  // vertical mode: s_ is the filter ROW
+        const int s_ = p.tpg * g + m / p.cbm, c = chunk * p.cbm + (m % p.cbm);  // vertical mode: s_ is the filter ROW
         for (int c0 = 0; c0 < N; c0 += 16) {
           uint32_t rr[16];
           tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (a - acc0) * N + c0, rr);
@@ -713,6 +718,7 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
   p.err_sink = error_sink_device();
   { const char* e2 = getenv("UEGAN_WGRAD_ISSUERS"); p.two_issuers = !(e2 && e2[0] == '1'); }
   if (p.tmem_cols == 0) p.tmem_cols = 512;
+  if (p.cbm == 0) { p.cbm = CB; p.tpg = TPG; p.a_row_bytes = 128; }
   const CUtensorMapDataType tdt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapSwizzle tsw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX, tmZ;
@@ -806,6 +812,7 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
   p.err_sink = error_sink_device();
   { const char* e2 = getenv("UEGAN_WGRAD_ISSUERS"); p.two_issuers = !(e2 && e2[0] == '1'); }
   if (p.tmem_cols == 0) p.tmem_cols = 512;
+  if (p.cbm == 0) { p.cbm = CB; p.tpg = TPG; p.a_row_bytes = 128; }
   const CUtensorMapDataType tdt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapSwizzle tsw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX, tmZ;
@@ -862,20 +869,25 @@ extern "C" int uegan_conv2d_wgrad_zwin(const uegan_tensor* x, const uegan_tensor
   UEGAN_CHECK(dz->n == x->n && dz->h == x->h && dz->w == x->w, "conv2d_wgrad_zwin: dz is %dx%dx%d, expected %dx%dx%d", dz->n,
               dz->h, dz->w, x->n, x->h, x->w);
   UEGAN_CHECK(cin <= x->c && cin_first + cin <= cin_total, "conv2d_wgrad_zwin: channel mismatch");
-  constexpr int es = 2, CB = 64, TPG = 2;
+  constexpr int es = 2, CB = 64;
   WgradPatchParams p;
   memset(&p, 0, sizeof(p));
+  // 32-channel x: a pixel is 64 bytes -- SWIZZLE_64B rows, four filter rows per M = 128 group instead of two half-empty ones
+  const char* e64 = getenv("UEGAN_NO_ZWIN64");
+  const bool row64 = x->c == 32 && !(e64 && e64[0] == '1');
+  const int CBM = row64 ? 32 : 64, TPG = 128 / CBM, arow = row64 ? 64 : 128;
+  p.cbm = CBM; p.tpg = TPG; p.a_row_bytes = arow;
   p.n_cols = (k * dz->c + 15) / 16 * 16;
   p.n_boxes = (p.n_cols + CB - 1) / CB;
   p.col_c = dz->c; p.col_rev = 1;
   p.k = k;
   p.kgroups = (k + TPG - 1) / TPG;
-  p.chunks = (cin + CB - 1) / CB;
+  p.chunks = (cin + CBM - 1) / CBM;
   p.vert = 1; p.rk = 1;
   p.pw = 8;
   p.ph = 8 + TPG * p.kgroups - 1;
-  p.lbo_bytes = p.pw * 128;
-  p.patch_bytes = p.ph * p.pw * 128;
+  p.lbo_bytes = p.pw * arow;
+  p.patch_bytes = (p.ph * p.pw * arow + 1023) / 1024 * 1024;
   p.dz_bytes = p.n_boxes * 64 * 128;
   p.acc_total = p.chunks * p.kgroups;
   const int N = p.n_cols;
@@ -914,13 +926,16 @@ extern "C" int uegan_conv2d_wgrad_zwin(const uegan_tensor* x, const uegan_tensor
   p.err_sink = error_sink_device();
   { const char* e2 = getenv("UEGAN_WGRAD_ISSUERS"); p.two_issuers = !(e2 && e2[0] == '1'); }
   if (p.tmem_cols == 0) p.tmem_cols = 512;
+  if (p.cbm == 0) { p.cbm = CB; p.tpg = TPG; p.a_row_bytes = 128; }
   CUtensorMap tmX, tmZ;
   {  // x, padded extent: {c, w, h, n}
     const uint64_t pix = (uint64_t)x->c * es, row = (uint64_t)t_wp(*x) * pix, img = (uint64_t)t_hp(*x) * row;
     uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)t_wp(*x), (uint64_t)t_hp(*x), (uint64_t)x->n};
     uint64_t strides[3] = {pix, row, img};
-    uint32_t box[4] = {(uint32_t)CB, (uint32_t)p.pw, (uint32_t)p.ph, 1u};
-    if (encode_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x->data, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    uint32_t box[4] = {(uint32_t)CBM, (uint32_t)p.pw, (uint32_t)p.ph, 1u};
+    if (encode_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x->data, dims, strides, box,
+                     row64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B))
+      return -1;
   }
   {  // the window map over dz: {window element, q, y, n}, q = 0 is the window that starts k - 1 pixels left of the interior
     const uint64_t pix = (uint64_t)dz->c * es, row = (uint64_t)t_wp(*dz) * pix, img = (uint64_t)t_hp(*dz) * row;
