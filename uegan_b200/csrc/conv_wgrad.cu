@@ -39,6 +39,9 @@ struct WgradParams {
   int cout, cin, cin_total, cin_first, x_c;
   int m_tiles, n_chunks;
   int a_bytes;                     // bytes of the M operand per stage (WgT::ABYTES)
+  // N-operand boxes: 64 pixels x 128 B (b_cb = CB channels), or -- 32-channel fp16 x -- 64 pixels x 64 B (SWIZZLE_64B,
+  // b_cb = 32): eight taps side by side fill N = 256 with real channels instead of four half-empty 64-channel boxes
+  int b_cb, b_box_bytes;
   float* dw;                       // OIHW fp32
   float* partial;                  // deterministic mode: [k-split slice][dw_numel] partial sums, reduced in slice order
   long long dw_numel;
@@ -117,7 +120,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int r = tap;  // swap mode only
   const int t_first = tap * p.tap_group;
   const int t_count = p.swap_mode ? 1 : min(p.tap_group, p.taps_total - t_first);
-  const int N = p.n_boxes * CB;
+  const int N = p.n_boxes * p.b_cb;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -144,18 +147,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // tap / channel group) is computed before the loop, and the tile counters advance by increments -- measured
         // r2j (ncu source page): with the coordinate arithmetic (divisions per box) inside the loop the MMA warp sat in
         // its full_bar wait for 80 % of its samples while this thread issued ~600 instructions per stage.
-        constexpr int MAXB = 256 / CB;  // N-operand boxes per stage
+        constexpr int MAXB = 8;  // N-operand boxes per stage (256 columns of 32-channel boxes)
         int stage = 0;
         uint32_t phase = 0;
         const int nB = p.swap_mode ? 1 : t_count * p.tap_boxes;
-        const uint32_t tx = kWgABytes + nB * kWgBoxBytes;
+        const uint32_t tx = kWgABytes + nB * p.b_box_bytes;
         int bc[MAXB], br[MAXB];
 #pragma unroll
         for (int j = 0; j < MAXB; ++j) {
           const int t = j / p.tap_boxes, g = j - t * p.tap_boxes;
           const int tp = t_first + t;
           const int tr = p.window_mode ? tp : tp / p.k, ts = p.window_mode ? 0 : tp - (tp / p.k) * p.k;
-          bc[j] = ts * p.x_c + nc * p.tap_boxes * CB + g * CB;
+          bc[j] = ts * p.x_c + nc * p.tap_boxes * p.b_cb + g * p.b_cb;
           br[j] = tr;
         }
         int tw_i = kt0 % p.tiles_w, th_i = (kt0 / p.tiles_w) % p.tiles_h, n = kt0 / (p.tiles_w * p.tiles_h);
@@ -180,7 +183,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // positions inside the window of k*C contiguous (s, c) values that starts at the pixel
 #pragma unroll
             for (int j = 0; j < MAXB; ++j)
-              if (j < nB) tma_load_5d(&tmB, &full_bar[stage], sb + j * kWgBoxBytes, bc[j], wo0, br[j], ho0, n);
+              if (j < nB) tma_load_5d(&tmB, &full_bar[stage], sb + j * p.b_box_bytes, bc[j], wo0, br[j], ho0, n);
           }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
           if (++tw_i == p.tiles_w) {
@@ -205,11 +208,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // 8-row atoms of 128-byte rows, SBO = 1024 bytes between them, LBO = one box between 64-channel groups.
           const uint64_t da0 = kF16 ? make_smem_desc(smem_u32(smem + stage * p.stage_bytes), kWgBoxBytes, 1024, UMMA_LAYOUT_SW128)
                                     : make_smem_desc(smem_u32(smem + stage * p.stage_bytes), kWgBoxBytes, 512, UMMA_LAYOUT_SW128_B32);
-          const uint64_t db0 = da0 + (kWgABytes >> 4);
+          const bool b64 = kF16 && p.b_box_bytes == kWgStageRows * 64;
+          const uint64_t db0 = b64 ? make_smem_desc(smem_u32(smem + stage * p.stage_bytes) + kWgABytes, (uint32_t)p.b_box_bytes, 512,
+                                                    UMMA_LAYOUT_SW64)
+                                   : da0 + (kWgABytes >> 4);
+          const uint32_t bstep = b64 ? KROWS * 4 : KROWS * 8;  // KROWS rows of 64 / 128 bytes, in 16-byte units
 #pragma unroll
           for (int ks = 0; ks < kWgStageRows / KROWS; ++ks) {  // KROWS pixels (KROWS x 128 bytes of rows) per MMA
-            umma_ss<kF16 ? 0 : 1>(tmem_base, da0 + ks * (KROWS * 8), db0 + ks * (KROWS * 8), idesc,
-                                  (first | ks) != 0 ? 1u : 0u);
+            umma_ss<kF16 ? 0 : 1>(tmem_base, da0 + ks * (KROWS * 8), db0 + ks * bstep, idesc, (first | ks) != 0 ? 1u : 0u);
           }
           first = 1;
           umma_commit(&empty_bar[stage]);
@@ -245,7 +251,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           continue;
         }
         if (o >= p.cout) continue;
-        const int ncol = p.tap_boxes * CB;  // columns per tap
+        const int ncol = p.tap_boxes * p.b_cb;  // columns per tap
         const int tl = c0 / ncol;           // a 16-column chunk never straddles taps (ncol is a multiple of 32)
         if (tl >= t_count) continue;
         const int tp = t_first + tl;
@@ -356,6 +362,10 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   // role swap pays whenever the output-channel side would leave MMA rows empty (Cout <= 32 of M = 128)
   const bool swap = !window && cout <= 32 && dz->c == 32;
   p.swap_mode = swap;
+  // 32-channel fp16 x (64-byte pixels): SWIZZLE_64B N-operand boxes
+  const char* e64 = getenv("UEGAN_NO_WGRAD64");
+  const bool b64 = f16 && !window && !swap && x->c == 32 && cin <= 32 && !(e64 && e64[0] == '1');
+  int CBN = CB;  // channels per N-operand box
   int N;
   if (swap) {
     N = CB; p.n_chunks = 1;  // the (<= 32) dz channels: one box, zero-filled beyond the tensor
@@ -371,6 +381,8 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
     N = CB * p.tap_group; p.n_chunks = 1;
   } else {
     // several taps per MMA while the per-tap width leaves room in N <= 256 (A = dz is then read once per GROUP)
+    if (b64) CBN = 32;
+    const int CB = CBN;  // (shadows the 128-byte box width for this branch)
     const int cpad = (cin + CB - 1) / CB * CB;
     const int ncol = cpad < 256 ? cpad : 256;
     p.n_chunks = (cpad + ncol - 1) / ncol;
@@ -380,10 +392,12 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
     if (p.tap_group > p.taps_total) p.tap_group = p.taps_total;
     N = p.tap_group * ncol;
   }
-  p.n_boxes = N / CB;
+  p.b_cb = CBN;
+  p.b_box_bytes = kWgStageRows * CBN * es;
+  p.n_boxes = N / CBN;
   if (!swap) p.taps = (p.taps_total + p.tap_group - 1) / p.tap_group;
   p.a_bytes = a_bytes;
-  p.stage_bytes = a_bytes + p.n_boxes * kWgBoxBytes;
+  p.stage_bytes = a_bytes + p.n_boxes * p.b_box_bytes;
   // Two CTAs per SM (each with half the smem ring and 256 of the 512 TMEM columns) when two stages still fit: the
   // launches are latency-bound (one TMA thread, one MMA thread, a short epilogue), and a second resident CTA overlaps them.
   const char* occ_env = getenv("UEGAN_WGRAD_OCC");
@@ -431,8 +445,8 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
     const uint64_t win = window ? (uint64_t)CB : (uint64_t)k * x->c;
     uint64_t dims[5] = {win, (uint64_t)Wo, (uint64_t)k, (uint64_t)Ho, (uint64_t)x->n};
     uint64_t strides[4] = {(uint64_t)stride * pix, row, (uint64_t)stride * row, img};
-    uint32_t box[5] = {(uint32_t)CB, 8u, 1u, 8u, 1u};
-    if (encode_tiled(&tmB, tdt, 5, base, dims, strides, box, tsw)) return -1;
+    uint32_t box[5] = {(uint32_t)CBN, 8u, 1u, 8u, 1u};
+    if (encode_tiled(&tmB, tdt, 5, base, dims, strides, box, b64 ? CU_TENSOR_MAP_SWIZZLE_64B : tsw)) return -1;
   }
   static bool attr_set = false;
   if (!attr_set) {
