@@ -913,12 +913,22 @@ extern "C" int uegan_conv2d_wgrad_zwin(const uegan_tensor* x, const uegan_tensor
   p.acc_per_cta = nch * p.kgroups;
   p.stage_bytes = nch * p.patch_bytes + p.dz_bytes;
   {
-    // two CTAs per SM when the accumulators fit half the TMEM and three stages fit half the shared memory
+    // several CTAs per SM (the launch is latency-bound: one TMA thread, one or two MMA threads, a short epilogue): the
+    // largest count whose accumulators share the 512 TMEM columns and whose rings (>= 3 stages for two CTAs, >= 2 beyond)
+    // share the shared memory
     const char* occ_env = getenv("UEGAN_WGRAD_OCC");
-    const int occ = occ_env ? atoi(occ_env) : 2;
-    const bool two = occ >= 2 && p.acc_per_cta * N <= 256 && 3 * p.stage_bytes <= 100 * 1024;
-    p.tmem_cols = two ? 256 : 512;
-    p.num_stages = (two ? 100 * 1024 : 200 * 1024) / p.stage_bytes;
+    const int occ_max = occ_env ? atoi(occ_env) : 2;
+    int cols = 32;
+    while (cols < p.acc_per_cta * N) cols <<= 1;
+    int occ = 1;
+    for (int o = occ_max < 4 ? occ_max : 4; o >= 2; --o) {
+      const int budget = (o == 2 ? 100 : (o == 3 ? 66 : 49)) * 1024;
+      if (cols * o <= 512 && (o == 2 ? 3 : 2) * p.stage_bytes <= budget) { occ = o; break; }
+    }
+    p.tmem_cols = occ == 1 ? 512 : cols < 512 / occ ? (occ == 3 ? 128 : 512 / occ) : 512 / occ;
+    if (occ == 3 && cols > 128) p.tmem_cols = cols;  // (three CTAs: 3 x cols <= 512 already checked)
+    const int budget = occ == 1 ? 200 * 1024 : (occ == 2 ? 100 : (occ == 3 ? 66 : 49)) * 1024;
+    p.num_stages = budget / p.stage_bytes;
   }
   if (p.num_stages > 6) p.num_stages = 6;
   UEGAN_CHECK(p.num_stages >= 2, "conv2d_wgrad_zwin: stage too large");
