@@ -150,7 +150,7 @@ __global__ void grad_combine_kernel(CombineArgs q, int cv_log2) {
 // ------------------------------------------------------------------------------------------
 // fold_inplace: t (halo = pad) holds the gradient w.r.t. the reflect-PADDED input of a conv (what a dgrad launch writes:
 // extent (h + 2 pad) x (w + 2 pad)).  Adjoint of nn.ReflectionPad2d in place: every interior pixel within `pad` of an
-// edge adds the halo pixels that were reflected copies of it; the halo is zeroed afterwards (uegan_halo_fill), so the
+// edge adds the halo pixels that were reflected copies of it and zeroes them (each has exactly one reader), so the
 // tensor is at once the folded gradient and a zero-haloed dgrad / wgrad operand.  Sources are halo pixels only, targets
 // interior pixels only: race-free.  Touches O(perimeter) data instead of a full read + write pass (grad_combine).
 // grid = (1, h, n); a row inside the top / bottom band processes every column, any other row only its 2*pad edge columns.
@@ -182,9 +182,13 @@ __global__ void fold_inplace_kernel(TGeom t, int cv_log2) {
       for (int ix = -1; ix < nx; ++ix) {
         if (iy < 0 && ix < 0) continue;
         float s[VN];
-        Vec<T>::load(base + toff(t, n, iy < 0 ? y : ys[iy], ix < 0 ? x : xs[ix], c), s);
+        T* src = base + toff(t, n, iy < 0 ? y : ys[iy], ix < 0 ? x : xs[ix], c);
+        Vec<T>::load(src, s);
 #pragma unroll
         for (int k = 0; k < VN; ++k) v[k] += s[k];
+        // every halo pixel is the reflected copy of exactly ONE interior pixel, so it is read by exactly one thread: that
+        // thread zeroes it (the tensor leaves as a zero-haloed operand without a separate halo pass)
+        *reinterpret_cast<uint4*>(src) = make_uint4(0u, 0u, 0u, 0u);
       }
     Vec<T>::store(dst, v);
   }
@@ -676,7 +680,7 @@ int uegan_fold_inplace(const uegan_tensor* t, void* stream) {
   const dim3 grid(1u, (unsigned)g.h, (unsigned)g.n);
   UEGAN_DISPATCH(t->dtype, fold_inplace_kernel, <<<grid, 256, 0, st>>>(g, lg));
   UEGAN_CUDA(cudaGetLastError());
-  return uegan_halo_fill(t, UEGAN_PAD_ZERO, stream);
+  return 0;
 }
 
 int uegan_dz_hstack(const uegan_tensor* dz, int32_t cout, int32_t k, const uegan_tensor* e, void* stream) {

@@ -657,7 +657,7 @@ def fold_inplace(dxp: NHWC, pad: int) -> NHWC:
     (interior h x w, ZERO halo p) that downstream wgrad / dgrad / elementwise kernels consume."""
     v = dxp.as_haloed(pad)
     L.check(L.load().uegan_fold_inplace(v.ref(), _stream()), "fold_inplace")
-    _count(2, "fold_inplace", v)
+    _count(1, "fold_inplace", v)
     return v
 
 
