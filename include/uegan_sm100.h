@@ -119,6 +119,12 @@ int uegan_pack_conv_weight_dgrad_scaled(const float* w_oihw, void* w_packed, int
                                         int32_t cin_first, int32_t cin, int32_t cout_stored, int32_t k_orig,
                                         int32_t stride, int32_t pi, int32_t pj, int32_t dtype, const float* w_scale_dev,
                                         void* stream);
+/* The four parity-class operands (pi, pj) = (0,0), (0,1), (1,0), (1,1) of a STRIDE-2 conv's data gradient, back to back
+ * (class stride = uegan_packed_weight_bytes(cin, cout_stored, ceil(k_orig / 2), dtype)), in one launch: the operand of a
+ * uegan_conv2d_fprop call with y_cls_c.  w_scale_dev may be NULL. */
+int uegan_pack_conv_weight_dgrad4(const float* w_oihw, void* w_packed, int32_t cout_orig, int32_t cin_total, int32_t cin_first,
+                                  int32_t cin, int32_t cout_stored, int32_t k_orig, int32_t dtype, const float* w_scale_dev,
+                                  void* stream);
 
 /* Per-tensor power-of-two scales (uegan_tensor.scale), maintained on the device so that CUDA-graph replays need no host
  * work.  One entry per tensor: the kernel samples up to `max_samples` stored values evenly across the buffer, takes

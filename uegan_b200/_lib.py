@@ -49,6 +49,7 @@ SYMBOLS = {
                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "uegan_pack_conv_weight_scaled": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p, C.c_void_p]),
     "uegan_pack_conv_weight_dgrad_scaled": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 10 + [C.c_void_p, C.c_void_p]),
+    "uegan_pack_conv_weight_dgrad4": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p, C.c_void_p]),
     "uegan_scale_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "uegan_conv2d_fprop": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "uegan_conv2d_rowsum_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

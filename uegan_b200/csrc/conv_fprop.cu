@@ -1052,6 +1052,11 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
                                    const float* __restrict__ wscale) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
+  if (gridDim.y > 1) {  // all four parity classes of a stride-2 data-gradient operand in one launch: class = blockIdx.y
+    pi = blockIdx.y >> 1;
+    pj = blockIdx.y & 1;
+    out += (long long)blockIdx.y * total;
+  }
   const int x = (int)(i % row_pad);
   const int r = (int)((i / row_pad) % k);
   const int o = (int)(i / ((long long)row_pad * k));
@@ -1089,14 +1094,14 @@ size_t uegan_packed_weight_bytes(int32_t cout, int32_t cin_stored, int32_t k, in
 
 static int pack_impl(const float* w_oihw, void* w_packed, int cout, int cin_total, int cin_first, int cin,
                      int cin_stored, int k, int dtype, int mode, int k_orig, int q, int pi, int pj, void* stream,
-                     const float* wscale = nullptr) {
+                     const float* wscale = nullptr, int classes = 1) {
   UEGAN_CHECK(w_oihw && w_packed, "pack_conv_weight: null pointer");
   UEGAN_CHECK(cin <= cin_stored, "pack_conv_weight: cin %d > stored %d", cin, cin_stored);
   UEGAN_CHECK(dtype_ok(dtype), "pack_conv_weight: bad dtype");
   const PackGeom g = pack_geom(cout, cin_stored, k, dtype);
   const long long total = (long long)g.cout_pad * k * g.row_pad;
   const int threads = 256;
-  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  const dim3 blocks((unsigned)((total + threads - 1) / threads), (unsigned)classes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == UEGAN_F32)
     pack_weight_kernel<float><<<blocks, threads, 0, st>>>(w_oihw, static_cast<float*>(w_packed), cout, cin_total,
@@ -1151,6 +1156,15 @@ int uegan_pack_conv_weight_dgrad_scaled(const float* w_oihw, void* w_packed, int
   const int k = (k_orig + stride - 1) / stride;
   return pack_impl(w_oihw, w_packed, cin, cin_total, cin_first, cout_orig, cout_stored, k, dtype, 1, k_orig, stride, pi,
                    pj, stream, w_scale_dev);
+}
+
+int uegan_pack_conv_weight_dgrad4(const float* w_oihw, void* w_packed, int32_t cout_orig, int32_t cin_total, int32_t cin_first,
+                                  int32_t cin, int32_t cout_stored, int32_t k_orig, int32_t dtype, const float* w_scale_dev,
+                                  void* stream) {
+  UEGAN_CHECK(cin_first + cin <= cin_total, "pack_conv_weight_dgrad4: channel range out of bounds");
+  const int k = (k_orig + 1) / 2;
+  return pack_impl(w_oihw, w_packed, cin, cin_total, cin_first, cout_orig, cout_stored, k, dtype, 1, k_orig, 2, 0, 0, stream,
+                   w_scale_dev, 4);
 }
 
 int uegan_conv2d_fprop(const uegan_conv_desc* desc, void* stream) {

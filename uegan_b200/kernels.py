@@ -552,9 +552,12 @@ def conv_dgrad(dz: NHWC, weight: torch.Tensor, k: int, stride: int, dxp: NHWC, c
             lib = L.load()
             cb = lib.uegan_packed_weight_bytes(cin_n, dz.c, kq, dz.dtype)
             buf = out if out is not None else torch.empty(4 * cb + 256, dtype=torch.uint8, device=weight.device)
-            for cls in range(4):
-                packed_weight_dgrad(weight, dz.c, dz.dtype, 2, cls >> 1, cls & 1, cin_first, cin,
-                                    out=buf[cls * cb:], w_scale=w_scale)
+            wd = weight.detach()
+            assert wd.is_cuda and wd.dtype == torch.float32 and wd.is_contiguous()
+            L.check(lib.uegan_pack_conv_weight_dgrad4(wd.data_ptr(), buf.data_ptr(), wd.shape[0], wd.shape[1], cin_first, cin_n,
+                                                      dz.c, k, dz.dtype, w_scale.data_ptr() if w_scale is not None else None,
+                                                      _stream()), "pack_conv_weight_dgrad4")
+            _count(1, "pack_weight_dgrad4")
             return buf
         wp = cache.get((key, "dg4", dz.dtype, dz.c), weight, fn4) if cache is not None else fn4()
         conv_generic(dz, wp, 4 * cout_arg, kq, 1, kq - 1, dxp, 0, None, alpha, L.ACT_NONE, None, L.ACT_NONE, y_mul=2,
