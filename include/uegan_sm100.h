@@ -80,6 +80,9 @@ typedef struct uegan_conv_desc {
                                   Needs Ho*Wo >= 128 (tiles within one image). */
   const uegan_tensor* y_premul; /* optional, with `mul` (16-bit tensors): the output BEFORE the multiplication is stored here
                                   as well (own scale) -- training keeps y4 next to y4.mul(x1), models.py:70 */
+  int32_t y_reflect_halo;      /* != 0: the epilogue also writes y's halo as the reflection padding of its interior
+                                  (nn.ReflectionPad2d of the consumer, models.py:82,93,161,173): uegan_halo_fill(y, REFLECT)
+                                  without a separate pass.  16-bit dense outputs, y.h, y.w > 2 * y.halo + 1 */
   int32_t y_cls_c;             /* 0, or (with y_mul = 2, y_off = 0) ALL FOUR parity classes of a stride-2 data gradient in
                                   one launch: cout = 4 * y_cls_c output columns, column (pi*2 + pj) * y_cls_c + c is
                                   channel c of the output pixel (2a + pi, 2b + pj); w_packed = the four class operands

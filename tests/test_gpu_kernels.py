@@ -291,6 +291,34 @@ def test_in_mse_bwd_direct(K):
         assert float(pv[:, -1].abs().max()) == 0.0 and float(pv[:, :, -1].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("case", [(2, 32, 24, 40, 32, 3, 1, 3), (1, 8, 32, 48, 32, 7, 1, 1), (2, 32, 32, 32, 64, 3, 2, 1),
+                                  (1, 64, 16, 24, 32, 3, 1, 2), (1, 128, 40, 24, 256, 5, 2, 2)])
+def test_conv_epilogue_reflect_halo(K, case):
+    """uegan_conv_desc.y_reflect_halo: the conv epilogue writes the reflection-padding halo of its output == the same conv
+    followed by uegan_halo_fill(REFLECT), bit for bit over the whole padded tensor (every tile mode: RGB / 64-byte /
+    128-byte patch, plain stride 2, N tiles > 1)."""
+    from uegan_b200 import _lib as L
+    n, cin, h, w, cout, k, stride, yhalo = case
+    g = torch.Generator(device="cuda").manual_seed(17 + cin + cout)
+    pad = (k - 1) // 2
+    real_cin = 3 if cin == 8 else cin
+    x = torch.randn(n, real_cin, h, w, device="cuda", generator=g).half().float()
+    wgt = (torch.randn(cout, real_cin, k, k, device="cuda", generator=g) / math.sqrt(real_cin * k * k)).half().float()
+    bias = torch.randn(cout, device="cuda", generator=g)
+    xt = fill_nhwc(K, x, cin, pad, L.PAD_REFLECT, L.F16)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    wp = K.packed_weight(wgt, cin, L.F16)
+    ya = K.NHWC(n, ho, wo, cout, yhalo, L.F16, "cuda", zero=True)
+    yb = K.NHWC(n, ho, wo, cout, yhalo, L.F16, "cuda", zero=True)
+    K.conv_fprop(xt, wp, cout, k, stride, pad, ya, bias=bias, act=L.ACT_LRELU, reflect_halo=True)
+    K.conv_fprop(xt, wp, cout, k, stride, pad, yb, bias=bias, act=L.ACT_LRELU)
+    K.halo_fill(yb, L.PAD_REFLECT)
+    assert K.device_error() == 0
+    assert torch.equal(ya.padded_view(), yb.padded_view())
+    ref = F.leaky_relu(F.conv2d(F.pad(x, (pad,) * 4, mode="reflect").double(), wgt.double(), bias.double(), stride=stride), 0.2)
+    assert relerr(ya.interior_nchw(), ref) < 1e-3
+
+
 @pytest.mark.parametrize("shape", [(2, 32, 12, 20), (1, 128, 9, 7)])
 def test_cat_build(K, shape):
     """uegan_cat_build (one-pass decoder concat, opt-in) == uegan_upsample2x into the first half + uegan_instance_norm into

@@ -36,7 +36,7 @@ class ConvDesc(C.Structure):
                 ("stride", C.c_int32), ("pad", C.c_int32), ("act", C.c_int32), ("w_packed", C.c_void_p),
                 ("w_scale", C.c_void_p), ("bias", C.c_void_p), ("alpha", C.c_void_p), ("mul", C.POINTER(Tensor)), ("out_nchw", C.c_void_p),
                 ("residual_nchw", C.c_void_p), ("aux_nchw", C.c_void_p), ("y_mul", C.c_int32), ("y_off_h", C.c_int32), ("y_off_w", C.c_int32),
-                ("mask", C.POINTER(Tensor)), ("mask_act", C.c_int32), ("in_stats", C.c_void_p), ("y_premul", C.POINTER(Tensor)), ("y_cls_c", C.c_int32)]
+                ("mask", C.POINTER(Tensor)), ("mask_act", C.c_int32), ("in_stats", C.c_void_p), ("y_premul", C.POINTER(Tensor)), ("y_reflect_halo", C.c_int32), ("y_cls_c", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/uegan_sm100.h declares

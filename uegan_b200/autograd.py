@@ -185,18 +185,19 @@ def _g_forward_pass(G, x, ws):
             G._wscale(name, holder)
         G._update_weight_scales()
 
-    def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE, mul=None, premul=None):
+    def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE, mul=None, premul=None, halo=False):
+        """halo: dst's reflection-padding halo is written too (by the epilogue, or by a halo_fill launch after it)."""
         cv = holder.conv
         K.conv_fprop(src, G._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, 0, cv.bias, None, act_, mul=mul,
-                     w_scale=G._wscale(name, cv), premul=premul)
+                     w_scale=G._wscale(name, cv), premul=premul, reflect_halo=halo)
 
     # opt-in (UEGAN_PREMUL=1): measured r3e it moves the multiply's 0.4 ms into dec4's epilogue-bound launch, no net gain
     f16_premul = G._dtype != F32 and __import__("os").environ.get("UEGAN_PREMUL") == "1"
     K.pack_input(x, P["x0"], L.PAD_REFLECT)
-    conv(P["x0"], "enc1", G.enc1, d, 7, 1, P["x1"], act); K.halo_fill(P["x1"])
-    conv(P["x1"], "enc2", G.enc2, 2 * d, 3, 2, P["x2"], act); K.halo_fill(P["x2"])
-    conv(P["x2"], "enc3", G.enc3, 4 * d, 3, 2, P["x3"], act); K.halo_fill(P["x3"])
-    conv(P["x3"], "enc4", G.enc4, 8 * d, 3, 2, P["x4"], act); K.halo_fill(P["x4"])
+    conv(P["x0"], "enc1", G.enc1, d, 7, 1, P["x1"], act, halo=True)
+    conv(P["x1"], "enc2", G.enc2, 2 * d, 3, 2, P["x2"], act, halo=True)
+    conv(P["x2"], "enc3", G.enc3, 4 * d, 3, 2, P["x3"], act, halo=True)
+    conv(P["x3"], "enc4", G.enc4, 8 * d, 3, 2, P["x4"], act, halo=True)
     conv(P["x4"], "enc5", G.enc5, 16 * d, 3, 2, P["x5"], act)
     _gam_forward(G, "ga5", G.ga5, P["x5"], 16 * d, P["z5"], P["x5n"], 0, P["st5"], ws)
     src = P["x5n"]
@@ -219,7 +220,7 @@ def _g_forward_pass(G, x, ws):
     if not f16_premul:
         K.grad_combine(P["y4m"], d, add_b=P["y"][3], mul=P["x1"])  # y4.mul(x1) (y4 itself is kept for backward)
     K.halo_fill(P["y4m"])
-    conv(P["y4m"], "dec5.0", G.dec5[0], d, 3, 1, P["t"]); K.halo_fill(P["t"])
+    conv(P["y4m"], "dec5.0", G.dec5[0], d, 3, 1, P["t"], halo=True)
     out = torch.empty_like(x)
     cv = G.dec5[1].conv
     K.conv_planar(P["t"], cv.weight, G._wcache, "dec5.1", 7, 3, cv.bias, None, L.ACT_TANH, out, x, aux_nchw=P["res"],
@@ -516,8 +517,7 @@ def _d_forward_pass(D, x, ws, training):
         dst = ws["ds"][i - 1]
         wsc = D._wscale(f"d{i}", wgt)
         wp = D._wcache.get((f"d{i}", dt), wgt, lambda out=None: K.packed_weight(wgt, src.c, dt, out=out, w_scale=wsc))
-        K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, D._act, w_scale=wsc)
-        K.halo_fill(dst)
+        K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, D._act, w_scale=wsc, reflect_halo=True)
         pred = torch.empty(x.shape[0], 1, dst.h, dst.w, dtype=torch.float32, device=x.device)
         K.conv_planar(dst, head.weight, D._wcache, f"p{i}", k, pad, None, None, D._head_act, pred,
                       w_scale=D._wscale(f"p{i}", head.weight))

@@ -78,6 +78,10 @@ struct ConvParams {
   // (pi, pj) lands at output pixel (2a + pi, 2b + pj); cls_row / cls_pix = element strides of ONE output row / pixel
   int cls_c, cls_h, cls_w;
   long long cls_row, cls_pix;
+  // reflect_halo = p > 0: the epilogue also writes the reflection-padding halo of y (nn.ReflectionPad2d of the CONSUMER,
+  // models.py:82,93,161,173): the thread that owns interior pixel (i, j) stores its value at every halo position that
+  // mirrors it (rows -i / 2(H-1)-i for i within p of an edge, same for columns) -- no separate halo pass over the tensor
+  int reflect_halo;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -304,6 +308,27 @@ __device__ __forceinline__ void epilogue_nhwc(const ConvParams& p, uint32_t tadd
       uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + oc);
       op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      if (p.reflect_halo) {
+        // mirrors of (mk_h, mk_w): at most one per axis (host: H, W > 2 * halo + 1)
+        const int hp = p.reflect_halo;
+        const int dr = (mk_h >= 1 && mk_h <= hp) ? -2 * mk_h : ((mk_h <= p.Ho - 2 && mk_h >= p.Ho - 1 - hp) ? 2 * (p.Ho - 1 - mk_h) : 0);
+        const int dc = (mk_w >= 1 && mk_w <= hp) ? -2 * mk_w : ((mk_w <= p.Wo - 2 && mk_w >= p.Wo - 1 - hp) ? 2 * (p.Wo - 1 - mk_w) : 0);
+        if (dr | dc) {
+          uint16_t* ob = reinterpret_cast<uint16_t*>(p.out) + oc;
+          if (dr) {
+            uint4* o2 = reinterpret_cast<uint4*>(ob + (long long)dr * p.out_row);
+            o2[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); o2[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          if (dc) {
+            uint4* o2 = reinterpret_cast<uint4*>(ob + (long long)dc * p.out_pix);
+            o2[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); o2[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          if (dr && dc) {
+            uint4* o2 = reinterpret_cast<uint4*>(ob + (long long)dr * p.out_row + (long long)dc * p.out_pix);
+            o2[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); o2[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
     } else {
       float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + oc);
 #pragma unroll
@@ -842,6 +867,12 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
       const long long moff = (long long)mt.halo * p.mul_row + (long long)mt.halo * p.mul_pix;
       p.mul = static_cast<const uint8_t*>(mt.data) + moff * dtype_size(mt.dtype);
       p.smul = mt.scale;
+    }
+    if (d.y_reflect_halo) {
+      UEGAN_CHECK(y.halo >= 1 && y.dtype != UEGAN_F32 && ymul == 1 && d.y_off_h == 0 && d.y_off_w == 0 && !d.y_cls_c &&
+                      y.h > 2 * y.halo + 1 && y.w > 2 * y.halo + 1 && !d.out_nchw,
+                  "conv: y_reflect_halo needs a dense 16-bit NHWC output with a halo and h, w > 2 * halo + 1");
+      p.reflect_halo = y.halo;
     }
     if (d.y_premul) {
       const uegan_tensor& pt = *d.y_premul;

@@ -164,12 +164,21 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
                act: int = L.ACT_NONE, mul: Optional[NHWC] = None, out_nchw: Optional[torch.Tensor] = None,
                residual_nchw: Optional[torch.Tensor] = None, in_stats: Optional[torch.Tensor] = None,
                aux_nchw: Optional[torch.Tensor] = None, w_scale: Optional[torch.Tensor] = None,
-               premul: Optional[NHWC] = None):
-    """premul: with `mul`, the output before the multiplication is stored there as well."""
+               premul: Optional[NHWC] = None, reflect_halo: bool = False):
+    """premul: with `mul`, the output before the multiplication is stored there as well.
+    reflect_halo: also write y's reflection-padding halo (falls back to a halo_fill launch where the epilogue cannot)."""
     lib = L.load()
     d = L.ConvDesc()
     d.x = x.ct
     d.y_premul = C.pointer(premul.ct) if premul is not None else None
+    fill_after = False
+    if reflect_halo and y is not None and y.halo > 0:
+        import os
+        if (y.dtype != L.F32 and y.h > 2 * y.halo + 1 and y.w > 2 * y.halo + 1 and in_stats is None
+                and os.environ.get("UEGAN_NO_EPILOGUE_HALO") != "1"):
+            d.y_reflect_halo = 1
+        else:
+            fill_after = True
     if y is not None:
         d.y = y.ct
     d.y_c_off, d.cout, d.k, d.stride, d.pad, d.act = y_c_off, cout, k, stride, pad, act
@@ -194,6 +203,8 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
         cin = 3 if x.c * (4 if x.dtype == L.F32 else 2) == 16 else x.c
         ev.append((s0, s1, 2.0 * x.n * ho * wo * cout * k * k * cin, x, cout, k, stride, "fprop", x.dtype))
     _count(1, f"fprop ->{cout} k{k}s{stride}{' +stats' if in_stats is not None else ''}", x)
+    if fill_after:
+        halo_fill(y, L.PAD_REFLECT)
 
 
 def rowsum_supported(cout: int, cin_stored: int, k: int, dtype: int) -> bool:

@@ -282,17 +282,18 @@ class Generator(nn.Module, _ScaledNet):
                 self._wscale(name, holder)
             self._update_weight_scales()
 
-        def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE, off=0, mul=None, bias=True):
+        def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE, off=0, mul=None, bias=True, halo=False):
+            # halo: dst's reflection-padding halo is written too (by the epilogue, or by a halo_fill launch after it)
             cv = c(holder)
             K.conv_fprop(src, self._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, off,
-                         cv.bias if bias else None, None, act_, mul, w_scale=self._wscale(name, cv))
+                         cv.bias if bias else None, None, act_, mul, w_scale=self._wscale(name, cv), reflect_halo=halo)
 
         if not packed:
             K.pack_input(x, P["x0"], L.PAD_REFLECT)
-        conv(P["x0"], "enc1", self.enc1, d, 7, 1, P["x1"], act); K.halo_fill(P["x1"])
-        conv(P["x1"], "enc2", self.enc2, 2 * d, 3, 2, P["x2"], act); K.halo_fill(P["x2"])
-        conv(P["x2"], "enc3", self.enc3, 4 * d, 3, 2, P["x3"], act); K.halo_fill(P["x3"])
-        conv(P["x3"], "enc4", self.enc4, 8 * d, 3, 2, P["x4"], act); K.halo_fill(P["x4"])
+        conv(P["x0"], "enc1", self.enc1, d, 7, 1, P["x1"], act, halo=True)
+        conv(P["x1"], "enc2", self.enc2, 2 * d, 3, 2, P["x2"], act, halo=True)
+        conv(P["x2"], "enc3", self.enc3, 4 * d, 3, 2, P["x3"], act, halo=True)
+        conv(P["x3"], "enc4", self.enc4, 8 * d, 3, 2, P["x4"], act, halo=True)
         conv(P["x4"], "enc5", self.enc5, 16 * d, 3, 2, P["x5"], act)
 
         def gam(name, ga, src, ch, z, dst, off, up=None):
@@ -331,9 +332,8 @@ class Generator(nn.Module, _ScaledNet):
                 gam(gn, ga, P[skip], ch, P[z], P[cat], ch)
             K.halo_fill(P[cat])
             last = dn == "dec4"
-            conv(P[cat], dn, dec, ch, 3, 1, P[y], act, 0, P["x1"] if last else None)  # dec4 fuses y4.mul(x1)
-        K.halo_fill(P["y4m"])
-        conv(P["y4m"], "dec5.0", self.dec5[0], d, 3, 1, P["t"]); K.halo_fill(P["t"])
+            conv(P[cat], dn, dec, ch, 3, 1, P[y], act, 0, P["x1"] if last else None, halo=last)  # dec4 fuses y4.mul(x1)
+        conv(P["y4m"], "dec5.0", self.dec5[0], d, 3, 1, P["t"], halo=True)
         out = torch.empty_like(x)
         cv = c(self.dec5[1])
         K.conv_planar(P["t"], cv.weight, self._wcache, "dec5.1", 7, 3, cv.bias, None, L.ACT_TANH, out, x,
@@ -503,8 +503,7 @@ class Discriminator(nn.Module, _ScaledNet):
             wsc = self._wscale(f"d{i}", wgt)
             wp = self._wcache.get((f"d{i}", dt), wgt,
                                   lambda out=None: K.packed_weight(wgt, src.c, dt, out=out, w_scale=wsc))
-            K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, self._act, w_scale=wsc)
-            K.halo_fill(dst)
+            K.conv_fprop(src, wp, wgt.shape[0], k, 2, pad, dst, 0, conv.bias, alpha, self._act, w_scale=wsc, reflect_halo=True)
             pred = torch.empty(b, 1, dst.h, dst.w, dtype=torch.float32, device=x.device)
             K.conv_planar(dst, head.weight, self._wcache, f"p{i}", k, pad, None, None, self._head_act, pred,
                           w_scale=self._wscale(f"p{i}", head.weight))
