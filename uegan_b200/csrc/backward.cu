@@ -84,59 +84,68 @@ __global__ void grad_combine_kernel(CombineArgs q, int cv_log2) {
   for (int k = 0; k < VN; ++k) v[k] = 0.f;
   const bool interior = (y >= 0 && y < q.dst.h && x >= 0 && x < q.dst.w);
   if (interior) {
+    // every operand's 16 bytes are requested before the first one is used (one memory latency per thread, not one per operand)
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    uint4 ra = z4, rb = z4, rc = z4, rm2 = z4, rmul = z4, rmask = z4;
+    const T* ab = static_cast<const T*>(q.a.data);
+    if (q.has_a) ra = ldg16(ab + toff(q.a, n, y + q.pa, x + q.pa, q.a_c_off + c));
+    if (q.has_b) rb = ldg16(static_cast<const T*>(q.b.data) + toff(q.b, n, y, x, q.b_c_off + c));
+    if (q.has_c) rc = ldg16(static_cast<const T*>(q.c.data) + toff(q.c, n, y, x, q.c_c_off + c));
+    if (q.has_dst2) rm2 = ldg16(static_cast<const T*>(q.mul2.data) + toff(q.mul2, n, y, x, q.mul2_c_off + c));
+    if (q.has_mul) rmul = ldg16(static_cast<const T*>(q.mul.data) + toff(q.mul, n, y, x, q.mul_c_off + c));
+    if (q.has_mask) rmask = ldg16(static_cast<const T*>(q.mask.data) + toff(q.mask, n, y, x, q.mask_c_off + c));
     // per-tensor power-of-two scales: every addend is brought to the destination's scale (exact multiplications)
     const float so = tscale(q.dst);
     const float fa = q.has_a ? so * tinv(q.a) : 1.f, fb = q.has_b ? so * tinv(q.b) : 1.f, fc = q.has_c ? so * tinv(q.c) : 1.f;
+    float t[VN];
     if (q.has_a) {
-      const T* ab = static_cast<const T*>(q.a.data);
-      // positions of the padded tensor that map to (y, x)
-      int ys[3], xs[3], ny = 0, nx = 0;
-      ys[ny++] = y + q.pa;
-      xs[nx++] = x + q.pa;
+      cvt16<T>(ra, t);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) v[k] += t[k] * fa;
       if (q.reflect_a && q.pa > 0) {
+        // further positions of the padded tensor that map to (y, x): only within `pa` of an edge
+        int ys[3], xs[3], ny = 0, nx = 0;
+        ys[ny++] = y + q.pa;
+        xs[nx++] = x + q.pa;
         if (y >= 1 && y <= q.pa) ys[ny++] = q.pa - y;
         if (y <= q.dst.h - 2 && y >= q.dst.h - 1 - q.pa) ys[ny++] = q.pa + 2 * (q.dst.h - 1) - y;
         if (x >= 1 && x <= q.pa) xs[nx++] = q.pa - x;
         if (x <= q.dst.w - 2 && x >= q.dst.w - 1 - q.pa) xs[nx++] = q.pa + 2 * (q.dst.w - 1) - x;
-      }
-      for (int iy = 0; iy < ny; ++iy)
-        for (int ix = 0; ix < nx; ++ix) {
-          float t[VN];
-          Vec<T>::load(ab + toff(q.a, n, ys[iy], xs[ix], q.a_c_off + c), t);
+        if (ny * nx > 1)
+          for (int iy = 0; iy < ny; ++iy)
+            for (int ix = iy == 0 ? 1 : 0; ix < nx; ++ix) {
+              Vec<T>::load(ab + toff(q.a, n, ys[iy], xs[ix], q.a_c_off + c), t);
 #pragma unroll
-          for (int k = 0; k < VN; ++k) v[k] += t[k] * fa;
-        }
+              for (int k = 0; k < VN; ++k) v[k] += t[k] * fa;
+            }
+      }
     }
     if (q.has_b) {
-      float t[VN];
-      Vec<T>::load(static_cast<const T*>(q.b.data) + toff(q.b, n, y, x, q.b_c_off + c), t);
+      cvt16<T>(rb, t);
 #pragma unroll
       for (int k = 0; k < VN; ++k) v[k] += t[k] * fb;
     }
     if (q.has_c) {
-      float t[VN];
-      Vec<T>::load(static_cast<const T*>(q.c.data) + toff(q.c, n, y, x, q.c_c_off + c), t);
+      cvt16<T>(rc, t);
 #pragma unroll
       for (int k = 0; k < VN; ++k) v[k] += t[k] * fc;
     }
     if (q.has_dst2) {
-      float t[VN], o2[VN];
+      float o2[VN];
       const float f2 = tscale(q.dst2) * tinv(q.mul2) * pow2_rcp(so);  // the sum is in dst's scale: powers of two, exact
-      Vec<T>::load(static_cast<const T*>(q.mul2.data) + toff(q.mul2, n, y, x, q.mul2_c_off + c), t);
+      cvt16<T>(rm2, t);
 #pragma unroll
       for (int k = 0; k < VN; ++k) o2[k] = v[k] * (t[k] * f2);
       Vec<T>::store(static_cast<T*>(q.dst2.data) + toff(q.dst2, n, y, x, q.dst2_c_off + c), o2);
     }
     if (q.has_mul) {
-      float t[VN];
       const float fm = tinv(q.mul);
-      Vec<T>::load(static_cast<const T*>(q.mul.data) + toff(q.mul, n, y, x, q.mul_c_off + c), t);
+      cvt16<T>(rmul, t);
 #pragma unroll
       for (int k = 0; k < VN; ++k) v[k] *= t[k] * fm;
     }
     if (q.has_mask) {
-      float t[VN];
-      Vec<T>::load(static_cast<const T*>(q.mask.data) + toff(q.mask, n, y, x, q.mask_c_off + c), t);
+      cvt16<T>(rmask, t);
 #pragma unroll
       for (int k = 0; k < VN; ++k) {
         if (q.act == UEGAN_ACT_LRELU) v[k] *= (t[k] > 0.f ? 1.f : 0.2f);
@@ -318,7 +327,31 @@ __global__ void __launch_bounds__(256) affine_apply_kernel(const AffineArgs q) {
   extern __shared__ float s_coef[];  // [6][cch]: mean_a, rstd_a (or cf*rstd_x), mean_b, rstd_b, m1, m2
   constexpr int VN = Vec<T>::N;
   const int n = blockIdx.z, C = q.cch;
-  {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int xp = t >> q.cv_log2;
+  const bool live = xp < (int)q.dst.wp;
+  const int c = (t & ((1 << q.cv_log2) - 1)) * VN;
+  const int x = xp - q.dst.halo;
+  const bool xin = live && x >= 0 && x < q.dst.w;
+  for (int it = 0; it < kAffineIters; ++it) {
+  const int row0 = ((int)blockIdx.y * kAffineIters + it) * ROWS;  // first padded row of this trip
+  if (row0 >= (int)q.dst.hp) break;                               // (block-uniform; never on the first trip)
+  // the data loads of the trip go out first; the statistics prologue of the block then overlaps their latency
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  uint4 ar[ROWS], br[ROWS], dr[ROWS];
+  bool in[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int y = row0 + r - q.dst.halo;
+    in[r] = xin && y >= 0 && y < q.dst.h;
+    ar[r] = br[r] = dr[r] = z4;
+    if (in[r]) {
+      ar[r] = ldg16(static_cast<const T*>(q.a.data) + toff(q.a, n, y, x, q.a_c_off + c));
+      br[r] = ldg16(static_cast<const T*>(q.b.data) + toff(q.b, n, y, x, c));
+      if (q.has_deep) dr[r] = ldg16(static_cast<const TG*>(q.deep.data) + toff(q.deep, n, y, x, c));
+    }
+  }
+  if (it == 0) {
     const float cf = q.coef * (q.gscale ? __ldg(q.gscale) : 1.f) * (q.s_num0 ? __ldg(q.s_num0) : 1.f) *
                      (q.s_num1 ? __ldg(q.s_num1) : 1.f) / (q.s_den ? __ldg(q.s_den) : 1.f);
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
@@ -331,54 +364,47 @@ __global__ void __launch_bounds__(256) affine_apply_kernel(const AffineArgs q) {
       s_coef[5 * C + ch] = (float)(q.sums[si + 1] * q.inv_npix);
     }
     if (threadIdx.x == 0) s_coef[6 * C] = cf;
+    __syncthreads();
   }
-  __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int xp = t >> q.cv_log2;
-  if (xp >= (int)q.dst.wp) return;
-  const int c = (t & ((1 << q.cv_log2) - 1)) * VN;
-  const int x = xp - q.dst.halo;
-  const bool xin = x >= 0 && x < q.dst.w;
+  if (!live) continue;
   const float cf = s_coef[6 * C];
-  for (int it = 0; it < kAffineIters; ++it) {
-  const int row0 = ((int)blockIdx.y * kAffineIters + it) * ROWS;  // first padded row of this trip
-  if (row0 >= (int)q.dst.hp) break;
   float av[ROWS][VN], bv[ROWS][VN], dv[ROWS][VN];
-  bool in[ROWS];
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) {  // all loads first (independent), then the arithmetic
-    const int y = row0 + r - q.dst.halo;
-    in[r] = xin && y >= 0 && y < q.dst.h;
-    if (in[r]) {
-      Vec<T>::load(static_cast<const T*>(q.a.data) + toff(q.a, n, y, x, q.a_c_off + c), av[r]);
-      Vec<T>::load(static_cast<const T*>(q.b.data) + toff(q.b, n, y, x, c), bv[r]);
-      if (q.has_deep) Vec<TG>::load(static_cast<const TG*>(q.deep.data) + toff(q.deep, n, y, x, c), dv[r]);
-    }
+  for (int r = 0; r < ROWS; ++r) {
+    cvt16<T>(ar[r], av[r]);
+    cvt16<T>(br[r], bv[r]);
+    cvt16<TG>(dr[r], dv[r]);
   }
+  // (out-of-image positions hold zeros and are computed like any other, then selected away: no per-element branches)
   float v[ROWS][VN];
+  if (q.mode == 0) {
+    // stored tensors: xh is the true normalised value (ra = rstd / s_z), the bracket is in dout's stored units;
+    // s_coef[6 * C] (= cf) carries s_z * s_dz / s_dout, which turns ra * bracket into dz's stored units
 #pragma unroll
-  for (int k = 0; k < VN; ++k) {
-    const float ma = s_coef[c + k], ra = s_coef[C + c + k], mb = s_coef[2 * C + c + k], rb = s_coef[3 * C + c + k];
-    const float m1 = s_coef[4 * C + c + k], m2 = s_coef[5 * C + c + k];
+    for (int k = 0; k < VN; ++k) {
+      const float ma = s_coef[c + k], ra = s_coef[C + c + k], m1 = s_coef[4 * C + c + k], m2 = s_coef[5 * C + c + k];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      float g = 0.f;
-      if (in[r]) {
-        if (q.mode == 0) {
-          // stored tensors: xh is the true normalised value (ra = rstd / s_z), the bracket is in dout's stored units;
-          // s_coef[6 * C] (= cf) carries s_z * s_dz / s_dout, which turns ra * bracket into dz's stored units
-          const float xh = (bv[r][k] - ma) * ra;
-          g = cf * ra * (av[r][k] - m1 - xh * m2);
-        } else {
-          const float xh = (av[r][k] - ma) * ra;
-          const float yh = (bv[r][k] - mb) * rb;
-          const float e = xh - yh;
-          g = cf * ra * (e - m1 - xh * m2);
-          if (q.has_deep) g += dv[r][k];
-          g = av[r][k] > 0.f ? g : 0.f;  // ReLU mask of the tap
-        }
+      for (int r = 0; r < ROWS; ++r) {
+        const float xh = (bv[r][k] - ma) * ra;
+        const float g = cf * ra * (av[r][k] - m1 - xh * m2);
+        v[r][k] = in[r] ? g : 0.f;
       }
-      v[r][k] = g;
+    }
+  } else {
+    const bool deep = q.has_deep != 0;
+#pragma unroll
+    for (int k = 0; k < VN; ++k) {
+      const float ma = s_coef[c + k], ra = s_coef[C + c + k], mb = s_coef[2 * C + c + k], rb = s_coef[3 * C + c + k];
+      const float m1 = s_coef[4 * C + c + k], m2 = s_coef[5 * C + c + k];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const float xh = (av[r][k] - ma) * ra;
+        const float yh = (bv[r][k] - mb) * rb;
+        const float e = xh - yh;
+        const float g0 = cf * ra * (e - m1 - xh * m2);
+        const float g = deep ? g0 + dv[r][k] : g0;
+        v[r][k] = (in[r] && av[r][k] > 0.f) ? g : 0.f;  // ReLU mask of the tap
+      }
     }
   }
 #pragma unroll
@@ -449,18 +475,31 @@ __global__ void upsample2x_bwd_kernel(TGeom g, int g_c_off, TGeom d, float sy, f
 #pragma unroll
   for (int k = 0; k < VN; ++k) acc[k] = 0.f;
   const T* gb = static_cast<const T*>(g.data);
+  // two candidate rows per trip: their (up to 12) loads are requested together, predicated on a non-zero weight, before
+  // the first one is consumed (one tap at a time serialised ~9 memory latencies per thread, r4e); the sum keeps the
+  // order of the scatter's adjoint (rows ascending, columns ascending) and zero-weight taps add nothing
 #pragma unroll
-  for (int jy = 0; jy < 6; ++jy) {
-    if (wy[jy] == 0.f) continue;
-    const T* gr = gb + toff(g, n, 2 * yi - 2 + jy, 2 * xi - 2, g_c_off + c);
+  for (int jy0 = 0; jy0 < 6; jy0 += 2) {
+    uint4 rr[2][6];
 #pragma unroll
-    for (int jx = 0; jx < 6; ++jx) {
-      if (wx[jx] == 0.f) continue;
-      float tv[VN];
-      Vec<T>::load(gr + (long long)jx * g.c, tv);
+    for (int a = 0; a < 2; ++a) {
+      const T* gr = gb + toff(g, n, 2 * yi - 2 + jy0 + a, 2 * xi - 2, g_c_off + c);
 #pragma unroll
-      for (int k = 0; k < VN; ++k) acc[k] += wy[jy] * wx[jx] * tv[k];  // same order as the scatter's adjoint sum
+      for (int jx = 0; jx < 6; ++jx) {
+        rr[a][jx] = make_uint4(0u, 0u, 0u, 0u);
+        if (wy[jy0 + a] != 0.f && wx[jx] != 0.f) rr[a][jx] = ldg16(gr + (long long)jx * g.c);
+      }
     }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int jx = 0; jx < 6; ++jx) {
+        if (wy[jy0 + a] == 0.f || wx[jx] == 0.f) continue;
+        float tv[VN];
+        cvt16<T>(rr[a][jx], tv);
+#pragma unroll
+        for (int k = 0; k < VN; ++k) acc[k] += wy[jy0 + a] * wx[jx] * tv[k];  // same order as the scatter's adjoint sum
+      }
   }
   const float rs = tscale(d) * tinv(g);
 #pragma unroll

@@ -71,6 +71,32 @@ template <> struct Vec<__half> {
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 };
+// Raw 16-byte vector load + a separate convert: kernels with several optional operands issue EVERY load first and convert /
+// combine afterwards, so one thread keeps all its operands in flight instead of waiting on each in turn (Vec<T>::load
+// followed by its use inside `if (has_x)` serialised up to five global-memory latencies per thread, r4e).
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+template <typename T> __device__ __forceinline__ void cvt16(const uint4& q, float (&v)[Vec<T>::N]);
+template <> __device__ __forceinline__ void cvt16<float>(const uint4& q, float (&v)[4]) {
+  v[0] = __uint_as_float(q.x); v[1] = __uint_as_float(q.y); v[2] = __uint_as_float(q.z); v[3] = __uint_as_float(q.w);
+}
+template <> __device__ __forceinline__ void cvt16<__half>(const uint4& q, float (&v)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+    v[2 * i] = __low2float(h);
+    v[2 * i + 1] = __high2float(h);
+  }
+}
+template <> __device__ __forceinline__ void cvt16<__nv_bfloat16>(const uint4& q, float (&v)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    v[2 * i] = __low2float(h);
+    v[2 * i + 1] = __high2float(h);
+  }
+}
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
