@@ -18,6 +18,7 @@ namespace uegan {
 template <typename T>
 __global__ void head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ outv, const float* __restrict__ xin,
                                 TGeom d, int cch, int mode, long long total) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int xp = (int)(i % d.wp);
@@ -72,6 +73,7 @@ struct CombineArgs {
 // grid = (x-chunks of a padded row, padded rows, images): no per-thread divisions (cv is a power of two)
 template <typename T>
 __global__ void grad_combine_kernel(CombineArgs q, int cv_log2) {
+  pdl_sync();
   constexpr int VN = Vec<T>::N;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int xp = t >> cv_log2;
@@ -166,6 +168,7 @@ __global__ void grad_combine_kernel(CombineArgs q, int cv_log2) {
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void fold_inplace_kernel(TGeom t, int cv_log2) {
+  pdl_sync();
   constexpr int VN = Vec<T>::N;
   const int y = blockIdx.y, n = blockIdx.z, pa = t.halo;
   const int cv = 1 << cv_log2;
@@ -211,6 +214,7 @@ __global__ void fold_inplace_kernel(TGeom t, int cv_log2) {
 // ------------------------------------------------------------------------------------------
 template <typename T, int COUT>
 __global__ void dz_hstack_kernel(TGeom dz, TGeom e, int k, long long total) {
+  pdl_sync();
   constexpr int VN = Vec<T>::N;  // dz stores one 16-byte vector per pixel (4 fp32 / 8 fp16 channels, COUT real ones)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -323,6 +327,7 @@ struct AffineArgs {
 // 1.08 -> 0.96 ms per step; the 16-bit tap backward slower, 1.55 -> 1.79 ms, so it keeps one trip)
 template <typename T, typename TG, int ROWS>
 __global__ void __launch_bounds__(256) affine_apply_kernel(const AffineArgs q) {
+  pdl_sync();
   constexpr int kAffineIters = sizeof(T) == 4 ? 4 : 1;
   extern __shared__ float s_coef[];  // [6][cch]: mean_a, rstd_a (or cf*rstd_x), mean_b, rstd_b, m1, m2
   constexpr int VN = Vec<T>::N;
@@ -426,7 +431,7 @@ static int launch_affine_apply(AffineArgs& q, cudaStream_t st) {
   UEGAN_CHECK(q.dst.n <= 65535 && (q.dst.hp + RB - 1) / RB <= 65535, "normalisation backward: tensor too large");
   q.cv_log2 = lg;
   const dim3 grid((unsigned)((q.dst.wp * cv + 255) / 256), (unsigned)((q.dst.hp + RB - 1) / RB), (unsigned)q.dst.n);
-  affine_apply_kernel<T, TG, ROWS><<<grid, 256, (6 * q.cch + 1) * sizeof(float), st>>>(q);
+  launch_pdl(affine_apply_kernel<T, TG, ROWS>, grid, 256, (6 * q.cch + 1) * sizeof(float), st, q);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -439,6 +444,7 @@ static int launch_affine_apply(AffineArgs& q, cudaStream_t st) {
 // grid = (x-chunks of an input row, input rows, images).
 template <typename T>
 __global__ void upsample2x_bwd_kernel(TGeom g, int g_c_off, TGeom d, float sy, float sx, int cv_log2) {
+  pdl_sync();
   constexpr int VN = Vec<T>::N;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int xi = t >> cv_log2;
@@ -514,6 +520,7 @@ __global__ void upsample2x_bwd_kernel(TGeom g, int g_c_off, TGeom d, float sy, f
 // ------------------------------------------------------------------------------------------
 template <typename T, typename TG>
 __global__ void maxpool2x2_bwd_kernel(TGeom src, TGeom dpool, TGeom dst, long long total) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   constexpr int VN = 8;
@@ -592,6 +599,7 @@ template <typename TG>
 __global__ void unpack_grad_kernel(TGeom s, float* __restrict__ dst, float s0, float s1, float s2, long long total,
                                    const float* __restrict__ skip_dout, const float* __restrict__ skip_res,
                                    const float* __restrict__ skip_x) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int x = (int)(i % s.w);
@@ -618,9 +626,9 @@ using namespace uegan;
 
 #define UEGAN_DISPATCH(dtype, KERNEL, ...)                      \
   do {                                                          \
-    if ((dtype) == UEGAN_F32) KERNEL<float> __VA_ARGS__;        \
-    else if ((dtype) == UEGAN_BF16) KERNEL<__nv_bfloat16> __VA_ARGS__; \
-    else KERNEL<__half> __VA_ARGS__;                            \
+    if ((dtype) == UEGAN_F32) launch_pdl(KERNEL<float>, __VA_ARGS__);        \
+    else if ((dtype) == UEGAN_BF16) launch_pdl(KERNEL<__nv_bfloat16>, __VA_ARGS__); \
+    else launch_pdl(KERNEL<__half>, __VA_ARGS__);                            \
   } while (0)
 
 extern "C" {
@@ -634,8 +642,8 @@ int uegan_head_bwd(const float* dout_nchw, const float* out_nchw, const float* x
   const TGeom d = geom(*dz);
   const long long total = (long long)d.n * d.hp * d.wp;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  UEGAN_DISPATCH(dz->dtype, head_bwd_kernel, <<<nblk(total, 256), 256, 0, st>>>(dout_nchw, out_nchw, x_nchw, d, channels,
-                                                                                mode, total));
+  UEGAN_DISPATCH(dz->dtype, head_bwd_kernel, nblk(total, 256), 256, 0, st, dout_nchw, out_nchw, x_nchw, d, channels,
+                                                                                mode, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -680,7 +688,7 @@ static int grad_combine_impl(const uegan_tensor* dst, int32_t dst_c_off, int32_t
   UEGAN_CHECK(q.dst.hp <= 65535 && q.dst.n <= 65535, "grad_combine: tensor too large for the launch grid");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(nblk((long long)q.dst.wp * cv, 256), (unsigned)q.dst.hp, (unsigned)q.dst.n);
-  UEGAN_DISPATCH(dst->dtype, grad_combine_kernel, <<<grid, 256, 0, st>>>(q, cv_log2));
+  UEGAN_DISPATCH(dst->dtype, grad_combine_kernel, grid, 256, 0, st, q, cv_log2);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -717,7 +725,7 @@ int uegan_fold_inplace(const uegan_tensor* t, void* stream) {
   UEGAN_CHECK(g.h <= 65535 && g.n <= 65535, "fold_inplace: tensor too large for the launch grid");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(1u, (unsigned)g.h, (unsigned)g.n);
-  UEGAN_DISPATCH(t->dtype, fold_inplace_kernel, <<<grid, 256, 0, st>>>(g, lg));
+  UEGAN_DISPATCH(t->dtype, fold_inplace_kernel, grid, 256, 0, st, g, lg);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -735,11 +743,11 @@ int uegan_dz_hstack(const uegan_tensor* dz, int32_t cout, int32_t k, const uegan
   const long long total = (long long)g.n * g.h * g.w;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dz->dtype == UEGAN_F32) {
-    if (cout == 1) dz_hstack_kernel<float, 1><<<nblk(total, 256), 256, 0, st>>>(d, g, k, total);
-    else dz_hstack_kernel<float, 3><<<nblk(total, 256), 256, 0, st>>>(d, g, k, total);
+    if (cout == 1) launch_pdl(dz_hstack_kernel<float, 1>, nblk(total, 256), 256, 0, st, d, g, k, total);
+    else launch_pdl(dz_hstack_kernel<float, 3>, nblk(total, 256), 256, 0, st, d, g, k, total);
   } else {
-    if (cout == 1) dz_hstack_kernel<__half, 1><<<nblk(total, 256), 256, 0, st>>>(d, g, k, total);
-    else dz_hstack_kernel<__half, 3><<<nblk(total, 256), 256, 0, st>>>(d, g, k, total);
+    if (cout == 1) launch_pdl(dz_hstack_kernel<__half, 1>, nblk(total, 256), 256, 0, st, d, g, k, total);
+    else launch_pdl(dz_hstack_kernel<__half, 3>, nblk(total, 256), 256, 0, st, d, g, k, total);
   }
   UEGAN_CUDA(cudaGetLastError());
   return 0;
@@ -821,7 +829,7 @@ int uegan_upsample2x_bwd(const uegan_tensor* dout, int32_t d_c_off, const uegan_
   UEGAN_CHECK(d.h <= 65535 && d.n <= 65535, "upsample2x_bwd: tensor too large for the launch grid");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(nblk((long long)d.w * cv, 256), (unsigned)d.h, (unsigned)d.n);
-  UEGAN_DISPATCH(dsrc->dtype, upsample2x_bwd_kernel, <<<grid, 256, 0, st>>>(g, d_c_off, d, sy, sx, lg));
+  UEGAN_DISPATCH(dsrc->dtype, upsample2x_bwd_kernel, grid, 256, 0, st, g, d_c_off, d, sy, sx, lg);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -835,7 +843,7 @@ int uegan_maxpool2x2_bwd(const uegan_tensor* src, const uegan_tensor* dpool, con
               "maxpool2x2_bwd: tensor mismatch");
   const TGeom s = geom(*src), g = geom(*dpool), d = geom(*dsrc);
   const long long total = (long long)g.n * g.h * g.w * (s.c / 8);
-  maxpool2x2_bwd_kernel<__half, __half><<<nblk(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(s, g, d, total);
+  launch_pdl(maxpool2x2_bwd_kernel<__half, __half>, nblk(total, 256), 256, 0, static_cast<cudaStream_t>(stream), s, g, d, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -893,8 +901,8 @@ int uegan_unpack_input_grad(const uegan_tensor* dx, const float* scale_host, flo
   const long long total = (long long)s.n * 3 * s.h * s.w;
   const float s0 = scale_host ? scale_host[0] : 1.f, s1 = scale_host ? scale_host[1] : 1.f, s2 = scale_host ? scale_host[2] : 1.f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  UEGAN_DISPATCH(dx->dtype, unpack_grad_kernel, <<<nblk(total, 256), 256, 0, st>>>(s, dst_nchw, s0, s1, s2, total,
-                                                                                   skip_dout_nchw, skip_res_nchw, skip_x_nchw));
+  UEGAN_DISPATCH(dx->dtype, unpack_grad_kernel, nblk(total, 256), 256, 0, st, s, dst_nchw, s0, s1, s2, total,
+                                                                                   skip_dout_nchw, skip_res_nchw, skip_x_nchw);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

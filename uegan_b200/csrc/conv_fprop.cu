@@ -410,6 +410,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 2 * kAccCols);
+  pdl_sync();  // everything above is on-chip set-up: it overlaps the tail of the preceding kernel
   if (p.bias && !p.out_nchw) {
     const float bm = (p.sy ? __ldg(p.sy) : 1.0f) / (p.smul ? __ldg(p.smul) : 1.0f);
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_bias[i] = i < p.cout ? __ldg(p.bias + i) * bm : 0.f;
@@ -1050,20 +1051,20 @@ int launch_conv_fprop(const uegan_conv_desc& d, cudaStream_t stream) {
   UEGAN_CHECK(!occ2 || smem_bytes <= 100 * 1024, "conv: internal: two-CTA build with %d bytes of shared memory", smem_bytes);
   if (occ2) {
     if (x.dtype == UEGAN_F32) {
-      if (patch) conv_fprop_kernel<1, 1, 1><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
-      else conv_fprop_kernel<1, 0, 1><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+      if (patch) launch_pdl(conv_fprop_kernel<1, 1, 1>, grid, 256, smem_bytes, stream, tmA, tmB, p);
+      else launch_pdl(conv_fprop_kernel<1, 0, 1>, grid, 256, smem_bytes, stream, tmA, tmB, p);
     } else {
-      if (patch) conv_fprop_kernel<0, 1, 1><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
-      else conv_fprop_kernel<0, 0, 1><<<grid, 256, smem_bytes, stream>>>(tmA, tmB, p);
+      if (patch) launch_pdl(conv_fprop_kernel<0, 1, 1>, grid, 256, smem_bytes, stream, tmA, tmB, p);
+      else launch_pdl(conv_fprop_kernel<0, 0, 1>, grid, 256, smem_bytes, stream, tmA, tmB, p);
     }
   } else if (x.dtype == UEGAN_F32) {
-    if (stream_w) conv_fprop_kernel<1, 2, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
-    else if (patch) conv_fprop_kernel<1, 1, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
-    else conv_fprop_kernel<1, 0, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    if (stream_w) launch_pdl(conv_fprop_kernel<1, 2, 0>, grid, 384, smem_bytes, stream, tmA, tmB, p);
+    else if (patch) launch_pdl(conv_fprop_kernel<1, 1, 0>, grid, 384, smem_bytes, stream, tmA, tmB, p);
+    else launch_pdl(conv_fprop_kernel<1, 0, 0>, grid, 384, smem_bytes, stream, tmA, tmB, p);
   } else {
-    if (stream_w) conv_fprop_kernel<0, 2, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
-    else if (patch) conv_fprop_kernel<0, 1, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
-    else conv_fprop_kernel<0, 0, 0><<<grid, 384, smem_bytes, stream>>>(tmA, tmB, p);
+    if (stream_w) launch_pdl(conv_fprop_kernel<0, 2, 0>, grid, 384, smem_bytes, stream, tmA, tmB, p);
+    else if (patch) launch_pdl(conv_fprop_kernel<0, 1, 0>, grid, 384, smem_bytes, stream, tmA, tmB, p);
+    else launch_pdl(conv_fprop_kernel<0, 0, 0>, grid, 384, smem_bytes, stream, tmA, tmB, p);
   }
   UEGAN_CUDA(cudaGetLastError());
   return 0;
@@ -1081,6 +1082,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
                                    int cin_first, int cin, int cin_stored, int k, int row_pad, int cout_pad,
                                    int mode, int k_orig, int q, int pi, int pj, long long total,
                                    const float* __restrict__ wscale) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   if (gridDim.y > 1) {  // all four parity classes of a stride-2 data-gradient operand in one launch: class = blockIdx.y
@@ -1135,15 +1137,15 @@ static int pack_impl(const float* w_oihw, void* w_packed, int cout, int cin_tota
   const dim3 blocks((unsigned)((total + threads - 1) / threads), (unsigned)classes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == UEGAN_F32)
-    pack_weight_kernel<float><<<blocks, threads, 0, st>>>(w_oihw, static_cast<float*>(w_packed), cout, cin_total,
+    launch_pdl(pack_weight_kernel<float>, blocks, threads, 0, st, w_oihw, static_cast<float*>(w_packed), cout, cin_total,
                                                           cin_first, cin, cin_stored, k, g.row_pad, g.cout_pad, mode,
                                                           k_orig, q, pi, pj, total, wscale);
   else if (dtype == UEGAN_BF16)
-    pack_weight_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed), cout,
+    launch_pdl(pack_weight_kernel<__nv_bfloat16>, blocks, threads, 0, st, w_oihw, static_cast<__nv_bfloat16*>(w_packed), cout,
                                                                    cin_total, cin_first, cin, cin_stored, k, g.row_pad,
                                                                    g.cout_pad, mode, k_orig, q, pi, pj, total, wscale);
   else
-    pack_weight_kernel<__half><<<blocks, threads, 0, st>>>(w_oihw, static_cast<__half*>(w_packed), cout, cin_total,
+    launch_pdl(pack_weight_kernel<__half>, blocks, threads, 0, st, w_oihw, static_cast<__half*>(w_packed), cout, cin_total,
                                                            cin_first, cin, cin_stored, k, g.row_pad, g.cout_pad, mode,
                                                            k_orig, q, pi, pj, total, wscale);
   UEGAN_CUDA(cudaGetLastError());

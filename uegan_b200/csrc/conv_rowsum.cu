@@ -131,6 +131,7 @@ conv_rowsum_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_sync();  // everything above is on-chip set-up: it overlaps the tail of the preceding kernel
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (warp == 0) {
@@ -240,6 +241,7 @@ conv_rowsum_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 template <typename T>
 __global__ void pack_weight_rowsum_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin_total,
                                           int cin_first, int cin, int csp, int k, int nb, const float* __restrict__ wscale) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nb * k * csp) return;
   const int c = i % csp, r = (i / csp) % k, nrow = i / (csp * k);
@@ -325,10 +327,10 @@ static int pack_rowsum_impl(const float* w_oihw, void* w_packed, int cout, int c
   const int total = nb * k * csp;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == UEGAN_F32)
-    pack_weight_rowsum_kernel<float><<<(total + 255) / 256, 256, 0, st>>>(w_oihw, static_cast<float*>(w_packed), cout,
+    launch_pdl(pack_weight_rowsum_kernel<float>, (total + 255) / 256, 256, 0, st, w_oihw, static_cast<float*>(w_packed), cout,
                                                                          cin_total, cin_first, cin, csp, k, nb, wscale);
   else
-    pack_weight_rowsum_kernel<__half><<<(total + 255) / 256, 256, 0, st>>>(w_oihw, static_cast<__half*>(w_packed), cout,
+    launch_pdl(pack_weight_rowsum_kernel<__half>, (total + 255) / 256, 256, 0, st, w_oihw, static_cast<__half*>(w_packed), cout,
                                                                           cin_total, cin_first, cin, csp, k, nb, wscale);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
@@ -397,8 +399,8 @@ int uegan_conv2d_fprop_rowsum(const uegan_conv_desc* desc, void* stream) {
   const int smem_bytes = p.w_total_bytes + p.num_stages * p.stage_bytes + 1024;
   const int max_ctas = p.occ2 ? 2 * num_sms() : num_sms();
   const int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
-  if (f16) conv_rowsum_kernel<1><<<grid, 384, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
-  else conv_rowsum_kernel<0><<<grid, 384, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  if (f16) launch_pdl(conv_rowsum_kernel<1>, grid, 384, smem_bytes, static_cast<cudaStream_t>(stream), tmA, tmB, p);
+  else launch_pdl(conv_rowsum_kernel<0>, grid, 384, smem_bytes, static_cast<cudaStream_t>(stream), tmA, tmB, p);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

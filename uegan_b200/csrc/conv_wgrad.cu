@@ -67,6 +67,7 @@ __device__ __forceinline__ void wg_publish(float* dw, float* partial, long long 
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(float* __restrict__ dw, const float* __restrict__ partial,
                                                            long long dw_numel, int slices, int cin_total, int cin_first,
                                                            int cin, int kk, int lanes_log2) {
+  pdl_sync();
   __shared__ float sh[256];
   const int L = 1 << lanes_log2, E = 256 >> lanes_log2;
   const int e = threadIdx.x & (E - 1), l = threadIdx.x >> (8 - lanes_log2);
@@ -139,6 +140,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_sync();  // everything above is on-chip set-up: it overlaps the tail of the preceding kernel
 
   if (kt0 < kt1) {
     if (warp == 0) {
@@ -309,7 +311,7 @@ static int wg_reduce(float* dw, const float* ws, long long dw_numel, int ksplit,
   int lanes_log2 = 0;
   while (lanes_log2 < 5 && (8 << lanes_log2) < slices) ++lanes_log2;
   const int E = 256 >> lanes_log2;
-  wgrad_reduce_kernel<<<(unsigned)((dw_numel + E - 1) / E), 256, 0, st>>>(dw, ws, dw_numel, slices, cin_total, cin_first, cin,
+  launch_pdl(wgrad_reduce_kernel, (unsigned)((dw_numel + E - 1) / E), 256, 0, st, dw, ws, dw_numel, slices, cin_total, cin_first, cin,
                                                                          k * k, lanes_log2);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
@@ -456,8 +458,8 @@ extern "C" int uegan_conv2d_wgrad(const uegan_tensor* x, const uegan_tensor* dz,
   }
   const int smem_bytes = p.num_stages * p.stage_bytes + 1024;
   dim3 grid((unsigned)p.ksplit, (unsigned)p.taps, (unsigned)(p.m_tiles * p.n_chunks));
-  if (f16) conv_wgrad_kernel<1><<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
-  else conv_wgrad_kernel<0><<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  if (f16) launch_pdl(conv_wgrad_kernel<1>, grid, 256, smem_bytes, static_cast<cudaStream_t>(stream), tmA, tmB, p);
+  else launch_pdl(conv_wgrad_kernel<0>, grid, 256, smem_bytes, static_cast<cudaStream_t>(stream), tmA, tmB, p);
   UEGAN_CUDA(cudaGetLastError());
   return wg_reduce(dw_oihw, ws, p.dw_numel, p.ksplit, p.total_ktiles, cin_total, cin_first, cin, k,
                    static_cast<cudaStream_t>(stream));
@@ -549,6 +551,7 @@ conv_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_sync();  // everything above is on-chip set-up: it overlaps the tail of the preceding kernel
 
   if (kt0 < kt1) {
     if (warp == 0) {
@@ -755,10 +758,10 @@ static int launch_wgrad_patch(const uegan_tensor* x, const uegan_tensor* dz, int
   dim3 grid((unsigned)p.ksplit, (unsigned)slices, 1u);
   if (f16) {
     if (wgrad_patch_set_attr<1>()) return -1;
-    conv_wgrad_patch_kernel<1><<<grid, 256, smem_bytes, stream>>>(tmX, tmZ, p);
+    launch_pdl(conv_wgrad_patch_kernel<1>, grid, 256, smem_bytes, stream, tmX, tmZ, p);
   } else {
     if (wgrad_patch_set_attr<0>()) return -1;
-    conv_wgrad_patch_kernel<0><<<grid, 256, smem_bytes, stream>>>(tmX, tmZ, p);
+    launch_pdl(conv_wgrad_patch_kernel<0>, grid, 256, smem_bytes, stream, tmX, tmZ, p);
   }
   if (cudaGetLastError() != cudaSuccess) return set_error("conv2d_wgrad: patch kernel launch failed");
   if (wg_reduce(dw, ws, p.dw_numel, p.ksplit, p.total_ktiles, cin_total, cin_first, cin, k, stream)) return -1;
@@ -848,10 +851,10 @@ extern "C" int uegan_conv2d_wgrad_hstack(const uegan_tensor* x, const uegan_tens
   dim3 grid((unsigned)p.ksplit, (unsigned)slices, 1u);
   if (f16) {
     if (wgrad_patch_set_attr<1>()) return -1;
-    conv_wgrad_patch_kernel<1><<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmX, tmZ, p);
+    launch_pdl(conv_wgrad_patch_kernel<1>, grid, 256, smem_bytes, static_cast<cudaStream_t>(stream), tmX, tmZ, p);
   } else {
     if (wgrad_patch_set_attr<0>()) return -1;
-    conv_wgrad_patch_kernel<0><<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmX, tmZ, p);
+    launch_pdl(conv_wgrad_patch_kernel<0>, grid, 256, smem_bytes, static_cast<cudaStream_t>(stream), tmX, tmZ, p);
   }
   UEGAN_CUDA(cudaGetLastError());
   return wg_reduce(dw_oihw, ws, p.dw_numel, p.ksplit, p.total_ktiles, cin_total, cin_first, cin, k,
@@ -972,7 +975,7 @@ extern "C" int uegan_conv2d_wgrad_zwin(const uegan_tensor* x, const uegan_tensor
   const int smem_bytes = p.num_stages * p.stage_bytes + 1024;
   dim3 grid((unsigned)p.ksplit, (unsigned)slices, 1u);
   if (wgrad_patch_set_attr<1>()) return -1;
-  conv_wgrad_patch_kernel<1><<<grid, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmX, tmZ, p);
+  launch_pdl(conv_wgrad_patch_kernel<1>, grid, 256, smem_bytes, static_cast<cudaStream_t>(stream), tmX, tmZ, p);
   UEGAN_CUDA(cudaGetLastError());
   return wg_reduce(dw_oihw, ws, p.dw_numel, p.ksplit, p.total_ktiles, cin_total, cin_first, cin, k,
                    static_cast<cudaStream_t>(stream));

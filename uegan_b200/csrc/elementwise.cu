@@ -142,6 +142,7 @@ __device__ __forceinline__ long long toff(const TGeom& g, int n, int y, int x, i
 // ------------------------------------------------------------------------------------------
 template <typename T, int NACC, typename Op>
 __global__ void __launch_bounds__(256) strip_reduce_kernel(Op op, int cch, int h, int w, int rows) {
+  pdl_sync();
   constexpr int VN = Vec<T>::N;
   __shared__ float sh[256 * VN * NACC];
   const int cv = cch / VN;
@@ -191,7 +192,7 @@ template <typename T, int NACC, typename Op>
 static void launch_strip_reduce(const Op& op, int cch, int n, int h, int w, cudaStream_t st) {
   const int rows = h >= 64 ? 8 : (h >= 16 ? 4 : h);
   dim3 grid((unsigned)((h + rows - 1) / rows), (unsigned)n);
-  strip_reduce_kernel<T, NACC, Op><<<grid, 256, 0, st>>>(op, cch, h, w, rows);
+  launch_pdl(strip_reduce_kernel<T, NACC, Op>, grid, 256, 0, st, op, cch, h, w, rows);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -200,6 +201,7 @@ static void launch_strip_reduce(const Op& op, int cch, int n, int h, int w, cuda
 template <typename T>
 __global__ void pack_input_kernel(const float* __restrict__ src, TGeom d, int reflect, float s0, float s1, float s2,
                                   float b0, float b1, float b2, long long total) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int xp = (int)(i % d.wp);
@@ -234,6 +236,7 @@ __global__ void pack_input_kernel(const float* __restrict__ src, TGeom d, int re
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void halo_fill_kernel(TGeom t, int reflect, long long total) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int cv = t.c / Vec<T>::N;
@@ -295,6 +298,7 @@ static void run_in_stats(const TGeom& s, double* stats, cudaStream_t st) {
 // = rstd / s, so that (stored - mean_st) * rstd_st is the true normalised value.
 __global__ void in_finalize_kernel(const double* __restrict__ stats, float* __restrict__ mr, int total, double inv_npix,
                                    float eps, const float* __restrict__ src_scale) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const double s = src_scale ? (double)__ldg(src_scale) : 1.0;
@@ -308,6 +312,7 @@ __global__ void in_finalize_kernel(const double* __restrict__ stats, float* __re
 // grid = (x-chunks of a row, rows, images): no per-thread divisions (cv is a power of two)
 template <typename T>
 __global__ void in_apply_kernel(TGeom s, TGeom d, int dst_c_off, const float* __restrict__ mr, int cv_log2) {
+  pdl_sync();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int x = t >> cv_log2;
   if (x >= s.w) return;
@@ -334,6 +339,7 @@ __global__ void in_apply_kernel(TGeom s, TGeom d, int dst_c_off, const float* __
 // grid = (x-chunks of an output row, output rows, images): no per-thread divisions (cv is a power of two)
 template <typename T>
 __global__ void upsample2x_kernel(TGeom s, TGeom d, int dst_c_off, float sy, float sx, int cv_log2) {
+  pdl_sync();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int xo = t >> cv_log2;
   if (xo >= d.w) return;
@@ -366,6 +372,7 @@ __global__ void upsample2x_kernel(TGeom s, TGeom d, int dst_c_off, float sy, flo
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void cat_build_kernel(TGeom u, TGeom z, TGeom d, const float* __restrict__ mr, float sy, float sx, int cv_log2) {
+  pdl_sync();
   constexpr int VN = Vec<T>::N;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int xo = t >> cv_log2;
@@ -406,6 +413,7 @@ __global__ void cat_build_kernel(TGeom u, TGeom z, TGeom d, const float* __restr
 
 template <typename T>
 __global__ void maxpool2x2_kernel(TGeom s, TGeom d, long long total) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int cv = s.c / Vec<T>::N;
@@ -428,6 +436,7 @@ __global__ void maxpool2x2_kernel(TGeom s, TGeom d, long long total) {
 
 template <typename T>
 __global__ void unpack_nchw_kernel(TGeom s, int c_off, int c_count, float* __restrict__ dst, long long total) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int x = (int)(i % s.w);
@@ -467,13 +476,13 @@ int uegan_pack_input(const float* x_nchw, const uegan_tensor* dst, int32_t pad_m
               b2 = shift_host ? shift_host[2] : 0.f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dst->dtype == UEGAN_F32)
-    pack_input_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(x_nchw, d, pad_mode == UEGAN_PAD_REFLECT, s0, s1, s2,
+    launch_pdl(pack_input_kernel<float>, nblocks(total, 256), 256, 0, st, x_nchw, d, pad_mode == UEGAN_PAD_REFLECT, s0, s1, s2,
                                                                   b0, b1, b2, total);
   else if (dst->dtype == UEGAN_BF16)
-    pack_input_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(x_nchw, d, pad_mode == UEGAN_PAD_REFLECT, s0,
+    launch_pdl(pack_input_kernel<__nv_bfloat16>, nblocks(total, 256), 256, 0, st, x_nchw, d, pad_mode == UEGAN_PAD_REFLECT, s0,
                                                                           s1, s2, b0, b1, b2, total);
   else
-    pack_input_kernel<__half><<<nblocks(total, 256), 256, 0, st>>>(x_nchw, d, pad_mode == UEGAN_PAD_REFLECT, s0,
+    launch_pdl(pack_input_kernel<__half>, nblocks(total, 256), 256, 0, st, x_nchw, d, pad_mode == UEGAN_PAD_REFLECT, s0,
                                                                           s1, s2, b0, b1, b2, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
@@ -491,11 +500,11 @@ int uegan_halo_fill(const uegan_tensor* t, int32_t pad_mode, void* stream) {
   const long long total = (long long)g.n * (2LL * g.halo * g.wp + 2LL * g.halo * g.h) * (g.c / vn);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (t->dtype == UEGAN_F32)
-    halo_fill_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(g, pad_mode == UEGAN_PAD_REFLECT, total);
+    launch_pdl(halo_fill_kernel<float>, nblocks(total, 256), 256, 0, st, g, pad_mode == UEGAN_PAD_REFLECT, total);
   else if (t->dtype == UEGAN_BF16)
-    halo_fill_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(g, pad_mode == UEGAN_PAD_REFLECT, total);
+    launch_pdl(halo_fill_kernel<__nv_bfloat16>, nblocks(total, 256), 256, 0, st, g, pad_mode == UEGAN_PAD_REFLECT, total);
   else
-    halo_fill_kernel<__half><<<nblocks(total, 256), 256, 0, st>>>(g, pad_mode == UEGAN_PAD_REFLECT, total);
+    launch_pdl(halo_fill_kernel<__half>, nblocks(total, 256), 256, 0, st, g, pad_mode == UEGAN_PAD_REFLECT, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -520,7 +529,7 @@ static int instance_norm_impl(const uegan_tensor* src, const uegan_tensor* dst, 
     else run_in_stats<__half>(s, stats_ws, st);
   }
   float* mr = reinterpret_cast<float*>(stats_ws + 2 * nc);  // finalised (mean, rstd) live after the raw sums
-  in_finalize_kernel<<<nblocks(nc, 128), 128, 0, st>>>(stats_ws, mr, nc, 1.0 / (double)npix, eps, src->scale);
+  launch_pdl(in_finalize_kernel, nblocks(nc, 128), 128, 0, st, stats_ws, mr, nc, 1.0 / (double)npix, eps, src->scale);
   const int vn = 16 / dtype_size(src->dtype);
   const int cv = s.c / vn;
   int lg = 0;
@@ -529,11 +538,11 @@ static int instance_norm_impl(const uegan_tensor* src, const uegan_tensor* dst, 
   UEGAN_CHECK(s.h <= 65535 && s.n <= 65535, "instance_norm: tensor too large for the launch grid");
   const dim3 grid(nblocks((long long)s.w * cv, 256), (unsigned)s.h, (unsigned)s.n);
   if (src->dtype == UEGAN_F32)
-    in_apply_kernel<float><<<grid, 256, 0, st>>>(s, d, dst_c_off, mr, lg);
+    launch_pdl(in_apply_kernel<float>, grid, 256, 0, st, s, d, dst_c_off, mr, lg);
   else if (src->dtype == UEGAN_BF16)
-    in_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(s, d, dst_c_off, mr, lg);
+    launch_pdl(in_apply_kernel<__nv_bfloat16>, grid, 256, 0, st, s, d, dst_c_off, mr, lg);
   else
-    in_apply_kernel<__half><<<grid, 256, 0, st>>>(s, d, dst_c_off, mr, lg);
+    launch_pdl(in_apply_kernel<__half>, grid, 256, 0, st, s, d, dst_c_off, mr, lg);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -555,7 +564,7 @@ int uegan_instance_norm_stats(const uegan_tensor* src, float eps, double* stats_
     else run_in_stats<__half>(s, stats_ws, st);
   }
   float* mr = reinterpret_cast<float*>(stats_ws + 2 * nc);
-  in_finalize_kernel<<<nblocks(nc, 128), 128, 0, st>>>(stats_ws, mr, nc, 1.0 / (double)npix, eps, src->scale);
+  launch_pdl(in_finalize_kernel, nblocks(nc, 128), 128, 0, st, stats_ws, mr, nc, 1.0 / (double)npix, eps, src->scale);
   *mean_rstd_out = mr;
   UEGAN_CUDA(cudaGetLastError());
   return 0;
@@ -589,11 +598,11 @@ int uegan_upsample2x(const uegan_tensor* src, const uegan_tensor* dst, int32_t d
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(nblocks((long long)d.w * cv, 256), (unsigned)d.h, (unsigned)d.n);
   if (src->dtype == UEGAN_F32)
-    upsample2x_kernel<float><<<grid, 256, 0, st>>>(s, d, dst_c_off, sy, sx, lg);
+    launch_pdl(upsample2x_kernel<float>, grid, 256, 0, st, s, d, dst_c_off, sy, sx, lg);
   else if (src->dtype == UEGAN_BF16)
-    upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(s, d, dst_c_off, sy, sx, lg);
+    launch_pdl(upsample2x_kernel<__nv_bfloat16>, grid, 256, 0, st, s, d, dst_c_off, sy, sx, lg);
   else
-    upsample2x_kernel<__half><<<grid, 256, 0, st>>>(s, d, dst_c_off, sy, sx, lg);
+    launch_pdl(upsample2x_kernel<__half>, grid, 256, 0, st, s, d, dst_c_off, sy, sx, lg);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -616,9 +625,9 @@ int uegan_cat_build(const uegan_tensor* u, const uegan_tensor* z, const float* m
   UEGAN_CHECK(gd.h <= 65535 && gd.n <= 65535, "cat_build: tensor too large for the launch grid");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(nblocks((long long)gd.w * cv, 256), (unsigned)gd.h, (unsigned)gd.n);
-  if (dst->dtype == UEGAN_F32) cat_build_kernel<float><<<grid, 256, 0, st>>>(gu, gz, gd, mean_rstd, sy, sx, lg);
-  else if (dst->dtype == UEGAN_BF16) cat_build_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(gu, gz, gd, mean_rstd, sy, sx, lg);
-  else cat_build_kernel<__half><<<grid, 256, 0, st>>>(gu, gz, gd, mean_rstd, sy, sx, lg);
+  if (dst->dtype == UEGAN_F32) launch_pdl(cat_build_kernel<float>, grid, 256, 0, st, gu, gz, gd, mean_rstd, sy, sx, lg);
+  else if (dst->dtype == UEGAN_BF16) launch_pdl(cat_build_kernel<__nv_bfloat16>, grid, 256, 0, st, gu, gz, gd, mean_rstd, sy, sx, lg);
+  else launch_pdl(cat_build_kernel<__half>, grid, 256, 0, st, gu, gz, gd, mean_rstd, sy, sx, lg);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -634,11 +643,11 @@ int uegan_maxpool2x2(const uegan_tensor* src, const uegan_tensor* dst, void* str
   const long long total = (long long)d.n * d.h * d.w * (s.c / vn);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (src->dtype == UEGAN_F32)
-    maxpool2x2_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(s, d, total);
+    launch_pdl(maxpool2x2_kernel<float>, nblocks(total, 256), 256, 0, st, s, d, total);
   else if (src->dtype == UEGAN_BF16)
-    maxpool2x2_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(s, d, total);
+    launch_pdl(maxpool2x2_kernel<__nv_bfloat16>, nblocks(total, 256), 256, 0, st, s, d, total);
   else
-    maxpool2x2_kernel<__half><<<nblocks(total, 256), 256, 0, st>>>(s, d, total);
+    launch_pdl(maxpool2x2_kernel<__half>, nblocks(total, 256), 256, 0, st, s, d, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -650,11 +659,11 @@ int uegan_unpack_nchw(const uegan_tensor* src, int32_t c_off, int32_t c_count, f
   const long long total = (long long)s.n * c_count * s.h * s.w;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (src->dtype == UEGAN_F32)
-    unpack_nchw_kernel<float><<<nblocks(total, 256), 256, 0, st>>>(s, c_off, c_count, dst_nchw, total);
+    launch_pdl(unpack_nchw_kernel<float>, nblocks(total, 256), 256, 0, st, s, c_off, c_count, dst_nchw, total);
   else if (src->dtype == UEGAN_BF16)
-    unpack_nchw_kernel<__nv_bfloat16><<<nblocks(total, 256), 256, 0, st>>>(s, c_off, c_count, dst_nchw, total);
+    launch_pdl(unpack_nchw_kernel<__nv_bfloat16>, nblocks(total, 256), 256, 0, st, s, c_off, c_count, dst_nchw, total);
   else
-    unpack_nchw_kernel<__half><<<nblocks(total, 256), 256, 0, st>>>(s, c_off, c_count, dst_nchw, total);
+    launch_pdl(unpack_nchw_kernel<__half>, nblocks(total, 256), 256, 0, st, s, c_off, c_count, dst_nchw, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

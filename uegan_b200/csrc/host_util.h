@@ -36,6 +36,30 @@ int encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, uint32_t rank, void* 
 
 int num_sms();
 
+// Programmatic dependent launch (opt-in, UEGAN_PDL=1; measured slower for the two-stream training graph, see pdl_enabled):
+// every kernel of this library starts with pdl_wait() (common.cuh:
+// griddepcontrol.wait -- returns once the preceding kernel of the stream has completed and its writes are visible) before
+// its first global-memory access and then releases its own successor (griddepcontrol.launch_dependents), so the next
+// kernel's CTAs are placed and run their on-chip prologue (smem carve-up, mbarrier init, TMEM allocation) while this one
+// drains, instead of after a full kernel boundary.  Correct by induction: a kernel's wait returns only after its
+// predecessor completed, whose own wait returned only after ITS predecessor completed.  Works inside stream capture
+// (programmatic graph edges).  Kernels launched without the attribute (ATen, the peer-memory optimiser) serialise fully.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // One host-mapped word the kernels' bounded waits write their code to before trapping.
 unsigned int* error_sink_host();
 unsigned int* error_sink_device();

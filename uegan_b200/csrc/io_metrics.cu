@@ -28,6 +28,7 @@ __device__ __forceinline__ float io_round_tf32(float v) {
 // one thread per padded pixel: 3 bytes in, one 16-byte channel vector out (+ three fp32 plane values for interior pixels)
 __global__ void pack_input_u8_kernel(const uint8_t* __restrict__ src, IoGeom d, int reflect, float m0, float m1, float m2,
                                      float s0, float s1, float s2, float* __restrict__ planes, long long total) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int xp = (int)(i % d.wp);
@@ -72,6 +73,7 @@ __global__ void pack_input_u8_kernel(const uint8_t* __restrict__ src, IoGeom d, 
 // fp32 NCHW in [-1, 1] -> uint8 HWC:  denorm = clamp((x + 1) / 2, 0, 1);  save_image: clamp(v * 255 + 0.5, 0, 255) -> uint8
 __global__ void unpack_output_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int h, int w, int cch,
                                         long long total) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // output byte index (n, y, x, c)
   if (i >= total) return;
   const int c = (int)(i % cch);
@@ -91,6 +93,7 @@ __global__ void unpack_output_u8_kernel(const float* __restrict__ src, uint8_t* 
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void sse_u8_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int h, int w, int cch, int crop,
                               unsigned long long* __restrict__ sse) {
+  pdl_sync();
   const int n = blockIdx.y;
   const int rw = (w - 2 * crop) * cch;  // bytes per cropped row
   const int rows = h - 2 * crop;
@@ -116,6 +119,7 @@ __global__ void sse_u8_kernel(const uint8_t* __restrict__ a, const uint8_t* __re
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ssim_u8_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int h, int w,
                                                      int cch, int crop, double* __restrict__ sums) {
+  pdl_sync();
   __shared__ double sh[8];
   const int n = blockIdx.y;
   const int H = h - 2 * crop, W = w - 2 * crop;  // the metric runs on the cropped image (CalcSSIM.py:47-52)
@@ -176,8 +180,7 @@ int uegan_pack_input_u8(const uint8_t* img_nhwc_u8, int32_t n, int32_t h, int32_
   }
   const long long total = (long long)n * d.hp * d.wp;
   if (total == 0) return 0;
-  pack_input_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      img_nhwc_u8, d, pad_mode == UEGAN_PAD_REFLECT, mean_host[0], mean_host[1], mean_host[2], std_host[0], std_host[1],
+  launch_pdl(pack_input_u8_kernel, (unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), img_nhwc_u8, d, pad_mode == UEGAN_PAD_REFLECT, mean_host[0], mean_host[1], mean_host[2], std_host[0], std_host[1],
       std_host[2], x_nchw_out, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
@@ -188,8 +191,7 @@ int uegan_unpack_output_u8(const float* x_nchw, uint8_t* out_nhwc_u8, int32_t n,
   UEGAN_CHECK(x_nchw && out_nhwc_u8 && c >= 1, "unpack_output_u8: null pointer");
   const long long total = (long long)n * h * w * c;
   if (total == 0) return 0;
-  unpack_output_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x_nchw, out_nhwc_u8, h, w, c, total);
+  launch_pdl(unpack_output_u8_kernel, (unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), x_nchw, out_nhwc_u8, h, w, c, total);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -204,7 +206,7 @@ int uegan_sse_u8(const uint8_t* a_nhwc, const uint8_t* b_nhwc, int32_t n, int32_
   long long blocks = (total + 256 * 8 - 1) / (256 * 8);
   if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
   if (blocks < 1) blocks = 1;
-  sse_u8_kernel<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, st>>>(a_nhwc, b_nhwc, h, w, c, crop,
+  launch_pdl(sse_u8_kernel, dim3((unsigned)blocks, (unsigned)n), 256, 0, st, a_nhwc, b_nhwc, h, w, c, crop,
                                                                     reinterpret_cast<unsigned long long*>(sse_out));
   UEGAN_CUDA(cudaGetLastError());
   return 0;
@@ -220,7 +222,7 @@ int uegan_ssim_u8(const uint8_t* a_nhwc, const uint8_t* b_nhwc, int32_t n, int32
   const long long total = (long long)(h - 2 * crop - 6) * (w - 2 * crop - 6) * c;
   long long blocks = (total + 255) / 256;
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-  ssim_u8_kernel<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, st>>>(a_nhwc, b_nhwc, h, w, c, crop, ssim_sum_out);
+  launch_pdl(ssim_u8_kernel, dim3((unsigned)blocks, (unsigned)n), 256, 0, st, a_nhwc, b_nhwc, h, w, c, crop, ssim_sum_out);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -27,6 +27,7 @@ __device__ __forceinline__ void block_atomic_add(double v, double* dst) {
 
 // ws[2*i] = sum real_i, ws[2*i+1] = sum fake_i
 __global__ void gan_sums_kernel(GanArgs a, double* __restrict__ ws) {
+  pdl_sync();
   const int i = blockIdx.y;
   double sr = 0.0, sf = 0.0;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.count[i]; j += (long long)gridDim.x * blockDim.x) {
@@ -53,6 +54,7 @@ __device__ __forceinline__ void gan_terms(int mode, float sgn, float x, float& t
   }
 }
 __global__ void gan_terms_kernel(GanArgs a, const double* __restrict__ ws, double* __restrict__ ws2) {
+  pdl_sync();
   const int i = blockIdx.y;
   const double inv = 1.0 / ((double)a.count[i] * a.count_mul);
   const float mr = (float)(ws[2 * i] * inv), mf = (float)(ws[2 * i + 1] * inv);
@@ -72,6 +74,7 @@ __global__ void gan_terms_kernel(GanArgs a, const double* __restrict__ ws, doubl
   block_atomic_add(g1, ws2 + 4 * i + 3);
 }
 __global__ void gan_finalize_kernel(GanArgs a, const double* __restrict__ ws2, float* __restrict__ loss) {
+  pdl_sync();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double l = 0.0;
     for (int i = 0; i < a.nscales; ++i) l += 0.5 * (ws2[4 * i] + ws2[4 * i + 1]) / ((double)a.count[i] * a.count_mul);
@@ -82,6 +85,7 @@ __global__ void gan_finalize_kernel(GanArgs a, const double* __restrict__ ws2, f
 // (the second part is the path through the batch-global mean, losses.py:351-353)
 __global__ void gan_backward_kernel(GanArgs a, const double* __restrict__ ws, const double* __restrict__ ws2,
                                     const float* __restrict__ gscale_ptr, float gscale_host) {
+  pdl_sync();
   const int i = blockIdx.y;
   const double inv = 1.0 / ((double)a.count[i] * a.count_mul);
   const float mr = (float)(ws[2 * i] * inv), mf = (float)(ws[2 * i + 1] * inv);
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(256) in_joint_finalize_kernel(const double* __
                                                                 const float* __restrict__ src_scale, float* __restrict__ mrx,
                                                                 float* __restrict__ mry, double* __restrict__ sums,
                                                                 double* __restrict__ accum) {
+  pdl_sync();
   __shared__ double sh[256];
   const int i = blockIdx.x * 256 + threadIdx.x;
   double contrib = 0.0;
@@ -220,6 +225,7 @@ __global__ void __launch_bounds__(256) in_joint_finalize_kernel(const double* __
 }
 // loss += weight * accum / numel ; accum reset
 __global__ void scalar_axpy_kernel(double* accum, double scale, float* loss) {
+  pdl_sync();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     loss[0] += (float)(accum[0] * scale);
     accum[0] = 0.0;
@@ -245,6 +251,7 @@ __device__ __forceinline__ float rec_dterm(float d, int type) {
 __global__ void msrec_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int planes, int h, int w,
                              int type, int scales, double* __restrict__ accum, float* __restrict__ grad, float w0_,
                              float w1_, float w2_, const float* __restrict__ gscale) {
+  pdl_sync();
   const float gs = gscale ? gscale[0] : 1.f;
   const float w0 = w0_ * gs, w1 = w1_ * gs, w2 = w2_ * gs;
   const int bw = w >> 2, bh = h >> 2;
@@ -302,6 +309,7 @@ __global__ void msrec_kernel(const float* __restrict__ pred, const float* __rest
   block_atomic_add(s2, accum + 2);
 }
 __global__ void msrec_finalize_kernel(double* accum, double c0, double c1, double c2, float* loss) {
+  pdl_sync();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     loss[0] = (float)(accum[0] * c0 + accum[1] * c1 + accum[2] * c2);
   }
@@ -334,9 +342,9 @@ int uegan_gan_loss_fwd(int32_t mode, int32_t for_discriminator, int32_t nscales,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   UEGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 6 * kMaxScales, st));
   dim3 grid(64, nscales);
-  gan_sums_kernel<<<grid, 256, 0, st>>>(a, ws);
-  gan_terms_kernel<<<grid, 256, 0, st>>>(a, ws, ws + 2 * kMaxScales);
-  gan_finalize_kernel<<<1, 32, 0, st>>>(a, ws + 2 * kMaxScales, loss_out);
+  launch_pdl(gan_sums_kernel, grid, 256, 0, st, a, ws);
+  launch_pdl(gan_terms_kernel, grid, 256, 0, st, a, ws, ws + 2 * kMaxScales);
+  launch_pdl(gan_finalize_kernel, 1, 32, 0, st, a, ws + 2 * kMaxScales, loss_out);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -352,12 +360,12 @@ int uegan_gan_loss_phase(int32_t phase, int32_t mode, int32_t for_discriminator,
   dim3 grid(64, nscales);
   if (phase == 0) {
     UEGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 6 * kMaxScales, st));
-    gan_sums_kernel<<<grid, 256, 0, st>>>(a, ws);
+    launch_pdl(gan_sums_kernel, grid, 256, 0, st, a, ws);
   } else if (phase == 1) {
-    gan_terms_kernel<<<grid, 256, 0, st>>>(a, ws, ws + 2 * kMaxScales);
+    launch_pdl(gan_terms_kernel, grid, 256, 0, st, a, ws, ws + 2 * kMaxScales);
   } else {
     UEGAN_CHECK(loss_out, "gan loss phase 2: null loss");
-    gan_finalize_kernel<<<1, 32, 0, st>>>(a, ws + 2 * kMaxScales, loss_out);
+    launch_pdl(gan_finalize_kernel, 1, 32, 0, st, a, ws + 2 * kMaxScales, loss_out);
   }
   UEGAN_CUDA(cudaGetLastError());
   return 0;
@@ -375,7 +383,7 @@ int uegan_gan_loss_bwd(int32_t mode, int32_t for_discriminator, int32_t nscales,
     a.d_fake[i] = d_fake ? d_fake[i] : nullptr;
   }
   dim3 grid(64, nscales);
-  gan_backward_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, ws, ws + 2 * kMaxScales, gscale_dev,
+  launch_pdl(gan_backward_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), a, ws, ws + 2 * kMaxScales, gscale_dev,
                                                                           gscale_host);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
@@ -402,7 +410,7 @@ int uegan_in_mse_fwd(const uegan_tensor* x, const uegan_tensor* y, const float* 
     InMseOp<__half> op{gx, gy, mean_rstd_x, mean_rstd_y, accum};
     launch_strip_reduce<__half, 1>(op, gx.c, gx.n, gx.h, gx.w, st);
   }
-  scalar_axpy_kernel<<<1, 32, 0, st>>>(accum, (double)weight / (double)total, loss_inout);
+  launch_pdl(scalar_axpy_kernel, 1, 32, 0, st, accum, (double)weight / (double)total, loss_inout);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -433,8 +441,8 @@ int uegan_in_mse_joint(const uegan_tensor* x, const uegan_tensor* y, float eps, 
     JointMomentsOp<__half> op{gx, gy, mom};
     launch_strip_reduce<__half, 5>(op, gx.c, gx.n, gx.h, gx.w, st);
   }
-  in_joint_finalize_kernel<<<(nc + 255) / 256, 256, 0, st>>>(mom, nc, npix, eps, x->scale, mrx, mry, sums, accum);
-  scalar_axpy_kernel<<<1, 32, 0, st>>>(accum, (double)weight / ((double)nc * npix), loss_inout);
+  launch_pdl(in_joint_finalize_kernel, (nc + 255) / 256, 256, 0, st, mom, nc, npix, eps, x->scale, mrx, mry, sums, accum);
+  launch_pdl(scalar_axpy_kernel, 1, 32, 0, st, accum, (double)weight / ((double)nc * npix), loss_inout);
   UEGAN_CUDA(cudaGetLastError());
   *mrx_out = mrx; *mry_out = mry; *sums_out = sums;
   return 0;
@@ -453,9 +461,9 @@ int uegan_msrec_loss(const float* pred_nchw, const float* gt_nchw, int32_t n, in
   const long long total = (long long)n * c * (h / 4) * (w / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  msrec_kernel<<<blocks, 256, 0, st>>>(pred_nchw, gt_nchw, n * c, h, w, type, scales, accum, grad_nchw,
+  launch_pdl(msrec_kernel, blocks, 256, 0, st, pred_nchw, gt_nchw, n * c, h, w, type, scales, accum, grad_nchw,
                                       (float)(c0 * grad_scale), (float)(c1 * grad_scale), (float)(c2 * grad_scale), gscale_dev);
-  msrec_finalize_kernel<<<1, 32, 0, st>>>(accum, c0, c1, c2, loss_out);
+  launch_pdl(msrec_finalize_kernel, 1, 32, 0, st, accum, c0, c1, c2, loss_out);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

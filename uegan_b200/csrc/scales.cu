@@ -9,6 +9,7 @@ namespace uegan {
 
 __global__ void __launch_bounds__(1024) scale_update_kernel(const uegan_scale_entry* __restrict__ tab, float target,
                                                            int max_samples) {
+  pdl_sync();
   __shared__ float sh[32];
   __shared__ int sh_bad[32];
   const uegan_scale_entry e = tab[blockIdx.x];
@@ -92,7 +93,7 @@ extern "C" int uegan_scale_update(const uegan_scale_entry* entries_dev, int32_t 
   UEGAN_CHECK(entries_dev || count == 0, "scale_update: null table");
   UEGAN_CHECK(target > 0.f && max_samples > 0, "scale_update: bad target / sample count");
   if (count <= 0) return 0;
-  scale_update_kernel<<<(unsigned)count, 1024, 0, static_cast<cudaStream_t>(stream)>>>(entries_dev, target, max_samples);
+  launch_pdl(scale_update_kernel, (unsigned)count, 1024, 0, static_cast<cudaStream_t>(stream), entries_dev, target, max_samples);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -12,6 +12,7 @@ namespace uegan {
 // t[col] = sum_row W[row][col] * u[row];  threads along columns (coalesced), each block covers a row slab.
 __global__ void sn_wt_u_kernel(const float* __restrict__ w, const float* __restrict__ u, float* __restrict__ t,
                                int rows, int cols, int rows_per_block) {
+  pdl_sync();
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= cols) return;
   const int r0 = blockIdx.y * rows_per_block;
@@ -24,6 +25,7 @@ __global__ void sn_wt_u_kernel(const float* __restrict__ w, const float* __restr
 
 // nrm2[0] = sum_i t[i]^2
 __global__ void sn_sumsq_kernel(const float* __restrict__ t, int n, double* __restrict__ out) {
+  pdl_sync();
   double acc = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += (double)t[i] * t[i];
   acc = warp_sum(acc);
@@ -33,6 +35,7 @@ __global__ void sn_sumsq_kernel(const float* __restrict__ t, int n, double* __re
 // optional v <- t / max(||t||, eps) (train), then wv[row] = W[row] . v ; one warp per row
 __global__ void sn_w_v_kernel(const float* __restrict__ w, const float* __restrict__ t, const double* __restrict__ t_sumsq,
                               float* __restrict__ v, float* __restrict__ wv, int rows, int cols, int train, float eps) {
+  pdl_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -52,6 +55,7 @@ __global__ void sn_w_v_kernel(const float* __restrict__ w, const float* __restri
 // single block: u <- normalize(wv) (train); sigma = u . wv; out[0] = sigma, out[1] = 1/sigma
 __global__ void sn_finalize_kernel(const float* __restrict__ wv, float* __restrict__ u, float* __restrict__ out, int rows,
                                    int train, float eps) {
+  pdl_sync();
   __shared__ double sh[32];
   __shared__ float s_inv;
   double acc = 0.0;
@@ -86,6 +90,7 @@ __global__ void sn_finalize_kernel(const float* __restrict__ wv, float* __restri
 // backward through sigma (u, v constants): dW = A - (<A, W> / sigma) * u v^T with A = (dL/dW_sn) / sigma already
 // produced by the wgrad kernel (alpha = 1/sigma).
 __global__ void sn_dot_kernel(const float* __restrict__ a, const float* __restrict__ w, long long n, double* __restrict__ out) {
+  pdl_sync();
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     acc += (double)a[i] * w[i];
@@ -95,6 +100,7 @@ __global__ void sn_dot_kernel(const float* __restrict__ a, const float* __restri
 __global__ void sn_rank1_kernel(float* __restrict__ a, const float* __restrict__ u, const float* __restrict__ v,
                                 const double* __restrict__ dot, const float* __restrict__ sigma, int rows, int cols,
                                 float* __restrict__ accum) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)rows * cols) return;
   const float coef = (float)(dot[0]) * sigma[1];  // <A, W> / sigma
@@ -121,6 +127,7 @@ struct SnBatch {
   float eps;
 };
 __global__ void sn_wt_u_batch_kernel(const SnBatch b, int rows_per_block) {
+  pdl_sync();
   const int l = blockIdx.z, rows = b.rows[l], cols = b.cols[l];
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_block;
@@ -133,6 +140,7 @@ __global__ void sn_wt_u_batch_kernel(const SnBatch b, int rows_per_block) {
   atomicAdd(b.t[l] + col, acc);
 }
 __global__ void sn_sumsq_batch_kernel(const SnBatch b) {
+  pdl_sync();
   const int l = blockIdx.y, n = b.cols[l];
   const float* __restrict__ t = b.t[l];
   double acc = 0.0;
@@ -142,6 +150,7 @@ __global__ void sn_sumsq_batch_kernel(const SnBatch b) {
 }
 // one BLOCK per row (a warp per row walked d5's 6400 columns in 200 dependent trips: 100 us, latency-bound)
 __global__ void __launch_bounds__(256) sn_w_v_batch_kernel(const SnBatch b) {
+  pdl_sync();
   __shared__ float sh[8];
   const int l = blockIdx.y, rows = b.rows[l], cols = b.cols[l];
   const int row = blockIdx.x;
@@ -170,6 +179,7 @@ __global__ void __launch_bounds__(256) sn_w_v_batch_kernel(const SnBatch b) {
   }
 }
 __global__ void sn_finalize_batch_kernel(const SnBatch b) {
+  pdl_sync();
   __shared__ double sh[32];
   __shared__ float s_inv;
   const int l = blockIdx.x, rows = b.rows[l];
@@ -239,13 +249,13 @@ extern "C" int uegan_spectral_sigma_batch(int32_t count, const float* const* w, 
   if (train) {
     const int rpb = 32;
     dim3 grid((max_cols + 127) / 128, (max_rows + rpb - 1) / rpb, count);
-    sn_wt_u_batch_kernel<<<grid, 128, 0, st>>>(b, rpb);
+    launch_pdl(sn_wt_u_batch_kernel, grid, 128, 0, st, b, rpb);
     int sb = (max_cols + 1023) / 1024;
     if (sb > 32) sb = 32;
-    sn_sumsq_batch_kernel<<<dim3(sb, count), 256, 0, st>>>(b);
+    launch_pdl(sn_sumsq_batch_kernel, dim3(sb, count), 256, 0, st, b);
   }
-  sn_w_v_batch_kernel<<<dim3(max_rows, count), 256, 0, st>>>(b);
-  sn_finalize_batch_kernel<<<count, 256, 0, st>>>(b);
+  launch_pdl(sn_w_v_batch_kernel, dim3(max_rows, count), 256, 0, st, b);
+  launch_pdl(sn_finalize_batch_kernel, count, 256, 0, st, b);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -264,11 +274,11 @@ extern "C" int uegan_spectral_sigma(const float* w, float* u, float* v, int32_t 
     UEGAN_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double), st));
     const int rpb = 32;
     dim3 grid((cols + 127) / 128, (rows + rpb - 1) / rpb);
-    sn_wt_u_kernel<<<grid, 128, 0, st>>>(w, u, t, rows, cols, rpb);
-    sn_sumsq_kernel<<<(cols + 1023) / 1024 < 32 ? (cols + 1023) / 1024 : 32, 256, 0, st>>>(t, cols, sumsq);
+    launch_pdl(sn_wt_u_kernel, grid, 128, 0, st, w, u, t, rows, cols, rpb);
+    launch_pdl(sn_sumsq_kernel, (cols + 1023) / 1024 < 32 ? (cols + 1023) / 1024 : 32, 256, 0, st, t, cols, sumsq);
   }
-  sn_w_v_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(w, t, sumsq, v, wv, rows, cols, train, eps);
-  sn_finalize_kernel<<<1, 256, 0, st>>>(wv, u, sigma_out, rows, train, eps);
+  launch_pdl(sn_w_v_kernel, (rows * 32 + 255) / 256, 256, 0, st, w, t, sumsq, v, wv, rows, cols, train, eps);
+  launch_pdl(sn_finalize_kernel, 1, 256, 0, st, wv, u, sigma_out, rows, train, eps);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -281,8 +291,8 @@ extern "C" int uegan_spectral_bwd(float* grad_inout, const float* w, const float
   UEGAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(double), st));
   int blocks = (int)((n + 1023) / 1024);
   if (blocks > 256) blocks = 256;
-  sn_dot_kernel<<<blocks, 256, 0, st>>>(grad_inout, w, n, ws);
-  sn_rank1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grad_inout, u, v, ws, sigma, rows, cols, accum_out);
+  launch_pdl(sn_dot_kernel, blocks, 256, 0, st, grad_inout, w, n, ws);
+  launch_pdl(sn_rank1_kernel, (unsigned)((n + 255) / 256), 256, 0, st, grad_inout, u, v, ws, sigma, rows, cols, accum_out);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
