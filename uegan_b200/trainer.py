@@ -178,7 +178,21 @@ class Trainer(object):
         self.G.train(); self.D.train()
         self.real_raw, self.real_exp = real_raw, real_exp
         local = 1.0 / self.world  # mean-type losses are per-rank means; gradients are SUMMED across ranks
-        self.fake_exp = self.G(real_raw)
+        # G(real_raw) (trainer.py:80) and G(real_exp) (the identity pass, trainer.py:106) see the same weights -- G is only
+        # updated at the end of the step -- and every layer of G is per-sample (InstanceNorm, GAM pooling): one forward /
+        # backward over the 2B images gives the same two results with half of G's kernel launches (UEGAN_BATCH_G=0: two
+        # passes, in the reference's order)
+        batch_g = os.environ.get("UEGAN_BATCH_G", "1") != "0" and real_raw.shape == real_exp.shape
+        if batch_g:
+            nb = real_raw.shape[0]
+            if getattr(self, "_gxy", None) is not None and real_raw is self._gx and real_exp is self._gy:
+                both_in = self._gxy  # the static input buffer of the captured step holds the two batches back to back
+            else:
+                both_in = torch.cat([real_raw, real_exp])
+            both = self.G(both_in)
+            self.fake_exp, real_exp_idt = both[:nb], both[nb:]
+        else:
+            self.fake_exp = self.G(real_raw)
         self.fake_exp_store = self.fake_exp_pool.query(self.fake_exp)
         # ---- update D
         self.d_grads.zero_grad()
@@ -208,7 +222,7 @@ class Trainer(object):
                 p.requires_grad_(True)
         g_adv_loss = a.lambda_adv * gan(real_exp_preds, fake_exp_preds, None, None, for_discriminator=False)
         g_percep_loss = a.lambda_percep * self.criterionPercep((self.fake_exp + 1.) / 2., (real_raw + 1.) / 2.)
-        self.real_exp_idt = self.G(real_exp)
+        self.real_exp_idt = real_exp_idt if batch_g else self.G(real_exp)
         g_idt_loss = a.lambda_idt * self.criterionIdt(self.real_exp_idt, real_exp)
         g_loss = g_adv_loss + local * (g_percep_loss + g_idt_loss)
         g_loss.backward()
@@ -234,7 +248,13 @@ class Trainer(object):
         assert self.args.pool_size == 0
         if self.group is not None and self.comm is None:
             raise RuntimeError("CUDA-graph capture at world size > 1 needs the peer-memory reductions (NCCL fallback active)")
-        self._gx, self._gy = real_raw.clone(), real_exp.clone()
+        if real_raw.shape == real_exp.shape:
+            nb = real_raw.shape[0]
+            self._gxy = torch.cat([real_raw, real_exp])  # one buffer: the batched G pass reads it without a copy
+            self._gx, self._gy = self._gxy[:nb], self._gxy[nb:]
+        else:
+            self._gxy = None
+            self._gx, self._gy = real_raw.clone(), real_exp.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
