@@ -276,3 +276,37 @@ def test_cuda_graph_replay_matches_eager():
         if moved is not None:
             assert moved > 0.5 * 5 * lr, moved  # five Adam steps of ~lr each really happened
     assert float((Tg.D.d3[0][1].weight_orig.detach() - w0).abs().mean()) > 0.5 * 5 * lr
+
+
+def test_batched_generator_pass_matches_two_passes(monkeypatch):
+    """trainer.py:80,106: G(real_raw) and G(real_exp) as ONE pass over 2B images (the default) give the losses and the
+    weight update of the two separate passes in the reference's order (UEGAN_BATCH_G=0): every layer of G is per-sample,
+    so the only differences are the shared per-tensor fp16 scales and the summation order of the weight gradients."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from uegan_b200.trainer import Trainer
+    from bench import train_args
+    raw = O.make_images((2, 3, 128, 128), 50).cuda()
+    exp = O.make_images((2, 3, 128, 128), 51).cuda()
+
+    def run(flag):
+        monkeypatch.setenv("UEGAN_BATCH_G", flag)
+        a = train_args(2)
+        a.cuda_graph, a.g_lr, a.d_lr = False, 1e-5, 1e-5
+        T = Trainer(None, a, vgg_state_dict=O.make_vgg_params())
+        T.G.load_state_dict(O.make_generator_params(32, 0, "o1"))
+        T.D.load_state_dict(O.make_discriminator_params(32, 1, "o1"))
+        g0 = {n: p.detach().clone() for n, p in T.G.named_parameters()}
+        vals = [T.train_step(raw, exp) for _ in range(2)]
+        return vals, g0, {n: p.detach().clone() for n, p in T.G.named_parameters()}
+
+    (v2, g0, w2), (v1, _, w1) = run("0"), run("1")
+    for k in v2[0]:
+        assert abs(v1[0][k] - v2[0][k]) <= 2e-3 * abs(v2[0][k]) + 1e-6, (k, v1[0][k], v2[0][k])
+        assert abs(v1[1][k] - v2[1][k]) <= 1e-2 * abs(v2[1][k]) + 1e-6, (k, v1[1][k], v2[1][k])
+    # two Adam steps of ~lr per weight: the two schedules move every tensor the same way (sign flips of near-zero
+    # gradients aside)
+    for name in ("enc1.main.1.weight", "dec2.main.1.weight", "dec5.1.main.1.weight"):
+        moved = float((w2[name] - g0[name]).abs().mean())
+        assert moved > 0.5e-5, (name, moved)
+        assert float((w1[name] - w2[name]).abs().mean()) < 0.25 * moved, (name, float((w1[name] - w2[name]).abs().mean()), moved)

@@ -164,9 +164,10 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
                act: int = L.ACT_NONE, mul: Optional[NHWC] = None, out_nchw: Optional[torch.Tensor] = None,
                residual_nchw: Optional[torch.Tensor] = None, in_stats: Optional[torch.Tensor] = None,
                aux_nchw: Optional[torch.Tensor] = None, w_scale: Optional[torch.Tensor] = None,
-               premul: Optional[NHWC] = None, reflect_halo: bool = False):
+               premul: Optional[NHWC] = None, reflect_halo: bool = False, halo_launch: bool = False):
     """premul: with `mul`, the output before the multiplication is stored there as well.
-    reflect_halo: also write y's reflection-padding halo (falls back to a halo_fill launch where the epilogue cannot)."""
+    reflect_halo: also write y's reflection-padding halo: mirrored stores in the conv epilogue, or -- where the epilogue
+    cannot, or with halo_launch -- a halo_fill launch after the conv."""
     lib = L.load()
     d = L.ConvDesc()
     d.x = x.ct
@@ -174,7 +175,7 @@ def conv_fprop(x: NHWC, w_packed: torch.Tensor, cout: int, k: int, stride: int, 
     fill_after = False
     if reflect_halo and y is not None and y.halo > 0:
         import os
-        if (y.dtype != L.F32 and y.h > 2 * y.halo + 1 and y.w > 2 * y.halo + 1 and in_stats is None
+        if (not halo_launch and y.dtype != L.F32 and y.h > 2 * y.halo + 1 and y.w > 2 * y.halo + 1 and in_stats is None
                 and os.environ.get("UEGAN_NO_EPILOGUE_HALO") != "1"):
             d.y_reflect_halo = 1
         else:

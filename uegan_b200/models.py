@@ -8,6 +8,8 @@ they are never called.  `forward` runs the native plan; there is no PyTorch/CPU 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -282,11 +284,17 @@ class Generator(nn.Module, _ScaledNet):
                 self._wscale(name, holder)
             self._update_weight_scales()
 
+        # inference: the reflection halo by a halo_fill launch after the conv (same-box A/B r4i: 4.94 vs 5.03 ms per batch
+        # of 32 with the mirrored stores in the epilogue, whose per-tile chain is what bounds these layers; the training
+        # step, where it is time-neutral and saves 35 launches, uses the epilogue: autograd.py)
+        halo_launch = os.environ.get("UEGAN_EPILOGUE_HALO") != "1"
+
         def conv(src, name, holder, cout, k, stride, dst, act_=L.ACT_NONE, off=0, mul=None, bias=True, halo=False):
             # halo: dst's reflection-padding halo is written too (by the epilogue, or by a halo_fill launch after it)
             cv = c(holder)
             K.conv_fprop(src, self._w(name, cv, src.c), cout, k, stride, (k - 1) // 2, dst, off,
-                         cv.bias if bias else None, None, act_, mul, w_scale=self._wscale(name, cv), reflect_halo=halo)
+                         cv.bias if bias else None, None, act_, mul, w_scale=self._wscale(name, cv), reflect_halo=halo,
+                         halo_launch=halo_launch)
 
         if not packed:
             K.pack_input(x, P["x0"], L.PAD_REFLECT)
