@@ -166,44 +166,77 @@ __global__ void grad_combine_kernel(CombineArgs q, int cv_log2) {
 // interior pixels only: race-free.  Touches O(perimeter) data instead of a full read + write pass (grad_combine).
 // grid = (1, h, n); a row inside the top / bottom band processes every column, any other row only its 2*pad edge columns.
 // ------------------------------------------------------------------------------------------
+// grid = (items of one image / 256, images): one thread per (receiving pixel, 16-byte channel vector).  The receiving
+// pixels are the `band` rows 1 .. pa and h-1-pa .. h-2 in full, plus the 2*pa edge columns of every other row (narrow
+// images: every pixel).  (One block per image row with a serial loop over its pixels -- the first version -- spent 46-125 us
+// per launch on 16 K nearly empty blocks and four dependent memory latencies per item, r4z.)
 template <typename T>
-__global__ void fold_inplace_kernel(TGeom t, int cv_log2) {
+__global__ void fold_inplace_kernel(TGeom t, int cv_log2, int all, int items_band, int items) {
   pdl_sync();
   constexpr int VN = Vec<T>::N;
-  const int y = blockIdx.y, n = blockIdx.z, pa = t.halo;
-  const int cv = 1 << cv_log2;
-  int ys[2], ny = 0;
-  if (y >= 1 && y <= pa) ys[ny++] = -y;                                  // interior row coordinate of the reflected source
-  if (y <= t.h - 2 && y >= t.h - 1 - pa) ys[ny++] = 2 * (t.h - 1) - y;
-  const bool band = ny > 0 || t.w <= 2 * pa + 1;  // (narrow images: the two edge column sets would overlap)
-  const int ncols = band ? t.w : 2 * pa;
-  T* base = static_cast<T*>(t.data);
-  for (int i = threadIdx.x; i < ncols * cv; i += blockDim.x) {
-    const int xi = i >> cv_log2, c = (i & (cv - 1)) * VN;
+  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= items) return;
+  const int n = blockIdx.y, pa = t.halo;
+  const int c = (it & ((1 << cv_log2) - 1)) * VN;
+  int y, x;
+  if (all) {
+    const int pix = it >> cv_log2;
+    y = pix / t.w;
+    x = pix - y * t.w;
+  } else if (it < items_band) {
+    const int pix = it >> cv_log2;
+    const int j = pix / t.w;  // band row index: 0 .. 2*pa-1
+    x = pix - j * t.w;
+    y = j < pa ? j + 1 : t.h - 1 - 2 * pa + j;
+  } else {
+    const int pix = (it - items_band) >> cv_log2;
+    const int i = pix / (2 * pa), xi = pix - i * (2 * pa);  // i: 0 .. h-2*pa-1 over the rows outside the bands
+    y = i == 0 ? 0 : (i == t.h - 2 * pa - 1 ? t.h - 1 : pa + i);
     // edge columns that receive reflected copies: 1 .. pa and w-1-pa .. w-2
-    const int x = band ? xi : (xi < pa ? xi + 1 : t.w - 1 - 2 * pa + xi);
-    int xs[2], nx = 0;
-    if (x >= 1 && x <= pa) xs[nx++] = -x;
-    if (x <= t.w - 2 && x >= t.w - 1 - pa) xs[nx++] = 2 * (t.w - 1) - x;
-    if (ny == 0 && nx == 0) continue;
-    float v[VN];
-    T* dst = base + toff(t, n, y, x, c);
-    Vec<T>::load(dst, v);
-    // same summation order as grad_combine: (y, x) first, then rows ascending, columns ascending
-    for (int iy = -1; iy < ny; ++iy)
-      for (int ix = -1; ix < nx; ++ix) {
-        if (iy < 0 && ix < 0) continue;
-        float s[VN];
-        T* src = base + toff(t, n, iy < 0 ? y : ys[iy], ix < 0 ? x : xs[ix], c);
-        Vec<T>::load(src, s);
-#pragma unroll
-        for (int k = 0; k < VN; ++k) v[k] += s[k];
-        // every halo pixel is the reflected copy of exactly ONE interior pixel, so it is read by exactly one thread: that
-        // thread zeroes it (the tensor leaves as a zero-haloed operand without a separate halo pass)
-        *reinterpret_cast<uint4*>(src) = make_uint4(0u, 0u, 0u, 0u);
-      }
-    Vec<T>::store(dst, v);
+    x = xi < pa ? xi + 1 : t.w - 1 - 2 * pa + xi;
   }
+  // interior coordinates of the reflected sources (they lie in the halo); index 0 of each axis is the pixel's own row / column
+  const bool vy1 = y >= 1 && y <= pa, vy2 = y <= t.h - 2 && y >= t.h - 1 - pa;
+  const bool vx1 = x >= 1 && x <= pa, vx2 = x <= t.w - 2 && x >= t.w - 1 - pa;
+  if (!(vy1 || vy2 || vx1 || vx2)) return;
+  const int yc[3] = {y, -y, 2 * (t.h - 1) - y}, xc[3] = {x, -x, 2 * (t.w - 1) - x};
+  const bool vy[3] = {true, vy1, vy2}, vx[3] = {true, vx1, vx2};
+  T* base = static_cast<T*>(t.data);
+  T* dst = base + toff(t, n, y, x, c);
+  // every halo pixel is the reflected copy of exactly ONE interior pixel, so it is read by exactly one thread: that thread
+  // zeroes it (the tensor leaves as a zero-haloed operand without a separate halo pass).  All loads first, then the stores;
+  // the eight candidate sources are static slots (registers, predicated), in grad_combine's summation order: (y, x)
+  // first, then rows ascending, columns ascending.
+  T* src[8];
+  uint4 raw[8];
+  bool ok[8];
+#pragma unroll
+  for (int iy = 0; iy < 3; ++iy)
+#pragma unroll
+    for (int ix = 0; ix < 3; ++ix) {
+      if (iy == 0 && ix == 0) continue;
+      const int sl = iy * 3 + ix - 1;
+      ok[sl] = vy[iy] && vx[ix];
+      src[sl] = base + toff(t, n, yc[iy], xc[ix], c);
+    }
+  const uint4 rd = *reinterpret_cast<const uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    raw[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (ok[i]) raw[i] = *reinterpret_cast<const uint4*>(src[i]);
+  }
+  float v[VN];
+  cvt16<T>(rd, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (ok[i]) {
+      float sv[VN];
+      cvt16<T>(raw[i], sv);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) v[k] += sv[k];
+      *reinterpret_cast<uint4*>(src[i]) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  Vec<T>::store(dst, v);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -481,31 +514,19 @@ __global__ void upsample2x_bwd_kernel(TGeom g, int g_c_off, TGeom d, float sy, f
 #pragma unroll
   for (int k = 0; k < VN; ++k) acc[k] = 0.f;
   const T* gb = static_cast<const T*>(g.data);
-  // two candidate rows per trip: their (up to 12) loads are requested together, predicated on a non-zero weight, before
-  // the first one is consumed (one tap at a time serialised ~9 memory latencies per thread, r4e); the sum keeps the
-  // order of the scatter's adjoint (rows ascending, columns ascending) and zero-weight taps add nothing
+  // (requesting two candidate rows of taps at once with predicated loads was measured 33 % slower, r4z: 78 registers)
 #pragma unroll
-  for (int jy0 = 0; jy0 < 6; jy0 += 2) {
-    uint4 rr[2][6];
+  for (int jy = 0; jy < 6; ++jy) {
+    if (wy[jy] == 0.f) continue;
+    const T* gr = gb + toff(g, n, 2 * yi - 2 + jy, 2 * xi - 2, g_c_off + c);
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const T* gr = gb + toff(g, n, 2 * yi - 2 + jy0 + a, 2 * xi - 2, g_c_off + c);
+    for (int jx = 0; jx < 6; ++jx) {
+      if (wx[jx] == 0.f) continue;
+      float tv[VN];
+      Vec<T>::load(gr + (long long)jx * g.c, tv);
 #pragma unroll
-      for (int jx = 0; jx < 6; ++jx) {
-        rr[a][jx] = make_uint4(0u, 0u, 0u, 0u);
-        if (wy[jy0 + a] != 0.f && wx[jx] != 0.f) rr[a][jx] = ldg16(gr + (long long)jx * g.c);
-      }
+      for (int k = 0; k < VN; ++k) acc[k] += wy[jy] * wx[jx] * tv[k];  // same order as the scatter's adjoint sum
     }
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int jx = 0; jx < 6; ++jx) {
-        if (wy[jy0 + a] == 0.f || wx[jx] == 0.f) continue;
-        float tv[VN];
-        cvt16<T>(rr[a][jx], tv);
-#pragma unroll
-        for (int k = 0; k < VN; ++k) acc[k] += wy[jy0 + a] * wx[jx] * tv[k];  // same order as the scatter's adjoint sum
-      }
   }
   const float rs = tscale(d) * tinv(g);
 #pragma unroll
@@ -722,10 +743,14 @@ int uegan_fold_inplace(const uegan_tensor* t, void* stream) {
   int lg = 0;
   while ((1 << lg) < cv) ++lg;
   UEGAN_CHECK((1 << lg) == cv, "fold_inplace: channels / vector width must be a power of two (got %d)", cv);
-  UEGAN_CHECK(g.h <= 65535 && g.n <= 65535, "fold_inplace: tensor too large for the launch grid");
+  UEGAN_CHECK(g.n <= 65535 && (long long)g.h * g.w * cv < (1ll << 30), "fold_inplace: tensor too large for the launch grid");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const dim3 grid(1u, (unsigned)g.h, (unsigned)g.n);
-  UEGAN_DISPATCH(t->dtype, fold_inplace_kernel, grid, 256, 0, st, g, lg);
+  const int pa = g.halo;
+  const int all = (g.h <= 2 * pa + 1 || g.w <= 2 * pa + 1) ? 1 : 0;  // narrow: the band / edge sets would overlap
+  const int items_band = all ? 0 : 2 * pa * g.w * cv;
+  const int items = all ? g.h * g.w * cv : items_band + (g.h - 2 * pa) * 2 * pa * cv;
+  const dim3 grid((unsigned)((items + 255) / 256), (unsigned)g.n);
+  UEGAN_DISPATCH(t->dtype, fold_inplace_kernel, grid, 256, 0, st, g, lg, all, items_band, items);
   UEGAN_CUDA(cudaGetLastError());
   return 0;
 }
