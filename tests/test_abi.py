@@ -102,3 +102,50 @@ def test_shape_policy_entry_points_without_gpu(monkeypatch):
     assert K.fused_stats_ok(512, 512, 64) is True and K.fused_stats_ok(4, 4, 64) is False
     monkeypatch.setenv("UEGAN_FUSED_STATS", "32")
     assert K.fused_stats_ok(512, 512, 64) is False and K.fused_stats_ok(512, 512, 32) is True
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """include/uegan_sm100.h compiled as plain C (gcc, no CUDA headers): sizeof / offsetof of every struct that crosses the
+    C ABI must equal the ctypes mirror in uegan_b200/_lib.py field by field -- a field added on one side only would shift
+    every later field silently."""
+    import shutil
+    import subprocess
+    import ctypes as C
+    from uegan_b200 import _lib as L
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    structs = {"uegan_tensor": L.Tensor, "uegan_conv_desc": L.ConvDesc, "uegan_scale_entry": L.ScaleEntry}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "uegan_sm100.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for ln in out.splitlines():
+        s, f, v = ln.split()
+        got[(s, f)] = int(v)
+    for cname, cls in structs.items():
+        assert got[(cname, "size")] == C.sizeof(cls), (cname, got[(cname, "size")], C.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+    # and the header declares no field the mirror lacks (sizes equal + last field's end == size up to padding)
+    hdr = open(os.path.join(ROOT, "include", "uegan_sm100.h")).read()
+    body = hdr[hdr.index("typedef struct uegan_conv_desc {"):hdr.index("} uegan_conv_desc;")]
+    import re
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    declared = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        stmt = stmt.split("{")[-1].strip()
+        if not stmt:
+            continue
+        names = stmt.replace("*", " ").split(",")
+        declared.append(names[0].split()[-1])
+        declared += [n.strip() for n in names[1:]]
+    assert declared == [f for f, _ in L.ConvDesc._fields_], declared
