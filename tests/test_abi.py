@@ -102,6 +102,16 @@ def test_shape_policy_entry_points_without_gpu(monkeypatch):
     assert K.fused_stats_ok(512, 512, 64) is True and K.fused_stats_ok(4, 4, 64) is False
     monkeypatch.setenv("UEGAN_FUSED_STATS", "32")
     assert K.fused_stats_ok(512, 512, 64) is False and K.fused_stats_ok(512, 512, 32) is True
+    # sliding-window weight gradient (uegan_conv2d_wgrad_zwin): fp16, stride 1, odd k, a zero halo >= k - 1 on dz, stacked
+    # columns k * dz_c <= 256 -- G's dec5.1 (3 of 8 stored channels, k 7), dec5.0 / dec4 (32 ch, k 3), dec3 (64 ch, k 3),
+    # the heads (1 of 8, k 3 / 5 / 7); not the 128-channel layers, not stride 2, not tf32
+    z = lib.uegan_conv2d_wgrad_zwin_supported
+    assert z(3, 8, 6, 32, 7, 1, L.F16) == 1 and z(32, 32, 2, 64, 3, 1, L.F16) == 1 and z(64, 64, 2, 128, 3, 1, L.F16) == 1
+    assert z(1, 8, 4, 256, 5, 1, L.F16) == 1
+    assert z(128, 128, 2, 256, 3, 1, L.F16) == 0  # 3 * 128 stacked columns > 256
+    assert z(32, 32, 1, 64, 3, 1, L.F16) == 0     # halo too small for the horizontal window
+    assert z(32, 32, 2, 64, 3, 2, L.F16) == 0 and z(32, 32, 2, 64, 3, 1, L.F32) == 0 and z(32, 32, 3, 64, 4, 1, L.F16) == 0
+    assert z(32, 32, 2, 8, 3, 1, L.F16) == 0      # x rows must be whole 64-byte (32-channel) units
 
 
 def test_struct_layouts_match_the_header(tmp_path):
